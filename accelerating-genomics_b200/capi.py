@@ -1,0 +1,248 @@
+"""ctypes binding of libagx.so -- the C ABI declared in include/agx.h.
+
+This is the Python host-side mirror used by the tests and bench.py; the C drivers under drivers/
+bind the same symbols directly.  There is no CPU fallback: if libagx.so is missing or no B200 is
+visible every compute call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+from typing import Iterable, Optional, Sequence
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libagx.so"
+
+# every symbol include/agx.h declares (tests check the .so exports all of them)
+SYMBOLS = [
+    "agx_init", "agx_init_devices", "agx_device_count", "agx_shutdown", "agx_last_error",
+    "agx_version", "agx_launch_count", "agx_reset_launch_count", "agx_set_profiling", "agx_profile_ms",
+    "sw_score_batch", "sw_score_batch_flat", "sw_score_batch_device",
+    "pairhmm_forward_batch", "pairhmm_forward_batches_flat", "pairhmm_forward_batches_device",
+    "agx_pairhmm_set_gatk_mode", "agx_pairhmm_set_force_fp64",
+]
+
+# the reference's scoring constants, antidiagonalSmithWaterman.c:40-43
+SW_MATCH, SW_MISMATCH, SW_GAP_OPEN, SW_GAP_EXTEND = 1, -1, -3, -1
+
+
+class AgxError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libagx error {code}: {msg}")
+        self.code = code
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load_library() -> C.CDLL:
+    """Load libagx.so (built in-tree by build.py).  Fails loudly when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise FileNotFoundError(
+            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback)")
+    lib = C.CDLL(str(LIB_PATH))
+    u8p, i32p, i64p, f64p = (C.POINTER(C.c_uint8), C.POINTER(C.c_int32), C.POINTER(C.c_int64),
+                             C.POINTER(C.c_double))
+    pp = C.POINTER(C.c_void_p)
+    lib.agx_init.argtypes = [C.c_int32]
+    lib.agx_init_devices.argtypes = [i32p, C.c_int32]
+    lib.agx_device_count.restype = C.c_int32
+    lib.agx_shutdown.restype = None
+    lib.agx_last_error.restype = C.c_char_p
+    lib.agx_version.restype = C.c_char_p
+    lib.agx_launch_count.restype = C.c_int64
+    lib.agx_reset_launch_count.restype = None
+    lib.agx_set_profiling.argtypes = [C.c_int32]
+    lib.agx_profile_ms.argtypes = [C.c_int32, C.c_int32]
+    lib.agx_profile_ms.restype = C.c_double
+    lib.sw_score_batch.argtypes = [pp, i32p, pp, i32p, C.c_int64] + [C.c_int32] * 4 + [i32p]
+    lib.sw_score_batch_flat.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64] + \
+        [C.c_int32] * 4 + [C.c_void_p]
+    lib.sw_score_batch_device.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                          C.c_int64] + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p]
+    lib.pairhmm_forward_batch.argtypes = [C.c_int32, pp, pp, pp, pp, pp, i32p, C.c_int32, pp, i32p, f64p]
+    lib.pairhmm_forward_batches_flat.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                                 C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                                 C.c_void_p, C.c_int64, C.c_void_p]
+    lib.pairhmm_forward_batches_device.argtypes = [
+        C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+        C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p,
+        C.c_void_p]
+    lib.agx_pairhmm_set_gatk_mode.argtypes = [C.c_int32]
+    lib.agx_pairhmm_set_force_fp64.argtypes = [C.c_int32]
+    for name in ("agx_init", "agx_init_devices", "sw_score_batch", "sw_score_batch_flat",
+                 "sw_score_batch_device", "pairhmm_forward_batch", "pairhmm_forward_batches_flat",
+                 "pairhmm_forward_batches_device", "agx_pairhmm_set_gatk_mode",
+                 "agx_pairhmm_set_force_fp64"):
+        getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise AgxError(rc, load_library().agx_last_error().decode(errors="replace"))
+
+
+# ------------------------------------------------------------------------------- runtime
+def init(n_gpus: int = 0) -> int:
+    _check(load_library().agx_init(int(n_gpus)))
+    return device_count()
+
+
+def init_devices(devices: Sequence[int]) -> int:
+    arr = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+    _check(load_library().agx_init_devices(arr, len(devices)))
+    return device_count()
+
+
+def device_count() -> int:
+    return int(load_library().agx_device_count())
+
+
+def shutdown() -> None:
+    load_library().agx_shutdown()
+
+
+def version() -> str:
+    return load_library().agx_version().decode()
+
+
+def launch_count() -> int:
+    return int(load_library().agx_launch_count())
+
+
+def reset_launch_count() -> None:
+    load_library().agx_reset_launch_count()
+
+
+PROF_SW_DUO, PROF_SW_WAVE, PROF_HMM_STREAM, PROF_HMM_FP64, PROF_SW_CLASSIFY, PROF_HMM_CLASSIFY = range(6)
+
+
+def set_profiling(on: bool) -> None:
+    load_library().agx_set_profiling(1 if on else 0)
+
+
+def profile_ms(device: int, which: int) -> float:
+    return float(load_library().agx_profile_ms(int(device), int(which)))
+
+
+def set_pairhmm_gatk_mode(on: bool) -> None:
+    _check(load_library().agx_pairhmm_set_gatk_mode(1 if on else 0))
+
+
+def set_pairhmm_force_fp64(on: bool) -> None:
+    _check(load_library().agx_pairhmm_set_force_fp64(1 if on else 0))
+
+
+# ------------------------------------------------------------------------------- helpers
+def _ptr(a: np.ndarray) -> int:
+    return a.ctypes.data
+
+
+def _as(a, dtype) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _byte_ptr_array(items: Sequence[bytes]):
+    """(array of void*, keep-alive list) for a sequence of bytes objects."""
+    keep = [C.create_string_buffer(bytes(x), len(x)) if len(x) else C.create_string_buffer(1) for x in items]
+    arr = (C.c_void_p * len(items))(*[C.addressof(k) for k in keep])
+    return arr, keep
+
+
+# ------------------------------------------------------------------------------- Smith-Waterman
+def sw_score_flat(seqs: np.ndarray, off: np.ndarray, length: np.ndarray,
+                  scoring=(SW_MATCH, SW_MISMATCH, SW_GAP_OPEN, SW_GAP_EXTEND)) -> np.ndarray:
+    """sw_score_batch_flat: seqs uint8 buffer, off/len of 2*n_pairs sequences (a0 b0 a1 b1 ...)."""
+    seqs = _as(seqs, np.uint8)
+    off = _as(off, np.int64)
+    length = _as(length, np.int32)
+    assert off.size == length.size and off.size % 2 == 0
+    n = off.size // 2
+    out = np.empty(n, dtype=np.int32)
+    _check(load_library().sw_score_batch_flat(_ptr(seqs), seqs.size, _ptr(off), _ptr(length), n,
+                                              *[int(s) for s in scoring], _ptr(out)))
+    return out
+
+
+def sw_score_batch(a: Sequence[bytes], b: Sequence[bytes],
+                   scoring=(SW_MATCH, SW_MISMATCH, SW_GAP_OPEN, SW_GAP_EXTEND)) -> np.ndarray:
+    """sw_score_batch: pointer-array form, sequences are raw bytes as the reference sees them."""
+    assert len(a) == len(b)
+    n = len(a)
+    pa, ka = _byte_ptr_array(a)
+    pb, kb = _byte_ptr_array(b)
+    la = (C.c_int32 * n)(*[len(x) for x in a])
+    lb = (C.c_int32 * n)(*[len(x) for x in b])
+    out = (C.c_int32 * max(n, 1))()
+    _check(load_library().sw_score_batch(C.cast(pa, C.POINTER(C.c_void_p)), la,
+                                         C.cast(pb, C.POINTER(C.c_void_p)), lb, n,
+                                         *[int(s) for s in scoring], out))
+    del ka, kb
+    return np.array(out[:n], dtype=np.int32)
+
+
+def sw_score_device(device: int, d_seqs: int, seqs_bytes: int, d_off: int, d_len: int, n_pairs: int,
+                    d_scores: int, stream: int = 0,
+                    scoring=(SW_MATCH, SW_MISMATCH, SW_GAP_OPEN, SW_GAP_EXTEND)) -> None:
+    """sw_score_batch_device: raw device pointers (e.g. torch tensor .data_ptr())."""
+    _check(load_library().sw_score_batch_device(int(device), d_seqs, int(seqs_bytes), d_off, d_len,
+                                                int(n_pairs), *[int(s) for s in scoring], d_scores,
+                                                stream or None))
+
+
+# ------------------------------------------------------------------------------- PairHMM
+def pairhmm_forward_batch(reads: Sequence[Sequence[bytes]], haps: Sequence[bytes]) -> np.ndarray:
+    """pairhmm_forward_batch: reads = [(bases, q, qi, qd, qg), ...]; returns [n_reads, n_haps]."""
+    nr, nh = len(reads), len(haps)
+    cols = []
+    keeps = []
+    for f in range(5):
+        arr, keep = _byte_ptr_array([r[f] for r in reads])
+        cols.append(C.cast(arr, C.POINTER(C.c_void_p)))
+        keeps.append((arr, keep))
+    rl = (C.c_int32 * max(nr, 1))(*[len(r[0]) for r in reads])
+    ph, kh = _byte_ptr_array(haps)
+    hl = (C.c_int32 * max(nh, 1))(*[len(h) for h in haps])
+    out = (C.c_double * max(nr * nh, 1))()
+    _check(load_library().pairhmm_forward_batch(nr, *cols, rl, nh, C.cast(ph, C.POINTER(C.c_void_p)), hl, out))
+    del keeps, kh
+    return np.array(out[:nr * nh], dtype=np.float64).reshape(nr, nh)
+
+
+def pairhmm_forward_flat(buf: np.ndarray, read_field_off: np.ndarray, read_len: np.ndarray,
+                         hap_off: np.ndarray, hap_len: np.ndarray, batch_read_start: np.ndarray,
+                         batch_hap_start: np.ndarray) -> np.ndarray:
+    """pairhmm_forward_batches_flat on host arrays; returns the flat log10 vector."""
+    buf = _as(buf, np.uint8)
+    rfo = _as(read_field_off, np.int64).reshape(-1)
+    rl = _as(read_len, np.int32)
+    ho = _as(hap_off, np.int64)
+    hl = _as(hap_len, np.int32)
+    brs = _as(batch_read_start, np.int64)
+    bhs = _as(batch_hap_start, np.int64)
+    nb = brs.size - 1
+    n_out = int(np.sum((brs[1:] - brs[:-1]) * (bhs[1:] - bhs[:-1])))
+    out = np.empty(max(n_out, 1), dtype=np.float64)
+    _check(load_library().pairhmm_forward_batches_flat(_ptr(buf), buf.size, _ptr(rfo), _ptr(rl), rl.size,
+                                                       _ptr(ho), _ptr(hl), hl.size, _ptr(brs), _ptr(bhs),
+                                                       nb, _ptr(out)))
+    return out[:n_out]
+
+
+def pairhmm_forward_device(device: int, d_buf: int, buf_bytes: int, d_read_field_off: int,
+                           d_read_len: int, d_read_batch: int, d_read_out_off: int, n_reads: int,
+                           d_hap_off: int, d_hap_len: int, n_haps: int, d_batch_hap_start: int,
+                           n_batches: int, n_pairs: int, d_out: int, stream: int = 0,
+                           fp64_rescue: bool = True) -> None:
+    _check(load_library().pairhmm_forward_batches_device(
+        int(device), d_buf, int(buf_bytes), d_read_field_off, d_read_len, d_read_batch, d_read_out_off,
+        int(n_reads), d_hap_off, d_hap_len, int(n_haps), d_batch_hap_start, int(n_batches), int(n_pairs),
+        1 if fp64_rescue else 0, d_out, stream or None))

@@ -1,0 +1,627 @@
+// api.cu -- C ABI of libagx.so (see include/agx.h): device contexts, the multi-GPU dispatcher
+// (pair / read sharding by cell count, one host thread + one stream per GPU, no collective) and the
+// host <-> device staging for the flat and pointer-array entry points.
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+
+namespace agx {
+
+std::atomic<int64_t> g_launches{0};
+std::atomic<int> g_profiling{0};
+
+void ProfSpan::begin(cudaStream_t st)
+{
+    if (!g_profiling.load(std::memory_order_relaxed)) return;
+    if (!e0) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
+    cudaEventRecord(e0, st);
+    armed = false;
+}
+void ProfSpan::end(cudaStream_t st)
+{
+    if (!g_profiling.load(std::memory_order_relaxed) || !e0) return;
+    cudaEventRecord(e1, st);
+    armed = true;
+}
+double ProfSpan::ms()
+{
+    if (!armed) return -1.0;
+    if (cudaEventSynchronize(e1) != cudaSuccess) return -1.0;
+    float v = 0.f;
+    if (cudaEventElapsedTime(&v, e0, e1) != cudaSuccess) return -1.0;
+    return (double)v;
+}
+void ProfSpan::destroy()
+{
+    if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
+    e0 = e1 = nullptr;
+    armed = false;
+}
+
+static thread_local std::string t_error;
+void set_error(const std::string &msg) { t_error = msg; }
+int fail(int code, const std::string &msg)
+{
+    t_error = msg;
+    return code;
+}
+
+namespace {
+
+// grow-only device buffer
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return AGX_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) return fail(AGX_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        cap = want;
+        return AGX_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return AGX_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) return fail(AGX_ENOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+        cap = want;
+        return AGX_OK;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+struct DeviceCtx {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    SwWorkspace sw;
+    HmmWorkspace hmm;
+    DevBuf d_bytes, d_a, d_b, d_c, d_d, d_e, d_f, d_out;   // staging for the host entry points
+    PinBuf h_a, h_b, h_out;
+    std::string error;   // error raised on this device's worker thread
+};
+
+std::mutex g_mu;
+std::vector<std::unique_ptr<DeviceCtx>> g_ctx;
+std::atomic<int> g_gatk{0}, g_force64{0};
+
+DeviceCtx *ctx_for_device(int device)
+{
+    for (auto &c : g_ctx)
+        if (c->device == device) return c.get();
+    return nullptr;
+}
+
+int init_devices(const std::vector<int> &ids)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    int n_visible = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_visible);
+    if (e != cudaSuccess || n_visible == 0)
+        return fail(AGX_ENODEVICE, std::string("no CUDA device: ") +
+                                       (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    std::vector<int> want = ids;
+    if (want.empty())
+        for (int i = 0; i < n_visible; ++i) want.push_back(i);
+    for (int d : want)
+        if (d < 0 || d >= n_visible) return fail(AGX_EINVAL, "agx_init: device ordinal out of range");
+    for (int d : want) {
+        if (ctx_for_device(d)) continue;
+        cudaDeviceProp prop;
+        AGX_CUDA(cudaGetDeviceProperties(&prop, d));
+        if (prop.major < 10)
+            return fail(AGX_ENODEVICE, std::string("device ") + prop.name +
+                                           " is not sm_100-class; libagx carries sm_100a code only");
+        auto c = std::make_unique<DeviceCtx>();
+        c->device = d;
+        AGX_CUDA(cudaSetDevice(d));
+        AGX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        g_ctx.push_back(std::move(c));
+    }
+    return AGX_OK;
+}
+
+// Split [0, n) into `parts` contiguous ranges of roughly equal weight.
+std::vector<int64_t> balanced_cuts(const std::vector<double> &prefix, int parts)
+{
+    const int64_t n = (int64_t)prefix.size() - 1;
+    std::vector<int64_t> cuts(parts + 1, n);
+    cuts[0] = 0;
+    const double total = prefix[n];
+    for (int k = 1; k < parts; ++k) {
+        const double target = total * k / parts;
+        cuts[k] = std::lower_bound(prefix.begin(), prefix.end(), target) - prefix.begin();
+        if (cuts[k] < cuts[k - 1]) cuts[k] = cuts[k - 1];
+        if (cuts[k] > n) cuts[k] = n;
+    }
+    return cuts;
+}
+
+// Run fn(ctx, shard_index) on every configured device, one host thread each.
+template <typename Fn> int for_each_device(int n_shards, Fn fn)
+{
+    std::vector<int> rcs(n_shards, AGX_OK);
+    std::vector<std::string> errs(n_shards);
+    auto body = [&](int k) {
+        DeviceCtx *c = g_ctx[k].get();
+        if (cudaSetDevice(c->device) != cudaSuccess) {
+            rcs[k] = AGX_ECUDA;
+            errs[k] = "cudaSetDevice failed";
+            return;
+        }
+        rcs[k] = fn(*c, k);
+        if (rcs[k] != AGX_OK) errs[k] = t_error;
+    };
+    if (n_shards == 1) {
+        body(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int k = 0; k < n_shards; ++k) th.emplace_back(body, k);
+        for (auto &t : th) t.join();
+    }
+    for (int k = 0; k < n_shards; ++k)
+        if (rcs[k] != AGX_OK) return fail(rcs[k], "gpu " + std::to_string(g_ctx[k]->device) + ": " + errs[k]);
+    return AGX_OK;
+}
+
+int require_init()
+{
+    if (g_ctx.empty()) {
+        int rc = init_devices({});
+        if (rc != AGX_OK) return rc;
+    }
+    return AGX_OK;
+}
+
+// ---------------------------------------------------------------- SW on one shard
+int sw_shard(DeviceCtx &c, const uint8_t *seqs, const int64_t *off, const int32_t *len, int64_t p0,
+             int64_t p1, SwScoring sc, int32_t *scores_out)
+{
+    const int64_t n = p1 - p0;
+    if (n <= 0) return AGX_OK;
+    // byte range covered by this shard
+    int64_t lo = INT64_MAX, hi = 0;
+    for (int64_t i = 2 * p0; i < 2 * p1; ++i) {
+        lo = std::min(lo, off[i]);
+        hi = std::max(hi, off[i] + len[i]);
+    }
+    if (hi < lo) { lo = 0; hi = 0; }
+    const int64_t nbytes = hi - lo;
+    int rc;
+    if ((rc = c.d_bytes.reserve((size_t)nbytes + 16)) != AGX_OK) return rc;
+    if ((rc = c.d_a.reserve((size_t)n * 2 * sizeof(int64_t))) != AGX_OK) return rc;
+    if ((rc = c.d_b.reserve((size_t)n * 2 * sizeof(int32_t))) != AGX_OK) return rc;
+    if ((rc = c.d_out.reserve((size_t)n * sizeof(int32_t))) != AGX_OK) return rc;
+    if ((rc = c.h_a.reserve((size_t)n * 2 * sizeof(int64_t))) != AGX_OK) return rc;
+    int64_t *h_off = c.h_a.as<int64_t>();
+    for (int64_t i = 0; i < 2 * n; ++i) h_off[i] = off[2 * p0 + i] - lo;
+    cudaStream_t st = c.stream;
+    AGX_CUDA(cudaMemcpyAsync(c.d_bytes.p, seqs + lo, (size_t)nbytes, cudaMemcpyHostToDevice, st));
+    AGX_CUDA(cudaMemcpyAsync(c.d_a.p, h_off, (size_t)n * 2 * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    AGX_CUDA(cudaMemcpyAsync(c.d_b.p, len + 2 * p0, (size_t)n * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    rc = sw_run_device(c.sw, c.d_bytes.as<uint8_t>(), c.d_a.as<int64_t>(), c.d_b.as<int32_t>(), n, sc,
+                       c.d_out.as<int32_t>(), st);
+    if (rc != AGX_OK) return rc;
+    AGX_CUDA(cudaMemcpyAsync(scores_out + p0, c.d_out.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    AGX_CUDA(cudaStreamSynchronize(st));
+    return AGX_OK;
+}
+
+int sw_flat_impl(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *off, const int32_t *len,
+                 int64_t n_pairs, SwScoring sc, int32_t *scores_out)
+{
+    if (n_pairs < 0) return fail(AGX_EINVAL, "sw: n_pairs < 0");
+    if (n_pairs == 0) return AGX_OK;
+    if (!seqs || !off || !len || !scores_out) return fail(AGX_EINVAL, "sw: null argument");
+    for (int64_t i = 0; i < 2 * n_pairs; ++i)
+        if (len[i] < 0 || off[i] < 0 || off[i] + len[i] > seqs_bytes)
+            return fail(AGX_EINVAL, "sw: sequence " + std::to_string(i) + " lies outside the buffer");
+    int rc = require_init();
+    if (rc != AGX_OK) return rc;
+    const int n_dev = (int)std::min<int64_t>((int64_t)g_ctx.size(), n_pairs);
+    std::vector<int64_t> cuts{0, n_pairs};
+    if (n_dev > 1) {
+        std::vector<double> prefix(n_pairs + 1, 0.0);
+        for (int64_t p = 0; p < n_pairs; ++p)
+            prefix[p + 1] = prefix[p] + (double)(len[2 * p] + 1) * (double)(len[2 * p + 1] + 1);
+        cuts = balanced_cuts(prefix, n_dev);
+    }
+    return for_each_device(n_dev, [&](DeviceCtx &c, int k) {
+        return sw_shard(c, seqs, off, len, cuts[k], cuts[k + 1], sc, scores_out);
+    });
+}
+
+// ---------------------------------------------------------------- PairHMM on one shard
+struct HmmHost {
+    const uint8_t *buf;
+    int64_t buf_bytes;
+    const int64_t *read_field_off;
+    const int32_t *read_len;
+    int64_t n_reads;
+    const int64_t *hap_off;
+    const int32_t *hap_len;
+    int64_t n_haps;
+    const int64_t *batch_read_start;
+    const int64_t *batch_hap_start;
+    int64_t n_batches;
+    std::vector<int32_t> read_batch;   // [n_reads]
+    std::vector<int64_t> read_out_off; // [n_reads]
+    int64_t n_pairs;
+};
+
+int hmm_shard(DeviceCtx &c, const HmmHost &h, int64_t r0, int64_t r1, double *out)
+{
+    const int64_t nr = r1 - r0;
+    if (nr <= 0) return AGX_OK;
+    const int32_t b0 = h.read_batch[r0], b1 = h.read_batch[r1 - 1] + 1;
+    const int64_t hh0 = h.batch_hap_start[b0], hh1 = h.batch_hap_start[b1];
+    const int64_t nh = hh1 - hh0, nb = b1 - b0;
+    // outputs of this shard are contiguous: [o0, o1)
+    const int64_t o0 = h.read_out_off[r0];
+    const int64_t last_b = h.read_batch[r1 - 1];
+    const int64_t o1 = h.read_out_off[r1 - 1] + (h.batch_hap_start[last_b + 1] - h.batch_hap_start[last_b]);
+    const int64_t n_out = o1 - o0;
+    if (n_out <= 0) return AGX_OK;
+
+    int64_t lo = INT64_MAX, hi = 0;
+    for (int64_t r = r0; r < r1; ++r)
+        for (int f = 0; f < 5; ++f) {
+            lo = std::min(lo, h.read_field_off[5 * r + f]);
+            hi = std::max(hi, h.read_field_off[5 * r + f] + h.read_len[r]);
+        }
+    for (int64_t x = hh0; x < hh1; ++x) {
+        lo = std::min(lo, h.hap_off[x]);
+        hi = std::max(hi, h.hap_off[x] + h.hap_len[x]);
+    }
+    const int64_t nbytes = hi - lo;
+
+    // shard-local index arrays, packed into one pinned block
+    const size_t sz_rfo = (size_t)nr * 5 * sizeof(int64_t), sz_roo = (size_t)nr * sizeof(int64_t),
+                 sz_ho = (size_t)nh * sizeof(int64_t), sz_bhs = (size_t)(nb + 1) * sizeof(int64_t),
+                 sz_rl = (size_t)nr * sizeof(int32_t), sz_rb = (size_t)nr * sizeof(int32_t),
+                 sz_hl = (size_t)nh * sizeof(int32_t);
+    const size_t total = sz_rfo + sz_roo + sz_ho + sz_bhs + sz_rl + sz_rb + sz_hl;
+    int rc;
+    if ((rc = c.h_a.reserve(total)) != AGX_OK) return rc;
+    if ((rc = c.d_a.reserve(total)) != AGX_OK) return rc;
+    if ((rc = c.d_bytes.reserve((size_t)nbytes + 16)) != AGX_OK) return rc;
+    if ((rc = c.d_out.reserve((size_t)n_out * sizeof(double))) != AGX_OK) return rc;
+    uint8_t *hp = c.h_a.as<uint8_t>();
+    int64_t *p_rfo = (int64_t *)hp;
+    int64_t *p_roo = (int64_t *)(hp + sz_rfo);
+    int64_t *p_ho = (int64_t *)(hp + sz_rfo + sz_roo);
+    int64_t *p_bhs = (int64_t *)(hp + sz_rfo + sz_roo + sz_ho);
+    int32_t *p_rl = (int32_t *)(hp + sz_rfo + sz_roo + sz_ho + sz_bhs);
+    int32_t *p_rb = (int32_t *)(hp + sz_rfo + sz_roo + sz_ho + sz_bhs + sz_rl);
+    int32_t *p_hl = (int32_t *)(hp + sz_rfo + sz_roo + sz_ho + sz_bhs + sz_rl + sz_rb);
+    for (int64_t r = 0; r < nr; ++r) {
+        for (int f = 0; f < 5; ++f) p_rfo[5 * r + f] = h.read_field_off[5 * (r0 + r) + f] - lo;
+        p_roo[r] = h.read_out_off[r0 + r] - o0;
+        p_rl[r] = h.read_len[r0 + r];
+        p_rb[r] = h.read_batch[r0 + r] - b0;
+    }
+    for (int64_t x = 0; x < nh; ++x) {
+        p_ho[x] = h.hap_off[hh0 + x] - lo;
+        p_hl[x] = h.hap_len[hh0 + x];
+    }
+    for (int64_t b = 0; b <= nb; ++b) p_bhs[b] = h.batch_hap_start[b0 + b] - hh0;
+
+    cudaStream_t st = c.stream;
+    AGX_CUDA(cudaMemcpyAsync(c.d_bytes.p, h.buf + lo, (size_t)nbytes, cudaMemcpyHostToDevice, st));
+    AGX_CUDA(cudaMemcpyAsync(c.d_a.p, hp, total, cudaMemcpyHostToDevice, st));
+    uint8_t *dp = c.d_a.as<uint8_t>();
+    HmmBatchView v;
+    v.buf = c.d_bytes.as<uint8_t>();
+    v.read_field_off = (const int64_t *)dp;
+    const int64_t *d_roo = (const int64_t *)(dp + sz_rfo);
+    v.hap_off = (const int64_t *)(dp + sz_rfo + sz_roo);
+    v.batch_hap_start = (const int64_t *)(dp + sz_rfo + sz_roo + sz_ho);
+    v.read_len = (const int32_t *)(dp + sz_rfo + sz_roo + sz_ho + sz_bhs);
+    v.read_batch = (const int32_t *)(dp + sz_rfo + sz_roo + sz_ho + sz_bhs + sz_rl);
+    v.hap_len = (const int32_t *)(dp + sz_rfo + sz_roo + sz_ho + sz_bhs + sz_rl + sz_rb);
+    v.n_reads = nr;
+    v.n_haps = nh;
+    v.n_batches = nb;
+    rc = hmm_run_device(c.hmm, v, d_roo, n_out, g_gatk.load() != 0, g_force64.load() != 0, true,
+                        c.d_out.as<double>(), st);
+    if (rc != AGX_OK) return rc;
+    AGX_CUDA(cudaMemcpyAsync(out + o0, c.d_out.p, (size_t)n_out * sizeof(double), cudaMemcpyDeviceToHost, st));
+    AGX_CUDA(cudaStreamSynchronize(st));
+    return AGX_OK;
+}
+
+int hmm_flat_impl(HmmHost &h, double *out)
+{
+    if (h.n_batches < 0 || h.n_reads < 0 || h.n_haps < 0) return fail(AGX_EINVAL, "pairhmm: negative count");
+    if (h.n_batches == 0 || h.n_reads == 0) return AGX_OK;
+    if (!h.buf || !h.read_field_off || !h.read_len || !h.hap_off || !h.hap_len || !h.batch_read_start ||
+        !h.batch_hap_start || !out)
+        return fail(AGX_EINVAL, "pairhmm: null argument");
+    if (h.batch_read_start[0] != 0 || h.batch_hap_start[0] != 0 ||
+        h.batch_read_start[h.n_batches] != h.n_reads || h.batch_hap_start[h.n_batches] != h.n_haps)
+        return fail(AGX_EINVAL, "pairhmm: batch_*_start must run from 0 to n_reads / n_haps");
+    for (int64_t r = 0; r < h.n_reads; ++r) {
+        if (h.read_len[r] < 1 || h.read_len[r] > 8192)
+            return fail(AGX_ERANGE, "pairhmm: read " + std::to_string(r) + " length outside [1, 8192]");
+        for (int f = 0; f < 5; ++f) {
+            const int64_t o = h.read_field_off[5 * r + f];
+            if (o < 0 || o + h.read_len[r] > h.buf_bytes)
+                return fail(AGX_EINVAL, "pairhmm: read " + std::to_string(r) + " lies outside the buffer");
+        }
+    }
+    for (int64_t x = 0; x < h.n_haps; ++x) {
+        if (h.hap_len[x] < 1 || h.hap_len[x] > (1 << 20))
+            return fail(AGX_ERANGE, "pairhmm: haplotype " + std::to_string(x) + " length outside [1, 2^20]");
+        if (h.hap_off[x] < 0 || h.hap_off[x] + h.hap_len[x] > h.buf_bytes)
+            return fail(AGX_EINVAL, "pairhmm: haplotype " + std::to_string(x) + " lies outside the buffer");
+    }
+    int rc = require_init();
+    if (rc != AGX_OK) return rc;
+
+    h.read_batch.resize(h.n_reads);
+    h.read_out_off.resize(h.n_reads);
+    std::vector<double> prefix(h.n_reads + 1, 0.0);
+    int64_t o = 0;
+    for (int64_t b = 0; b < h.n_batches; ++b) {
+        const int64_t rs = h.batch_read_start[b], re = h.batch_read_start[b + 1];
+        const int64_t hs = h.batch_hap_start[b], he = h.batch_hap_start[b + 1];
+        if (re < rs || he < hs) return fail(AGX_EINVAL, "pairhmm: batch_*_start must be non-decreasing");
+        double hap_cells = 0;
+        for (int64_t x = hs; x < he; ++x) hap_cells += h.hap_len[x];
+        for (int64_t r = rs; r < re; ++r) {
+            h.read_batch[r] = (int32_t)b;
+            h.read_out_off[r] = o;
+            o += he - hs;
+            prefix[r + 1] = prefix[r] + hap_cells * h.read_len[r];
+        }
+    }
+    h.n_pairs = o;
+    if (o == 0) return AGX_OK;
+    const int n_dev = (int)std::min<int64_t>((int64_t)g_ctx.size(), h.n_reads);
+    std::vector<int64_t> cuts{0, h.n_reads};
+    if (n_dev > 1) cuts = balanced_cuts(prefix, n_dev);
+    return for_each_device(n_dev, [&](DeviceCtx &c, int k) {
+        return hmm_shard(c, h, cuts[k], cuts[k + 1], out);
+    });
+}
+
+}  // namespace
+}  // namespace agx
+
+using namespace agx;
+
+// =============================================================================== C ABI
+extern "C" {
+
+int agx_init(int32_t n_gpus)
+{
+    std::vector<int> ids;
+    if (n_gpus > 0)
+        for (int i = 0; i < n_gpus; ++i) ids.push_back(i);
+    return init_devices(ids);
+}
+
+int agx_init_devices(const int32_t *device_ids, int32_t n_devices)
+{
+    if (n_devices <= 0 || !device_ids) return fail(AGX_EINVAL, "agx_init_devices: empty device list");
+    return init_devices(std::vector<int>(device_ids, device_ids + n_devices));
+}
+
+int32_t agx_device_count(void) { return (int32_t)g_ctx.size(); }
+
+void agx_shutdown(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto &c : g_ctx) {
+        cudaSetDevice(c->device);
+        if (c->stream) cudaStreamSynchronize(c->stream);
+        sw_workspace_free(c->sw);
+        hmm_workspace_free(c->hmm);
+        for (DevBuf *b : {&c->d_bytes, &c->d_a, &c->d_b, &c->d_c, &c->d_d, &c->d_e, &c->d_f, &c->d_out}) b->release();
+        for (PinBuf *b : {&c->h_a, &c->h_b, &c->h_out}) b->release();
+        if (c->stream) cudaStreamDestroy(c->stream);
+    }
+    g_ctx.clear();
+}
+
+const char *agx_last_error(void) { return t_error.c_str(); }
+const char *agx_version(void) { return "agx 0.1 sm_100a"; }
+int64_t agx_launch_count(void) { return g_launches.load(); }
+void agx_reset_launch_count(void) { g_launches.store(0); }
+
+int agx_set_profiling(int32_t on) { g_profiling.store(on ? 1 : 0); return AGX_OK; }
+
+double agx_profile_ms(int32_t device, int32_t which)
+{
+    DeviceCtx *c = ctx_for_device(device);
+    if (!c) return -1.0;
+    cudaSetDevice(device);
+    switch (which) {
+    case AGX_PROF_SW_DUO: return c->sw.prof_duo.ms();
+    case AGX_PROF_SW_WAVE: return c->sw.prof_wave.ms();
+    case AGX_PROF_SW_CLASSIFY: return c->sw.prof_classify.ms();
+    case AGX_PROF_HMM_STREAM: return c->hmm.prof_stream.ms();
+    case AGX_PROF_HMM_FP64: return c->hmm.prof_fp64.ms();
+    case AGX_PROF_HMM_CLASSIFY: return c->hmm.prof_classify.ms();
+    default: return -1.0;
+    }
+}
+
+int agx_pairhmm_set_gatk_mode(int32_t on) { g_gatk.store(on ? 1 : 0); return AGX_OK; }
+int agx_pairhmm_set_force_fp64(int32_t on) { g_force64.store(on ? 1 : 0); return AGX_OK; }
+
+int sw_score_batch_flat(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *off, const int32_t *len,
+                        int64_t n_pairs, int32_t match, int32_t mismatch, int32_t gap_open,
+                        int32_t gap_extend, int32_t *scores_out)
+{
+    return sw_flat_impl(seqs, seqs_bytes, off, len, n_pairs, SwScoring{match, mismatch, gap_open, gap_extend},
+                        scores_out);
+}
+
+int sw_score_batch(const uint8_t *const *a, const int32_t *a_len, const uint8_t *const *b,
+                   const int32_t *b_len, int64_t n_pairs, int32_t match, int32_t mismatch,
+                   int32_t gap_open, int32_t gap_extend, int32_t *scores_out)
+{
+    if (n_pairs < 0) return fail(AGX_EINVAL, "sw: n_pairs < 0");
+    if (n_pairs == 0) return AGX_OK;
+    if (!a || !a_len || !b || !b_len || !scores_out) return fail(AGX_EINVAL, "sw: null argument");
+    // gather the pointer arrays into one flat image (a0 b0 a1 b1 ...)
+    int64_t total = 0;
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        if (a_len[p] < 0 || b_len[p] < 0 || (a_len[p] && !a[p]) || (b_len[p] && !b[p]))
+            return fail(AGX_EINVAL, "sw: bad sequence " + std::to_string(p));
+        total += (int64_t)a_len[p] + b_len[p];
+    }
+    std::vector<uint8_t> flat((size_t)total + 1);
+    std::vector<int64_t> off((size_t)n_pairs * 2);
+    std::vector<int32_t> len((size_t)n_pairs * 2);
+    int64_t w = 0;
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        off[2 * p] = w; len[2 * p] = a_len[p];
+        if (a_len[p]) memcpy(flat.data() + w, a[p], (size_t)a_len[p]);
+        w += a_len[p];
+        off[2 * p + 1] = w; len[2 * p + 1] = b_len[p];
+        if (b_len[p]) memcpy(flat.data() + w, b[p], (size_t)b_len[p]);
+        w += b_len[p];
+    }
+    return sw_flat_impl(flat.data(), total, off.data(), len.data(), n_pairs,
+                        SwScoring{match, mismatch, gap_open, gap_extend}, scores_out);
+}
+
+int sw_score_batch_device(int32_t device, const uint8_t *d_seqs, int64_t seqs_bytes, const int64_t *d_off,
+                          const int32_t *d_len, int64_t n_pairs, int32_t match, int32_t mismatch,
+                          int32_t gap_open, int32_t gap_extend, int32_t *d_scores_out, void *stream)
+{
+    (void)seqs_bytes;
+    if (n_pairs < 0) return fail(AGX_EINVAL, "sw: n_pairs < 0");
+    if (n_pairs == 0) return AGX_OK;
+    if (!d_seqs || !d_off || !d_len || !d_scores_out) return fail(AGX_EINVAL, "sw: null argument");
+    DeviceCtx *c = ctx_for_device(device);
+    if (!c) return fail(AGX_ENODEVICE, "sw_score_batch_device: device " + std::to_string(device) +
+                                           " was not passed to agx_init");
+    AGX_CUDA(cudaSetDevice(device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    return sw_run_device(c->sw, d_seqs, d_off, d_len, n_pairs, SwScoring{match, mismatch, gap_open, gap_extend},
+                         d_scores_out, st);
+}
+
+int pairhmm_forward_batches_flat(const uint8_t *buf, int64_t buf_bytes, const int64_t *read_field_off,
+                                 const int32_t *read_len, int64_t n_reads, const int64_t *hap_off,
+                                 const int32_t *hap_len, int64_t n_haps, const int64_t *batch_read_start,
+                                 const int64_t *batch_hap_start, int64_t n_batches, double *log10_out)
+{
+    HmmHost h;
+    h.buf = buf; h.buf_bytes = buf_bytes;
+    h.read_field_off = read_field_off; h.read_len = read_len; h.n_reads = n_reads;
+    h.hap_off = hap_off; h.hap_len = hap_len; h.n_haps = n_haps;
+    h.batch_read_start = batch_read_start; h.batch_hap_start = batch_hap_start; h.n_batches = n_batches;
+    h.n_pairs = 0;
+    return hmm_flat_impl(h, log10_out);
+}
+
+int pairhmm_forward_batch(int32_t n_reads, const uint8_t *const *bases, const uint8_t *const *q,
+                          const uint8_t *const *qi, const uint8_t *const *qd, const uint8_t *const *qg,
+                          const int32_t *read_len, int32_t n_haps, const uint8_t *const *haps,
+                          const int32_t *hap_len, double *log10_out)
+{
+    if (n_reads < 0 || n_haps < 0) return fail(AGX_EINVAL, "pairhmm: negative count");
+    if (n_reads == 0 || n_haps == 0) return AGX_OK;
+    if (!bases || !q || !qi || !qd || !qg || !read_len || !haps || !hap_len || !log10_out)
+        return fail(AGX_EINVAL, "pairhmm: null argument");
+    int64_t total = 0;
+    for (int r = 0; r < n_reads; ++r) {
+        if (read_len[r] < 1) return fail(AGX_ERANGE, "pairhmm: read " + std::to_string(r) + " is empty");
+        if (!bases[r] || !q[r] || !qi[r] || !qd[r] || !qg[r]) return fail(AGX_EINVAL, "pairhmm: null read field");
+        total += 5 * (int64_t)read_len[r];
+    }
+    for (int x = 0; x < n_haps; ++x) {
+        if (hap_len[x] < 1) return fail(AGX_ERANGE, "pairhmm: haplotype " + std::to_string(x) + " is empty");
+        if (!haps[x]) return fail(AGX_EINVAL, "pairhmm: null haplotype");
+        total += hap_len[x];
+    }
+    std::vector<uint8_t> flat((size_t)total + 1);
+    std::vector<int64_t> rfo((size_t)n_reads * 5), ho((size_t)n_haps);
+    int64_t w = 0;
+    for (int r = 0; r < n_reads; ++r) {
+        const uint8_t *f[5] = {bases[r], q[r], qi[r], qd[r], qg[r]};
+        for (int k = 0; k < 5; ++k) {
+            rfo[5 * (size_t)r + k] = w;
+            memcpy(flat.data() + w, f[k], (size_t)read_len[r]);
+            w += read_len[r];
+        }
+    }
+    for (int x = 0; x < n_haps; ++x) {
+        ho[x] = w;
+        memcpy(flat.data() + w, haps[x], (size_t)hap_len[x]);
+        w += hap_len[x];
+    }
+    const int64_t brs[2] = {0, n_reads}, bhs[2] = {0, n_haps};
+    return pairhmm_forward_batches_flat(flat.data(), total, rfo.data(), read_len, n_reads, ho.data(), hap_len,
+                                        n_haps, brs, bhs, 1, log10_out);
+}
+
+int pairhmm_forward_batches_device(int32_t device, const uint8_t *d_buf, int64_t buf_bytes,
+                                   const int64_t *d_read_field_off, const int32_t *d_read_len,
+                                   const int32_t *d_read_batch, const int64_t *d_read_out_off,
+                                   int64_t n_reads, const int64_t *d_hap_off, const int32_t *d_hap_len,
+                                   int64_t n_haps, const int64_t *d_batch_hap_start, int64_t n_batches,
+                                   int64_t n_pairs, int32_t fp64_rescue, double *d_log10_out, void *stream)
+{
+    (void)buf_bytes;
+    if (n_reads < 0 || n_haps < 0 || n_batches < 0 || n_pairs < 0) return fail(AGX_EINVAL, "pairhmm: negative count");
+    if (n_reads == 0 || n_pairs == 0) return AGX_OK;
+    if (!d_buf || !d_read_field_off || !d_read_len || !d_read_batch || !d_read_out_off || !d_hap_off ||
+        !d_hap_len || !d_batch_hap_start || !d_log10_out)
+        return fail(AGX_EINVAL, "pairhmm: null argument");
+    DeviceCtx *c = ctx_for_device(device);
+    if (!c) return fail(AGX_ENODEVICE, "pairhmm_forward_batches_device: device " + std::to_string(device) +
+                                           " was not passed to agx_init");
+    AGX_CUDA(cudaSetDevice(device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    HmmBatchView v;
+    v.buf = d_buf;
+    v.read_field_off = d_read_field_off;
+    v.read_len = d_read_len;
+    v.read_batch = d_read_batch;
+    v.n_reads = n_reads;
+    v.hap_off = d_hap_off;
+    v.hap_len = d_hap_len;
+    v.n_haps = n_haps;
+    v.batch_hap_start = d_batch_hap_start;
+    v.n_batches = n_batches;
+    return hmm_run_device(c->hmm, v, d_read_out_off, n_pairs, g_gatk.load() != 0, g_force64.load() != 0,
+                          fp64_rescue != 0, d_log10_out, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,103 @@
+// common.cuh -- shared declarations for libagx (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/agx.h"
+
+namespace agx {
+
+// ---- error plumbing -----------------------------------------------------------------------
+void set_error(const std::string &msg);
+int fail(int code, const std::string &msg);
+
+#define AGX_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess)                                                                 \
+            return ::agx::fail(AGX_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+extern std::atomic<int64_t> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- optional per-kernel timing (agx_set_profiling): CUDA events around the dominant kernels ----
+struct ProfSpan {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    bool armed = false;
+    void begin(cudaStream_t st);
+    void end(cudaStream_t st);
+    double ms();          // synchronises e1; < 0 when nothing was recorded
+    void destroy();
+};
+extern std::atomic<int> g_profiling;
+enum { AGX_PROF_SW_DUO = 0, AGX_PROF_SW_WAVE = 1, AGX_PROF_HMM_STREAM = 2, AGX_PROF_HMM_FP64 = 3,
+       AGX_PROF_SW_CLASSIFY = 4, AGX_PROF_HMM_CLASSIFY = 5, AGX_PROF_COUNT = 6 };
+
+// ---- Smith-Waterman -----------------------------------------------------------------------
+struct SwScoring {
+    int32_t match, mismatch, gap_open, gap_extend;
+};
+
+// Number of length classes handled by the packed s16x2 inter-task kernel; the extra class
+// (index SW_N_DUO_CLASSES) is the generic s32 wavefront kernel.
+constexpr int SW_N_DUO_CLASSES = 11;
+constexpr int SW_N_CLASSES = SW_N_DUO_CLASSES + 1;
+
+// Per-call device scratch for the SW path (owned by the device context).
+struct SwWorkspace {
+    int32_t *order = nullptr;        // [n_pairs]   pair ids grouped by class
+    int32_t *pair_class = nullptr;   // [n_pairs]
+    int32_t *counters = nullptr;     // [SW_N_CLASSES] histogram, then [SW_N_CLASSES] cursors, then misc
+    int32_t *wave_scratch = nullptr; // boundary columns for the wavefront kernel
+    int64_t cap_pairs = 0;
+    int64_t cap_wave = 0;
+    int32_t *h_counters = nullptr;   // pinned mirror of counters
+    ProfSpan prof_duo, prof_wave, prof_classify;
+};
+
+// Enqueue the whole SW path for one device-resident batch on `st`.
+int sw_run_device(SwWorkspace &ws, const uint8_t *d_seqs, const int64_t *d_off, const int32_t *d_len,
+                  int64_t n_pairs, SwScoring sc, int32_t *d_scores, cudaStream_t st);
+int sw_workspace_reserve(SwWorkspace &ws, int64_t n_pairs);
+void sw_workspace_free(SwWorkspace &ws);
+
+// ---- PairHMM ------------------------------------------------------------------------------
+struct HmmWorkspace {
+    int32_t *order = nullptr;     // [n_reads] read ids grouped by row class
+    int32_t *counters = nullptr;  // class histogram / cursors / rescue count
+    int32_t *h_counters = nullptr;
+    int64_t *rescue = nullptr;    // [cap_pairs] flat output indices needing FP64
+    int64_t cap_reads = 0;
+    int64_t cap_pairs = 0;
+    double *d_lut = nullptr;      // 256-entry Phred+33 -> probability table (host libm pow)
+    void *scratch = nullptr;      // boundary rows of the striped kernel
+    int64_t cap_scratch = 0;
+    ProfSpan prof_stream, prof_fp64, prof_classify;
+};
+
+struct HmmBatchView {
+    const uint8_t *buf;
+    const int64_t *read_field_off;  // [5*n_reads]
+    const int32_t *read_len;        // [n_reads]
+    const int32_t *read_batch;      // [n_reads]
+    int64_t n_reads;
+    const int64_t *hap_off;
+    const int32_t *hap_len;
+    int64_t n_haps;
+    const int64_t *batch_hap_start; // [n_batches+1]
+    int64_t n_batches;
+};
+
+int hmm_workspace_reserve(HmmWorkspace &ws, int64_t n_reads, int64_t n_pairs);
+void hmm_workspace_free(HmmWorkspace &ws);
+// d_read_out_off[r] = index in d_out of (read r, first haplotype of its batch); n_pairs = total outputs.
+int hmm_run_device(HmmWorkspace &ws, const HmmBatchView &v, const int64_t *d_read_out_off,
+                   int64_t n_pairs, bool gatk_mode, bool force_fp64, bool rescue, double *d_out,
+                   cudaStream_t st);
+
+}  // namespace agx

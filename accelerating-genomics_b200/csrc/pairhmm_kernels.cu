@@ -1,0 +1,548 @@
+// pairhmm_kernels.cu -- PairHMM forward (M / insertion X / deletion Y) on B200 (sm_100a).
+//
+// Replaces pairHMM/antidiagsPairHMM.c:99-117 (prior setup), :120-241 (recurrence), :206-212 and
+// :242 (final log10 sum); the same maths is pairHMM/pairHMMmatrix.c:20-66.  Restated
+// (SURVEY.md section 8a, rows a6-a10), with Q* = 10^-((c-33)/10) of the read row i-1:
+//     M[i][j] = prior(i,j) * ((1-(Qi+Qd)) * M[i-1][j-1] + (1-Qg) * (X[i-1][j-1] + Y[i-1][j-1]))
+//     X[i][j] = M[i-1][j] * Qi + X[i-1][j] * Qg
+//     Y[i][j] = M[i][j-1] * Qd + Y[i][j-1] * Qg
+//     prior   = (r == h || r == 'N' || h == 'N') ? 1-Qr : Qr          (reference quirk: no /3)
+//     row 0: M = X = 0, Y = SCALE / hap_len;  column 0 (i >= 1): 0
+//     result  = log10(sum_j M[R][j] + X[R][j]) - log10(SCALE)
+//
+// Two kernels:
+//   hmm_stream_kernel<K>   FP32 fast path.  One warp per read; lane t owns K consecutive read rows
+//                          in registers (rows are bottom-aligned, so row R is always the last row
+//                          of lane 31); ALL haplotypes of the read's batch stream through the warp
+//                          back to back, column by column, lane t one column behind lane t-1
+//                          (the bottom row of a lane moves down with __shfl_up_sync).  The
+//                          recurrence is carried on X' = X/Qi_i and Y' = Y/Qd_i, which turns the
+//                          X and Y updates into one FMA each (6 FP32 instructions per cell instead
+//                          of 8).  SCALE = 2^120.  Sums that are not finite or are too small to
+//                          be trusted in FP32 are queued for the FP64 kernel.
+//   hmm_striped_kernel<T,K> generic path: one warp per (read, haplotype), any read length (row
+//                          stripes of 32*K rows chained through a boundary row in global memory).
+//                          With T = double it evaluates the reference's expression in the
+//                          reference's own association order without FMA contraction and with
+//                          SCALE = DBL_MAX/16, i.e. it is the FP64 rescue / exact-parity path.
+#include <cfloat>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace agx {
+
+namespace {
+
+constexpr int HMM_MAX_K = 8;                    // stream kernel: reads up to 256 rows
+constexpr int HMM_N_CLASSES = HMM_MAX_K + 1;    // classes 0..7 -> K = 1..8, class 8 -> striped
+constexpr int HMM_LONG = HMM_MAX_K;
+constexpr int HCNT_RESCUE = HMM_N_CLASSES;      // counters[HCNT_RESCUE]  = rescue list length
+constexpr int HCNT_MAXHAP = HMM_N_CLASSES + 1;  // counters[HCNT_MAXHAP]  = longest haplotype
+constexpr int HCNT_WORDS = HMM_N_CLASSES + 4;
+constexpr int HMM_WARPS = 4;
+
+constexpr float SCALE_F = 1.329227995784916e36f;  // 2^120
+// a forward sum below this (2^-100) may have lost low-order terms to FP32 underflow
+constexpr float RESCUE_BELOW = 7.888609052210118e-31f;
+
+__global__ void __launch_bounds__(256)
+hmm_classify_kernel(const int32_t *__restrict__ read_len, int64_t n_reads,
+                    const int32_t *__restrict__ hap_len, int64_t n_haps,
+                    int32_t *__restrict__ order, int32_t *__restrict__ counters, int force_long)
+{
+    __shared__ int32_t s_cnt[HMM_N_CLASSES];
+    __shared__ int32_t s_base[HMM_N_CLASSES];
+    __shared__ int32_t s_maxhap;
+    if (threadIdx.x < HMM_N_CLASSES) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_maxhap = 0;
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int cls = -1, rank = 0;
+    if (i < n_reads) {
+        const int32_t R = read_len[i];
+        cls = (R <= 32 * HMM_MAX_K && !force_long) ? (R + 31) / 32 - 1 : HMM_LONG;
+        if (cls < 0) cls = 0;
+        rank = atomicAdd(&s_cnt[cls], 1);
+    }
+    if (i < n_haps) atomicMax(&s_maxhap, hap_len[i]);
+    __syncthreads();
+    if (threadIdx.x < HMM_N_CLASSES && s_cnt[threadIdx.x] > 0)
+        s_base[threadIdx.x] = atomicAdd(&counters[threadIdx.x], s_cnt[threadIdx.x]);
+    if (threadIdx.x == 0 && s_maxhap > 0) atomicMax(&counters[HCNT_MAXHAP], s_maxhap);
+    __syncthreads();
+    if (cls >= 0) order[(int64_t)cls * n_reads + s_base[cls] + rank] = (int32_t)i;
+}
+
+// ------------------------------------------------------------------------------------------
+// FP32 streaming kernel
+// ------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(HMM_WARPS * 32)
+hmm_stream_kernel(HmmBatchView v, const int64_t *__restrict__ read_out_off,
+                  const int32_t *__restrict__ order_cls, int32_t n_items,
+                  const double *__restrict__ lut_g, int gatk, double *__restrict__ out,
+                  int2 *__restrict__ rescue, int32_t *__restrict__ rescue_count)
+{
+    __shared__ double lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = lut_g[i];
+    __syncthreads();
+
+    const int t = threadIdx.x & 31;
+    const int item = blockIdx.x * HMM_WARPS + (threadIdx.x >> 5);
+    if (item >= n_items) return;
+    const int32_t r = order_cls[item];
+    const int32_t R = v.read_len[r];
+    const int32_t bt = v.read_batch[r];
+    const int64_t h0 = v.batch_hap_start[bt], h1 = v.batch_hap_start[bt + 1];
+    if (h1 <= h0) return;
+    const int64_t obase = read_out_off[r];
+
+    // ---- prior / transition setup for this lane's K rows (rows bottom-aligned) ----------------
+    const int pad = 32 * K - R;
+    const uint8_t *f_b = v.buf + v.read_field_off[5 * (int64_t)r + 0];
+    const uint8_t *f_q = v.buf + v.read_field_off[5 * (int64_t)r + 1];
+    const uint8_t *f_i = v.buf + v.read_field_off[5 * (int64_t)r + 2];
+    const uint8_t *f_d = v.buf + v.read_field_off[5 * (int64_t)r + 3];
+    const uint8_t *f_g = v.buf + v.read_field_off[5 * (int64_t)r + 4];
+
+    float pm[K], px[K], ca[K], cbx[K], cby[K], ccx[K], cg[K];
+    int32_t rb[K];
+#pragma unroll
+    for (int jj = 0; jj < K; ++jj) {
+        const int i = t * K + jj - pad;      // 0-based read position of this row
+        if (i < 0) {
+            // padding rows reproduce row 0: M = X = 0 and Y stays at its initial value
+            pm[jj] = px[jj] = 0.f; ca[jj] = cbx[jj] = cby[jj] = ccx[jj] = 0.f; cg[jj] = 1.f;
+            rb[jj] = 0x100;
+        } else {
+            const double Qr = lut[f_q[i]], Qi = lut[f_i[i]], Qd = lut[f_d[i]], Qg = lut[f_g[i]];
+            // previous row's Qi / Qd un-scale X' and Y' of the diagonal cell; row 0 is unscaled
+            const double Qi_up = (i > 0) ? lut[f_i[i - 1]] : 1.0;
+            const double Qd_up = (i > 0) ? lut[f_d[i - 1]] : 1.0;
+            const int32_t base = f_b[i];
+            const double mm = 1.0 - (Qi + Qd), gm = 1.0 - Qg;
+            pm[jj] = (float)(1.0 - Qr);
+            px[jj] = (base == 'N') ? pm[jj] : (float)(gatk ? Qr / 3.0 : Qr);
+            ca[jj] = (float)mm;
+            cbx[jj] = (float)(gm * Qi_up);
+            cby[jj] = (float)(gm * Qd_up);
+            ccx[jj] = (i > 0) ? (float)(Qg * Qi_up / Qi) : 0.f;
+            cg[jj] = (float)Qg;
+            rb[jj] = base;
+        }
+    }
+    const float qi_last = (float)lut[f_i[R - 1]];   // X[R][j] = Qi_R * X'[R][j]
+    const bool top_boundary = (t * K - 1) < pad;    // the row above this lane's first row is row 0
+
+    // ---- streaming state ------------------------------------------------------------------------
+    float M[K], X[K], Y[K];
+#pragma unroll
+    for (int jj = 0; jj < K; ++jj) { M[jj] = X[jj] = Y[jj] = 0.f; }
+    float pdM = 0.f, pdX = 0.f, pdY = 0.f;           // what arrived one step ago = diagonal inputs
+    float bM = 0.f, bX = 0.f, bY = 0.f;              // this lane's bottom row, sent down next step
+    float acc = 0.f, init = 0.f;
+
+    int64_t hidx = h0 - 1;     // virtual haplotype of length t: lane t idles for t steps
+    int32_t c = 1, Hlen = t;
+    const uint8_t *hptr = nullptr;
+
+    int64_t total = 31;
+    for (int64_t h = h0; h < h1; ++h) total += v.hap_len[h];
+
+#pragma unroll 1
+    for (int64_t s = 0; s < total; ++s) {
+        if (c > Hlen) {
+            // ---- this lane finished a haplotype: emit (lane 31 owns row R) and start the next ----
+            if (t == 31 && hidx >= h0) {
+                const int64_t o = obase + (hidx - h0);
+                if (!(acc >= RESCUE_BELOW) || !isfinite(acc)) {
+                    rescue[atomicAdd(rescue_count, 1)] = make_int2(r, (int)hidx);
+                    out[o] = nan("");
+                } else {
+                    out[o] = log10((double)acc) - log10((double)SCALE_F);
+                }
+            }
+            ++hidx;
+            acc = 0.f;
+            c = 1;
+            if (hidx < h1) {
+                Hlen = v.hap_len[hidx];
+                hptr = v.buf + v.hap_off[hidx];
+                init = SCALE_F / (float)Hlen;
+            } else {
+                Hlen = 0x7fffffff;   // drained: keep stepping on neutral input
+                hptr = nullptr;
+            }
+#pragma unroll
+            for (int jj = 0; jj < K; ++jj) { M[jj] = 0.f; X[jj] = 0.f; Y[jj] = (t * K + jj < pad) ? init : 0.f; }
+            pdM = 0.f; pdX = 0.f; pdY = top_boundary ? init : 0.f;
+        }
+        const int32_t hb = (hptr != nullptr && hidx >= h0) ? (int32_t)__ldg(hptr + (c - 1)) : 0x200;
+        const bool hN = (hb == 'N');
+
+        float upM = __shfl_up_sync(0xffffffffu, bM, 1);
+        float upX = __shfl_up_sync(0xffffffffu, bX, 1);
+        float upY = __shfl_up_sync(0xffffffffu, bY, 1);
+        if (t == 0) { upM = 0.f; upX = 0.f; upY = init; }
+        float dM = pdM, dX = pdX, dY = pdY;
+        pdM = upM; pdX = upX; pdY = upY;
+#pragma unroll
+        for (int jj = 0; jj < K; ++jj) {
+            const float oM = M[jj], oX = X[jj], oY = Y[jj];
+            const float pr = (rb[jj] == hb || hN) ? pm[jj] : px[jj];
+            float vv = cby[jj] * dY;
+            vv = fmaf(cbx[jj], dX, vv);
+            vv = fmaf(ca[jj], dM, vv);
+            const float mn = pr * vv;
+            const float xn = fmaf(ccx[jj], upX, upM);
+            const float yn = fmaf(cg[jj], oY, oM);
+            dM = oM; dX = oX; dY = oY;
+            upM = mn; upX = xn;
+            M[jj] = mn; X[jj] = xn; Y[jj] = yn;
+        }
+        bM = M[K - 1]; bX = X[K - 1]; bY = Y[K - 1];
+        acc += fmaf(qi_last, bX, bM);
+        ++c;
+    }
+    // the last haplotype of lane 31 ends exactly at the last step
+    if (t == 31 && hidx >= h0 && hidx < h1 && c > Hlen) {
+        const int64_t o = obase + (hidx - h0);
+        if (!(acc >= RESCUE_BELOW) || !isfinite(acc)) {
+            rescue[atomicAdd(rescue_count, 1)] = make_int2(r, (int)hidx);
+            out[o] = nan("");
+        } else {
+            out[o] = log10((double)acc) - log10((double)SCALE_F);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// generic striped kernel (FP64 exact-order path, long reads)
+// ------------------------------------------------------------------------------------------
+template <typename T> struct Num;
+template <> struct Num<float> {
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float scale() { return SCALE_F; }
+    static __device__ __forceinline__ bool bad(float s) { return !(s >= RESCUE_BELOW) || !isfinite(s); }
+};
+template <> struct Num<double> {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double scale() { return DBL_MAX / 16; }
+    static __device__ __forceinline__ bool bad(double) { return false; }
+};
+
+template <typename T, int K>
+__device__ void hmm_striped_pair(const HmmBatchView &v, const double *lut, int32_t r, int64_t h,
+                                 int gatk, T *scratch, double *out_slot, int2 *rescue,
+                                 int32_t *rescue_count)
+{
+    const int t = threadIdx.x & 31;
+    const int32_t R = v.read_len[r];
+    const int32_t H = v.hap_len[h];
+    const uint8_t *hap = v.buf + v.hap_off[h];
+    const uint8_t *f_b = v.buf + v.read_field_off[5 * (int64_t)r + 0];
+    const uint8_t *f_q = v.buf + v.read_field_off[5 * (int64_t)r + 1];
+    const uint8_t *f_i = v.buf + v.read_field_off[5 * (int64_t)r + 2];
+    const uint8_t *f_d = v.buf + v.read_field_off[5 * (int64_t)r + 3];
+    const uint8_t *f_g = v.buf + v.read_field_off[5 * (int64_t)r + 4];
+    constexpr int ROWS = 32 * K;
+    const int n_stripes = (R + ROWS - 1) / ROWS;
+    const int pad = n_stripes * ROWS - R;
+    const T init = Num<T>::scale() / (T)H;
+    T acc = (T)0;
+
+    for (int st = 0; st < n_stripes; ++st) {
+        T pm[K], px[K], cmm[K], cgm[K], cqi[K], cqd[K], cqg[K];
+        int32_t rb[K];
+        T M[K], X[K], Y[K];
+#pragma unroll
+        for (int jj = 0; jj < K; ++jj) {
+            const int i = st * ROWS + t * K + jj - pad;
+            if (i < 0) {
+                pm[jj] = px[jj] = (T)0; cmm[jj] = cgm[jj] = cqi[jj] = cqd[jj] = (T)0; cqg[jj] = (T)1;
+                rb[jj] = 0x100;
+                Y[jj] = init;
+            } else {
+                const double Qr = lut[f_q[i]], Qi = lut[f_i[i]], Qd = lut[f_d[i]], Qg = lut[f_g[i]];
+                const int32_t base = f_b[i];
+                pm[jj] = (T)(1 - Qr);
+                px[jj] = (base == 'N') ? pm[jj] : (T)(gatk ? Qr / 3 : Qr);
+                cmm[jj] = (T)(1 - (Qi + Qd));
+                cgm[jj] = (T)(1 - Qg);
+                cqi[jj] = (T)Qi; cqd[jj] = (T)Qd; cqg[jj] = (T)Qg;
+                rb[jj] = base;
+                Y[jj] = (T)0;
+            }
+            M[jj] = X[jj] = (T)0;
+        }
+        const bool first = (st == 0), last = (st == n_stripes - 1);
+        const bool top_boundary = first && ((t * K - 1) < pad);
+        T pdM = (T)0, pdX = (T)0, pdY = top_boundary ? init : (T)0;
+        T bM = (T)0, bX = (T)0, bY = (T)0;
+        T inM = (T)0, inX = (T)0, inY = (T)0;   // boundary row prefetched for lane 0
+        const int S = H + 31;
+        for (int s0 = 0; s0 < S; s0 += 32) {
+            if (!first) {
+                const int cc = s0 + t + 1;       // column this lane prefetches for lane 0
+                if (cc <= H) {
+                    inM = __ldcg(scratch + 3 * (int64_t)cc);
+                    inX = __ldcg(scratch + 3 * (int64_t)cc + 1);
+                    inY = __ldcg(scratch + 3 * (int64_t)cc + 2);
+                }
+            }
+            const int send = min(32, S - s0);
+            for (int u = 0; u < send; ++u) {
+                const int s = s0 + u;
+                const int c = s - t + 1;
+                const bool active = (c >= 1 && c <= H);
+                const int32_t hb = active ? (int32_t)__ldg(hap + c - 1) : 0x200;
+                const bool hN = (hb == 'N');
+                T upM = __shfl_up_sync(0xffffffffu, bM, 1);
+                T upX = __shfl_up_sync(0xffffffffu, bX, 1);
+                T upY = __shfl_up_sync(0xffffffffu, bY, 1);
+                const T sM = __shfl_sync(0xffffffffu, inM, u);
+                const T sX = __shfl_sync(0xffffffffu, inX, u);
+                const T sY = __shfl_sync(0xffffffffu, inY, u);
+                if (t == 0) {
+                    if (first) { upM = (T)0; upX = (T)0; upY = init; }
+                    else       { upM = sM; upX = sX; upY = sY; }
+                }
+                if (active) {
+                    T dM = pdM, dX = pdX, dY = pdY;
+                    pdM = upM; pdX = upX; pdY = upY;
+#pragma unroll
+                    for (int jj = 0; jj < K; ++jj) {
+                        const T oM = M[jj], oX = X[jj], oY = Y[jj];
+                        const T pr = (rb[jj] == hb || hN) ? pm[jj] : px[jj];
+                        // reference association order, no FMA contraction
+                        // (antidiagsPairHMM.c:184-195 / pairHMMmatrix.c:51-53)
+                        const T mn = Num<T>::mul(pr, Num<T>::add(Num<T>::mul(cmm[jj], dM),
+                                                                 Num<T>::mul(cgm[jj], Num<T>::add(dX, dY))));
+                        const T xn = Num<T>::add(Num<T>::mul(upM, cqi[jj]), Num<T>::mul(upX, cqg[jj]));
+                        const T yn = Num<T>::add(Num<T>::mul(oM, cqd[jj]), Num<T>::mul(oY, cqg[jj]));
+                        dM = oM; dX = oX; dY = oY;
+                        upM = mn; upX = xn;
+                        M[jj] = mn; X[jj] = xn; Y[jj] = yn;
+                    }
+                    bM = M[K - 1]; bX = X[K - 1]; bY = Y[K - 1];
+                    if (t == 31) {
+                        if (last) {
+                            acc = Num<T>::add(acc, Num<T>::add(bM, bX));
+                        } else {
+                            scratch[3 * (int64_t)c] = bM;
+                            scratch[3 * (int64_t)c + 1] = bX;
+                            scratch[3 * (int64_t)c + 2] = bY;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        __threadfence_block();
+        __syncwarp();
+    }
+    if (t == 31) {
+        if (Num<T>::bad(acc) && rescue != nullptr) {
+            rescue[atomicAdd(rescue_count, 1)] = make_int2(r, (int)h);
+            *out_slot = nan("");
+        } else {
+            *out_slot = log10((double)acc) - log10((double)Num<T>::scale());
+        }
+    }
+}
+
+// mode 0: items are explicit (read, haplotype) pairs; mode 1: items are reads, all haplotypes each
+template <typename T, int K>
+__global__ void __launch_bounds__(HMM_WARPS * 32)
+hmm_striped_kernel(HmmBatchView v, const int64_t *__restrict__ read_out_off,
+                   const int2 *__restrict__ pair_list, const int32_t *__restrict__ read_list,
+                   const int32_t *__restrict__ n_items_ptr, int32_t n_items_host,
+                   const double *__restrict__ lut_g, int gatk, T *__restrict__ scratch,
+                   int64_t scratch_stride, double *__restrict__ out, int2 *__restrict__ rescue,
+                   int32_t *__restrict__ rescue_count)
+{
+    __shared__ double lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = lut_g[i];
+    __syncthreads();
+    const int64_t warp = (int64_t)blockIdx.x * HMM_WARPS + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * HMM_WARPS;
+    const int32_t n_items = n_items_ptr ? *n_items_ptr : n_items_host;
+    T *my_scratch = scratch + warp * scratch_stride;
+    for (int64_t it = warp; it < n_items; it += n_warps) {
+        if (pair_list) {
+            const int2 pr = pair_list[it];
+            const int32_t bt = v.read_batch[pr.x];
+            const int64_t o = read_out_off[pr.x] + (pr.y - v.batch_hap_start[bt]);
+            hmm_striped_pair<T, K>(v, lut, pr.x, pr.y, gatk, my_scratch, out + o, rescue, rescue_count);
+        } else {
+            const int32_t r = read_list[it];
+            const int32_t bt = v.read_batch[r];
+            const int64_t h0 = v.batch_hap_start[bt], h1 = v.batch_hap_start[bt + 1];
+            for (int64_t h = h0; h < h1; ++h)
+                hmm_striped_pair<T, K>(v, lut, r, h, gatk, my_scratch, out + read_out_off[r] + (h - h0),
+                                       rescue, rescue_count);
+        }
+    }
+}
+
+template <int K>
+int launch_stream(const HmmBatchView &v, const int64_t *read_out_off, const int32_t *order,
+                  int32_t count, const double *lut, int gatk, double *out, int2 *rescue,
+                  int32_t *rescue_count, cudaStream_t st)
+{
+    if (count == 0) return AGX_OK;
+    const int blocks = (count + HMM_WARPS - 1) / HMM_WARPS;
+    hmm_stream_kernel<K><<<blocks, HMM_WARPS * 32, 0, st>>>(
+        v, read_out_off, order + (int64_t)(K - 1) * v.n_reads, count, lut, gatk, out, rescue, rescue_count);
+    count_launch();
+    AGX_CUDA(cudaGetLastError());
+    return AGX_OK;
+}
+
+}  // namespace
+
+int hmm_workspace_reserve(HmmWorkspace &ws, int64_t n_reads, int64_t n_pairs)
+{
+    if (!ws.counters) {
+        AGX_CUDA(cudaMalloc(&ws.counters, HCNT_WORDS * sizeof(int32_t)));
+        AGX_CUDA(cudaMallocHost(&ws.h_counters, HCNT_WORDS * sizeof(int32_t)));
+        AGX_CUDA(cudaMalloc(&ws.d_lut, 256 * sizeof(double)));
+        // Phred+33 -> probability with the HOST libm pow(), exactly the reference's expression
+        // (antidiagsPairHMM.c:104-107); characters are `char` there, i.e. signed on x86.
+        double lut[256];
+        for (int c = 0; c < 256; ++c) lut[c] = pow(10.0, -((double)(signed char)c - 33.0) * 0.1);
+        AGX_CUDA(cudaMemcpy(ws.d_lut, lut, sizeof lut, cudaMemcpyHostToDevice));
+    }
+    if (n_reads > ws.cap_reads) {
+        if (ws.order) cudaFree(ws.order);
+        ws.order = nullptr; ws.cap_reads = 0;
+        AGX_CUDA(cudaMalloc(&ws.order, (size_t)n_reads * HMM_N_CLASSES * sizeof(int32_t)));
+        ws.cap_reads = n_reads;
+    }
+    if (n_pairs > ws.cap_pairs) {
+        if (ws.rescue) cudaFree(ws.rescue);
+        ws.rescue = nullptr; ws.cap_pairs = 0;
+        AGX_CUDA(cudaMalloc(&ws.rescue, (size_t)n_pairs * sizeof(int2)));
+        ws.cap_pairs = n_pairs;
+    }
+    return AGX_OK;
+}
+
+void hmm_workspace_free(HmmWorkspace &ws)
+{
+    if (ws.order) cudaFree(ws.order);
+    if (ws.counters) cudaFree(ws.counters);
+    if (ws.h_counters) cudaFreeHost(ws.h_counters);
+    if (ws.rescue) cudaFree(ws.rescue);
+    if (ws.d_lut) cudaFree(ws.d_lut);
+    if (ws.scratch) cudaFree(ws.scratch);
+    ws.prof_stream.destroy(); ws.prof_fp64.destroy(); ws.prof_classify.destroy();
+    ws = HmmWorkspace();
+}
+
+static int hmm_scratch_reserve(HmmWorkspace &ws, int64_t bytes)
+{
+    if (bytes > ws.cap_scratch) {
+        if (ws.scratch) cudaFree(ws.scratch);
+        ws.scratch = nullptr; ws.cap_scratch = 0;
+        AGX_CUDA(cudaMalloc(&ws.scratch, (size_t)bytes));
+        ws.cap_scratch = bytes;
+    }
+    return AGX_OK;
+}
+
+int hmm_run_device(HmmWorkspace &ws, const HmmBatchView &v, const int64_t *d_read_out_off,
+                   int64_t n_pairs, bool gatk_mode, bool force_fp64, bool do_rescue, double *d_out,
+                   cudaStream_t st)
+{
+    if (v.n_reads == 0 || n_pairs == 0) return AGX_OK;
+    if (v.n_reads > (int64_t)1 << 30 || v.n_haps > (int64_t)1 << 30)
+        return fail(AGX_ERANGE, "pairhmm: more than 2^30 reads or haplotypes in one call");
+    int rc = hmm_workspace_reserve(ws, v.n_reads, n_pairs);
+    if (rc != AGX_OK) return rc;
+
+    AGX_CUDA(cudaMemsetAsync(ws.counters, 0, HCNT_WORDS * sizeof(int32_t), st));
+    const int64_t nmax = v.n_reads > v.n_haps ? v.n_reads : v.n_haps;
+    hmm_classify_kernel<<<(int)((nmax + 255) / 256), 256, 0, st>>>(
+        v.read_len, v.n_reads, v.hap_len, v.n_haps, ws.order, ws.counters, force_fp64 ? 1 : 0);
+    count_launch();
+    AGX_CUDA(cudaGetLastError());
+    AGX_CUDA(cudaMemcpyAsync(ws.h_counters, ws.counters, HCNT_WORDS * sizeof(int32_t),
+                             cudaMemcpyDeviceToHost, st));
+    AGX_CUDA(cudaStreamSynchronize(st));
+    int32_t counts[HMM_N_CLASSES];
+    for (int c = 0; c < HMM_N_CLASSES; ++c) counts[c] = ws.h_counters[c];
+    const int32_t max_hap = ws.h_counters[HCNT_MAXHAP];
+    const int gatk = gatk_mode ? 1 : 0;
+    int2 *rescue = reinterpret_cast<int2 *>(ws.rescue);
+    int32_t *rescue_count = ws.counters + HCNT_RESCUE;
+
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t stride = 3 * ((int64_t)max_hap + 2);
+
+    if (!force_fp64) {
+        ws.prof_stream.begin(st);
+#define AGX_STREAM(KK)                                                                              \
+    if ((rc = launch_stream<KK>(v, d_read_out_off, ws.order, counts[KK - 1], ws.d_lut, gatk, d_out, \
+                                rescue, rescue_count, st)) != AGX_OK)                               \
+        return rc;
+        AGX_STREAM(1) AGX_STREAM(2) AGX_STREAM(3) AGX_STREAM(4)
+        AGX_STREAM(5) AGX_STREAM(6) AGX_STREAM(7) AGX_STREAM(8)
+#undef AGX_STREAM
+        ws.prof_stream.end(st);
+        if (counts[HMM_LONG] > 0) {
+            // reads longer than 256 rows: FP32 striped kernel, one warp per read
+            int64_t warps = counts[HMM_LONG];
+            if (warps > (int64_t)sms * 16) warps = (int64_t)sms * 16;
+            const int blocks = (int)((warps + HMM_WARPS - 1) / HMM_WARPS);
+            rc = hmm_scratch_reserve(ws, stride * blocks * HMM_WARPS * (int64_t)sizeof(float));
+            if (rc != AGX_OK) return rc;
+            hmm_striped_kernel<float, 8><<<blocks, HMM_WARPS * 32, 0, st>>>(
+                v, d_read_out_off, nullptr, ws.order + (int64_t)HMM_LONG * v.n_reads, nullptr,
+                counts[HMM_LONG], ws.d_lut, gatk, reinterpret_cast<float *>(ws.scratch), stride, d_out,
+                rescue, rescue_count);
+            count_launch();
+            AGX_CUDA(cudaGetLastError());
+        }
+        if (!do_rescue) return AGX_OK;
+        AGX_CUDA(cudaMemcpyAsync(ws.h_counters + HCNT_RESCUE, rescue_count, sizeof(int32_t),
+                                 cudaMemcpyDeviceToHost, st));
+        AGX_CUDA(cudaStreamSynchronize(st));
+        const int32_t n_rescue = ws.h_counters[HCNT_RESCUE];
+        if (n_rescue == 0) return AGX_OK;
+        int64_t warps = n_rescue;
+        if (warps > (int64_t)sms * 16) warps = (int64_t)sms * 16;
+        const int blocks = (int)((warps + HMM_WARPS - 1) / HMM_WARPS);
+        rc = hmm_scratch_reserve(ws, stride * blocks * HMM_WARPS * (int64_t)sizeof(double));
+        if (rc != AGX_OK) return rc;
+        ws.prof_fp64.begin(st);
+        hmm_striped_kernel<double, 4><<<blocks, HMM_WARPS * 32, 0, st>>>(
+            v, d_read_out_off, rescue, nullptr, nullptr, n_rescue, ws.d_lut, gatk,
+            reinterpret_cast<double *>(ws.scratch), stride, d_out, nullptr, nullptr);
+        ws.prof_fp64.end(st);
+        count_launch();
+        AGX_CUDA(cudaGetLastError());
+        return AGX_OK;
+    }
+
+    // force_fp64: every read goes through the exact-order FP64 kernel (classified "long" above)
+    int64_t warps = counts[HMM_LONG];
+    if (warps > (int64_t)sms * 16) warps = (int64_t)sms * 16;
+    const int blocks = (int)((warps + HMM_WARPS - 1) / HMM_WARPS);
+    if (blocks == 0) return AGX_OK;
+    rc = hmm_scratch_reserve(ws, stride * blocks * HMM_WARPS * (int64_t)sizeof(double));
+    if (rc != AGX_OK) return rc;
+    hmm_striped_kernel<double, 4><<<blocks, HMM_WARPS * 32, 0, st>>>(
+        v, d_read_out_off, nullptr, ws.order + (int64_t)HMM_LONG * v.n_reads, nullptr, counts[HMM_LONG],
+        ws.d_lut, gatk, reinterpret_cast<double *>(ws.scratch), stride, d_out, nullptr, nullptr);
+    count_launch();
+    AGX_CUDA(cudaGetLastError());
+    return AGX_OK;
+}
+
+}  // namespace agx

@@ -1,0 +1,545 @@
+// sw_kernels.cu -- score-only affine-gap Smith-Waterman on B200 (sm_100a).
+//
+// Replaces the DP of smithWaterman/antidiagonalSmithWaterman.c:246-348 (reference paths are
+// relative to the reference repository).  Recurrence restated:
+//     P[i][j] = max(D[i-1][j] + go + ge, P[i-1][j] + ge)        vertical gap   ("F" below)
+//     Q[i][j] = max(D[i][j-1] + go + ge, Q[i][j-1] + ge)        horizontal gap ("E" below)
+//     D[i][j] = max(P, Q, D[i-1][j-1] + (x==y ? match : mismatch), 0)      ("H" below)
+//     score   = max D
+// with D = 0 on row/column 0 and P/Q = -inf there.  Because D >= 0, every P/Q value that is <= 0
+// is interchangeable with -inf, so boundaries are initialised with goe = go + ge instead of INT_MIN.
+//
+// Three kernels:
+//   sw_classify_kernel   device-side batch packer: strips the trailing '\n' symbol, picks the
+//                        length class of every pair and appends it to that class's work list.
+//   sw_duo_kernel<G,K>   INTER-TASK kernel.  A sub-warp of G lanes scores TWO pairs at once, one in
+//                        each 16-bit half of a register (DPX s16x2: VIADDMNMX / VIMNMX3.RELU /
+//                        VIADD.16x2).  Each lane keeps K columns of both pairs in registers and the
+//                        rows stream through the sub-warp systolically (lane t is one row behind
+//                        lane t-1; the boundary column moves with __shfl_up_sync).
+//   sw_wave_kernel       INTRA-TASK kernel for everything else (long sequences, non-ACGT bytes,
+//                        scores that could overflow s16): one warp per pair, s32 DPX, 32 lanes x 8
+//                        columns per stripe, stripes chained through a boundary column in global
+//                        memory.  It compares raw bytes, so '\n', 'N', lower case ... behave exactly
+//                        as in the reference (:332).
+#include "common.cuh"
+
+namespace agx {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// class table of the duo kernel: columns capacity = G*K
+// ------------------------------------------------------------------------------------------
+struct DuoClass { int g, k; };
+__host__ __device__ constexpr DuoClass duo_class(int c)
+{
+    constexpr DuoClass t[SW_N_DUO_CLASSES] = {{8, 4},  {8, 8},  {8, 12},  {8, 16},  {8, 19}, {8, 24},
+                                              {8, 32}, {16, 24}, {16, 32}, {32, 24}, {32, 32}};
+    return t[c];
+}
+__host__ __device__ constexpr int duo_cap(int c) { return duo_class(c).g * duo_class(c).k; }
+constexpr int DUO_MAX_CAP = duo_cap(SW_N_DUO_CLASSES - 1);  // 1024
+constexpr int GENERIC = SW_N_DUO_CLASSES;
+
+// counters layout (int32): [0, NC) class counts / append cursors; NC: max raw length seen
+constexpr int CNT_MAXLEN = SW_N_CLASSES;
+constexpr int CNT_WORDS = SW_N_CLASSES + 4;
+
+struct DuoConst {
+    uint32_t goe2;    // (go+ge) in both halves
+    uint32_t ext2;    // ge in both halves
+    uint32_t xb4;     // byte (mismatch - goe) replicated 4x      : PRMT source for "no match"
+    uint32_t mxor;    // (match - goe) ^ (mismatch - goe), one byte
+    int32_t goe, match;
+};
+
+// prmt.b32 in its default mode: selector nibble bit 3 replicates the sign of the selected byte
+// (__byte_perm masks that bit off, so the PTX is spelled out).
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(s));
+    return d;
+}
+
+__device__ __forceinline__ bool strip_newline(const uint8_t *p, int32_t &n)
+{
+    if (n > 0 && p[n - 1] == '\n') { --n; return true; }
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------
+// classify / bin
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sw_classify_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
+                   const int32_t *__restrict__ len, int64_t n_pairs, int32_t s16_max_short,
+                   int32_t match, int32_t *__restrict__ order, int32_t *__restrict__ counters,
+                   int32_t *__restrict__ scores)
+{
+    __shared__ int32_t s_cnt[SW_N_CLASSES];
+    __shared__ int32_t s_base[SW_N_CLASSES];
+    __shared__ int32_t s_maxlen;
+    if (threadIdx.x < SW_N_CLASSES) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_maxlen = 0;
+    __syncthreads();
+
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int cls = -1, rank = 0;
+    if (p < n_pairs) {
+        int32_t lx = len[2 * p], ly = len[2 * p + 1];
+        const int32_t raw_max = lx > ly ? lx : ly;
+        const bool nx = strip_newline(seqs + off[2 * p], lx);
+        const bool ny = strip_newline(seqs + off[2 * p + 1], ly);
+        const int32_t shorter = lx < ly ? lx : ly;
+        if (shorter == 0) {
+            // one side holds nothing but (possibly) its newline symbol: the only positive cell is
+            // '\n' against '\n', present iff both lines end with one
+            scores[p] = (nx && ny) ? match : 0;
+        } else {
+            cls = GENERIC;
+            if (shorter <= s16_max_short) {
+#pragma unroll
+                for (int c = SW_N_DUO_CLASSES - 1; c >= 0; --c)
+                    if (shorter <= duo_cap(c)) cls = c;
+            }
+            rank = atomicAdd(&s_cnt[cls], 1);
+            atomicMax(&s_maxlen, raw_max);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < SW_N_CLASSES && s_cnt[threadIdx.x] > 0)
+        s_base[threadIdx.x] = atomicAdd(&counters[threadIdx.x], s_cnt[threadIdx.x]);
+    if (threadIdx.x == 0 && s_maxlen > 0) atomicMax(&counters[CNT_MAXLEN], s_maxlen);
+    __syncthreads();
+    if (cls >= 0) order[(int64_t)cls * n_pairs + s_base[cls] + rank] = (int32_t)p;
+}
+
+// ------------------------------------------------------------------------------------------
+// inter-task duo kernel (s16x2 DPX)
+// ------------------------------------------------------------------------------------------
+constexpr int DUO_THREADS = 128;
+constexpr int DUO_CH = 32;    // rows converted per refill
+constexpr int DUO_RING = 64;  // row ring slots (>= DUO_CH + G)
+
+struct DuoSeq {
+    const uint8_t *a;  // columns (shorter sequence)
+    const uint8_t *b;  // rows (longer sequence)
+    int32_t la, lb;
+    bool both_nl;
+};
+
+__device__ __forceinline__ DuoSeq load_pair(const uint8_t *seqs, const int64_t *off,
+                                            const int32_t *len, int32_t p)
+{
+    DuoSeq d;
+    const uint8_t *x = seqs + off[2 * (int64_t)p];
+    const uint8_t *y = seqs + off[2 * (int64_t)p + 1];
+    int32_t lx = len[2 * (int64_t)p], ly = len[2 * (int64_t)p + 1];
+    const bool nx = strip_newline(x, lx);
+    const bool ny = strip_newline(y, ly);
+    d.both_nl = nx && ny;
+    if (lx <= ly) { d.a = x; d.la = lx; d.b = y; d.lb = ly; }
+    else          { d.a = y; d.la = ly; d.b = x; d.lb = lx; }
+    return d;
+}
+
+// ASCII -> 2-bit code (A 0, C 1, T 2, G 3); ok is cleared for anything outside "ACGT".
+__device__ __forceinline__ uint32_t base_code(uint32_t ch, bool &ok)
+{
+    const uint32_t code = (ch >> 1) & 3u;
+    ok = ok && (((0x47544341u >> (8 * code)) & 0xffu) == ch);
+    return code;
+}
+
+template <int G, int K>
+__global__ void __launch_bounds__(DUO_THREADS)
+sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
+              const int32_t *__restrict__ len, const int32_t *__restrict__ order_cls,
+              int32_t n_in_class, DuoConst kc, int32_t *__restrict__ scores,
+              int32_t *__restrict__ generic_list, int32_t *__restrict__ generic_cursor)
+{
+    constexpr int CAP = G * K;
+    constexpr int SUBS = DUO_THREADS / G;
+    __shared__ uint2 ring[SUBS][DUO_RING];
+
+    const int lane = threadIdx.x & 31;
+    const int t = threadIdx.x & (G - 1);          // lane inside the sub-warp
+    const int sub = threadIdx.x / G;              // sub-warp inside the CTA
+    const int duo = blockIdx.x * SUBS + sub;
+
+    // ---- the two pairs of this sub-warp ------------------------------------------------------
+    int32_t pid[2] = {-1, -1};
+    DuoSeq sq[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int32_t slot = 2 * duo + h;
+        sq[h].a = sq[h].b = nullptr; sq[h].la = sq[h].lb = 0; sq[h].both_nl = false;
+        if (slot < n_in_class) {
+            pid[h] = order_cls[slot];
+            sq[h] = load_pair(seqs, off, len, pid[h]);
+        }
+    }
+    // rows are bottom-aligned to the longest b of the whole warp so the step loop is warp-uniform
+    int32_t Lb = max(sq[0].lb, sq[1].lb);
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) Lb = max(Lb, __shfl_xor_sync(0xffffffffu, Lb, m));
+    const int S = Lb + G - 1;
+
+    // ---- column selectors (columns right-aligned; padding columns select "sign of byte 0") ----
+    bool ok = true;
+    uint32_t sel[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int idx = t * K + j - (CAP - sq[h].la);
+            uint32_t nib_lo = 8u + 4u * h, nib_hi = 8u + 4u * h;     // padding: 0x0000 / 0xffff
+            if (idx >= 0) {
+                const uint32_t code = base_code(sq[h].a[idx], ok);
+                nib_lo = code + 4u * h;
+                nib_hi = nib_lo | 8u;                                 // sign-extend that byte
+            }
+            s |= (nib_lo | (nib_hi << 4)) << (8 * h);
+        }
+        sel[j] = s;
+    }
+
+    // ---- state ---------------------------------------------------------------------------------
+    uint32_t Gp[K], F[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) { Gp[j] = kc.goe2; F[j] = kc.goe2; }
+    uint32_t rmax = kc.goe2, g_out = kc.goe2, e_out = kc.goe2, g_in_prev = kc.goe2;
+
+    for (int i = t; i < DUO_RING; i += G) ring[sub][i] = make_uint2(kc.xb4, kc.xb4);
+
+    for (int s0 = 0; s0 < S; s0 += DUO_CH) {
+        __syncwarp();
+        // refill: rows [s0, s0 + DUO_CH) -> PRMT source words, 4 bytes per pair
+#pragma unroll
+        for (int i = 0; i < DUO_CH / G; ++i) {
+            const int r = s0 + t + G * i;
+            uint32_t w[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int idx = r - (Lb - sq[h].lb);
+                w[h] = kc.xb4;
+                if (idx >= 0 && r < Lb) {
+                    const uint32_t code = base_code(sq[h].b[idx], ok);
+                    w[h] = kc.xb4 ^ (kc.mxor << (8 * code));
+                }
+            }
+            ring[sub][r & (DUO_RING - 1)] = make_uint2(w[0], w[1]);
+        }
+        __syncwarp();
+
+        const int send = min(DUO_CH, S - s0);
+#pragma unroll 1
+        for (int u = 0; u < send; ++u) {
+            const int s = s0 + u;
+            const uint2 R = ring[sub][(s - t) & (DUO_RING - 1)];
+            uint32_t g_in = __shfl_up_sync(0xffffffffu, g_out, 1, G);
+            uint32_t e = __shfl_up_sync(0xffffffffu, e_out, 1, G);
+            if (t == 0) { g_in = kc.goe2; e = kc.goe2; }
+            uint32_t gdiag = g_in_prev;
+            g_in_prev = g_in;
+            uint32_t gleft = g_in;
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const uint32_t tt = prmt(R.x, R.y, sel[j]);                  // (subst - goe) per half
+                const uint32_t d = __vadd2(gdiag, tt);                    // H[i-1][j-1] + subst
+                e = __viaddmax_s16x2(e, kc.ext2, gleft);                  // E[i][j]
+                F[j] = __viaddmax_s16x2(F[j], kc.ext2, Gp[j]);            // F[i][j]
+                const uint32_t hcell = __vimax3_s16x2_relu(e, F[j], d);   // H[i][j]
+                gdiag = Gp[j];
+                gleft = __vadd2(hcell, kc.goe2);                          // H[i][j] + goe
+                Gp[j] = gleft;
+                if (j & 1) rmax = __vimax3_s16x2(rmax, Gp[j - 1], gleft);
+                else if (j == K - 1) rmax = __vmaxs2(rmax, gleft);
+            }
+            g_out = gleft;
+            e_out = e;
+        }
+    }
+
+    // ---- results ---------------------------------------------------------------------------------
+#pragma unroll
+    for (int m = G / 2; m >= 1; m >>= 1) rmax = __vmaxs2(rmax, __shfl_xor_sync(0xffffffffu, rmax, m, G));
+    const uint32_t corner2 = __shfl_sync(0xffffffffu, Gp[K - 1], G - 1, G);
+    uint32_t okbits = __ballot_sync(0xffffffffu, ok);
+    const uint32_t submask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+    const bool all_ok = (okbits & submask) == submask;
+    if (t == 0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (pid[h] < 0) continue;
+            if (!all_ok) {
+                // a byte outside ACGT in either pair of the duo: let the byte-exact kernel redo it
+                generic_list[atomicAdd(generic_cursor, 1)] = pid[h];
+                continue;
+            }
+            const int32_t best = (int32_t)(int16_t)(rmax >> (16 * h)) - kc.goe;
+            const int32_t corner = (int32_t)(int16_t)(corner2 >> (16 * h)) - kc.goe;
+            // '\n' is the last symbol of both lines: it can only match at the corner cell
+            scores[pid[h]] = sq[h].both_nl ? max(best, corner + kc.match) : best;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// intra-task wavefront kernel (s32 DPX), one warp per pair, raw bytes
+// ------------------------------------------------------------------------------------------
+constexpr int WAVE_K = 8;                 // columns per lane
+constexpr int WAVE_W = 32 * WAVE_K;       // stripe width
+constexpr int WAVE_WARPS = 4;             // warps per CTA
+constexpr int WAVE_RING = 64;
+
+__global__ void __launch_bounds__(WAVE_WARPS * 32)
+sw_wave_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
+               const int32_t *__restrict__ len, const int32_t *__restrict__ list,
+               const int32_t *__restrict__ list_count, SwScoring sc, int32_t *__restrict__ scores,
+               int32_t *__restrict__ scratch, int64_t scratch_stride)
+{
+    __shared__ int32_t r_byte[WAVE_WARPS][WAVE_RING];
+    __shared__ int32_t r_g[WAVE_WARPS][WAVE_RING];
+    __shared__ int32_t r_e[WAVE_WARPS][WAVE_RING];
+
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int64_t warp = (int64_t)blockIdx.x * WAVE_WARPS + wib;
+    const int64_t n_warps = (int64_t)gridDim.x * WAVE_WARPS;
+    const int32_t goe = sc.gap_open + sc.gap_extend;
+    const int32_t ext = sc.gap_extend;
+    int32_t *bnd = scratch + warp * scratch_stride;   // [2 * rows] : (G, E) of the stripe's last column
+    const int32_t count = *list_count;
+
+    for (int64_t it = warp; it < count; it += n_warps) {
+        const int32_t p = list[it];
+        const uint8_t *x = seqs + off[2 * (int64_t)p];
+        const uint8_t *y = seqs + off[2 * (int64_t)p + 1];
+        int32_t lx = len[2 * (int64_t)p], ly = len[2 * (int64_t)p + 1];
+        // columns = shorter sequence (fewer stripes), rows = longer
+        const uint8_t *a = x, *b = y;
+        int32_t la = lx, lb = ly;
+        if (lx > ly) { a = y; la = ly; b = x; lb = lx; }
+
+        int32_t best = 0;
+        const int n_stripes = (la + WAVE_W - 1) / WAVE_W;
+        for (int st = 0; st < n_stripes; ++st) {
+            const int c0 = st * WAVE_W + lane * WAVE_K;
+            int32_t acol[WAVE_K], Gp[WAVE_K], F[WAVE_K];
+#pragma unroll
+            for (int j = 0; j < WAVE_K; ++j) {
+                acol[j] = (c0 + j < la) ? (int32_t)a[c0 + j] : 0x100;   // 0x100 never equals a byte
+                Gp[j] = goe;
+                F[j] = goe;
+            }
+            int32_t g_out = goe, e_out = goe, g_in_prev = goe;
+            const bool first = (st == 0), last = (st == n_stripes - 1);
+            const int S = lb + 31;
+            for (int s0 = 0; s0 < S; s0 += 32) {
+                __syncwarp();
+                {
+                    const int r = s0 + lane;
+                    int32_t bb = 0x200, gi = goe, ei = goe;
+                    if (r < lb) {
+                        bb = b[r];
+                        if (!first) { gi = __ldcg(bnd + 2 * r); ei = __ldcg(bnd + 2 * r + 1); }
+                    }
+                    r_byte[wib][r & (WAVE_RING - 1)] = bb;
+                    r_g[wib][r & (WAVE_RING - 1)] = gi;
+                    r_e[wib][r & (WAVE_RING - 1)] = ei;
+                }
+                __syncwarp();
+                const int send = min(32, S - s0);
+#pragma unroll 1
+                for (int u = 0; u < send; ++u) {
+                    const int s = s0 + u;
+                    const int slot = (s - lane) & (WAVE_RING - 1);
+                    const int32_t rb = (s - lane >= 0) ? r_byte[wib][slot] : 0x200;
+                    int32_t g_in = __shfl_up_sync(0xffffffffu, g_out, 1);
+                    int32_t e = __shfl_up_sync(0xffffffffu, e_out, 1);
+                    if (lane == 0) { g_in = r_g[wib][slot]; e = r_e[wib][slot]; }
+                    int32_t gdiag = g_in_prev;
+                    g_in_prev = g_in;
+                    int32_t gleft = g_in;
+#pragma unroll
+                    for (int j = 0; j < WAVE_K; ++j) {
+                        const int32_t d = gdiag + ((acol[j] == rb) ? sc.match - goe : sc.mismatch - goe);
+                        e = __viaddmax_s32(e, ext, gleft);
+                        F[j] = __viaddmax_s32(F[j], ext, Gp[j]);
+                        const int32_t hcell = __vimax3_s32_relu(e, F[j], d);
+                        gdiag = Gp[j];
+                        gleft = hcell + goe;
+                        Gp[j] = gleft;
+                        best = max(best, hcell);
+                    }
+                    g_out = gleft;
+                    e_out = e;
+                    const int r = s - 31;
+                    if (!last && lane == 31 && r >= 0 && r < lb) {
+                        bnd[2 * r] = g_out;
+                        bnd[2 * r + 1] = e_out;
+                    }
+                }
+            }
+            __syncwarp();
+            __threadfence_block();
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, m));
+        if (lane == 0) scores[p] = best;
+    }
+}
+
+template <int C>
+int launch_duo_class(const uint8_t *d_seqs, const int64_t *d_off, const int32_t *d_len,
+                     const int32_t *order, int64_t n_pairs, int32_t count, const DuoConst &kc,
+                     int32_t *d_scores, int32_t *counters, cudaStream_t st)
+{
+    constexpr int G = duo_class(C).g, K = duo_class(C).k;
+    constexpr int SUBS = DUO_THREADS / G;
+    const int duos = (count + 1) / 2;
+    const int blocks = (duos + SUBS - 1) / SUBS;
+    if (blocks == 0) return AGX_OK;
+    sw_duo_kernel<G, K><<<blocks, DUO_THREADS, 0, st>>>(
+        d_seqs, d_off, d_len, order + (int64_t)C * n_pairs, count, kc, d_scores,
+        const_cast<int32_t *>(order) + (int64_t)GENERIC * n_pairs, counters + GENERIC);
+    count_launch();
+    AGX_CUDA(cudaGetLastError());
+    return AGX_OK;
+}
+
+template <int C>
+int launch_all_duo(const uint8_t *d_seqs, const int64_t *d_off, const int32_t *d_len,
+                   const int32_t *order, int64_t n_pairs, const int32_t *counts, const DuoConst &kc,
+                   int32_t *d_scores, int32_t *counters, cudaStream_t st)
+{
+    if constexpr (C < SW_N_DUO_CLASSES) {
+        int rc = launch_duo_class<C>(d_seqs, d_off, d_len, order, n_pairs, counts[C], kc, d_scores,
+                                     counters, st);
+        if (rc != AGX_OK) return rc;
+        return launch_all_duo<C + 1>(d_seqs, d_off, d_len, order, n_pairs, counts, kc, d_scores,
+                                     counters, st);
+    } else {
+        return AGX_OK;
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// host side of the SW path
+// ------------------------------------------------------------------------------------------
+int sw_workspace_reserve(SwWorkspace &ws, int64_t n_pairs)
+{
+    if (!ws.counters) {
+        AGX_CUDA(cudaMalloc(&ws.counters, CNT_WORDS * sizeof(int32_t)));
+        AGX_CUDA(cudaMallocHost(&ws.h_counters, CNT_WORDS * sizeof(int32_t)));
+    }
+    if (n_pairs > ws.cap_pairs) {
+        if (ws.order) cudaFree(ws.order);
+        ws.order = nullptr;
+        ws.cap_pairs = 0;
+        AGX_CUDA(cudaMalloc(&ws.order, (size_t)n_pairs * SW_N_CLASSES * sizeof(int32_t)));
+        ws.cap_pairs = n_pairs;
+    }
+    return AGX_OK;
+}
+
+void sw_workspace_free(SwWorkspace &ws)
+{
+    if (ws.order) cudaFree(ws.order);
+    if (ws.counters) cudaFree(ws.counters);
+    if (ws.wave_scratch) cudaFree(ws.wave_scratch);
+    if (ws.h_counters) cudaFreeHost(ws.h_counters);
+    ws.prof_duo.destroy(); ws.prof_wave.destroy(); ws.prof_classify.destroy();
+    ws = SwWorkspace();
+}
+
+int sw_run_device(SwWorkspace &ws, const uint8_t *d_seqs, const int64_t *d_off, const int32_t *d_len,
+                  int64_t n_pairs, SwScoring sc, int32_t *d_scores, cudaStream_t st)
+{
+    if (n_pairs == 0) return AGX_OK;
+    if (n_pairs > (int64_t)1 << 30) return fail(AGX_ERANGE, "sw: more than 2^30 pairs in one call");
+    if (!(sc.match > 0 && sc.mismatch < 0 && sc.gap_open <= 0 && sc.gap_extend < 0))
+        return fail(AGX_ERANGE, "sw: scoring must satisfy match > 0 > mismatch, gap_open <= 0, gap_extend < 0");
+    int rc = sw_workspace_reserve(ws, n_pairs);
+    if (rc != AGX_OK) return rc;
+
+    const int32_t goe = sc.gap_open + sc.gap_extend;
+    // s16x2 path: substitution bytes must fit a signed byte and the best score a signed 16-bit half
+    const bool s16_ok = (sc.match - goe) <= 127 && (sc.mismatch - goe) >= -128 && goe >= -1024 &&
+                        sc.match <= 30;
+    const int32_t s16_max_short = s16_ok ? min(DUO_MAX_CAP, 32000 / sc.match) : 0;
+
+    AGX_CUDA(cudaMemsetAsync(ws.counters, 0, CNT_WORDS * sizeof(int32_t), st));
+    const int cblocks = (int)((n_pairs + 255) / 256);
+    ws.prof_classify.begin(st);
+    sw_classify_kernel<<<cblocks, 256, 0, st>>>(d_seqs, d_off, d_len, n_pairs, s16_max_short,
+                                                sc.match, ws.order, ws.counters, d_scores);
+    count_launch();
+    ws.prof_classify.end(st);
+    AGX_CUDA(cudaGetLastError());
+    AGX_CUDA(cudaMemcpyAsync(ws.h_counters, ws.counters, CNT_WORDS * sizeof(int32_t),
+                             cudaMemcpyDeviceToHost, st));
+    AGX_CUDA(cudaStreamSynchronize(st));
+
+    int32_t counts[SW_N_CLASSES];
+    int64_t n_duo = 0;
+    for (int c = 0; c < SW_N_CLASSES; ++c) counts[c] = ws.h_counters[c];
+    for (int c = 0; c < SW_N_DUO_CLASSES; ++c) n_duo += counts[c];
+    const int32_t max_len = ws.h_counters[CNT_MAXLEN];
+
+    DuoConst kc;
+    kc.goe = goe;
+    kc.match = sc.match;
+    kc.goe2 = ((uint32_t)(uint16_t)(int16_t)goe) * 0x00010001u;
+    kc.ext2 = ((uint32_t)(uint16_t)(int16_t)sc.gap_extend) * 0x00010001u;
+    const uint32_t xb = (uint32_t)(uint8_t)(int8_t)(sc.mismatch - goe);
+    const uint32_t mb = (uint32_t)(uint8_t)(int8_t)(sc.match - goe);
+    kc.xb4 = xb * 0x01010101u;
+    kc.mxor = xb ^ mb;
+
+    ws.prof_duo.begin(st);
+    rc = launch_all_duo<0>(d_seqs, d_off, d_len, ws.order, n_pairs, counts, kc, d_scores,
+                           ws.counters, st);
+    ws.prof_duo.end(st);
+    if (rc != AGX_OK) return rc;
+
+    // generic list = pairs classified generic up front + pairs the duo kernels bounced (non-ACGT)
+    const int64_t generic_upper = (int64_t)counts[GENERIC] + n_duo;
+    if (generic_upper > 0 && (counts[GENERIC] > 0 || n_duo > 0)) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int64_t want_warps = generic_upper;
+        const int64_t max_warps = (int64_t)sms * 16;
+        if (want_warps > max_warps) want_warps = max_warps;
+        const int64_t stride = 2 * (int64_t)max_len + 64;
+        // keep the boundary scratch under 2 GiB: fewer (persistent) warps when rows are very long
+        const int64_t fit = ((int64_t)1 << 29) / stride;
+        if (want_warps > fit) want_warps = fit > WAVE_WARPS ? fit : WAVE_WARPS;
+        const int blocks = (int)((want_warps + WAVE_WARPS - 1) / WAVE_WARPS);
+        const int64_t need = stride * blocks * WAVE_WARPS;
+        if (need > ws.cap_wave) {
+            if (ws.wave_scratch) cudaFree(ws.wave_scratch);
+            ws.wave_scratch = nullptr;
+            ws.cap_wave = 0;
+            AGX_CUDA(cudaMalloc(&ws.wave_scratch, (size_t)need * sizeof(int32_t)));
+            ws.cap_wave = need;
+        }
+        ws.prof_wave.begin(st);
+        sw_wave_kernel<<<blocks, WAVE_WARPS * 32, 0, st>>>(
+            d_seqs, d_off, d_len, ws.order + (int64_t)GENERIC * n_pairs, ws.counters + GENERIC, sc,
+            d_scores, ws.wave_scratch, stride);
+        ws.prof_wave.end(st);
+        count_launch();
+        AGX_CUDA(cudaGetLastError());
+    }
+    return AGX_OK;
+}
+
+}  // namespace agx

@@ -1,0 +1,135 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so) and runners for the compiled reference
+programs (oracle/_ref/*).
+
+TEST INFRASTRUCTURE: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module.  Nothing under accelerating-genomics_b200/ or
+drivers/ does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import tempfile
+from pathlib import Path
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIB = HERE / "liboracle.so"
+REF = HERE / "_ref"
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB.exists():
+            subprocess.run(["make", "-C", str(HERE), "liboracle.so"], check=True, capture_output=True)
+        l = C.CDLL(str(LIB))
+        l.oracle_sw_score.restype = C.c_int32
+        l.oracle_sw_score.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32] + [C.c_int32] * 4 + \
+            [C.POINTER(C.c_int32)]
+        l.oracle_sw_file.restype = C.c_int64
+        l.oracle_sw_file.argtypes = [C.c_char_p, C.c_int32, C.c_void_p, C.c_int64, C.POINTER(C.c_int32)]
+        l.oracle_pairhmm_prob.restype = C.c_double
+        l.oracle_pairhmm_prob.argtypes = [C.c_uint8]
+        l.oracle_pairhmm_forward.restype = C.c_double
+        l.oracle_pairhmm_forward.argtypes = [C.c_char_p] * 5 + [C.c_int32, C.c_char_p, C.c_int32, C.c_int32]
+        l.oracle_pairhmm_file.restype = C.c_int64
+        l.oracle_pairhmm_file.argtypes = [C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int32)]
+        _lib = l
+    return _lib
+
+
+def sw_score(a: bytes, b: bytes, scoring=(1, -1, -3, -1), want_corner: bool = False):
+    corner = C.c_int32(0)
+    s = lib().oracle_sw_score(a, len(a), b, len(b), *scoring, C.byref(corner))
+    return (int(s), int(corner.value)) if want_corner else int(s)
+
+
+def sw_scores_flat(buf: np.ndarray, off: np.ndarray, ln: np.ndarray, scoring=(1, -1, -3, -1)) -> np.ndarray:
+    data = np.ascontiguousarray(buf, dtype=np.uint8).tobytes()
+    n = off.size // 2
+    out = np.empty(n, dtype=np.int32)
+    for p in range(n):
+        a = data[off[2 * p]:off[2 * p] + ln[2 * p]]
+        b = data[off[2 * p + 1]:off[2 * p + 1] + ln[2 * p + 1]]
+        out[p] = sw_score(a, b, scoring)
+    return out
+
+
+def sw_file(path: str, line_buf: int = 1000, cap: int = 1 << 22):
+    out = np.empty(cap, dtype=np.int32)
+    header = C.c_int32(0)
+    n = lib().oracle_sw_file(str(path).encode(), line_buf, out.ctypes.data, cap, C.byref(header))
+    if n < 0:
+        raise OSError(f"oracle_sw_file failed on {path}")
+    return out[:min(n, cap)].copy(), int(header.value)
+
+
+def pairhmm_forward(read, hap: bytes, gatk: bool = False) -> float:
+    bases, q, qi, qd, qg = read
+    return float(lib().oracle_pairhmm_forward(bases, q, qi, qd, qg, len(bases), hap, len(hap), 1 if gatk else 0))
+
+
+def pairhmm_file(path: str, cap: int = 1 << 22):
+    out = np.empty(cap, dtype=np.float64)
+    nb = C.c_int32(0)
+    n = lib().oracle_pairhmm_file(str(path).encode(), out.ctypes.data, cap, C.byref(nb))
+    if n < 0:
+        raise OSError(f"oracle_pairhmm_file failed on {path}")
+    return out[:min(n, cap)].copy(), int(nb.value)
+
+
+def pairhmm_flat(inp, gatk: bool = False, limit: Optional[int] = None) -> np.ndarray:
+    """Oracle over an accelerating_genomics_b200.formats.HmmInput (read-major inside each batch)."""
+    data = inp.buf.tobytes()
+    out: List[float] = []
+    for b in range(inp.n_batches):
+        r0, r1 = int(inp.batch_read_start[b]), int(inp.batch_read_start[b + 1])
+        h0, h1 = int(inp.batch_hap_start[b]), int(inp.batch_hap_start[b + 1])
+        haps = [data[inp.hap_off[h]:inp.hap_off[h] + inp.hap_len[h]] for h in range(h0, h1)]
+        for r in range(r0, r1):
+            L = int(inp.read_len[r])
+            fields = tuple(data[int(o):int(o) + L] for o in inp.read_field_off[r])
+            for hp in haps:
+                out.append(pairhmm_forward(fields, hp, gatk))
+                if limit is not None and len(out) >= limit:
+                    return np.asarray(out)
+    return np.asarray(out)
+
+
+# ------------------------------------------------------------------ compiled reference programs
+def ref_available(name: str = "sw_antidiag") -> bool:
+    return (REF / name).exists()
+
+
+def run_ref_sw(path: str, long_lines: bool = False, timeout: float = 600.0):
+    """Run the compiled reference SW program; returns (scores, header, stdout)."""
+    exe = REF / ("sw_antidiag_long" if long_lines else "sw_antidiag")
+    cmd = f"ulimit -s unlimited 2>/dev/null; exec {exe} {path}" if long_lines else f"exec {exe} {path}"
+    r = subprocess.run(["bash", "-c", cmd], capture_output=True, timeout=timeout)
+    text = r.stdout.decode(errors="replace")
+    scores = [int(l.split()[1]) for l in text.splitlines() if l.startswith("Score:")]
+    header = None
+    for l in text.splitlines():
+        if l.startswith("line_num:"):
+            header = int(l.split()[1])
+    return np.asarray(scores, dtype=np.int32), header, text
+
+
+def run_ref_pairhmm(path: str, which: str = "pairhmm_matrix", timeout: float = 600.0):
+    """Run a compiled reference PairHMM program; returns (values parsed from its %f output, text)."""
+    exe = REF / which
+    with tempfile.NamedTemporaryFile(suffix=".out", delete=False) as t:
+        outp = t.name
+    try:
+        subprocess.run([str(exe), str(path), outp], capture_output=True, timeout=timeout, check=True)
+        text = Path(outp).read_text()
+    finally:
+        os.unlink(outp)
+    vals = np.asarray([float(x) for x in text.split()], dtype=np.float64)
+    return vals, text

@@ -1,0 +1,76 @@
+"""The C drivers (drivers/smithWaterman.c, drivers/pairHMM.c) are drop-ins for the reference
+programs: same command line, same stdout / output-file text on the recorded inputs."""
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, read_golden
+
+pytestmark = pytest.mark.gpu
+BIN = ROOT / "drivers" / "bin"
+
+
+def _strip_elapsed(text):
+    return "".join(l + "\n" for l in text.splitlines() if not l.startswith("elapsed"))
+
+
+@pytest.mark.parametrize("name", ["sw_gen_header", "sw_ragged", "sw_short", "sw_150", "sw_no_trailing_nl",
+                                  "sw_alphabet", "sw_linebuf", "sw_dangling", "sw_header_small", "sw_1kbp"])
+def test_sw_driver_stdout_is_the_references(name):
+    r = subprocess.run([str(BIN / "smithWaterman"), str(GOLDEN / f"{name}.in")], capture_output=True, text=True,
+                       env=dict(os.environ, AGX_NUM_GPUS="1"))
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.splitlines()[-1].startswith("elapsed ")
+    assert _strip_elapsed(r.stdout) == (GOLDEN / f"{name}.ref.out").read_text()
+
+
+def test_sw_driver_long_line_buffer():
+    r = subprocess.run([str(BIN / "smithWaterman"), str(GOLDEN / "sw_5kbp.in")], capture_output=True, text=True,
+                       env=dict(os.environ, AGX_NUM_GPUS="1", AGX_SW_LINE_BUF="4200000"))
+    assert r.returncode == 0, r.stderr
+    assert _strip_elapsed(r.stdout) == (GOLDEN / "sw_5kbp.ref_long.out").read_text()
+
+
+def test_sw_driver_usage_and_errors(tmp_path):
+    r = subprocess.run([str(BIN / "smithWaterman")], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stderr.startswith("Usage: ") and "<file_path>" in r.stderr
+    r = subprocess.run([str(BIN / "smithWaterman"), str(tmp_path / "missing")], capture_output=True, text=True)
+    assert r.returncode == 1 and "Error opening file" in r.stderr
+    empty = tmp_path / "empty"
+    empty.write_bytes(b"")
+    r = subprocess.run([str(BIN / "smithWaterman"), str(empty)], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stdout == "file is empty"
+
+
+@pytest.mark.parametrize("name", ["pairhmm_test", "pairhmm_10s", "pairhmm_synth_small", "pairhmm_synth_long"])
+def test_pairhmm_driver_output(tmp_path, name):
+    inp = tmp_path / "in.txt"
+    inp.write_bytes(read_golden(f"{name}.in"))
+    ref_text = (GOLDEN / f"{name}.pairhmm_antidiag.out").read_text()
+    ref = np.array([float(x) for x in ref_text.split()])
+    # default (FP32 + rescue) path: within tolerance of the reference's printed values
+    out = tmp_path / "out.txt"
+    r = subprocess.run([str(BIN / "pairHMM"), str(inp), str(out)], capture_output=True, text=True,
+                       env=dict(os.environ, AGX_NUM_GPUS="1"))
+    assert r.returncode == 0, r.stderr
+    got = np.array([float(x) for x in out.read_text().split()])
+    assert got.shape == ref.shape
+    assert np.all(np.abs(got - ref) <= 1e-5 * np.abs(ref) + 1.5e-6)
+    lines = r.stdout.splitlines()
+    n_batches = sum(1 for l in lines if l.startswith("#batch:"))
+    assert lines[0] == "#batch: 1" and lines[-1] == f"#batch: {n_batches}"
+    assert [l for l in lines if not l.startswith("#")] == out.read_text().split()
+    # exact-order FP64 path: the output file is byte-identical to the reference's
+    out64 = tmp_path / "out64.txt"
+    r = subprocess.run([str(BIN / "pairHMM"), str(inp), str(out64)], capture_output=True, text=True,
+                       env=dict(os.environ, AGX_NUM_GPUS="1", AGX_PAIRHMM_FP64="1"))
+    assert r.returncode == 0, r.stderr
+    assert out64.read_text() == ref_text
+
+
+def test_pairhmm_driver_usage():
+    r = subprocess.run([str(BIN / "pairHMM"), "only-one"], capture_output=True, text=True)
+    assert r.returncode == 1 and "<input_file_r> <output_file>" in r.stderr

@@ -1,0 +1,85 @@
+"""Host-side format handling (accelerating-genomics_b200/formats.py, synth.py) against the oracle's
+file-level restatement and the recorded reference outputs.  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, read_golden, ref_scores
+
+
+@pytest.mark.parametrize("name", ["sw_gen_header", "sw_ragged", "sw_no_trailing_nl", "sw_linebuf",
+                                  "sw_dangling", "sw_header_small", "sw_1kbp", "sw_alphabet"])
+def test_parse_sw_reproduces_reference_pairing(agx, oracle_mod, name):
+    data = (GOLDEN / f"{name}.in").read_bytes()
+    inp = agx.formats.parse_sw(data)
+    want = ref_scores(f"{name}.ref.out")
+    assert inp.n_pairs == len(want)
+    got = oracle_mod.sw_scores_flat(inp.buf, inp.off, inp.len)
+    assert got.tolist() == want
+    assert f"line_num: {inp.header}" in (GOLDEN / f"{name}.ref.out").read_text()
+
+
+def test_parse_sw_quirks(agx):
+    F = agx.formats
+    # SW-Q2: header counts lines; generator.py writes the number of alignments -> half the pairs
+    inp = F.parse_sw(b"2\nAAAA\nCCCC\nGGGG\nTTTT\n")
+    assert inp.n_pairs == 1 and inp.header == 2
+    # SW-Q1: the newline stays in the sequence
+    assert inp.len.tolist() == [5, 5]
+    # SW-Q3: 1000-byte buffer splits a 1000-character line into 999 + ("X\n")
+    long = b"A" * 1000
+    inp = F.parse_sw(b"2\n" + long + b"\n" + b"C" * 10 + b"\n")
+    assert inp.len.tolist() == [999, 2]
+    inp = F.parse_sw(b"2\n" + long + b"\n" + b"C" * 10 + b"\n", line_buf=10000)
+    assert inp.len.tolist() == [1001, 11]
+    # EOF in the middle of a pair: the dangling line is reported, not scored
+    inp = F.parse_sw(b"4\nAA\nCC\nGG\n")
+    assert inp.n_pairs == 1 and inp.dangling == b"GG\n"
+    # header larger than the file / zero / garbage
+    assert F.parse_sw(b"100\nAA\nCC\n").n_pairs == 1
+    assert F.parse_sw(b"0\nAA\nCC\n").n_pairs == 0
+    assert F.parse_sw(b"x\nAA\nCC\n").n_pairs == 0
+    with pytest.raises(ValueError):
+        F.parse_sw(b"")
+
+
+def test_write_sw_roundtrip(agx):
+    F = agx.formats
+    pairs = [(b"ACGT", b"AGGT"), (b"T", b"TT")]
+    inp = F.parse_sw(F.write_sw(pairs))
+    assert inp.n_pairs == 2
+    seqs = [inp.buf[o:o + l].tobytes() for o, l in zip(inp.off, inp.len)]
+    assert seqs == [b"ACGT\n", b"AGGT\n", b"T\n", b"TT\n"]
+
+
+@pytest.mark.parametrize("name", ["pairhmm_test", "pairhmm_10s", "pairhmm_synth_small", "pairhmm_synth_long"])
+def test_parse_pairhmm_against_oracle(agx, oracle_mod, tmp_path, name):
+    data = read_golden(f"{name}.in")
+    inp = agx.formats.parse_pairhmm(data)
+    ref = np.array([float(x) for x in (GOLDEN / f"{name}.pairhmm_matrix.out").read_text().split()])
+    assert inp.n_pairs == len(ref)
+    limit = 200
+    got = oracle_mod.pairhmm_flat(inp, limit=limit)
+    assert np.max(np.abs(got - ref[:len(got)])) <= 1e-6
+
+
+def test_parse_pairhmm_shapes(agx):
+    inp = agx.formats.parse_pairhmm(read_golden("pairhmm_10s.in"))
+    assert inp.n_batches == 7 and inp.n_pairs == 3550 and inp.cells() == 62380634
+    one = agx.formats.parse_pairhmm(read_golden("pairhmm_test.in"))
+    assert one.n_batches == 1 and one.read_len.tolist() == [41] and one.hap_len.tolist() == [41]
+
+
+def test_synth_matches_its_own_index(agx):
+    S, F = agx.synth, agx.formats
+    hm = S.pairhmm_batches(3, 7, 2, seed=4, read_len=(10, 40), hap_len=(30, 60))
+    re = F.parse_pairhmm(bytes(hm.buf))
+    for a, b in ((hm.read_field_off, re.read_field_off), (hm.read_len, re.read_len), (hm.hap_off, re.hap_off),
+                 (hm.hap_len, re.hap_len), (hm.batch_read_start, re.batch_read_start),
+                 (hm.batch_hap_start, re.batch_hap_start)):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    sw = S.sw_uniform_pairs(33, 150, seed=2)
+    re = F.parse_sw(bytes(sw.buf))
+    assert np.array_equal(sw.off, re.off) and np.array_equal(sw.len, re.len) and re.header == 66
+    assert set(np.unique(sw.buf[sw.off[0]:sw.off[0] + 150]).tolist()) <= set(b"ACGT")
+    # seeded: same seed, same bytes
+    assert np.array_equal(S.sw_uniform_pairs(33, 150, seed=2).buf, sw.buf)

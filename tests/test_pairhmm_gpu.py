@@ -1,0 +1,146 @@
+"""PairHMM parity on the GPU, through the C ABI, against the recorded reference outputs and the CPU
+oracle.  Tolerance (BASELINE.json north_star): |gpu - ref| <= 1e-5 * |ref| on the log10 likelihood."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, read_golden
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5          # north_star: relative tolerance on log10 likelihoods
+PRINT_EPS = 5.1e-7      # the reference prints %f: its recorded outputs carry +-5e-7 rounding
+
+
+def _run_flat(gpu_lib, inp):
+    return gpu_lib.pairhmm_forward_flat(inp.buf, inp.read_field_off, inp.read_len, inp.hap_off, inp.hap_len,
+                                        inp.batch_read_start, inp.batch_hap_start)
+
+
+def _rel_err(got, want):
+    return np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-300))
+
+
+GOLDENS = ["pairhmm_test", "pairhmm_10s", "pairhmm_synth_small", "pairhmm_synth_cfg4", "pairhmm_synth_long",
+           "pairhmm_synth_tall"]
+
+
+@pytest.mark.parametrize("name", GOLDENS)
+def test_golden_vs_reference_output(agx, gpu_lib, name):
+    inp = agx.formats.parse_pairhmm(read_golden(f"{name}.in"))
+    got = _run_flat(gpu_lib, inp)
+    ref = np.array([float(x) for x in (GOLDEN / f"{name}.pairhmm_antidiag.out").read_text().split()])
+    assert got.shape == ref.shape and np.all(np.isfinite(got))
+    assert np.all(np.abs(got - ref) <= REL_TOL * np.abs(ref) + PRINT_EPS)
+
+
+@pytest.mark.parametrize("name", GOLDENS)
+def test_golden_vs_oracle_double(agx, gpu_lib, oracle_mod, name):
+    inp = agx.formats.parse_pairhmm(read_golden(f"{name}.in"))
+    got = _run_flat(gpu_lib, inp)
+    want = oracle_mod.pairhmm_flat(inp)
+    assert _rel_err(got, want) <= REL_TOL
+
+
+def test_committed_golden_value(agx, gpu_lib):
+    inp = agx.formats.parse_pairhmm(read_golden("pairhmm_test.in"))
+    got = _run_flat(gpu_lib, inp)
+    assert "%f" % got[0] == "-4.485565"     # pairHMM/test_set/test.out
+
+
+def test_fp64_kernel_keeps_reference_operation_order(agx, gpu_lib, oracle_mod):
+    inp = agx.formats.parse_pairhmm(read_golden("pairhmm_10s.in"))
+    gpu_lib.set_pairhmm_force_fp64(True)
+    try:
+        got = _run_flat(gpu_lib, inp)
+    finally:
+        gpu_lib.set_pairhmm_force_fp64(False)
+    want = oracle_mod.pairhmm_flat(inp)
+    assert _rel_err(got, want) <= 1e-13
+    ref_text = (GOLDEN / "pairhmm_10s.pairhmm_antidiag.out").read_text().split()
+    assert ["%f" % v for v in got] == ref_text
+
+
+def test_pointer_array_entry_point(gpu_lib, oracle_mod):
+    reads = [(b"ACGTACGTAC", b"IIIIIIIIII", b"IIIIIIIIII", b"IIIIIIIIII", b"++++++++++"),
+             (b"ACGTNCGTAC", b"5555555555", b"IIIIDIIIII", b"HHHHCHHHHH", b"++++++++++"),
+             (b"T", b"#", b"I", b"I", b"+")]
+    haps = [b"ACGTACGTAC", b"TTACGTACGTACGG", b"ACGTANGTAC", b"G"]
+    got = gpu_lib.pairhmm_forward_batch(reads, haps)
+    assert got.shape == (3, 4)
+    for r, rd in enumerate(reads):
+        for h, hp in enumerate(haps):
+            want = oracle_mod.pairhmm_forward(rd, hp)
+            assert abs(got[r, h] - want) <= REL_TOL * abs(want)
+
+
+def test_unrelated_pairs_take_the_fp64_rescue(agx, gpu_lib, oracle_mod):
+    # uniform random reads against unrelated haplotypes: likelihoods far below FP32 range
+    inp = agx.synth.pairhmm_batches(2, 16, 3, seed=21, unrelated_frac=1.0, read_len=(150, 250))
+    want = oracle_mod.pairhmm_flat(inp)
+    assert want.min() < -70
+    got = _run_flat(gpu_lib, inp)
+    assert np.all(np.isfinite(got))
+    assert _rel_err(got, want) <= REL_TOL
+
+
+def test_extreme_qualities(gpu_lib, oracle_mod):
+    # Phred 0 ('!') through 93 ('~') in every quality track, N in read and haplotype
+    rng = np.random.default_rng(8)
+    L = 120
+    bases = bytes(np.frombuffer(b"ACGTN", np.uint8)[rng.integers(0, 5, size=L)])
+    hap = bytes(np.frombuffer(b"ACGTN", np.uint8)[rng.integers(0, 5, size=200)])
+    reads = []
+    for _ in range(12):
+        q = bytes(rng.integers(33, 127, size=L).astype(np.uint8))
+        qi = bytes(rng.integers(43, 127, size=L).astype(np.uint8))
+        qd = bytes(rng.integers(43, 127, size=L).astype(np.uint8))
+        qg = bytes(rng.integers(36, 127, size=L).astype(np.uint8))
+        reads.append((bases, q, qi, qd, qg))
+    got = gpu_lib.pairhmm_forward_batch(reads, [hap, hap[:50]])
+    for r, rd in enumerate(reads):
+        for h, hp in enumerate([hap, hap[:50]]):
+            want = oracle_mod.pairhmm_forward(rd, hp)
+            assert np.isfinite(got[r, h]) == np.isfinite(want)
+            if np.isfinite(want):
+                assert abs(got[r, h] - want) <= REL_TOL * abs(want)
+
+
+def test_gatk_mode_is_separate(agx, gpu_lib, oracle_mod):
+    inp = agx.synth.pairhmm_batches(2, 10, 3, seed=5)
+    gpu_lib.set_pairhmm_gatk_mode(True)
+    try:
+        got = _run_flat(gpu_lib, inp)
+    finally:
+        gpu_lib.set_pairhmm_gatk_mode(False)
+    assert _rel_err(got, oracle_mod.pairhmm_flat(inp, gatk=True)) <= REL_TOL
+    assert _rel_err(_run_flat(gpu_lib, inp), oracle_mod.pairhmm_flat(inp)) <= REL_TOL
+
+
+def test_argument_ranges(gpu_lib):
+    with pytest.raises(gpu_lib.AgxError) as e:
+        gpu_lib.pairhmm_forward_batch([(b"", b"", b"", b"", b"")], [b"ACGT"])
+    assert e.value.code == -5
+
+
+def test_device_resident_entry_point(agx, gpu_lib, oracle_mod):
+    import torch
+    inp = agx.synth.pairhmm_batches(6, 40, 5, seed=12)
+    dev = torch.device("cuda:0")
+    nb = inp.n_batches
+    nh_b = np.diff(inp.batch_hap_start)
+    read_batch = np.repeat(np.arange(nb, dtype=np.int32), np.diff(inp.batch_read_start))
+    out_off = np.concatenate(([0], np.cumsum(nh_b[read_batch])))[:-1].astype(np.int64)
+    n_pairs = inp.n_pairs
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_buf, d_rfo, d_rl = t(inp.buf.copy()), t(inp.read_field_off.reshape(-1)), t(inp.read_len)
+    d_rb, d_roo, d_ho, d_hl, d_bhs = t(read_batch), t(out_off), t(inp.hap_off), t(inp.hap_len), t(inp.batch_hap_start)
+    d_out = torch.zeros(n_pairs, dtype=torch.float64, device=dev)
+    gpu_lib.pairhmm_forward_device(0, d_buf.data_ptr(), d_buf.numel(), d_rfo.data_ptr(), d_rl.data_ptr(),
+                                   d_rb.data_ptr(), d_roo.data_ptr(), inp.read_len.size, d_ho.data_ptr(),
+                                   d_hl.data_ptr(), inp.hap_len.size, d_bhs.data_ptr(), nb, n_pairs,
+                                   d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy()
+    assert np.allclose(got, _run_flat(gpu_lib, inp), rtol=0, atol=0)
+    want = oracle_mod.pairhmm_flat(inp, limit=300)
+    assert _rel_err(got[:300], want) <= REL_TOL

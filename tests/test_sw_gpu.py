@@ -1,0 +1,164 @@
+"""Smith-Waterman parity on the GPU, through the C ABI (libagx.so), against the recorded reference
+outputs and the CPU oracle.  Bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ref_scores
+
+pytestmark = pytest.mark.gpu
+
+SW_FILES = ["sw_gen_header", "sw_ragged", "sw_short", "sw_150", "sw_no_trailing_nl", "sw_alphabet",
+            "sw_two_letter", "sw_linebuf", "sw_dangling", "sw_header_small", "sw_mid", "sw_1kbp"]
+
+
+@pytest.mark.parametrize("name", SW_FILES)
+def test_golden_files_bit_exact(agx, gpu_lib, name):
+    inp = agx.formats.parse_sw((GOLDEN / f"{name}.in").read_bytes())
+    got = gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len)
+    assert got.tolist() == ref_scores(f"{name}.ref.out")
+
+
+@pytest.mark.parametrize("name", ["sw_1kbp", "sw_5kbp"])
+def test_golden_long_lines(agx, gpu_lib, name):
+    # BASELINE config 1 (1 kbp x 1 kbp) with un-split lines: the MAX_LINE_LENGTH-raised reference
+    inp = agx.formats.parse_sw((GOLDEN / f"{name}.in").read_bytes(), line_buf=4200000)
+    got = gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len)
+    assert got.tolist() == ref_scores(f"{name}.ref_long.out")
+
+
+def _random_pairs(rng, n, lo, hi, alphabet=b"ACGT", nl=True, related=0.5):
+    alpha = np.frombuffer(alphabet, np.uint8)
+    a, b = [], []
+    for _ in range(n):
+        la, lb = rng.integers(lo, hi + 1, size=2)
+        x = alpha[rng.integers(0, alpha.size, size=la)]
+        if rng.random() < related:
+            y = x.copy()
+            m = rng.random(la) < 0.1
+            y[m] = alpha[rng.integers(0, alpha.size, size=int(m.sum()))]
+            y = y[rng.random(la) > 0.04][:lb] if la else y
+        else:
+            y = alpha[rng.integers(0, alpha.size, size=lb)]
+        tail = b"\n" if nl else b""
+        a.append(x.tobytes() + tail)
+        b.append(y.tobytes() + tail)
+    return a, b
+
+
+def _check(gpu_lib, oracle_mod, a, b, scoring=(1, -1, -3, -1)):
+    got = gpu_lib.sw_score_batch(a, b, scoring)
+    want = [oracle_mod.sw_score(x, y, scoring) for x, y in zip(a, b)]
+    bad = [i for i, (g, w) in enumerate(zip(got.tolist(), want)) if g != w]
+    assert not bad, f"{len(bad)} mismatches, first {bad[:5]}: got {got[bad[:5]]}, want {[want[i] for i in bad[:5]]}"
+
+
+def test_random_ragged_batch(gpu_lib, oracle_mod):
+    rng = np.random.default_rng(1)
+    a, b = _random_pairs(rng, 3000, 1, 300)
+    _check(gpu_lib, oracle_mod, a, b)
+
+
+def test_every_length_class_boundary(gpu_lib, oracle_mod):
+    # column capacities of the duo kernel: 32 64 96 128 152 192 256 384 512 768 1024, then generic
+    rng = np.random.default_rng(2)
+    a, b = [], []
+    for L in (1, 2, 31, 32, 33, 63, 64, 65, 96, 97, 128, 129, 150, 151, 152, 153, 192, 193, 256, 257, 384, 385,
+              512, 513, 768, 769, 1023, 1024, 1025, 1500):
+        for rows in (L, L + 1, 2 * L + 7, 40):
+            x, y = _random_pairs(rng, 1, L, L, related=1.0)
+            a.append(x[0])
+            yy = (y[0].rstrip(b"\n") * 3)[:rows] + b"\n"
+            b.append(yy)
+    _check(gpu_lib, oracle_mod, a, b)
+
+
+def test_long_rows_short_columns(gpu_lib, oracle_mod):
+    rng = np.random.default_rng(3)
+    alpha = np.frombuffer(b"ACGT", np.uint8)
+    a = [alpha[rng.integers(0, 4, size=n)].tobytes() + b"\n" for n in (20, 100, 150, 300)]
+    b = [alpha[rng.integers(0, 4, size=n)].tobytes() + b"\n" for n in (5000, 3000, 20000, 9000)]
+    # plant the short sequence inside the long one so the best score is large
+    b = [y[:1000] + x.rstrip(b"\n") + y[1000:] for x, y in zip(a, b)]
+    _check(gpu_lib, oracle_mod, a, b)
+
+
+@pytest.mark.parametrize("alphabet", [b"ACGTN", b"acgtACGT", b"AC", b"ACGT\r", b"ACGU*-"])
+def test_byte_exact_alphabets(gpu_lib, oracle_mod, alphabet):
+    rng = np.random.default_rng(4)
+    a, b = _random_pairs(rng, 300, 1, 200, alphabet=alphabet)
+    _check(gpu_lib, oracle_mod, a, b)
+
+
+def test_newline_combinations_and_empties(gpu_lib, oracle_mod):
+    a = [b"ACGT\n", b"AAAA\n", b"ACGT\n", b"ACGT", b"\n", b"\n", b"", b"ACGT\n", b"A", b"\n\n", b"AC\nGT\n"]
+    b = [b"ACGT\n", b"TTTT\n", b"ACGT", b"ACGT", b"\n", b"ACGT\n", b"ACGT\n", b"", b"A", b"\n", b"AC\nGT\n"]
+    _check(gpu_lib, oracle_mod, a, b)
+    got = gpu_lib.sw_score_batch(a, b)
+    assert got[:4].tolist() == [5, 1, 4, 4]       # SURVEY 8b probes
+
+
+def test_no_newline_batch(gpu_lib, oracle_mod):
+    rng = np.random.default_rng(5)
+    a, b = _random_pairs(rng, 500, 1, 180, nl=False)
+    _check(gpu_lib, oracle_mod, a, b)
+
+
+@pytest.mark.parametrize("scoring", [(2, -3, -5, -2), (1, -4, 0, -1), (5, -4, -10, -1), (3, -1, -200, -3)])
+def test_other_scoring_parameters(gpu_lib, oracle_mod, scoring):
+    rng = np.random.default_rng(6)
+    a, b = _random_pairs(rng, 400, 1, 220)
+    _check(gpu_lib, oracle_mod, a, b, scoring)
+
+
+def test_scoring_sign_convention_is_enforced(gpu_lib):
+    with pytest.raises(gpu_lib.AgxError) as e:
+        gpu_lib.sw_score_batch([b"ACGT"], [b"ACGT"], (1, 1, -3, -1))
+    assert e.value.code == -5
+
+
+def test_s16_overflow_is_routed_to_s32(gpu_lib, oracle_mod):
+    # match = 40: 1000 matching bases would overflow a signed 16-bit half
+    x = (b"ACGT" * 250) + b"\n"
+    _check(gpu_lib, oracle_mod, [x], [x], (40, -1, -3, -1))
+    assert gpu_lib.sw_score_batch([x], [x], (40, -1, -3, -1))[0] == 40 * 1001
+
+
+def test_device_resident_entry_point(agx, gpu_lib, oracle_mod):
+    import torch
+    inp = agx.synth.sw_uniform_pairs(4096, 150, seed=3)
+    dev = torch.device("cuda:0")
+    d_buf = torch.from_numpy(inp.buf.copy()).to(dev)
+    d_off = torch.from_numpy(inp.off).to(dev)
+    d_len = torch.from_numpy(inp.len).to(dev)
+    d_out = torch.full((inp.n_pairs,), -7, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    gpu_lib.sw_score_device(0, d_buf.data_ptr(), d_buf.numel(), d_off.data_ptr(), d_len.data_ptr(),
+                            inp.n_pairs, d_out.data_ptr(), st)
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy()
+    want = oracle_mod.sw_scores_flat(inp.buf, inp.off[:2 * 512], inp.len[:2 * 512])
+    assert got[:512].tolist() == want.tolist()
+    assert np.array_equal(got, gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len))
+
+
+def test_config3_shape_properties(agx, gpu_lib, oracle_mod):
+    """BASELINE config 3 shape (150 x 150), 200k pairs: size-independent properties + oracle sample."""
+    n = 200_000
+    inp = agx.synth.sw_uniform_pairs(n, 150, seed=9)
+    got = gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len)
+    assert got.min() >= 1 and got.max() <= 151
+    # symmetry: swapping a and b never changes the score
+    swap = np.arange(2 * n).reshape(n, 2)[:, ::-1].reshape(-1)
+    assert np.array_equal(gpu_lib.sw_score_flat(inp.buf, inp.off[swap], inp.len[swap]), got)
+    # a sequence against itself scores length + 1 (the newline symbol matches too)
+    self_off = np.repeat(inp.off[0::2], 2)
+    assert np.all(gpu_lib.sw_score_flat(inp.buf, self_off, inp.len) == 151)
+    # order independence: a permuted batch gives the permuted scores
+    perm = np.random.default_rng(0).permutation(n)
+    idx = np.stack([2 * perm, 2 * perm + 1], axis=1).reshape(-1)
+    assert np.array_equal(gpu_lib.sw_score_flat(inp.buf, inp.off[idx], inp.len[idx]), got[perm])
+    # oracle on a sample
+    pick = np.random.default_rng(1).choice(n, size=1500, replace=False)
+    idx = np.stack([2 * pick, 2 * pick + 1], axis=1).reshape(-1)
+    want = oracle_mod.sw_scores_flat(inp.buf, inp.off[idx], inp.len[idx])
+    assert got[pick].tolist() == want.tolist()
