@@ -28,16 +28,22 @@ enum Op {
     OP_VIADDMNMX_S16X2, OP_VIMNMX3_S16X2_RELU, OP_VIADD_16X2, OP_VIMNMX_S16X2, OP_PRMT,
     OP_VIADDMNMX_S32, OP_VIMNMX3_S32_RELU, OP_IADD3, OP_LOP3, OP_IMAD,
     OP_FFMA, OP_FMUL, OP_FADD, OP_FSEL,
-    OP_MIX_DPX_IMAD, OP_MIX_DPX_FFMA, OP_MIX_FFMA_SEL, OP_SWCELL, OP_SHFL, OP_COUNT
+    OP_MIX_DPX_IMAD, OP_MIX_DPX_FFMA, OP_MIX_FFMA_SEL, OP_SWCELL, OP_SHFL,
+    OP_MIX_VIADD_VIADDMNMX, OP_MIX_VIADDMNMX_VIMNMX3, OP_MIX_PRMT_VIADDMNMX, OP_MIX_VIADD_PRMT, OP_MIX_VIADD_IMAD,
+    OP_MIX_VIMNMX3_IMAD, OP_MIX_PRMT_IMAD, OP_MIX_LOP3_VIADDMNMX, OP_MIX_VIADD_FFMA, OP_SWCELL_FULL, OP_COUNT
 };
 static const char *op_name[OP_COUNT] = {
     "VIADDMNMX.S16x2", "VIMNMX3.S16x2.RELU", "VIADD.16x2", "VIMNMX.S16x2", "PRMT",
     "VIADDMNMX.S32", "VIMNMX3.S32.RELU", "IADD3", "LOP3", "IMAD",
     "FFMA", "FMUL", "FADD", "FSEL(ISETP+SEL)",
     "mix 1 VIADDMNMX.S16x2 : 1 IMAD", "mix 1 VIADDMNMX.S16x2 : 1 FFMA", "mix 3 FFMA : 1 ISETP+FSEL",
-    "SW s16x2 cell (6.5 alu ops, 2 cells)", "SHFL.UP"};
+    "SW s16x2 cell w/o PRMT (6 ops)", "SHFL.UP",
+    "mix VIADD.16x2 : VIADDMNMX.S16x2", "mix VIADDMNMX.S16x2 : VIMNMX3.S16x2", "mix PRMT : VIADDMNMX.S16x2",
+    "mix VIADD.16x2 : PRMT", "mix VIADD.16x2 : IMAD", "mix VIMNMX3.S16x2 : IMAD", "mix PRMT : IMAD",
+    "mix LOP3 : VIADDMNMX.S16x2", "mix VIADD.16x2 : FFMA", "SW s16x2 cell with PRMT (7 ops)"};
 // lane-ops counted per chain step
-static const double op_count[OP_COUNT] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 5, 6.5, 1};
+static const double op_count[OP_COUNT] = {1, 2, 1, 2, 1, 1, 2, 1, 1, 1, 1, 1, 1, 2, 2, 2, 5, 6, 1,
+                                              2, 2, 2, 2, 2, 2, 2, 2, 2, 7};
 
 __device__ __forceinline__ void ffma(uint32_t &x, uint32_t a, uint32_t b)
 {
@@ -93,6 +99,37 @@ __device__ __forceinline__ void step(uint32_t &x, uint32_t &y, uint32_t a, uint3
         y = __vadd2(h, b);
         x = __vmaxs2(x, y);   // stands in for the running max (0.5 / cell in the real kernel)
     } else if constexpr (OP == OP_SHFL) x = __shfl_up_sync(0xffffffffu, x, 1);
+    else if constexpr (OP == OP_MIX_VIADD_VIADDMNMX) { x = __vadd2(x, a); y = __viaddmax_s16x2(y, a, b); }
+    else if constexpr (OP == OP_MIX_VIADDMNMX_VIMNMX3) { x = __viaddmax_s16x2(x, a, b); y = __vimax3_s16x2(y, x, c); }
+    else if constexpr (OP == OP_MIX_PRMT_VIADDMNMX) {
+        asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(x) : "r"(a), "r"(b));
+        y = __viaddmax_s16x2(y, a, b);
+    } else if constexpr (OP == OP_MIX_VIADD_PRMT) {
+        x = __vadd2(x, a);
+        asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(y) : "r"(a), "r"(b));
+    } else if constexpr (OP == OP_MIX_VIADD_IMAD) {
+        x = __vadd2(x, a);
+        asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(y) : "r"(a), "r"(b));
+    } else if constexpr (OP == OP_MIX_VIMNMX3_IMAD) {
+        x = __vimax3_s16x2(x, y, c);
+        asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(y) : "r"(a), "r"(b));
+    } else if constexpr (OP == OP_MIX_PRMT_IMAD) {
+        asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(x) : "r"(a), "r"(b));
+        asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(y) : "r"(a), "r"(b));
+    } else if constexpr (OP == OP_MIX_LOP3_VIADDMNMX) {
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x) : "r"(a), "r"(b));
+        y = __viaddmax_s16x2(y, a, b);
+    } else if constexpr (OP == OP_MIX_VIADD_FFMA) { x = __vadd2(x, a); ffma(y, a, b); }
+    else if constexpr (OP == OP_SWCELL_FULL) {
+        uint32_t t;
+        asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(x), "r"(b), "r"(c));
+        const uint32_t d = __vadd2(y, t);
+        x = __viaddmax_s16x2(x, a, y);
+        const uint32_t f = __viaddmax_s16x2(y, a, d);
+        const uint32_t h = __vimax3_s16x2_relu(x, f, d);
+        y = __vadd2(h, b);
+        x = __vmaxs2(x, y);
+    }
 }
 
 template <int OP>
