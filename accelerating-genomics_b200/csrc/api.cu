@@ -353,7 +353,7 @@ int hmm_shard(DeviceCtx &c, const HmmHost &h, int64_t r0, int64_t r1, double *ou
     v.n_reads = nr;
     v.n_haps = nh;
     v.n_batches = nb;
-    rc = hmm_run_device(c.hmm, v, d_roo, n_out, g_gatk.load() != 0, g_force64.load() != 0, true,
+    rc = hmm_run_device(c.hmm, v, nbytes, d_roo, n_out, g_gatk.load() != 0, g_force64.load() != 0, true,
                         c.d_out.as<double>(), st);
     if (rc != AGX_OK) return rc;
     AGX_CUDA(cudaMemcpyAsync(out + o0, c.d_out.p, (size_t)n_out * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -598,8 +598,7 @@ int pairhmm_forward_batches_device(int32_t device, const uint8_t *d_buf, int64_t
                                    int64_t n_haps, const int64_t *d_batch_hap_start, int64_t n_batches,
                                    int64_t n_pairs, int32_t fp64_rescue, double *d_log10_out, void *stream)
 {
-    (void)buf_bytes;
-    if (n_reads < 0 || n_haps < 0 || n_batches < 0 || n_pairs < 0) return fail(AGX_EINVAL, "pairhmm: negative count");
+    if (n_reads < 0 || n_haps < 0 || n_batches < 0 || n_pairs < 0 || buf_bytes < 0) return fail(AGX_EINVAL, "pairhmm: negative count");
     if (n_reads == 0 || n_pairs == 0) return AGX_OK;
     if (!d_buf || !d_read_field_off || !d_read_len || !d_read_batch || !d_read_out_off || !d_hap_off ||
         !d_hap_len || !d_batch_hap_start || !d_log10_out)
@@ -620,7 +619,7 @@ int pairhmm_forward_batches_device(int32_t device, const uint8_t *d_buf, int64_t
     v.n_haps = n_haps;
     v.batch_hap_start = d_batch_hap_start;
     v.n_batches = n_batches;
-    return hmm_run_device(c->hmm, v, d_read_out_off, n_pairs, g_gatk.load() != 0, g_force64.load() != 0,
+    return hmm_run_device(c->hmm, v, buf_bytes, d_read_out_off, n_pairs, g_gatk.load() != 0, g_force64.load() != 0,
                           fp64_rescue != 0, d_log10_out, st);
 }
 

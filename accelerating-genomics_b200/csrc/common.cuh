@@ -77,6 +77,8 @@ struct HmmWorkspace {
     double *d_lut = nullptr;      // 256-entry Phred+33 -> probability table (host libm pow)
     void *scratch = nullptr;      // boundary rows of the striped kernel
     int64_t cap_scratch = 0;
+    void *prep = nullptr;         // haplotype codes + records + FP32 forward sums of the stream kernel
+    int64_t cap_prep = 0;
     ProfSpan prof_stream, prof_fp64, prof_classify;
 };
 
@@ -96,7 +98,7 @@ struct HmmBatchView {
 int hmm_workspace_reserve(HmmWorkspace &ws, int64_t n_reads, int64_t n_pairs);
 void hmm_workspace_free(HmmWorkspace &ws);
 // d_read_out_off[r] = index in d_out of (read r, first haplotype of its batch); n_pairs = total outputs.
-int hmm_run_device(HmmWorkspace &ws, const HmmBatchView &v, const int64_t *d_read_out_off,
+int hmm_run_device(HmmWorkspace &ws, const HmmBatchView &v, int64_t buf_bytes, const int64_t *d_read_out_off,
                    int64_t n_pairs, bool gatk_mode, bool force_fp64, bool rescue, double *d_out,
                    cudaStream_t st);
 

@@ -75,28 +75,84 @@ hmm_classify_kernel(const int32_t *__restrict__ read_len, int64_t n_reads,
 }
 
 // ------------------------------------------------------------------------------------------
+// haplotype preparation: symbol codes + per-haplotype record
+// ------------------------------------------------------------------------------------------
+// Haplotype symbols are recoded once per call to the byte offset of their row in the per-warp prior
+// table of the stream kernel: A 0, C 1, T 2, G 3, N 4 (the wildcard), anything else 5.  A haplotype
+// holding a symbol outside "ACGTN" cannot use the table (the reference compares raw bytes, so such a
+// symbol may still equal a read base); its record carries init = NaN, which makes every forward sum
+// NaN and sends its pairs to the byte-exact FP64 kernel.
+struct __align__(16) HapInfo {
+    int64_t off;     // offset of the haplotype in buf (and of its codes in the code buffer)
+    int32_t len;
+    float init;      // SCALE / len, or NaN
+};
+
+constexpr int HMM_NSYM = 6;
+
+__device__ __forceinline__ uint32_t hap_symbol(uint32_t ch)
+{
+    const uint32_t code = (ch >> 1) & 3u;                       // A 0, C 1, T 2, G 3
+    if (((0x47544341u >> (8 * code)) & 0xffu) == ch) return code;
+    return ch == 'N' ? 4u : 5u;
+}
+
+__global__ void __launch_bounds__(128)
+hmm_prep_haps_kernel(const uint8_t *__restrict__ buf, const int64_t *__restrict__ hap_off,
+                     const int32_t *__restrict__ hap_len, int64_t n_haps, uint8_t *__restrict__ codes,
+                     HapInfo *__restrict__ info)
+{
+    __shared__ int s_bad;
+    for (int64_t h = blockIdx.x; h < n_haps; h += gridDim.x) {
+        if (threadIdx.x == 0) s_bad = 0;
+        __syncthreads();
+        const int64_t off = hap_off[h];
+        const int32_t len = hap_len[h];
+        int bad = 0;
+        for (int32_t i = threadIdx.x; i < len; i += blockDim.x) {
+            const uint32_t sym = hap_symbol(buf[off + i]);
+            bad |= (sym == 5u);
+            codes[off + i] = (uint8_t)sym;
+        }
+        if (bad) s_bad = 1;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            HapInfo hi;
+            hi.off = off;
+            hi.len = len;
+            hi.init = s_bad ? nanf("") : SCALE_F / (float)len;
+            info[h] = hi;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // FP32 streaming kernel
 // ------------------------------------------------------------------------------------------
 template <int K>
 __global__ void __launch_bounds__(HMM_WARPS * 32)
 hmm_stream_kernel(HmmBatchView v, const int64_t *__restrict__ read_out_off,
                   const int32_t *__restrict__ order_cls, int32_t n_items,
-                  const double *__restrict__ lut_g, int gatk, double *__restrict__ out,
-                  int2 *__restrict__ rescue, int32_t *__restrict__ rescue_count)
+                  const double *__restrict__ lut_g, int gatk, const uint8_t *__restrict__ codes,
+                  const HapInfo *__restrict__ hapinfo, float *__restrict__ sums)
 {
+    constexpr int CH = (K + 3) / 4;                    // float4 chunks of priors per lane
     __shared__ double lut[256];
+    __shared__ float4 prior_tab[HMM_WARPS][HMM_NSYM][CH][32];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = lut_g[i];
     __syncthreads();
 
     const int t = threadIdx.x & 31;
-    const int item = blockIdx.x * HMM_WARPS + (threadIdx.x >> 5);
+    const int wib = threadIdx.x >> 5;
+    const int item = blockIdx.x * HMM_WARPS + wib;
     if (item >= n_items) return;
     const int32_t r = order_cls[item];
     const int32_t R = v.read_len[r];
     const int32_t bt = v.read_batch[r];
-    const int64_t h0 = v.batch_hap_start[bt], h1 = v.batch_hap_start[bt + 1];
+    const int32_t h0 = (int32_t)v.batch_hap_start[bt], h1 = (int32_t)v.batch_hap_start[bt + 1];
     if (h1 <= h0) return;
-    const int64_t obase = read_out_off[r];
+    float *my_sums = sums + read_out_off[r];
 
     // ---- prior / transition setup for this lane's K rows (rows bottom-aligned) ----------------
     const int pad = 32 * K - R;
@@ -106,34 +162,55 @@ hmm_stream_kernel(HmmBatchView v, const int64_t *__restrict__ read_out_off,
     const uint8_t *f_d = v.buf + v.read_field_off[5 * (int64_t)r + 3];
     const uint8_t *f_g = v.buf + v.read_field_off[5 * (int64_t)r + 4];
 
-    float pm[K], px[K], ca[K], cbx[K], cby[K], ccx[K], cg[K];
-    int32_t rb[K];
+    float ca[K], cbx[K], cby[K], ccx[K], cg[K];
+    {
+        float pm[CH * 4], px[CH * 4];
+        uint32_t rsym[CH * 4];
 #pragma unroll
-    for (int jj = 0; jj < K; ++jj) {
-        const int i = t * K + jj - pad;      // 0-based read position of this row
-        if (i < 0) {
-            // padding rows reproduce row 0: M = X = 0 and Y stays at its initial value
-            pm[jj] = px[jj] = 0.f; ca[jj] = cbx[jj] = cby[jj] = ccx[jj] = 0.f; cg[jj] = 1.f;
-            rb[jj] = 0x100;
-        } else {
-            const double Qr = lut[f_q[i]], Qi = lut[f_i[i]], Qd = lut[f_d[i]], Qg = lut[f_g[i]];
-            // previous row's Qi / Qd un-scale X' and Y' of the diagonal cell; row 0 is unscaled
-            const double Qi_up = (i > 0) ? lut[f_i[i - 1]] : 1.0;
-            const double Qd_up = (i > 0) ? lut[f_d[i - 1]] : 1.0;
-            const int32_t base = f_b[i];
-            const double mm = 1.0 - (Qi + Qd), gm = 1.0 - Qg;
-            pm[jj] = (float)(1.0 - Qr);
-            px[jj] = (base == 'N') ? pm[jj] : (float)(gatk ? Qr / 3.0 : Qr);
-            ca[jj] = (float)mm;
-            cbx[jj] = (float)(gm * Qi_up);
-            cby[jj] = (float)(gm * Qd_up);
-            ccx[jj] = (i > 0) ? (float)(Qg * Qi_up / Qi) : 0.f;
-            cg[jj] = (float)Qg;
-            rb[jj] = base;
+        for (int jj = 0; jj < CH * 4; ++jj) { pm[jj] = px[jj] = 0.f; rsym[jj] = 5u; }
+#pragma unroll
+        for (int jj = 0; jj < K; ++jj) {
+            const int i = t * K + jj - pad;      // 0-based read position of this row
+            if (i < 0) {
+                // padding rows reproduce row 0: M = X = 0 and Y stays at its initial value
+                ca[jj] = cbx[jj] = cby[jj] = ccx[jj] = 0.f; cg[jj] = 1.f;
+            } else {
+                const double Qr = lut[f_q[i]], Qi = lut[f_i[i]], Qd = lut[f_d[i]], Qg = lut[f_g[i]];
+                // previous row's Qi / Qd un-scale X' and Y' of the diagonal cell; row 0 is unscaled
+                const double Qi_up = (i > 0) ? lut[f_i[i - 1]] : 1.0;
+                const double Qd_up = (i > 0) ? lut[f_d[i - 1]] : 1.0;
+                const uint32_t base = f_b[i];
+                const double mm = 1.0 - (Qi + Qd), gm = 1.0 - Qg;
+                pm[jj] = (float)(1.0 - Qr);
+                px[jj] = (float)(gatk ? Qr / 3.0 : Qr);
+                rsym[jj] = (base == 'N') ? 4u : hap_symbol(base);   // 5: matches nothing but N
+                ca[jj] = (float)mm;
+                cbx[jj] = (float)(gm * Qi_up);
+                cby[jj] = (float)(gm * Qd_up);
+                ccx[jj] = (i > 0) ? (float)(Qg * Qi_up / Qi) : 0.f;
+                cg[jj] = (float)Qg;
+            }
+        }
+        // priors per haplotype symbol: p(r, h) = (r == h || r == 'N' || h == 'N') ? 1-Qr : Qr
+#pragma unroll
+        for (int sym = 0; sym < HMM_NSYM; ++sym) {
+#pragma unroll
+            for (int ch = 0; ch < CH; ++ch) {
+                float q[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int jj = ch * 4 + e;
+                    const bool match = (sym == 4) || (rsym[jj] == 4u) || (sym < 4 && rsym[jj] == (uint32_t)sym);
+                    q[e] = match ? pm[jj] : px[jj];
+                }
+                prior_tab[wib][sym][ch][t] = make_float4(q[0], q[1], q[2], q[3]);
+            }
         }
     }
+    __syncwarp();
     const float qi_last = (float)lut[f_i[R - 1]];   // X[R][j] = Qi_R * X'[R][j]
     const bool top_boundary = (t * K - 1) < pad;    // the row above this lane's first row is row 0
+    const int n_pad_rows = pad - t * K;             // rows jj < n_pad_rows of this lane are padding
 
     // ---- streaming state ------------------------------------------------------------------------
     float M[K], X[K], Y[K];
@@ -143,43 +220,44 @@ hmm_stream_kernel(HmmBatchView v, const int64_t *__restrict__ read_out_off,
     float bM = 0.f, bX = 0.f, bY = 0.f;              // this lane's bottom row, sent down next step
     float acc = 0.f, init = 0.f;
 
-    int64_t hidx = h0 - 1;     // virtual haplotype of length t: lane t idles for t steps
+    int32_t hidx = h0 - 1;     // virtual haplotype of length t: lane t idles for t steps
     int32_t c = 1, Hlen = t;
-    const uint8_t *hptr = nullptr;
+    const uint8_t *cptr = codes;                     // codes of the current haplotype
+    uint32_t code_next = 5u;
 
-    int64_t total = 31;
-    for (int64_t h = h0; h < h1; ++h) total += v.hap_len[h];
+    int32_t total = 31;
+    for (int32_t h = h0; h < h1; ++h) total += hapinfo[h].len;
 
-#pragma unroll 1
-    for (int64_t s = 0; s < total; ++s) {
+    const float4 *tab_lane = &prior_tab[wib][0][0][t];
+    constexpr int SYM_STRIDE = CH * 32;              // float4 elements between symbols
+
+#pragma unroll 2
+    for (int32_t s = 0; s < total; ++s) {
         if (c > Hlen) {
-            // ---- this lane finished a haplotype: emit (lane 31 owns row R) and start the next ----
-            if (t == 31 && hidx >= h0) {
-                const int64_t o = obase + (hidx - h0);
-                if (!(acc >= RESCUE_BELOW) || !isfinite(acc)) {
-                    rescue[atomicAdd(rescue_count, 1)] = make_int2(r, (int)hidx);
-                    out[o] = nan("");
-                } else {
-                    out[o] = log10((double)acc) - log10((double)SCALE_F);
-                }
-            }
+            // ---- this lane finished a haplotype: lane 31 owns row R and emits the forward sum ----
+            if (t == 31 && hidx >= h0) my_sums[hidx - h0] = acc;
             ++hidx;
             acc = 0.f;
             c = 1;
             if (hidx < h1) {
-                Hlen = v.hap_len[hidx];
-                hptr = v.buf + v.hap_off[hidx];
-                init = SCALE_F / (float)Hlen;
+                const HapInfo hi = hapinfo[hidx];
+                Hlen = hi.len;
+                cptr = codes + hi.off;
+                init = hi.init;
+                code_next = cptr[0];
             } else {
                 Hlen = 0x7fffffff;   // drained: keep stepping on neutral input
-                hptr = nullptr;
+                code_next = 5u;
             }
 #pragma unroll
-            for (int jj = 0; jj < K; ++jj) { M[jj] = 0.f; X[jj] = 0.f; Y[jj] = (t * K + jj < pad) ? init : 0.f; }
+            for (int jj = 0; jj < K; ++jj) { M[jj] = 0.f; X[jj] = 0.f; Y[jj] = (jj < n_pad_rows) ? init : 0.f; }
             pdM = 0.f; pdX = 0.f; pdY = top_boundary ? init : 0.f;
         }
-        const int32_t hb = (hptr != nullptr && hidx >= h0) ? (int32_t)__ldg(hptr + (c - 1)) : 0x200;
-        const bool hN = (hb == 'N');
+        const uint32_t code = code_next;
+        if (c < Hlen && hidx >= h0 && hidx < h1) code_next = cptr[c];          // prefetch the next column's symbol
+        float4 pr4[CH];
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) pr4[ch] = tab_lane[code * SYM_STRIDE + ch * 32];
 
         float upM = __shfl_up_sync(0xffffffffu, bM, 1);
         float upX = __shfl_up_sync(0xffffffffu, bX, 1);
@@ -190,7 +268,8 @@ hmm_stream_kernel(HmmBatchView v, const int64_t *__restrict__ read_out_off,
 #pragma unroll
         for (int jj = 0; jj < K; ++jj) {
             const float oM = M[jj], oX = X[jj], oY = Y[jj];
-            const float pr = (rb[jj] == hb || hN) ? pm[jj] : px[jj];
+            const float4 p4 = pr4[jj / 4];
+            const float pr = (jj % 4 == 0) ? p4.x : (jj % 4 == 1) ? p4.y : (jj % 4 == 2) ? p4.z : p4.w;
             float vv = cby[jj] * dY;
             vv = fmaf(cbx[jj], dX, vv);
             vv = fmaf(ca[jj], dM, vv);
@@ -206,13 +285,29 @@ hmm_stream_kernel(HmmBatchView v, const int64_t *__restrict__ read_out_off,
         ++c;
     }
     // the last haplotype of lane 31 ends exactly at the last step
-    if (t == 31 && hidx >= h0 && hidx < h1 && c > Hlen) {
-        const int64_t o = obase + (hidx - h0);
-        if (!(acc >= RESCUE_BELOW) || !isfinite(acc)) {
-            rescue[atomicAdd(rescue_count, 1)] = make_int2(r, (int)hidx);
-            out[o] = nan("");
+    if (t == 31 && hidx >= h0 && hidx < h1 && c > Hlen) my_sums[hidx - h0] = acc;
+}
+
+// forward sums -> log10 likelihoods; sums FP32 cannot be trusted with are queued for the FP64 kernel
+__global__ void __launch_bounds__(256)
+hmm_finalize_kernel(HmmBatchView v, const int64_t *__restrict__ read_out_off,
+                    const int32_t *__restrict__ order, int32_t n_items, const float *__restrict__ sums,
+                    double *__restrict__ out, int2 *__restrict__ rescue, int32_t *__restrict__ rescue_count)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    const int32_t r = order[i];
+    const int32_t bt = v.read_batch[r];
+    const int32_t h0 = (int32_t)v.batch_hap_start[bt], h1 = (int32_t)v.batch_hap_start[bt + 1];
+    const int64_t o = read_out_off[r];
+    const double lscale = log10((double)SCALE_F);
+    for (int32_t h = h0; h < h1; ++h) {
+        const float sfl = sums[o + (h - h0)];
+        if (!(sfl >= RESCUE_BELOW) || !isfinite(sfl)) {
+            rescue[atomicAdd(rescue_count, 1)] = make_int2(r, h);
+            out[o + (h - h0)] = nan("");
         } else {
-            out[o] = log10((double)acc) - log10((double)SCALE_F);
+            out[o + (h - h0)] = log10((double)sfl) - lscale;
         }
     }
 }
@@ -390,13 +485,13 @@ hmm_striped_kernel(HmmBatchView v, const int64_t *__restrict__ read_out_off,
 
 template <int K>
 int launch_stream(const HmmBatchView &v, const int64_t *read_out_off, const int32_t *order,
-                  int32_t count, const double *lut, int gatk, double *out, int2 *rescue,
-                  int32_t *rescue_count, cudaStream_t st)
+                  int32_t count, const double *lut, int gatk, const uint8_t *codes,
+                  const HapInfo *info, float *sums, cudaStream_t st)
 {
     if (count == 0) return AGX_OK;
     const int blocks = (count + HMM_WARPS - 1) / HMM_WARPS;
     hmm_stream_kernel<K><<<blocks, HMM_WARPS * 32, 0, st>>>(
-        v, read_out_off, order + (int64_t)(K - 1) * v.n_reads, count, lut, gatk, out, rescue, rescue_count);
+        v, read_out_off, order + (int64_t)(K - 1) * v.n_reads, count, lut, gatk, codes, info, sums);
     count_launch();
     AGX_CUDA(cudaGetLastError());
     return AGX_OK;
@@ -439,6 +534,7 @@ void hmm_workspace_free(HmmWorkspace &ws)
     if (ws.rescue) cudaFree(ws.rescue);
     if (ws.d_lut) cudaFree(ws.d_lut);
     if (ws.scratch) cudaFree(ws.scratch);
+    if (ws.prep) cudaFree(ws.prep);
     ws.prof_stream.destroy(); ws.prof_fp64.destroy(); ws.prof_classify.destroy();
     ws = HmmWorkspace();
 }
@@ -454,7 +550,7 @@ static int hmm_scratch_reserve(HmmWorkspace &ws, int64_t bytes)
     return AGX_OK;
 }
 
-int hmm_run_device(HmmWorkspace &ws, const HmmBatchView &v, const int64_t *d_read_out_off,
+int hmm_run_device(HmmWorkspace &ws, const HmmBatchView &v, int64_t buf_bytes, const int64_t *d_read_out_off,
                    int64_t n_pairs, bool gatk_mode, bool force_fp64, bool do_rescue, double *d_out,
                    cudaStream_t st)
 {
@@ -486,15 +582,50 @@ int hmm_run_device(HmmWorkspace &ws, const HmmBatchView &v, const int64_t *d_rea
     const int64_t stride = 3 * ((int64_t)max_hap + 2);
 
     if (!force_fp64) {
+        // haplotype symbol codes + per-haplotype records + FP32 forward sums live in one scratch block
+        int64_t n_stream = 0;
+        for (int c = 0; c < HMM_MAX_K; ++c) n_stream += counts[c];
+        uint8_t *codes = nullptr;
+        HapInfo *info = nullptr;
+        float *sums = nullptr;
+        if (n_stream > 0) {
+            const int64_t info_bytes = ((v.n_haps * (int64_t)sizeof(HapInfo) + 255) / 256) * 256;
+            const int64_t sums_bytes = ((n_pairs * (int64_t)sizeof(float) + 255) / 256) * 256;
+            const int64_t need = info_bytes + sums_bytes + buf_bytes + 256;
+            if (need > ws.cap_prep) {
+                if (ws.prep) cudaFree(ws.prep);
+                ws.prep = nullptr; ws.cap_prep = 0;
+                AGX_CUDA(cudaMalloc(&ws.prep, (size_t)need));
+                ws.cap_prep = need;
+            }
+            info = reinterpret_cast<HapInfo *>(ws.prep);
+            sums = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(ws.prep) + info_bytes);
+            codes = reinterpret_cast<uint8_t *>(ws.prep) + info_bytes + sums_bytes;
+            const int pblocks = (int)(v.n_haps < (int64_t)sms * 16 ? v.n_haps : (int64_t)sms * 16);
+            hmm_prep_haps_kernel<<<pblocks, 128, 0, st>>>(v.buf, v.hap_off, v.hap_len, v.n_haps, codes, info);
+            count_launch();
+            AGX_CUDA(cudaGetLastError());
+        }
         ws.prof_stream.begin(st);
-#define AGX_STREAM(KK)                                                                              \
-    if ((rc = launch_stream<KK>(v, d_read_out_off, ws.order, counts[KK - 1], ws.d_lut, gatk, d_out, \
-                                rescue, rescue_count, st)) != AGX_OK)                               \
+#define AGX_STREAM(KK)                                                                          \
+    if ((rc = launch_stream<KK>(v, d_read_out_off, ws.order, counts[KK - 1], ws.d_lut, gatk,    \
+                                codes, info, sums, st)) != AGX_OK)                              \
         return rc;
         AGX_STREAM(1) AGX_STREAM(2) AGX_STREAM(3) AGX_STREAM(4)
         AGX_STREAM(5) AGX_STREAM(6) AGX_STREAM(7) AGX_STREAM(8)
 #undef AGX_STREAM
         ws.prof_stream.end(st);
+        if (n_stream > 0) {
+            // classes 0..HMM_MAX_K-1 are contiguous in `order` only per class: finalize class by class
+            for (int c = 0; c < HMM_MAX_K; ++c) {
+                if (counts[c] == 0) continue;
+                hmm_finalize_kernel<<<(counts[c] + 255) / 256, 256, 0, st>>>(
+                    v, d_read_out_off, ws.order + (int64_t)c * v.n_reads, counts[c], sums, d_out, rescue,
+                    rescue_count);
+                count_launch();
+            }
+            AGX_CUDA(cudaGetLastError());
+        }
         if (counts[HMM_LONG] > 0) {
             // reads longer than 256 rows: FP32 striped kernel, one warp per read
             int64_t warps = counts[HMM_LONG];

@@ -236,7 +236,7 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
         __syncwarp();
 
         const int send = min(DUO_CH, S - s0);
-#pragma unroll 1
+#pragma unroll 2
         for (int u = 0; u < send; ++u) {
             const int s = s0 + u;
             const uint2 R = ring[sub][(s - t) & (DUO_RING - 1)];
