@@ -122,7 +122,7 @@ def reset_launch_count() -> None:
     load_library().agx_reset_launch_count()
 
 
-PROF_SW_DUO, PROF_SW_WAVE, PROF_HMM_STREAM, PROF_HMM_FP64, PROF_SW_CLASSIFY, PROF_HMM_CLASSIFY = range(6)
+PROF_SW_DUO, PROF_SW_WAVE, PROF_HMM_STREAM, PROF_HMM_FP64, PROF_SW_CLASSIFY, PROF_HMM_CLASSIFY, PROF_SW_LONG = range(7)
 
 
 def set_profiling(on: bool) -> None:

@@ -36,7 +36,7 @@ struct ProfSpan {
 };
 extern std::atomic<int> g_profiling;
 enum { AGX_PROF_SW_DUO = 0, AGX_PROF_SW_WAVE = 1, AGX_PROF_HMM_STREAM = 2, AGX_PROF_HMM_FP64 = 3,
-       AGX_PROF_SW_CLASSIFY = 4, AGX_PROF_HMM_CLASSIFY = 5, AGX_PROF_COUNT = 6 };
+       AGX_PROF_SW_CLASSIFY = 4, AGX_PROF_HMM_CLASSIFY = 5, AGX_PROF_SW_LONG = 6, AGX_PROF_COUNT = 7 };
 
 // ---- Smith-Waterman -----------------------------------------------------------------------
 struct SwScoring {
@@ -46,7 +46,25 @@ struct SwScoring {
 // Number of length classes handled by the packed s16x2 inter-task kernel; the extra class
 // (index SW_N_DUO_CLASSES) is the generic s32 wavefront kernel.
 constexpr int SW_N_DUO_CLASSES = 11;
-constexpr int SW_N_CLASSES = SW_N_DUO_CLASSES + 1;
+// + the generic one-warp-per-pair wavefront class + the whole-GPU long-alignment class
+constexpr int SW_N_CLASSES = SW_N_DUO_CLASSES + 2;
+// a pair goes to the whole-GPU kernel (sw_long.cu) when it has at least this many cells and its
+// shorter side does not fit the inter-task kernel
+constexpr int64_t SW_LONG_CELLS_DEFAULT = (int64_t)1 << 28;
+int64_t sw_long_cells();   // SW_LONG_CELLS_DEFAULT unless the environment sets AGX_SW_LONG_CELLS
+
+// scratch of the long-alignment kernel
+struct SwLongWorkspace {
+    int32_t *buf = nullptr;   // boundary column (2 * rows) + per-stripe progress counters + best
+    int64_t cap = 0;          // in int32 elements
+    uint8_t *seq = nullptr;   // device copies of the two sequences (host entry point)
+    int64_t cap_seq = 0;
+};
+int sw_long_device(SwLongWorkspace &ws, const uint8_t *d_a, int64_t la, const uint8_t *d_b, int64_t lb,
+                   SwScoring sc, int32_t *d_best, cudaStream_t st);
+int sw_long_host_multi(int n_dev, const int *dev, cudaStream_t *st, SwLongWorkspace **ws, const uint8_t *a,
+                       int64_t la, const uint8_t *b, int64_t lb, SwScoring sc, int32_t *score_out);
+void sw_long_workspace_free(SwLongWorkspace &ws);
 
 // Per-call device scratch for the SW path (owned by the device context).
 struct SwWorkspace {
@@ -57,7 +75,8 @@ struct SwWorkspace {
     int64_t cap_pairs = 0;
     int64_t cap_wave = 0;
     int32_t *h_counters = nullptr;   // pinned mirror of counters
-    ProfSpan prof_duo, prof_wave, prof_classify;
+    ProfSpan prof_duo, prof_wave, prof_classify, prof_long;
+    SwLongWorkspace lng;
 };
 
 // Enqueue the whole SW path for one device-resident batch on `st`.

@@ -22,6 +22,9 @@
 //                        columns per stripe, stripes chained through a boundary column in global
 //                        memory.  It compares raw bytes, so '\n', 'N', lower case ... behave exactly
 //                        as in the reference (:332).
+#include <cstdlib>
+#include <vector>
+
 #include "common.cuh"
 
 namespace agx {
@@ -41,6 +44,7 @@ __host__ __device__ constexpr DuoClass duo_class(int c)
 __host__ __device__ constexpr int duo_cap(int c) { return duo_class(c).g * duo_class(c).k; }
 constexpr int DUO_MAX_CAP = duo_cap(SW_N_DUO_CLASSES - 1);  // 1024
 constexpr int GENERIC = SW_N_DUO_CLASSES;
+constexpr int LONGC = SW_N_DUO_CLASSES + 1;
 
 // counters layout (int32): [0, NC) class counts / append cursors; NC: max raw length seen
 constexpr int CNT_MAXLEN = SW_N_CLASSES;
@@ -75,7 +79,7 @@ __device__ __forceinline__ bool strip_newline(const uint8_t *p, int32_t &n)
 __global__ void __launch_bounds__(256)
 sw_classify_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
                    const int32_t *__restrict__ len, int64_t n_pairs, int32_t s16_max_short,
-                   int32_t match, int32_t *__restrict__ order, int32_t *__restrict__ counters,
+                   int64_t long_cells, int32_t match, int32_t *__restrict__ order, int32_t *__restrict__ counters,
                    int32_t *__restrict__ scores)
 {
     __shared__ int32_t s_cnt[SW_N_CLASSES];
@@ -99,7 +103,8 @@ sw_classify_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__
             scores[p] = (nx && ny) ? match : 0;
         } else {
             cls = GENERIC;
-            if (shorter <= s16_max_short) {
+            if ((int64_t)len[2 * p] * (int64_t)len[2 * p + 1] >= long_cells && shorter > DUO_MAX_CAP) cls = LONGC;
+            else if (shorter <= s16_max_short) {
 #pragma unroll
                 for (int c = SW_N_DUO_CLASSES - 1; c >= 0; --c)
                     if (shorter <= duo_cap(c)) cls = c;
@@ -433,6 +438,16 @@ int launch_all_duo(const uint8_t *d_seqs, const int64_t *d_off, const int32_t *d
 // ------------------------------------------------------------------------------------------
 // host side of the SW path
 // ------------------------------------------------------------------------------------------
+int64_t sw_long_cells()
+{
+    static const int64_t v = [] {
+        const char *e = getenv("AGX_SW_LONG_CELLS");
+        const long long x = e ? atoll(e) : 0;
+        return x > 0 ? (int64_t)x : SW_LONG_CELLS_DEFAULT;
+    }();
+    return v;
+}
+
 int sw_workspace_reserve(SwWorkspace &ws, int64_t n_pairs)
 {
     if (!ws.counters) {
@@ -455,7 +470,8 @@ void sw_workspace_free(SwWorkspace &ws)
     if (ws.counters) cudaFree(ws.counters);
     if (ws.wave_scratch) cudaFree(ws.wave_scratch);
     if (ws.h_counters) cudaFreeHost(ws.h_counters);
-    ws.prof_duo.destroy(); ws.prof_wave.destroy(); ws.prof_classify.destroy();
+    sw_long_workspace_free(ws.lng);
+    ws.prof_duo.destroy(); ws.prof_wave.destroy(); ws.prof_classify.destroy(); ws.prof_long.destroy();
     ws = SwWorkspace();
 }
 
@@ -479,7 +495,7 @@ int sw_run_device(SwWorkspace &ws, const uint8_t *d_seqs, const int64_t *d_off, 
     const int cblocks = (int)((n_pairs + 255) / 256);
     ws.prof_classify.begin(st);
     sw_classify_kernel<<<cblocks, 256, 0, st>>>(d_seqs, d_off, d_len, n_pairs, s16_max_short,
-                                                sc.match, ws.order, ws.counters, d_scores);
+                                                sw_long_cells(), sc.match, ws.order, ws.counters, d_scores);
     count_launch();
     ws.prof_classify.end(st);
     AGX_CUDA(cudaGetLastError());
@@ -508,6 +524,27 @@ int sw_run_device(SwWorkspace &ws, const uint8_t *d_seqs, const int64_t *d_off, 
                            ws.counters, st);
     ws.prof_duo.end(st);
     if (rc != AGX_OK) return rc;
+
+    // whole-GPU alignments, one after the other (each one fills the device by itself)
+    if (counts[LONGC] > 0) {
+        std::vector<int32_t> ids(counts[LONGC]);
+        AGX_CUDA(cudaMemcpyAsync(ids.data(), ws.order + (int64_t)LONGC * n_pairs, ids.size() * sizeof(int32_t),
+                                 cudaMemcpyDeviceToHost, st));
+        AGX_CUDA(cudaStreamSynchronize(st));
+        ws.prof_long.begin(st);
+        for (int32_t p : ids) {
+            int64_t o[2];
+            int32_t l[2];
+            AGX_CUDA(cudaMemcpyAsync(o, d_off + 2 * (int64_t)p, sizeof o, cudaMemcpyDeviceToHost, st));
+            AGX_CUDA(cudaMemcpyAsync(l, d_len + 2 * (int64_t)p, sizeof l, cudaMemcpyDeviceToHost, st));
+            AGX_CUDA(cudaStreamSynchronize(st));
+            // columns = the longer sequence (more stripes in flight), rows = the shorter
+            const int hi = l[0] >= l[1] ? 0 : 1;
+            rc = sw_long_device(ws.lng, d_seqs + o[hi], l[hi], d_seqs + o[1 - hi], l[1 - hi], sc, d_scores + p, st);
+            if (rc != AGX_OK) return rc;
+        }
+        ws.prof_long.end(st);
+    }
 
     // generic list = pairs classified generic up front + pairs the duo kernels bounced (non-ACGT)
     const int64_t generic_upper = (int64_t)counts[GENERIC] + n_duo;

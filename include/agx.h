@@ -67,7 +67,8 @@ void agx_reset_launch_count(void);
  * its dominant kernels with CUDA events on the stream they are launched on; agx_profile_ms()
  * returns the duration (ms) of the LAST recorded span on `device`, or a negative number if that
  * span never ran.  which: 0 SW inter-task (duo) kernels, 1 SW wavefront kernel, 2 PairHMM FP32
- * stream kernels, 3 PairHMM FP64 kernel, 4 SW classify kernel, 5 PairHMM classify kernel. */
+ * stream kernels, 3 PairHMM FP64 kernel, 4 SW classify kernel, 5 PairHMM classify kernel,
+ * 6 SW whole-GPU long-alignment kernel(s). */
 int agx_set_profiling(int32_t on);
 double agx_profile_ms(int32_t device, int32_t which);
 
@@ -80,7 +81,11 @@ double agx_profile_ms(int32_t device, int32_t which);
  * gap_extend < 0, the first base of a gap costs gap_open + gap_extend (:313, :321).  The
  * reference's constants are (1, -1, -3, -1) (:40-43).  Other sign combinations -> AGX_ERANGE.
  * scores_out[p] is bit-exact with the reference's `Score: %d` (:348).
- * Pairs are sharded across the configured GPUs by cell count; no collective is involved. */
+ * Pairs are sharded across the configured GPUs by cell count; no collective is involved.
+ * A pair with >= 2^28 cells whose shorter side exceeds 1024 symbols is scored on its own by the
+ * intra-task wavefront kernel: its columns are striped over all SMs and, in the host entry points,
+ * over all configured GPUs (boundary columns move between neighbouring GPUs as NVLink peer stores).
+ * The threshold can be changed with the environment variable AGX_SW_LONG_CELLS. */
 int sw_score_batch(const uint8_t *const *a, const int32_t *a_len,
                    const uint8_t *const *b, const int32_t *b_len, int64_t n_pairs,
                    int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend,

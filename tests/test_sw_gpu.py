@@ -162,3 +162,59 @@ def test_config3_shape_properties(agx, gpu_lib, oracle_mod):
     idx = np.stack([2 * pick, 2 * pick + 1], axis=1).reshape(-1)
     want = oracle_mod.sw_scores_flat(inp.buf, inp.off[idx], inp.len[idx])
     assert got[pick].tolist() == want.tolist()
+
+
+# ---------------------------------------------------------------- long alignments (intra-task wavefront over all SMs)
+def _long_pair(agx, n, seed, related=True):
+    data = agx.synth.sw_long_pair(n, seed=seed, related=related)
+    return agx.formats.parse_sw(data, line_buf=1 << 30)
+
+
+@pytest.mark.parametrize("n,related", [(20000, True), (18000, False), (33000, True)])
+def test_long_alignment_whole_gpu_kernel(agx, gpu_lib, oracle_mod, n, related):
+    """>= 2^28 cells: the pair takes the stripe-pipelined whole-GPU kernel (BASELINE config 5 path)."""
+    inp = _long_pair(agx, n, seed=n, related=related)
+    assert int(inp.len[0]) * int(inp.len[1]) >= 1 << 28
+    gpu_lib.set_profiling(True)
+    got = gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len)
+    want = oracle_mod.sw_scores_flat(inp.buf, inp.off, inp.len)
+    assert got.tolist() == want.tolist()
+    if related:
+        assert got[0] > n // 2
+
+
+def test_long_alignment_device_entry_point_and_mixed_batch(agx, gpu_lib, oracle_mod):
+    import torch
+    big = agx.synth.sw_long_pair(17000, seed=5)
+    small = agx.synth.sw_random_file(np.random.default_rng(7), 50, 1, 300, alphabet=b"ACGTN")
+    # one file: 50 short pairs, the long pair, with non-ACGT bytes in the long pair too
+    body_big = big.split(b"\n", 1)[1].replace(b"ACGTAC", b"ACNTAC", 3)
+    data = b"102\n" + small.split(b"\n", 1)[1] + body_big
+    inp = agx.formats.parse_sw(data, line_buf=1 << 30)
+    assert inp.n_pairs == 51
+    want = oracle_mod.sw_scores_flat(inp.buf, inp.off, inp.len)
+    got = gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len)
+    assert got.tolist() == want.tolist()
+    dev = torch.device("cuda:0")
+    d_buf, d_off, d_len = (torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (inp.buf, inp.off, inp.len))
+    d_out = torch.zeros(inp.n_pairs, dtype=torch.int32, device=dev)
+    gpu_lib.sw_score_device(0, d_buf.data_ptr(), d_buf.numel(), d_off.data_ptr(), d_len.data_ptr(), inp.n_pairs,
+                            d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert d_out.cpu().numpy().tolist() == want.tolist()
+    assert gpu_lib.profile_ms(0, gpu_lib.PROF_SW_LONG) > 0
+
+
+def test_long_alignment_properties_100kbp(agx, gpu_lib):
+    """100 kbp x 100 kbp (10^10 cells): too large for the oracle in a test; size-independent properties."""
+    inp = _long_pair(agx, 100_000, seed=3, related=True)
+    s = int(gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len)[0])
+    swap = np.array([1, 0])
+    assert int(gpu_lib.sw_score_flat(inp.buf, inp.off[swap], inp.len[swap])[0]) == s      # symmetry
+    self_s = int(gpu_lib.sw_score_flat(inp.buf, inp.off[[0, 0]], inp.len[[0, 0]])[0])
+    assert self_s == 100_001                                                               # a vs a, newline included
+    assert 50_000 < s < self_s
+    # a prefix pair can never beat the full pair (local alignment is monotone in its inputs)
+    half = inp.len.copy()
+    half[:] = 50_000
+    assert int(gpu_lib.sw_score_flat(inp.buf, inp.off, half)[0]) <= s
