@@ -275,7 +275,9 @@ int sw_long_host_multi(int n_dev, const int *dev, cudaStream_t *st, SwLongWorksp
     std::vector<LongArgs> args(n_dev);
     std::vector<int> ks(n_dev);
     std::vector<int64_t> c_lo(n_dev + 1);
-    for (int gidx = 0; gidx <= n_dev; ++gidx) c_lo[gidx] = la * gidx / n_dev;
+    // interior cuts sit on multiples of the widest stripe (256 columns): only the very last stripe of the
+    // matrix may carry padding columns, whose boundary nobody consumes
+    for (int gidx = 0; gidx <= n_dev; ++gidx) c_lo[gidx] = (gidx == n_dev) ? la : (la * gidx / n_dev) / 256 * 256;
     // allocate + upload on every GPU, clear the flags, then make sure ALL GPUs are clear before any launch
     for (int gidx = 0; gidx < n_dev; ++gidx) {
         AGX_CUDA(cudaSetDevice(dev[gidx]));

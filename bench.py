@@ -425,6 +425,64 @@ def bench_hmm(agx, args, rank, local_rank, world, device):
     }
 
 
+def run_sw_long(args):
+    """BASELINE configs[4]: ONE pair of --long-len x --long-len, columns striped over --gpus B200s of this
+    box inside one process (NVLink peer boundary exchange), through the host C ABI."""
+    import torch
+    import agxpkg
+    import oracle
+    agx = agxpkg.load()
+    cap = agx.capi
+    n_gpus = min(args.gpus, torch.cuda.device_count())
+    cap.init(n_gpus)
+    cap.set_profiling(True)
+    L = args.long_len
+    inp = agx.formats.parse_sw(agx.synth.sw_long_pair(L, seed=5, related=True), line_buf=1 << 30)
+    cells = float(L) * float(L)
+    for _ in range(max(1, min(args.warmup, 2))):
+        score = int(cap.sw_score_flat(inp.buf, inp.off, inp.len)[0])
+    cap.reset_launch_count()
+    with ClockSampler(0) as clk:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            score = int(cap.sw_score_flat(inp.buf, inp.off, inp.len)[0])
+        dt = (time.perf_counter() - t0) / args.steps
+    launches = cap.launch_count()
+    # CPU: the MAX_LINE_LENGTH-raised reference build on a smaller square, extrapolation labelled
+    cpu = None
+    ref_exe = ROOT / "oracle" / "_ref" / "sw_antidiag_long"
+    if not args.no_cpu_baseline and ref_exe.exists():
+        n_small = 20000
+        with tempfile.TemporaryDirectory() as td:
+            pth = Path(td) / "small.in"
+            pth.write_bytes(agx.synth.sw_long_pair(n_small, seed=6, related=True))
+            t1 = time.perf_counter()
+            oracle.run_ref_sw(str(pth), long_lines=True)
+            cdt = time.perf_counter() - t1
+        g = n_small * n_small / cdt / 1e9
+        cpu = {"value": g, "unit": "GCUPS", "cores": 1, "kind": "reference",
+               "sample": f"oracle/_ref/sw_antidiag_long (MAX_LINE_LENGTH raised, arithmetic untouched) on one {n_small}x{n_small} pair; "
+                         f"the reference is single-threaded per pair; {L}x{L} would take ~{cells / (g * 1e9) / 3600:.1f} core-hours (extrapolated)"}
+    peaks = measured_peaks()
+    peak = peaks["alu_tlaneops"] * 1e12 if peaks and peaks.get("alu_tlaneops") else NOMINAL_ALU
+    line = {"metric": "SW and PairHMM GCUPS", "value": cells / dt / 1e9, "unit": "GCUPS", "n_gpus": n_gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": f"sw_long: one pair {L}x{L} (BASELINE configs[4]), column stripes over {n_gpus} GPU(s) in one process",
+                       "score": score},
+            "e2e": {"value": cells / dt / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": int(2 * (L + 1)) * n_gpus,
+                    "d2h_bytes_per_step": 4 * n_gpus},
+            "roofline": {"bound": "alu", "kernel": "sw_long_kernel<K> (s32 DPX)", "achieved": cells * 8 / dt / 1e12 / n_gpus,
+                         "peak": peak / 1e12, "unit": "Tlaneop/s per GPU (INT32/DPX pipe)", "frac": cells * 8 / dt / n_gpus / peak,
+                         "ops_per_cell": 8.0, "traffic": None},
+            "gpu_launches": int(launches), "clocks": clk.summary()}
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    cap.shutdown()
+    return 0
+
+
 def run_gpu_arm(args):
     import torch
     import agxpkg
@@ -506,7 +564,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["agx", "reference"], default="agx")
-    ap.add_argument("--workload", choices=["both", "sw", "pairhmm"], default="both")
+    ap.add_argument("--workload", choices=["both", "sw", "pairhmm", "sw_long"], default="both")
+    ap.add_argument("--long-len", type=int, default=1_000_000, help="sw_long: side of the single pair")
     ap.add_argument("--sw-pairs", type=int, default=1_000_000, help="SW pairs per GPU per step")
     ap.add_argument("--hmm-batches", type=int, default=1000, help="PairHMM batches (200 reads x 5 haps) per GPU per step")
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="CPU-baseline sample size, seconds of work per core")
@@ -516,6 +575,8 @@ def main():
         args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.workload == "sw_long":
+        return run_sw_long(args)
     return run_gpu_arm(args)
 
 

@@ -1,0 +1,76 @@
+"""Multi-GPU paths of libagx inside ONE process (the library's own dispatcher: one host thread + one
+stream per GPU).  Needs >= 2 GPUs; skipped on a single-GPU box."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def multi(agx):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    cap = agx.capi
+    cap.shutdown()
+    n = cap.init(0)              # every visible GPU
+    assert n == torch.cuda.device_count()
+    yield cap, n
+    cap.shutdown()
+
+
+def test_sw_batch_is_sharded_over_all_gpus(agx, multi, oracle_mod):
+    cap, n = multi
+    rng = np.random.default_rng(0)
+    data = agx.synth.sw_random_file(rng, 4000, 1, 260, alphabet=b"ACGT")
+    inp = agx.formats.parse_sw(data)
+    got = cap.sw_score_flat(inp.buf, inp.off, inp.len)
+    cap.shutdown()
+    cap.init(1)
+    one = cap.sw_score_flat(inp.buf, inp.off, inp.len)
+    cap.shutdown()
+    cap.init(0)
+    assert np.array_equal(got, one)
+    pick = rng.choice(inp.n_pairs, size=300, replace=False)
+    idx = np.stack([2 * pick, 2 * pick + 1], axis=1).reshape(-1)
+    assert got[pick].tolist() == oracle_mod.sw_scores_flat(inp.buf, inp.off[idx], inp.len[idx]).tolist()
+
+
+def test_pairhmm_reads_are_sharded_over_all_gpus(agx, multi, oracle_mod):
+    cap, n = multi
+    inp = agx.synth.pairhmm_batches(7, 30, 4, seed=33)
+    args = (inp.buf, inp.read_field_off, inp.read_len, inp.hap_off, inp.hap_len, inp.batch_read_start, inp.batch_hap_start)
+    got = cap.pairhmm_forward_flat(*args)
+    want = oracle_mod.pairhmm_flat(inp)
+    assert np.max(np.abs(got - want) / np.abs(want)) <= 1e-5
+    # a single batch is split by reads too
+    one_batch = agx.synth.pairhmm_batches(1, 64, 3, seed=34)
+    args = (one_batch.buf, one_batch.read_field_off, one_batch.read_len, one_batch.hap_off, one_batch.hap_len,
+            one_batch.batch_read_start, one_batch.batch_hap_start)
+    got = cap.pairhmm_forward_flat(*args)
+    want = oracle_mod.pairhmm_flat(one_batch)
+    assert np.max(np.abs(got - want) / np.abs(want)) <= 1e-5
+
+
+@pytest.mark.parametrize("n,related", [(20000, True), (24000, False)])
+def test_long_alignment_column_stripes_across_gpus(agx, multi, oracle_mod, n, related):
+    """One pair, columns striped over the GPUs, boundary columns exchanged as NVLink peer stores."""
+    cap, ngpu = multi
+    data = agx.synth.sw_long_pair(n, seed=n + 1, related=related)
+    inp = agx.formats.parse_sw(data, line_buf=1 << 30)
+    got = cap.sw_score_flat(inp.buf, inp.off, inp.len)
+    want = oracle_mod.sw_scores_flat(inp.buf, inp.off, inp.len)
+    assert got.tolist() == want.tolist()
+
+
+def test_long_alignment_multi_gpu_equals_single_gpu_200kbp(agx, multi):
+    cap, ngpu = multi
+    data = agx.synth.sw_long_pair(200_000, seed=9, related=True)
+    inp = agx.formats.parse_sw(data, line_buf=1 << 30)
+    many = int(cap.sw_score_flat(inp.buf, inp.off, inp.len)[0])
+    cap.shutdown()
+    cap.init(1)
+    one = int(cap.sw_score_flat(inp.buf, inp.off, inp.len)[0])
+    cap.shutdown()
+    cap.init(0)
+    assert many == one and many > 100_000
