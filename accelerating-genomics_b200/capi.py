@@ -12,8 +12,11 @@ from typing import Iterable, Optional, Sequence
 
 import numpy as np
 
+import os
+
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libagx.so"
+# AGX_LIB_PATH selects an alternative build of the same library (kernel-tuning experiments only)
+LIB_PATH = Path(os.environ["AGX_LIB_PATH"]) if os.environ.get("AGX_LIB_PATH") else PKG / "libagx.so"
 
 # every symbol include/agx.h declares (tests check the .so exports all of them)
 SYMBOLS = [

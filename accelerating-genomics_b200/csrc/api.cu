@@ -2,6 +2,7 @@
 // (pair / read sharding by cell count, one host thread + one stream per GPU, no collective) and the
 // host <-> device staging for the flat and pointer-array entry points.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -102,10 +103,20 @@ struct PinBuf {
     template <typename T> T *as() { return reinterpret_cast<T *>(p); }
 };
 
+// stream + workspace + staging buffers of one in-flight SW chunk
+struct SwLane {
+    cudaStream_t st = nullptr;
+    SwWorkspace ws;
+    DevBuf bytes, off, len, out;
+    PinBuf h_out;              // results land here first: a D2H copy into pageable user memory would block
+    int64_t pend_q0 = 0, pend_m = 0;   // chunk whose results still sit in h_out
+};
+
 struct DeviceCtx {
     int device = -1;
     cudaStream_t stream = nullptr;
-    SwWorkspace sw;
+    SwLane lane[2];          // lane[0].st == stream
+    SwWorkspace &sw = lane[0].ws;
     HmmWorkspace hmm;
     DevBuf d_bytes, d_a, d_b, d_c, d_d, d_e, d_f, d_out;   // staging for the host entry points
     PinBuf h_a, h_b, h_out;
@@ -147,6 +158,8 @@ int init_devices(const std::vector<int> &ids)
         c->device = d;
         AGX_CUDA(cudaSetDevice(d));
         AGX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->lane[0].st = c->stream;
+        AGX_CUDA(cudaStreamCreateWithFlags(&c->lane[1].st, cudaStreamNonBlocking));
         g_ctx.push_back(std::move(c));
     }
     return AGX_OK;
@@ -205,36 +218,82 @@ int require_init()
 }
 
 // ---------------------------------------------------------------- SW on one shard
-int sw_shard(DeviceCtx &c, const uint8_t *seqs, const int64_t *off, const int32_t *len, int64_t p0,
-             int64_t p1, SwScoring sc, int32_t *scores_out)
+// One shard = a contiguous range of pairs on one GPU.  It is cut into chunks that alternate between the
+// context's two lanes (stream + workspace + staging buffers each): the host->device copy of chunk k+1 is
+// queued before the host blocks on chunk k's grid-sizing read-back, so copies overlap the DP kernels.
+// Offsets are uploaded as they are; the device base pointer is shifted by the chunk's first byte instead.
+int sw_shard(DeviceCtx &c, const uint8_t *seqs, int64_t seqs_bytes, const int64_t *off, const int32_t *len,
+             int64_t p0, int64_t p1, SwScoring sc, int32_t *scores_out)
 {
     const int64_t n = p1 - p0;
     if (n <= 0) return AGX_OK;
-    // byte range covered by this shard
-    int64_t lo = INT64_MAX, hi = 0;
-    for (int64_t i = 2 * p0; i < 2 * p1; ++i) {
-        lo = std::min(lo, off[i]);
-        hi = std::max(hi, off[i] + len[i]);
+    int64_t chunk = n;
+    if (n > 98304) {
+        chunk = (n + 3) / 4;
+        if (chunk < 65536) chunk = 65536;
+        if (chunk > 524288) chunk = 524288;
     }
-    if (hi < lo) { lo = 0; hi = 0; }
-    const int64_t nbytes = hi - lo;
-    int rc;
-    if ((rc = c.d_bytes.reserve((size_t)nbytes + 16)) != AGX_OK) return rc;
-    if ((rc = c.d_a.reserve((size_t)n * 2 * sizeof(int64_t))) != AGX_OK) return rc;
-    if ((rc = c.d_b.reserve((size_t)n * 2 * sizeof(int32_t))) != AGX_OK) return rc;
-    if ((rc = c.d_out.reserve((size_t)n * sizeof(int32_t))) != AGX_OK) return rc;
-    if ((rc = c.h_a.reserve((size_t)n * 2 * sizeof(int64_t))) != AGX_OK) return rc;
-    int64_t *h_off = c.h_a.as<int64_t>();
-    for (int64_t i = 0; i < 2 * n; ++i) h_off[i] = off[2 * p0 + i] - lo;
-    cudaStream_t st = c.stream;
-    AGX_CUDA(cudaMemcpyAsync(c.d_bytes.p, seqs + lo, (size_t)nbytes, cudaMemcpyHostToDevice, st));
-    AGX_CUDA(cudaMemcpyAsync(c.d_a.p, h_off, (size_t)n * 2 * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    AGX_CUDA(cudaMemcpyAsync(c.d_b.p, len + 2 * p0, (size_t)n * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    rc = sw_run_device(c.sw, c.d_bytes.as<uint8_t>(), c.d_a.as<int64_t>(), c.d_b.as<int32_t>(), n, sc,
-                       c.d_out.as<int32_t>(), st);
+    if (const char *e = getenv("AGX_SW_CHUNK")) {        // tuning knob: pairs per chunk (0 = one chunk)
+        const long long v = atoll(e);
+        chunk = v > 0 ? std::min<int64_t>(v, n) : n;
+    }
+    const int64_t n_chunks = (n + chunk - 1) / chunk;
+    std::vector<int64_t> lo(n_chunks, 0);
+
+    auto stage = [&](int64_t k) -> int {
+        SwLane &L = c.lane[k & 1];
+        const int64_t q0 = p0 + k * chunk, q1 = std::min(p1, q0 + chunk), m = q1 - q0;
+        int64_t l = INT64_MAX, h = 0;
+        for (int64_t i = 2 * q0; i < 2 * q1; ++i) {      // offsets were validated by sw_flat_impl
+            l = std::min(l, off[i]);
+            h = std::max(h, off[i] + len[i]);
+        }
+        if (h < l) { l = 0; h = 0; }
+        lo[k] = l;
+        int rc;
+        if ((rc = L.bytes.reserve((size_t)(h - l) + 16)) != AGX_OK) return rc;
+        if ((rc = L.off.reserve((size_t)m * 2 * sizeof(int64_t))) != AGX_OK) return rc;
+        if ((rc = L.len.reserve((size_t)m * 2 * sizeof(int32_t))) != AGX_OK) return rc;
+        if ((rc = L.out.reserve((size_t)m * sizeof(int32_t))) != AGX_OK) return rc;
+        AGX_CUDA(cudaMemcpyAsync(L.bytes.p, seqs + l, (size_t)(h - l), cudaMemcpyHostToDevice, L.st));
+        AGX_CUDA(cudaMemcpyAsync(L.off.p, off + 2 * q0, (size_t)m * 2 * sizeof(int64_t), cudaMemcpyHostToDevice, L.st));
+        AGX_CUDA(cudaMemcpyAsync(L.len.p, len + 2 * q0, (size_t)m * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, L.st));
+        return AGX_OK;
+    };
+
+    // results of a lane's previous chunk: wait for them and hand them to the caller
+    auto drain = [&](SwLane &L) -> int {
+        if (L.pend_m == 0) return AGX_OK;
+        AGX_CUDA(cudaStreamSynchronize(L.st));
+        memcpy(scores_out + L.pend_q0, L.h_out.p, (size_t)L.pend_m * sizeof(int32_t));
+        L.pend_m = 0;
+        return AGX_OK;
+    };
+    c.lane[0].pend_m = c.lane[1].pend_m = 0;
+
+    int rc = stage(0);
     if (rc != AGX_OK) return rc;
-    AGX_CUDA(cudaMemcpyAsync(scores_out + p0, c.d_out.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    AGX_CUDA(cudaStreamSynchronize(st));
+    for (int64_t k = 0; k < n_chunks; ++k) {
+        SwLane &L = c.lane[k & 1];
+        const int64_t q0 = p0 + k * chunk, q1 = std::min(p1, q0 + chunk), m = q1 - q0;
+        if ((rc = L.h_out.reserve((size_t)m * sizeof(int32_t))) != AGX_OK) return rc;
+        // blocks until chunk k is on the device and classified, then queues its DP kernels
+        rc = sw_run_device(L.ws, L.bytes.as<uint8_t>() - lo[k], L.off.as<int64_t>(), L.len.as<int32_t>(), m, sc,
+                           L.out.as<int32_t>(), L.st);
+        if (rc != AGX_OK) return rc;
+        AGX_CUDA(cudaMemcpyAsync(L.h_out.p, L.out.p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, L.st));
+        L.pend_q0 = q0;
+        L.pend_m = m;
+        if (k + 1 < n_chunks) {
+            // the other lane still owns chunk k-1's results; collect them, then refill it with chunk k+1
+            if ((rc = drain(c.lane[(k + 1) & 1])) != AGX_OK) return rc;
+            if ((rc = stage(k + 1)) != AGX_OK) return rc;
+        }
+    }
+    if ((rc = drain(c.lane[0])) != AGX_OK) return rc;
+    if ((rc = drain(c.lane[1])) != AGX_OK) return rc;
+    AGX_CUDA(cudaStreamSynchronize(c.lane[0].st));
+    AGX_CUDA(cudaStreamSynchronize(c.lane[1].st));
     return AGX_OK;
 }
 
@@ -244,15 +303,27 @@ int sw_flat_impl(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *off, co
     if (n_pairs < 0) return fail(AGX_EINVAL, "sw: n_pairs < 0");
     if (n_pairs == 0) return AGX_OK;
     if (!seqs || !off || !len || !scores_out) return fail(AGX_EINVAL, "sw: null argument");
-    for (int64_t i = 0; i < 2 * n_pairs; ++i)
-        if (len[i] < 0 || off[i] < 0 || off[i] + len[i] > seqs_bytes)
-            return fail(AGX_EINVAL, "sw: sequence " + std::to_string(i) + " lies outside the buffer");
+    // one branch-free pass validates every (offset, length) before any device work
+    int32_t longest = 0, shortest = 0;
+    int64_t min_off = 0, max_end = 0;
+    for (int64_t i = 0; i < 2 * n_pairs; ++i) {
+        longest = std::max(longest, len[i]);
+        shortest = std::min(shortest, len[i]);
+        min_off = std::min(min_off, off[i]);
+        max_end = std::max(max_end, off[i] + len[i]);
+    }
+    if (shortest < 0 || min_off < 0 || max_end > seqs_bytes) {
+        for (int64_t i = 0; i < 2 * n_pairs; ++i)
+            if (len[i] < 0 || off[i] < 0 || off[i] + len[i] > seqs_bytes)
+                return fail(AGX_EINVAL, "sw: sequence " + std::to_string(i) + " lies outside the buffer");
+    }
     int rc = require_init();
     if (rc != AGX_OK) return rc;
 
     // very long alignments: one at a time, columns striped over every configured GPU (sw_long.cu)
     std::vector<int64_t> giants;
-    for (int64_t p = 0; p < n_pairs; ++p)
+    const bool maybe_giant = (int64_t)longest * (int64_t)longest >= sw_long_cells() && longest > 1025;
+    for (int64_t p = 0; maybe_giant && p < n_pairs; ++p)
         if ((int64_t)len[2 * p] * (int64_t)len[2 * p + 1] >= sw_long_cells() &&
             std::min(len[2 * p], len[2 * p + 1]) > 1025)
             giants.push_back(p);
@@ -298,7 +369,7 @@ int sw_flat_impl(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *off, co
         cuts = balanced_cuts(prefix, n_dev);
     }
     return for_each_device(n_dev, [&](DeviceCtx &c, int k) {
-        return sw_shard(c, seqs, off, len, cuts[k], cuts[k + 1], sc, scores_out);
+        return sw_shard(c, seqs, seqs_bytes, off, len, cuts[k], cuts[k + 1], sc, scores_out);
     });
 }
 
@@ -486,7 +557,13 @@ void agx_shutdown(void)
     for (auto &c : g_ctx) {
         cudaSetDevice(c->device);
         if (c->stream) cudaStreamSynchronize(c->stream);
-        sw_workspace_free(c->sw);
+        if (c->lane[1].st) cudaStreamSynchronize(c->lane[1].st);
+        for (SwLane &L : c->lane) {
+            sw_workspace_free(L.ws);
+            for (DevBuf *b : {&L.bytes, &L.off, &L.len, &L.out}) b->release();
+            L.h_out.release();
+        }
+        if (c->lane[1].st) cudaStreamDestroy(c->lane[1].st);
         hmm_workspace_free(c->hmm);
         for (DevBuf *b : {&c->d_bytes, &c->d_a, &c->d_b, &c->d_c, &c->d_d, &c->d_e, &c->d_f, &c->d_out}) b->release();
         for (PinBuf *b : {&c->h_a, &c->h_b, &c->h_out}) b->release();

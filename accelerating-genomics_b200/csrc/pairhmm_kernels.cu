@@ -40,7 +40,13 @@ constexpr int HMM_LONG = HMM_MAX_K;
 constexpr int HCNT_RESCUE = HMM_N_CLASSES;      // counters[HCNT_RESCUE]  = rescue list length
 constexpr int HCNT_MAXHAP = HMM_N_CLASSES + 1;  // counters[HCNT_MAXHAP]  = longest haplotype
 constexpr int HCNT_WORDS = HMM_N_CLASSES + 4;
-constexpr int HMM_WARPS = 4;
+#ifndef AGX_HMM_WARPS
+#define AGX_HMM_WARPS 1
+#endif
+#ifndef AGX_HMM_MINBLOCKS
+#define AGX_HMM_MINBLOCKS 20
+#endif
+constexpr int HMM_WARPS = AGX_HMM_WARPS;
 
 constexpr float SCALE_F = 1.329227995784916e36f;  // 2^120
 // a forward sum below this (2^-100) may have lost low-order terms to FP32 underflow
@@ -131,11 +137,12 @@ hmm_prep_haps_kernel(const uint8_t *__restrict__ buf, const int64_t *__restrict_
 // FP32 streaming kernel
 // ------------------------------------------------------------------------------------------
 template <int K>
-__global__ void __launch_bounds__(HMM_WARPS * 32)
+__global__ void __launch_bounds__(HMM_WARPS * 32, AGX_HMM_MINBLOCKS)
 hmm_stream_kernel(HmmBatchView v, const int64_t *__restrict__ read_out_off,
                   const int32_t *__restrict__ order_cls, int32_t n_items,
                   const double *__restrict__ lut_g, int gatk, const uint8_t *__restrict__ codes,
-                  const HapInfo *__restrict__ hapinfo, float *__restrict__ sums)
+                  const uint8_t *__restrict__ zero_pad, const HapInfo *__restrict__ hapinfo,
+                  float *__restrict__ sums)
 {
     constexpr int CH = (K + 3) / 4;                    // float4 chunks of priors per lane
     __shared__ double lut[256];
@@ -220,41 +227,49 @@ hmm_stream_kernel(HmmBatchView v, const int64_t *__restrict__ read_out_off,
     float bM = 0.f, bX = 0.f, bY = 0.f;              // this lane's bottom row, sent down next step
     float acc = 0.f, init = 0.f;
 
-    int32_t hidx = h0 - 1;     // virtual haplotype of length t: lane t idles for t steps
-    int32_t c = 1, Hlen = t;
-    const uint8_t *cptr = codes;                     // codes of the current haplotype
-    uint32_t code_next = 5u;
+    // Per-lane haplotype cursor.  Lane t starts on a virtual haplotype of t columns (it idles for t
+    // steps) whose symbols come from a zeroed pad; `rem` counts the columns left in the current
+    // haplotype and `cp` walks its symbol codes (stride `inc`, 0 once the lane has drained).
+    int32_t hidx = h0 - 1;
+    int32_t rem = t;
+    const uint8_t *cp = zero_pad;
+    int64_t inc = 0;
+    uint32_t code_next = 0u;
 
     int32_t total = 31;
     for (int32_t h = h0; h < h1; ++h) total += hapinfo[h].len;
 
     const float4 *tab_lane = &prior_tab[wib][0][0][t];
     constexpr int SYM_STRIDE = CH * 32;              // float4 elements between symbols
+    const bool lane0 = (t == 0);
 
 #pragma unroll 2
     for (int32_t s = 0; s < total; ++s) {
-        if (c > Hlen) {
+        if (rem == 0) {
             // ---- this lane finished a haplotype: lane 31 owns row R and emits the forward sum ----
             if (t == 31 && hidx >= h0) my_sums[hidx - h0] = acc;
             ++hidx;
             acc = 0.f;
-            c = 1;
             if (hidx < h1) {
                 const HapInfo hi = hapinfo[hidx];
-                Hlen = hi.len;
-                cptr = codes + hi.off;
+                rem = hi.len;
+                cp = codes + hi.off;
+                inc = 1;
                 init = hi.init;
-                code_next = cptr[0];
+                code_next = *cp;
             } else {
-                Hlen = 0x7fffffff;   // drained: keep stepping on neutral input
-                code_next = 5u;
+                rem = 0x7fffffff;    // drained: keep stepping on neutral input
+                cp = zero_pad;
+                inc = 0;
+                code_next = 0u;
             }
 #pragma unroll
             for (int jj = 0; jj < K; ++jj) { M[jj] = 0.f; X[jj] = 0.f; Y[jj] = (jj < n_pad_rows) ? init : 0.f; }
             pdM = 0.f; pdX = 0.f; pdY = top_boundary ? init : 0.f;
         }
         const uint32_t code = code_next;
-        if (c < Hlen && hidx >= h0 && hidx < h1) code_next = cptr[c];          // prefetch the next column's symbol
+        cp += inc;
+        code_next = *cp;                                  // prefetch the next column's symbol
         float4 pr4[CH];
 #pragma unroll
         for (int ch = 0; ch < CH; ++ch) pr4[ch] = tab_lane[code * SYM_STRIDE + ch * 32];
@@ -262,7 +277,7 @@ hmm_stream_kernel(HmmBatchView v, const int64_t *__restrict__ read_out_off,
         float upM = __shfl_up_sync(0xffffffffu, bM, 1);
         float upX = __shfl_up_sync(0xffffffffu, bX, 1);
         float upY = __shfl_up_sync(0xffffffffu, bY, 1);
-        if (t == 0) { upM = 0.f; upX = 0.f; upY = init; }
+        if (lane0) { upM = 0.f; upX = 0.f; upY = init; }
         float dM = pdM, dX = pdX, dY = pdY;
         pdM = upM; pdX = upX; pdY = upY;
 #pragma unroll
@@ -282,10 +297,10 @@ hmm_stream_kernel(HmmBatchView v, const int64_t *__restrict__ read_out_off,
         }
         bM = M[K - 1]; bX = X[K - 1]; bY = Y[K - 1];
         acc += fmaf(qi_last, bX, bM);
-        ++c;
+        --rem;
     }
     // the last haplotype of lane 31 ends exactly at the last step
-    if (t == 31 && hidx >= h0 && hidx < h1 && c > Hlen) my_sums[hidx - h0] = acc;
+    if (t == 31 && hidx >= h0 && hidx < h1 && rem == 0) my_sums[hidx - h0] = acc;
 }
 
 // forward sums -> log10 likelihoods; sums FP32 cannot be trusted with are queued for the FP64 kernel
@@ -485,13 +500,14 @@ hmm_striped_kernel(HmmBatchView v, const int64_t *__restrict__ read_out_off,
 
 template <int K>
 int launch_stream(const HmmBatchView &v, const int64_t *read_out_off, const int32_t *order,
-                  int32_t count, const double *lut, int gatk, const uint8_t *codes,
+                  int32_t count, const double *lut, int gatk, const uint8_t *codes, int64_t codes_bytes,
                   const HapInfo *info, float *sums, cudaStream_t st)
 {
     if (count == 0) return AGX_OK;
     const int blocks = (count + HMM_WARPS - 1) / HMM_WARPS;
     hmm_stream_kernel<K><<<blocks, HMM_WARPS * 32, 0, st>>>(
-        v, read_out_off, order + (int64_t)(K - 1) * v.n_reads, count, lut, gatk, codes, info, sums);
+        v, read_out_off, order + (int64_t)(K - 1) * v.n_reads, count, lut, gatk, codes, codes + codes_bytes,
+        info, sums);
     count_launch();
     AGX_CUDA(cudaGetLastError());
     return AGX_OK;
@@ -586,12 +602,13 @@ int hmm_run_device(HmmWorkspace &ws, const HmmBatchView &v, int64_t buf_bytes, c
         int64_t n_stream = 0;
         for (int c = 0; c < HMM_MAX_K; ++c) n_stream += counts[c];
         uint8_t *codes = nullptr;
+        const int64_t codes_bytes = ((buf_bytes + 255) / 256) * 256;   // a zeroed pad follows the codes
         HapInfo *info = nullptr;
         float *sums = nullptr;
         if (n_stream > 0) {
             const int64_t info_bytes = ((v.n_haps * (int64_t)sizeof(HapInfo) + 255) / 256) * 256;
             const int64_t sums_bytes = ((n_pairs * (int64_t)sizeof(float) + 255) / 256) * 256;
-            const int64_t need = info_bytes + sums_bytes + buf_bytes + 256;
+            const int64_t need = info_bytes + sums_bytes + codes_bytes + 256;
             if (need > ws.cap_prep) {
                 if (ws.prep) cudaFree(ws.prep);
                 ws.prep = nullptr; ws.cap_prep = 0;
@@ -601,6 +618,7 @@ int hmm_run_device(HmmWorkspace &ws, const HmmBatchView &v, int64_t buf_bytes, c
             info = reinterpret_cast<HapInfo *>(ws.prep);
             sums = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(ws.prep) + info_bytes);
             codes = reinterpret_cast<uint8_t *>(ws.prep) + info_bytes + sums_bytes;
+            AGX_CUDA(cudaMemsetAsync(codes + codes_bytes, 0, 256, st));
             const int pblocks = (int)(v.n_haps < (int64_t)sms * 16 ? v.n_haps : (int64_t)sms * 16);
             hmm_prep_haps_kernel<<<pblocks, 128, 0, st>>>(v.buf, v.hap_off, v.hap_len, v.n_haps, codes, info);
             count_launch();
@@ -609,7 +627,7 @@ int hmm_run_device(HmmWorkspace &ws, const HmmBatchView &v, int64_t buf_bytes, c
         ws.prof_stream.begin(st);
 #define AGX_STREAM(KK)                                                                          \
     if ((rc = launch_stream<KK>(v, d_read_out_off, ws.order, counts[KK - 1], ws.d_lut, gatk,    \
-                                codes, info, sums, st)) != AGX_OK)                              \
+                                codes, codes_bytes, info, sums, st)) != AGX_OK)                 \
         return rc;
         AGX_STREAM(1) AGX_STREAM(2) AGX_STREAM(3) AGX_STREAM(4)
         AGX_STREAM(5) AGX_STREAM(6) AGX_STREAM(7) AGX_STREAM(8)

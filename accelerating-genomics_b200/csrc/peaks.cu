@@ -198,6 +198,85 @@ void run(int sms, uint32_t *d_out, long long *d_cyc, int blocks_per_sm)
     fflush(stdout);
 }
 
+// ---- FP32 with realistic operand patterns ---------------------------------------------------------
+// (a) FFMA whose three sources are three DIFFERENT registers (the ordinary peak test reuses a and b)
+// (b) the PairHMM cell of hmm_stream_kernel: K rows, per-row coefficients in registers, the same
+//     dependency structure (independent M terms, X chain down the rows), no loads, no shuffles
+template <int MODE, int K>
+__global__ void __launch_bounds__(256) fp_pattern_kernel(float *out, long long *cycles, float seed, int iters)
+{
+    float ca[K], cbx[K], cby[K], ccx[K], cg[K], pr[K], M[K], X[K], Y[K];
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        ca[j] = 0.9f + seed * (j + 1); cbx[j] = 1e-4f * (j + 1) + seed; cby[j] = 2e-4f * (j + 2) + seed;
+        ccx[j] = 0.1f + seed * j; cg[j] = 0.1f + seed * (j + 3); pr[j] = 0.99f - seed * j;
+        M[j] = seed * tid + j; X[j] = seed + j; Y[j] = 1.f + seed * j;
+    }
+    float upM0 = seed, upX0 = seed * 2, dM0 = seed * 3, dX0 = seed * 4, dY0 = seed * 5;
+    __syncthreads();
+    const long long t0 = clock64();
+#pragma unroll 2
+    for (int it = 0; it < iters; ++it) {
+        if constexpr (MODE == 0) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                M[j] = fmaf(ca[j], cbx[j], M[j]);
+                X[j] = fmaf(cby[j], ccx[j], X[j]);
+                Y[j] = fmaf(cg[j], pr[j], Y[j]);
+            }
+        } else {
+            float upM = upM0, upX = upX0, dM = dM0, dX = dX0, dY = dY0;
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const float oM = M[j], oX = X[j], oY = Y[j];
+                float vv = cby[j] * dY;
+                vv = fmaf(cbx[j], dX, vv);
+                vv = fmaf(ca[j], dM, vv);
+                const float mn = pr[j] * vv;
+                const float xn = fmaf(ccx[j], upX, upM);
+                const float yn = fmaf(cg[j], oY, oM);
+                dM = oM; dX = oX; dY = oY;
+                upM = mn; upX = xn;
+                M[j] = mn; X[j] = xn; Y[j] = yn;
+            }
+            upM0 = M[K - 1]; upX0 = X[K - 1]; dM0 = upM0; dX0 = upX0; dY0 = Y[K - 1];
+        }
+    }
+    const long long t1 = clock64();
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc += M[j] + X[j] + Y[j];
+    out[tid] = acc;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int MODE, int K> void run_fp_pattern(int sms, uint32_t *d_out, long long *d_cyc, int blocks_per_sm, const char *name)
+{
+    const int threads = 256, iters = 4096;
+    const int blocks = sms * blocks_per_sm;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int w = 0; w < 3; ++w) fp_pattern_kernel<MODE, K><<<blocks, threads>>>((float *)d_out, d_cyc, 1e-3f, iters);
+    CK(cudaDeviceSynchronize());
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(e0));
+        fp_pattern_kernel<MODE, K><<<blocks, threads>>>((float *)d_out, d_cyc, 1e-3f + rep * 1e-6f, iters);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best_ms) best_ms = ms;
+    }
+    const double per_thread = (double)iters * K * (MODE == 0 ? 3 : 6);
+    const double lane_ops = per_thread * threads * blocks;
+    printf("{\"op\": \"%s\", \"tera_lane_ops_per_s\": %.3f, \"ms\": %.4f, \"warps_per_sm\": %d}\n", name,
+           lane_ops / (best_ms * 1e-3) / 1e12, best_ms, blocks_per_sm * threads / 32);
+    fflush(stdout);
+}
+
 template <int OP> void run_all(int sms, uint32_t *d_out, long long *d_cyc, int bps)
 {
     if constexpr (OP < OP_COUNT) {
@@ -221,5 +300,9 @@ int main(int argc, char **argv)
     CK(cudaMalloc(&d_out, sizeof(uint32_t) * sms * bps * 256));
     CK(cudaMalloc(&d_cyc, sizeof(long long) * sms * bps));
     run_all<0>(sms, d_out, d_cyc, bps);
+    run_fp_pattern<0, 8>(sms, d_out, d_cyc, 2, "FFMA, three distinct source registers (16 warps/SM)");
+    run_fp_pattern<1, 8>(sms, d_out, d_cyc, 2, "PairHMM cell pattern K=8, 6 FP32 instr/cell (16 warps/SM)");
+    run_fp_pattern<1, 6>(sms, d_out, d_cyc, 2, "PairHMM cell pattern K=6, 6 FP32 instr/cell (16 warps/SM)");
+    run_fp_pattern<1, 8>(sms, d_out, d_cyc, 1, "PairHMM cell pattern K=8, 6 FP32 instr/cell (8 warps/SM)");
     return 0;
 }
