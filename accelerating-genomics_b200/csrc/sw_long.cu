@@ -18,6 +18,7 @@
 //     peer stores over NVLink (cudaDeviceEnablePeerAccess); no collective is involved, the final
 //     score is the max of the per-GPU maxima.
 #include <algorithm>
+#include <cstdlib>
 #include <thread>
 #include <vector>
 
@@ -29,7 +30,7 @@ namespace {
 
 constexpr int LONG_WARPS = 4;     // warps per CTA
 constexpr int LONG_RING = 64;
-constexpr int LONG_RB = 128;      // rows per published block (multiple of 32)
+constexpr int LONG_RB_DEFAULT = 32;   // rows per published block (multiple of 32)
 
 struct LongArgs {
     const uint8_t *a;         // columns owned by this GPU
@@ -42,6 +43,7 @@ struct LongArgs {
     int32_t *next_progress;   // &progress[0] of the next GPU (peer) or nullptr
     int32_t *best;            // running maximum (atomicMax)
     int32_t first_gpu;        // stripe 0 of this GPU is the true left edge of the matrix
+    int32_t rb;               // rows per published block (multiple of 32)
     SwScoring sc;
 };
 
@@ -55,7 +57,7 @@ __device__ __forceinline__ int32_t ld_acquire(const int32_t *p, bool sys)
     return v;
 }
 
-template <int K>
+template <int K, bool SHORT>
 __global__ void __launch_bounds__(LONG_WARPS * 32)
 sw_long_kernel(LongArgs g)
 {
@@ -73,8 +75,9 @@ sw_long_kernel(LongArgs g)
     const int32_t sub_match = g.sc.match - goe, sub_mis = g.sc.mismatch - goe;
     const int32_t lb = g.lb;
     const int n_stripes = (g.la + W - 1) / W;
+    const int LONG_RB = g.rb;
     const int n_blocks = (lb + LONG_RB - 1) / LONG_RB;
-    int32_t best = 0;
+    int32_t bestg = goe;          // running max of H + goe
 
     for (int st = warp; st < n_stripes; st += n_warps) {
         const int c0 = st * W + lane * K;
@@ -143,16 +146,37 @@ sw_long_kernel(LongArgs g)
                 int32_t gdiag = g_in_prev;
                 g_in_prev = g_in;
                 int32_t gleft = g_in;
+                if constexpr (SHORT) {
+                    // Short dependency chain: with T = max(F, diag + s, 0) (known from the previous row),
+                    //   E[j] = max(E[j-1] + ext, T[j-1] + goe)   (E[j-1] + ext >= E[j-1] + goe since go <= 0)
+                    //   H[j] = max(E[j], T[j])
+                    // so consecutive cells of a row are linked by ONE VIADDMNMX instead of three ALU ops,
+                    // at the price of one more ALU op per cell: pays when few warps share an SM.
+                    int32_t tg_prev = g_in;
 #pragma unroll
-                for (int j = 0; j < K; ++j) {
-                    const int32_t d = gdiag + ((acol[j] == rb) ? sub_match : sub_mis);
-                    e = __viaddmax_s32(e, ext, gleft);
-                    F[j] = __viaddmax_s32(F[j], ext, Gp[j]);
-                    const int32_t hcell = __vimax3_s32_relu(e, F[j], d);
-                    gdiag = Gp[j];
-                    gleft = hcell + goe;
-                    Gp[j] = gleft;
-                    best = max(best, hcell);
+                    for (int j = 0; j < K; ++j) {
+                        const int32_t d = gdiag + ((acol[j] == rb) ? sub_match : sub_mis);
+                        F[j] = __viaddmax_s32(F[j], ext, Gp[j]);
+                        const int32_t tg = __vimax_s32_relu(F[j], d) + goe;      // T[j] + goe
+                        e = __viaddmax_s32(e, ext, tg_prev);                       // E[i][j]
+                        gdiag = Gp[j];
+                        gleft = max(e + goe, tg);                                  // H[i][j] + goe
+                        Gp[j] = gleft;
+                        tg_prev = tg;
+                        bestg = max(bestg, gleft);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        const int32_t d = gdiag + ((acol[j] == rb) ? sub_match : sub_mis);
+                        e = __viaddmax_s32(e, ext, gleft);
+                        F[j] = __viaddmax_s32(F[j], ext, Gp[j]);
+                        const int32_t hcell = __vimax3_s32_relu(e, F[j], d);
+                        gdiag = Gp[j];
+                        gleft = hcell + goe;
+                        Gp[j] = gleft;
+                        bestg = max(bestg, gleft);
+                    }
                 }
                 g_out = gleft;
                 e_out = e;
@@ -174,42 +198,69 @@ sw_long_kernel(LongArgs g)
         __syncwarp();
     }
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, m));
+    for (int m = 16; m >= 1; m >>= 1) bestg = max(bestg, __shfl_xor_sync(0xffffffffu, bestg, m));
+    const int32_t best = bestg - goe;
     if (lane == 0 && best > 0) atomicMax(g.best, best);
 }
 
-template <int K> int long_launch(const LongArgs &args, int n_stripes, cudaStream_t st)
+template <int K, bool SHORT> int long_launch(const LongArgs &args, int n_stripes, cudaStream_t st)
 {
     int dev = 0, sms = 0, per_sm = 0;
     AGX_CUDA(cudaGetDevice(&dev));
     AGX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    AGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_long_kernel<K>, LONG_WARPS * 32, 0));
+    AGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_long_kernel<K, SHORT>, LONG_WARPS * 32, 0));
     if (per_sm < 1) return fail(AGX_ECUDA, "sw_long: kernel does not fit on an SM");
     int blocks = sms * per_sm;                        // all co-resident: required by the stripe wavefront
     const int want = (n_stripes + LONG_WARPS - 1) / LONG_WARPS;
     if (blocks > want) blocks = want;
     LongArgs a = args;
     void *params[] = {&a};
-    AGX_CUDA(cudaLaunchCooperativeKernel((const void *)sw_long_kernel<K>, dim3(blocks), dim3(LONG_WARPS * 32),
+    AGX_CUDA(cudaLaunchCooperativeKernel((const void *)sw_long_kernel<K, SHORT>, dim3(blocks), dim3(LONG_WARPS * 32),
                                          params, 0, st));
     count_launch();
     return AGX_OK;
 }
 
-int pick_k(int64_t la, int sms)
+int env_int(const char *name, int dflt)
 {
-    // widest stripe that still gives every resident warp slot (~16 per SM) a stripe
-    const int64_t slots = (int64_t)sms * 16;
-    if ((la + 255) / 256 >= slots) return 8;
-    if ((la + 127) / 128 >= slots) return 4;
+    const char *e = getenv(name);
+    return (e && atoi(e) > 0) ? atoi(e) : dflt;
+}
+
+// Stripe width.  The stripe wavefront costs (total stripes x hop + rows) steps, so stripes should be as
+// wide as the register file allows while every SM still gets a few of them.
+int pick_k(int64_t cols_per_gpu, int sms)
+{
+    const int forced = env_int("AGX_LONG_K", 0);
+    if (forced == 2 || forced == 4 || forced == 8 || forced == 16 || forced == 32) return forced;
+    for (int k : {32, 16, 8, 4}) {
+        const int64_t stripes = (cols_per_gpu + 32 * k - 1) / (32 * k);
+        if (stripes >= (int64_t)sms * 2) return k;       // at least two stripes per SM
+    }
     return 2;
 }
 
+int pick_rb() { return (env_int("AGX_LONG_RB", LONG_RB_DEFAULT) + 31) / 32 * 32; }
+
 int long_dispatch(int k, const LongArgs &args, cudaStream_t st)
 {
-    if (k == 8) return long_launch<8>(args, (args.la + 255) / 256, st);
-    if (k == 4) return long_launch<4>(args, (args.la + 127) / 128, st);
-    return long_launch<2>(args, (args.la + 63) / 64, st);
+    const int n = (args.la + 32 * k - 1) / (32 * k);
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // few warps per SM: latency-bound, take the short E chain; many: issue-bound, take the lean one
+    int short_chain = (n < sms * 4) ? 1 : 0;
+    if (const char *e = getenv("AGX_LONG_CHAIN")) short_chain = atoi(e) != 0;
+#define AGX_LONG_CASE(KK)                                                                     \
+    case KK: return short_chain ? long_launch<KK, true>(args, n, st) : long_launch<KK, false>(args, n, st);
+    switch (k) {
+        AGX_LONG_CASE(32)
+        AGX_LONG_CASE(16)
+        AGX_LONG_CASE(8)
+        AGX_LONG_CASE(4)
+    default: return short_chain ? long_launch<2, true>(args, n, st) : long_launch<2, false>(args, n, st);
+    }
+#undef AGX_LONG_CASE
 }
 
 }  // namespace
@@ -240,6 +291,7 @@ int sw_long_device(SwLongWorkspace &ws, const uint8_t *d_a, int64_t la, const ui
     args.next_bnd = nullptr; args.next_progress = nullptr;
     args.best = d_best;
     args.first_gpu = 1;
+    args.rb = pick_rb();
     args.sc = sc;
     AGX_CUDA(cudaMemsetAsync(args.progress, 0, (size_t)(n_stripes + 2) * sizeof(int32_t), st));
     AGX_CUDA(cudaMemsetAsync(d_best, 0, sizeof(int32_t), st));
@@ -260,7 +312,7 @@ int sw_long_host_multi(int n_dev, const int *dev, cudaStream_t *st, SwLongWorksp
 {
     if (la <= 0 || lb <= 0) { *score_out = 0; return AGX_OK; }
     if (la > INT32_MAX - 1024 || lb > INT32_MAX / 2 - 1024) return fail(AGX_ERANGE, "sw_long: sequence too long");
-    if (n_dev > 1 && la < (int64_t)n_dev * 4096) n_dev = 1;       // not worth splitting
+    if (n_dev > 1 && la < (int64_t)n_dev * 8192) n_dev = 1;       // not worth splitting
     // peer access between neighbours
     for (int gidx = 0; gidx + 1 < n_dev; ++gidx) {
         int can = 0;
@@ -275,9 +327,9 @@ int sw_long_host_multi(int n_dev, const int *dev, cudaStream_t *st, SwLongWorksp
     std::vector<LongArgs> args(n_dev);
     std::vector<int> ks(n_dev);
     std::vector<int64_t> c_lo(n_dev + 1);
-    // interior cuts sit on multiples of the widest stripe (256 columns): only the very last stripe of the
-    // matrix may carry padding columns, whose boundary nobody consumes
-    for (int gidx = 0; gidx <= n_dev; ++gidx) c_lo[gidx] = (gidx == n_dev) ? la : (la * gidx / n_dev) / 256 * 256;
+    // interior cuts sit on multiples of the widest stripe (32 lanes x 32 columns): only the very last
+    // stripe of the matrix may carry padding columns, whose boundary nobody consumes
+    for (int gidx = 0; gidx <= n_dev; ++gidx) c_lo[gidx] = (gidx == n_dev) ? la : (la * gidx / n_dev) / 1024 * 1024;
     // allocate + upload on every GPU, clear the flags, then make sure ALL GPUs are clear before any launch
     for (int gidx = 0; gidx < n_dev; ++gidx) {
         AGX_CUDA(cudaSetDevice(dev[gidx]));
@@ -311,6 +363,7 @@ int sw_long_host_multi(int n_dev, const int *dev, cudaStream_t *st, SwLongWorksp
         x.best = w.buf + 2 * lb + n_stripes + 2;
         x.next_bnd = nullptr; x.next_progress = nullptr;
         x.first_gpu = (gidx == 0);
+        x.rb = pick_rb();
         x.sc = sc;
         AGX_CUDA(cudaMemsetAsync(x.progress, 0, (size_t)(n_stripes + 3) * sizeof(int32_t), st[gidx]));
     }

@@ -63,6 +63,18 @@ def test_long_alignment_column_stripes_across_gpus(agx, multi, oracle_mod, n, re
     assert got.tolist() == want.tolist()
 
 
+@pytest.mark.parametrize("k", [4, 8, 16, 32])
+def test_long_alignment_every_stripe_width_across_gpus(agx, multi, oracle_mod, k, monkeypatch):
+    """Stripe widths 128..1024 columns: the GPU cut must sit on a stripe boundary for every one."""
+    cap, ngpu = multi
+    monkeypatch.setenv("AGX_LONG_K", str(k))
+    data = agx.synth.sw_long_pair(21000 + 37 * k, seed=k, related=True)
+    inp = agx.formats.parse_sw(data, line_buf=1 << 30)
+    got = cap.sw_score_flat(inp.buf, inp.off, inp.len)
+    want = oracle_mod.sw_scores_flat(inp.buf, inp.off, inp.len)
+    assert got.tolist() == want.tolist()
+
+
 def test_long_alignment_multi_gpu_equals_single_gpu_200kbp(agx, multi):
     cap, ngpu = multi
     data = agx.synth.sw_long_pair(200_000, seed=9, related=True)

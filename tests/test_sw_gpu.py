@@ -183,6 +183,16 @@ def test_long_alignment_whole_gpu_kernel(agx, gpu_lib, oracle_mod, n, related):
         assert got[0] > n // 2
 
 
+@pytest.mark.parametrize("k,chain", [(2, 0), (4, 1), (8, 0), (16, 1), (32, 0), (32, 1)])
+def test_long_alignment_stripe_widths_and_chain_forms(agx, gpu_lib, oracle_mod, k, chain, monkeypatch):
+    monkeypatch.setenv("AGX_LONG_K", str(k))
+    monkeypatch.setenv("AGX_LONG_CHAIN", str(chain))
+    monkeypatch.setenv("AGX_LONG_RB", "32" if k % 8 else "96")
+    inp = _long_pair(agx, 17000 + 111 * k, seed=k + chain, related=bool(chain))
+    got = gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len)
+    assert got.tolist() == oracle_mod.sw_scores_flat(inp.buf, inp.off, inp.len).tolist()
+
+
 def test_long_alignment_device_entry_point_and_mixed_batch(agx, gpu_lib, oracle_mod):
     import torch
     big = agx.synth.sw_long_pair(17000, seed=5)
