@@ -258,7 +258,7 @@ def run_reference_arm(args):
                     "cpu_baseline": ref.baseline_obj("hmm", hmm_val),
                     "e2e": {"value": hmm_val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -478,9 +478,26 @@ def run_sw_long(args):
             "gpu_launches": int(launches), "clocks": clk.summary()}
     if cpu:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    emit(line)
     cap.shutdown()
     return 0
+
+
+def bind_to_gpu_numa_node(index: int):
+    """Pin this rank to the CPUs next to its GPU (NVML's ideal affinity) before any host buffer is
+    touched, so pinned staging memory is allocated on the GPU's NUMA node."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        if cpus & allowed:
+            os.sched_setaffinity(0, cpus & allowed)
+    except Exception:
+        pass
 
 
 def run_gpu_arm(args):
@@ -494,6 +511,7 @@ def run_gpu_arm(args):
         raise SystemExit("bench.py needs a CUDA device (libagx has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    bind_to_gpu_numa_node(local_rank)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
@@ -549,13 +567,44 @@ def run_gpu_arm(args):
             if cpu_hmm is not None:
                 sub["cpu_baseline"] = cpu_hmm
             line["pairhmm"] = sub
-        print(json.dumps(line), flush=True)
+        emit(line)
     cap.shutdown()
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+class OneLineStdout:
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, for one) write to
+    fd 1 too, so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved fd."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line: str):
+        sys.stdout.flush()
+        os.write(self.saved, (line + "\n").encode())
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+OUT = None
+
+
+def emit(obj):
+    line = json.dumps(obj)
+    if OUT is not None:
+        OUT.emit(line)
+    else:
+        print(line, flush=True)
 
 
 def main():
@@ -573,11 +622,13 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "agx":
         args.warmup = max(args.warmup, 3)
-    if args.impl == "reference":
-        return run_reference_arm(args)
-    if args.workload == "sw_long":
-        return run_sw_long(args)
-    return run_gpu_arm(args)
+    global OUT
+    with OneLineStdout() as OUT:
+        if args.impl == "reference":
+            return run_reference_arm(args)
+        if args.workload == "sw_long":
+            return run_sw_long(args)
+        return run_gpu_arm(args)
 
 
 if __name__ == "__main__":
