@@ -158,8 +158,11 @@ __device__ __forceinline__ uint32_t base_code(uint32_t ch, bool &ok)
     return code;
 }
 
+#ifndef AGX_DUO_MINBLOCKS
+#define AGX_DUO_MINBLOCKS 5
+#endif
 template <int G, int K>
-__global__ void __launch_bounds__(DUO_THREADS)
+__global__ void __launch_bounds__(DUO_THREADS, AGX_DUO_MINBLOCKS)
 sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
               const int32_t *__restrict__ len, const int32_t *__restrict__ order_cls,
               int32_t n_in_class, DuoConst kc, int32_t *__restrict__ scores,

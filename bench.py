@@ -344,7 +344,10 @@ def bench_sw(agx, args, rank, local_rank, world, device):
                      "peak": peak / 1e12, "unit": "Tlaneop/s (INT32/DPX pipe)", "frac": achieved / peak,
                      "peak_source": peak_src, "ops_per_cell": SW_OPS_PER_CELL, "kernel_ms": k_ms,
                      "kernel_gcups": cells / (k_ms * 1e-3) / 1e9, "kernel_share_of_step": k_ms / ms,
-                     "traffic": None,
+                     "traffic": (peaks["sw_duo_dram_bytes_per_pair_150x150"] * n
+                                 if peaks and peaks.get("sw_duo_dram_bytes_per_pair_150x150") else None),
+                     "traffic_note": "DRAM bytes per launch from the committed ncu capture (profiles/r1d_sw_duo_ncu.txt), "
+                                     "scaled by pairs; the kernel is ALU-bound, HBM time for this is ~0.05 ms",
                      "loader": {"kernel": "sw_classify_kernel", "ms": float(np.mean(cls_ms)), "bound": "hbm"}},
         "gpu_launches": int(launches), "clocks": clk.summary(),
         "pairs_per_gpu": n, "cells_per_gpu": cells,
