@@ -22,7 +22,7 @@ LIB_PATH = Path(os.environ["AGX_LIB_PATH"]) if os.environ.get("AGX_LIB_PATH") el
 SYMBOLS = [
     "agx_init", "agx_init_devices", "agx_device_count", "agx_shutdown", "agx_last_error",
     "agx_version", "agx_launch_count", "agx_reset_launch_count", "agx_set_profiling", "agx_profile_ms",
-    "sw_score_batch", "sw_score_batch_flat", "sw_score_batch_device",
+    "sw_score_batch", "sw_score_batch_flat", "sw_score_batch_device", "sw_score_file_image",
     "pairhmm_forward_batch", "pairhmm_forward_batches_flat", "pairhmm_forward_batches_device",
     "agx_pairhmm_set_gatk_mode", "agx_pairhmm_set_force_fp64",
 ]
@@ -69,6 +69,10 @@ def load_library() -> C.CDLL:
         [C.c_int32] * 4 + [C.c_void_p]
     lib.sw_score_batch_device.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                           C.c_int64] + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p]
+    lib.sw_score_file_image.argtypes = [C.c_void_p, C.c_int64, C.c_int32] + [C.c_int32] * 4 + \
+        [C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int64),
+         C.POINTER(C.c_int32)]
+    lib.sw_score_file_image.restype = C.c_int
     lib.pairhmm_forward_batch.argtypes = [C.c_int32, pp, pp, pp, pp, pp, i32p, C.c_int32, pp, i32p, f64p]
     lib.pairhmm_forward_batches_flat.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                                  C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
@@ -190,6 +194,24 @@ def sw_score_batch(a: Sequence[bytes], b: Sequence[bytes],
                                          *[int(s) for s in scoring], out))
     del ka, kb
     return np.array(out[:n], dtype=np.int32)
+
+
+def sw_score_file_image(image, line_buf: int = 1000,
+                        scoring=(SW_MATCH, SW_MISMATCH, SW_GAP_OPEN, SW_GAP_EXTEND)):
+    """sw_score_file_image: the whole file image, chunked into fgets() lines on the GPU.
+    Returns (scores, header, dangling_bytes)."""
+    img = np.frombuffer(image, dtype=np.uint8) if isinstance(image, (bytes, bytearray)) else _as(image, np.uint8)
+    cap = max(1, img.size // 2 + 2)
+    out = np.empty(cap, dtype=np.int32)
+    n = C.c_int64(0)
+    header = C.c_int32(0)
+    d_off = C.c_int64(-1)
+    d_len = C.c_int32(0)
+    _check(load_library().sw_score_file_image(_ptr(img) if img.size else None, img.size, int(line_buf),
+                                              *[int(s) for s in scoring], _ptr(out), cap, C.byref(n),
+                                              C.byref(header), C.byref(d_off), C.byref(d_len)))
+    dangling = img[d_off.value:d_off.value + d_len.value].tobytes() if d_off.value >= 0 else b""
+    return out[:n.value].copy(), int(header.value), dangling
 
 
 def sw_score_device(device: int, d_seqs: int, seqs_bytes: int, d_off: int, d_len: int, n_pairs: int,

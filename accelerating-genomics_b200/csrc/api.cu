@@ -115,6 +115,7 @@ struct SwLane {
 struct DeviceCtx {
     int device = -1;
     cudaStream_t stream = nullptr;
+    SwParseWorkspace parse;
     SwLane lane[2];          // lane[0].st == stream
     SwWorkspace &sw = lane[0].ws;
     HmmWorkspace hmm;
@@ -564,6 +565,7 @@ void agx_shutdown(void)
             L.h_out.release();
         }
         if (c->lane[1].st) cudaStreamDestroy(c->lane[1].st);
+        sw_parse_workspace_free(c->parse);
         hmm_workspace_free(c->hmm);
         for (DevBuf *b : {&c->d_bytes, &c->d_a, &c->d_b, &c->d_c, &c->d_d, &c->d_e, &c->d_f, &c->d_out}) b->release();
         for (PinBuf *b : {&c->h_a, &c->h_b, &c->h_out}) b->release();
@@ -605,6 +607,70 @@ int sw_score_batch_flat(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *
 {
     return sw_flat_impl(seqs, seqs_bytes, off, len, n_pairs, SwScoring{match, mismatch, gap_open, gap_extend},
                         scores_out);
+}
+
+int sw_score_file_image(const uint8_t *image, int64_t image_bytes, int32_t line_buf, int32_t match,
+                        int32_t mismatch, int32_t gap_open, int32_t gap_extend, int32_t *scores_out,
+                        int64_t scores_cap, int64_t *n_pairs_out, int32_t *header_out, int64_t *dangling_off,
+                        int32_t *dangling_len)
+{
+    if (n_pairs_out) *n_pairs_out = 0;
+    if (header_out) *header_out = 0;
+    if (dangling_off) *dangling_off = -1;
+    if (dangling_len) *dangling_len = 0;
+    if (!image || image_bytes <= 0) return fail(AGX_EINVAL, "sw: empty file image");
+    if (line_buf < 2) return fail(AGX_EINVAL, "sw: line buffer must hold at least one character");
+    // the header is the first fgets() chunk (antidiagonalSmithWaterman.c:205-209)
+    const int64_t cap = line_buf - 1;
+    const int64_t lim = std::min<int64_t>(image_bytes, cap);
+    const void *nl = memchr(image, '\n', (size_t)lim);
+    const int64_t hlen = nl ? (const uint8_t *)nl - image + 1 : lim;
+    char tmp[32];
+    const size_t c = (size_t)std::min<int64_t>(hlen, (int64_t)sizeof tmp - 1);
+    memcpy(tmp, image, c);
+    tmp[c] = 0;
+    const int line_num = atoi(tmp);
+    if (header_out) *header_out = line_num;
+    const int64_t want_pairs = line_num > 0 ? ((int64_t)line_num + 1) / 2 : 0;
+    if (want_pairs == 0 || hlen >= image_bytes) return AGX_OK;
+    if (!scores_out) return fail(AGX_EINVAL, "sw: null argument");
+    int rc = require_init();
+    if (rc != AGX_OK) return rc;
+    DeviceCtx &ctx = *g_ctx[0];
+    AGX_CUDA(cudaSetDevice(ctx.device));
+    SwLane &L = ctx.lane[0];
+    cudaStream_t st = L.st;
+    if ((rc = L.bytes.reserve((size_t)image_bytes + 64)) != AGX_OK) return rc;
+    AGX_CUDA(cudaMemcpyAsync(L.bytes.p, image, (size_t)image_bytes, cudaMemcpyHostToDevice, st));
+    int64_t *d_off = nullptr;
+    int32_t *d_len = nullptr;
+    int64_t n_chunks = 0;
+    rc = sw_parse_device(ctx.parse, L.bytes.as<uint8_t>(), hlen, image_bytes, line_buf, 2 * want_pairs, &d_off, &d_len,
+                         &n_chunks, st);
+    if (rc != AGX_OK) return rc;
+    const int64_t n_pairs = std::min(want_pairs, n_chunks / 2);
+    if (n_pairs > scores_cap) return fail(AGX_ERANGE, "sw: scores_out holds " + std::to_string(scores_cap) +
+                                                          " scores, the file has " + std::to_string(n_pairs) + " pairs");
+    if (n_pairs > 0) {
+        if ((rc = L.out.reserve((size_t)n_pairs * sizeof(int32_t))) != AGX_OK) return rc;
+        rc = sw_run_device(L.ws, L.bytes.as<uint8_t>(), d_off, d_len, n_pairs,
+                           SwScoring{match, mismatch, gap_open, gap_extend}, L.out.as<int32_t>(), st);
+        if (rc != AGX_OK) return rc;
+        AGX_CUDA(cudaMemcpyAsync(scores_out, L.out.p, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
+    if (want_pairs > n_chunks / 2 && (n_chunks & 1)) {
+        // EOF in the middle of a pair: the reference echoes the dangling first line (:223-227)
+        int64_t o = 0;
+        int32_t l = 0;
+        AGX_CUDA(cudaMemcpyAsync(&o, d_off + n_chunks - 1, sizeof o, cudaMemcpyDeviceToHost, st));
+        AGX_CUDA(cudaMemcpyAsync(&l, d_len + n_chunks - 1, sizeof l, cudaMemcpyDeviceToHost, st));
+        AGX_CUDA(cudaStreamSynchronize(st));
+        if (dangling_off) *dangling_off = o;
+        if (dangling_len) *dangling_len = l;
+    }
+    AGX_CUDA(cudaStreamSynchronize(st));
+    if (n_pairs_out) *n_pairs_out = n_pairs;
+    return AGX_OK;
 }
 
 int sw_score_batch(const uint8_t *const *a, const int32_t *a_len, const uint8_t *const *b,

@@ -85,6 +85,18 @@ int sw_run_device(SwWorkspace &ws, const uint8_t *d_seqs, const int64_t *d_off, 
 int sw_workspace_reserve(SwWorkspace &ws, int64_t n_pairs);
 void sw_workspace_free(SwWorkspace &ws);
 
+// device-side fgets() chunking of a Smith-Waterman file image (sw_parse.cu)
+struct SwParseWorkspace {
+    void *buf = nullptr;      // tile counts / bases
+    int64_t cap = 0;
+    void *buf2 = nullptr;     // newline positions, chunks per line, chunk table
+    int64_t cap2 = 0;
+    int64_t *h_total = nullptr;
+};
+int sw_parse_device(SwParseWorkspace &ws, const uint8_t *d_img, int64_t begin, int64_t end, int32_t line_buf,
+                    int64_t max_chunks, int64_t **d_off, int32_t **d_len, int64_t *n_chunks_out, cudaStream_t st);
+void sw_parse_workspace_free(SwParseWorkspace &ws);
+
 // ---- PairHMM ------------------------------------------------------------------------------
 struct HmmWorkspace {
     int32_t *order = nullptr;     // [n_reads] read ids grouped by row class

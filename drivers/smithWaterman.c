@@ -11,8 +11,9 @@
  *     smithWaterman.cu:40);
  *   - one "Score: %d" per pair in file order (:348), the dangling first line of an incomplete last
  *     pair echoed (:223-227), then "elapsed %f" in seconds (:351-352).
- * The DP itself (:246-347) runs on the GPU(s) through sw_score_batch_flat(); AGX_NUM_GPUS=<n>
- * limits the devices used (default: all visible).  There is no CPU fallback.
+ * The file image is handed to sw_score_file_image(): the fgets() chunking and the DP (:246-347) both
+ * run on the GPU; the host only reads the file and prints.  AGX_NUM_GPUS=<n> limits the devices the
+ * library binds (default: all visible).  There is no CPU fallback.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -54,78 +55,47 @@ int main(int argc, char *argv[])
         printf("file is empty");
         return 1;
     }
-    long line_buf = 1000;
+    long line_buf = 1000;                         /* MAX_LINE_LENGTH, antidiagonalSmithWaterman.c:44 */
     const char *env = getenv("AGX_SW_LINE_BUF");
     if (env && atol(env) >= 2) line_buf = atol(env);
-    const size_t chunk_max = (size_t)line_buf - 1;
 
-    /* fgets() semantics over the image: up to chunk_max bytes, stopping after a '\n' */
-    size_t n_chunks = 0, chunk_cap = 1024;
-    int64_t *off = malloc(chunk_cap * sizeof *off);
-    int32_t *len = malloc(chunk_cap * sizeof *len);
-    size_t pos = 0;
-    int line_num = 0;
-    int have_header = 0;
-    while (pos < size) {
-        size_t lim = size - pos < chunk_max ? size - pos : chunk_max;
-        unsigned char *nl = memchr(img + pos, '\n', lim);
-        size_t l = nl ? (size_t)(nl - (img + pos)) + 1 : lim;
-        if (!have_header) {
-            char tmp[32];
-            size_t c = l < sizeof tmp - 1 ? l : sizeof tmp - 1;
-            memcpy(tmp, img + pos, c);
-            tmp[c] = 0;
-            line_num = atoi(tmp);
-            have_header = 1;
-        } else {
-            if (n_chunks == chunk_cap) {
-                chunk_cap *= 2;
-                off = realloc(off, chunk_cap * sizeof *off);
-                len = realloc(len, chunk_cap * sizeof *len);
-                if (!off || !len) { fprintf(stderr, "out of memory\n"); return 1; }
-            }
-            off[n_chunks] = (int64_t)pos;
-            len[n_chunks] = (int32_t)l;
-            n_chunks++;
-            /* the loop `for (i = 0; i < line_num; i += 2)` never reads more than this */
-            if (line_num > 0 && n_chunks >= (size_t)(line_num + 1) / 2 * 2) { pos += l; break; }
-            if (line_num <= 0) { pos += l; break; }
-        }
-        pos += l;
+    /* header = atoi(first fgets() chunk) (:205-210); printed before any GPU work, like the reference */
+    {
+        size_t lim = size < (size_t)line_buf - 1 ? size : (size_t)line_buf - 1;
+        unsigned char *nl = memchr(img, '\n', lim);
+        size_t l = nl ? (size_t)(nl - img) + 1 : lim;
+        char tmp[32];
+        size_t c = l < sizeof tmp - 1 ? l : sizeof tmp - 1;
+        memcpy(tmp, img, c);
+        tmp[c] = 0;
+        printf("line_num: %d\n", atoi(tmp));
     }
-    printf("line_num: %d\n", line_num);
     double iStart = seconds();
 
-    int64_t want_pairs = line_num > 0 ? ((int64_t)line_num + 1) / 2 : 0;
-    int64_t have_pairs = (int64_t)(n_chunks / 2);
-    int64_t n_pairs = want_pairs < have_pairs ? want_pairs : have_pairs;
-    int dangling = (want_pairs > have_pairs) && (n_chunks % 2 == 1);
-
-    if (n_pairs > 0) {
-        int n_gpus = 0;
-        env = getenv("AGX_NUM_GPUS");
-        if (env) n_gpus = atoi(env);
-        if (agx_init(n_gpus) != AGX_OK) {
-            fprintf(stderr, "Error: %s\n", agx_last_error());
-            exit(1);
-        }
-        int32_t *scores = malloc((size_t)n_pairs * sizeof *scores);
-        /* the reference's constants, antidiagonalSmithWaterman.c:40-43 */
-        int rc = sw_score_batch_flat(img, (int64_t)size, off, len, n_pairs, 1, -1, -3, -1, scores);
-        if (rc != AGX_OK) {
-            fprintf(stderr, "Error: code: %d, reason: %s\n", rc, agx_last_error());
-            exit(1);
-        }
-        for (int64_t p = 0; p < n_pairs; p++) printf("Score: %d\n", scores[p]);
-        free(scores);
+    int n_gpus = 0;
+    env = getenv("AGX_NUM_GPUS");
+    if (env) n_gpus = atoi(env);
+    int64_t score_cap = (int64_t)(size / 2 + 2), n_pairs = 0, dangling_off = -1;
+    int32_t header = 0, dangling_len = 0;
+    int32_t *scores = malloc((size_t)score_cap * sizeof *scores);
+    if (!scores) { fprintf(stderr, "out of memory\n"); return 1; }
+    /* the fgets() chunking (:216-227) and the DP (:246-347) both run on the GPU; the reference's
+       scoring constants are :40-43 */
+    int rc = agx_init(n_gpus);
+    if (rc == AGX_OK)
+        rc = sw_score_file_image(img, (int64_t)size, (int32_t)line_buf, 1, -1, -3, -1, scores, score_cap, &n_pairs,
+                                 &header, &dangling_off, &dangling_len);
+    if (rc != AGX_OK) {
+        fprintf(stderr, "Error: code: %d, reason: %s\n", rc, agx_last_error());
+        exit(1);
     }
-    if (dangling) fwrite(img + off[n_chunks - 1], 1, (size_t)len[n_chunks - 1], stdout);
+    for (int64_t p = 0; p < n_pairs; p++) printf("Score: %d\n", scores[p]);
+    if (dangling_off >= 0) fwrite(img + dangling_off, 1, (size_t)dangling_len, stdout);   /* :223-227 */
+    free(scores);
 
     double iElaps = seconds() - iStart;
     printf("elapsed %f\n", iElaps);
     agx_shutdown();
-    free(off);
-    free(len);
     free(img);
     return 0;
 }

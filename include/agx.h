@@ -99,6 +99,19 @@ int sw_score_batch_flat(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *
                         int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend,
                         int32_t *scores_out);
 
+/* Scores a whole generator.py-style FILE IMAGE; the fgets() chunking of
+ * antidiagonalSmithWaterman.c:201-227 is reproduced on the GPU (sw_parse.cu), so the caller builds no
+ * (offset, length) arrays: line 1 is atoi()'d into the number of LINES to consume (:209), every
+ * following sequence is one fgets(line_buf) chunk -- at most line_buf-1 bytes, '\n' kept -- and
+ * ceil(lines/2) pairs are scored (:216).  line_buf = 1000 is the reference's MAX_LINE_LENGTH (:44).
+ * *n_pairs_out = pairs scored (scores_out[0 .. n)), *header_out = atoi(line 1); when the file ends in
+ * the middle of a pair, *dangling_off / *dangling_len locate the first line of that pair (the
+ * reference echoes it, :223-227), else *dangling_off = -1.  Runs on the first configured GPU. */
+int sw_score_file_image(const uint8_t *image, int64_t image_bytes, int32_t line_buf,
+                        int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend,
+                        int32_t *scores_out, int64_t scores_cap, int64_t *n_pairs_out,
+                        int32_t *header_out, int64_t *dangling_off, int32_t *dangling_len);
+
 /* Device-resident variant for one GPU: every pointer is a device pointer on `device`
  * (a CUDA ordinal that was passed to agx_init*), work is enqueued on `stream`
  * (a cudaStream_t / CUstream cast to void*, NULL = the library's stream for that device).

@@ -228,3 +228,40 @@ def test_long_alignment_properties_100kbp(agx, gpu_lib):
     half = inp.len.copy()
     half[:] = 50_000
     assert int(gpu_lib.sw_score_flat(inp.buf, inp.off, half)[0]) <= s
+
+
+# ---------------------------------------------------------------- device-side file parser (sw_score_file_image)
+@pytest.mark.parametrize("name", SW_FILES + ["sw_5kbp"])
+def test_file_image_entry_point_matches_reference_stdout(agx, gpu_lib, name):
+    """The GPU-side fgets() chunker reproduces the reference's pairing, header and dangling-line rules."""
+    data = (GOLDEN / f"{name}.in").read_bytes()
+    if name == "sw_5kbp":
+        scores, header, dangling = gpu_lib.sw_score_file_image(data, line_buf=4200000)
+        assert scores.tolist() == ref_scores("sw_5kbp.ref_long.out")
+        return
+    scores, header, dangling = gpu_lib.sw_score_file_image(data)
+    text = (GOLDEN / f"{name}.ref.out").read_text()
+    assert scores.tolist() == ref_scores(f"{name}.ref.out")
+    assert f"line_num: {header}" in text
+    host = agx.formats.parse_sw(data)
+    assert dangling == host.dangling
+
+
+@pytest.mark.parametrize("line_buf", [2, 3, 17, 64, 1000, 5000])
+def test_file_image_chunking_equals_host_mirror(agx, gpu_lib, line_buf):
+    rng = np.random.default_rng(line_buf)
+    # ragged lines, some far longer than the buffer, empty lines, no trailing newline, odd line count
+    alpha = np.frombuffer(b"ACGT", np.uint8)
+    lines = [alpha[rng.integers(0, 4, size=int(n))].tobytes() for n in rng.integers(0, 3 * line_buf + 40, size=301)]
+    data = b"400\n" + b"\n".join(lines)
+    host = agx.formats.parse_sw(data, line_buf=line_buf)
+    scores, header, dangling = gpu_lib.sw_score_file_image(data, line_buf=line_buf)
+    assert header == host.header and dangling == host.dangling      # a tiny buffer splits the header line too
+    assert scores.tolist() == gpu_lib.sw_score_flat(host.buf, host.off, host.len).tolist()
+
+
+def test_file_image_config3_shape(agx, gpu_lib):
+    inp = agx.synth.sw_uniform_pairs(100_000, 150, seed=11)
+    scores, header, dangling = gpu_lib.sw_score_file_image(inp.buf)
+    assert header == 200_000 and dangling == b""
+    assert np.array_equal(scores, gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len))
