@@ -197,12 +197,15 @@ def sw_score_batch(a: Sequence[bytes], b: Sequence[bytes],
 
 
 def sw_score_file_image(image, line_buf: int = 1000,
-                        scoring=(SW_MATCH, SW_MISMATCH, SW_GAP_OPEN, SW_GAP_EXTEND)):
+                        scoring=(SW_MATCH, SW_MISMATCH, SW_GAP_OPEN, SW_GAP_EXTEND), max_pairs=None, out=None):
     """sw_score_file_image: the whole file image, chunked into fgets() lines on the GPU.
-    Returns (scores, header, dangling_bytes)."""
+    Returns (scores, header, dangling_bytes).  `out` (int32, optionally pinned) receives the scores;
+    by default a buffer for `max_pairs` (or the worst case image_bytes / 2) is allocated."""
     img = np.frombuffer(image, dtype=np.uint8) if isinstance(image, (bytes, bytearray)) else _as(image, np.uint8)
-    cap = max(1, img.size // 2 + 2)
-    out = np.empty(cap, dtype=np.int32)
+    if out is None:
+        cap = max(1, img.size // 2 + 2) if max_pairs is None else max(1, int(max_pairs))
+        out = np.empty(cap, dtype=np.int32)
+    cap = out.size
     n = C.c_int64(0)
     header = C.c_int32(0)
     d_off = C.c_int64(-1)

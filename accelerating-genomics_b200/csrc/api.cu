@@ -2,6 +2,8 @@
 // (pair / read sharding by cell count, one host thread + one stream per GPU, no collective) and the
 // host <-> device staging for the flat and pointer-array entry points.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -115,7 +117,11 @@ struct SwLane {
 struct DeviceCtx {
     int device = -1;
     cudaStream_t stream = nullptr;
-    SwParseWorkspace parse;
+    SwParseWorkspace parse[2];
+    cudaStream_t copy_stream = nullptr;    // uploads of sw_score_file_image
+    cudaStream_t prep_stream = nullptr;    // high priority: chunking + length classes of the next region
+    cudaEvent_t lane_done[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> seg_events;   // upload segments of sw_score_file_image
     SwLane lane[2];          // lane[0].st == stream
     SwWorkspace &sw = lane[0].ws;
     HmmWorkspace hmm;
@@ -161,6 +167,11 @@ int init_devices(const std::vector<int> &ids)
         AGX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->lane[0].st = c->stream;
         AGX_CUDA(cudaStreamCreateWithFlags(&c->lane[1].st, cudaStreamNonBlocking));
+        AGX_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        int prio_lo = 0, prio_hi = 0;
+        AGX_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        AGX_CUDA(cudaStreamCreateWithPriority(&c->prep_stream, cudaStreamNonBlocking, prio_hi));
+        for (cudaEvent_t &ev : c->lane_done) AGX_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         g_ctx.push_back(std::move(c));
     }
     return AGX_OK;
@@ -565,7 +576,12 @@ void agx_shutdown(void)
             L.h_out.release();
         }
         if (c->lane[1].st) cudaStreamDestroy(c->lane[1].st);
-        sw_parse_workspace_free(c->parse);
+        sw_parse_workspace_free(c->parse[0]);
+        sw_parse_workspace_free(c->parse[1]);
+        if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+        if (c->prep_stream) cudaStreamDestroy(c->prep_stream);
+        for (cudaEvent_t ev : c->lane_done) if (ev) cudaEventDestroy(ev);
+        for (cudaEvent_t ev : c->seg_events) cudaEventDestroy(ev);
         hmm_workspace_free(c->hmm);
         for (DevBuf *b : {&c->d_bytes, &c->d_a, &c->d_b, &c->d_c, &c->d_d, &c->d_e, &c->d_f, &c->d_out}) b->release();
         for (PinBuf *b : {&c->h_a, &c->h_b, &c->h_out}) b->release();
@@ -609,6 +625,11 @@ int sw_score_batch_flat(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *
                         scores_out);
 }
 
+// The image goes to the device in segments on a copy stream; line-aligned regions are chunked (sw_parse.cu)
+// and scored on the compute stream as soon as the segment that completes them has landed, so the DP
+// kernels run under the remaining host->device copies.  A region that ends in the middle of a pair hands
+// its last chunk to the next region (fgets() keeps no state besides the file position, so chunking may
+// restart at any chunk start).
 int sw_score_file_image(const uint8_t *image, int64_t image_bytes, int32_t line_buf, int32_t match,
                         int32_t mismatch, int32_t gap_open, int32_t gap_extend, int32_t *scores_out,
                         int64_t scores_cap, int64_t *n_pairs_out, int32_t *header_out, int64_t *dangling_off,
@@ -638,38 +659,143 @@ int sw_score_file_image(const uint8_t *image, int64_t image_bytes, int32_t line_
     if (rc != AGX_OK) return rc;
     DeviceCtx &ctx = *g_ctx[0];
     AGX_CUDA(cudaSetDevice(ctx.device));
-    SwLane &L = ctx.lane[0];
-    cudaStream_t st = L.st;
+    SwLane &L = ctx.lane[0];                 // owns the image and the scores on the device
+    cudaStream_t copy_st = ctx.copy_stream;
+    const SwScoring sc{match, mismatch, gap_open, gap_extend};
+
+    // every chunk holds at least one byte: an upper bound on the pairs this image can yield
+    const int64_t max_pairs = std::min<int64_t>(want_pairs, (image_bytes - hlen) / 2 + 1);
     if ((rc = L.bytes.reserve((size_t)image_bytes + 64)) != AGX_OK) return rc;
-    AGX_CUDA(cudaMemcpyAsync(L.bytes.p, image, (size_t)image_bytes, cudaMemcpyHostToDevice, st));
-    int64_t *d_off = nullptr;
-    int32_t *d_len = nullptr;
-    int64_t n_chunks = 0;
-    rc = sw_parse_device(ctx.parse, L.bytes.as<uint8_t>(), hlen, image_bytes, line_buf, 2 * want_pairs, &d_off, &d_len,
-                         &n_chunks, st);
-    if (rc != AGX_OK) return rc;
-    const int64_t n_pairs = std::min(want_pairs, n_chunks / 2);
-    if (n_pairs > scores_cap) return fail(AGX_ERANGE, "sw: scores_out holds " + std::to_string(scores_cap) +
-                                                          " scores, the file has " + std::to_string(n_pairs) + " pairs");
-    if (n_pairs > 0) {
-        if ((rc = L.out.reserve((size_t)n_pairs * sizeof(int32_t))) != AGX_OK) return rc;
-        rc = sw_run_device(L.ws, L.bytes.as<uint8_t>(), d_off, d_len, n_pairs,
-                           SwScoring{match, mismatch, gap_open, gap_extend}, L.out.as<int32_t>(), st);
-        if (rc != AGX_OK) return rc;
-        AGX_CUDA(cudaMemcpyAsync(scores_out, L.out.p, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if ((rc = L.out.reserve((size_t)max_pairs * sizeof(int32_t))) != AGX_OK) return rc;
+
+    // ---- upload in segments, one event per segment ------------------------------------------------
+    // Every region costs the host three stream round trips (newline count, chunk count, length-class
+    // counts: ~0.3 ms in all), so regions must be few and none shorter than the ~16 MiB that arrive in
+    // that time; what is left to do when the last byte lands is one region, so the last ones are short:
+    // eighths of the image first, then half of what is left each time.
+    std::vector<int64_t> seg_end;
+    {
+        const int64_t floor_sz = (int64_t)16 << 20;
+        int64_t fixed = 0;
+        if (const char *e = getenv("AGX_SW_IMAGE_SEGMENT")) fixed = atoll(e);   // tuning knob: bytes per segment
+        for (int64_t pos = 0; pos < image_bytes;) {
+            const int64_t left = image_bytes - pos;
+            int64_t sz = fixed > 0 ? fixed : std::max(floor_sz, std::min(image_bytes / 8, left / 2));
+            if (left - sz < floor_sz / 2) sz = left;
+            pos += sz;
+            seg_end.push_back(pos);
+        }
     }
-    if (want_pairs > n_chunks / 2 && (n_chunks & 1)) {
-        // EOF in the middle of a pair: the reference echoes the dangling first line (:223-227)
-        int64_t o = 0;
-        int32_t l = 0;
-        AGX_CUDA(cudaMemcpyAsync(&o, d_off + n_chunks - 1, sizeof o, cudaMemcpyDeviceToHost, st));
-        AGX_CUDA(cudaMemcpyAsync(&l, d_len + n_chunks - 1, sizeof l, cudaMemcpyDeviceToHost, st));
-        AGX_CUDA(cudaStreamSynchronize(st));
-        if (dangling_off) *dangling_off = o;
-        if (dangling_len) *dangling_len = l;
+    const int64_t n_seg = (int64_t)seg_end.size();
+    while ((int64_t)ctx.seg_events.size() < n_seg) {
+        cudaEvent_t ev;
+        AGX_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx.seg_events.push_back(ev);
     }
+    // pinned image: the copies are truly asynchronous, queue them all; pageable image: cudaMemcpyAsync
+    // stages through the driver and blocks the host, so stay one segment ahead of the region being scored
+    cudaPointerAttributes img_attr;
+    const bool img_pinned = cudaPointerGetAttributes(&img_attr, image) == cudaSuccess && img_attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    int64_t queued = 0;
+    auto upload_through = [&](int64_t k_last) -> int {
+        for (; queued <= k_last && queued < n_seg; ++queued) {
+            const int64_t b = queued ? seg_end[queued - 1] : 0, e = seg_end[queued];
+            AGX_CUDA(cudaMemcpyAsync(L.bytes.as<uint8_t>() + b, image + b, (size_t)(e - b), cudaMemcpyHostToDevice, copy_st));
+            AGX_CUDA(cudaEventRecord(ctx.seg_events[queued], copy_st));
+        }
+        return AGX_OK;
+    };
+    if ((rc = upload_through(img_pinned ? n_seg - 1 : 0)) != AGX_OK) return rc;
+
+    // ---- chunk + score region by region, alternating between the two lanes ------------------------
+    // (a lane = stream + workspaces; while the host waits for region k+1's chunk counts on one lane, the
+    // DP kernels of region k keep the GPU busy on the other)
+    int64_t begin = hlen, remaining = 2 * want_pairs, pairs_done = 0;
+    int64_t n_chunks = 0, last_off = -1;
+    int32_t last_len = 0;
+    bool tail_odd = false;
+    int64_t region = 0;
+    const bool trace = getenv("AGX_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto now_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+    for (int64_t k = 0; k < n_seg && remaining > 0; ++k) {
+        if ((rc = upload_through(k + 1)) != AGX_OK) break;
+        const int64_t avail = seg_end[k];
+        int64_t end = avail;
+        if (k + 1 < n_seg) {
+            // the region ends after the last newline that has landed
+            const void *r = avail > begin ? memrchr(image + begin, '\n', (size_t)(avail - begin)) : nullptr;
+            if (!r) continue;                                    // one line spans this whole segment
+            end = (const uint8_t *)r - image + 1;
+        }
+        if (end <= begin) continue;
+        const int li = (int)(region++ & 1);
+        cudaStream_t st = ctx.lane[li].st, prep = ctx.prep_stream;
+        // chunking and the length-class pass run on the high-priority stream, so they start when the
+        // segment lands instead of queueing behind the other lane's DP blocks; the lane's buffers are
+        // free once its previous region (two regions back) has been scored
+        AGX_CUDA(cudaStreamWaitEvent(prep, ctx.seg_events[k], 0));
+        if (region > 2) AGX_CUDA(cudaStreamWaitEvent(prep, ctx.lane_done[li], 0));
+        int64_t *d_off = nullptr;
+        int32_t *d_len = nullptr;
+        const double t_p0 = trace ? now_ms() : 0;
+        rc = sw_parse_device(ctx.parse[li], L.bytes.as<uint8_t>(), begin, end, line_buf, remaining, image[end - 1],
+                             &d_off, &d_len, &n_chunks, &last_off, &last_len, prep);
+        if (rc != AGX_OK) break;
+        const double t_p1 = trace ? now_ms() : 0;
+        const int64_t m = n_chunks / 2;
+        if (pairs_done + m > scores_cap) {
+            rc = fail(AGX_ERANGE, "sw: scores_out holds " + std::to_string(scores_cap) + " scores, the file has more pairs");
+            break;
+        }
+        if (m > 0) {
+            rc = sw_run_device(ctx.lane[li].ws, L.bytes.as<uint8_t>(), d_off, d_len, m, sc,
+                               L.out.as<int32_t>() + pairs_done, st, prep);
+            if (rc != AGX_OK) break;
+        }
+        AGX_CUDA(cudaEventRecord(ctx.lane_done[li], st));
+        if (trace)
+            fprintf(stderr, "[agx] region %lld seg %lld bytes [%lld, %lld) lane %d: parse %.3f -> %.3f ms, scored %lld pairs by %.3f ms\n",
+                    (long long)region - 1, (long long)k, (long long)begin, (long long)end, li, t_p0, t_p1, (long long)m, now_ms());
+        pairs_done += m;
+        remaining -= 2 * m;
+        tail_odd = (n_chunks & 1) != 0;
+        // an unpaired last chunk is read again as the first chunk of the next region
+        begin = tail_odd ? last_off : end;
+    }
+    cudaStream_t st = ctx.lane[0].st;
+    if (rc != AGX_OK) {
+        cudaStreamSynchronize(copy_st);
+        cudaStreamSynchronize(ctx.prep_stream);
+        cudaStreamSynchronize(ctx.lane[1].st);
+        cudaStreamSynchronize(st);
+        return rc;
+    }
+    AGX_CUDA(cudaStreamSynchronize(ctx.lane[1].st));
+    if (pairs_done > 0) {
+        cudaPointerAttributes attr;
+        const bool pinned = cudaPointerGetAttributes(&attr, scores_out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (pinned) {
+            AGX_CUDA(cudaMemcpyAsync(scores_out, L.out.p, (size_t)pairs_done * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            AGX_CUDA(cudaStreamSynchronize(st));
+        } else {
+            if ((rc = L.h_out.reserve((size_t)pairs_done * sizeof(int32_t))) != AGX_OK) return rc;
+            AGX_CUDA(cudaMemcpyAsync(L.h_out.p, L.out.p, (size_t)pairs_done * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            AGX_CUDA(cudaStreamSynchronize(st));
+            memcpy(scores_out, L.h_out.p, (size_t)pairs_done * sizeof(int32_t));
+        }
+    }
+    AGX_CUDA(cudaStreamSynchronize(copy_st));
     AGX_CUDA(cudaStreamSynchronize(st));
-    if (n_pairs_out) *n_pairs_out = n_pairs;
+    if (trace) fprintf(stderr, "[agx] file image done at %.3f ms\n", now_ms());
+    if (remaining > 0 && tail_odd) {
+        // EOF in the middle of a pair: the reference echoes the dangling first line (:223-227)
+        if (dangling_off) *dangling_off = last_off;
+        if (dangling_len) *dangling_len = last_len;
+    }
+    if (n_pairs_out) *n_pairs_out = pairs_done;
     return AGX_OK;
 }
 

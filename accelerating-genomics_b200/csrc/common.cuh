@@ -79,9 +79,11 @@ struct SwWorkspace {
     SwLongWorkspace lng;
 };
 
-// Enqueue the whole SW path for one device-resident batch on `st`.
+// Enqueue the whole SW path for one device-resident batch on `st`.  With prep_st (a high-priority
+// stream) the length-class pass runs there, so it is not queued behind DP kernels of another batch; the
+// caller then guarantees that `ws` and the inputs are no longer in use by earlier work on `st`.
 int sw_run_device(SwWorkspace &ws, const uint8_t *d_seqs, const int64_t *d_off, const int32_t *d_len,
-                  int64_t n_pairs, SwScoring sc, int32_t *d_scores, cudaStream_t st);
+                  int64_t n_pairs, SwScoring sc, int32_t *d_scores, cudaStream_t st, cudaStream_t prep_st = nullptr);
 int sw_workspace_reserve(SwWorkspace &ws, int64_t n_pairs);
 void sw_workspace_free(SwWorkspace &ws);
 
@@ -94,7 +96,8 @@ struct SwParseWorkspace {
     int64_t *h_total = nullptr;
 };
 int sw_parse_device(SwParseWorkspace &ws, const uint8_t *d_img, int64_t begin, int64_t end, int32_t line_buf,
-                    int64_t max_chunks, int64_t **d_off, int32_t **d_len, int64_t *n_chunks_out, cudaStream_t st);
+                    int64_t max_chunks, int last_byte, int64_t **d_off, int32_t **d_len, int64_t *n_chunks_out,
+                    int64_t *last_off, int32_t *last_len, cudaStream_t st);
 void sw_parse_workspace_free(SwParseWorkspace &ws);
 
 // ---- PairHMM ------------------------------------------------------------------------------

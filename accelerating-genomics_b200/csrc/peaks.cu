@@ -11,6 +11,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #define CK(x)                                                                      \
     do {                                                                           \
@@ -30,7 +31,8 @@ enum Op {
     OP_FFMA, OP_FMUL, OP_FADD, OP_FSEL,
     OP_MIX_DPX_IMAD, OP_MIX_DPX_FFMA, OP_MIX_FFMA_SEL, OP_SWCELL, OP_SHFL,
     OP_MIX_VIADD_VIADDMNMX, OP_MIX_VIADDMNMX_VIMNMX3, OP_MIX_PRMT_VIADDMNMX, OP_MIX_VIADD_PRMT, OP_MIX_VIADD_IMAD,
-    OP_MIX_VIMNMX3_IMAD, OP_MIX_PRMT_IMAD, OP_MIX_LOP3_VIADDMNMX, OP_MIX_VIADD_FFMA, OP_SWCELL_FULL, OP_COUNT
+    OP_MIX_VIMNMX3_IMAD, OP_MIX_PRMT_IMAD, OP_MIX_LOP3_VIADDMNMX, OP_MIX_VIADD_FFMA, OP_SWCELL_FULL,
+    OP_HMNMX2, OP_MIX_HMNMX2_VIADDMNMX, OP_MIX_HMNMX2_VIADD, OP_COUNT
 };
 static const char *op_name[OP_COUNT] = {
     "VIADDMNMX.S16x2", "VIMNMX3.S16x2.RELU", "VIADD.16x2", "VIMNMX.S16x2", "PRMT",
@@ -40,10 +42,11 @@ static const char *op_name[OP_COUNT] = {
     "SW s16x2 cell w/o PRMT (6 ops)", "SHFL.UP",
     "mix VIADD.16x2 : VIADDMNMX.S16x2", "mix VIADDMNMX.S16x2 : VIMNMX3.S16x2", "mix PRMT : VIADDMNMX.S16x2",
     "mix VIADD.16x2 : PRMT", "mix VIADD.16x2 : IMAD", "mix VIMNMX3.S16x2 : IMAD", "mix PRMT : IMAD",
-    "mix LOP3 : VIADDMNMX.S16x2", "mix VIADD.16x2 : FFMA", "SW s16x2 cell with PRMT (7 ops)"};
+    "mix LOP3 : VIADDMNMX.S16x2", "mix VIADD.16x2 : FFMA", "SW s16x2 cell with PRMT (7 ops)",
+    "HMNMX2 (max.f16x2)", "mix HMNMX2 : VIADDMNMX.S16x2", "mix HMNMX2 : VIADD.16x2"};
 // lane-ops counted per chain step
 static const double op_count[OP_COUNT] = {1, 2, 1, 2, 1, 1, 2, 1, 1, 1, 1, 1, 1, 2, 2, 2, 5, 6, 1,
-                                              2, 2, 2, 2, 2, 2, 2, 2, 2, 7};
+                                              2, 2, 2, 2, 2, 2, 2, 2, 2, 7, 2, 2, 2};
 
 __device__ __forceinline__ void ffma(uint32_t &x, uint32_t a, uint32_t b)
 {
@@ -120,6 +123,17 @@ __device__ __forceinline__ void step(uint32_t &x, uint32_t &y, uint32_t a, uint3
         asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x) : "r"(a), "r"(b));
         y = __viaddmax_s16x2(y, a, b);
     } else if constexpr (OP == OP_MIX_VIADD_FFMA) { x = __vadd2(x, a); ffma(y, a, b); }
+    else if constexpr (OP == OP_HMNMX2) {
+        // operands change every step, so ptxas cannot fold max(max(x, a), a)
+        asm volatile("max.f16x2 %0, %0, %1;" : "+r"(x) : "r"(y));
+        asm volatile("min.f16x2 %0, %0, %1;" : "+r"(y) : "r"(x));
+    } else if constexpr (OP == OP_MIX_HMNMX2_VIADDMNMX) {
+        y = __viaddmax_s16x2(y, a, b);
+        asm volatile("max.f16x2 %0, %0, %1;" : "+r"(x) : "r"(y));
+    } else if constexpr (OP == OP_MIX_HMNMX2_VIADD) {
+        y = __vadd2(y, a);
+        asm volatile("max.f16x2 %0, %0, %1;" : "+r"(x) : "r"(y));
+    }
     else if constexpr (OP == OP_SWCELL_FULL) {
         uint32_t t;
         asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(x), "r"(b), "r"(c));
@@ -277,6 +291,289 @@ template <int MODE, int K> void run_fp_pattern(int sms, uint32_t *d_out, long lo
     fflush(stdout);
 }
 
+
+// ---- packed FP32 (sm_100a FFMA2 / FMUL2 / FADD2 = PTX fma.rn.f32x2 ...) ---------------------------
+// One instruction, two FP32 lanes per thread.  Questions answered here: does the packed form raise
+// the FP32 lane throughput, and does it free issue slots for the other pipes?
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
+{
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b),
+                       rc = *reinterpret_cast<unsigned long long *>(&c), rd;
+    asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b)
+{
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b), rd;
+    asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+
+// MODE 0: FFMA2 only; 1: FFMA2 with a scalar (broadcast) multiplier; 2: 1 FFMA2 : 1 LOP3;
+// 3: 1 FFMA2 : 1 FFMA; 4: 1 FFMA2 : 1 SHFL.UP (per 4); 5: 1 FFMA2 : 2 LOP3
+template <int MODE>
+__global__ void __launch_bounds__(256) fp2_kernel(float *out, long long *cycles, float seed, int iters)
+{
+    float2 x[NCHAIN];
+    uint32_t y[NCHAIN];
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < NCHAIN; ++i) { x[i] = make_float2(seed * (tid + i), seed + i); y[i] = tid * 7 + i; }
+    const float2 a = make_float2(1.f + seed, 1.f - seed), b = make_float2(seed, -seed);
+    const float sc = 1.f + 2 * seed;
+    const uint32_t ia = __float_as_uint(seed) | 0x10001u, ib = __float_as_uint(seed) ^ 0x3f800000u;
+    __syncthreads();
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+            for (int i = 0; i < NCHAIN; ++i) {
+                if constexpr (MODE == 1) x[i] = ffma2(x[i], make_float2(sc, sc), b);
+                else x[i] = ffma2(x[i], a, b);
+                if constexpr (MODE == 2 || MODE == 5)
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(y[i]) : "r"(ia), "r"(ib));
+                if constexpr (MODE == 5)
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(y[i]) : "r"(ib), "r"(ia));
+                if constexpr (MODE == 3) ffma(y[i], ia, ib);
+                if constexpr (MODE == 4) { if ((i & 3) == 0) y[i] = __shfl_up_sync(0xffffffffu, y[i], 1); }
+            }
+    }
+    const long long t1 = clock64();
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCHAIN; ++i) acc += x[i].x + x[i].y + __uint_as_float(y[i]);
+    out[tid] = acc;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int MODE> void run_fp2(int sms, uint32_t *d_out, long long *d_cyc, int blocks_per_sm, const char *name,
+                                 double fp_lane_ops, double other_ops)
+{
+    const int threads = 256, iters = 2048;
+    const int blocks = sms * blocks_per_sm;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int w = 0; w < 3; ++w) fp2_kernel<MODE><<<blocks, threads>>>((float *)d_out, d_cyc, 1e-3f, iters);
+    CK(cudaDeviceSynchronize());
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(e0));
+        fp2_kernel<MODE><<<blocks, threads>>>((float *)d_out, d_cyc, 1e-3f + rep * 1e-6f, iters);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best_ms) best_ms = ms;
+    }
+    const double steps = (double)iters * UNROLL * NCHAIN * threads * blocks;
+    printf("{\"op\": \"%s\", \"fp32_tera_lane_ops_per_s\": %.3f, \"other_tera_lane_ops_per_s\": %.3f, "
+           "\"tera_warp_instr_x32_per_s\": %.3f, \"ms\": %.4f, \"warps_per_sm\": %d}\n",
+           name, steps * fp_lane_ops / (best_ms * 1e-3) / 1e12, steps * other_ops / (best_ms * 1e-3) / 1e12,
+           steps * (1 + other_ops) / (best_ms * 1e-3) / 1e12, best_ms, blocks_per_sm * threads / 32);
+    fflush(stdout);
+}
+
+// PairHMM cell with two haplotype columns per lane packed in f32x2 (per-row coefficients are scalars,
+// broadcast by FFMA2's .F32 operand form): 5 packed instructions + 0 unpacked per 2 cells when the prior
+// is already a pair, MODE 1: prior multiply unpacked (2 FMUL) as in a per-symbol table lookup
+template <int MODE, int K>
+__global__ void __launch_bounds__(256) fp2_pattern_kernel(float *out, long long *cycles, float seed, int iters)
+{
+    float ca[K], cbx[K], cby[K], ccx[K], cg[K];
+    float2 pr[K], M[K], X[K], Y[K];
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        ca[j] = 0.9f + seed * (j + 1); cbx[j] = 1e-4f * (j + 1) + seed; cby[j] = 2e-4f * (j + 2) + seed;
+        ccx[j] = 0.1f + seed * j; cg[j] = 0.1f + seed * (j + 3); pr[j] = make_float2(0.99f - seed * j, 0.01f + seed * j);
+        M[j] = make_float2(seed * tid + j, seed); X[j] = make_float2(seed + j, seed * 2); Y[j] = make_float2(1.f + seed * j, 1.f);
+    }
+    float2 upM0 = make_float2(seed, seed), upX0 = upM0, dM0 = upM0, dX0 = upM0, dY0 = upM0;
+    __syncthreads();
+    const long long t0 = clock64();
+#pragma unroll 2
+    for (int it = 0; it < iters; ++it) {
+        float2 upM = upM0, upX = upX0, dM = dM0, dX = dX0, dY = dY0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const float2 oM = M[j], oX = X[j], oY = Y[j];
+            float2 vv = fmul2(make_float2(cby[j], cby[j]), dY);
+            vv = ffma2(make_float2(cbx[j], cbx[j]), dX, vv);
+            vv = ffma2(make_float2(ca[j], ca[j]), dM, vv);
+            float2 mn;
+            if constexpr (MODE == 0) mn = fmul2(pr[j], vv);
+            else { mn.x = pr[j].x * vv.x; mn.y = pr[j].y * vv.y; }
+            const float2 xn = ffma2(make_float2(ccx[j], ccx[j]), upX, upM);
+            const float2 yn = ffma2(make_float2(cg[j], cg[j]), oY, oM);
+            dM = oM; dX = oX; dY = oY;
+            upM = mn; upX = xn;
+            M[j] = mn; X[j] = xn; Y[j] = yn;
+        }
+        upM0 = M[K - 1]; upX0 = X[K - 1]; dM0 = upM0; dX0 = upX0; dY0 = Y[K - 1];
+    }
+    const long long t1 = clock64();
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc += M[j].x + X[j].x + Y[j].x + M[j].y + X[j].y + Y[j].y;
+    out[tid] = acc;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int MODE, int K> void run_fp2_pattern(int sms, uint32_t *d_out, long long *d_cyc, int blocks_per_sm, const char *name)
+{
+    const int threads = 256, iters = 4096;
+    const int blocks = sms * blocks_per_sm;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int w = 0; w < 3; ++w) fp2_pattern_kernel<MODE, K><<<blocks, threads>>>((float *)d_out, d_cyc, 1e-3f, iters);
+    CK(cudaDeviceSynchronize());
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(e0));
+        fp2_pattern_kernel<MODE, K><<<blocks, threads>>>((float *)d_out, d_cyc, 1e-3f + rep * 1e-6f, iters);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best_ms) best_ms = ms;
+    }
+    const double cells = (double)iters * K * 2 * threads * blocks;
+    printf("{\"op\": \"%s\", \"tera_cells_per_s\": %.3f, \"fp32_tera_lane_ops_per_s\": %.3f, \"ms\": %.4f, \"warps_per_sm\": %d}\n",
+           name, cells / (best_ms * 1e-3) / 1e12, cells * 6 / (best_ms * 1e-3) / 1e12, best_ms, blocks_per_sm * threads / 32);
+    fflush(stdout);
+}
+
+
+// ---- the whole inner loop of the PairHMM stream kernel, not just its FP32 part ----------------------
+// One warp per block as in hmm_stream_kernel: per step a symbol prefetch (LDG.U8), the prior lookup
+// (LDS.128 from a per-warp table), the three boundary shuffles, the lane-0 selects, K cells, the running
+// sum and the haplotype counter.  PACKED = 0: one read per warp, scalar FP32 (what ships today);
+// PACKED = 1: two reads per warp, every FP32 instruction in its f32x2 form (FFMA2 / FMUL2).
+template <int PACKED, int K>
+__global__ void __launch_bounds__(32) hmm_loop_kernel(float *out, const uint8_t *codes, float seed, int steps)
+{
+    constexpr int V = PACKED ? 2 : 1;
+    constexpr int CH = (K * V + 3) / 4;
+    __shared__ float4 tab[6][CH][32];
+    const int t = threadIdx.x;
+    for (int sgn = 0; sgn < 6; ++sgn)
+        for (int c = 0; c < CH; ++c) tab[sgn][c][t] = make_float4(0.9f + seed * sgn, 0.01f + seed * c, 0.9f, 0.02f + seed * t);
+    __syncwarp();
+    float2 ca[K], cbx[K], cby[K], ccx[K], cg[K], M[K], X[K], Y[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        // coefficients come from memory so that they have to live in registers, as in the real kernel
+        const float2 *cf = reinterpret_cast<const float2 *>(out) + (size_t)(blockIdx.x * 32 + t) * 0 + j * 5;
+        ca[j] = cf[0]; cbx[j] = cf[1]; cby[j] = cf[2]; ccx[j] = cf[3]; cg[j] = cf[4];
+        M[j] = make_float2(seed * t + j, seed); X[j] = make_float2(seed + j, seed * 2); Y[j] = make_float2(1.f + seed * j, 1.f);
+    }
+    float2 pdM = make_float2(0.f, 0.f), pdX = pdM, pdY = pdM, bM = pdM, bX = pdM, bY = pdM, acc = pdM;
+    const float2 qi_last = make_float2(0.5f + seed, 0.5f - seed);
+    const float init = 1.f + seed;
+    const uint8_t *cp = codes + (blockIdx.x & 1023) * 64;
+    uint32_t code_next = *cp;
+    int rem = steps + 5;
+    const float4 *tab_lane = &tab[0][0][t];
+    const bool lane0 = (t == 0);
+#pragma unroll 2
+    for (int s = 0; s < steps; ++s) {
+        if (rem == 0) { rem = steps; acc = make_float2(0.f, 0.f); cp = codes; }
+        const uint32_t code = code_next;
+        cp += 1;
+        code_next = *cp;
+        float4 pr4[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) pr4[c] = tab_lane[code * (CH * 32) + c * 32];
+        float2 upM, upX, upY;
+        upM.x = __shfl_up_sync(0xffffffffu, bM.x, 1); upX.x = __shfl_up_sync(0xffffffffu, bX.x, 1); upY.x = __shfl_up_sync(0xffffffffu, bY.x, 1);
+        if (PACKED) { upM.y = __shfl_up_sync(0xffffffffu, bM.y, 1); upX.y = __shfl_up_sync(0xffffffffu, bX.y, 1); upY.y = __shfl_up_sync(0xffffffffu, bY.y, 1); }
+        else { upM.y = upX.y = upY.y = 0.f; }
+        if (lane0) { upM = make_float2(0.f, 0.f); upX = upM; upY = make_float2(init, init); }
+        float2 dM = pdM, dX = pdX, dY = pdY;
+        pdM = upM; pdX = upX; pdY = upY;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const float2 oM = M[j], oX = X[j], oY = Y[j];
+            float2 mn, xn, yn;
+            if (PACKED) {
+                const float4 p4 = pr4[j / 2];
+                const float2 pr = (j & 1) ? make_float2(p4.z, p4.w) : make_float2(p4.x, p4.y);
+                float2 vv = fmul2(cby[j], dY);
+                vv = ffma2(cbx[j], dX, vv);
+                vv = ffma2(ca[j], dM, vv);
+                mn = fmul2(pr, vv);
+                xn = ffma2(ccx[j], upX, upM);
+                yn = ffma2(cg[j], oY, oM);
+            } else {
+                const float4 p4 = pr4[j / 4];
+                const float pr = (j % 4 == 0) ? p4.x : (j % 4 == 1) ? p4.y : (j % 4 == 2) ? p4.z : p4.w;
+                float vv = cby[j].x * dY.x;
+                vv = fmaf(cbx[j].x, dX.x, vv);
+                vv = fmaf(ca[j].x, dM.x, vv);
+                mn.x = pr * vv; mn.y = 0.f;
+                xn.x = fmaf(ccx[j].x, upX.x, upM.x); xn.y = 0.f;
+                yn.x = fmaf(cg[j].x, oY.x, oM.x); yn.y = 0.f;
+            }
+            dM = oM; dX = oX; dY = oY;
+            upM = mn; upX = xn;
+            M[j] = mn; X[j] = xn; Y[j] = yn;
+        }
+        bM = M[K - 1]; bX = X[K - 1]; bY = Y[K - 1];
+        if (PACKED) acc = ffma2(qi_last, bX, ffma2(make_float2(1.f, 1.f), bM, acc));
+        else acc.x += fmaf(qi_last.x, bX.x, bM.x);
+        --rem;
+    }
+    float r = acc.x + acc.y;
+#pragma unroll
+    for (int j = 0; j < K; ++j) r += M[j].x + M[j].y + Y[j].x + Y[j].y;
+    out[blockIdx.x * 32 + t] = r;
+}
+
+template <int PACKED, int K> void run_hmm_loop(int sms, int warps_per_sm, const char *name)
+{
+    const int blocks = sms * warps_per_sm, steps = 20000;
+    float *d_out;
+    uint8_t *d_codes;
+    CK(cudaMalloc(&d_out, sizeof(float) * blocks * 32));
+    CK(cudaMalloc(&d_codes, 1 << 20));
+    {
+        uint8_t *h = (uint8_t *)malloc(1 << 20);
+        for (int i = 0; i < (1 << 20); ++i) h[i] = (uint8_t)((i * 2654435761u >> 13) % 5);
+        CK(cudaMemcpy(d_codes, h, 1 << 20, cudaMemcpyHostToDevice));
+        free(h);
+    }
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hmm_loop_kernel<PACKED, K>, 32, 0));
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, hmm_loop_kernel<PACKED, K>));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int w = 0; w < 2; ++w) hmm_loop_kernel<PACKED, K><<<blocks, 32>>>(d_out, d_codes, 1e-3f, steps);
+    CK(cudaDeviceSynchronize());
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(e0));
+        hmm_loop_kernel<PACKED, K><<<blocks, 32>>>(d_out, d_codes, 1e-3f + rep * 1e-6f, steps);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best_ms) best_ms = ms;
+    }
+    const double cells = (double)steps * K * (PACKED ? 2 : 1) * 32 * blocks;
+    printf("{\"op\": \"%s\", \"tera_cells_per_s\": %.3f, \"ms\": %.4f, \"warps_per_sm_launched\": %d, "
+           "\"max_warps_per_sm\": %d, \"registers\": %d}\n",
+           name, cells / (best_ms * 1e-3) / 1e12, best_ms, warps_per_sm, occ, fa.numRegs);
+    fflush(stdout);
+    CK(cudaFree(d_out));
+    CK(cudaFree(d_codes));
+}
+
 template <int OP> void run_all(int sms, uint32_t *d_out, long long *d_cyc, int bps)
 {
     if constexpr (OP < OP_COUNT) {
@@ -299,7 +596,35 @@ int main(int argc, char **argv)
     long long *d_cyc;
     CK(cudaMalloc(&d_out, sizeof(uint32_t) * sms * bps * 256));
     CK(cudaMalloc(&d_cyc, sizeof(long long) * sms * bps));
-    run_all<0>(sms, d_out, d_cyc, bps);
+    const bool only_fp = argc > 2 && !strcmp(argv[2], "fp");
+    const bool only_hm = argc > 2 && !strcmp(argv[2], "hm");
+    if (only_hm) {
+        run<OP_HMNMX2>(sms, d_out, d_cyc, bps);
+        run<OP_MIX_HMNMX2_VIADDMNMX>(sms, d_out, d_cyc, bps);
+        run<OP_MIX_HMNMX2_VIADD>(sms, d_out, d_cyc, bps);
+        return 0;
+    }
+    if (argc > 2 && !strcmp(argv[2], "loop")) {
+        run_hmm_loop<0, 8>(sms, 20, "PairHMM inner loop, scalar FP32, K=8, 20 warps/SM");
+        run_hmm_loop<0, 6>(sms, 20, "PairHMM inner loop, scalar FP32, K=6, 20 warps/SM");
+        run_hmm_loop<1, 8>(sms, 12, "PairHMM inner loop, two reads f32x2, K=8, 12 warps/SM");
+        run_hmm_loop<1, 8>(sms, 8, "PairHMM inner loop, two reads f32x2, K=8, 8 warps/SM");
+        run_hmm_loop<1, 6>(sms, 12, "PairHMM inner loop, two reads f32x2, K=6, 12 warps/SM");
+        run_hmm_loop<1, 6>(sms, 16, "PairHMM inner loop, two reads f32x2, K=6, 16 warps/SM");
+        run_hmm_loop<1, 4>(sms, 20, "PairHMM inner loop, two reads f32x2, K=4, 20 warps/SM");
+        return 0;
+    }
+    if (!only_fp) run_all<0>(sms, d_out, d_cyc, bps);
+    run_fp2<0>(sms, d_out, d_cyc, bps, "FFMA2 (packed f32x2)", 2, 0);
+    run_fp2<1>(sms, d_out, d_cyc, bps, "FFMA2, scalar broadcast multiplier", 2, 0);
+    run_fp2<2>(sms, d_out, d_cyc, bps, "mix 1 FFMA2 : 1 LOP3", 2, 1);
+    run_fp2<5>(sms, d_out, d_cyc, bps, "mix 1 FFMA2 : 2 LOP3", 2, 2);
+    run_fp2<3>(sms, d_out, d_cyc, bps, "mix 1 FFMA2 : 1 FFMA", 3, 0);
+    run_fp2<4>(sms, d_out, d_cyc, bps, "mix 4 FFMA2 : 1 SHFL.UP", 2, 0.25);
+    run_fp2_pattern<0, 8>(sms, d_out, d_cyc, 2, "PairHMM cell pattern f32x2 K=8, 3 packed instr/cell (16 warps/SM)");
+    run_fp2_pattern<1, 8>(sms, d_out, d_cyc, 2, "PairHMM cell pattern f32x2 K=8, prior multiply unpacked (16 warps/SM)");
+    run_fp2_pattern<0, 6>(sms, d_out, d_cyc, 2, "PairHMM cell pattern f32x2 K=6, 3 packed instr/cell (16 warps/SM)");
+    run_fp2_pattern<0, 8>(sms, d_out, d_cyc, 1, "PairHMM cell pattern f32x2 K=8, 3 packed instr/cell (8 warps/SM)");
     run_fp_pattern<0, 8>(sms, d_out, d_cyc, 2, "FFMA, three distinct source registers (16 warps/SM)");
     run_fp_pattern<1, 8>(sms, d_out, d_cyc, 2, "PairHMM cell pattern K=8, 6 FP32 instr/cell (16 warps/SM)");
     run_fp_pattern<1, 6>(sms, d_out, d_cyc, 2, "PairHMM cell pattern K=6, 6 FP32 instr/cell (16 warps/SM)");

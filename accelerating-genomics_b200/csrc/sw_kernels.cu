@@ -479,9 +479,10 @@ void sw_workspace_free(SwWorkspace &ws)
 }
 
 int sw_run_device(SwWorkspace &ws, const uint8_t *d_seqs, const int64_t *d_off, const int32_t *d_len,
-                  int64_t n_pairs, SwScoring sc, int32_t *d_scores, cudaStream_t st)
+                  int64_t n_pairs, SwScoring sc, int32_t *d_scores, cudaStream_t st, cudaStream_t prep_st)
 {
     if (n_pairs == 0) return AGX_OK;
+    cudaStream_t cst = prep_st ? prep_st : st;     // stream of the length-class pass
     if (n_pairs > (int64_t)1 << 30) return fail(AGX_ERANGE, "sw: more than 2^30 pairs in one call");
     if (!(sc.match > 0 && sc.mismatch < 0 && sc.gap_open <= 0 && sc.gap_extend < 0))
         return fail(AGX_ERANGE, "sw: scoring must satisfy match > 0 > mismatch, gap_open <= 0, gap_extend < 0");
@@ -494,17 +495,17 @@ int sw_run_device(SwWorkspace &ws, const uint8_t *d_seqs, const int64_t *d_off, 
                         sc.match <= 30;
     const int32_t s16_max_short = s16_ok ? min(DUO_MAX_CAP, 32000 / sc.match) : 0;
 
-    AGX_CUDA(cudaMemsetAsync(ws.counters, 0, CNT_WORDS * sizeof(int32_t), st));
+    AGX_CUDA(cudaMemsetAsync(ws.counters, 0, CNT_WORDS * sizeof(int32_t), cst));
     const int cblocks = (int)((n_pairs + 255) / 256);
-    ws.prof_classify.begin(st);
-    sw_classify_kernel<<<cblocks, 256, 0, st>>>(d_seqs, d_off, d_len, n_pairs, s16_max_short,
-                                                sw_long_cells(), sc.match, ws.order, ws.counters, d_scores);
+    ws.prof_classify.begin(cst);
+    sw_classify_kernel<<<cblocks, 256, 0, cst>>>(d_seqs, d_off, d_len, n_pairs, s16_max_short,
+                                                 sw_long_cells(), sc.match, ws.order, ws.counters, d_scores);
     count_launch();
-    ws.prof_classify.end(st);
+    ws.prof_classify.end(cst);
     AGX_CUDA(cudaGetLastError());
     AGX_CUDA(cudaMemcpyAsync(ws.h_counters, ws.counters, CNT_WORDS * sizeof(int32_t),
-                             cudaMemcpyDeviceToHost, st));
-    AGX_CUDA(cudaStreamSynchronize(st));
+                             cudaMemcpyDeviceToHost, cst));
+    AGX_CUDA(cudaStreamSynchronize(cst));
 
     int32_t counts[SW_N_CLASSES];
     int64_t n_duo = 0;

@@ -208,17 +208,21 @@ line_chunks_kernel(const int64_t *__restrict__ nl_pos, int64_t n_nl, int64_t beg
 __global__ void __launch_bounds__(256)
 chunk_emit_kernel(const int64_t *__restrict__ nl_pos, int64_t n_nl, int64_t begin, int64_t end, int32_t cap,
                   int64_t n_lines, const int64_t *__restrict__ chunk_base, int64_t max_chunks,
-                  int64_t *__restrict__ off, int32_t *__restrict__ len)
+                  int64_t *__restrict__ off, int32_t *__restrict__ len, int64_t *__restrict__ totals)
 {
+    // totals[0] = number of chunks in the region (written by the scan); totals[1], totals[2] receive the
+    // offset and length of the last chunk that is kept
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_lines) return;
     int64_t s = k == 0 ? begin : nl_pos[k - 1] + 1;
     const int64_t e = k < n_nl ? nl_pos[k] + 1 : end;
     int64_t c = chunk_base[k];
+    const int64_t last = (totals[0] < max_chunks ? totals[0] : max_chunks) - 1;
     while (s < e && c < max_chunks) {
         const int64_t l = (e - s) < cap ? (e - s) : cap;
         off[c] = s;
         len[c] = (int32_t)l;
+        if (c == last) { totals[1] = s; totals[2] = l; }
         s += l;
         ++c;
     }
@@ -234,21 +238,26 @@ void sw_parse_workspace_free(SwParseWorkspace &ws)
     ws = SwParseWorkspace();
 }
 
-// Splits d_img[begin, end) into fgets(line_buf) chunks.  On return *d_off / *d_len point into the
-// workspace and hold min(total chunks, max_chunks) entries; *n_chunks_out is that count.
-// Synchronises `st` twice (newline count, chunk count).
+// Splits d_img[begin, end) into fgets(line_buf) chunks; `begin` must be a position fgets() would start a
+// read at (a line start or a chunk start -- fgets keeps no state besides the file position).  On return
+// *d_off / *d_len point into the workspace and hold min(total chunks, max_chunks) entries; *n_chunks_out
+// is that count and *last_off / *last_len describe the last of them.  last_byte = d_img[end-1] if the
+// caller knows it, -1 to have it read back.  Synchronises `st` twice (newline count, chunk count).
 int sw_parse_device(SwParseWorkspace &ws, const uint8_t *d_img, int64_t begin, int64_t end, int32_t line_buf,
-                    int64_t max_chunks, int64_t **d_off, int32_t **d_len, int64_t *n_chunks_out, cudaStream_t st)
+                    int64_t max_chunks, int last_byte, int64_t **d_off, int32_t **d_len, int64_t *n_chunks_out,
+                    int64_t *last_off, int32_t *last_len, cudaStream_t st)
 {
     *n_chunks_out = 0;
     *d_off = nullptr;
     *d_len = nullptr;
+    if (last_off) *last_off = -1;
+    if (last_len) *last_len = 0;
     if (end <= begin || max_chunks <= 0) return AGX_OK;
     if (line_buf < 2) return fail(AGX_EINVAL, "sw: line buffer must hold at least one character");
     const int32_t cap = line_buf - 1;
     const int64_t n_bytes = end - begin;
     const int64_t tiles = (end - (begin & ~(int64_t)15) + TILE_BYTES - 1) / TILE_BYTES;
-    if (!ws.h_total) AGX_CUDA(cudaMallocHost(&ws.h_total, 2 * sizeof(int64_t)));
+    if (!ws.h_total) AGX_CUDA(cudaMallocHost(&ws.h_total, 4 * sizeof(int64_t)));
 
     auto align = [](int64_t x) { return (x + 255) / 256 * 256; };
     // first stage: tile counts, their scan, total
@@ -279,10 +288,12 @@ int sw_parse_device(SwParseWorkspace &ws, const uint8_t *d_img, int64_t begin, i
     AGX_CUDA(cudaMemcpyAsync(ws.h_total, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     AGX_CUDA(cudaStreamSynchronize(st));
     const int64_t n_nl = ws.h_total[0];
-    // does the image end with a newline?  (one byte read)
-    uint8_t last = 0;
-    AGX_CUDA(cudaMemcpyAsync(&last, d_img + end - 1, 1, cudaMemcpyDeviceToHost, st));
-    AGX_CUDA(cudaStreamSynchronize(st));
+    // does the region end with a newline?  (one byte read unless the caller knows)
+    uint8_t last = (uint8_t)last_byte;
+    if (last_byte < 0) {
+        AGX_CUDA(cudaMemcpyAsync(&last, d_img + end - 1, 1, cudaMemcpyDeviceToHost, st));
+        AGX_CUDA(cudaStreamSynchronize(st));
+    }
     const int64_t n_lines = n_nl + (last == '\n' ? 0 : 1);
     if (n_nl > (int64_t)1 << 31) return fail(AGX_ERANGE, "sw: more than 2^31 lines");
 
@@ -318,12 +329,17 @@ int sw_parse_device(SwParseWorkspace &ws, const uint8_t *d_img, int64_t begin, i
     count_launch();
     rc = exclusive_scan(cpl, n_lines, chunk_base, tmp2, d_total2, st);
     if (rc != AGX_OK) return rc;
-    chunk_emit_kernel<<<lblocks, 256, 0, st>>>(nl_pos, n_nl, begin, end, cap, n_lines, chunk_base, chunk_bound, off, len);
+    chunk_emit_kernel<<<lblocks, 256, 0, st>>>(nl_pos, n_nl, begin, end, cap, n_lines, chunk_base, chunk_bound, off, len,
+                                               d_total2);
     count_launch();
     AGX_CUDA(cudaGetLastError());
-    AGX_CUDA(cudaMemcpyAsync(ws.h_total + 1, d_total2, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    AGX_CUDA(cudaMemcpyAsync(ws.h_total + 1, d_total2, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     AGX_CUDA(cudaStreamSynchronize(st));
     *n_chunks_out = std::min<int64_t>(ws.h_total[1], chunk_bound);
+    if (*n_chunks_out > 0) {
+        if (last_off) *last_off = ws.h_total[2];
+        if (last_len) *last_len = (int32_t)ws.h_total[3];
+    }
     *d_off = off;
     *d_len = len;
     return AGX_OK;

@@ -265,3 +265,33 @@ def test_file_image_config3_shape(agx, gpu_lib):
     scores, header, dangling = gpu_lib.sw_score_file_image(inp.buf)
     assert header == 200_000 and dangling == b""
     assert np.array_equal(scores, gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len))
+
+
+@pytest.mark.parametrize("segment", [64, 1000, 4096, 1 << 20])
+def test_file_image_streaming_segments(agx, gpu_lib, segment, monkeypatch):
+    """Upload segments of any size (pairs, lines and fgets() chunks straddle them) give the same scores."""
+    rng = np.random.default_rng(segment)
+    alpha = np.frombuffer(b"ACGT", np.uint8)
+    lines = [alpha[rng.integers(0, 4, size=int(n))].tobytes() for n in rng.integers(0, 2600, size=403)]
+    data = b"404\n" + b"\n".join(lines) + b"\n"
+    host = agx.formats.parse_sw(data)
+    want = gpu_lib.sw_score_flat(host.buf, host.off, host.len)
+    monkeypatch.setenv("AGX_SW_IMAGE_SEGMENT", str(segment))
+    scores, header, dangling = gpu_lib.sw_score_file_image(data)
+    assert header == host.header and dangling == host.dangling
+    assert scores.tolist() == want.tolist()
+    for name in SW_FILES:
+        g = (GOLDEN / f"{name}.in").read_bytes()
+        scores, header, dangling = gpu_lib.sw_score_file_image(g)
+        assert scores.tolist() == ref_scores(f"{name}.ref.out")
+        assert dangling == agx.formats.parse_sw(g).dangling
+
+
+def test_file_image_pinned_image_and_output(agx, gpu_lib):
+    import torch
+    inp = agx.synth.sw_uniform_pairs(50_000, 150, seed=5)
+    h_img = torch.from_numpy(inp.buf).pin_memory()
+    h_out = torch.empty(50_000, dtype=torch.int32).pin_memory()
+    scores, header, dangling = gpu_lib.sw_score_file_image(h_img.numpy(), out=h_out.numpy())
+    assert header == 100_000 and dangling == b"" and scores.size == 50_000
+    assert np.array_equal(scores, gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len))
