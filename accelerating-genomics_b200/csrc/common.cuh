@@ -103,6 +103,9 @@ void sw_parse_workspace_free(SwParseWorkspace &ws);
 // ---- PairHMM ------------------------------------------------------------------------------
 struct HmmWorkspace {
     int32_t *order = nullptr;     // [n_reads] read ids grouped by row class
+    void *pairs = nullptr;        // [HMM_MAX_K][n_reads] int2: reads paired for the two-reads-per-warp kernel
+    int32_t *batch_first = nullptr;   // [n_batches] first read, then [n_batches] one past the last read
+    int64_t cap_batches = 0;
     int32_t *counters = nullptr;  // class histogram / cursors / rescue count
     int32_t *h_counters = nullptr;
     int64_t *rescue = nullptr;    // [cap_pairs] flat output indices needing FP64
@@ -114,6 +117,10 @@ struct HmmWorkspace {
     void *prep = nullptr;         // haplotype codes + records + FP32 forward sums of the stream kernel
     int64_t cap_prep = 0;
     ProfSpan prof_stream, prof_fp64, prof_classify;
+    // the row-class launches of the stream kernel run side by side so that one class's tail wave
+    // overlaps the next class's first wave
+    cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
 };
 
 struct HmmBatchView {
@@ -129,7 +136,7 @@ struct HmmBatchView {
     int64_t n_batches;
 };
 
-int hmm_workspace_reserve(HmmWorkspace &ws, int64_t n_reads, int64_t n_pairs);
+int hmm_workspace_reserve(HmmWorkspace &ws, int64_t n_reads, int64_t n_pairs, int64_t n_batches);
 void hmm_workspace_free(HmmWorkspace &ws);
 // d_read_out_off[r] = index in d_out of (read r, first haplotype of its batch); n_pairs = total outputs.
 int hmm_run_device(HmmWorkspace &ws, const HmmBatchView &v, int64_t buf_bytes, const int64_t *d_read_out_off,

@@ -10,8 +10,14 @@
 //     row 0: M = X = 0, Y = SCALE / hap_len;  column 0 (i >= 1): 0
 //     result  = log10(sum_j M[R][j] + X[R][j]) - log10(SCALE)
 //
-// Two kernels:
-//   hmm_stream_kernel<K>   FP32 fast path.  One warp per read; lane t owns K consecutive read rows
+// Three kernels:
+//   hmm_duo_kernel<K>      FP32 fast path, TWO reads of the same batch and row class per warp: the same
+//                          streaming scheme as hmm_stream_kernel below, with read A in the low and read B
+//                          in the high half of every value and every FP32 instruction in its packed
+//                          sm_100 form (FFMA2 / FMUL2 / FADD2 = fma.rn.f32x2 ...): one issue slot per two
+//                          cells, and the per-step costs (three boundary shuffles, prior lookup, symbol
+//                          prefetch, haplotype counter) are paid once for 2*K cells instead of K.
+//   hmm_stream_kernel<K>   FP32 fast path for the reads left without a partner.  One warp per read; lane t owns K consecutive read rows
 //                          in registers (rows are bottom-aligned, so row R is always the last row
 //                          of lane 31); ALL haplotypes of the read's batch stream through the warp
 //                          back to back, column by column, lane t one column behind lane t-1
@@ -25,8 +31,10 @@
 //                          With T = double it evaluates the reference's expression in the
 //                          reference's own association order without FMA contraction and with
 //                          SCALE = DBL_MAX/16, i.e. it is the FP64 rescue / exact-parity path.
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -39,7 +47,9 @@ constexpr int HMM_N_CLASSES = HMM_MAX_K + 1;    // classes 0..7 -> K = 1..8, cla
 constexpr int HMM_LONG = HMM_MAX_K;
 constexpr int HCNT_RESCUE = HMM_N_CLASSES;      // counters[HCNT_RESCUE]  = rescue list length
 constexpr int HCNT_MAXHAP = HMM_N_CLASSES + 1;  // counters[HCNT_MAXHAP]  = longest haplotype
-constexpr int HCNT_WORDS = HMM_N_CLASSES + 4;
+constexpr int HCNT_UNSORTED = HMM_N_CLASSES + 2;   // != 0: read_batch is not non-decreasing (no pairing)
+constexpr int HCNT_PAIRS = HMM_N_CLASSES + 4;   // counters[HCNT_PAIRS + c] = read pairs of row class c
+constexpr int HCNT_WORDS = HCNT_PAIRS + HMM_MAX_K;
 #ifndef AGX_HMM_WARPS
 #define AGX_HMM_WARPS 1
 #endif
@@ -78,6 +88,92 @@ hmm_classify_kernel(const int32_t *__restrict__ read_len, int64_t n_reads,
     if (threadIdx.x == 0 && s_maxhap > 0) atomicMax(&counters[HCNT_MAXHAP], s_maxhap);
     __syncthreads();
     if (cls >= 0) order[(int64_t)cls * n_reads + s_base[cls] + rank] = (int32_t)i;
+}
+
+// ------------------------------------------------------------------------------------------
+// read pairing for hmm_duo_kernel
+// ------------------------------------------------------------------------------------------
+// first / one-past-last read of every batch (reads of a batch are consecutive when read_batch is
+// non-decreasing; anything else raises HCNT_UNSORTED and the host falls back to one read per warp)
+__global__ void __launch_bounds__(256)
+hmm_ranges_kernel(const int32_t *__restrict__ read_batch, int64_t n_reads, const int32_t *__restrict__ hap_len,
+                  int64_t n_haps, int32_t *__restrict__ batch_first, int32_t *__restrict__ batch_end,
+                  int32_t *__restrict__ counters)
+{
+    __shared__ int32_t s_maxhap;
+    if (threadIdx.x == 0) s_maxhap = 0;
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_reads) {
+        const int32_t b = read_batch[i];
+        if (i == 0 || read_batch[i - 1] != b) batch_first[b] = (int32_t)i;
+        if (i == n_reads - 1 || read_batch[i + 1] != b) batch_end[b] = (int32_t)i + 1;
+        if (i > 0 && read_batch[i - 1] > b) counters[HCNT_UNSORTED] = 1;
+    }
+    if (i < n_haps) atomicMax(&s_maxhap, hap_len[i]);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_maxhap > 0) atomicMax(&counters[HCNT_MAXHAP], s_maxhap);
+}
+
+// One warp per batch: reads of the same row class are paired in file order; a class with an odd number
+// of reads leaves one single (-> hmm_stream_kernel); reads longer than the stream kernels take go to the
+// striped kernel's list.  pairs[c][...] / order[c][...] are filled through warp-aggregated atomics.
+__global__ void __launch_bounds__(128)
+hmm_pair_kernel(const int32_t *__restrict__ read_len, int64_t n_reads, int64_t n_batches,
+                const int32_t *__restrict__ batch_first, const int32_t *__restrict__ batch_end,
+                int2 *__restrict__ pairs, int32_t *__restrict__ order, int32_t *__restrict__ counters)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = warp; b < n_batches; b += n_warps) {
+        const int32_t rs = batch_first[b], re = batch_end[b];
+        if (rs < 0 || re <= rs) continue;
+        int32_t pend[HMM_MAX_K];
+#pragma unroll
+        for (int c = 0; c < HMM_MAX_K; ++c) pend[c] = -1;
+        for (int32_t base = rs; base < re; base += 32) {
+            const int32_t r = base + lane;
+            int cls = -1;
+            if (r < re) {
+                const int32_t R = read_len[r];
+                cls = R <= 32 * HMM_MAX_K ? (R + 31) / 32 - 1 : HMM_LONG;
+                if (cls < 0) cls = 0;
+            }
+            const uint32_t mlong = __ballot_sync(0xffffffffu, cls == HMM_LONG);
+            if (mlong) {
+                int32_t pos = 0;
+                if (lane == 0) pos = atomicAdd(&counters[HMM_LONG], __popc(mlong));
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+                if (cls == HMM_LONG) order[(int64_t)HMM_LONG * n_reads + pos + __popc(mlong & lt)] = r;
+            }
+#pragma unroll
+            for (int c = 0; c < HMM_MAX_K; ++c) {
+                const uint32_t m = __ballot_sync(0xffffffffu, cls == c);
+                if (m == 0) continue;
+                const int hasp = pend[c] >= 0 ? 1 : 0;
+                const int total = __popc(m) + hasp;
+                const int np = total >> 1;
+                int32_t pos = 0;
+                if (np > 0 && lane == 0) pos = atomicAdd(&counters[HCNT_PAIRS + c], np);
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+                const int e = __popc(m & lt) + hasp;          // my index in [pending read] + this tile's reads
+                if (cls == c && (e & 1)) {
+                    // second read of a pair: the first is the pending read or the lane just before me in m
+                    const int32_t first = (e == 1 && hasp) ? pend[c] : base + (int32_t)__fns(m, 0, e - hasp);
+                    pairs[(int64_t)c * n_reads + pos + (e >> 1)] = make_int2(first, r);
+                }
+                // an odd total leaves the tile's last read of this class pending
+                pend[c] = (total & 1) ? base + (31 - __clz(m)) : -1;
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < HMM_MAX_K; ++c)
+                if (pend[c] >= 0) order[(int64_t)c * n_reads + atomicAdd(&counters[c], 1)] = pend[c];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -303,6 +399,217 @@ hmm_stream_kernel(HmmBatchView v, const int64_t *__restrict__ read_out_off,
     if (t == 31 && hidx >= h0 && hidx < h1 && rem == 0) my_sums[hidx - h0] = acc;
 }
 
+// ------------------------------------------------------------------------------------------
+// FP32 streaming kernel, two reads per warp, packed f32x2 arithmetic
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
+{
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b),
+                       rc = *reinterpret_cast<unsigned long long *>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b)
+{
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b), rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b)
+{
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b), rd;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+
+// Resident one-warp blocks per SM the register budget is cut for.  Each of the four SM sub-partitions has
+// its own 16 K registers, so the useful targets are multiples of four: 12 blocks -> 168 registers per
+// thread, 16 -> 128, 20 -> 96.
+#ifndef AGX_DUO_OCC
+#define AGX_DUO_OCC 0
+#endif
+__host__ __device__ constexpr int duo_min_blocks(int K)
+{
+    return AGX_DUO_OCC == 1   ? (K >= 8 ? 8 : K >= 5 ? 12 : K == 4 ? 16 : 20)      // roomy
+           : AGX_DUO_OCC == 2 ? (K >= 7 ? 12 : K >= 5 ? 16 : 20)                   // tight
+                              : (K >= 6 ? 12 : K >= 4 ? 16 : 20);
+}
+
+template <int K>
+__global__ void __launch_bounds__(32, duo_min_blocks(K))
+hmm_duo_kernel(HmmBatchView v, const int64_t *__restrict__ read_out_off, const int2 *__restrict__ items,
+               int32_t n_items, const double *__restrict__ lut, int gatk, const uint8_t *__restrict__ codes,
+               const uint8_t *__restrict__ zero_pad, const HapInfo *__restrict__ hapinfo,
+               float *__restrict__ sums)
+{
+    constexpr int CH = (K + 1) / 2;                    // float4 = (row 2c: A, B; row 2c+1: A, B)
+    __shared__ float4 prior_tab[HMM_NSYM][CH][32];
+
+    const int t = threadIdx.x;
+    const int item = blockIdx.x;
+    if (item >= n_items) return;
+    const int2 rr = items[item];
+    const int32_t bt = v.read_batch[rr.x];             // both reads belong to this batch
+    const int32_t h0 = (int32_t)v.batch_hap_start[bt], h1 = (int32_t)v.batch_hap_start[bt + 1];
+    if (h1 <= h0) return;
+    float *sums_a = sums + read_out_off[rr.x];
+    float *sums_b = sums + read_out_off[rr.y];
+
+    // ---- prior / transition setup: .x = read A, .y = read B (rows of both bottom-aligned) ---------
+    float2 ca[K], cbx[K], cby[K], ccx[K], cg[K];
+    float2 qi_last;
+    int n_pad_rows[2];
+    bool top_boundary[2];
+    {
+        float pm[2][CH * 2], px[2][CH * 2];
+        uint32_t rsym[2][CH * 2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int32_t r = h ? rr.y : rr.x;
+            const int32_t R = v.read_len[r];
+            const int pad = 32 * K - R;
+            const uint8_t *f_b = v.buf + v.read_field_off[5 * (int64_t)r + 0];
+            const uint8_t *f_q = v.buf + v.read_field_off[5 * (int64_t)r + 1];
+            const uint8_t *f_i = v.buf + v.read_field_off[5 * (int64_t)r + 2];
+            const uint8_t *f_d = v.buf + v.read_field_off[5 * (int64_t)r + 3];
+            const uint8_t *f_g = v.buf + v.read_field_off[5 * (int64_t)r + 4];
+#pragma unroll
+            for (int jj = 0; jj < CH * 2; ++jj) { pm[h][jj] = px[h][jj] = 0.f; rsym[h][jj] = 5u; }
+#pragma unroll
+            for (int jj = 0; jj < K; ++jj) {
+                const int i = t * K + jj - pad;      // 0-based read position of this row
+                float a = 0.f, bx = 0.f, by = 0.f, cx = 0.f, g = 1.f;   // padding rows reproduce row 0
+                if (i >= 0) {
+                    const double Qr = __ldg(lut + f_q[i]), Qi = __ldg(lut + f_i[i]), Qd = __ldg(lut + f_d[i]),
+                                 Qg = __ldg(lut + f_g[i]);
+                    const double Qi_up = (i > 0) ? __ldg(lut + f_i[i - 1]) : 1.0;
+                    const double Qd_up = (i > 0) ? __ldg(lut + f_d[i - 1]) : 1.0;
+                    const uint32_t base = f_b[i];
+                    const double mm = 1.0 - (Qi + Qd), gm = 1.0 - Qg;
+                    pm[h][jj] = (float)(1.0 - Qr);
+                    px[h][jj] = (float)(gatk ? Qr / 3.0 : Qr);
+                    rsym[h][jj] = (base == 'N') ? 4u : hap_symbol(base);
+                    a = (float)mm;
+                    bx = (float)(gm * Qi_up);
+                    by = (float)(gm * Qd_up);
+                    cx = (i > 0) ? (float)(Qg * Qi_up / Qi) : 0.f;
+                    g = (float)Qg;
+                }
+                if (h == 0) { ca[jj].x = a; cbx[jj].x = bx; cby[jj].x = by; ccx[jj].x = cx; cg[jj].x = g; }
+                else        { ca[jj].y = a; cbx[jj].y = bx; cby[jj].y = by; ccx[jj].y = cx; cg[jj].y = g; }
+            }
+            const float ql = (float)__ldg(lut + f_i[R - 1]);   // X[R][j] = Qi_R * X'[R][j]
+            if (h == 0) qi_last.x = ql; else qi_last.y = ql;
+            top_boundary[h] = (t * K - 1) < pad;     // the row above this lane's first row is row 0
+            n_pad_rows[h] = pad - t * K;             // rows jj < n_pad_rows of this lane are padding
+        }
+#pragma unroll
+        for (int sym = 0; sym < HMM_NSYM; ++sym) {
+#pragma unroll
+            for (int ch = 0; ch < CH; ++ch) {
+                float q[2][2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int jj = ch * 2 + e;
+                        const bool match = (sym == 4) || (rsym[h][jj] == 4u) || (sym < 4 && rsym[h][jj] == (uint32_t)sym);
+                        q[e][h] = match ? pm[h][jj] : px[h][jj];
+                    }
+                prior_tab[sym][ch][t] = make_float4(q[0][0], q[0][1], q[1][0], q[1][1]);
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- streaming state ------------------------------------------------------------------------
+    const float2 zero2 = make_float2(0.f, 0.f);
+    float2 M[K], X[K], Y[K];
+#pragma unroll
+    for (int jj = 0; jj < K; ++jj) { M[jj] = X[jj] = Y[jj] = zero2; }
+    float2 pdM = zero2, pdX = zero2, pdY = zero2;    // what arrived one step ago = diagonal inputs
+    float2 bM = zero2, bX = zero2, bY = zero2;       // this lane's bottom row, sent down next step
+    float2 acc = zero2;
+    float init = 0.f;
+
+    int32_t hidx = h0 - 1;
+    int32_t rem = t;
+    const uint8_t *cp = zero_pad;
+    int64_t inc = 0;
+    uint32_t code_next = 0u;
+
+    int32_t total = 31;
+    for (int32_t h = h0; h < h1; ++h) total += hapinfo[h].len;
+
+    const float4 *tab_lane = &prior_tab[0][0][t];
+    constexpr int SYM_STRIDE = CH * 32;              // float4 elements between symbols
+    const bool lane0 = (t == 0);
+
+#pragma unroll 2
+    for (int32_t s = 0; s < total; ++s) {
+        if (rem == 0) {
+            // ---- this lane finished a haplotype: lane 31 owns the last row of both reads ----
+            if (t == 31 && hidx >= h0) { sums_a[hidx - h0] = acc.x; sums_b[hidx - h0] = acc.y; }
+            ++hidx;
+            acc = zero2;
+            if (hidx < h1) {
+                const HapInfo hi = hapinfo[hidx];
+                rem = hi.len;
+                cp = codes + hi.off;
+                inc = 1;
+                init = hi.init;
+                code_next = *cp;
+            } else {
+                rem = 0x7fffffff;    // drained: keep stepping on neutral input
+                cp = zero_pad;
+                inc = 0;
+                code_next = 0u;
+            }
+#pragma unroll
+            for (int jj = 0; jj < K; ++jj) {
+                M[jj] = zero2; X[jj] = zero2;
+                Y[jj] = make_float2((jj < n_pad_rows[0]) ? init : 0.f, (jj < n_pad_rows[1]) ? init : 0.f);
+            }
+            pdM = zero2; pdX = zero2;
+            pdY = make_float2(top_boundary[0] ? init : 0.f, top_boundary[1] ? init : 0.f);
+        }
+        const uint32_t code = code_next;
+        cp += inc;
+        code_next = *cp;                                  // prefetch the next column's symbol
+        float4 pr4[CH];
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) pr4[ch] = tab_lane[code * SYM_STRIDE + ch * 32];
+
+        float2 upM, upX, upY;
+        upM.x = __shfl_up_sync(0xffffffffu, bM.x, 1); upM.y = __shfl_up_sync(0xffffffffu, bM.y, 1);
+        upX.x = __shfl_up_sync(0xffffffffu, bX.x, 1); upX.y = __shfl_up_sync(0xffffffffu, bX.y, 1);
+        upY.x = __shfl_up_sync(0xffffffffu, bY.x, 1); upY.y = __shfl_up_sync(0xffffffffu, bY.y, 1);
+        if (lane0) { upM = zero2; upX = zero2; upY = make_float2(init, init); }
+        float2 dM = pdM, dX = pdX, dY = pdY;
+        pdM = upM; pdX = upX; pdY = upY;
+#pragma unroll
+        for (int jj = 0; jj < K; ++jj) {
+            const float2 oM = M[jj], oX = X[jj], oY = Y[jj];
+            const float4 p4 = pr4[jj / 2];
+            const float2 pr = (jj & 1) ? make_float2(p4.z, p4.w) : make_float2(p4.x, p4.y);
+            float2 vv = fmul2(cby[jj], dY);
+            vv = ffma2(cbx[jj], dX, vv);
+            vv = ffma2(ca[jj], dM, vv);
+            const float2 mn = fmul2(pr, vv);
+            const float2 xn = ffma2(ccx[jj], upX, upM);
+            const float2 yn = ffma2(cg[jj], oY, oM);
+            dM = oM; dX = oX; dY = oY;
+            upM = mn; upX = xn;
+            M[jj] = mn; X[jj] = xn; Y[jj] = yn;
+        }
+        bM = M[K - 1]; bX = X[K - 1]; bY = Y[K - 1];
+        acc = fadd2(acc, ffma2(qi_last, bX, bM));
+        --rem;
+    }
+    // the last haplotype of lane 31 ends exactly at the last step
+    if (t == 31 && hidx >= h0 && hidx < h1 && rem == 0) { sums_a[hidx - h0] = acc.x; sums_b[hidx - h0] = acc.y; }
+}
+
 // forward sums -> log10 likelihoods; sums FP32 cannot be trusted with are queued for the FP64 kernel
 __global__ void __launch_bounds__(256)
 hmm_finalize_kernel(HmmBatchView v, const int64_t *__restrict__ read_out_off,
@@ -311,7 +618,9 @@ hmm_finalize_kernel(HmmBatchView v, const int64_t *__restrict__ read_out_off,
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_items) return;
-    const int32_t r = order[i];
+    // order == nullptr: every read that fits the stream kernels (the rest is the striped kernel's)
+    const int32_t r = order ? order[i] : i;
+    if (!order && v.read_len[r] > 32 * HMM_MAX_K) return;
     const int32_t bt = v.read_batch[r];
     const int32_t h0 = (int32_t)v.batch_hap_start[bt], h1 = (int32_t)v.batch_hap_start[bt + 1];
     const int64_t o = read_out_off[r];
@@ -513,10 +822,29 @@ int launch_stream(const HmmBatchView &v, const int64_t *read_out_off, const int3
     return AGX_OK;
 }
 
+template <int K>
+int launch_duo(const HmmBatchView &v, const int64_t *read_out_off, const int2 *pairs, int32_t count,
+               const double *lut, int gatk, const uint8_t *codes, int64_t codes_bytes, const HapInfo *info,
+               float *sums, cudaStream_t st)
+{
+    if (count == 0) return AGX_OK;
+    hmm_duo_kernel<K><<<count, 32, 0, st>>>(v, read_out_off, pairs + (int64_t)(K - 1) * v.n_reads, count, lut, gatk,
+                                             codes, codes + codes_bytes, info, sums);
+    count_launch();
+    AGX_CUDA(cudaGetLastError());
+    return AGX_OK;
+}
+
 }  // namespace
 
-int hmm_workspace_reserve(HmmWorkspace &ws, int64_t n_reads, int64_t n_pairs)
+int hmm_workspace_reserve(HmmWorkspace &ws, int64_t n_reads, int64_t n_pairs, int64_t n_batches)
 {
+    if (n_batches > ws.cap_batches) {
+        if (ws.batch_first) cudaFree(ws.batch_first);
+        ws.batch_first = nullptr; ws.cap_batches = 0;
+        AGX_CUDA(cudaMalloc(&ws.batch_first, (size_t)n_batches * 2 * sizeof(int32_t)));
+        ws.cap_batches = n_batches;
+    }
     if (!ws.counters) {
         AGX_CUDA(cudaMalloc(&ws.counters, HCNT_WORDS * sizeof(int32_t)));
         AGX_CUDA(cudaMallocHost(&ws.h_counters, HCNT_WORDS * sizeof(int32_t)));
@@ -526,11 +854,19 @@ int hmm_workspace_reserve(HmmWorkspace &ws, int64_t n_reads, int64_t n_pairs)
         double lut[256];
         for (int c = 0; c < 256; ++c) lut[c] = pow(10.0, -((double)(signed char)c - 33.0) * 0.1);
         AGX_CUDA(cudaMemcpy(ws.d_lut, lut, sizeof lut, cudaMemcpyHostToDevice));
+        for (int i = 0; i < 3; ++i) {
+            AGX_CUDA(cudaStreamCreateWithFlags(&ws.aux[i], cudaStreamNonBlocking));
+            AGX_CUDA(cudaEventCreateWithFlags(&ws.ev_join[i], cudaEventDisableTiming));
+        }
+        AGX_CUDA(cudaEventCreateWithFlags(&ws.ev_fork, cudaEventDisableTiming));
     }
     if (n_reads > ws.cap_reads) {
         if (ws.order) cudaFree(ws.order);
         ws.order = nullptr; ws.cap_reads = 0;
         AGX_CUDA(cudaMalloc(&ws.order, (size_t)n_reads * HMM_N_CLASSES * sizeof(int32_t)));
+        if (ws.pairs) cudaFree(ws.pairs);
+        ws.pairs = nullptr;
+        AGX_CUDA(cudaMalloc(&ws.pairs, (size_t)n_reads * HMM_MAX_K * sizeof(int2)));
         ws.cap_reads = n_reads;
     }
     if (n_pairs > ws.cap_pairs) {
@@ -545,6 +881,8 @@ int hmm_workspace_reserve(HmmWorkspace &ws, int64_t n_reads, int64_t n_pairs)
 void hmm_workspace_free(HmmWorkspace &ws)
 {
     if (ws.order) cudaFree(ws.order);
+    if (ws.pairs) cudaFree(ws.pairs);
+    if (ws.batch_first) cudaFree(ws.batch_first);
     if (ws.counters) cudaFree(ws.counters);
     if (ws.h_counters) cudaFreeHost(ws.h_counters);
     if (ws.rescue) cudaFree(ws.rescue);
@@ -552,6 +890,11 @@ void hmm_workspace_free(HmmWorkspace &ws)
     if (ws.scratch) cudaFree(ws.scratch);
     if (ws.prep) cudaFree(ws.prep);
     ws.prof_stream.destroy(); ws.prof_fp64.destroy(); ws.prof_classify.destroy();
+    for (int i = 0; i < 3; ++i) {
+        if (ws.aux[i]) cudaStreamDestroy(ws.aux[i]);
+        if (ws.ev_join[i]) cudaEventDestroy(ws.ev_join[i]);
+    }
+    if (ws.ev_fork) cudaEventDestroy(ws.ev_fork);
     ws = HmmWorkspace();
 }
 
@@ -573,20 +916,47 @@ int hmm_run_device(HmmWorkspace &ws, const HmmBatchView &v, int64_t buf_bytes, c
     if (v.n_reads == 0 || n_pairs == 0) return AGX_OK;
     if (v.n_reads > (int64_t)1 << 30 || v.n_haps > (int64_t)1 << 30)
         return fail(AGX_ERANGE, "pairhmm: more than 2^30 reads or haplotypes in one call");
-    int rc = hmm_workspace_reserve(ws, v.n_reads, n_pairs);
+    int rc = hmm_workspace_reserve(ws, v.n_reads, n_pairs, v.n_batches);
     if (rc != AGX_OK) return rc;
 
-    AGX_CUDA(cudaMemsetAsync(ws.counters, 0, HCNT_WORDS * sizeof(int32_t), st));
+    static const bool no_duo = getenv("AGX_PAIRHMM_NO_DUO") != nullptr;   // A/B switch: one read per warp only
     const int64_t nmax = v.n_reads > v.n_haps ? v.n_reads : v.n_haps;
-    hmm_classify_kernel<<<(int)((nmax + 255) / 256), 256, 0, st>>>(
-        v.read_len, v.n_reads, v.hap_len, v.n_haps, ws.order, ws.counters, force_fp64 ? 1 : 0);
-    count_launch();
-    AGX_CUDA(cudaGetLastError());
-    AGX_CUDA(cudaMemcpyAsync(ws.h_counters, ws.counters, HCNT_WORDS * sizeof(int32_t),
-                             cudaMemcpyDeviceToHost, st));
-    AGX_CUDA(cudaStreamSynchronize(st));
-    int32_t counts[HMM_N_CLASSES];
+    int2 *pairs = reinterpret_cast<int2 *>(ws.pairs);
+    bool paired = !force_fp64 && !no_duo;
+    ws.prof_classify.begin(st);
+    AGX_CUDA(cudaMemsetAsync(ws.counters, 0, HCNT_WORDS * sizeof(int32_t), st));
+    if (paired) {
+        // reads of the same batch and row class are paired for hmm_duo_kernel
+        int32_t *batch_first = ws.batch_first, *batch_end = ws.batch_first + v.n_batches;
+        AGX_CUDA(cudaMemsetAsync(batch_first, 0xff, (size_t)v.n_batches * sizeof(int32_t), st));
+        AGX_CUDA(cudaMemsetAsync(batch_end, 0, (size_t)v.n_batches * sizeof(int32_t), st));
+        hmm_ranges_kernel<<<(int)((nmax + 255) / 256), 256, 0, st>>>(v.read_batch, v.n_reads, v.hap_len, v.n_haps,
+                                                                    batch_first, batch_end, ws.counters);
+        const int64_t pair_blocks = std::min<int64_t>((v.n_batches + 3) / 4, 148 * 16);
+        hmm_pair_kernel<<<(int)pair_blocks, 128, 0, st>>>(v.read_len, v.n_reads, v.n_batches, batch_first, batch_end,
+                                                        pairs, ws.order, ws.counters);
+        count_launch(2);
+        AGX_CUDA(cudaGetLastError());
+        AGX_CUDA(cudaMemcpyAsync(ws.h_counters, ws.counters, HCNT_WORDS * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        AGX_CUDA(cudaStreamSynchronize(st));
+        if (ws.h_counters[HCNT_UNSORTED]) {
+            paired = false;               // reads of a batch are not consecutive: one read per warp
+            AGX_CUDA(cudaMemsetAsync(ws.counters, 0, HCNT_WORDS * sizeof(int32_t), st));
+        }
+    }
+    if (!paired) {
+        hmm_classify_kernel<<<(int)((nmax + 255) / 256), 256, 0, st>>>(
+            v.read_len, v.n_reads, v.hap_len, v.n_haps, ws.order, ws.counters, force_fp64 ? 1 : 0);
+        count_launch();
+        AGX_CUDA(cudaGetLastError());
+        AGX_CUDA(cudaMemcpyAsync(ws.h_counters, ws.counters, HCNT_WORDS * sizeof(int32_t),
+                                 cudaMemcpyDeviceToHost, st));
+        AGX_CUDA(cudaStreamSynchronize(st));
+    }
+    ws.prof_classify.end(st);
+    int32_t counts[HMM_N_CLASSES], pair_counts[HMM_MAX_K];
     for (int c = 0; c < HMM_N_CLASSES; ++c) counts[c] = ws.h_counters[c];
+    for (int c = 0; c < HMM_MAX_K; ++c) pair_counts[c] = paired ? ws.h_counters[HCNT_PAIRS + c] : 0;
     const int32_t max_hap = ws.h_counters[HCNT_MAXHAP];
     const int gatk = gatk_mode ? 1 : 0;
     int2 *rescue = reinterpret_cast<int2 *>(ws.rescue);
@@ -600,7 +970,7 @@ int hmm_run_device(HmmWorkspace &ws, const HmmBatchView &v, int64_t buf_bytes, c
     if (!force_fp64) {
         // haplotype symbol codes + per-haplotype records + FP32 forward sums live in one scratch block
         int64_t n_stream = 0;
-        for (int c = 0; c < HMM_MAX_K; ++c) n_stream += counts[c];
+        for (int c = 0; c < HMM_MAX_K; ++c) n_stream += counts[c] + 2 * (int64_t)pair_counts[c];
         uint8_t *codes = nullptr;
         const int64_t codes_bytes = ((buf_bytes + 255) / 256) * 256;   // a zeroed pad follows the codes
         HapInfo *info = nullptr;
@@ -625,23 +995,47 @@ int hmm_run_device(HmmWorkspace &ws, const HmmBatchView &v, int64_t buf_bytes, c
             AGX_CUDA(cudaGetLastError());
         }
         ws.prof_stream.begin(st);
-#define AGX_STREAM(KK)                                                                          \
-    if ((rc = launch_stream<KK>(v, d_read_out_off, ws.order, counts[KK - 1], ws.d_lut, gatk,    \
-                                codes, codes_bytes, info, sums, st)) != AGX_OK)                 \
-        return rc;
-        AGX_STREAM(1) AGX_STREAM(2) AGX_STREAM(3) AGX_STREAM(4)
-        AGX_STREAM(5) AGX_STREAM(6) AGX_STREAM(7) AGX_STREAM(8)
+        // longest rows first, launches spread round-robin over st and the auxiliary streams
+        AGX_CUDA(cudaEventRecord(ws.ev_fork, st));
+        int n_launched = 0;
+        bool aux_used[3] = {false, false, false};
+        auto next_stream = [&](cudaStream_t &out) -> int {
+            const int slot = n_launched++ % 4;
+            out = slot == 0 ? st : ws.aux[slot - 1];
+            if (slot > 0 && !aux_used[slot - 1]) {
+                AGX_CUDA(cudaStreamWaitEvent(out, ws.ev_fork, 0));
+                aux_used[slot - 1] = true;
+            }
+            return AGX_OK;
+        };
+#define AGX_STREAM(KK)                                                                              \
+    if (pair_counts[KK - 1] > 0) {                                                                  \
+        cudaStream_t s_;                                                                            \
+        if ((rc = next_stream(s_)) != AGX_OK) return rc;                                            \
+        if ((rc = launch_duo<KK>(v, d_read_out_off, pairs, pair_counts[KK - 1], ws.d_lut, gatk,     \
+                                 codes, codes_bytes, info, sums, s_)) != AGX_OK)                    \
+            return rc;                                                                              \
+    }                                                                                               \
+    if (counts[KK - 1] > 0) {                                                                       \
+        cudaStream_t s_;                                                                            \
+        if ((rc = next_stream(s_)) != AGX_OK) return rc;                                            \
+        if ((rc = launch_stream<KK>(v, d_read_out_off, ws.order, counts[KK - 1], ws.d_lut, gatk,    \
+                                    codes, codes_bytes, info, sums, s_)) != AGX_OK)                 \
+            return rc;                                                                              \
+    }
+        AGX_STREAM(8) AGX_STREAM(7) AGX_STREAM(6) AGX_STREAM(5)
+        AGX_STREAM(4) AGX_STREAM(3) AGX_STREAM(2) AGX_STREAM(1)
 #undef AGX_STREAM
+        for (int i = 0; i < 3; ++i)
+            if (aux_used[i]) {
+                AGX_CUDA(cudaEventRecord(ws.ev_join[i], ws.aux[i]));
+                AGX_CUDA(cudaStreamWaitEvent(st, ws.ev_join[i], 0));
+            }
         ws.prof_stream.end(st);
         if (n_stream > 0) {
-            // classes 0..HMM_MAX_K-1 are contiguous in `order` only per class: finalize class by class
-            for (int c = 0; c < HMM_MAX_K; ++c) {
-                if (counts[c] == 0) continue;
-                hmm_finalize_kernel<<<(counts[c] + 255) / 256, 256, 0, st>>>(
-                    v, d_read_out_off, ws.order + (int64_t)c * v.n_reads, counts[c], sums, d_out, rescue,
-                    rescue_count);
-                count_launch();
-            }
+            hmm_finalize_kernel<<<(int)((v.n_reads + 255) / 256), 256, 0, st>>>(
+                v, d_read_out_off, nullptr, (int32_t)v.n_reads, sums, d_out, rescue, rescue_count);
+            count_launch();
             AGX_CUDA(cudaGetLastError());
         }
         if (counts[HMM_LONG] > 0) {
