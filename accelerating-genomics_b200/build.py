@@ -21,7 +21,7 @@ NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-O3,-Wall", "--expt-relaxed-constexpr"]
 
-LIB_SOURCES = ["api.cu", "sw_kernels.cu", "sw_long.cu", "sw_parse.cu", "pairhmm_kernels.cu"]
+LIB_SOURCES = ["api.cu", "sw_kernels.cu", "sw_long.cu", "sw_parse.cu", "pairhmm_kernels.cu", "pairhmm_parse.cu"]
 
 
 def _run(cmd, **kw):

@@ -24,6 +24,7 @@ SYMBOLS = [
     "agx_version", "agx_launch_count", "agx_reset_launch_count", "agx_set_profiling", "agx_profile_ms",
     "sw_score_batch", "sw_score_batch_flat", "sw_score_batch_device", "sw_score_file_image",
     "pairhmm_forward_batch", "pairhmm_forward_batches_flat", "pairhmm_forward_batches_device",
+    "pairhmm_forward_file_image",
     "agx_pairhmm_set_gatk_mode", "agx_pairhmm_set_force_fp64",
 ]
 
@@ -73,6 +74,9 @@ def load_library() -> C.CDLL:
         [C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int64),
          C.POINTER(C.c_int32)]
     lib.sw_score_file_image.restype = C.c_int
+    lib.pairhmm_forward_file_image.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                                               C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+    lib.pairhmm_forward_file_image.restype = C.c_int
     lib.pairhmm_forward_batch.argtypes = [C.c_int32, pp, pp, pp, pp, pp, i32p, C.c_int32, pp, i32p, f64p]
     lib.pairhmm_forward_batches_flat.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                                  C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
@@ -263,6 +267,24 @@ def pairhmm_forward_flat(buf: np.ndarray, read_field_off: np.ndarray, read_len: 
                                                        _ptr(ho), _ptr(hl), hl.size, _ptr(brs), _ptr(bhs),
                                                        nb, _ptr(out)))
     return out[:n_out]
+
+
+def pairhmm_forward_file_image(image, copy: bool = True):
+    """pairhmm_forward_file_image: the raw pairHMM/test_set-format file image, parsed on the GPU.
+    Returns (log10 values, pairs per batch, incomplete).  With copy=False the arrays alias the library's
+    pinned result buffers (valid until the next PairHMM call)."""
+    img = np.frombuffer(image, dtype=np.uint8) if isinstance(image, (bytes, bytearray)) else _as(image, np.uint8)
+    p_out, p_bp = C.c_void_p(), C.c_void_p()
+    n_out, n_b, inc = C.c_int64(0), C.c_int64(0), C.c_int32(0)
+    _check(load_library().pairhmm_forward_file_image(_ptr(img) if img.size else None, img.size, C.byref(p_out),
+                                                     C.byref(n_out), C.byref(p_bp), C.byref(n_b), C.byref(inc)))
+    vals = np.ctypeslib.as_array(C.cast(p_out, C.POINTER(C.c_double)), shape=(n_out.value,)) if n_out.value else \
+        np.empty(0, np.float64)
+    bp = np.ctypeslib.as_array(C.cast(p_bp, C.POINTER(C.c_int32)), shape=(n_b.value,)) if n_b.value else \
+        np.empty(0, np.int32)
+    if copy:
+        vals, bp = vals.copy(), bp.copy()
+    return vals, bp, int(inc.value)
 
 
 def pairhmm_forward_device(device: int, d_buf: int, buf_bytes: int, d_read_field_off: int,

@@ -125,6 +125,7 @@ struct DeviceCtx {
     SwLane lane[2];          // lane[0].st == stream
     SwWorkspace &sw = lane[0].ws;
     HmmWorkspace hmm;
+    HmmParseWorkspace hmm_parse;
     DevBuf d_bytes, d_a, d_b, d_c, d_d, d_e, d_f, d_out;   // staging for the host entry points
     PinBuf h_a, h_b, h_out;
     std::string error;   // error raised on this device's worker thread
@@ -583,6 +584,7 @@ void agx_shutdown(void)
         for (cudaEvent_t ev : c->lane_done) if (ev) cudaEventDestroy(ev);
         for (cudaEvent_t ev : c->seg_events) cudaEventDestroy(ev);
         hmm_workspace_free(c->hmm);
+        hmm_parse_workspace_free(c->hmm_parse);
         for (DevBuf *b : {&c->d_bytes, &c->d_a, &c->d_b, &c->d_c, &c->d_d, &c->d_e, &c->d_f, &c->d_out}) b->release();
         for (PinBuf *b : {&c->h_a, &c->h_b, &c->h_out}) b->release();
         if (c->stream) cudaStreamDestroy(c->stream);
@@ -858,6 +860,59 @@ int pairhmm_forward_batches_flat(const uint8_t *buf, int64_t buf_bytes, const in
     h.batch_read_start = batch_read_start; h.batch_hap_start = batch_hap_start; h.n_batches = n_batches;
     h.n_pairs = 0;
     return hmm_flat_impl(h, log10_out);
+}
+
+int pairhmm_forward_file_image(const uint8_t *image, int64_t image_bytes, const double **log10_out, int64_t *n_out,
+                               const int32_t **batch_pairs, int64_t *n_batches, int32_t *incomplete)
+{
+    if (log10_out) *log10_out = nullptr;
+    if (n_out) *n_out = 0;
+    if (batch_pairs) *batch_pairs = nullptr;
+    if (n_batches) *n_batches = 0;
+    if (incomplete) *incomplete = 0;
+    if (image_bytes < 0 || (image_bytes > 0 && !image)) return fail(AGX_EINVAL, "pairhmm: null file image");
+    if (!log10_out || !n_out || !batch_pairs || !n_batches) return fail(AGX_EINVAL, "pairhmm: null argument");
+    if (image_bytes == 0) return AGX_OK;
+    int rc = require_init();
+    if (rc != AGX_OK) return rc;
+    DeviceCtx &c = *g_ctx[0];
+    AGX_CUDA(cudaSetDevice(c.device));
+    cudaStream_t st = c.stream;
+    if ((rc = c.d_bytes.reserve((size_t)image_bytes + 64)) != AGX_OK) return rc;
+    AGX_CUDA(cudaMemcpyAsync(c.d_bytes.p, image, (size_t)image_bytes, cudaMemcpyHostToDevice, st));
+    HmmParsed ps;
+    if ((rc = hmm_parse_device(c.hmm_parse, c.d_bytes.as<uint8_t>(), image_bytes, image[image_bytes - 1], &ps, st)) != AGX_OK)
+        return rc;
+    if (incomplete) *incomplete = ps.incomplete;
+    if (ps.n_batches > 0) {
+        if ((rc = c.h_b.reserve((size_t)ps.n_batches * sizeof(int32_t))) != AGX_OK) return rc;
+        AGX_CUDA(cudaMemcpyAsync(c.h_b.p, ps.batch_pairs, (size_t)ps.n_batches * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
+    if (ps.n_out > 0) {
+        if ((rc = c.d_out.reserve((size_t)ps.n_out * sizeof(double))) != AGX_OK) return rc;
+        if ((rc = c.h_out.reserve((size_t)ps.n_out * sizeof(double))) != AGX_OK) return rc;
+        HmmBatchView v;
+        v.buf = c.d_bytes.as<uint8_t>();
+        v.read_field_off = ps.read_field_off;
+        v.read_len = ps.read_len;
+        v.read_batch = ps.read_batch;
+        v.n_reads = ps.n_reads;
+        v.hap_off = ps.hap_off;
+        v.hap_len = ps.hap_len;
+        v.n_haps = ps.n_haps;
+        v.batch_hap_start = ps.batch_hap_start;
+        v.n_batches = ps.n_batches;
+        rc = hmm_run_device(c.hmm, v, image_bytes, ps.read_out_off, ps.n_out, g_gatk.load() != 0, g_force64.load() != 0,
+                            true, c.d_out.as<double>(), st);
+        if (rc != AGX_OK) return rc;
+        AGX_CUDA(cudaMemcpyAsync(c.h_out.p, c.d_out.p, (size_t)ps.n_out * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    AGX_CUDA(cudaStreamSynchronize(st));
+    *n_out = ps.n_out;
+    *n_batches = ps.n_batches;
+    *log10_out = ps.n_out > 0 ? c.h_out.as<double>() : nullptr;
+    *batch_pairs = ps.n_batches > 0 ? c.h_b.as<int32_t>() : nullptr;
+    return AGX_OK;
 }
 
 int pairhmm_forward_batch(int32_t n_reads, const uint8_t *const *bases, const uint8_t *const *q,

@@ -99,6 +99,11 @@ int sw_parse_device(SwParseWorkspace &ws, const uint8_t *d_img, int64_t begin, i
                     int64_t max_chunks, int last_byte, int64_t **d_off, int32_t **d_len, int64_t *n_chunks_out,
                     int64_t *last_off, int32_t *last_len, cudaStream_t st);
 void sw_parse_workspace_free(SwParseWorkspace &ws);
+// shared text-indexing pieces (sw_parse.cu), also used by the PairHMM file parser
+int text_newline_index(SwParseWorkspace &ws, const uint8_t *d_img, int64_t begin, int64_t end, int64_t extra_bytes_per_line,
+                       int64_t **d_nl_pos, int64_t *n_nl_out, void **d_extra, cudaStream_t st);
+int device_exclusive_scan(const int32_t *in, int64_t n, int64_t *out, int64_t *tmp, int64_t *d_total, cudaStream_t st);
+int64_t device_scan_tmp_elems(int64_t n);
 
 // ---- PairHMM ------------------------------------------------------------------------------
 struct HmmWorkspace {
@@ -135,6 +140,28 @@ struct HmmBatchView {
     const int64_t *batch_hap_start; // [n_batches+1]
     int64_t n_batches;
 };
+
+// device-side parser of the pairHMM/test_set text format (pairhmm_parse.cu)
+struct HmmParseWorkspace {
+    SwParseWorkspace idx;     // newline index
+    void *buf = nullptr;      // per-line flags / ranks, scan temporaries, info block
+    int64_t cap = 0;
+    void *tables = nullptr;   // per-batch tables
+    int64_t cap_tables = 0;
+    void *arrays = nullptr;   // per-read / per-haplotype arrays
+    int64_t cap_arrays = 0;
+    int64_t *h_info = nullptr;
+};
+struct HmmParsed {            // device pointers into the workspace
+    int64_t n_batches = 0, n_reads = 0, n_haps = 0, n_out = 0;
+    int32_t incomplete = 0;   // 1: EOF inside the reads of a last batch, 2: inside its haplotypes (batch dropped)
+    int64_t *read_field_off = nullptr, *read_out_off = nullptr, *hap_off = nullptr;
+    int32_t *read_len = nullptr, *read_batch = nullptr, *hap_len = nullptr, *batch_pairs = nullptr;
+    int64_t *batch_read_start = nullptr, *batch_hap_start = nullptr, *batch_out_start = nullptr;
+};
+int hmm_parse_device(HmmParseWorkspace &ws, const uint8_t *d_img, int64_t bytes, int last_byte, HmmParsed *out,
+                     cudaStream_t st);
+void hmm_parse_workspace_free(HmmParseWorkspace &ws);
 
 int hmm_workspace_reserve(HmmWorkspace &ws, int64_t n_reads, int64_t n_pairs, int64_t n_batches);
 void hmm_workspace_free(HmmWorkspace &ws);

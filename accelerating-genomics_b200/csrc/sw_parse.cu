@@ -230,6 +230,64 @@ chunk_emit_kernel(const int64_t *__restrict__ nl_pos, int64_t n_nl, int64_t begi
 
 }  // namespace
 
+int device_exclusive_scan(const int32_t *in, int64_t n, int64_t *out, int64_t *tmp, int64_t *d_total, cudaStream_t st)
+{
+    return exclusive_scan(in, n, out, tmp, d_total, st);
+}
+int64_t device_scan_tmp_elems(int64_t n) { return n / SCAN_TILE + 2; }
+
+// Position of every '\n' in d_img[begin, end), in order.  *d_nl_pos points into ws.buf2 (n_nl int64 followed
+// by `extra_bytes` the caller may use).  Synchronises `st` once (the newline count sizes the table).
+int text_newline_index(SwParseWorkspace &ws, const uint8_t *d_img, int64_t begin, int64_t end, int64_t extra_bytes_per_line,
+                       int64_t **d_nl_pos, int64_t *n_nl_out, void **d_extra, cudaStream_t st)
+{
+    *d_nl_pos = nullptr;
+    *n_nl_out = 0;
+    if (d_extra) *d_extra = nullptr;
+    if (end <= begin) return AGX_OK;
+    const int64_t tiles = (end - (begin & ~(int64_t)15) + TILE_BYTES - 1) / TILE_BYTES;
+    if (!ws.h_total) AGX_CUDA(cudaMallocHost(&ws.h_total, 4 * sizeof(int64_t)));
+    auto align = [](int64_t x) { return (x + 255) / 256 * 256; };
+    const int64_t sz_tc = align(tiles * 4), sz_tb = align(tiles * 8), sz_tmp = align((tiles / SCAN_TILE + 2) * 8);
+    const int64_t need = sz_tc + sz_tb + sz_tmp + 256;
+    if (need > ws.cap) {
+        if (ws.buf) cudaFree(ws.buf);
+        ws.buf = nullptr; ws.cap = 0;
+        AGX_CUDA(cudaMalloc(&ws.buf, (size_t)need));
+        ws.cap = need;
+    }
+    uint8_t *base = reinterpret_cast<uint8_t *>(ws.buf);
+    int32_t *tile_count = reinterpret_cast<int32_t *>(base);
+    int64_t *tile_base64 = reinterpret_cast<int64_t *>(base + sz_tc);
+    int64_t *tmp = reinterpret_cast<int64_t *>(base + sz_tc + sz_tb);
+    int64_t *d_total = reinterpret_cast<int64_t *>(base + sz_tc + sz_tb + sz_tmp);
+    nl_count_kernel<<<(int)tiles, TILE_THREADS, 0, st>>>(d_img, begin, end, tile_count);
+    count_launch();
+    AGX_CUDA(cudaGetLastError());
+    int rc = exclusive_scan(tile_count, tiles, tile_base64, tmp, d_total, st);
+    if (rc != AGX_OK) return rc;
+    AGX_CUDA(cudaMemcpyAsync(ws.h_total, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    AGX_CUDA(cudaStreamSynchronize(st));
+    const int64_t n_nl = ws.h_total[0];
+    if (n_nl > (int64_t)1 << 31) return fail(AGX_ERANGE, "more than 2^31 lines");
+    const int64_t sz_np = align(std::max<int64_t>(n_nl, 1) * 8);
+    const int64_t need2 = sz_np + align((n_nl + 2) * extra_bytes_per_line) + 256;
+    if (need2 > ws.cap2) {
+        if (ws.buf2) cudaFree(ws.buf2);
+        ws.buf2 = nullptr; ws.cap2 = 0;
+        AGX_CUDA(cudaMalloc(&ws.buf2, (size_t)need2));
+        ws.cap2 = need2;
+    }
+    int64_t *nl_pos = reinterpret_cast<int64_t *>(ws.buf2);
+    nl_emit_kernel<<<(int)tiles, TILE_THREADS, 0, st>>>(d_img, begin, end, tile_base64, nl_pos);
+    count_launch();
+    AGX_CUDA(cudaGetLastError());
+    *d_nl_pos = nl_pos;
+    *n_nl_out = n_nl;
+    if (d_extra) *d_extra = reinterpret_cast<uint8_t *>(ws.buf2) + sz_np;
+    return AGX_OK;
+}
+
 void sw_parse_workspace_free(SwParseWorkspace &ws)
 {
     if (ws.buf) cudaFree(ws.buf);

@@ -10,8 +10,11 @@
  *     line buffer 5001 bytes (:353);
  *   - stdout: "#batch: %d" before every batch and once more at EOF (:372), each likelihood "%f"
  *     (:459); output file: one "%f" per (read, haplotype), read-major (:461).
- * The prior setup, the M/X/Y recurrence and the final log10 sum (:99-117, :120-242) run on the
- * GPU(s) through pairhmm_forward_batches_flat(); AGX_NUM_GPUS=<n> limits the devices (default: all);
+ * The file image is handed to pairhmm_forward_file_image(): the batch walk / field splitting
+ * (:375-441), the prior setup, the M/X/Y recurrence and the final log10 sum (:99-117, :120-242) all run
+ * on the GPU.  Only a file with a line longer than the reference's 5000-byte fgets() buffer -- which the
+ * reference would read in pieces -- is split on the host below and goes through
+ * pairhmm_forward_batches_flat() instead.  AGX_NUM_GPUS=<n> limits the devices (default: all);
  * AGX_PAIRHMM_GATK=1 selects the corrected GATK mismatch prior (Qr/3), which is NOT the
  * reference's semantics; AGX_PAIRHMM_FP64=1 sends every pair through the FP64 kernel that keeps
  * the reference's own operation order.  There is no CPU fallback.
@@ -59,34 +62,10 @@ static int next_line(const unsigned char *img, size_t size, size_t *pos, size_t 
     return 1;
 }
 
-int main(int argc, const char *argv[])
+/* Host-side fgets() walk (antidiagsPairHMM.c:375-441) for files whose lines exceed the line buffer. */
+static int split_on_host(const unsigned char *img, size_t size, double **lh_out, int64_t *n_out_p,
+                         int32_t **bp_out, int64_t *n_batches_p, const char **err_p)
 {
-    if (argc != 3) {
-        fprintf(stderr, "Usage: %s <input_file_r> <output_file>\n", argv[0]);
-        return EXIT_FAILURE;
-    }
-    FILE *in = fopen(argv[1], "rb");
-    if (in == NULL) {
-        perror("Error opening input file_r");
-        return EXIT_FAILURE;
-    }
-    FILE *out = fopen(argv[2], "w");
-    if (out == NULL) {
-        perror("Error opening output file");
-        fclose(in);
-        return EXIT_FAILURE;
-    }
-    size_t cap = 1 << 20, size = 0;
-    unsigned char *img = malloc(cap);
-    for (;;) {
-        if (size == cap) { cap *= 2; img = realloc(img, cap); }
-        if (!img) { fprintf(stderr, "out of memory\n"); return EXIT_FAILURE; }
-        size_t got = fread(img + size, 1, cap - size, in);
-        if (got == 0) break;
-        size += got;
-    }
-    fclose(in);
-
     vec64 rfo = {0}, ho = {0}, brs = {0}, bhs = {0};
     vec32 rl = {0}, hl = {0};
     push64(&brs, 0);
@@ -128,34 +107,90 @@ int main(int argc, const char *argv[])
     }
     const int64_t n_batches = (int64_t)brs.n - 1;
     int64_t n_out = 0;
-    for (int64_t b = 0; b < n_batches; b++)
-        n_out += (brs.v[b + 1] - brs.v[b]) * (bhs.v[b + 1] - bhs.v[b]);
-
+    int32_t *bp = malloc((size_t)(n_batches > 0 ? n_batches : 1) * sizeof *bp);
+    for (int64_t b = 0; b < n_batches; b++) {
+        bp[b] = (int32_t)((brs.v[b + 1] - brs.v[b]) * (bhs.v[b + 1] - bhs.v[b]));
+        n_out += bp[b];
+    }
     double *lh = malloc((size_t)(n_out > 0 ? n_out : 1) * sizeof *lh);
-    if (n_out > 0) {
-        int n_gpus = 0;
-        const char *env = getenv("AGX_NUM_GPUS");
-        if (env) n_gpus = atoi(env);
-        if (agx_init(n_gpus) != AGX_OK) {
-            fprintf(stderr, "Error: %s\n", agx_last_error());
-            return EXIT_FAILURE;
-        }
-        env = getenv("AGX_PAIRHMM_GATK");
-        if (env && atoi(env)) agx_pairhmm_set_gatk_mode(1);
-        env = getenv("AGX_PAIRHMM_FP64");   /* every pair through the exact-order FP64 kernel */
-        if (env && atoi(env)) agx_pairhmm_set_force_fp64(1);
-        int rc = pairhmm_forward_batches_flat(img, (int64_t)size, rfo.v, rl.v, (int64_t)rl.n, ho.v, hl.v,
-                                              (int64_t)hl.n, brs.v, bhs.v, n_batches, lh);
-        if (rc != AGX_OK) {
-            fprintf(stderr, "Error: code: %d, reason: %s\n", rc, agx_last_error());
-            return EXIT_FAILURE;
-        }
+    int rc = AGX_OK;
+    if (n_out > 0)
+        rc = pairhmm_forward_batches_flat(img, (int64_t)size, rfo.v, rl.v, (int64_t)rl.n, ho.v, hl.v,
+                                          (int64_t)hl.n, brs.v, bhs.v, n_batches, lh);
+    free(rfo.v); free(ho.v); free(brs.v); free(bhs.v); free(rl.v); free(hl.v);
+    *lh_out = lh;
+    *n_out_p = n_out;
+    *bp_out = bp;
+    *n_batches_p = n_batches;
+    *err_p = err;
+    return rc;
+}
+
+int main(int argc, const char *argv[])
+{
+    if (argc != 3) {
+        fprintf(stderr, "Usage: %s <input_file_r> <output_file>\n", argv[0]);
+        return EXIT_FAILURE;
+    }
+    FILE *in = fopen(argv[1], "rb");
+    if (in == NULL) {
+        perror("Error opening input file_r");
+        return EXIT_FAILURE;
+    }
+    FILE *out = fopen(argv[2], "w");
+    if (out == NULL) {
+        perror("Error opening output file");
+        fclose(in);
+        return EXIT_FAILURE;
+    }
+    size_t cap = 1 << 20, size = 0;
+    unsigned char *img = malloc(cap);
+    for (;;) {
+        if (size == cap) { cap *= 2; img = realloc(img, cap); }
+        if (!img) { fprintf(stderr, "out of memory\n"); return EXIT_FAILURE; }
+        size_t got = fread(img + size, 1, cap - size, in);
+        if (got == 0) break;
+        size += got;
+    }
+    fclose(in);
+
+    int n_gpus = 0;
+    const char *env = getenv("AGX_NUM_GPUS");
+    if (env) n_gpus = atoi(env);
+    if (agx_init(n_gpus) != AGX_OK) {
+        fprintf(stderr, "Error: %s\n", agx_last_error());
+        return EXIT_FAILURE;
+    }
+    env = getenv("AGX_PAIRHMM_GATK");
+    if (env && atoi(env)) agx_pairhmm_set_gatk_mode(1);
+    env = getenv("AGX_PAIRHMM_FP64");   /* every pair through the exact-order FP64 kernel */
+    if (env && atoi(env)) agx_pairhmm_set_force_fp64(1);
+
+    const char *err = NULL;
+    const double *lh = NULL;
+    const int32_t *batch_pairs = NULL;
+    int64_t n_out = 0, n_batches = 0;
+    int32_t incomplete = 0;
+    double *lh_host = NULL;          /* host-split path only */
+    int32_t *bp_host = NULL;
+    int rc = pairhmm_forward_file_image(img, (int64_t)size, &lh, &n_out, &batch_pairs, &n_batches, &incomplete);
+    if (rc == AGX_OK) {
+        if (incomplete == 1) err = "Error reading reads.\n";
+        if (incomplete == 2) err = "Error reading haplotypes.\n";
+    } else if (rc == AGX_ERANGE && strstr(agx_last_error(), "line buffer")) {
+        rc = split_on_host(img, size, &lh_host, &n_out, &bp_host, &n_batches, &err);
+        lh = lh_host;
+        batch_pairs = bp_host;
+    }
+    if (rc != AGX_OK) {
+        fprintf(stderr, "Error: code: %d, reason: %s\n", rc, agx_last_error());
+        return EXIT_FAILURE;
     }
     int64_t o = 0;
     int iteration = 1;
     for (int64_t b = 0; b < n_batches; b++, iteration++) {
         printf("#batch: %d\n", iteration);
-        int64_t cnt = (brs.v[b + 1] - brs.v[b]) * (bhs.v[b + 1] - bhs.v[b]);
+        int64_t cnt = batch_pairs[b];
         for (int64_t k = 0; k < cnt; k++, o++) {
             printf("%f\n", lh[o]);
             fprintf(out, "%f\n", lh[o]);
@@ -169,7 +204,8 @@ int main(int argc, const char *argv[])
     }
     fclose(out);
     agx_shutdown();
-    free(lh);
+    free(lh_host);
+    free(bp_host);
     free(img);
     return EXIT_SUCCESS;
 }

@@ -154,6 +154,22 @@ int pairhmm_forward_batches_flat(const uint8_t *buf, int64_t buf_bytes,
                                  const int64_t *batch_hap_start, int64_t n_batches,
                                  double *log10_out);
 
+/* A whole pairHMM/test_set-style FILE IMAGE: the batch walk of antidiagsPairHMM.c:375-441 (header line
+ * "<num_read> <num_haplotypes>", read lines of five whitespace-separated fields with read length
+ * (line length - 4) / 5 (:418), haplotype lines) is reproduced on the GPU (pairhmm_parse.cu), so the
+ * caller builds no index arrays and does not need to know the number of results beforehand:
+ * *log10_out points at *n_out values, batches in file order, read-major inside a batch (the reference's
+ * output order :459-461), and *batch_pairs at *n_batches counts (reads x haplotypes of each batch: what a
+ * driver needs to print "#batch: %d" between them).  Both arrays live in pinned host memory OWNED BY THE
+ * LIBRARY and stay valid until the next PairHMM call or agx_shutdown().  *incomplete = 1 / 2 when the
+ * file ends inside the reads / haplotypes of a last batch: that batch is dropped; the reference prints
+ * "Error reading reads." / "Error reading haplotypes." after the earlier ones (:405, :431).
+ * AGX_ERANGE when a line exceeds the reference's 5000-byte line buffer (:353) or a read length falls
+ * outside [1, 8192].  Runs on the first configured GPU. */
+int pairhmm_forward_file_image(const uint8_t *image, int64_t image_bytes, const double **log10_out,
+                               int64_t *n_out, const int32_t **batch_pairs, int64_t *n_batches,
+                               int32_t *incomplete);
+
 /* Device-resident variant for one GPU (all pointers device pointers on `device`, work ordered on
  * `stream`).  d_read_batch[r] is the batch of read r; d_read_out_off[r] is the index in
  * d_log10_out of (read r, first haplotype of its batch); n_pairs = sum_b nr_b*nh_b.

@@ -144,3 +144,76 @@ def test_device_resident_entry_point(agx, gpu_lib, oracle_mod):
     assert np.allclose(got, _run_flat(gpu_lib, inp), rtol=0, atol=0)
     want = oracle_mod.pairhmm_flat(inp, limit=300)
     assert _rel_err(got[:300], want) <= REL_TOL
+
+
+# ---------------------------------------------------------------- device-side file parser (pairhmm_forward_file_image)
+@pytest.mark.parametrize("name", GOLDENS)
+def test_file_image_entry_point_equals_host_parsed_call(agx, gpu_lib, name):
+    """Batch walk, field splitting and index arrays built on the GPU give the values of the host-parsed call."""
+    data = read_golden(f"{name}.in")
+    inp = agx.formats.parse_pairhmm(data)
+    vals, batch_pairs, incomplete = gpu_lib.pairhmm_forward_file_image(data)
+    assert incomplete == 0
+    assert batch_pairs.tolist() == (np.diff(inp.batch_read_start) * np.diff(inp.batch_hap_start)).tolist()
+    assert np.array_equal(vals, _run_flat(gpu_lib, inp))
+    ref = np.array([float(x) for x in (GOLDEN / f"{name}.pairhmm_antidiag.out").read_text().split()])
+    assert np.all(np.abs(vals - ref) <= REL_TOL * np.abs(ref) + PRINT_EPS)
+
+
+def _small_batches(agx, seed, n_batches=7):
+    inp = agx.synth.pairhmm_batches(n_batches, 9, 3, seed=seed)
+    return inp, bytes(inp.buf)
+
+
+def test_file_image_irregular_headers_follow_the_reference_walk(agx, gpu_lib):
+    """Headers that sscanf("%d %d") accepts but that are not plain 'digits blank digits' lines (leading
+    blanks, '+', trailing text), an empty batch and a last line without newline."""
+    inp, data = _small_batches(agx, 3)
+    lines = data.split(b"\n")
+    assert lines[-1] == b""
+    lines = lines[:-1]
+    heads = [i for i, l in enumerate(lines) if len(l.split()) == 2 and l.split()[0].isdigit()]
+    assert len(heads) == 7
+    a, b = lines[heads[1]].split()
+    lines[heads[1]] = b"  " + a + b"\t " + b
+    a, b = lines[heads[2]].split()
+    lines[heads[2]] = b"+" + a + b" " + b + b" trailing words"
+    lines.insert(heads[3], b"0 0")                      # a batch with nothing in it
+    mod = b"\n".join(lines)                             # and no newline after the last haplotype
+    host = agx.formats.parse_pairhmm(mod)
+    assert host.n_batches == 8
+    vals, batch_pairs, incomplete = gpu_lib.pairhmm_forward_file_image(mod)
+    assert incomplete == 0
+    assert batch_pairs.tolist() == (np.diff(host.batch_read_start) * np.diff(host.batch_hap_start)).tolist()
+    assert np.array_equal(vals, _run_flat(gpu_lib, host))
+    assert np.array_equal(vals, _run_flat(gpu_lib, inp))
+
+
+@pytest.mark.parametrize("cut,code", [("reads", 1), ("haps", 2)])
+def test_file_image_truncated_last_batch(agx, gpu_lib, cut, code):
+    inp, data = _small_batches(agx, 5, n_batches=4)
+    lines = data.split(b"\n")[:-1]
+    # batch = 1 header + 9 reads + 3 haplotypes = 13 lines; cut inside the last batch
+    keep = 3 * 13 + (1 + 4 if cut == "reads" else 1 + 9 + 1)
+    mod = b"\n".join(lines[:keep]) + b"\n"
+    vals, batch_pairs, incomplete = gpu_lib.pairhmm_forward_file_image(mod)
+    assert incomplete == code and batch_pairs.tolist() == [27, 27, 27]
+    assert np.array_equal(vals, _run_flat(gpu_lib, inp)[:81])
+
+
+def test_file_image_rejects_lines_beyond_the_reference_line_buffer(agx, gpu_lib):
+    hap = b"ACGT" * 1300                                 # 5200 > 5000
+    read = (b"ACGTACGTAC", b"IIIIIIIIII", b"NNNNNNNNNN", b"NNNNNNNNNN", b"++++++++++")
+    data = agx.formats.write_pairhmm([([read], [hap])])
+    with pytest.raises(gpu_lib.AgxError) as e:
+        gpu_lib.pairhmm_forward_file_image(data)
+    assert "line buffer" in str(e.value)
+    with pytest.raises(gpu_lib.AgxError):
+        gpu_lib.pairhmm_forward_file_image(b"1 1\nAC II\nACGT\n")      # fewer than five fields
+
+
+def test_file_image_config4_shape(agx, gpu_lib):
+    inp = agx.synth.pairhmm_batches(40, 200, 5, seed=17)
+    vals, batch_pairs, incomplete = gpu_lib.pairhmm_forward_file_image(inp.buf)
+    assert incomplete == 0 and batch_pairs.tolist() == [1000] * 40
+    assert np.array_equal(vals, _run_flat(gpu_lib, inp))
