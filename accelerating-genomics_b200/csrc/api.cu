@@ -348,7 +348,9 @@ int sw_flat_impl(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *off, co
         std::vector<SwLongWorkspace *> wss;
         for (auto &c : g_ctx) { devs.push_back(c->device); sts.push_back(c->stream); wss.push_back(&c->sw.lng); }
         for (int64_t p : giants) {
-            const int hi = len[2 * p] >= len[2 * p + 1] ? 0 : 1;
+            // columns = the longer sequence (more stripes in flight); AGX_LONG_SWAP flips that for experiments
+            int hi = len[2 * p] >= len[2 * p + 1] ? 0 : 1;
+            if (getenv("AGX_LONG_SWAP")) hi = 1 - hi;
             rc = sw_long_host_multi((int)devs.size(), devs.data(), sts.data(), wss.data(), seqs + off[2 * p + hi],
                                     len[2 * p + hi], seqs + off[2 * p + 1 - hi], len[2 * p + 1 - hi], sc,
                                     scores_out + p);

@@ -7,17 +7,19 @@
 // stripe j may process row block i as soon as stripe j-1 has published the right boundary column
 // (H+goe and E per row) of that block.
 //
-//   - ONE boundary array of 2*rows int32 per GPU is shared by all stripes and updated in place: the
-//     region of row block i always holds the boundary of the last stripe that passed it, and stripes
-//     pass a block strictly in order.
-//   - progress[j] (one int per stripe) counts the row blocks whose boundary stripe j-1 has published for
-//     stripe j; a warp spins on it with __nanosleep back-off.  All warps are co-resident (cooperative
-//     launch), so the wait always ends.
-//   - Multi-GPU: GPU g owns a contiguous range of columns.  The last stripe of GPU g writes its
-//     boundary column straight into GPU g+1's boundary array and bumps GPU g+1's progress[0] with
-//     peer stores over NVLink (cudaDeviceEnablePeerAccess); no collective is involved, the final
-//     score is the max of the per-GPU maxima.
+//   - ONE boundary array per GPU (one 16-byte entry per row) is shared by all stripes and updated in
+//     place: entry r always holds the boundary of the last stripe that passed row r, and stripes pass a
+//     row strictly in order.
+//   - An entry is {H+goe, tag, E, tag} with tag = the (global) index of the stripe that wrote it, stored
+//     with ONE 128-bit store.  The consumer polls the data itself: no flags, no fences, one memory round
+//     trip per hand-off, and the entries of the next 32 rows are requested a whole block ahead, so the
+//     latency of the hand-off is off the critical path whenever the producer is a block ahead.  All warps
+//     are co-resident (cooperative launch), so a poll always ends.
+//   - Multi-GPU: GPU g owns a contiguous range of columns.  The last stripe of GPU g writes its entries
+//     straight into GPU g+1's boundary array with peer stores over NVLink (cudaDeviceEnablePeerAccess);
+//     no collective is involved, the final score is the max of the per-GPU maxima.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <thread>
 #include <vector>
@@ -30,31 +32,57 @@ namespace {
 
 constexpr int LONG_WARPS = 4;     // warps per CTA
 constexpr int LONG_RING = 64;
-constexpr int LONG_RB_DEFAULT = 32;   // rows per published block (multiple of 32)
 
 struct LongArgs {
     const uint8_t *a;         // columns owned by this GPU
     int32_t la;
     const uint8_t *b;         // rows
     int32_t lb;
-    int32_t *bnd;             // [2 * lb] local boundary array (in place)
-    int32_t *progress;        // [n_stripes + 1]; progress[j] gates stripe j
-    int32_t *next_bnd;        // boundary array of the next GPU (peer) or nullptr
-    int32_t *next_progress;   // &progress[0] of the next GPU (peer) or nullptr
+    int4 *bnd;                // [lb] local boundary entries (in place)
+    int4 *next_bnd;           // boundary array of the next GPU (peer) or nullptr
     int32_t *best;            // running maximum (atomicMax)
-    int32_t first_gpu;        // stripe 0 of this GPU is the true left edge of the matrix
-    int32_t rb;               // rows per published block (multiple of 32)
+    int32_t stripe_base;      // global index of this GPU's stripe 0 (0: the true left edge of the matrix)
     SwScoring sc;
 };
 
-// acquire loads of a progress counter: .gpu for a counter written on this GPU, .sys for the one a peer
-// GPU bumps over NVLink
-__device__ __forceinline__ int32_t ld_acquire(const int32_t *p, bool sys)
+// A boundary entry may be (re)written by another SM or by a peer GPU while it is polled: relaxed (strong)
+// accesses at the narrowest scope that covers writer and reader -- .gpu inside one GPU, .sys across NVLink.
+// 1: request the next block's entries a block ahead (needs a two-block start-up slack); 0: read them when
+// the block starts.  Measured on B200 (125 kbp x 1 Mbp share of an 8-GPU run): 0 is 5-10 % faster.
+#ifndef AGX_LONG_PREFETCH
+#define AGX_LONG_PREFETCH 0
+#endif
+#ifndef AGX_LONG_MEMOPS
+#define AGX_LONG_MEMOPS 1
+#endif
+__device__ __forceinline__ int4 ld_entry(const int4 *p, bool sys)
 {
-    int32_t v;
-    if (sys) asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    else     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    int4 v;
+#if AGX_LONG_MEMOPS == 0
+    asm volatile("ld.volatile.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+#else
+    if (sys)
+        asm volatile("ld.relaxed.sys.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    else
+        asm volatile("ld.relaxed.gpu.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+#endif
     return v;
+}
+__device__ __forceinline__ void st_entry(int4 *p, int4 v, bool sys)
+{
+#if AGX_LONG_MEMOPS == 0
+    asm volatile("st.volatile.global.v4.s32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#elif AGX_LONG_MEMOPS == 2
+    if (sys)
+        asm volatile("st.relaxed.sys.global.v4.s32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else
+        asm volatile("st.global.cg.v4.s32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+#else
+    if (sys)
+        asm volatile("st.relaxed.sys.global.v4.s32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else
+        asm volatile("st.relaxed.gpu.global.v4.s32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#endif
 }
 
 template <int K, bool SHORT>
@@ -65,6 +93,7 @@ sw_long_kernel(LongArgs g)
     __shared__ int32_t r_byte[LONG_WARPS][LONG_RING];
     __shared__ int32_t r_g[LONG_WARPS][LONG_RING];
     __shared__ int32_t r_e[LONG_WARPS][LONG_RING];
+    __shared__ int2 stage[LONG_WARPS][32];      // boundary of the rows finished in the current block
 
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -75,8 +104,6 @@ sw_long_kernel(LongArgs g)
     const int32_t sub_match = g.sc.match - goe, sub_mis = g.sc.mismatch - goe;
     const int32_t lb = g.lb;
     const int n_stripes = (g.la + W - 1) / W;
-    const int LONG_RB = g.rb;
-    const int n_blocks = (lb + LONG_RB - 1) / LONG_RB;
     int32_t bestg = goe;          // running max of H + goe
 
     for (int st = warp; st < n_stripes; st += n_warps) {
@@ -89,51 +116,79 @@ sw_long_kernel(LongArgs g)
             F[j] = goe;
         }
         int32_t g_out = goe, e_out = goe, g_in_prev = goe;
-        const bool left_edge = (st == 0) && g.first_gpu;
+        const int32_t gst = g.stripe_base + st;                          // global stripe index = my tag
+        const bool left_edge = (gst == 0);
         const bool last = (st == n_stripes - 1);
-        int32_t *out_bnd = last ? g.next_bnd : g.bnd;                    // nullptr: nothing to publish
-        int32_t *out_prog = last ? g.next_progress : (g.progress + st + 1);
-        const bool remote = last && g.next_bnd != nullptr;
-        const bool gate_is_remote = (st == 0) && !g.first_gpu;
+        int4 *out_bnd = last ? g.next_bnd : g.bnd;                       // nullptr: nothing to hand on
+        const bool out_remote = last;                                    // the next GPU's array, over NVLink
+        const bool in_remote = (st == 0);                                // written by the previous GPU
         const int S = lb + 31;
-        int published = 0;
+
+#if AGX_LONG_PREFETCH
+        // Slack: a stripe starts only when the left neighbour has handed on TWO blocks of rows.  From then
+        // on both advance at the same pace, so the entries requested at the top of a block (for the next
+        // block) were written a whole block earlier and their latency hides behind 32 row steps; a stripe
+        // that has to poll has lost its slack and takes a short extra nap to get it back.
+        // (polling is warp-uniform: lanes that diverge inside a sleep loop would sleep one after the other)
+        if (!left_edge) {
+            const bool mine = lane + 32 < lb;
+            int4 probe = make_int4(0, gst - 1, 0, gst - 1);
+            if (mine) probe = ld_entry(g.bnd + 32 + lane, in_remote);
+            unsigned ns = 64;
+            while (__any_sync(0xffffffffu, probe.y != gst - 1 || probe.w != gst - 1)) {
+                __nanosleep(ns);
+                if (ns < 1024) ns *= 2;
+                if (mine) probe = ld_entry(g.bnd + 32 + lane, in_remote);
+            }
+        }
+#endif
+        // inputs of the first 32 rows
+        int32_t nb = 0x200;
+        int4 nx = make_int4(goe, gst - 1, goe, gst - 1);
+        if (lane < lb) {
+            nb = g.b[lane];
+            if (!left_edge) nx = ld_entry(g.bnd + lane, in_remote);
+        }
         for (int s0 = 0; s0 < S; s0 += 32) {
-            // publish the row blocks whose boundary writes are complete (rows < s0 - 31)
-            if (out_bnd != nullptr) {
-                const int done = (s0 >= 32) ? min(n_blocks, (s0 - 32) / LONG_RB) : 0;
-                if (done > published) {
-                    __syncwarp();
-                    if (lane == 31) {
-                        if (remote) __threadfence_system(); else __threadfence();
-                        *((volatile int32_t *)out_prog) = done;
-                    }
-                    published = done;
-                }
-            }
-            // wait until the left neighbour has published the block these 32 rows belong to
-            if (!left_edge && s0 < lb) {
-                const int need = min(n_blocks, s0 / LONG_RB + 1);
-                if (lane == 0) {
-                    unsigned ns = 32;
-                    while (ld_acquire(g.progress + st, gate_is_remote) < need) {
-                        __nanosleep(ns);
-                        if (ns < 1024) ns *= 2;
-                    }
-                }
-                __syncwarp();
-            }
             {
                 const int r = s0 + lane;
-                int32_t bb = 0x200, gi = goe, ei = goe;
-                if (r < lb) {
-                    bb = g.b[r];
-                    if (!left_edge) { gi = __ldcg(g.bnd + 2 * (int64_t)r); ei = __ldcg(g.bnd + 2 * (int64_t)r + 1); }
+                if (!left_edge) {
+                    // normally valid already (requested a block ago, written two blocks ago)
+                    unsigned ns = 32;
+                    bool polled = false;
+                    while (__any_sync(0xffffffffu, nx.y != gst - 1 || nx.w != gst - 1)) {
+                        __nanosleep(ns);
+                        if (ns < 512) ns *= 2;
+                        if (r < lb && (nx.y != gst - 1 || nx.w != gst - 1)) nx = ld_entry(g.bnd + r, in_remote);
+                        polled = true;
+                    }
+#if AGX_LONG_PREFETCH
+                    if (polled) __nanosleep(600);
+#else
+                    (void)polled;
+#endif
                 }
-                r_byte[wib][r & (LONG_RING - 1)] = bb;
-                r_g[wib][r & (LONG_RING - 1)] = gi;
-                r_e[wib][r & (LONG_RING - 1)] = ei;
+                r_byte[wib][r & (LONG_RING - 1)] = nb;
+                r_g[wib][r & (LONG_RING - 1)] = nx.x;
+                r_e[wib][r & (LONG_RING - 1)] = nx.z;
             }
             __syncwarp();
+#if AGX_LONG_PREFETCH
+            {
+                // request the next block's inputs now; they are checked when that block starts
+                const int r = s0 + 32 + lane;
+                nb = 0x200;
+                nx = make_int4(goe, gst - 1, goe, gst - 1);
+                if (r < lb) {
+                    nb = g.b[r];
+#if AGX_LONG_PREFETCH == 2
+                    if (!left_edge) nx = __ldcg(g.bnd + r);
+#else
+                    if (!left_edge) nx = ld_entry(g.bnd + r, in_remote);
+#endif
+                }
+            }
+#endif
             const int send = min(32, S - s0);
 #pragma unroll 1
             for (int u = 0; u < send; ++u) {
@@ -163,7 +218,8 @@ sw_long_kernel(LongArgs g)
                         gleft = max(e + goe, tg);                                  // H[i][j] + goe
                         Gp[j] = gleft;
                         tg_prev = tg;
-                        bestg = max(bestg, gleft);
+                        if (j & 1) bestg = __vimax3_s32(bestg, Gp[j - 1], gleft);
+                        else if (j == K - 1) bestg = max(bestg, gleft);
                     }
                 } else {
 #pragma unroll
@@ -175,24 +231,35 @@ sw_long_kernel(LongArgs g)
                         gdiag = Gp[j];
                         gleft = hcell + goe;
                         Gp[j] = gleft;
-                        bestg = max(bestg, gleft);
+                        if (j & 1) bestg = __vimax3_s32(bestg, Gp[j - 1], gleft);
+                        else if (j == K - 1) bestg = max(bestg, gleft);
                     }
                 }
                 g_out = gleft;
                 e_out = e;
-                const int r = s - 31;
-                if (out_bnd != nullptr && lane == 31 && r >= 0 && r < lb) {
-                    out_bnd[2 * (int64_t)r] = g_out;
-                    out_bnd[2 * (int64_t)r + 1] = e_out;
+                // lane 31 has just finished row s - 31 of the stripe's last column: stage it for the flush
+                if (lane == 31) stage[wib][u] = make_int2(g_out, e_out);
+            }
+#if !AGX_LONG_PREFETCH
+            {
+                const int r = s0 + 32 + lane;
+                nb = 0x200;
+                nx = make_int4(goe, gst - 1, goe, gst - 1);
+                if (r < lb) {
+                    nb = g.b[r];
+                    if (!left_edge) nx = ld_entry(g.bnd + r, in_remote);
                 }
             }
-        }
-        // every row of this stripe is written: publish the last blocks
-        if (out_bnd != nullptr) {
-            __syncwarp();
-            if (lane == 31) {
-                if (remote) __threadfence_system(); else __threadfence();
-                *((volatile int32_t *)out_prog) = n_blocks;
+#endif
+            // hand the rows completed in this block (s0 - 31 .. s0) on with one 128-bit store per lane
+            if (out_bnd != nullptr) {
+                __syncwarp();
+                const int r = s0 - 31 + lane;
+                if (lane < send && r >= 0 && r < lb) {
+                    const int2 ge = stage[wib][lane];
+                    st_entry(out_bnd + r, make_int4(ge.x, gst, ge.y, gst), out_remote);
+                }
+                __syncwarp();
             }
         }
         __syncwarp();
@@ -227,20 +294,41 @@ int env_int(const char *name, int dflt)
     return (e && atoi(e) > 0) ? atoi(e) : dflt;
 }
 
-// Stripe width.  The stripe wavefront costs (total stripes x hop + rows) steps, so stripes should be as
-// wide as the register file allows while every SM still gets a few of them.
-int pick_k(int64_t cols_per_gpu, int sms)
+// Stripe width.  The stripe wavefront costs (stripes x hop + rows) row steps, and a step costs about
+// warps-per-scheduler x (10 K + 25) issue slots: wide stripes shorten the first term, but the stripes must
+// also fill the SM sub-partitions evenly (977 stripes on 592 schedulers run at the pace of the ones that
+// hold two).  pick_k() evaluates that model over the instantiated widths.
+constexpr int LONG_KS[] = {2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 18, 20, 22, 24, 27, 30, 32};
+
+int pick_k(int64_t cols_per_gpu, int64_t rows, int sms)
 {
     const int forced = env_int("AGX_LONG_K", 0);
-    if (forced == 2 || forced == 4 || forced == 8 || forced == 16 || forced == 32) return forced;
-    for (int k : {32, 16, 8, 4}) {
+    for (int k : LONG_KS)
+        if (k == forced) return k;
+    const int64_t slots = (int64_t)sms * 4;
+    double best = 0;
+    int best_k = 8;
+    for (int k : LONG_KS) {
         const int64_t stripes = (cols_per_gpu + 32 * k - 1) / (32 * k);
-        if (stripes >= (int64_t)sms * 2) return k;       // at least two stripes per SM
+        const int64_t w = (stripes + slots - 1) / slots;
+        const int regs = 40 + 4 * k;                                  // 3 K state + temporaries
+        if (w * 4 * 32 * regs > 65536) continue;                      // would not be co-resident
+        const double cost = ((double)stripes * 64 + (double)rows) * (double)w * (10.0 * k + 25.0);
+        if (best == 0 || cost < best) { best = cost; best_k = k; }
     }
-    return 2;
+    return best_k;
 }
 
-int pick_rb() { return (env_int("AGX_LONG_RB", LONG_RB_DEFAULT) + 31) / 32 * 32; }
+template <int I = 0> int long_dispatch_k(int k, bool short_chain, const LongArgs &args, int n, cudaStream_t st)
+{
+    if constexpr (I < (int)(sizeof(LONG_KS) / sizeof(LONG_KS[0]))) {
+        if (LONG_KS[I] == k)
+            return short_chain ? long_launch<LONG_KS[I], true>(args, n, st) : long_launch<LONG_KS[I], false>(args, n, st);
+        return long_dispatch_k<I + 1>(k, short_chain, args, n, st);
+    } else {
+        return fail(AGX_EINVAL, "sw_long: stripe width not instantiated");
+    }
+}
 
 int long_dispatch(int k, const LongArgs &args, cudaStream_t st)
 {
@@ -248,19 +336,10 @@ int long_dispatch(int k, const LongArgs &args, cudaStream_t st)
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // few warps per SM: latency-bound, take the short E chain; many: issue-bound, take the lean one
-    int short_chain = (n < sms * 4) ? 1 : 0;
+    // one warp per scheduler: latency-bound, take the short E chain; more: issue-bound, take the lean one
+    bool short_chain = n <= sms * 4;
     if (const char *e = getenv("AGX_LONG_CHAIN")) short_chain = atoi(e) != 0;
-#define AGX_LONG_CASE(KK)                                                                     \
-    case KK: return short_chain ? long_launch<KK, true>(args, n, st) : long_launch<KK, false>(args, n, st);
-    switch (k) {
-        AGX_LONG_CASE(32)
-        AGX_LONG_CASE(16)
-        AGX_LONG_CASE(8)
-        AGX_LONG_CASE(4)
-    default: return short_chain ? long_launch<2, true>(args, n, st) : long_launch<2, false>(args, n, st);
-    }
-#undef AGX_LONG_CASE
+    return long_dispatch_k<0>(k, short_chain, args, n, st);
 }
 
 }  // namespace
@@ -275,9 +354,8 @@ int sw_long_device(SwLongWorkspace &ws, const uint8_t *d_a, int64_t la, const ui
     int dev = 0, sms = 148;
     AGX_CUDA(cudaGetDevice(&dev));
     AGX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int k = pick_k(la, sms);
-    const int64_t n_stripes = (la + 32 * k - 1) / (32 * k);
-    const int64_t need = 2 * lb + n_stripes + 2;
+    const int k = pick_k(la, lb, sms);
+    const int64_t need = 4 * lb + 4;                       // int32 words: one 16-byte entry per row
     if (need > ws.cap) {
         if (ws.buf) cudaFree(ws.buf);
         ws.buf = nullptr; ws.cap = 0;
@@ -286,14 +364,12 @@ int sw_long_device(SwLongWorkspace &ws, const uint8_t *d_a, int64_t la, const ui
     }
     LongArgs args;
     args.a = d_a; args.la = (int32_t)la; args.b = d_b; args.lb = (int32_t)lb;
-    args.bnd = ws.buf;
-    args.progress = ws.buf + 2 * lb;
-    args.next_bnd = nullptr; args.next_progress = nullptr;
+    args.bnd = reinterpret_cast<int4 *>(ws.buf);
+    args.next_bnd = nullptr;
     args.best = d_best;
-    args.first_gpu = 1;
-    args.rb = pick_rb();
+    args.stripe_base = 0;
     args.sc = sc;
-    AGX_CUDA(cudaMemsetAsync(args.progress, 0, (size_t)(n_stripes + 2) * sizeof(int32_t), st));
+    AGX_CUDA(cudaMemsetAsync(args.bnd, 0xff, (size_t)lb * sizeof(int4), st));     // tag -1: written by nobody
     AGX_CUDA(cudaMemsetAsync(d_best, 0, sizeof(int32_t), st));
     return long_dispatch(k, args, st);
 }
@@ -327,20 +403,26 @@ int sw_long_host_multi(int n_dev, const int *dev, cudaStream_t *st, SwLongWorksp
     std::vector<LongArgs> args(n_dev);
     std::vector<int> ks(n_dev);
     std::vector<int64_t> c_lo(n_dev + 1);
-    // interior cuts sit on multiples of the widest stripe (32 lanes x 32 columns): only the very last
+    // one stripe width everywhere, interior cuts on multiples of it: only the very last
     // stripe of the matrix may carry padding columns, whose boundary nobody consumes
-    for (int gidx = 0; gidx <= n_dev; ++gidx) c_lo[gidx] = (gidx == n_dev) ? la : (la * gidx / n_dev) / 1024 * 1024;
-    // allocate + upload on every GPU, clear the flags, then make sure ALL GPUs are clear before any launch
+    int sms0 = 148;
+    AGX_CUDA(cudaDeviceGetAttribute(&sms0, cudaDevAttrMultiProcessorCount, dev[0]));
+    const int k_all = pick_k((la + n_dev - 1) / n_dev, lb, sms0);
+    const int64_t wcols = 32 * (int64_t)k_all;
+    for (int gidx = 0; gidx <= n_dev; ++gidx)
+        c_lo[gidx] = (gidx == n_dev) ? la : std::min<int64_t>(la, (la * gidx / n_dev + wcols / 2) / wcols * wcols);
+    // allocate + upload on every GPU, clear the tags, then make sure ALL GPUs are clear before any launch
+    int32_t stripe_base = 0;
     for (int gidx = 0; gidx < n_dev; ++gidx) {
         AGX_CUDA(cudaSetDevice(dev[gidx]));
         int sms = 148;
         AGX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev[gidx]));
         const int64_t cols = c_lo[gidx + 1] - c_lo[gidx];
-        const int k = pick_k(cols, sms);
+        const int k = k_all;
         ks[gidx] = k;
         const int64_t n_stripes = (cols + 32 * k - 1) / (32 * k);
         SwLongWorkspace &w = *ws[gidx];
-        const int64_t need = 2 * lb + n_stripes + 2 + 1;
+        const int64_t need = 4 * lb + 4;                   // one 16-byte entry per row + the best score
         if (need > w.cap) {
             if (w.buf) cudaFree(w.buf);
             w.buf = nullptr; w.cap = 0;
@@ -358,19 +440,16 @@ int sw_long_host_multi(int n_dev, const int *dev, cudaStream_t *st, SwLongWorksp
         AGX_CUDA(cudaMemcpyAsync(w.seq + cols, b, (size_t)lb, cudaMemcpyHostToDevice, st[gidx]));
         LongArgs &x = args[gidx];
         x.a = w.seq; x.la = (int32_t)cols; x.b = w.seq + cols; x.lb = (int32_t)lb;
-        x.bnd = w.buf;
-        x.progress = w.buf + 2 * lb;
-        x.best = w.buf + 2 * lb + n_stripes + 2;
-        x.next_bnd = nullptr; x.next_progress = nullptr;
-        x.first_gpu = (gidx == 0);
-        x.rb = pick_rb();
+        x.bnd = reinterpret_cast<int4 *>(w.buf);
+        x.best = w.buf + 4 * lb;
+        x.next_bnd = nullptr;
+        x.stripe_base = stripe_base;
+        stripe_base += (int32_t)n_stripes;
         x.sc = sc;
-        AGX_CUDA(cudaMemsetAsync(x.progress, 0, (size_t)(n_stripes + 3) * sizeof(int32_t), st[gidx]));
+        AGX_CUDA(cudaMemsetAsync(x.bnd, 0xff, (size_t)lb * sizeof(int4), st[gidx]));   // tag -1: written by nobody
+        AGX_CUDA(cudaMemsetAsync(x.best, 0, sizeof(int32_t), st[gidx]));
     }
-    for (int gidx = 0; gidx + 1 < n_dev; ++gidx) {
-        args[gidx].next_bnd = args[gidx + 1].bnd;
-        args[gidx].next_progress = args[gidx + 1].progress;
-    }
+    for (int gidx = 0; gidx + 1 < n_dev; ++gidx) args[gidx].next_bnd = args[gidx + 1].bnd;
     for (int gidx = 0; gidx < n_dev; ++gidx) {
         AGX_CUDA(cudaSetDevice(dev[gidx]));
         AGX_CUDA(cudaStreamSynchronize(st[gidx]));
