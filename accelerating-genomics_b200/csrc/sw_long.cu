@@ -43,7 +43,24 @@ struct LongArgs {
     int32_t *best;            // running maximum (atomicMax)
     int32_t stripe_base;      // global index of this GPU's stripe 0 (0: the true left edge of the matrix)
     SwScoring sc;
+    const uint8_t *lut;       // CODED kernels: byte -> symbol code 0..6 (both sequences use <= 7 distinct bytes)
+    int32_t one;              // the constant 1, opaque to ptxas: x + y as IMAD (FMA pipe) instead of IADD3 (ALU pipe)
 };
+
+// prmt.b32 in its default mode: selector nibble bit 3 replicates the sign of the selected byte
+__device__ __forceinline__ int32_t prmt_s(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return (int32_t)d;
+}
+// a + b on the FMA pipe (IMAD) -- the ALU pipe is the bottleneck of these kernels
+__device__ __forceinline__ int32_t add_fma(int32_t a, int32_t b, int32_t one)
+{
+    int32_t d;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
+    return d;
+}
 
 // A boundary entry may be (re)written by another SM or by a peer GPU while it is polled: relaxed (strong)
 // accesses at the narrowest scope that covers writer and reader -- .gpu inside one GPU, .sys across NVLink.
@@ -85,12 +102,17 @@ __device__ __forceinline__ void st_entry(int4 *p, int4 v, bool sys)
 #endif
 }
 
-template <int K, bool SHORT>
+// CODED: both sequences use at most 7 distinct bytes.  Columns carry a PRMT selector instead of their byte,
+// rows an 8-byte table (substitution score - goe for each symbol code), and the substitution score of a cell
+// is ONE PRMT (sign-extending byte select) instead of ISETP + SEL; the two additions of a cell go to the FMA
+// pipe as IMADs.  ALU-pipe instructions per cell: 7.5 -> 4.5 (lean chain), 8.5 -> 5.5 (short chain).
+template <int K, bool SHORT, bool CODED>
 __global__ void __launch_bounds__(LONG_WARPS * 32)
 sw_long_kernel(LongArgs g)
 {
     constexpr int W = 32 * K;
-    __shared__ int32_t r_byte[LONG_WARPS][LONG_RING];
+    __shared__ int32_t r_byte[LONG_WARPS][LONG_RING];      // row byte, or the low half of the row's score table
+    __shared__ int32_t r_hi[CODED ? LONG_WARPS : 1][CODED ? LONG_RING : 1];
     __shared__ int32_t r_g[LONG_WARPS][LONG_RING];
     __shared__ int32_t r_e[LONG_WARPS][LONG_RING];
     __shared__ int2 stage[LONG_WARPS][32];      // boundary of the rows finished in the current block
@@ -105,13 +127,29 @@ sw_long_kernel(LongArgs g)
     const int32_t lb = g.lb;
     const int n_stripes = (g.la + W - 1) / W;
     int32_t bestg = goe;          // running max of H + goe
+    const int32_t one = g.one;
+    const uint32_t xb4 = (uint32_t)(uint8_t)(int8_t)sub_mis * 0x01010101u;          // every symbol: mismatch
+    const uint32_t mxor = (uint32_t)(uint8_t)(int8_t)sub_mis ^ (uint32_t)(uint8_t)(int8_t)sub_match;
+    // row symbol -> its 8-byte score table (byte k = score against symbol code k); code 7 never matches
+    auto row_table = [&](int32_t r, uint32_t &lo, uint32_t &hi) {
+        lo = xb4; hi = xb4;
+        if (r < lb) {
+            const uint32_t c = g.lut[g.b[r]];
+            if (c < 4) lo ^= mxor << (8 * c); else hi ^= mxor << (8 * (c - 4));
+        }
+    };
 
     for (int st = warp; st < n_stripes; st += n_warps) {
         const int c0 = st * W + lane * K;
         int32_t acol[K], Gp[K], F[K];
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-            acol[j] = (c0 + j < g.la) ? (int32_t)g.a[c0 + j] : 0x100;
+            if constexpr (CODED) {
+                const uint32_t c = (c0 + j < g.la) ? (uint32_t)g.lut[g.a[c0 + j]] : 7u;
+                acol[j] = (int32_t)(c | ((8u | c) * 0x1110u));              // byte c, sign-extended to 32 bits
+            } else {
+                acol[j] = (c0 + j < g.la) ? (int32_t)g.a[c0 + j] : 0x100;
+            }
             Gp[j] = goe;
             F[j] = goe;
         }
@@ -144,9 +182,11 @@ sw_long_kernel(LongArgs g)
 #endif
         // inputs of the first 32 rows
         int32_t nb = 0x200;
+        uint32_t nhi = 0;
         int4 nx = make_int4(goe, gst - 1, goe, gst - 1);
+        if constexpr (CODED) { uint32_t lo; row_table(lane, lo, nhi); nb = (int32_t)lo; }
         if (lane < lb) {
-            nb = g.b[lane];
+            if constexpr (!CODED) nb = g.b[lane];
             if (!left_edge) nx = ld_entry(g.bnd + lane, in_remote);
         }
         for (int s0 = 0; s0 < S; s0 += 32) {
@@ -169,6 +209,7 @@ sw_long_kernel(LongArgs g)
 #endif
                 }
                 r_byte[wib][r & (LONG_RING - 1)] = nb;
+                if constexpr (CODED) r_hi[wib][r & (LONG_RING - 1)] = (int32_t)nhi;
                 r_g[wib][r & (LONG_RING - 1)] = nx.x;
                 r_e[wib][r & (LONG_RING - 1)] = nx.z;
             }
@@ -179,8 +220,9 @@ sw_long_kernel(LongArgs g)
                 const int r = s0 + 32 + lane;
                 nb = 0x200;
                 nx = make_int4(goe, gst - 1, goe, gst - 1);
+                if constexpr (CODED) { uint32_t lo; row_table(r, lo, nhi); nb = (int32_t)lo; }
                 if (r < lb) {
-                    nb = g.b[r];
+                    if constexpr (!CODED) nb = g.b[r];
 #if AGX_LONG_PREFETCH == 2
                     if (!left_edge) nx = __ldcg(g.bnd + r);
 #else
@@ -194,7 +236,9 @@ sw_long_kernel(LongArgs g)
             for (int u = 0; u < send; ++u) {
                 const int s = s0 + u;
                 const int slot = (s - lane) & (LONG_RING - 1);
-                const int32_t rb = (s - lane >= 0) ? r_byte[wib][slot] : 0x200;
+                int32_t rb = (s - lane >= 0) ? r_byte[wib][slot] : (CODED ? (int32_t)xb4 : 0x200);
+                uint32_t rhi = xb4;
+                if constexpr (CODED) { if (s - lane >= 0) rhi = (uint32_t)r_hi[wib][slot]; }
                 int32_t g_in = __shfl_up_sync(0xffffffffu, g_out, 1);
                 int32_t e = __shfl_up_sync(0xffffffffu, e_out, 1);
                 if (lane == 0) { g_in = r_g[wib][slot]; e = r_e[wib][slot]; }
@@ -210,12 +254,15 @@ sw_long_kernel(LongArgs g)
                     int32_t tg_prev = g_in;
 #pragma unroll
                     for (int j = 0; j < K; ++j) {
-                        const int32_t d = gdiag + ((acol[j] == rb) ? sub_match : sub_mis);
+                        int32_t d, tg;
+                        if constexpr (CODED) d = add_fma(gdiag, prmt_s((uint32_t)rb, rhi, (uint32_t)acol[j]), one);
+                        else d = gdiag + ((acol[j] == rb) ? sub_match : sub_mis);
                         F[j] = __viaddmax_s32(F[j], ext, Gp[j]);
-                        const int32_t tg = __vimax_s32_relu(F[j], d) + goe;      // T[j] + goe
+                        if constexpr (CODED) tg = add_fma(__vimax_s32_relu(F[j], d), goe, one);
+                        else tg = __vimax_s32_relu(F[j], d) + goe;                 // T[j] + goe
                         e = __viaddmax_s32(e, ext, tg_prev);                       // E[i][j]
                         gdiag = Gp[j];
-                        gleft = max(e + goe, tg);                                  // H[i][j] + goe
+                        gleft = __viaddmax_s32(e, goe, tg);                        // H[i][j] + goe
                         Gp[j] = gleft;
                         tg_prev = tg;
                         if (j & 1) bestg = __vimax3_s32(bestg, Gp[j - 1], gleft);
@@ -224,12 +271,14 @@ sw_long_kernel(LongArgs g)
                 } else {
 #pragma unroll
                     for (int j = 0; j < K; ++j) {
-                        const int32_t d = gdiag + ((acol[j] == rb) ? sub_match : sub_mis);
+                        int32_t d;
+                        if constexpr (CODED) d = add_fma(gdiag, prmt_s((uint32_t)rb, rhi, (uint32_t)acol[j]), one);
+                        else d = gdiag + ((acol[j] == rb) ? sub_match : sub_mis);
                         e = __viaddmax_s32(e, ext, gleft);
                         F[j] = __viaddmax_s32(F[j], ext, Gp[j]);
                         const int32_t hcell = __vimax3_s32_relu(e, F[j], d);
                         gdiag = Gp[j];
-                        gleft = hcell + goe;
+                        if constexpr (CODED) gleft = add_fma(hcell, goe, one); else gleft = hcell + goe;
                         Gp[j] = gleft;
                         if (j & 1) bestg = __vimax3_s32(bestg, Gp[j - 1], gleft);
                         else if (j == K - 1) bestg = max(bestg, gleft);
@@ -245,8 +294,9 @@ sw_long_kernel(LongArgs g)
                 const int r = s0 + 32 + lane;
                 nb = 0x200;
                 nx = make_int4(goe, gst - 1, goe, gst - 1);
+                if constexpr (CODED) { uint32_t lo; row_table(r, lo, nhi); nb = (int32_t)lo; }
                 if (r < lb) {
-                    nb = g.b[r];
+                    if constexpr (!CODED) nb = g.b[r];
                     if (!left_edge) nx = ld_entry(g.bnd + r, in_remote);
                 }
             }
@@ -270,19 +320,19 @@ sw_long_kernel(LongArgs g)
     if (lane == 0 && best > 0) atomicMax(g.best, best);
 }
 
-template <int K, bool SHORT> int long_launch(const LongArgs &args, int n_stripes, cudaStream_t st)
+template <int K, bool SHORT, bool CODED> int long_launch(const LongArgs &args, int n_stripes, cudaStream_t st)
 {
     int dev = 0, sms = 0, per_sm = 0;
     AGX_CUDA(cudaGetDevice(&dev));
     AGX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    AGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_long_kernel<K, SHORT>, LONG_WARPS * 32, 0));
+    AGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_long_kernel<K, SHORT, CODED>, LONG_WARPS * 32, 0));
     if (per_sm < 1) return fail(AGX_ECUDA, "sw_long: kernel does not fit on an SM");
     int blocks = sms * per_sm;                        // all co-resident: required by the stripe wavefront
     const int want = (n_stripes + LONG_WARPS - 1) / LONG_WARPS;
     if (blocks > want) blocks = want;
     LongArgs a = args;
     void *params[] = {&a};
-    AGX_CUDA(cudaLaunchCooperativeKernel((const void *)sw_long_kernel<K, SHORT>, dim3(blocks), dim3(LONG_WARPS * 32),
+    AGX_CUDA(cudaLaunchCooperativeKernel((const void *)sw_long_kernel<K, SHORT, CODED>, dim3(blocks), dim3(LONG_WARPS * 32),
                                          params, 0, st));
     count_launch();
     return AGX_OK;
@@ -298,33 +348,50 @@ int env_int(const char *name, int dflt)
 // warps-per-scheduler x (10 K + 25) issue slots: wide stripes shorten the first term, but the stripes must
 // also fill the SM sub-partitions evenly (977 stripes on 592 schedulers run at the pace of the ones that
 // hold two).  pick_k() evaluates that model over the instantiated widths.
-constexpr int LONG_KS[] = {2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 18, 20, 22, 24, 27, 30, 32};
+constexpr int LONG_KS[] = {2, 4, 6, 7, 8, 10, 12, 14, 16, 20, 24, 27, 32};     // CODED kernels
+constexpr int LONG_KS_RAW[] = {4, 8, 16, 32};                                  // raw-byte kernels (> 7 distinct symbols)
 
-int pick_k(int64_t cols_per_gpu, int64_t rows, int sms)
+int pick_k(int64_t cols_per_gpu, int64_t rows, int sms, bool coded)
 {
     const int forced = env_int("AGX_LONG_K", 0);
-    for (int k : LONG_KS)
-        if (k == forced) return k;
+    const int *ks = coded ? LONG_KS : LONG_KS_RAW;
+    const int nk = coded ? (int)(sizeof(LONG_KS) / sizeof(int)) : (int)(sizeof(LONG_KS_RAW) / sizeof(int));
+    for (int i = 0; i < nk; ++i)
+        if (ks[i] == forced) return forced;
     const int64_t slots = (int64_t)sms * 4;
+    const double per_col = coded ? 7.0 : 10.0;                        // issue slots per cell
     double best = 0;
     int best_k = 8;
-    for (int k : LONG_KS) {
+    for (int i = 0; i < nk; ++i) {
+        const int k = ks[i];
         const int64_t stripes = (cols_per_gpu + 32 * k - 1) / (32 * k);
         const int64_t w = (stripes + slots - 1) / slots;
         const int regs = 40 + 4 * k;                                  // 3 K state + temporaries
         if (w * 4 * 32 * regs > 65536) continue;                      // would not be co-resident
-        const double cost = ((double)stripes * 64 + (double)rows) * (double)w * (10.0 * k + 25.0);
+        const double cost = ((double)stripes * 64 + (double)rows) * (double)w * (per_col * k + 25.0);
         if (best == 0 || cost < best) { best = cost; best_k = k; }
     }
     return best_k;
 }
 
-template <int I = 0> int long_dispatch_k(int k, bool short_chain, const LongArgs &args, int n, cudaStream_t st)
+template <int I = 0> int long_dispatch_coded(int k, bool short_chain, const LongArgs &args, int n, cudaStream_t st)
 {
     if constexpr (I < (int)(sizeof(LONG_KS) / sizeof(LONG_KS[0]))) {
         if (LONG_KS[I] == k)
-            return short_chain ? long_launch<LONG_KS[I], true>(args, n, st) : long_launch<LONG_KS[I], false>(args, n, st);
-        return long_dispatch_k<I + 1>(k, short_chain, args, n, st);
+            return short_chain ? long_launch<LONG_KS[I], true, true>(args, n, st)
+                               : long_launch<LONG_KS[I], false, true>(args, n, st);
+        return long_dispatch_coded<I + 1>(k, short_chain, args, n, st);
+    } else {
+        return fail(AGX_EINVAL, "sw_long: stripe width not instantiated");
+    }
+}
+template <int I = 0> int long_dispatch_raw(int k, bool short_chain, const LongArgs &args, int n, cudaStream_t st)
+{
+    if constexpr (I < (int)(sizeof(LONG_KS_RAW) / sizeof(LONG_KS_RAW[0]))) {
+        if (LONG_KS_RAW[I] == k)
+            return short_chain ? long_launch<LONG_KS_RAW[I], true, false>(args, n, st)
+                               : long_launch<LONG_KS_RAW[I], false, false>(args, n, st);
+        return long_dispatch_raw<I + 1>(k, short_chain, args, n, st);
     } else {
         return fail(AGX_EINVAL, "sw_long: stripe width not instantiated");
     }
@@ -339,7 +406,50 @@ int long_dispatch(int k, const LongArgs &args, cudaStream_t st)
     // one warp per scheduler: latency-bound, take the short E chain; more: issue-bound, take the lean one
     bool short_chain = n <= sms * 4;
     if (const char *e = getenv("AGX_LONG_CHAIN")) short_chain = atoi(e) != 0;
-    return long_dispatch_k<0>(k, short_chain, args, n, st);
+    return args.lut ? long_dispatch_coded<0>(k, short_chain, args, n, st) : long_dispatch_raw<0>(k, short_chain, args, n, st);
+}
+
+// byte -> symbol code for sequences with at most 7 distinct bytes (code 7 is the "matches nothing" padding);
+// false when there are more, or when the scores do not fit the byte table of the CODED kernels
+bool build_lut(const uint32_t present[8], SwScoring sc, uint8_t lut[256])
+{
+    if (getenv("AGX_LONG_RAW")) return false;                         // A/B switch: raw-byte kernels only
+    const int32_t goe = sc.gap_open + sc.gap_extend;
+    if (sc.match - goe > 127 || sc.mismatch - goe < -128 || sc.match - goe < -128 || sc.mismatch - goe > 127) return false;
+    int n = 0;
+    for (int c = 0; c < 256; ++c) {
+        lut[c] = 7;
+        if (present[c >> 5] >> (c & 31) & 1u) {
+            if (n == 7) return false;
+            lut[c] = (uint8_t)n++;
+        }
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(256)
+byte_presence_kernel(const uint8_t *__restrict__ a, int64_t la, const uint8_t *__restrict__ b, int64_t lb,
+                     uint32_t *__restrict__ present)
+{
+    __shared__ uint32_t s_mask[8];
+    if (threadIdx.x < 8) s_mask[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < la + lb; i += stride) {
+        const uint32_t c = i < la ? a[i] : b[i - la];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) m[w] |= ((c >> 5) == (uint32_t)w) ? (1u << (c & 31)) : 0u;
+    }
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        uint32_t v = m[w];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicOr(&s_mask[w], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < 8 && s_mask[threadIdx.x]) atomicOr(&present[threadIdx.x], s_mask[threadIdx.x]);
 }
 
 }  // namespace
@@ -354,15 +464,29 @@ int sw_long_device(SwLongWorkspace &ws, const uint8_t *d_a, int64_t la, const ui
     int dev = 0, sms = 148;
     AGX_CUDA(cudaGetDevice(&dev));
     AGX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int k = pick_k(la, lb, sms);
-    const int64_t need = 4 * lb + 4;                       // int32 words: one 16-byte entry per row
+    const int64_t need = 4 * lb + 4 + 8 + 64;              // int32 words: entries, best, presence mask, code table
     if (need > ws.cap) {
         if (ws.buf) cudaFree(ws.buf);
         ws.buf = nullptr; ws.cap = 0;
         AGX_CUDA(cudaMalloc(&ws.buf, (size_t)need * sizeof(int32_t)));
         ws.cap = need;
     }
+    // which bytes occur?  <= 7 distinct ones (DNA, with or without N / newline) take the CODED kernels
+    uint32_t *d_present = reinterpret_cast<uint32_t *>(ws.buf + 4 * lb + 4);
+    uint8_t *d_lut = reinterpret_cast<uint8_t *>(ws.buf + 4 * lb + 4 + 8);
+    AGX_CUDA(cudaMemsetAsync(d_present, 0, 8 * sizeof(uint32_t), st));
+    byte_presence_kernel<<<sms * 4, 256, 0, st>>>(d_a, la, d_b, lb, d_present);
+    count_launch();
+    uint32_t present[8];
+    AGX_CUDA(cudaMemcpyAsync(present, d_present, sizeof present, cudaMemcpyDeviceToHost, st));
+    AGX_CUDA(cudaStreamSynchronize(st));
+    uint8_t lut[256];
+    const bool coded = build_lut(present, sc, lut);
+    if (coded) AGX_CUDA(cudaMemcpyAsync(d_lut, lut, sizeof lut, cudaMemcpyHostToDevice, st));
+    const int k = pick_k(la, lb, sms, coded);
     LongArgs args;
+    args.lut = coded ? d_lut : nullptr;
+    args.one = 1;
     args.a = d_a; args.la = (int32_t)la; args.b = d_b; args.lb = (int32_t)lb;
     args.bnd = reinterpret_cast<int4 *>(ws.buf);
     args.next_bnd = nullptr;
@@ -407,7 +531,12 @@ int sw_long_host_multi(int n_dev, const int *dev, cudaStream_t *st, SwLongWorksp
     // stripe of the matrix may carry padding columns, whose boundary nobody consumes
     int sms0 = 148;
     AGX_CUDA(cudaDeviceGetAttribute(&sms0, cudaDevAttrMultiProcessorCount, dev[0]));
-    const int k_all = pick_k((la + n_dev - 1) / n_dev, lb, sms0);
+    uint32_t present[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t i = 0; i < la; ++i) present[a[i] >> 5] |= 1u << (a[i] & 31);
+    for (int64_t i = 0; i < lb; ++i) present[b[i] >> 5] |= 1u << (b[i] & 31);
+    uint8_t lut[256];
+    const bool coded = build_lut(present, sc, lut);
+    const int k_all = pick_k((la + n_dev - 1) / n_dev, lb, sms0, coded);
     const int64_t wcols = 32 * (int64_t)k_all;
     for (int gidx = 0; gidx <= n_dev; ++gidx)
         c_lo[gidx] = (gidx == n_dev) ? la : std::min<int64_t>(la, (la * gidx / n_dev + wcols / 2) / wcols * wcols);
@@ -429,7 +558,7 @@ int sw_long_host_multi(int n_dev, const int *dev, cudaStream_t *st, SwLongWorksp
             AGX_CUDA(cudaMalloc(&w.buf, (size_t)need * sizeof(int32_t)));
             w.cap = need;
         }
-        const int64_t seq_need = cols + lb + 64;
+        const int64_t seq_need = cols + lb + 64 + 256;     // + the byte -> code table
         if (seq_need > w.cap_seq) {
             if (w.seq) cudaFree(w.seq);
             w.seq = nullptr; w.cap_seq = 0;
@@ -438,7 +567,11 @@ int sw_long_host_multi(int n_dev, const int *dev, cudaStream_t *st, SwLongWorksp
         }
         AGX_CUDA(cudaMemcpyAsync(w.seq, a + c_lo[gidx], (size_t)cols, cudaMemcpyHostToDevice, st[gidx]));
         AGX_CUDA(cudaMemcpyAsync(w.seq + cols, b, (size_t)lb, cudaMemcpyHostToDevice, st[gidx]));
+        uint8_t *d_lut = w.seq + (cols + lb + 63) / 64 * 64;
+        if (coded) AGX_CUDA(cudaMemcpyAsync(d_lut, lut, sizeof lut, cudaMemcpyHostToDevice, st[gidx]));
         LongArgs &x = args[gidx];
+        x.lut = coded ? d_lut : nullptr;
+        x.one = 1;
         x.a = w.seq; x.la = (int32_t)cols; x.b = w.seq + cols; x.lb = (int32_t)lb;
         x.bnd = reinterpret_cast<int4 *>(w.buf);
         x.best = w.buf + 4 * lb;

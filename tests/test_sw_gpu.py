@@ -183,14 +183,40 @@ def test_long_alignment_whole_gpu_kernel(agx, gpu_lib, oracle_mod, n, related):
         assert got[0] > n // 2
 
 
-@pytest.mark.parametrize("k,chain", [(2, 0), (4, 1), (8, 0), (16, 1), (32, 0), (32, 1)])
+@pytest.mark.parametrize("k,chain", [(2, 0), (4, 1), (7, 0), (8, 0), (14, 1), (16, 1), (27, 0), (32, 0), (32, 1)])
 def test_long_alignment_stripe_widths_and_chain_forms(agx, gpu_lib, oracle_mod, k, chain, monkeypatch):
+    """Every instantiated stripe width, both chain forms; DNA takes the symbol-coded (PRMT) kernels."""
     monkeypatch.setenv("AGX_LONG_K", str(k))
     monkeypatch.setenv("AGX_LONG_CHAIN", str(chain))
-    monkeypatch.setenv("AGX_LONG_RB", "32" if k % 8 else "96")
     inp = _long_pair(agx, 17000 + 111 * k, seed=k + chain, related=bool(chain))
     got = gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len)
     assert got.tolist() == oracle_mod.sw_scores_flat(inp.buf, inp.off, inp.len).tolist()
+
+
+@pytest.mark.parametrize("alphabet,k", [(b"ACGTNRYKMSWB", 8), (b"ACGTNRYKMSWB", 32), (b"ACGTNac", 6), (b"AC", 10)])
+def test_long_alignment_alphabets(agx, gpu_lib, oracle_mod, alphabet, k, monkeypatch):
+    """More than 7 distinct bytes: the raw-byte kernels; up to 7 (here with lower case): the coded ones."""
+    monkeypatch.setenv("AGX_LONG_K", str(k))
+    rng = np.random.default_rng(k)
+    alpha = np.frombuffer(alphabet, np.uint8)
+    n = 17500
+    a = alpha[rng.integers(0, alpha.size, size=n)]
+    b = a.copy()
+    mut = rng.random(n) < 0.2
+    b[mut] = alpha[rng.integers(0, alpha.size, size=int(mut.sum()))]
+    buf = np.concatenate([a, b[: n - 300]])
+    off = np.array([0, n], dtype=np.int64)
+    ln = np.array([n, n - 300], dtype=np.int32)
+    assert int(ln[0]) * int(ln[1]) >= 1 << 28
+    got = gpu_lib.sw_score_flat(buf, off, ln)
+    assert got.tolist() == oracle_mod.sw_scores_flat(buf, off, ln).tolist()
+
+
+def test_long_alignment_raw_and_coded_kernels_agree(agx, gpu_lib, monkeypatch):
+    inp = _long_pair(agx, 60000, seed=3, related=True)
+    coded = gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len)
+    monkeypatch.setenv("AGX_LONG_RAW", "1")
+    assert gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len).tolist() == coded.tolist()
 
 
 def test_long_alignment_device_entry_point_and_mixed_batch(agx, gpu_lib, oracle_mod):
