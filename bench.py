@@ -363,7 +363,7 @@ def bench_sw(agx, args, rank, local_rank, world, device):
                      "kernel_gcups": cells / (k_ms * 1e-3) / 1e9, "kernel_share_of_step": k_ms / ms,
                      "traffic": (peaks["sw_duo_dram_bytes_per_pair_150x150"] * n
                                  if peaks and peaks.get("sw_duo_dram_bytes_per_pair_150x150") else None),
-                     "traffic_note": "DRAM bytes per launch from the committed ncu capture (profiles/r1d_sw_duo_ncu.txt), "
+                     "traffic_note": "DRAM bytes per launch from the committed ncu capture (profiles/r1f_sw_duo_ncu.txt), "
                                      "scaled by pairs; the kernel is ALU-bound, HBM time for this is ~0.05 ms",
                      "loader": {"kernel": "sw_classify_kernel", "ms": float(np.mean(cls_ms)), "bound": "hbm"}},
         "gpu_launches": int(launches), "clocks": clk.summary(),
@@ -457,7 +457,11 @@ def bench_hmm(agx, args, rank, local_rank, world, device):
         "roofline": {"bound": "alu", "kernel": "hmm_duo_kernel<K=4..8> (FP32, two reads per warp, f32x2) + hmm_stream_kernel for unpaired reads", "achieved": achieved / 1e12,
                      "peak": peak / 1e12, "unit": "Tlaneinstr/s (FP32 pipe)", "frac": achieved / peak,
                      "peak_source": peak_src, "ops_per_cell": HMM_OPS_PER_CELL, "kernel_ms": k_ms,
-                     "kernel_gcups": cells / (k_ms * 1e-3) / 1e9, "kernel_share_of_step": k_ms / ms, "traffic": None},
+                     "kernel_gcups": cells / (k_ms * 1e-3) / 1e9, "kernel_share_of_step": k_ms / ms,
+                     "traffic": (peaks["hmm_dram_bytes_per_step_config4"] * (args.hmm_batches / 1000.0)
+                                 if peaks and peaks.get("hmm_dram_bytes_per_step_config4") else None),
+                     "traffic_note": "DRAM bytes of the stream-kernel launches of one step from the committed ncu launch "
+                                     "list (profiles/r1f_launch_shares.txt), scaled by batches; FP32-bound, HBM time ~0.04 ms"},
         "gpu_launches": int(launches), "clocks": clk.summary(),
         "pairs_per_gpu": n_pairs, "cells_per_gpu": cells,
     }
