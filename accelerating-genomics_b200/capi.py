@@ -20,7 +20,8 @@ LIB_PATH = Path(os.environ["AGX_LIB_PATH"]) if os.environ.get("AGX_LIB_PATH") el
 
 # every symbol include/agx.h declares (tests check the .so exports all of them)
 SYMBOLS = [
-    "agx_init", "agx_init_devices", "agx_device_count", "agx_shutdown", "agx_last_error",
+    "agx_init", "agx_init_devices", "agx_device_count", "agx_device_ordinal", "agx_device_name", "agx_shutdown",
+    "agx_last_error",
     "agx_version", "agx_launch_count", "agx_reset_launch_count", "agx_set_profiling", "agx_profile_ms",
     "sw_score_batch", "sw_score_batch_flat", "sw_score_batch_device", "sw_score_file_image",
     "pairhmm_forward_batch", "pairhmm_forward_batches_flat", "pairhmm_forward_batches_device",
@@ -57,6 +58,10 @@ def load_library() -> C.CDLL:
     lib.agx_init.argtypes = [C.c_int32]
     lib.agx_init_devices.argtypes = [i32p, C.c_int32]
     lib.agx_device_count.restype = C.c_int32
+    lib.agx_device_ordinal.argtypes = [C.c_int32]
+    lib.agx_device_ordinal.restype = C.c_int32
+    lib.agx_device_name.argtypes = [C.c_int32]
+    lib.agx_device_name.restype = C.c_char_p
     lib.agx_shutdown.restype = None
     lib.agx_last_error.restype = C.c_char_p
     lib.agx_version.restype = C.c_char_p

@@ -129,6 +129,7 @@ struct DeviceCtx {
     DevBuf d_bytes, d_a, d_b, d_c, d_d, d_e, d_f, d_out;   // staging for the host entry points
     PinBuf h_a, h_b, h_out;
     std::string error;   // error raised on this device's worker thread
+    std::string name;    // agx_device_name()
 };
 
 std::mutex g_mu;
@@ -565,6 +566,22 @@ int agx_init_devices(const int32_t *device_ids, int32_t n_devices)
 }
 
 int32_t agx_device_count(void) { return (int32_t)g_ctx.size(); }
+
+int32_t agx_device_ordinal(int32_t index)
+{
+    return (index >= 0 && index < (int32_t)g_ctx.size()) ? g_ctx[index]->device : -1;
+}
+
+const char *agx_device_name(int32_t index)
+{
+    if (index < 0 || index >= (int32_t)g_ctx.size()) return "";
+    DeviceCtx &c = *g_ctx[index];
+    if (c.name.empty()) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, c.device) == cudaSuccess) c.name = prop.name;
+    }
+    return c.name.c_str();
+}
 
 void agx_shutdown(void)
 {

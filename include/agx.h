@@ -49,6 +49,11 @@ int agx_init_devices(const int32_t *device_ids, int32_t n_devices);
 /* Number of GPUs the library is bound to (0 before agx_init). */
 int32_t agx_device_count(void);
 
+/* CUDA ordinal and name of the index-th bound GPU (what smithWaterman.cu:393 / hipvers.cpp:389 print as
+ * "[main] Using Device %d: %s"); -1 / "" when index is out of range.  The string lives until agx_shutdown(). */
+int32_t agx_device_ordinal(int32_t index);
+const char *agx_device_name(int32_t index);
+
 /* Release every device/host resource.  Safe to call when not initialised. */
 void agx_shutdown(void);
 

@@ -74,3 +74,29 @@ def test_pairhmm_driver_output(tmp_path, name):
 def test_pairhmm_driver_usage():
     r = subprocess.run([str(BIN / "pairHMM"), "only-one"], capture_output=True, text=True)
     assert r.returncode == 1 and "<input_file_r> <output_file>" in r.stderr
+
+
+def test_sw_gpu_cli_of_the_reference(tmp_path, agx, oracle_mod):
+    """drivers/smithWatermanGpu.c keeps the command line and the output conventions of hipvers.cpp /
+    smithWaterman.cu: <input> <output> <block_size>, results appended, 10000-byte line buffer."""
+    import sys
+    inp, out = tmp_path / "input.txt", tmp_path / "scores.txt"
+    subprocess.run([sys.executable, str(ROOT / "drivers" / "generator.py"), "900", "1400", "40", "--seed", "3",
+                    "--out", str(inp)], check=True)
+    parsed = agx.formats.parse_sw(inp.read_bytes(), line_buf=10000)
+    want = oracle_mod.sw_scores_flat(parsed.buf, parsed.off, parsed.len).tolist()
+    assert len(want) == 20                                         # header = alignments: half the pairs (SW-Q2)
+    out.write_text("Score: -1\n")                                  # the reference opens the file in append mode
+    for block_size in ("64", "256"):
+        r = subprocess.run([str(BIN / "smithWatermanGpu"), str(inp), str(out), block_size], capture_output=True,
+                           text=True, env=dict(os.environ, AGX_NUM_GPUS="1"))
+        assert r.returncode == 0, r.stderr
+        lines = r.stdout.splitlines()
+        assert lines[0].startswith("[main] Using Device ") and "B200" in lines[0]
+        assert lines[1:4] == ["num_of_sequences: 40", f"[main] block_size: {block_size}", "[main] grid_size: 20"]
+        assert lines[4].startswith("elapsed ")
+    got = [int(l.split()[1]) for l in out.read_text().splitlines()]
+    assert got == [-1] + want + want
+    r = subprocess.run([str(BIN / "smithWatermanGpu"), str(inp)], capture_output=True, text=True,
+                       env=dict(os.environ, AGX_NUM_GPUS="1"))
+    assert r.returncode == 1 and "<input_file_path> <output_file_path> <block_size>" in r.stderr

@@ -83,3 +83,24 @@ def test_synth_matches_its_own_index(agx):
     assert set(np.unique(sw.buf[sw.off[0]:sw.off[0] + 150]).tolist()) <= set(b"ACGT")
     # seeded: same seed, same bytes
     assert np.array_equal(S.sw_uniform_pairs(33, 150, seed=2).buf, sw.buf)
+
+
+def test_seeded_generator_keeps_the_reference_format(agx, oracle_mod, tmp_path):
+    """drivers/generator.py: generator.py's format (line 1 = alignments, 2N lines over ATGC, lengths in
+    [MIN, MAX]) with the lengths, the count and the seed as arguments."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    gen = ROOT / "drivers" / "generator.py"
+    a, b = tmp_path / "a.txt", tmp_path / "b.txt"
+    for out in (a, b):
+        subprocess.run([sys.executable, str(gen), "64", "80", "30", "--seed", "7", "--out", str(out)], check=True)
+    assert a.read_bytes() == b.read_bytes()                       # seeded
+    lines = a.read_text().split("\n")
+    assert lines[0] == "30" and lines[-1] == "" and len(lines) == 62
+    assert all(64 <= len(l) <= 80 and set(l) <= set("ATGC") for l in lines[1:-1])
+    inp = agx.formats.parse_sw(a.read_bytes())
+    assert inp.n_pairs == 15                                      # SW-Q2: the programs score half of them
+    subprocess.run([sys.executable, str(gen), "64", "80", "30", "--seed", "8", "--header-lines", "--out", str(b)],
+                   check=True)
+    assert b.read_bytes() != a.read_bytes() and agx.formats.parse_sw(b.read_bytes()).n_pairs == 30
