@@ -124,8 +124,8 @@ struct DeviceCtx {
     std::vector<cudaEvent_t> seg_events;   // upload segments of sw_score_file_image
     SwLane lane[2];          // lane[0].st == stream
     SwWorkspace &sw = lane[0].ws;
-    HmmWorkspace hmm;
-    HmmParseWorkspace hmm_parse;
+    HmmWorkspace hmm, hmm_b;                 // hmm_b / hmm_parse_b: second lane of pairhmm_forward_file_image
+    HmmParseWorkspace hmm_parse, hmm_parse_b;
     DevBuf d_bytes, d_a, d_b, d_c, d_d, d_e, d_f, d_out;   // staging for the host entry points
     PinBuf h_a, h_b, h_out;
     std::string error;   // error raised on this device's worker thread
@@ -480,7 +480,7 @@ int hmm_shard(DeviceCtx &c, const HmmHost &h, int64_t r0, int64_t r1, double *ou
     v.n_reads = nr;
     v.n_haps = nh;
     v.n_batches = nb;
-    rc = hmm_run_device(c.hmm, v, nbytes, d_roo, n_out, g_gatk.load() != 0, g_force64.load() != 0, true,
+    rc = hmm_run_device(c.hmm, v, nbytes, d_roo, n_out, g_gatk.load() != 0, g_force64.load() != 0, 1,
                         c.d_out.as<double>(), st);
     if (rc != AGX_OK) return rc;
     AGX_CUDA(cudaMemcpyAsync(out + o0, c.d_out.p, (size_t)n_out * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -603,7 +603,9 @@ void agx_shutdown(void)
         for (cudaEvent_t ev : c->lane_done) if (ev) cudaEventDestroy(ev);
         for (cudaEvent_t ev : c->seg_events) cudaEventDestroy(ev);
         hmm_workspace_free(c->hmm);
+        hmm_workspace_free(c->hmm_b);
         hmm_parse_workspace_free(c->hmm_parse);
+        hmm_parse_workspace_free(c->hmm_parse_b);
         for (DevBuf *b : {&c->d_bytes, &c->d_a, &c->d_b, &c->d_c, &c->d_d, &c->d_e, &c->d_f, &c->d_out}) b->release();
         for (PinBuf *b : {&c->h_a, &c->h_b, &c->h_out}) b->release();
         if (c->stream) cudaStreamDestroy(c->stream);
@@ -881,6 +883,10 @@ int pairhmm_forward_batches_flat(const uint8_t *buf, int64_t buf_bytes, const in
     return hmm_flat_impl(h, log10_out);
 }
 
+// Like sw_score_file_image: the image is uploaded in segments on the copy stream; each region (whole batches)
+// is parsed and paired on the high-priority stream and scored on one of two alternating lanes, so the upload
+// and the host round trips of region k+1 hide behind the stream kernels of region k.  A batch that straddles
+// a region boundary is parsed again at the start of the next region.
 int pairhmm_forward_file_image(const uint8_t *image, int64_t image_bytes, const double **log10_out, int64_t *n_out,
                                const int32_t **batch_pairs, int64_t *n_batches, int32_t *incomplete)
 {
@@ -896,41 +902,135 @@ int pairhmm_forward_file_image(const uint8_t *image, int64_t image_bytes, const 
     if (rc != AGX_OK) return rc;
     DeviceCtx &c = *g_ctx[0];
     AGX_CUDA(cudaSetDevice(c.device));
-    cudaStream_t st = c.stream;
+    cudaStream_t lane_st[2] = {c.lane[0].st, c.lane[1].st};
+    HmmWorkspace *lane_ws[2] = {&c.hmm, &c.hmm_b};
+    HmmParseWorkspace *lane_parse[2] = {&c.hmm_parse, &c.hmm_parse_b};
     if ((rc = c.d_bytes.reserve((size_t)image_bytes + 64)) != AGX_OK) return rc;
-    AGX_CUDA(cudaMemcpyAsync(c.d_bytes.p, image, (size_t)image_bytes, cudaMemcpyHostToDevice, st));
-    HmmParsed ps;
-    if ((rc = hmm_parse_device(c.hmm_parse, c.d_bytes.as<uint8_t>(), image_bytes, image[image_bytes - 1], &ps, st)) != AGX_OK)
+
+    // segments: a short first one so that scoring starts early, then doubling (the stream kernels need ~7x
+    // the time the upload of the same bytes takes, so the copy never falls behind)
+    std::vector<int64_t> seg_end;
+    {
+        int64_t fixed = 0;
+        if (const char *e = getenv("AGX_HMM_IMAGE_SEGMENT")) fixed = atoll(e);   // tuning knob: fixed segment bytes
+        int64_t sz = (int64_t)16 << 20;
+        for (int64_t pos = 0; pos < image_bytes;) {
+            int64_t step = fixed > 0 ? fixed : sz;
+            if (image_bytes - pos - step < step / 2) step = image_bytes - pos;
+            pos += step;
+            seg_end.push_back(pos);
+            sz *= 2;
+        }
+    }
+    const int64_t n_seg = (int64_t)seg_end.size();
+    while ((int64_t)c.seg_events.size() < n_seg) {
+        cudaEvent_t ev;
+        AGX_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        c.seg_events.push_back(ev);
+    }
+    cudaPointerAttributes img_attr;
+    const bool img_pinned = cudaPointerGetAttributes(&img_attr, image) == cudaSuccess && img_attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    int64_t queued = 0;
+    auto upload_through = [&](int64_t k_last) -> int {
+        for (; queued <= k_last && queued < n_seg; ++queued) {
+            const int64_t b = queued ? seg_end[queued - 1] : 0, e = seg_end[queued];
+            AGX_CUDA(cudaMemcpyAsync(c.d_bytes.as<uint8_t>() + b, image + b, (size_t)(e - b), cudaMemcpyHostToDevice, c.copy_stream));
+            AGX_CUDA(cudaEventRecord(c.seg_events[queued], c.copy_stream));
+        }
+        return AGX_OK;
+    };
+    if ((rc = upload_through(img_pinned ? n_seg - 1 : 0)) != AGX_OK) return rc;
+
+    // results: the number of outputs is not known before the last region is parsed, so the device buffer
+    // grows region by region (regions are few); batch counts go to the host as they are parsed
+    std::vector<int32_t> bp_all;
+    int64_t out_done = 0, begin = 0, region = 0;
+    int32_t inc = 0;
+    cudaStream_t prep = c.prep_stream;
+    for (int64_t k = 0; k < n_seg; ++k) {
+        if ((rc = upload_through(k + 1)) != AGX_OK) break;
+        const int64_t avail = seg_end[k];
+        int64_t end = avail;
+        if (k + 1 < n_seg) {
+            const void *r = avail > begin ? memrchr(image + begin, '\n', (size_t)(avail - begin)) : nullptr;
+            if (!r) continue;
+            end = (const uint8_t *)r - image + 1;
+        }
+        if (end <= begin) continue;
+        const int li = (int)(region & 1);
+        AGX_CUDA(cudaStreamWaitEvent(prep, c.seg_events[k], 0));
+        if (region >= 2) AGX_CUDA(cudaStreamWaitEvent(prep, c.lane_done[li], 0));   // the lane's arrays are free again
+        HmmParsed ps;
+        if ((rc = hmm_parse_device(*lane_parse[li], c.d_bytes.as<uint8_t>(), begin, end, image[end - 1], &ps, prep)) != AGX_OK) break;
+        const bool last_region = (k + 1 == n_seg);
+        if (last_region) inc = ps.incomplete;
+        if (ps.n_batches == 0) {
+            if (ps.next_begin <= begin && !last_region) continue;      // one batch spans the whole region: wait for more
+            begin = ps.next_begin;
+            continue;
+        }
+        ++region;
+        // batch counts of this region (pageable destination: the copy is complete when the call returns)
+        const size_t b0 = bp_all.size();
+        bp_all.resize(b0 + (size_t)ps.n_batches);
+        AGX_CUDA(cudaMemcpyAsync(bp_all.data() + b0, ps.batch_pairs, (size_t)ps.n_batches * sizeof(int32_t), cudaMemcpyDeviceToHost, prep));
+        AGX_CUDA(cudaStreamSynchronize(prep));
+        if (ps.n_out > 0) {
+            if ((size_t)(out_done + ps.n_out) * sizeof(double) > c.d_out.cap) {
+                // grow, keeping what earlier regions wrote (both lanes must be idle while the buffer moves)
+                AGX_CUDA(cudaStreamSynchronize(lane_st[0]));
+                AGX_CUDA(cudaStreamSynchronize(lane_st[1]));
+                DevBuf bigger;
+                const double frac = (double)(end - 0) / (double)image_bytes;
+                const size_t want = (size_t)((double)(out_done + ps.n_out) / (frac > 0.05 ? frac : 0.05) * 1.1) * sizeof(double);
+                if ((rc = bigger.reserve(std::max(want, (size_t)(out_done + ps.n_out) * sizeof(double)))) != AGX_OK) break;
+                if (out_done > 0) AGX_CUDA(cudaMemcpy(bigger.p, c.d_out.p, (size_t)out_done * sizeof(double), cudaMemcpyDeviceToDevice));
+                c.d_out.release();
+                c.d_out = bigger;
+            }
+            HmmBatchView v;
+            v.buf = c.d_bytes.as<uint8_t>();
+            v.read_field_off = ps.read_field_off;
+            v.read_len = ps.read_len;
+            v.read_batch = ps.read_batch;
+            v.n_reads = ps.n_reads;
+            v.hap_off = ps.hap_off;
+            v.hap_len = ps.hap_len;
+            v.n_haps = ps.n_haps;
+            v.batch_hap_start = ps.batch_hap_start;
+            v.n_batches = ps.n_batches;
+            rc = hmm_run_device(*lane_ws[li], v, image_bytes, ps.read_out_off, ps.n_out, g_gatk.load() != 0,
+                                g_force64.load() != 0, 2, c.d_out.as<double>() + out_done, lane_st[li], prep);
+            if (rc != AGX_OK) break;
+            out_done += ps.n_out;
+        }
+        AGX_CUDA(cudaEventRecord(c.lane_done[li], lane_st[li]));
+        begin = ps.next_begin;
+    }
+    if (rc != AGX_OK) {
+        cudaStreamSynchronize(c.copy_stream);
+        cudaStreamSynchronize(prep);
+        cudaStreamSynchronize(lane_st[0]);
+        cudaStreamSynchronize(lane_st[1]);
         return rc;
-    if (incomplete) *incomplete = ps.incomplete;
-    if (ps.n_batches > 0) {
-        if ((rc = c.h_b.reserve((size_t)ps.n_batches * sizeof(int32_t))) != AGX_OK) return rc;
-        AGX_CUDA(cudaMemcpyAsync(c.h_b.p, ps.batch_pairs, (size_t)ps.n_batches * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     }
-    if (ps.n_out > 0) {
-        if ((rc = c.d_out.reserve((size_t)ps.n_out * sizeof(double))) != AGX_OK) return rc;
-        if ((rc = c.h_out.reserve((size_t)ps.n_out * sizeof(double))) != AGX_OK) return rc;
-        HmmBatchView v;
-        v.buf = c.d_bytes.as<uint8_t>();
-        v.read_field_off = ps.read_field_off;
-        v.read_len = ps.read_len;
-        v.read_batch = ps.read_batch;
-        v.n_reads = ps.n_reads;
-        v.hap_off = ps.hap_off;
-        v.hap_len = ps.hap_len;
-        v.n_haps = ps.n_haps;
-        v.batch_hap_start = ps.batch_hap_start;
-        v.n_batches = ps.n_batches;
-        rc = hmm_run_device(c.hmm, v, image_bytes, ps.read_out_off, ps.n_out, g_gatk.load() != 0, g_force64.load() != 0,
-                            true, c.d_out.as<double>(), st);
-        if (rc != AGX_OK) return rc;
-        AGX_CUDA(cudaMemcpyAsync(c.h_out.p, c.d_out.p, (size_t)ps.n_out * sizeof(double), cudaMemcpyDeviceToHost, st));
+    AGX_CUDA(cudaStreamSynchronize(lane_st[1]));
+    if (out_done > 0) {
+        if ((rc = c.h_out.reserve((size_t)out_done * sizeof(double))) != AGX_OK) return rc;
+        AGX_CUDA(cudaMemcpyAsync(c.h_out.p, c.d_out.p, (size_t)out_done * sizeof(double), cudaMemcpyDeviceToHost, lane_st[0]));
     }
-    AGX_CUDA(cudaStreamSynchronize(st));
-    *n_out = ps.n_out;
-    *n_batches = ps.n_batches;
-    *log10_out = ps.n_out > 0 ? c.h_out.as<double>() : nullptr;
-    *batch_pairs = ps.n_batches > 0 ? c.h_b.as<int32_t>() : nullptr;
+    AGX_CUDA(cudaStreamSynchronize(lane_st[0]));
+    AGX_CUDA(cudaStreamSynchronize(c.copy_stream));
+    if (!bp_all.empty()) {
+        if ((rc = c.h_b.reserve(bp_all.size() * sizeof(int32_t))) != AGX_OK) return rc;
+        memcpy(c.h_b.p, bp_all.data(), bp_all.size() * sizeof(int32_t));
+    }
+    if (incomplete) *incomplete = inc;
+    *n_out = out_done;
+    *n_batches = (int64_t)bp_all.size();
+    *log10_out = out_done > 0 ? c.h_out.as<double>() : nullptr;
+    *batch_pairs = bp_all.empty() ? nullptr : c.h_b.as<int32_t>();
     return AGX_OK;
 }
 

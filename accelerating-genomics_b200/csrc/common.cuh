@@ -155,19 +155,23 @@ struct HmmParseWorkspace {
 struct HmmParsed {            // device pointers into the workspace
     int64_t n_batches = 0, n_reads = 0, n_haps = 0, n_out = 0;
     int32_t incomplete = 0;   // 1: EOF inside the reads of a last batch, 2: inside its haplotypes (batch dropped)
+    int64_t next_begin = 0;   // where parsing resumes: the dropped batch's header, else the end of the region
     int64_t *read_field_off = nullptr, *read_out_off = nullptr, *hap_off = nullptr;
     int32_t *read_len = nullptr, *read_batch = nullptr, *hap_len = nullptr, *batch_pairs = nullptr;
     int64_t *batch_read_start = nullptr, *batch_hap_start = nullptr, *batch_out_start = nullptr;
 };
-int hmm_parse_device(HmmParseWorkspace &ws, const uint8_t *d_img, int64_t bytes, int last_byte, HmmParsed *out,
-                     cudaStream_t st);
+int hmm_parse_device(HmmParseWorkspace &ws, const uint8_t *d_img, int64_t begin, int64_t bytes, int last_byte,
+                     HmmParsed *out, cudaStream_t st);
 void hmm_parse_workspace_free(HmmParseWorkspace &ws);
 
 int hmm_workspace_reserve(HmmWorkspace &ws, int64_t n_reads, int64_t n_pairs, int64_t n_batches);
 void hmm_workspace_free(HmmWorkspace &ws);
 // d_read_out_off[r] = index in d_out of (read r, first haplotype of its batch); n_pairs = total outputs.
+// rescue: 0 = leave pairs FP32 cannot be trusted with as NaN, 1 = re-run them in FP64 (one more stream
+// synchronisation to size that launch), 2 = the same without the synchronisation (the FP64 kernel reads the
+// count on the device; it is launched even when there is nothing to do).
 int hmm_run_device(HmmWorkspace &ws, const HmmBatchView &v, int64_t buf_bytes, const int64_t *d_read_out_off,
-                   int64_t n_pairs, bool gatk_mode, bool force_fp64, bool rescue, double *d_out,
-                   cudaStream_t st);
+                   int64_t n_pairs, bool gatk_mode, bool force_fp64, int rescue, double *d_out,
+                   cudaStream_t st, cudaStream_t prep_st = nullptr);
 
 }  // namespace agx

@@ -910,8 +910,8 @@ static int hmm_scratch_reserve(HmmWorkspace &ws, int64_t bytes)
 }
 
 int hmm_run_device(HmmWorkspace &ws, const HmmBatchView &v, int64_t buf_bytes, const int64_t *d_read_out_off,
-                   int64_t n_pairs, bool gatk_mode, bool force_fp64, bool do_rescue, double *d_out,
-                   cudaStream_t st)
+                   int64_t n_pairs, bool gatk_mode, bool force_fp64, int do_rescue, double *d_out,
+                   cudaStream_t st, cudaStream_t prep_st)
 {
     if (v.n_reads == 0 || n_pairs == 0) return AGX_OK;
     if (v.n_reads > (int64_t)1 << 30 || v.n_haps > (int64_t)1 << 30)
@@ -919,41 +919,44 @@ int hmm_run_device(HmmWorkspace &ws, const HmmBatchView &v, int64_t buf_bytes, c
     int rc = hmm_workspace_reserve(ws, v.n_reads, n_pairs, v.n_batches);
     if (rc != AGX_OK) return rc;
 
+    // read pairing / row classes: on prep_st (high priority) when given, so that it is not queued behind the
+    // stream kernels of another batch; the caller then guarantees ws is not in use by earlier work on st
+    cudaStream_t cst = prep_st ? prep_st : st;
     static const bool no_duo = getenv("AGX_PAIRHMM_NO_DUO") != nullptr;   // A/B switch: one read per warp only
     const int64_t nmax = v.n_reads > v.n_haps ? v.n_reads : v.n_haps;
     int2 *pairs = reinterpret_cast<int2 *>(ws.pairs);
     bool paired = !force_fp64 && !no_duo;
-    ws.prof_classify.begin(st);
-    AGX_CUDA(cudaMemsetAsync(ws.counters, 0, HCNT_WORDS * sizeof(int32_t), st));
+    ws.prof_classify.begin(cst);
+    AGX_CUDA(cudaMemsetAsync(ws.counters, 0, HCNT_WORDS * sizeof(int32_t), cst));
     if (paired) {
         // reads of the same batch and row class are paired for hmm_duo_kernel
         int32_t *batch_first = ws.batch_first, *batch_end = ws.batch_first + v.n_batches;
-        AGX_CUDA(cudaMemsetAsync(batch_first, 0xff, (size_t)v.n_batches * sizeof(int32_t), st));
-        AGX_CUDA(cudaMemsetAsync(batch_end, 0, (size_t)v.n_batches * sizeof(int32_t), st));
-        hmm_ranges_kernel<<<(int)((nmax + 255) / 256), 256, 0, st>>>(v.read_batch, v.n_reads, v.hap_len, v.n_haps,
+        AGX_CUDA(cudaMemsetAsync(batch_first, 0xff, (size_t)v.n_batches * sizeof(int32_t), cst));
+        AGX_CUDA(cudaMemsetAsync(batch_end, 0, (size_t)v.n_batches * sizeof(int32_t), cst));
+        hmm_ranges_kernel<<<(int)((nmax + 255) / 256), 256, 0, cst>>>(v.read_batch, v.n_reads, v.hap_len, v.n_haps,
                                                                     batch_first, batch_end, ws.counters);
         const int64_t pair_blocks = std::min<int64_t>((v.n_batches + 3) / 4, 148 * 16);
-        hmm_pair_kernel<<<(int)pair_blocks, 128, 0, st>>>(v.read_len, v.n_reads, v.n_batches, batch_first, batch_end,
+        hmm_pair_kernel<<<(int)pair_blocks, 128, 0, cst>>>(v.read_len, v.n_reads, v.n_batches, batch_first, batch_end,
                                                         pairs, ws.order, ws.counters);
         count_launch(2);
         AGX_CUDA(cudaGetLastError());
-        AGX_CUDA(cudaMemcpyAsync(ws.h_counters, ws.counters, HCNT_WORDS * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        AGX_CUDA(cudaStreamSynchronize(st));
+        AGX_CUDA(cudaMemcpyAsync(ws.h_counters, ws.counters, HCNT_WORDS * sizeof(int32_t), cudaMemcpyDeviceToHost, cst));
+        AGX_CUDA(cudaStreamSynchronize(cst));
         if (ws.h_counters[HCNT_UNSORTED]) {
             paired = false;               // reads of a batch are not consecutive: one read per warp
-            AGX_CUDA(cudaMemsetAsync(ws.counters, 0, HCNT_WORDS * sizeof(int32_t), st));
+            AGX_CUDA(cudaMemsetAsync(ws.counters, 0, HCNT_WORDS * sizeof(int32_t), cst));
         }
     }
     if (!paired) {
-        hmm_classify_kernel<<<(int)((nmax + 255) / 256), 256, 0, st>>>(
+        hmm_classify_kernel<<<(int)((nmax + 255) / 256), 256, 0, cst>>>(
             v.read_len, v.n_reads, v.hap_len, v.n_haps, ws.order, ws.counters, force_fp64 ? 1 : 0);
         count_launch();
         AGX_CUDA(cudaGetLastError());
         AGX_CUDA(cudaMemcpyAsync(ws.h_counters, ws.counters, HCNT_WORDS * sizeof(int32_t),
-                                 cudaMemcpyDeviceToHost, st));
-        AGX_CUDA(cudaStreamSynchronize(st));
+                                 cudaMemcpyDeviceToHost, cst));
+        AGX_CUDA(cudaStreamSynchronize(cst));
     }
-    ws.prof_classify.end(st);
+    ws.prof_classify.end(cst);
     int32_t counts[HMM_N_CLASSES], pair_counts[HMM_MAX_K];
     for (int c = 0; c < HMM_N_CLASSES; ++c) counts[c] = ws.h_counters[c];
     for (int c = 0; c < HMM_MAX_K; ++c) pair_counts[c] = paired ? ws.h_counters[HCNT_PAIRS + c] : 0;
@@ -1053,11 +1056,16 @@ int hmm_run_device(HmmWorkspace &ws, const HmmBatchView &v, int64_t buf_bytes, c
             AGX_CUDA(cudaGetLastError());
         }
         if (!do_rescue) return AGX_OK;
-        AGX_CUDA(cudaMemcpyAsync(ws.h_counters + HCNT_RESCUE, rescue_count, sizeof(int32_t),
-                                 cudaMemcpyDeviceToHost, st));
-        AGX_CUDA(cudaStreamSynchronize(st));
-        const int32_t n_rescue = ws.h_counters[HCNT_RESCUE];
-        if (n_rescue == 0) return AGX_OK;
+        int32_t n_rescue = 0;
+        if (do_rescue == 1) {
+            AGX_CUDA(cudaMemcpyAsync(ws.h_counters + HCNT_RESCUE, rescue_count, sizeof(int32_t),
+                                     cudaMemcpyDeviceToHost, st));
+            AGX_CUDA(cudaStreamSynchronize(st));
+            n_rescue = ws.h_counters[HCNT_RESCUE];
+            if (n_rescue == 0) return AGX_OK;
+        } else {
+            n_rescue = (int32_t)std::min<int64_t>(n_pairs, (int64_t)sms * 4);   // grid only; the count stays on the device
+        }
         int64_t warps = n_rescue;
         if (warps > (int64_t)sms * 16) warps = (int64_t)sms * 16;
         const int blocks = (int)((warps + HMM_WARPS - 1) / HMM_WARPS);
@@ -1065,7 +1073,7 @@ int hmm_run_device(HmmWorkspace &ws, const HmmBatchView &v, int64_t buf_bytes, c
         if (rc != AGX_OK) return rc;
         ws.prof_fp64.begin(st);
         hmm_striped_kernel<double, 4><<<blocks, HMM_WARPS * 32, 0, st>>>(
-            v, d_read_out_off, rescue, nullptr, nullptr, n_rescue, ws.d_lut, gatk,
+            v, d_read_out_off, rescue, nullptr, do_rescue == 2 ? rescue_count : nullptr, n_rescue, ws.d_lut, gatk,
             reinterpret_cast<double *>(ws.scratch), stride, d_out, nullptr, nullptr);
         ws.prof_fp64.end(st);
         count_launch();

@@ -34,17 +34,19 @@ enum {
     PI_OUT = 6,
     PI_ERROR = 7,        // validation: 1 read length, 2 haplotype length, 3 field outside line, 4 long line, 5 too many pairs
     PI_ERROR_AT = 8,     // line of the first validation error
+    PI_NEXT_BEGIN = 9,   // byte offset of the header of the dropped (incomplete) last batch, else the region end
     PI_WORDS = 12
 };
 
 __device__ __forceinline__ bool is_blank(uint32_t c) { return c == ' ' || c == '\t'; }
 
 struct LineSpan { int64_t s, e; };   // [s, e) without the '\n'
-__device__ __forceinline__ LineSpan line_span(const int64_t *nl_pos, int64_t n_nl, int64_t end, int64_t k)
+struct Bounds { int64_t b, e; };     // the parsed region of the image: bytes [b, e), b is a line start
+__device__ __forceinline__ LineSpan line_span(const int64_t *nl_pos, int64_t n_nl, Bounds bd, int64_t k)
 {
     LineSpan sp;
-    sp.s = k == 0 ? 0 : nl_pos[k - 1] + 1;
-    sp.e = k < n_nl ? nl_pos[k] : end;
+    sp.s = k == 0 ? bd.b : nl_pos[k - 1] + 1;
+    sp.e = k < n_nl ? nl_pos[k] : bd.e;
     return sp;
 }
 
@@ -66,7 +68,7 @@ __device__ void scan_two_ints(const uint8_t *img, LineSpan sp, int32_t &a, int32
 
 // strict shape of a header in a well-formed file: digits, blanks, digits, nothing else
 __global__ void __launch_bounds__(256)
-hmm_header_flag_kernel(const uint8_t *__restrict__ img, const int64_t *__restrict__ nl_pos, int64_t n_nl, int64_t end,
+hmm_header_flag_kernel(const uint8_t *__restrict__ img, const int64_t *__restrict__ nl_pos, int64_t n_nl, Bounds end,
                        int64_t n_lines, int32_t *__restrict__ flag)
 {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -85,7 +87,7 @@ hmm_header_flag_kernel(const uint8_t *__restrict__ img, const int64_t *__restric
 }
 
 __global__ void __launch_bounds__(256)
-hmm_headers_kernel(const uint8_t *__restrict__ img, const int64_t *__restrict__ nl_pos, int64_t n_nl, int64_t end,
+hmm_headers_kernel(const uint8_t *__restrict__ img, const int64_t *__restrict__ nl_pos, int64_t n_nl, Bounds end,
                    int64_t n_lines, const int32_t *__restrict__ flag, const int64_t *__restrict__ rank,
                    int32_t *__restrict__ hdr_line, int32_t *__restrict__ nr, int32_t *__restrict__ nh,
                    int32_t *__restrict__ npairs, int64_t *__restrict__ info)
@@ -126,7 +128,7 @@ hmm_check_chain_kernel(const int32_t *__restrict__ hdr_line, const int32_t *__re
 
 // the reference's own walk, one thread: flags the lines it would read as headers
 __global__ void hmm_walk_kernel(const uint8_t *__restrict__ img, const int64_t *__restrict__ nl_pos, int64_t n_nl,
-                                int64_t end, int64_t n_lines, int32_t *__restrict__ flag, int64_t *__restrict__ info)
+                                Bounds end, int64_t n_lines, int32_t *__restrict__ flag, int64_t *__restrict__ info)
 {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     int64_t line = 0;
@@ -143,7 +145,8 @@ __global__ void hmm_walk_kernel(const uint8_t *__restrict__ img, const int64_t *
     }
 }
 
-__global__ void hmm_totals_kernel(const int64_t *info_in, const int64_t *__restrict__ tot_r,
+__global__ void hmm_totals_kernel(const int64_t *__restrict__ nl_pos, Bounds bd, const int32_t *__restrict__ hdr_line,
+                                  const int64_t *info_in, const int64_t *__restrict__ tot_r,
                                   const int64_t *__restrict__ tot_h, const int64_t *__restrict__ tot_o,
                                   const int32_t *__restrict__ nr, const int32_t *__restrict__ nh,
                                   const int32_t *__restrict__ npairs, int64_t *__restrict__ brs,
@@ -154,7 +157,12 @@ __global__ void hmm_totals_kernel(const int64_t *info_in, const int64_t *__restr
     const int64_t H = info_in[PI_HEADERS];
     const int64_t nb = H - (info_in[PI_INCOMPLETE] ? 1 : 0);
     int64_t r = *tot_r, h = *tot_h, o = *tot_o;
-    if (info_in[PI_INCOMPLETE] && H > 0) { r -= nr[H - 1]; h -= nh[H - 1]; o -= npairs[H - 1]; }
+    info[PI_NEXT_BEGIN] = bd.e;
+    if (info_in[PI_INCOMPLETE] && H > 0) {
+        r -= nr[H - 1]; h -= nh[H - 1]; o -= npairs[H - 1];
+        const int32_t k = hdr_line[H - 1];
+        info[PI_NEXT_BEGIN] = k == 0 ? bd.b : nl_pos[k - 1] + 1;
+    }
     info[PI_BATCHES] = nb;
     info[PI_READS] = r;
     info[PI_HAPS] = h;
@@ -164,7 +172,7 @@ __global__ void hmm_totals_kernel(const int64_t *info_in, const int64_t *__restr
 
 // One warp per line.  Header rank (inclusive) - 1 = batch of the line.
 __global__ void __launch_bounds__(128)
-hmm_fill_lines_kernel(const uint8_t *__restrict__ img, const int64_t *__restrict__ nl_pos, int64_t n_nl, int64_t end,
+hmm_fill_lines_kernel(const uint8_t *__restrict__ img, const int64_t *__restrict__ nl_pos, int64_t n_nl, Bounds end,
                       int64_t n_lines, const int32_t *__restrict__ flag, const int64_t *__restrict__ rank,
                       const int32_t *__restrict__ hdr_line, const int32_t *__restrict__ nr,
                       const int32_t *__restrict__ nh, const int64_t *__restrict__ brs,
@@ -222,7 +230,7 @@ hmm_fill_lines_kernel(const uint8_t *__restrict__ img, const int64_t *__restrict
 #pragma unroll
         for (int f = 0; f < 5; ++f) {
             read_field_off[5 * r + f] = fo[f];
-            if (fo[f] + len > end) { info[PI_ERROR] = 3; info[PI_ERROR_AT] = k; }
+            if (fo[f] + len > end.e) { info[PI_ERROR] = 3; info[PI_ERROR_AT] = k; }
         }
         read_len[r] = (int32_t)len;
         read_batch[r] = (int32_t)b;
@@ -243,19 +251,23 @@ void hmm_parse_workspace_free(HmmParseWorkspace &ws)
     ws = HmmParseWorkspace();
 }
 
-// Parses d_img[0, bytes) into the arrays of `out` (all device pointers into the workspace).
-// Synchronises `st` three times (newline count, header count, totals + validation).
-int hmm_parse_device(HmmParseWorkspace &ws, const uint8_t *d_img, int64_t bytes, int last_byte, HmmParsed *out,
-                     cudaStream_t st)
+// Parses d_img[begin, bytes) (begin = the start of a header line) into the arrays of `out` (all device
+// pointers into the workspace; offsets are offsets into d_img).  A last batch that runs past `bytes` is
+// dropped and reported through out->incomplete / out->next_begin, so a caller that holds only a prefix of the
+// file can parse it region by region.  Synchronises `st` four times.
+int hmm_parse_device(HmmParseWorkspace &ws, const uint8_t *d_img, int64_t begin, int64_t bytes, int last_byte,
+                     HmmParsed *out, cudaStream_t st)
 {
     *out = HmmParsed();
-    if (bytes <= 0) return AGX_OK;
+    out->next_begin = bytes;
+    if (bytes <= begin) return AGX_OK;
+    const Bounds bd{begin, bytes};
     if (!ws.h_info) AGX_CUDA(cudaMallocHost(&ws.h_info, PI_WORDS * sizeof(int64_t)));
     auto align = [](int64_t x) { return (x + 255) / 256 * 256; };
 
     int64_t *nl_pos = nullptr;
     int64_t n_nl = 0;
-    int rc = text_newline_index(ws.idx, d_img, 0, bytes, 0, &nl_pos, &n_nl, nullptr, st);
+    int rc = text_newline_index(ws.idx, d_img, begin, bytes, 0, &nl_pos, &n_nl, nullptr, st);
     if (rc != AGX_OK) return rc;
     const int64_t n_lines = n_nl + (last_byte == '\n' ? 0 : 1);
     if (n_lines == 0) return AGX_OK;
@@ -279,7 +291,7 @@ int hmm_parse_device(HmmParseWorkspace &ws, const uint8_t *d_img, int64_t bytes,
     AGX_CUDA(cudaMemsetAsync(info, 0, 256 + 64, st));
 
     const int lblocks = (int)((n_lines + 255) / 256);
-    hmm_header_flag_kernel<<<lblocks, 256, 0, st>>>(d_img, nl_pos, n_nl, bytes, n_lines, flag);
+    hmm_header_flag_kernel<<<lblocks, 256, 0, st>>>(d_img, nl_pos, n_nl, bd, n_lines, flag);
     count_launch();
     int64_t H = 0;
     int32_t *hdr_line = nullptr, *nr = nullptr, *nh = nullptr, *npairs = nullptr;
@@ -307,7 +319,7 @@ int hmm_parse_device(HmmParseWorkspace &ws, const uint8_t *d_img, int64_t bytes,
         out->batch_hap_start = reinterpret_cast<int64_t *>(tb + 5 * sz_i32 + sz_i64);
         out->batch_out_start = reinterpret_cast<int64_t *>(tb + 5 * sz_i32 + 2 * sz_i64);
         if (H > 0) {
-            hmm_headers_kernel<<<lblocks, 256, 0, st>>>(d_img, nl_pos, n_nl, bytes, n_lines, flag, rank, hdr_line, nr,
+            hmm_headers_kernel<<<lblocks, 256, 0, st>>>(d_img, nl_pos, n_nl, bd, n_lines, flag, rank, hdr_line, nr,
                                                         nh, npairs, info);
             count_launch();
         }
@@ -321,7 +333,7 @@ int hmm_parse_device(HmmParseWorkspace &ws, const uint8_t *d_img, int64_t bytes,
             // not a tiling of header-shaped lines: follow the reference's walk, then redo scan + headers
             AGX_CUDA(cudaMemsetAsync(flag, 0, (size_t)n_lines * sizeof(int32_t), st));
             AGX_CUDA(cudaMemsetAsync(info, 0, PI_WORDS * sizeof(int64_t), st));
-            hmm_walk_kernel<<<1, 32, 0, st>>>(d_img, nl_pos, n_nl, bytes, n_lines, flag, info);
+            hmm_walk_kernel<<<1, 32, 0, st>>>(d_img, nl_pos, n_nl, bd, n_lines, flag, info);
             count_launch();
         }
     }
@@ -330,13 +342,14 @@ int hmm_parse_device(HmmParseWorkspace &ws, const uint8_t *d_img, int64_t bytes,
     if ((rc = device_exclusive_scan(nr, H, out->batch_read_start, tmp + scan_tmp, tot + 0, st)) != AGX_OK) return rc;
     if ((rc = device_exclusive_scan(nh, H, out->batch_hap_start, tmp + 2 * scan_tmp, tot + 1, st)) != AGX_OK) return rc;
     if ((rc = device_exclusive_scan(npairs, H, out->batch_out_start, tmp + 3 * scan_tmp, tot + 2, st)) != AGX_OK) return rc;
-    hmm_totals_kernel<<<1, 1, 0, st>>>(info, tot + 0, tot + 1, tot + 2, nr, nh, npairs, out->batch_read_start,
+    hmm_totals_kernel<<<1, 1, 0, st>>>(nl_pos, bd, hdr_line, info, tot + 0, tot + 1, tot + 2, nr, nh, npairs, out->batch_read_start,
                                        out->batch_hap_start, out->batch_out_start, info);
     count_launch();
     AGX_CUDA(cudaMemcpyAsync(ws.h_info, info, PI_WORDS * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     AGX_CUDA(cudaStreamSynchronize(st));
     if (ws.h_info[PI_ERROR] == 5) return fail(AGX_ERANGE, "pairhmm: a batch holds more than 2^31 pairs");
     out->incomplete = (int32_t)ws.h_info[PI_INCOMPLETE];
+    out->next_begin = ws.h_info[PI_NEXT_BEGIN];
     out->n_batches = ws.h_info[PI_BATCHES];
     out->n_reads = ws.h_info[PI_READS];
     out->n_haps = ws.h_info[PI_HAPS];
@@ -363,7 +376,7 @@ int hmm_parse_device(HmmParseWorkspace &ws, const uint8_t *d_img, int64_t bytes,
     out->hap_len = reinterpret_cast<int32_t *>(ab + sz_rfo + sz_roo + sz_ho + sz_rl + sz_rb);
 
     const int64_t fblocks = (n_lines * 32 + 127) / 128;
-    hmm_fill_lines_kernel<<<(int)fblocks, 128, 0, st>>>(d_img, nl_pos, n_nl, bytes, n_lines, flag, rank, hdr_line, nr, nh,
+    hmm_fill_lines_kernel<<<(int)fblocks, 128, 0, st>>>(d_img, nl_pos, n_nl, bd, n_lines, flag, rank, hdr_line, nr, nh,
                                                         out->batch_read_start, out->batch_hap_start,
                                                         out->batch_out_start, info, out->read_field_off, out->read_len,
                                                         out->read_batch, out->read_out_off, out->hap_off, out->hap_len,

@@ -217,3 +217,20 @@ def test_file_image_config4_shape(agx, gpu_lib):
     vals, batch_pairs, incomplete = gpu_lib.pairhmm_forward_file_image(inp.buf)
     assert incomplete == 0 and batch_pairs.tolist() == [1000] * 40
     assert np.array_equal(vals, _run_flat(gpu_lib, inp))
+
+
+@pytest.mark.parametrize("segment", [700, 5000, 1 << 16])
+def test_file_image_streaming_segments(agx, gpu_lib, segment, monkeypatch):
+    """Upload segments far smaller than a batch, batches straddling them, a truncated last batch."""
+    inp = agx.synth.pairhmm_batches(12, 14, 3, seed=segment)
+    data = bytes(inp.buf)
+    want = _run_flat(gpu_lib, inp)
+    monkeypatch.setenv("AGX_HMM_IMAGE_SEGMENT", str(segment))
+    vals, batch_pairs, incomplete = gpu_lib.pairhmm_forward_file_image(data)
+    assert incomplete == 0 and batch_pairs.tolist() == [42] * 12
+    assert np.array_equal(vals, want)
+    lines = data.split(b"\n")[:-1]
+    cut = b"\n".join(lines[: 11 * 18 + 6]) + b"\n"                  # batch = 1 + 14 + 3 lines; EOF inside the reads
+    vals, batch_pairs, incomplete = gpu_lib.pairhmm_forward_file_image(cut)
+    assert incomplete == 1 and batch_pairs.tolist() == [42] * 11
+    assert np.array_equal(vals, want[: 11 * 42])
