@@ -648,6 +648,83 @@ int sw_score_batch_flat(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *
                         scores_out);
 }
 
+// sw_score_file_image over several GPUs: the image is cut into one byte range per GPU at line starts; every
+// GPU uploads and chunks its own range (phase 1, one host thread per GPU), the host turns the chunk counts
+// into the global pairing -- a range that starts at an odd chunk index scores its first chunk against the
+// last chunk of the range before it, whose bytes it uploaded as well -- and every GPU scores the pairs whose
+// second chunk it holds (phase 2).  Returns 1 when the input does not suit this path (the caller then takes
+// the single-GPU one).
+static int sw_file_image_multi(const uint8_t *image, int64_t image_bytes, int64_t hlen, int32_t line_buf, SwScoring sc,
+                        int64_t want_pairs, int32_t *scores_out, int64_t scores_cap, int64_t *n_pairs_out,
+                        int64_t *dangling_off, int32_t *dangling_len)
+{
+    const int n_dev = (int)g_ctx.size();
+    const int64_t body = image_bytes - hlen;
+    if (n_dev < 2 || body < (int64_t)n_dev * (4 << 20)) return 1;
+    std::vector<int64_t> cut(n_dev + 1, image_bytes);
+    cut[0] = hlen;
+    for (int d = 1; d < n_dev; ++d) {
+        const int64_t nominal = hlen + body * d / n_dev;
+        const void *nl = memchr(image + nominal, '\n', (size_t)(image_bytes - nominal));
+        cut[d] = nl ? (const uint8_t *)nl - image + 1 : image_bytes;
+        if (cut[d] < cut[d - 1]) cut[d] = cut[d - 1];
+    }
+    struct Part { int64_t n_chunks = 0, last_off = -1; int32_t last_len = 0; int64_t *d_off = nullptr; int32_t *d_len = nullptr; };
+    std::vector<Part> part(n_dev);
+    const int64_t max_chunks = 2 * want_pairs;
+    int rc = for_each_device(n_dev, [&](DeviceCtx &c, int d) -> int {
+        SwLane &L = c.lane[0];
+        int r;
+        if ((r = L.bytes.reserve((size_t)image_bytes + 64)) != AGX_OK) return r;
+        if (cut[d + 1] <= cut[d]) return AGX_OK;
+        const int64_t up0 = std::max<int64_t>(hlen, cut[d] - (line_buf - 1));       // + the chunk before the range
+        AGX_CUDA(cudaMemcpyAsync(L.bytes.as<uint8_t>() + up0, image + up0, (size_t)(cut[d + 1] - up0), cudaMemcpyHostToDevice, L.st));
+        return sw_parse_device(c.parse[0], L.bytes.as<uint8_t>(), cut[d], cut[d + 1], line_buf, max_chunks,
+                               image[cut[d + 1] - 1], &part[d].d_off, &part[d].d_len, &part[d].n_chunks, &part[d].last_off,
+                               &part[d].last_len, L.st);
+    });
+    if (rc != AGX_OK) return rc;
+    for (int d = 0; d < n_dev; ++d)
+        if (part[d].n_chunks == 0) return 1;            // e.g. one line longer than a range: not for this path
+    // global chunk numbering, truncated to what line 1 asks for
+    std::vector<int64_t> start(n_dev + 1, 0), used(n_dev, 0);
+    for (int d = 0; d < n_dev; ++d) {
+        used[d] = std::max<int64_t>(0, std::min(part[d].n_chunks, max_chunks - start[d]));
+        start[d + 1] = start[d] + used[d];
+    }
+    const int64_t total = start[n_dev], n_pairs = total / 2;
+    if (n_pairs > scores_cap)
+        return fail(AGX_ERANGE, "sw: scores_out holds " + std::to_string(scores_cap) + " scores, the file has " +
+                                    std::to_string(n_pairs) + " pairs");
+    rc = for_each_device(n_dev, [&](DeviceCtx &c, int d) -> int {
+        SwLane &L = c.lane[0];
+        const int64_t p_lo = start[d] / 2, p_hi = (start[d] + used[d]) / 2, m = p_hi - p_lo;
+        if (m <= 0) return AGX_OK;
+        const int shift = (int)(start[d] & 1);          // odd: pair p_lo = (last chunk of the range before, my chunk 0)
+        if (shift) {
+            AGX_CUDA(cudaMemcpyAsync(part[d].d_off - 1, &part[d - 1].last_off, sizeof(int64_t), cudaMemcpyHostToDevice, L.st));
+            AGX_CUDA(cudaMemcpyAsync(part[d].d_len - 1, &part[d - 1].last_len, sizeof(int32_t), cudaMemcpyHostToDevice, L.st));
+        }
+        int r;
+        if ((r = L.out.reserve((size_t)m * sizeof(int32_t))) != AGX_OK) return r;
+        if ((r = L.h_out.reserve((size_t)m * sizeof(int32_t))) != AGX_OK) return r;
+        r = sw_run_device(L.ws, L.bytes.as<uint8_t>(), part[d].d_off - shift, part[d].d_len - shift, m, sc, L.out.as<int32_t>(), L.st);
+        if (r != AGX_OK) return r;
+        AGX_CUDA(cudaMemcpyAsync(L.h_out.p, L.out.p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, L.st));
+        AGX_CUDA(cudaStreamSynchronize(L.st));
+        memcpy(scores_out + p_lo, L.h_out.p, (size_t)m * sizeof(int32_t));
+        return AGX_OK;
+    });
+    if (rc != AGX_OK) return rc;
+    if (want_pairs > n_pairs && (total & 1)) {
+        // EOF in the middle of a pair: the dangling first line is the last chunk of the file
+        if (dangling_off) *dangling_off = part[n_dev - 1].last_off;
+        if (dangling_len) *dangling_len = part[n_dev - 1].last_len;
+    }
+    if (n_pairs_out) *n_pairs_out = n_pairs;
+    return AGX_OK;
+}
+
 // The image goes to the device in segments on a copy stream; line-aligned regions are chunked (sw_parse.cu)
 // and scored on the compute stream as soon as the segment that completes them has landed, so the DP
 // kernels run under the remaining host->device copies.  A region that ends in the middle of a pair hands
@@ -680,6 +757,10 @@ int sw_score_file_image(const uint8_t *image, int64_t image_bytes, int32_t line_
     if (!scores_out) return fail(AGX_EINVAL, "sw: null argument");
     int rc = require_init();
     if (rc != AGX_OK) return rc;
+    const SwScoring sc_multi{match, mismatch, gap_open, gap_extend};
+    rc = sw_file_image_multi(image, image_bytes, hlen, line_buf, sc_multi, want_pairs, scores_out, scores_cap, n_pairs_out,
+                             dangling_off, dangling_len);
+    if (rc != 1) return rc;                  // done (or failed) on several GPUs; 1 = take the single-GPU path
     DeviceCtx &ctx = *g_ctx[0];
     AGX_CUDA(cudaSetDevice(ctx.device));
     SwLane &L = ctx.lane[0];                 // owns the image and the scores on the device

@@ -361,7 +361,8 @@ int sw_parse_device(SwParseWorkspace &ws, const uint8_t *d_img, int64_t begin, i
     // chunk table size is known after the chunk scan; lines <= cap bytes give exactly n_lines chunks, and a
     // split line adds at most len/cap more: bound by n_lines + n_bytes / cap
     const int64_t chunk_bound = std::min<int64_t>(max_chunks, n_lines + n_bytes / cap + 1);
-    const int64_t sz_off = align(chunk_bound * 8), sz_len = align(chunk_bound * 4);
+    // one spare entry in front of each table: a caller may put the chunk that precedes the region there
+    const int64_t sz_off = align((chunk_bound + 1) * 8), sz_len = align((chunk_bound + 1) * 4);
     const int64_t need2 = sz_np + sz_cpl + sz_cb + sz_tmp2 + sz_off + sz_len + 512;
     if (need2 > ws.cap2) {
         if (ws.buf2) cudaFree(ws.buf2);
@@ -374,8 +375,8 @@ int sw_parse_device(SwParseWorkspace &ws, const uint8_t *d_img, int64_t begin, i
     int32_t *cpl = reinterpret_cast<int32_t *>(b2 + sz_np);
     int64_t *chunk_base = reinterpret_cast<int64_t *>(b2 + sz_np + sz_cpl);
     int64_t *tmp2 = reinterpret_cast<int64_t *>(b2 + sz_np + sz_cpl + sz_cb);
-    int64_t *off = reinterpret_cast<int64_t *>(b2 + sz_np + sz_cpl + sz_cb + sz_tmp2);
-    int32_t *len = reinterpret_cast<int32_t *>(b2 + sz_np + sz_cpl + sz_cb + sz_tmp2 + sz_off);
+    int64_t *off = reinterpret_cast<int64_t *>(b2 + sz_np + sz_cpl + sz_cb + sz_tmp2) + 1;
+    int32_t *len = reinterpret_cast<int32_t *>(b2 + sz_np + sz_cpl + sz_cb + sz_tmp2 + sz_off) + 1;
     int64_t *d_total2 = reinterpret_cast<int64_t *>(b2 + sz_np + sz_cpl + sz_cb + sz_tmp2 + sz_off + sz_len);
 
     nl_emit_kernel<<<(int)tiles, TILE_THREADS, 0, st>>>(d_img, begin, end, tile_base64, nl_pos);

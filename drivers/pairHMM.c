@@ -154,7 +154,7 @@ int main(int argc, const char *argv[])
     }
     fclose(in);
 
-    int n_gpus = 0;
+    int n_gpus = 1;                      /* AGX_NUM_GPUS=<n> binds more (0 = every visible GPU) */
     const char *env = getenv("AGX_NUM_GPUS");
     if (env) n_gpus = atoi(env);
     if (agx_init(n_gpus) != AGX_OK) {
@@ -173,7 +173,16 @@ int main(int argc, const char *argv[])
     int32_t incomplete = 0;
     double *lh_host = NULL;          /* host-split path only */
     int32_t *bp_host = NULL;
-    int rc = pairhmm_forward_file_image(img, (int64_t)size, &lh, &n_out, &batch_pairs, &n_batches, &incomplete);
+    int rc;
+    if (agx_device_count() > 1) {
+        /* several GPUs bound (AGX_NUM_GPUS > 1): the file-image entry point runs on one GPU, the flat one
+           shards the reads over all of them, so split on the host and take that one */
+        rc = split_on_host(img, size, &lh_host, &n_out, &bp_host, &n_batches, &err);
+        lh = lh_host;
+        batch_pairs = bp_host;
+    } else {
+        rc = pairhmm_forward_file_image(img, (int64_t)size, &lh, &n_out, &batch_pairs, &n_batches, &incomplete);
+    }
     if (rc == AGX_OK) {
         if (incomplete == 1) err = "Error reading reads.\n";
         if (incomplete == 2) err = "Error reading haplotypes.\n";

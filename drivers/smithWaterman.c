@@ -12,8 +12,8 @@
  *   - one "Score: %d" per pair in file order (:348), the dangling first line of an incomplete last
  *     pair echoed (:223-227), then "elapsed %f" in seconds (:351-352).
  * The file image is handed to sw_score_file_image(): the fgets() chunking and the DP (:246-347) both
- * run on the GPU; the host only reads the file and prints.  AGX_NUM_GPUS=<n> limits the devices the
- * library binds (default: all visible).  There is no CPU fallback.
+ * run on the GPU; the host only reads the file and prints.  AGX_NUM_GPUS=<n> binds n GPUs (default 1,
+ * 0 = all visible): a large file is then cut into one byte range per GPU.  There is no CPU fallback.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -72,7 +72,7 @@ int main(int argc, char *argv[])
     }
     double iStart = seconds();
 
-    int n_gpus = 0;
+    int n_gpus = 1;                               /* AGX_NUM_GPUS=<n> binds more (0 = every visible GPU) */
     env = getenv("AGX_NUM_GPUS");
     if (env) n_gpus = atoi(env);
     int64_t score_cap = (int64_t)(size / 2 + 2), n_pairs = 0, dangling_off = -1;

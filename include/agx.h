@@ -111,7 +111,9 @@ int sw_score_batch_flat(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *
  * ceil(lines/2) pairs are scored (:216).  line_buf = 1000 is the reference's MAX_LINE_LENGTH (:44).
  * *n_pairs_out = pairs scored (scores_out[0 .. n)), *header_out = atoi(line 1); when the file ends in
  * the middle of a pair, *dangling_off / *dangling_len locate the first line of that pair (the
- * reference echoes it, :223-227), else *dangling_off = -1.  Runs on the first configured GPU. */
+ * reference echoes it, :223-227), else *dangling_off = -1.  With several GPUs bound and an image of at least
+ * 4 MiB per GPU the image is cut into one byte range per GPU (no collective: every GPU chunks and scores its
+ * own range); otherwise the upload is streamed to the first GPU and overlapped with its DP kernels. */
 int sw_score_file_image(const uint8_t *image, int64_t image_bytes, int32_t line_buf,
                         int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend,
                         int32_t *scores_out, int64_t scores_cap, int64_t *n_pairs_out,

@@ -86,3 +86,25 @@ def test_long_alignment_multi_gpu_equals_single_gpu_200kbp(agx, multi):
     cap.shutdown()
     cap.init(0)
     assert many == one and many > 100_000
+
+
+@pytest.mark.parametrize("seed,header_frac,trail", [(1, 1.0, True), (2, 1.0, False), (3, 0.7, True), (4, 1.3, True)])
+def test_sw_file_image_is_cut_into_one_range_per_gpu(agx, multi, seed, header_frac, trail):
+    """sw_score_file_image on several GPUs: ranges that start at an odd chunk index (their first chunk pairs
+    with the previous range's last one), lines split by the fgets() buffer, a header that asks for fewer or
+    more lines than the file holds, a dangling last line."""
+    cap, n = multi
+    rng = np.random.default_rng(seed)
+    alpha = np.frombuffer(b"ACGT", np.uint8)
+    n_lines = 60001                                              # odd: the last line dangles when all are asked for
+    lens = rng.integers(1, 700, size=n_lines)
+    lens[rng.integers(0, n_lines, size=40)] = rng.integers(1000, 2600, size=40)   # split by the 1000-byte buffer
+    lines = [alpha[rng.integers(0, 4, size=int(l))].tobytes() for l in lens]
+    header = int(header_frac * n_lines)
+    data = str(header).encode() + b"\n" + b"\n".join(lines) + (b"\n" if trail else b"")
+    assert len(data) >= n * (4 << 20)
+    host = agx.formats.parse_sw(data)
+    want = cap.sw_score_flat(host.buf, host.off, host.len)
+    scores, hdr, dangling = cap.sw_score_file_image(data)
+    assert hdr == header and dangling == host.dangling
+    assert scores.tolist() == want.tolist()
