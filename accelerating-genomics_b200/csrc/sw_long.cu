@@ -69,6 +69,11 @@ __device__ __forceinline__ int32_t add_fma(int32_t a, int32_t b, int32_t one)
 #ifndef AGX_LONG_PREFETCH
 #define AGX_LONG_PREFETCH 0
 #endif
+// row steps unrolled per loop trip (lets ptxas start the chain-independent part of the next row early)
+#ifndef AGX_LONG_UNROLL
+#define AGX_LONG_UNROLL 1
+#endif
+constexpr int LONG_UNROLL = AGX_LONG_UNROLL;
 #ifndef AGX_LONG_MEMOPS
 #define AGX_LONG_MEMOPS 1
 #endif
@@ -232,7 +237,7 @@ sw_long_kernel(LongArgs g)
             }
 #endif
             const int send = min(32, S - s0);
-#pragma unroll 1
+#pragma unroll LONG_UNROLL
             for (int u = 0; u < send; ++u) {
                 const int s = s0 + u;
                 const int slot = (s - lane) & (LONG_RING - 1);
@@ -320,6 +325,211 @@ sw_long_kernel(LongArgs g)
     if (lane == 0 && best > 0) atomicMax(g.best, best);
 }
 
+// Two rows per step (symbol-coded cells only).  With one warp per scheduler a row step is a latency chain --
+// shuffle in, K dependent cells, shuffle out: ~200 clocks whatever K is -- so lane t advances TWO rows per
+// step (rows 2(s-t), 2(s-t)+1): the shuffle latency and the loop are paid once per two rows, and the two
+// rows' chains run one column apart, which doubles the instruction-level parallelism a lone warp offers.
+// A block is 32 steps = 64 rows; everything else (tagged entries, staged flush, uniform polling) as above.
+template <int K, bool SHORT>
+__global__ void __launch_bounds__(LONG_WARPS * 32)
+sw_long2_kernel(LongArgs g)
+{
+    constexpr int W = 32 * K;
+    constexpr int RING = 128;
+    __shared__ int32_t r_lo[LONG_WARPS][RING];
+    __shared__ int32_t r_hi[LONG_WARPS][RING];
+    __shared__ int32_t r_g[LONG_WARPS][RING];
+    __shared__ int32_t r_e[LONG_WARPS][RING];
+    __shared__ int2 stage[LONG_WARPS][64];
+
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int warp = blockIdx.x * LONG_WARPS + wib;
+    const int n_warps = gridDim.x * LONG_WARPS;
+    const int32_t goe = g.sc.gap_open + g.sc.gap_extend;
+    const int32_t ext = g.sc.gap_extend;
+    const int32_t sub_match = g.sc.match - goe, sub_mis = g.sc.mismatch - goe;
+    const int32_t lb = g.lb;
+    const int n_stripes = (g.la + W - 1) / W;
+    int32_t bestg = goe;
+    const int32_t one = g.one;
+    const uint32_t xb4 = (uint32_t)(uint8_t)(int8_t)sub_mis * 0x01010101u;
+    const uint32_t mxor = (uint32_t)(uint8_t)(int8_t)sub_mis ^ (uint32_t)(uint8_t)(int8_t)sub_match;
+    auto row_table = [&](int32_t r, uint32_t &lo, uint32_t &hi) {
+        lo = xb4; hi = xb4;
+        if (r < lb) {
+            const uint32_t c = g.lut[g.b[r]];
+            if (c < 4) lo ^= mxor << (8 * c); else hi ^= mxor << (8 * (c - 4));
+        }
+    };
+
+    for (int st = warp; st < n_stripes; st += n_warps) {
+        const int c0 = st * W + lane * K;
+        int32_t acol[K], Gp[K], F[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const uint32_t c = (c0 + j < g.la) ? (uint32_t)g.lut[g.a[c0 + j]] : 7u;
+            acol[j] = (int32_t)(c | ((8u | c) * 0x1110u));
+            Gp[j] = goe;
+            F[j] = goe;
+        }
+        int32_t g_out0 = goe, e_out0 = goe, g_out1 = goe, e_out1 = goe, g_in_prev = goe;
+        const int32_t gst = g.stripe_base + st;
+        const bool left_edge = (gst == 0);
+        const bool last = (st == n_stripes - 1);
+        int4 *out_bnd = last ? g.next_bnd : g.bnd;
+        const bool out_remote = last;
+        const bool in_remote = (st == 0);
+        const int S = (lb + 1) / 2 + 31;                 // steps: lane 31 finishes row lb-1 at step (lb-1)/2 + 31
+
+        // inputs of the first 64 rows: this lane loads rows lane and 32 + lane of every block
+        const int4 fresh = make_int4(goe, gst - 1, goe, gst - 1);
+        int4 nxa = fresh, nxb = fresh;
+        uint32_t la_lo, la_hi, lb_lo, lb_hi;
+        row_table(lane, la_lo, la_hi);
+        row_table(32 + lane, lb_lo, lb_hi);
+        if (!left_edge) {
+            if (lane < lb) nxa = ld_entry(g.bnd + lane, in_remote);
+            if (32 + lane < lb) nxb = ld_entry(g.bnd + 32 + lane, in_remote);
+        }
+        for (int s0 = 0; s0 < S; s0 += 32) {
+            {
+                const int ra = 2 * s0 + lane, rb_ = ra + 32;
+                if (!left_edge) {
+                    unsigned ns = 32;
+                    while (__any_sync(0xffffffffu, nxa.y != gst - 1 || nxa.w != gst - 1 || nxb.y != gst - 1 || nxb.w != gst - 1)) {
+                        __nanosleep(ns);
+                        if (ns < 512) ns *= 2;
+                        if (ra < lb && (nxa.y != gst - 1 || nxa.w != gst - 1)) nxa = ld_entry(g.bnd + ra, in_remote);
+                        if (rb_ < lb && (nxb.y != gst - 1 || nxb.w != gst - 1)) nxb = ld_entry(g.bnd + rb_, in_remote);
+                    }
+                }
+                r_lo[wib][ra & (RING - 1)] = (int32_t)la_lo;  r_hi[wib][ra & (RING - 1)] = (int32_t)la_hi;
+                r_g[wib][ra & (RING - 1)] = nxa.x;            r_e[wib][ra & (RING - 1)] = nxa.z;
+                r_lo[wib][rb_ & (RING - 1)] = (int32_t)lb_lo; r_hi[wib][rb_ & (RING - 1)] = (int32_t)lb_hi;
+                r_g[wib][rb_ & (RING - 1)] = nxb.x;           r_e[wib][rb_ & (RING - 1)] = nxb.z;
+            }
+            __syncwarp();
+            const int send = min(32, S - s0);
+#pragma unroll 1
+            for (int u = 0; u < send; ++u) {
+                const int s = s0 + u;
+                const bool live = (s - lane) >= 0;
+                const int slot0 = (2 * (s - lane)) & (RING - 1), slot1 = slot0 + 1;
+                uint32_t t0lo = xb4, t0hi = xb4, t1lo = xb4, t1hi = xb4;
+                if (live) {
+                    t0lo = (uint32_t)r_lo[wib][slot0]; t0hi = (uint32_t)r_hi[wib][slot0];
+                    t1lo = (uint32_t)r_lo[wib][slot1]; t1hi = (uint32_t)r_hi[wib][slot1];
+                }
+                int32_t g_in0 = __shfl_up_sync(0xffffffffu, g_out0, 1);
+                int32_t e0 = __shfl_up_sync(0xffffffffu, e_out0, 1);
+                int32_t g_in1 = __shfl_up_sync(0xffffffffu, g_out1, 1);
+                int32_t e1 = __shfl_up_sync(0xffffffffu, e_out1, 1);
+                if (lane == 0) {
+                    g_in0 = r_g[wib][slot0]; e0 = r_e[wib][slot0];
+                    g_in1 = r_g[wib][slot1]; e1 = r_e[wib][slot1];
+                }
+                int32_t gdiag0 = g_in_prev;              // (H+goe)[i0-1][c0-1]
+                g_in_prev = g_in1;
+                int32_t gdiag1 = g_in0;                  // (H+goe)[i0][c0-1]
+                int32_t gleft0 = g_in0, gleft1 = g_in1;
+                if constexpr (SHORT) {
+                    int32_t tgp0 = g_in0, tgp1 = g_in1;
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        const int32_t d0 = add_fma(gdiag0, prmt_s(t0lo, t0hi, (uint32_t)acol[j]), one);
+                        const int32_t F0 = __viaddmax_s32(F[j], ext, Gp[j]);
+                        const int32_t tg0 = add_fma(__vimax_s32_relu(F0, d0), goe, one);
+                        e0 = __viaddmax_s32(e0, ext, tgp0);
+                        gdiag0 = Gp[j];
+                        const int32_t g0 = __viaddmax_s32(e0, goe, tg0);          // (H+goe)[i0][j]
+                        const int32_t d1 = add_fma(gdiag1, prmt_s(t1lo, t1hi, (uint32_t)acol[j]), one);
+                        const int32_t F1 = __viaddmax_s32(F0, ext, g0);
+                        const int32_t tg1 = add_fma(__vimax_s32_relu(F1, d1), goe, one);
+                        e1 = __viaddmax_s32(e1, ext, tgp1);
+                        gdiag1 = g0;
+                        const int32_t g1 = __viaddmax_s32(e1, goe, tg1);          // (H+goe)[i1][j]
+                        tgp0 = tg0; tgp1 = tg1;
+                        gleft0 = g0; gleft1 = g1;
+                        Gp[j] = g1; F[j] = F1;
+                        bestg = __vimax3_s32(bestg, g0, g1);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        const int32_t d0 = add_fma(gdiag0, prmt_s(t0lo, t0hi, (uint32_t)acol[j]), one);
+                        e0 = __viaddmax_s32(e0, ext, gleft0);
+                        const int32_t F0 = __viaddmax_s32(F[j], ext, Gp[j]);
+                        const int32_t g0 = add_fma(__vimax3_s32_relu(e0, F0, d0), goe, one);
+                        gdiag0 = Gp[j];
+                        const int32_t d1 = add_fma(gdiag1, prmt_s(t1lo, t1hi, (uint32_t)acol[j]), one);
+                        e1 = __viaddmax_s32(e1, ext, gleft1);
+                        const int32_t F1 = __viaddmax_s32(F0, ext, g0);
+                        const int32_t g1 = add_fma(__vimax3_s32_relu(e1, F1, d1), goe, one);
+                        gdiag1 = g0;
+                        gleft0 = g0; gleft1 = g1;
+                        Gp[j] = g1; F[j] = F1;
+                        bestg = __vimax3_s32(bestg, g0, g1);
+                    }
+                }
+                g_out0 = gleft0; e_out0 = e0; g_out1 = gleft1; e_out1 = e1;
+                if (lane == 31) {
+                    stage[wib][2 * u] = make_int2(g_out0, e_out0);
+                    stage[wib][2 * u + 1] = make_int2(g_out1, e_out1);
+                }
+            }
+            // inputs of the next block
+            {
+                const int ra = 2 * (s0 + 32) + lane, rb_ = ra + 32;
+                row_table(ra, la_lo, la_hi);
+                row_table(rb_, lb_lo, lb_hi);
+                nxa = fresh; nxb = fresh;
+                if (!left_edge) {
+                    if (ra < lb) nxa = ld_entry(g.bnd + ra, in_remote);
+                    if (rb_ < lb) nxb = ld_entry(g.bnd + rb_, in_remote);
+                }
+            }
+            // hand on the rows lane 31 finished in this block: rows 2(s0-31) .. 2(s0-31) + 2*send - 1
+            if (out_bnd != nullptr) {
+                __syncwarp();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int q = lane + 32 * h;
+                    const int r = 2 * (s0 - 31) + q;
+                    if (q < 2 * send && r >= 0 && r < lb) {
+                        const int2 ge = stage[wib][q];
+                        st_entry(out_bnd + r, make_int4(ge.x, gst, ge.y, gst), out_remote);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) bestg = max(bestg, __shfl_xor_sync(0xffffffffu, bestg, m));
+    const int32_t best = bestg - goe;
+    if (lane == 0 && best > 0) atomicMax(g.best, best);
+}
+
+template <int K, bool SHORT> int long_launch2(const LongArgs &args, int n_stripes, cudaStream_t st)
+{
+    int dev = 0, sms = 0, per_sm = 0;
+    AGX_CUDA(cudaGetDevice(&dev));
+    AGX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    AGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_long2_kernel<K, SHORT>, LONG_WARPS * 32, 0));
+    if (per_sm < 1) return fail(AGX_ECUDA, "sw_long: kernel does not fit on an SM");
+    int blocks = sms * per_sm;
+    const int want = (n_stripes + LONG_WARPS - 1) / LONG_WARPS;
+    if (blocks > want) blocks = want;
+    LongArgs a = args;
+    void *params[] = {&a};
+    AGX_CUDA(cudaLaunchCooperativeKernel((const void *)sw_long2_kernel<K, SHORT>, dim3(blocks), dim3(LONG_WARPS * 32),
+                                         params, 0, st));
+    count_launch();
+    return AGX_OK;
+}
+
 template <int K, bool SHORT, bool CODED> int long_launch(const LongArgs &args, int n_stripes, cudaStream_t st)
 {
     int dev = 0, sms = 0, per_sm = 0;
@@ -374,13 +584,16 @@ int pick_k(int64_t cols_per_gpu, int64_t rows, int sms, bool coded)
     return best_k;
 }
 
-template <int I = 0> int long_dispatch_coded(int k, bool short_chain, const LongArgs &args, int n, cudaStream_t st)
+template <int I = 0> int long_dispatch_coded(int k, bool short_chain, bool two_rows, const LongArgs &args, int n, cudaStream_t st)
 {
     if constexpr (I < (int)(sizeof(LONG_KS) / sizeof(LONG_KS[0]))) {
-        if (LONG_KS[I] == k)
+        if (LONG_KS[I] == k) {
+            if (two_rows)
+                return short_chain ? long_launch2<LONG_KS[I], true>(args, n, st) : long_launch2<LONG_KS[I], false>(args, n, st);
             return short_chain ? long_launch<LONG_KS[I], true, true>(args, n, st)
                                : long_launch<LONG_KS[I], false, true>(args, n, st);
-        return long_dispatch_coded<I + 1>(k, short_chain, args, n, st);
+        }
+        return long_dispatch_coded<I + 1>(k, short_chain, two_rows, args, n, st);
     } else {
         return fail(AGX_EINVAL, "sw_long: stripe width not instantiated");
     }
@@ -406,7 +619,10 @@ int long_dispatch(int k, const LongArgs &args, cudaStream_t st)
     // one warp per scheduler: latency-bound, take the short E chain; more: issue-bound, take the lean one
     bool short_chain = n <= sms * 4;
     if (const char *e = getenv("AGX_LONG_CHAIN")) short_chain = atoi(e) != 0;
-    return args.lut ? long_dispatch_coded<0>(k, short_chain, args, n, st) : long_dispatch_raw<0>(k, short_chain, args, n, st);
+    // one warp per scheduler: two rows per step (see sw_long2_kernel)
+    bool two_rows = n <= sms * 4;
+    if (const char *e = getenv("AGX_LONG_ROWS")) two_rows = atoi(e) == 2;
+    return args.lut ? long_dispatch_coded<0>(k, short_chain, two_rows, args, n, st) : long_dispatch_raw<0>(k, short_chain, args, n, st);
 }
 
 // byte -> symbol code for sequences with at most 7 distinct bytes (code 7 is the "matches nothing" padding);

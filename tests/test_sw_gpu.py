@@ -212,11 +212,26 @@ def test_long_alignment_alphabets(agx, gpu_lib, oracle_mod, alphabet, k, monkeyp
     assert got.tolist() == oracle_mod.sw_scores_flat(buf, off, ln).tolist()
 
 
+@pytest.mark.parametrize("k,chain,n", [(2, 1, 16500), (7, 1, 16411), (7, 0, 17003), (8, 1, 21001), (27, 0, 16999), (32, 1, 18000)])
+def test_long_alignment_two_rows_per_step(agx, gpu_lib, oracle_mod, k, chain, n, monkeypatch):
+    """sw_long2_kernel (two rows per step, 64-row hand-off blocks): odd and even row counts, both chain forms."""
+    monkeypatch.setenv("AGX_LONG_ROWS", "2")
+    monkeypatch.setenv("AGX_LONG_K", str(k))
+    monkeypatch.setenv("AGX_LONG_CHAIN", str(chain))
+    inp = _long_pair(agx, n, seed=n + k, related=bool(chain))
+    got = gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len)
+    assert got.tolist() == oracle_mod.sw_scores_flat(inp.buf, inp.off, inp.len).tolist()
+
+
 def test_long_alignment_raw_and_coded_kernels_agree(agx, gpu_lib, monkeypatch):
     inp = _long_pair(agx, 60000, seed=3, related=True)
     coded = gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len)
     monkeypatch.setenv("AGX_LONG_RAW", "1")
     assert gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len).tolist() == coded.tolist()
+    monkeypatch.delenv("AGX_LONG_RAW")
+    for rows in ("1", "2"):
+        monkeypatch.setenv("AGX_LONG_ROWS", rows)
+        assert gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len).tolist() == coded.tolist()
 
 
 def test_long_alignment_device_entry_point_and_mixed_batch(agx, gpu_lib, oracle_mod):
