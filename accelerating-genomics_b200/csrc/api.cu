@@ -910,26 +910,39 @@ int sw_score_batch(const uint8_t *const *a, const int32_t *a_len, const uint8_t 
     if (n_pairs < 0) return fail(AGX_EINVAL, "sw: n_pairs < 0");
     if (n_pairs == 0) return AGX_OK;
     if (!a || !a_len || !b || !b_len || !scores_out) return fail(AGX_EINVAL, "sw: null argument");
-    // gather the pointer arrays into one flat image (a0 b0 a1 b1 ...)
+    // gather the pointer arrays into one flat image (a0 b0 a1 b1 ...) in pinned memory, several host threads
+    int rc = require_init();
+    if (rc != AGX_OK) return rc;
+    std::vector<int64_t> off((size_t)n_pairs * 2);
+    std::vector<int32_t> len((size_t)n_pairs * 2);
     int64_t total = 0;
     for (int64_t p = 0; p < n_pairs; ++p) {
         if (a_len[p] < 0 || b_len[p] < 0 || (a_len[p] && !a[p]) || (b_len[p] && !b[p]))
             return fail(AGX_EINVAL, "sw: bad sequence " + std::to_string(p));
-        total += (int64_t)a_len[p] + b_len[p];
+        off[2 * p] = total; len[2 * p] = a_len[p];
+        total += a_len[p];
+        off[2 * p + 1] = total; len[2 * p + 1] = b_len[p];
+        total += b_len[p];
     }
-    std::vector<uint8_t> flat((size_t)total + 1);
-    std::vector<int64_t> off((size_t)n_pairs * 2);
-    std::vector<int32_t> len((size_t)n_pairs * 2);
-    int64_t w = 0;
-    for (int64_t p = 0; p < n_pairs; ++p) {
-        off[2 * p] = w; len[2 * p] = a_len[p];
-        if (a_len[p]) memcpy(flat.data() + w, a[p], (size_t)a_len[p]);
-        w += a_len[p];
-        off[2 * p + 1] = w; len[2 * p + 1] = b_len[p];
-        if (b_len[p]) memcpy(flat.data() + w, b[p], (size_t)b_len[p]);
-        w += b_len[p];
+    DeviceCtx &c0 = *g_ctx[0];
+    AGX_CUDA(cudaSetDevice(c0.device));
+    if ((rc = c0.h_a.reserve((size_t)total + 1)) != AGX_OK) return rc;
+    uint8_t *flat = c0.h_a.as<uint8_t>();
+    auto gather = [&](int64_t p0, int64_t p1) {
+        for (int64_t p = p0; p < p1; ++p) {
+            if (a_len[p]) memcpy(flat + off[2 * p], a[p], (size_t)a_len[p]);
+            if (b_len[p]) memcpy(flat + off[2 * p + 1], b[p], (size_t)b_len[p]);
+        }
+    };
+    int n_thr = (int)std::min<int64_t>(std::max(1u, std::min(16u, std::thread::hardware_concurrency())), total / (4 << 20) + 1);
+    if (n_thr <= 1) {
+        gather(0, n_pairs);
+    } else {
+        std::vector<std::thread> th;
+        for (int k = 0; k < n_thr; ++k) th.emplace_back(gather, n_pairs * k / n_thr, n_pairs * (k + 1) / n_thr);
+        for (auto &t : th) t.join();
     }
-    return sw_flat_impl(flat.data(), total, off.data(), len.data(), n_pairs,
+    return sw_flat_impl(flat, total, off.data(), len.data(), n_pairs,
                         SwScoring{match, mismatch, gap_open, gap_extend}, scores_out);
 }
 
