@@ -922,7 +922,7 @@ int hmm_run_device(HmmWorkspace &ws, const HmmBatchView &v, int64_t buf_bytes, c
     // read pairing / row classes: on prep_st (high priority) when given, so that it is not queued behind the
     // stream kernels of another batch; the caller then guarantees ws is not in use by earlier work on st
     cudaStream_t cst = prep_st ? prep_st : st;
-    static const bool no_duo = getenv("AGX_PAIRHMM_NO_DUO") != nullptr;   // A/B switch: one read per warp only
+    const bool no_duo = getenv("AGX_PAIRHMM_NO_DUO") != nullptr;          // A/B switch: one read per warp only
     const int64_t nmax = v.n_reads > v.n_haps ? v.n_reads : v.n_haps;
     int2 *pairs = reinterpret_cast<int2 *>(ws.pairs);
     bool paired = !force_fp64 && !no_duo;

@@ -80,6 +80,12 @@ class ClockSampler:
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            # the first queries of a process are slow (tens of ms): take them now, not inside a 20 ms timed region
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            try:
+                pynvml.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
         except Exception:
             self.nv = None
 
@@ -300,11 +306,12 @@ def bench_sw(agx, args, rank, local_rank, world, device):
 
     for _ in range(args.warmup):
         step_resident()
+    sampler = ClockSampler(local_rank)
     barrier(world)
     cap.reset_launch_count()
     kern_ms, cls_ms = [], []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
+    with sampler as clk:
         ev0.record()
         for _ in range(args.steps):
             step_resident()
@@ -398,11 +405,12 @@ def bench_hmm(agx, args, rank, local_rank, world, device):
 
     for _ in range(args.warmup):
         step_resident()
+    sampler = ClockSampler(local_rank)
     barrier(world)
     cap.reset_launch_count()
     kern_ms = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
+    with sampler as clk:
         ev0.record()
         for _ in range(args.steps):
             step_resident()

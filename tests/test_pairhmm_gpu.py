@@ -234,3 +234,38 @@ def test_file_image_streaming_segments(agx, gpu_lib, segment, monkeypatch):
     vals, batch_pairs, incomplete = gpu_lib.pairhmm_forward_file_image(cut)
     assert incomplete == 1 and batch_pairs.tolist() == [42] * 11
     assert np.array_equal(vals, want[: 11 * 42])
+
+
+def test_config4_shape_properties(agx, gpu_lib, oracle_mod, monkeypatch):
+    """BASELINE config 4 shape (200 reads x 5 haplotypes per batch, reads 100-250, haplotypes 200-500),
+    100 000 pairs: size-independent properties + oracle sample."""
+    inp = agx.synth.pairhmm_batches(100, 200, 5, seed=21, unrelated_frac=0.001)
+    got = _run_flat(gpu_lib, inp)
+    assert got.shape == (100_000,) and np.all(np.isfinite(got))
+    # two reads per warp (packed f32x2) and one read per warp give bit-identical values
+    monkeypatch.setenv("AGX_PAIRHMM_NO_DUO", "1")
+    assert np.array_equal(_run_flat(gpu_lib, inp), got)
+    monkeypatch.delenv("AGX_PAIRHMM_NO_DUO")
+    # the FP64 kernel (reference operation order) agrees within the stated tolerance everywhere
+    gpu_lib.set_pairhmm_force_fp64(True)
+    try:
+        f64 = _run_flat(gpu_lib, inp)
+    finally:
+        gpu_lib.set_pairhmm_force_fp64(False)
+    assert _rel_err(got, f64) <= REL_TOL
+    # order independence: reversing the reads of every batch (other partners in the two-read kernel) permutes the output
+    rs = inp.batch_read_start
+    perm = np.concatenate([np.arange(rs[b], rs[b + 1])[::-1] for b in range(inp.n_batches)])
+    rev = _run_flat(gpu_lib, type(inp)(inp.buf, inp.read_field_off[perm], inp.read_len[perm], inp.hap_off, inp.hap_len,
+                                        inp.batch_read_start, inp.batch_hap_start))
+    nh = 5
+    assert np.array_equal(rev.reshape(-1, nh), got.reshape(-1, nh)[perm])
+    # a read listed twice scores the same in both slots
+    dup = np.repeat(np.arange(200), 2)[:200]
+    one = type(inp)(inp.buf, inp.read_field_off[dup], inp.read_len[dup], inp.hap_off[:5], inp.hap_len[:5],
+                    np.array([0, 200], np.int64), np.array([0, 5], np.int64))
+    d = _run_flat(gpu_lib, one).reshape(200, nh)
+    assert np.array_equal(d[0::2], d[1::2])
+    # oracle on a sample
+    want = oracle_mod.pairhmm_flat(inp, limit=400)
+    assert _rel_err(got[:400], want) <= REL_TOL
