@@ -20,8 +20,10 @@
 //   sw_wave_kernel       INTRA-TASK kernel for everything else (long sequences, non-ACGT bytes,
 //                        scores that could overflow s16): one warp per pair, s32 DPX, 32 lanes x 8
 //                        columns per stripe, stripes chained through a boundary column in global
-//                        memory.  It compares raw bytes, so '\n', 'N', lower case ... behave exactly
-//                        as in the reference (:332).
+//                        memory.  A symbol-coded pass (A C G T N and newline: PRMT substitution score,
+//                        additions on the FMA pipe) runs first; a pair with any other byte is redone by
+//                        the raw-byte pass, so '\n', 'N', lower case ... behave exactly as in the
+//                        reference (:332).
 #include <cstdlib>
 #include <vector>
 
@@ -304,22 +306,158 @@ constexpr int WAVE_W = 32 * WAVE_K;       // stripe width
 constexpr int WAVE_WARPS = 4;             // warps per CTA
 constexpr int WAVE_RING = 64;
 
+// prmt.b32 with a sign-extending selector, as a signed value
+__device__ __forceinline__ int32_t prmt_s(uint32_t a, uint32_t b, uint32_t sel) { return (int32_t)prmt(a, b, sel); }
+// a + b as IMAD (FMA pipe): the ALU pipe is what these kernels run out of; `one` is 1, opaque to ptxas
+__device__ __forceinline__ int32_t add_fma(int32_t a, int32_t b, int32_t one)
+{
+    int32_t d;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
+    return d;
+}
+// the CODED pass knows A C G T N '\n' (codes 0..5); code 7 is the "matches nothing" padding
+__device__ __forceinline__ uint32_t wave_code(uint32_t ch, bool &ok)
+{
+    const uint32_t c2 = (ch >> 1) & 3u;
+    if (((0x47544341u >> (8 * c2)) & 0xffu) == ch) return c2;
+    if (ch == 'N') return 4u;
+    if (ch == '\n') return 5u;
+    ok = false;
+    return 6u;
+}
+
+// One pair on one warp.  CODED: substitution score = one sign-extending PRMT from an 8-byte per-row table,
+// additions on the FMA pipe (4.5 instead of 7.5 ALU-pipe instructions per cell, as in sw_long.cu); it gives
+// up (returns false) when it meets a byte outside its alphabet and the raw-byte pass redoes the pair.
+template <bool CODED>
+__device__ bool wave_pair(const uint8_t *a, int32_t la, const uint8_t *b, int32_t lb, SwScoring sc, int32_t one,
+                          int32_t *bnd, int32_t (*r_byte)[WAVE_RING], int32_t (*r_hi)[WAVE_RING],
+                          int32_t (*r_g)[WAVE_RING], int32_t (*r_e)[WAVE_RING], int2 (*stage)[32], int32_t &best_out)
+{
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int32_t goe = sc.gap_open + sc.gap_extend;
+    const int32_t ext = sc.gap_extend;
+    const int32_t sub_match = sc.match - goe, sub_mis = sc.mismatch - goe;
+    const uint32_t xb4 = (uint32_t)(uint8_t)(int8_t)sub_mis * 0x01010101u;
+    const uint32_t mxor = (uint32_t)(uint8_t)(int8_t)sub_mis ^ (uint32_t)(uint8_t)(int8_t)sub_match;
+    bool ok = true;
+    int32_t bestg = goe;
+    const int n_stripes = (la + WAVE_W - 1) / WAVE_W;
+    for (int st = 0; st < n_stripes; ++st) {
+        const int c0 = st * WAVE_W + lane * WAVE_K;
+        int32_t acol[WAVE_K], Gp[WAVE_K], F[WAVE_K];
+#pragma unroll
+        for (int j = 0; j < WAVE_K; ++j) {
+            if constexpr (CODED) {
+                const uint32_t c = (c0 + j < la) ? wave_code(a[c0 + j], ok) : 7u;
+                acol[j] = (int32_t)(c | ((8u | c) * 0x1110u));
+            } else {
+                acol[j] = (c0 + j < la) ? (int32_t)a[c0 + j] : 0x100;   // 0x100 never equals a byte
+            }
+            Gp[j] = goe;
+            F[j] = goe;
+        }
+        int32_t g_out = goe, e_out = goe, g_in_prev = goe;
+        const bool first = (st == 0), last = (st == n_stripes - 1);
+        const int S = lb + 31;
+        // boundary of the previous stripe for the first 32 rows; later blocks are requested a block ahead
+        int2 nx = make_int2(goe, goe);
+        if (!first && lane < lb) nx = __ldcg(reinterpret_cast<const int2 *>(bnd) + lane);
+        for (int s0 = 0; s0 < S; s0 += 32) {
+            __syncwarp();
+            {
+                const int r = s0 + lane;
+                int32_t bb = CODED ? (int32_t)xb4 : 0x200;
+                uint32_t hi = xb4;
+                if (r < lb) {
+                    if constexpr (CODED) {
+                        const uint32_t c = wave_code(b[r], ok);
+                        uint32_t lo = xb4;
+                        if (c < 4) lo ^= mxor << (8 * c); else hi ^= mxor << (8 * (c - 4));
+                        bb = (int32_t)lo;
+                    } else {
+                        bb = b[r];
+                    }
+                }
+                r_byte[wib][r & (WAVE_RING - 1)] = bb;
+                if constexpr (CODED) r_hi[wib][r & (WAVE_RING - 1)] = (int32_t)hi;
+                r_g[wib][r & (WAVE_RING - 1)] = nx.x;
+                r_e[wib][r & (WAVE_RING - 1)] = nx.y;
+                // the rows this stripe overwrites in this block are s0-31 .. s0: rows s0+32.. are still the
+                // previous stripe's, so the next block's boundary can be requested now
+                const int rn = s0 + 32 + lane;
+                nx = make_int2(goe, goe);
+                if (!first && rn < lb) nx = __ldcg(reinterpret_cast<const int2 *>(bnd) + rn);
+            }
+            __syncwarp();
+            const int send = min(32, S - s0);
+#pragma unroll 1
+            for (int u = 0; u < send; ++u) {
+                const int s = s0 + u;
+                const int slot = (s - lane) & (WAVE_RING - 1);
+                const int32_t rb = (s - lane >= 0) ? r_byte[wib][slot] : (CODED ? (int32_t)xb4 : 0x200);
+                uint32_t rhi = xb4;
+                if constexpr (CODED) { if (s - lane >= 0) rhi = (uint32_t)r_hi[wib][slot]; }
+                int32_t g_in = __shfl_up_sync(0xffffffffu, g_out, 1);
+                int32_t e = __shfl_up_sync(0xffffffffu, e_out, 1);
+                if (lane == 0) { g_in = r_g[wib][slot]; e = r_e[wib][slot]; }
+                int32_t gdiag = g_in_prev;
+                g_in_prev = g_in;
+                int32_t gleft = g_in;
+#pragma unroll
+                for (int j = 0; j < WAVE_K; ++j) {
+                    int32_t d;
+                    if constexpr (CODED) d = add_fma(gdiag, prmt_s((uint32_t)rb, rhi, (uint32_t)acol[j]), one);
+                    else d = gdiag + ((acol[j] == rb) ? sub_match : sub_mis);
+                    e = __viaddmax_s32(e, ext, gleft);
+                    F[j] = __viaddmax_s32(F[j], ext, Gp[j]);
+                    const int32_t hcell = __vimax3_s32_relu(e, F[j], d);
+                    gdiag = Gp[j];
+                    if constexpr (CODED) gleft = add_fma(hcell, goe, one); else gleft = hcell + goe;
+                    Gp[j] = gleft;
+                    if (j & 1) bestg = __vimax3_s32(bestg, Gp[j - 1], gleft);
+                    else if (j == WAVE_K - 1) bestg = max(bestg, gleft);
+                }
+                g_out = gleft;
+                e_out = e;
+                if (lane == 31) stage[wib][u] = make_int2(g_out, e_out);     // row s - 31 of the last column
+            }
+            // one coalesced store per block instead of a global store per row step
+            if (!last) {
+                __syncwarp();
+                const int r = s0 - 31 + lane;
+                if (lane < send && r >= 0 && r < lb) reinterpret_cast<int2 *>(bnd)[r] = stage[wib][lane];
+            }
+        }
+        __syncwarp();
+        __threadfence_block();
+        if constexpr (CODED) {
+            if (!__all_sync(0xffffffffu, ok)) return false;     // a byte outside the coded alphabet: redo raw
+        }
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) bestg = max(bestg, __shfl_xor_sync(0xffffffffu, bestg, m));
+    best_out = max(bestg - goe, 0);
+    return true;
+}
+
 __global__ void __launch_bounds__(WAVE_WARPS * 32)
 sw_wave_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
                const int32_t *__restrict__ len, const int32_t *__restrict__ list,
-               const int32_t *__restrict__ list_count, SwScoring sc, int32_t *__restrict__ scores,
-               int32_t *__restrict__ scratch, int64_t scratch_stride)
+               const int32_t *__restrict__ list_count, SwScoring sc, int32_t one, int32_t coded_ok,
+               int32_t *__restrict__ scores, int32_t *__restrict__ scratch, int64_t scratch_stride)
 {
     __shared__ int32_t r_byte[WAVE_WARPS][WAVE_RING];
+    __shared__ int32_t r_hi[WAVE_WARPS][WAVE_RING];
     __shared__ int32_t r_g[WAVE_WARPS][WAVE_RING];
     __shared__ int32_t r_e[WAVE_WARPS][WAVE_RING];
+    __shared__ int2 stage[WAVE_WARPS][32];
 
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int64_t warp = (int64_t)blockIdx.x * WAVE_WARPS + wib;
     const int64_t n_warps = (int64_t)gridDim.x * WAVE_WARPS;
-    const int32_t goe = sc.gap_open + sc.gap_extend;
-    const int32_t ext = sc.gap_extend;
     int32_t *bnd = scratch + warp * scratch_stride;   // [2 * rows] : (G, E) of the stripe's last column
     const int32_t count = *list_count;
 
@@ -334,70 +472,9 @@ sw_wave_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off
         if (lx > ly) { a = y; la = ly; b = x; lb = lx; }
 
         int32_t best = 0;
-        const int n_stripes = (la + WAVE_W - 1) / WAVE_W;
-        for (int st = 0; st < n_stripes; ++st) {
-            const int c0 = st * WAVE_W + lane * WAVE_K;
-            int32_t acol[WAVE_K], Gp[WAVE_K], F[WAVE_K];
-#pragma unroll
-            for (int j = 0; j < WAVE_K; ++j) {
-                acol[j] = (c0 + j < la) ? (int32_t)a[c0 + j] : 0x100;   // 0x100 never equals a byte
-                Gp[j] = goe;
-                F[j] = goe;
-            }
-            int32_t g_out = goe, e_out = goe, g_in_prev = goe;
-            const bool first = (st == 0), last = (st == n_stripes - 1);
-            const int S = lb + 31;
-            for (int s0 = 0; s0 < S; s0 += 32) {
-                __syncwarp();
-                {
-                    const int r = s0 + lane;
-                    int32_t bb = 0x200, gi = goe, ei = goe;
-                    if (r < lb) {
-                        bb = b[r];
-                        if (!first) { gi = __ldcg(bnd + 2 * r); ei = __ldcg(bnd + 2 * r + 1); }
-                    }
-                    r_byte[wib][r & (WAVE_RING - 1)] = bb;
-                    r_g[wib][r & (WAVE_RING - 1)] = gi;
-                    r_e[wib][r & (WAVE_RING - 1)] = ei;
-                }
-                __syncwarp();
-                const int send = min(32, S - s0);
-#pragma unroll 1
-                for (int u = 0; u < send; ++u) {
-                    const int s = s0 + u;
-                    const int slot = (s - lane) & (WAVE_RING - 1);
-                    const int32_t rb = (s - lane >= 0) ? r_byte[wib][slot] : 0x200;
-                    int32_t g_in = __shfl_up_sync(0xffffffffu, g_out, 1);
-                    int32_t e = __shfl_up_sync(0xffffffffu, e_out, 1);
-                    if (lane == 0) { g_in = r_g[wib][slot]; e = r_e[wib][slot]; }
-                    int32_t gdiag = g_in_prev;
-                    g_in_prev = g_in;
-                    int32_t gleft = g_in;
-#pragma unroll
-                    for (int j = 0; j < WAVE_K; ++j) {
-                        const int32_t d = gdiag + ((acol[j] == rb) ? sc.match - goe : sc.mismatch - goe);
-                        e = __viaddmax_s32(e, ext, gleft);
-                        F[j] = __viaddmax_s32(F[j], ext, Gp[j]);
-                        const int32_t hcell = __vimax3_s32_relu(e, F[j], d);
-                        gdiag = Gp[j];
-                        gleft = hcell + goe;
-                        Gp[j] = gleft;
-                        best = max(best, hcell);
-                    }
-                    g_out = gleft;
-                    e_out = e;
-                    const int r = s - 31;
-                    if (!last && lane == 31 && r >= 0 && r < lb) {
-                        bnd[2 * r] = g_out;
-                        bnd[2 * r + 1] = e_out;
-                    }
-                }
-            }
-            __syncwarp();
-            __threadfence_block();
-        }
-#pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, m));
+        bool done = false;
+        if (coded_ok) done = wave_pair<true>(a, la, b, lb, sc, one, bnd, r_byte, r_hi, r_g, r_e, stage, best);
+        if (!done) wave_pair<false>(a, la, b, lb, sc, one, bnd, r_byte, r_hi, r_g, r_e, stage, best);
         if (lane == 0) scores[p] = best;
     }
 }
@@ -573,9 +650,12 @@ int sw_run_device(SwWorkspace &ws, const uint8_t *d_seqs, const int64_t *d_off, 
             ws.cap_wave = need;
         }
         ws.prof_wave.begin(st);
+        // the coded pass needs the two substitution scores (minus goe) to fit a signed byte
+        const bool coded_ok = (sc.match - goe) <= 127 && (sc.match - goe) >= -128 && (sc.mismatch - goe) <= 127 &&
+                              (sc.mismatch - goe) >= -128 && getenv("AGX_WAVE_RAW") == nullptr;
         sw_wave_kernel<<<blocks, WAVE_WARPS * 32, 0, st>>>(
-            d_seqs, d_off, d_len, ws.order + (int64_t)GENERIC * n_pairs, ws.counters + GENERIC, sc,
-            d_scores, ws.wave_scratch, stride);
+            d_seqs, d_off, d_len, ws.order + (int64_t)GENERIC * n_pairs, ws.counters + GENERIC, sc, 1,
+            coded_ok ? 1 : 0, d_scores, ws.wave_scratch, stride);
         ws.prof_wave.end(st);
         count_launch();
         AGX_CUDA(cudaGetLastError());
