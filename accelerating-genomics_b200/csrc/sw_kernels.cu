@@ -198,7 +198,7 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
     const int S = Lb + G - 1;
 
     // ---- column selectors (columns right-aligned; padding columns select "sign of byte 0") ----
-    bool ok = true;
+    bool okh[2] = {true, true};      // per half: a byte outside ACGT spoils only the pair that holds it
     uint32_t sel[K];
 #pragma unroll
     for (int j = 0; j < K; ++j) {
@@ -208,7 +208,7 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
             const int idx = t * K + j - (CAP - sq[h].la);
             uint32_t nib_lo = 8u + 4u * h, nib_hi = 8u + 4u * h;     // padding: 0x0000 / 0xffff
             if (idx >= 0) {
-                const uint32_t code = base_code(sq[h].a[idx], ok);
+                const uint32_t code = base_code(sq[h].a[idx], okh[h]);
                 nib_lo = code + 4u * h;
                 nib_hi = nib_lo | 8u;                                 // sign-extend that byte
             }
@@ -237,7 +237,7 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
                 const int idx = r - (Lb - sq[h].lb);
                 w[h] = kc.xb4;
                 if (idx >= 0 && r < Lb) {
-                    const uint32_t code = base_code(sq[h].b[idx], ok);
+                    const uint32_t code = base_code(sq[h].b[idx], okh[h]);
                     w[h] = kc.xb4 ^ (kc.mxor << (8 * code));
                 }
             }
@@ -278,15 +278,16 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
 #pragma unroll
     for (int m = G / 2; m >= 1; m >>= 1) rmax = __vmaxs2(rmax, __shfl_xor_sync(0xffffffffu, rmax, m, G));
     const uint32_t corner2 = __shfl_sync(0xffffffffu, Gp[K - 1], G - 1, G);
-    uint32_t okbits = __ballot_sync(0xffffffffu, ok);
     const uint32_t submask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
-    const bool all_ok = (okbits & submask) == submask;
+    const uint32_t okbits0 = __ballot_sync(0xffffffffu, okh[0]), okbits1 = __ballot_sync(0xffffffffu, okh[1]);
+    const bool all_ok[2] = {(okbits0 & submask) == submask, (okbits1 & submask) == submask};
     if (t == 0) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             if (pid[h] < 0) continue;
-            if (!all_ok) {
-                // a byte outside ACGT in either pair of the duo: let the byte-exact kernel redo it
+            if (!all_ok[h]) {
+                // a byte outside ACGT in this pair: let the byte-exact kernel redo it (the other half of
+                // the registers never mixes with this one, so the duo's other pair keeps its score)
                 generic_list[atomicAdd(generic_cursor, 1)] = pid[h];
                 continue;
             }
