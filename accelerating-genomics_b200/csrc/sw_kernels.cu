@@ -191,15 +191,14 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
             sq[h] = load_pair(seqs, off, len, pid[h]);
         }
     }
-    // rows are bottom-aligned to the longest b of the whole warp so the step loop is warp-uniform
-    int32_t Lb = max(sq[0].lb, sq[1].lb);
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) Lb = max(Lb, __shfl_xor_sync(0xffffffffu, Lb, m));
-    const int S = Lb + G - 1;
-
     // ---- column selectors (columns right-aligned; padding columns select "sign of byte 0") ----
-    bool okh[2] = {true, true};      // per half: a byte outside ACGT spoils only the pair that holds it
+    // 'N' (any one extra symbol would do): as a ROW symbol it is the all-mismatch table, which is exact as long
+    // as the column sequence holds no 'N'.  So a pair whose column sequence has an 'N' is swapped (the score is
+    // symmetric) when the other sequence fits the columns and has none; only pairs with an 'N' on both sides,
+    // or with any other byte outside ACGT, go to the byte-exact kernel.
+    bool okh[2] = {true, true};      // per half: such a byte spoils only the pair that holds it
     uint32_t sel[K];
+    const uint32_t submask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
 #pragma unroll
     for (int j = 0; j < K; ++j) {
         uint32_t s = 0;
@@ -216,6 +215,57 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
         }
         sel[j] = s;
     }
+    if (__any_sync(0xffffffffu, !(okh[0] && okh[1]))) {
+        // cold path: some column sequence of this warp holds a byte outside ACGT.  Is it only 'N'?  Then swap
+        // the pair when the other sequence fits the columns; the selectors are rebuilt (twice at most).
+#pragma unroll 1
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            bool saw_n[2] = {false, false};
+            okh[0] = okh[1] = true;
+#pragma unroll 1
+            for (int j = 0; j < K; ++j) {
+                uint32_t s = 0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int idx = t * K + j - (CAP - sq[h].la);
+                    uint32_t nib_lo = 8u + 4u * h, nib_hi = 8u + 4u * h;
+                    if (idx >= 0) {
+                        const uint32_t ch = sq[h].a[idx];
+                        bool valid = true;
+                        const uint32_t code = base_code(ch, valid);
+                        saw_n[h] = saw_n[h] || ch == 'N';
+                        okh[h] = okh[h] && (valid || ch == 'N');
+                        nib_lo = code + 4u * h;
+                        nib_hi = nib_lo | 8u;
+                    }
+                    s |= (nib_lo | (nib_hi << 4)) << (8 * h);
+                }
+                // sel[] is indexed dynamically here (the loop is not unrolled to keep this path small)
+#pragma unroll
+                for (int jj = 0; jj < K; ++jj)
+                    if (jj == j) sel[jj] = s;
+            }
+            bool redo = false;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (__ballot_sync(0xffffffffu, saw_n[h]) & submask) {   // uniform inside the sub-warp
+                    if (attempt == 0 && sq[h].lb <= CAP) {
+                        const uint8_t *tp = sq[h].a; sq[h].a = sq[h].b; sq[h].b = tp;
+                        const int32_t tl = sq[h].la; sq[h].la = sq[h].lb; sq[h].lb = tl;
+                        redo = true;
+                    } else {
+                        okh[h] = false;                              // 'N' on both sides, or the other side does not fit
+                    }
+                }
+            }
+            if (!__any_sync(0xffffffffu, redo)) break;
+        }
+    }
+    // rows are bottom-aligned to the longest b of the whole warp so the step loop is warp-uniform
+    int32_t Lb = max(sq[0].lb, sq[1].lb);
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) Lb = max(Lb, __shfl_xor_sync(0xffffffffu, Lb, m));
+    const int S = Lb + G - 1;
 
     // ---- state ---------------------------------------------------------------------------------
     uint32_t Gp[K], F[K];
@@ -237,8 +287,11 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
                 const int idx = r - (Lb - sq[h].lb);
                 w[h] = kc.xb4;
                 if (idx >= 0 && r < Lb) {
-                    const uint32_t code = base_code(sq[h].b[idx], okh[h]);
-                    w[h] = kc.xb4 ^ (kc.mxor << (8 * code));
+                    const uint32_t ch = sq[h].b[idx];
+                    if (ch != 'N') {                               // 'N': matches no column symbol (none is 'N')
+                        const uint32_t code = base_code(ch, okh[h]);
+                        w[h] = kc.xb4 ^ (kc.mxor << (8 * code));
+                    }
                 }
             }
             ring[sub][r & (DUO_RING - 1)] = make_uint2(w[0], w[1]);
@@ -278,7 +331,6 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
 #pragma unroll
     for (int m = G / 2; m >= 1; m >>= 1) rmax = __vmaxs2(rmax, __shfl_xor_sync(0xffffffffu, rmax, m, G));
     const uint32_t corner2 = __shfl_sync(0xffffffffu, Gp[K - 1], G - 1, G);
-    const uint32_t submask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
     const uint32_t okbits0 = __ballot_sync(0xffffffffu, okh[0]), okbits1 = __ballot_sync(0xffffffffu, okh[1]);
     const bool all_ok[2] = {(okbits0 & submask) == submask, (okbits1 & submask) == submask};
     if (t == 0) {

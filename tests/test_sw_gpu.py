@@ -336,3 +336,31 @@ def test_file_image_pinned_image_and_output(agx, gpu_lib):
     scores, header, dangling = gpu_lib.sw_score_file_image(h_img.numpy(), out=h_out.numpy())
     assert header == 100_000 and dangling == b"" and scores.size == 50_000
     assert np.array_equal(scores, gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len))
+
+
+def test_short_pairs_with_n_stay_bit_exact(gpu_lib, oracle_mod):
+    """'N' in the shorter / the longer / both sequences, at the ends, unequal lengths around the class
+    capacities: the s16x2 kernel swaps roles or hands the pair to the byte-exact kernel; either way raw-byte
+    semantics (N == N is a match, N vs ACGT a mismatch) hold."""
+    rng = np.random.default_rng(42)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    seqs = []
+    for k in range(600):
+        la = int(rng.integers(1, 320))
+        lb = int(rng.integers(1, 320)) if k % 3 else la
+        a = acgt[rng.integers(0, 4, size=la)].copy()
+        b = a.copy()[:lb] if (k % 4 == 0 and lb <= la) else acgt[rng.integers(0, 4, size=lb)].copy()
+        mode = k % 5
+        if mode in (0, 2):
+            a[rng.integers(0, la, size=1 + k % 3)] = ord("N")
+        if mode in (1, 2):
+            b[rng.integers(0, b.size, size=1 + k % 2)] = ord("N")
+        if mode == 3:
+            a[-1] = ord("N"); b[0] = ord("N")
+        nl = b"\n" if k % 7 else b""
+        seqs += [a.tobytes() + nl, b.tobytes() + nl]
+    buf = np.frombuffer(b"".join(seqs), np.uint8)
+    ln = np.array([len(x) for x in seqs], np.int32)
+    off = np.concatenate(([0], np.cumsum(ln)[:-1])).astype(np.int64)
+    got = gpu_lib.sw_score_flat(buf, off, ln)
+    assert got.tolist() == oracle_mod.sw_scores_flat(buf, off, ln).tolist()
