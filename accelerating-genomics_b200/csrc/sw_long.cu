@@ -12,9 +12,9 @@
 //     row strictly in order.
 //   - An entry is {H+goe, tag, E, tag} with tag = the (global) index of the stripe that wrote it, stored
 //     with ONE 128-bit store.  The consumer polls the data itself: no flags, no fences, one memory round
-//     trip per hand-off, and the entries of the next 32 rows are requested a whole block ahead, so the
-//     latency of the hand-off is off the critical path whenever the producer is a block ahead.  All warps
-//     are co-resident (cooperative launch), so a poll always ends.
+//     trip per hand-off.  Lane 31 stages the boundary in shared memory and the warp hands 32 rows on with
+//     one coalesced store per block; polling is warp-uniform.  All warps are co-resident (cooperative
+//     launch), so a poll always ends.
 //   - Multi-GPU: GPU g owns a contiguous range of columns.  The last stripe of GPU g writes its entries
 //     straight into GPU g+1's boundary array with peer stores over NVLink (cudaDeviceEnablePeerAccess);
 //     no collective is involved, the final score is the max of the per-GPU maxima.
@@ -62,49 +62,31 @@ __device__ __forceinline__ int32_t add_fma(int32_t a, int32_t b, int32_t one)
     return d;
 }
 
-// A boundary entry may be (re)written by another SM or by a peer GPU while it is polled: relaxed (strong)
-// accesses at the narrowest scope that covers writer and reader -- .gpu inside one GPU, .sys across NVLink.
-// 1: request the next block's entries a block ahead (needs a two-block start-up slack); 0: read them when
-// the block starts.  Measured on B200 (125 kbp x 1 Mbp share of an 8-GPU run): 0 is 5-10 % faster.
-#ifndef AGX_LONG_PREFETCH
-#define AGX_LONG_PREFETCH 0
-#endif
-// row steps unrolled per loop trip (lets ptxas start the chain-independent part of the next row early)
+// row steps unrolled per loop trip (measured: 2 and 4 change the run time by -2 % .. +2 %; 1 keeps the code small)
 #ifndef AGX_LONG_UNROLL
 #define AGX_LONG_UNROLL 1
 #endif
 constexpr int LONG_UNROLL = AGX_LONG_UNROLL;
-#ifndef AGX_LONG_MEMOPS
-#define AGX_LONG_MEMOPS 1
-#endif
+
+// A boundary entry may be (re)written by another SM or by a peer GPU while it is polled: relaxed (strong)
+// accesses at the narrowest scope that covers writer and reader -- .gpu inside one GPU, .sys across NVLink.
+// (ld/st.volatile and plain .cg stores were measured too: no difference.)  Requesting the next block's entries
+// a block ahead was also tried: it needs a two-block start-up slack and came out 5-10 % slower.
 __device__ __forceinline__ int4 ld_entry(const int4 *p, bool sys)
 {
     int4 v;
-#if AGX_LONG_MEMOPS == 0
-    asm volatile("ld.volatile.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-#else
     if (sys)
         asm volatile("ld.relaxed.sys.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     else
         asm volatile("ld.relaxed.gpu.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-#endif
     return v;
 }
 __device__ __forceinline__ void st_entry(int4 *p, int4 v, bool sys)
 {
-#if AGX_LONG_MEMOPS == 0
-    asm volatile("st.volatile.global.v4.s32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-#elif AGX_LONG_MEMOPS == 2
-    if (sys)
-        asm volatile("st.relaxed.sys.global.v4.s32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-    else
-        asm volatile("st.global.cg.v4.s32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
-#else
     if (sys)
         asm volatile("st.relaxed.sys.global.v4.s32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
     else
         asm volatile("st.relaxed.gpu.global.v4.s32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-#endif
 }
 
 // CODED: both sequences use at most 7 distinct bytes.  Columns carry a PRMT selector instead of their byte,
@@ -167,24 +149,6 @@ sw_long_kernel(LongArgs g)
         const bool in_remote = (st == 0);                                // written by the previous GPU
         const int S = lb + 31;
 
-#if AGX_LONG_PREFETCH
-        // Slack: a stripe starts only when the left neighbour has handed on TWO blocks of rows.  From then
-        // on both advance at the same pace, so the entries requested at the top of a block (for the next
-        // block) were written a whole block earlier and their latency hides behind 32 row steps; a stripe
-        // that has to poll has lost its slack and takes a short extra nap to get it back.
-        // (polling is warp-uniform: lanes that diverge inside a sleep loop would sleep one after the other)
-        if (!left_edge) {
-            const bool mine = lane + 32 < lb;
-            int4 probe = make_int4(0, gst - 1, 0, gst - 1);
-            if (mine) probe = ld_entry(g.bnd + 32 + lane, in_remote);
-            unsigned ns = 64;
-            while (__any_sync(0xffffffffu, probe.y != gst - 1 || probe.w != gst - 1)) {
-                __nanosleep(ns);
-                if (ns < 1024) ns *= 2;
-                if (mine) probe = ld_entry(g.bnd + 32 + lane, in_remote);
-            }
-        }
-#endif
         // inputs of the first 32 rows
         int32_t nb = 0x200;
         uint32_t nhi = 0;
@@ -198,20 +162,13 @@ sw_long_kernel(LongArgs g)
             {
                 const int r = s0 + lane;
                 if (!left_edge) {
-                    // normally valid already (requested a block ago, written two blocks ago)
+                    // wait until the left neighbour has handed these 32 rows on
                     unsigned ns = 32;
-                    bool polled = false;
                     while (__any_sync(0xffffffffu, nx.y != gst - 1 || nx.w != gst - 1)) {
                         __nanosleep(ns);
                         if (ns < 512) ns *= 2;
                         if (r < lb && (nx.y != gst - 1 || nx.w != gst - 1)) nx = ld_entry(g.bnd + r, in_remote);
-                        polled = true;
                     }
-#if AGX_LONG_PREFETCH
-                    if (polled) __nanosleep(600);
-#else
-                    (void)polled;
-#endif
                 }
                 r_byte[wib][r & (LONG_RING - 1)] = nb;
                 if constexpr (CODED) r_hi[wib][r & (LONG_RING - 1)] = (int32_t)nhi;
@@ -219,23 +176,6 @@ sw_long_kernel(LongArgs g)
                 r_e[wib][r & (LONG_RING - 1)] = nx.z;
             }
             __syncwarp();
-#if AGX_LONG_PREFETCH
-            {
-                // request the next block's inputs now; they are checked when that block starts
-                const int r = s0 + 32 + lane;
-                nb = 0x200;
-                nx = make_int4(goe, gst - 1, goe, gst - 1);
-                if constexpr (CODED) { uint32_t lo; row_table(r, lo, nhi); nb = (int32_t)lo; }
-                if (r < lb) {
-                    if constexpr (!CODED) nb = g.b[r];
-#if AGX_LONG_PREFETCH == 2
-                    if (!left_edge) nx = __ldcg(g.bnd + r);
-#else
-                    if (!left_edge) nx = ld_entry(g.bnd + r, in_remote);
-#endif
-                }
-            }
-#endif
             const int send = min(32, S - s0);
 #pragma unroll LONG_UNROLL
             for (int u = 0; u < send; ++u) {
@@ -294,8 +234,8 @@ sw_long_kernel(LongArgs g)
                 // lane 31 has just finished row s - 31 of the stripe's last column: stage it for the flush
                 if (lane == 31) stage[wib][u] = make_int2(g_out, e_out);
             }
-#if !AGX_LONG_PREFETCH
             {
+                // inputs of the next block
                 const int r = s0 + 32 + lane;
                 nb = 0x200;
                 nx = make_int4(goe, gst - 1, goe, gst - 1);
@@ -305,7 +245,6 @@ sw_long_kernel(LongArgs g)
                     if (!left_edge) nx = ld_entry(g.bnd + r, in_remote);
                 }
             }
-#endif
             // hand the rows completed in this block (s0 - 31 .. s0) on with one 128-bit store per lane
             if (out_bnd != nullptr) {
                 __syncwarp();
