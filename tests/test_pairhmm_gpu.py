@@ -269,3 +269,27 @@ def test_config4_shape_properties(agx, gpu_lib, oracle_mod, monkeypatch):
     # oracle on a sample
     want = oracle_mod.pairhmm_flat(inp, limit=400)
     assert _rel_err(got[:400], want) <= REL_TOL
+
+
+def test_device_entry_point_with_reads_in_any_order(agx, gpu_lib):
+    """d_read_batch need not be sorted: the read pairing then steps aside (one read per warp) and the values,
+    written through d_read_out_off, do not change."""
+    import torch
+    inp = agx.synth.pairhmm_batches(8, 30, 4, seed=31)
+    want = _run_flat(gpu_lib, inp)
+    dev = torch.device("cuda:0")
+    nb = inp.n_batches
+    nh_b = np.diff(inp.batch_hap_start)
+    read_batch = np.repeat(np.arange(nb, dtype=np.int32), np.diff(inp.batch_read_start))
+    out_off = np.concatenate(([0], np.cumsum(nh_b[read_batch])))[:-1].astype(np.int64)
+    perm = np.random.default_rng(1).permutation(read_batch.size)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_buf, d_rfo, d_rl = t(inp.buf.copy()), t(inp.read_field_off[perm].reshape(-1)), t(inp.read_len[perm])
+    d_rb, d_roo, d_ho, d_hl, d_bhs = t(read_batch[perm]), t(out_off[perm]), t(inp.hap_off), t(inp.hap_len), t(inp.batch_hap_start)
+    d_out = torch.zeros(inp.n_pairs, dtype=torch.float64, device=dev)
+    gpu_lib.pairhmm_forward_device(0, d_buf.data_ptr(), d_buf.numel(), d_rfo.data_ptr(), d_rl.data_ptr(),
+                                   d_rb.data_ptr(), d_roo.data_ptr(), inp.read_len.size, d_ho.data_ptr(),
+                                   d_hl.data_ptr(), inp.hap_len.size, d_bhs.data_ptr(), nb, inp.n_pairs,
+                                   d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), want)
