@@ -154,7 +154,7 @@ struct HmmParseWorkspace {
 };
 struct HmmParsed {            // device pointers into the workspace
     int64_t n_batches = 0, n_reads = 0, n_haps = 0, n_out = 0;
-    int32_t incomplete = 0;   // 1: EOF inside the reads of a last batch, 2: inside its haplotypes (batch dropped)
+    int32_t incomplete = 0;   // the file ends inside a last batch (dropped): 2 = "Error reading haplotypes.", 1 = "... reads."
     int64_t next_begin = 0;   // where parsing resumes: the dropped batch's header, else the end of the region
     int64_t *read_field_off = nullptr, *read_out_off = nullptr, *hap_off = nullptr;
     int32_t *read_len = nullptr, *read_batch = nullptr, *hap_len = nullptr, *batch_pairs = nullptr;

@@ -27,7 +27,9 @@ constexpr int HMM_LINE_MAX = 5000;   // fgets(line, MAX_READ_LEN*5+1 = 5001): lo
 enum {
     PI_HEADERS = 0,      // number of header lines found (scan total)
     PI_IRREGULAR = 1,    // the header chain does not tile the file: fall back to the serial walk
-    PI_INCOMPLETE = 2,   // 1: EOF inside the reads of the last batch, 2: inside its haplotypes
+    PI_INCOMPLETE = 2,   // the file ends inside the last batch; 2: the reference says "Error reading haplotypes."
+                         // (its haplotype cursor runs ahead of the read cursor, :388-396), 1: "Error reading reads."
+                         // (only possible for a batch without haplotypes, :411-414)
     PI_BATCHES = 3,      // complete batches
     PI_READS = 4,
     PI_HAPS = 5,
@@ -120,7 +122,7 @@ hmm_check_chain_kernel(const int32_t *__restrict__ hdr_line, const int32_t *__re
     if (b + 1 < H) {
         if (next != hdr_line[b + 1]) info[PI_IRREGULAR] = 1;
     } else if (next > n_lines) {
-        info[PI_INCOMPLETE] = ((int64_t)hdr_line[b] + 1 + nr[b] > n_lines) ? 1 : 2;
+        info[PI_INCOMPLETE] = nh[b] > 0 ? 2 : 1;
     } else if (next < n_lines) {
         info[PI_IRREGULAR] = 1;      // lines after the last batch that do not look like a header
     }
@@ -139,8 +141,7 @@ __global__ void hmm_walk_kernel(const uint8_t *__restrict__ img, const int64_t *
         if (a < 0) a = 0;
         if (c < 0) c = 0;
         flag[line] = 1;
-        if (line + 1 + a > n_lines) { info[PI_INCOMPLETE] = 1; break; }
-        if (line + 1 + a + c > n_lines) { info[PI_INCOMPLETE] = 2; break; }
+        if (line + 1 + a + c > n_lines) { info[PI_INCOMPLETE] = c > 0 ? 2 : 1; break; }
         line += 1 + (int64_t)a + c;
     }
 }

@@ -81,7 +81,11 @@ static int split_on_host(const unsigned char *img, size_t size, double **lh_out,
         sscanf(head, "%d %d", &num_read, &num_haplotypes);
         size_t r_mark = rl.n, h_mark = hl.n;
         for (int i = 0; i < num_read && !err; i++) {
-            if (!next_line(img, size, &pos, &start, &l)) { err = "Error reading reads.\n"; break; }
+            /* the reference's haplotype cursor runs ahead (:388-396): it is the one that meets EOF first */
+            if (!next_line(img, size, &pos, &start, &l)) {
+                err = num_haplotypes > 0 ? "Error reading haplotypes.\n" : "Error reading reads.\n";
+                break;
+            }
             int len_read = ((int)l - 4) / 5;
             if (len_read < 0) len_read = 0;
             /* the five whitespace-separated fields, as sscanf("%s %s %s %s %s") finds them */

@@ -168,9 +168,11 @@ int pairhmm_forward_batches_flat(const uint8_t *buf, int64_t buf_bytes,
  * *log10_out points at *n_out values, batches in file order, read-major inside a batch (the reference's
  * output order :459-461), and *batch_pairs at *n_batches counts (reads x haplotypes of each batch: what a
  * driver needs to print "#batch: %d" between them).  Both arrays live in pinned host memory OWNED BY THE
- * LIBRARY and stay valid until the next PairHMM call or agx_shutdown().  *incomplete = 1 / 2 when the
- * file ends inside the reads / haplotypes of a last batch: that batch is dropped; the reference prints
- * "Error reading reads." / "Error reading haplotypes." after the earlier ones (:405, :431).
+ * LIBRARY and stay valid until the next PairHMM call or agx_shutdown().  *incomplete != 0 when the file
+ * ends inside a last batch: that batch is dropped and the reference's message is "Error reading
+ * haplotypes." (*incomplete = 2: its haplotype cursor runs ahead of its read cursor, :388-396, so this is
+ * what it prints whenever the batch has haplotypes) or "Error reading reads." (*incomplete = 1: a batch
+ * without haplotypes, :411-414).
  * AGX_ERANGE when a line exceeds the reference's 5000-byte line buffer (:353) or a read length falls
  * outside [1, 8192].  Runs on the first configured GPU. */
 int pairhmm_forward_file_image(const uint8_t *image, int64_t image_bytes, const double **log10_out,

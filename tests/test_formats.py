@@ -104,3 +104,48 @@ def test_seeded_generator_keeps_the_reference_format(agx, oracle_mod, tmp_path):
     subprocess.run([sys.executable, str(gen), "64", "80", "30", "--seed", "8", "--header-lines", "--out", str(b)],
                    check=True)
     assert b.read_bytes() != a.read_bytes() and agx.formats.parse_sw(b.read_bytes()).n_pairs == 30
+
+
+def _irregular_pairhmm_file(agx):
+    inp = agx.synth.pairhmm_batches(7, 9, 3, seed=3)
+    lines = bytes(inp.buf).split(b"\n")[:-1]
+    heads = [i for i, l in enumerate(lines) if len(l.split()) == 2 and l.split()[0].isdigit()]
+    a, b = lines[heads[1]].split()
+    lines[heads[1]] = b"  " + a + b"\t " + b                     # leading blanks, a tab
+    a, b = lines[heads[2]].split()
+    lines[heads[2]] = b"+" + a + b" " + b + b" trailing words"    # sign, trailing text
+    lines.insert(heads[3], b"0 0")                                # a batch with nothing in it
+    return b"\n".join(lines)                                      # and no newline after the last haplotype
+
+
+@pytest.mark.parametrize("which", ["pairhmm_matrix", "pairhmm_antidiag_noleak"])
+def test_pairhmm_header_walk_is_the_references(agx, oracle_mod, tmp_path, which):
+    """The mirror of the batch walk (formats.parse_pairhmm, which the GPU parser is tested against) agrees
+    with the compiled reference on headers only sscanf("%d %d") would accept."""
+    if not oracle_mod.ref_available(which):
+        pytest.skip("compiled reference not available")
+    data = _irregular_pairhmm_file(agx)
+    path = tmp_path / "irregular.in"
+    path.write_bytes(data)
+    vals, _ = oracle_mod.run_ref_pairhmm(str(path), which)
+    host = agx.formats.parse_pairhmm(data)
+    assert host.n_batches == 8 and len(vals) == host.n_pairs == 189
+    assert np.max(np.abs(vals - oracle_mod.pairhmm_flat(host))) <= 1e-6
+
+
+@pytest.mark.parametrize("keep,extra,message", [(3 * 13 + 5, b"", b"Error reading haplotypes."),
+                                                (3 * 13 + 11, b"", b"Error reading haplotypes."),
+                                                (13, b"3 0\nACGT IIII NNNN NNNN ++++\n", b"Error reading reads.")])
+def test_pairhmm_truncated_file_message_of_the_reference(agx, oracle_mod, tmp_path, keep, extra, message):
+    """What the reference says when the file ends inside a batch: its haplotype cursor runs ahead of its read
+    cursor (antidiagsPairHMM.c:388-396), so it is "Error reading haplotypes." unless the batch has none.
+    (The reference then crashes in its cleanup; only the message is pinned here.)"""
+    import subprocess
+    if not oracle_mod.ref_available("pairhmm_antidiag_noleak"):
+        pytest.skip("compiled reference not available")
+    inp = agx.synth.pairhmm_batches(4, 9, 3, seed=5)
+    lines = bytes(inp.buf).split(b"\n")[:-1]                      # a batch = 1 + 9 + 3 lines
+    path = tmp_path / "cut.in"
+    path.write_bytes(b"\n".join(lines[:keep]) + b"\n" + extra)
+    r = subprocess.run([str(oracle_mod.REF / "pairhmm_antidiag_noleak"), str(path), str(tmp_path / "o")], capture_output=True)
+    assert r.returncode != 0 and r.stderr.startswith(message)

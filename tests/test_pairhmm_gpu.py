@@ -189,8 +189,10 @@ def test_file_image_irregular_headers_follow_the_reference_walk(agx, gpu_lib):
     assert np.array_equal(vals, _run_flat(gpu_lib, inp))
 
 
-@pytest.mark.parametrize("cut,code", [("reads", 1), ("haps", 2)])
+@pytest.mark.parametrize("cut,code", [("reads", 2), ("haps", 2)])
 def test_file_image_truncated_last_batch(agx, gpu_lib, cut, code):
+    """The reference's haplotype cursor runs ahead of its read cursor (antidiagsPairHMM.c:388-396), so a file
+    that ends anywhere inside a batch with haplotypes makes it say "Error reading haplotypes." (code 2)."""
     inp, data = _small_batches(agx, 5, n_batches=4)
     lines = data.split(b"\n")[:-1]
     # batch = 1 header + 9 reads + 3 haplotypes = 13 lines; cut inside the last batch
@@ -232,8 +234,11 @@ def test_file_image_streaming_segments(agx, gpu_lib, segment, monkeypatch):
     lines = data.split(b"\n")[:-1]
     cut = b"\n".join(lines[: 11 * 18 + 6]) + b"\n"                  # batch = 1 + 14 + 3 lines; EOF inside the reads
     vals, batch_pairs, incomplete = gpu_lib.pairhmm_forward_file_image(cut)
-    assert incomplete == 1 and batch_pairs.tolist() == [42] * 11
+    assert incomplete == 2 and batch_pairs.tolist() == [42] * 11
     assert np.array_equal(vals, want[: 11 * 42])
+    # a batch without haplotypes that runs out of reads is the one case of "Error reading reads." (code 1)
+    vals, batch_pairs, incomplete = gpu_lib.pairhmm_forward_file_image(b"\n".join(lines[:18]) + b"\n3 0\n" + lines[1] + b"\n")
+    assert incomplete == 1 and batch_pairs.tolist() == [42]
 
 
 def test_config4_shape_properties(agx, gpu_lib, oracle_mod, monkeypatch):
