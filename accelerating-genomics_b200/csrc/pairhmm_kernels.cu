@@ -545,8 +545,56 @@ hmm_duo_kernel(HmmBatchView v, const int64_t *__restrict__ read_out_off, const i
     constexpr int SYM_STRIDE = CH * 32;              // float4 elements between symbols
     const bool lane0 = (t == 0);
 
-#pragma unroll 2
-    for (int32_t s = 0; s < total; ++s) {
+    // One column step (no haplotype switch inside: see the driver loop below).
+    auto step = [&]() {
+            const uint32_t code = code_next;
+            cp += inc;
+            code_next = *cp;                                  // prefetch the next column's symbol
+            float4 pr4[CH];
+#pragma unroll
+            for (int ch = 0; ch < CH; ++ch) pr4[ch] = tab_lane[code * SYM_STRIDE + ch * 32];
+
+            float2 upM, upX, upY;
+            upM.x = __shfl_up_sync(0xffffffffu, bM.x, 1); upM.y = __shfl_up_sync(0xffffffffu, bM.y, 1);
+            upX.x = __shfl_up_sync(0xffffffffu, bX.x, 1); upX.y = __shfl_up_sync(0xffffffffu, bX.y, 1);
+            upY.x = __shfl_up_sync(0xffffffffu, bY.x, 1); upY.y = __shfl_up_sync(0xffffffffu, bY.y, 1);
+            if (lane0) { upM = zero2; upX = zero2; upY = make_float2(init, init); }
+            float2 dM = pdM, dX = pdX, dY = pdY;
+            pdM = upM; pdX = upX; pdY = upY;
+#pragma unroll
+            for (int jj = 0; jj < K; ++jj) {
+                const float2 oM = M[jj], oX = X[jj], oY = Y[jj];
+                const float4 p4 = pr4[jj / 2];
+                const float2 pr = (jj & 1) ? make_float2(p4.z, p4.w) : make_float2(p4.x, p4.y);
+                float2 vv = fmul2(cby[jj], dY);
+                vv = ffma2(cbx[jj], dX, vv);
+                vv = ffma2(ca[jj], dM, vv);
+                const float2 mn = fmul2(pr, vv);
+                const float2 xn = ffma2(ccx[jj], upX, upM);
+                const float2 yn = ffma2(cg[jj], oY, oM);
+                dM = oM; dX = oX; dY = oY;
+                upM = mn; upX = xn;
+                M[jj] = mn; X[jj] = xn; Y[jj] = yn;
+            }
+            bM = M[K - 1]; bX = X[K - 1]; bY = Y[K - 1];
+            acc = fadd2(acc, ffma2(qi_last, bX, bM));
+            --rem;
+    };
+    // Driver: lanes switch haplotype at different steps (lane t lags t columns), and a switch rewrites the whole
+    // state, so a per-step "if (rem == 0)" is a scheduling barrier in every step.  Instead the warp asks how
+    // many steps remain until ANY lane switches (one REDUX.MIN) and runs that many branch-free, four per loop
+    // trip -- ptxas then overlaps the independent parts of consecutive columns; only the ~32 steps around each
+    // haplotype boundary take the checked single-step path.
+    int32_t s = 0;
+    while (s < total) {
+        const int32_t n = min((int32_t)__reduce_min_sync(0xffffffffu, rem), total - s);
+        if (n >= 4) {
+            const int32_t n4 = n & ~3;
+#pragma unroll 1
+            for (int32_t q = 0; q < n4; q += 4) { step(); step(); step(); step(); }
+            s += n4;
+            continue;
+        }
         if (rem == 0) {
             // ---- this lane finished a haplotype: lane 31 owns the last row of both reads ----
             if (t == 31 && hidx >= h0) { sums_a[hidx - h0] = acc.x; sums_b[hidx - h0] = acc.y; }
@@ -573,38 +621,8 @@ hmm_duo_kernel(HmmBatchView v, const int64_t *__restrict__ read_out_off, const i
             pdM = zero2; pdX = zero2;
             pdY = make_float2(top_boundary[0] ? init : 0.f, top_boundary[1] ? init : 0.f);
         }
-        const uint32_t code = code_next;
-        cp += inc;
-        code_next = *cp;                                  // prefetch the next column's symbol
-        float4 pr4[CH];
-#pragma unroll
-        for (int ch = 0; ch < CH; ++ch) pr4[ch] = tab_lane[code * SYM_STRIDE + ch * 32];
-
-        float2 upM, upX, upY;
-        upM.x = __shfl_up_sync(0xffffffffu, bM.x, 1); upM.y = __shfl_up_sync(0xffffffffu, bM.y, 1);
-        upX.x = __shfl_up_sync(0xffffffffu, bX.x, 1); upX.y = __shfl_up_sync(0xffffffffu, bX.y, 1);
-        upY.x = __shfl_up_sync(0xffffffffu, bY.x, 1); upY.y = __shfl_up_sync(0xffffffffu, bY.y, 1);
-        if (lane0) { upM = zero2; upX = zero2; upY = make_float2(init, init); }
-        float2 dM = pdM, dX = pdX, dY = pdY;
-        pdM = upM; pdX = upX; pdY = upY;
-#pragma unroll
-        for (int jj = 0; jj < K; ++jj) {
-            const float2 oM = M[jj], oX = X[jj], oY = Y[jj];
-            const float4 p4 = pr4[jj / 2];
-            const float2 pr = (jj & 1) ? make_float2(p4.z, p4.w) : make_float2(p4.x, p4.y);
-            float2 vv = fmul2(cby[jj], dY);
-            vv = ffma2(cbx[jj], dX, vv);
-            vv = ffma2(ca[jj], dM, vv);
-            const float2 mn = fmul2(pr, vv);
-            const float2 xn = ffma2(ccx[jj], upX, upM);
-            const float2 yn = ffma2(cg[jj], oY, oM);
-            dM = oM; dX = oX; dY = oY;
-            upM = mn; upX = xn;
-            M[jj] = mn; X[jj] = xn; Y[jj] = yn;
-        }
-        bM = M[K - 1]; bX = X[K - 1]; bY = Y[K - 1];
-        acc = fadd2(acc, ffma2(qi_last, bX, bM));
-        --rem;
+        step();
+        ++s;
     }
     // the last haplotype of lane 31 ends exactly at the last step
     if (t == 31 && hidx >= h0 && hidx < h1 && rem == 0) { sums_a[hidx - h0] = acc.x; sums_b[hidx - h0] = acc.y; }
