@@ -57,6 +57,10 @@ constexpr int HCNT_WORDS = HCNT_PAIRS + HMM_MAX_K;
 #define AGX_HMM_MINBLOCKS 20
 #endif
 constexpr int HMM_WARPS = AGX_HMM_WARPS;
+#ifndef AGX_HMM_FAST
+#define AGX_HMM_FAST 8
+#endif
+constexpr int HMM_FAST = AGX_HMM_FAST;           // branch-free column steps per loop trip of hmm_duo_kernel
 
 constexpr float SCALE_F = 1.329227995784916e36f;  // 2^120
 // a forward sum below this (2^-100) may have lost low-order terms to FP32 underflow
@@ -588,11 +592,14 @@ hmm_duo_kernel(HmmBatchView v, const int64_t *__restrict__ read_out_off, const i
     int32_t s = 0;
     while (s < total) {
         const int32_t n = min((int32_t)__reduce_min_sync(0xffffffffu, rem), total - s);
-        if (n >= 4) {
-            const int32_t n4 = n & ~3;
+        if (n >= HMM_FAST) {
+            const int32_t nf = n - n % HMM_FAST;
 #pragma unroll 1
-            for (int32_t q = 0; q < n4; q += 4) { step(); step(); step(); step(); }
-            s += n4;
+            for (int32_t q = 0; q < nf; q += HMM_FAST) {
+#pragma unroll
+                for (int r_ = 0; r_ < HMM_FAST; ++r_) step();
+            }
+            s += nf;
             continue;
         }
         if (rem == 0) {
