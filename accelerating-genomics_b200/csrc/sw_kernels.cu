@@ -448,7 +448,8 @@ __device__ bool wave_pair(const uint8_t *a, int32_t la, const uint8_t *b, int32_
             }
             __syncwarp();
             const int send = min(32, S - s0);
-#pragma unroll 1
+            // row steps per loop trip: measured on 3 kbp pairs 1 -> 1766, 2 -> 1786, 4 -> 1874 GCUPS
+#pragma unroll 4
             for (int u = 0; u < send; ++u) {
                 const int s = s0 + u;
                 const int slot = (s - lane) & (WAVE_RING - 1);
