@@ -69,7 +69,7 @@ def build_drivers(force: bool = False) -> None:
     if peaks.exists():
         out = BIN / "agx_peaks"
         if force or _stale(out, [peaks]):
-            _run([NVCC, *ARCH, "-O3", "-std=c++17", "-lineinfo", peaks, "-o", out])
+            _run([NVCC, *ARCH, "-O3", "-std=c++17", "-lineinfo", peaks, "-o", out, "-ldl"])
 
 
 def build_oracle() -> None:

@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <chrono>
 
 #define CK(x)                                                                      \
     do {                                                                           \
@@ -21,6 +22,61 @@
             exit(1);                                                               \
         }                                                                          \
     } while (0)
+
+// ---- SM clock / throttle reasons while the kernels run: NVML through dlopen (no link-time dependency) ----
+#include <dlfcn.h>
+#include <atomic>
+#include <thread>
+#include <vector>
+#include <algorithm>
+struct Nvml {
+    void *h = nullptr, *dev = nullptr;
+    int (*clock)(void *, int, unsigned *) = nullptr;
+    int (*reasons)(void *, unsigned long long *) = nullptr;
+    std::atomic<bool> stop{false};
+    std::vector<unsigned> mhz;
+    unsigned long long seen = 0;
+    std::thread th;
+    bool open(int index)
+    {
+        h = dlopen("libnvidia-ml.so.1", RTLD_NOW);
+        if (!h) return false;
+        auto init = (int (*)())dlsym(h, "nvmlInit_v2");
+        auto get = (int (*)(unsigned, void **))dlsym(h, "nvmlDeviceGetHandleByIndex_v2");
+        clock = (int (*)(void *, int, unsigned *))dlsym(h, "nvmlDeviceGetClockInfo");
+        reasons = (int (*)(void *, unsigned long long *))dlsym(h, "nvmlDeviceGetCurrentClocksEventReasons");
+        if (!reasons) reasons = (int (*)(void *, unsigned long long *))dlsym(h, "nvmlDeviceGetCurrentClocksThrottleReasons");
+        if (!init || !get || !clock || init() != 0 || get((unsigned)index, &dev) != 0) return false;
+        return true;
+    }
+    void start()
+    {
+        if (!dev) return;
+        stop = false;
+        th = std::thread([this] {
+            while (!stop.load()) {
+                unsigned v = 0;
+                if (clock(dev, 1 /* NVML_CLOCK_SM */, &v) == 0) mhz.push_back(v);
+                unsigned long long r = 0;
+                if (reasons && reasons(dev, &r) == 0) seen |= r;
+                std::this_thread::sleep_for(std::chrono::milliseconds(5));
+            }
+        });
+    }
+    void finish()
+    {
+        if (!dev) { printf("{\"clocks\": null}\n"); return; }
+        stop = true;
+        th.join();
+        std::sort(mhz.begin(), mhz.end());
+        const unsigned med = mhz.empty() ? 0 : mhz[mhz.size() / 2];
+        printf("{\"clocks\": {\"sm_mhz_median\": %u, \"sm_mhz_min\": %u, \"sm_mhz_max\": %u, \"samples\": %zu, "
+               "\"reasons_mask\": \"0x%llx\", \"hw_slowdown\": %d, \"hw_thermal_slowdown\": %d, \"sw_thermal_slowdown\": %d, "
+               "\"sw_power_cap\": %d}}\n",
+               med, mhz.empty() ? 0 : mhz.front(), mhz.empty() ? 0 : mhz.back(), mhz.size(), seen, (int)((seen >> 3) & 1),
+               (int)((seen >> 6) & 1), (int)((seen >> 5) & 1), (int)((seen >> 2) & 1));
+    }
+};
 
 constexpr int NCHAIN = 8;
 constexpr int UNROLL = 8;   // ops per chain per loop iteration
@@ -32,7 +88,8 @@ enum Op {
     OP_MIX_DPX_IMAD, OP_MIX_DPX_FFMA, OP_MIX_FFMA_SEL, OP_SWCELL, OP_SHFL,
     OP_MIX_VIADD_VIADDMNMX, OP_MIX_VIADDMNMX_VIMNMX3, OP_MIX_PRMT_VIADDMNMX, OP_MIX_VIADD_PRMT, OP_MIX_VIADD_IMAD,
     OP_MIX_VIMNMX3_IMAD, OP_MIX_PRMT_IMAD, OP_MIX_LOP3_VIADDMNMX, OP_MIX_VIADD_FFMA, OP_SWCELL_FULL,
-    OP_HMNMX2, OP_MIX_HMNMX2_VIADDMNMX, OP_MIX_HMNMX2_VIADD, OP_COUNT
+    OP_HMNMX2, OP_MIX_HMNMX2_VIADDMNMX, OP_MIX_HMNMX2_VIADD,
+    OP_IDP4A, OP_MIX_IDP4A_VIADDMNMX, OP_MIX_IDP4A_IMAD, OP_SWCELL_S32, OP_SWCELL_S32_DP4A, OP_COUNT
 };
 static const char *op_name[OP_COUNT] = {
     "VIADDMNMX.S16x2", "VIMNMX3.S16x2.RELU", "VIADD.16x2", "VIMNMX.S16x2", "PRMT",
@@ -43,10 +100,13 @@ static const char *op_name[OP_COUNT] = {
     "mix VIADD.16x2 : VIADDMNMX.S16x2", "mix VIADDMNMX.S16x2 : VIMNMX3.S16x2", "mix PRMT : VIADDMNMX.S16x2",
     "mix VIADD.16x2 : PRMT", "mix VIADD.16x2 : IMAD", "mix VIMNMX3.S16x2 : IMAD", "mix PRMT : IMAD",
     "mix LOP3 : VIADDMNMX.S16x2", "mix VIADD.16x2 : FFMA", "SW s16x2 cell with PRMT (7 ops)",
-    "HMNMX2 (max.f16x2)", "mix HMNMX2 : VIADDMNMX.S16x2", "mix HMNMX2 : VIADD.16x2"};
+    "HMNMX2 (max.f16x2)", "mix HMNMX2 : VIADDMNMX.S16x2", "mix HMNMX2 : VIADD.16x2",
+    "IDP.4A (dp4a.s32.s32)", "mix IDP.4A : VIADDMNMX.S32", "mix IDP.4A : IMAD",
+    "SW s32 coded cell (PRMT + 2 IMAD + 3 DPX, 6 ops)", "SW s32 cell, dp4a substitution (1 IDP + 1 IMAD + 3 DPX, 5 ops)"};
 // lane-ops counted per chain step
 static const double op_count[OP_COUNT] = {1, 2, 1, 2, 1, 1, 2, 1, 1, 1, 1, 1, 1, 2, 2, 2, 5, 6, 1,
-                                              2, 2, 2, 2, 2, 2, 2, 2, 2, 7, 2, 2, 2};
+                                              2, 2, 2, 2, 2, 2, 2, 2, 2, 7, 2, 2, 2,
+                                              1, 2, 2, 6, 5};
 
 __device__ __forceinline__ void ffma(uint32_t &x, uint32_t a, uint32_t b)
 {
@@ -134,6 +194,31 @@ __device__ __forceinline__ void step(uint32_t &x, uint32_t &y, uint32_t a, uint3
         y = __vadd2(y, a);
         asm volatile("max.f16x2 %0, %0, %1;" : "+r"(x) : "r"(y));
     }
+    else if constexpr (OP == OP_IDP4A) x = (uint32_t)__dp4a((int)a, (int)b, (int)x);
+    else if constexpr (OP == OP_MIX_IDP4A_VIADDMNMX) { x = (uint32_t)__dp4a((int)a, (int)b, (int)x); y = __viaddmax_s32(y, a, b); }
+    else if constexpr (OP == OP_MIX_IDP4A_IMAD) {
+        x = (uint32_t)__dp4a((int)a, (int)b, (int)x);
+        asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(y) : "r"(a), "r"(b));
+    } else if constexpr (OP == OP_SWCELL_S32) {
+        // one symbol-coded s32 cell of sw_long.cu: x = E chain, y = H + goe of the previous row
+        uint32_t t, d, g;
+        asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(a), "r"(b), "r"(c));
+        asm volatile("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(y), "r"(1 | (c & 0)), "r"(t));
+        x = __viaddmax_s32(x, a, y);
+        const uint32_t f = __viaddmax_s32(y, a, d);
+        const uint32_t h = __vimax3_s32_relu(x, f, d);
+        asm volatile("mad.lo.s32 %0, %1, %2, %3;" : "=r"(g) : "r"(h), "r"(1 | (c & 0)), "r"(b));
+        y = g;
+    } else if constexpr (OP == OP_SWCELL_S32_DP4A) {
+        // the same cell with the substitution score added by one dp4a (byte-select by a one-hot multiplier)
+        uint32_t g;
+        const uint32_t d = (uint32_t)__dp4a((int)a, (int)(0x00000100u | (c & 0)), (int)y);
+        x = __viaddmax_s32(x, a, y);
+        const uint32_t f = __viaddmax_s32(y, a, d);
+        const uint32_t h = __vimax3_s32_relu(x, f, d);
+        asm volatile("mad.lo.s32 %0, %1, %2, %3;" : "=r"(g) : "r"(h), "r"(1 | (c & 0)), "r"(b));
+        y = g;
+    }
     else if constexpr (OP == OP_SWCELL_FULL) {
         uint32_t t;
         asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(x), "r"(b), "r"(c));
@@ -204,11 +289,11 @@ void run(int sms, uint32_t *d_out, long long *d_cyc, int blocks_per_sm)
     const double lane_ops = ops_per_thread * threads * blocks;
     // all blocks of an SM are co-resident (blocks_per_sm * 256 threads <= 2048), so an SM's work
     // is blocks_per_sm blocks during ~best_cyc cycles
+    // (clock64 is a per-SM cycle counter: mean block span; the SM clock itself is in the NVML "clocks" record)
     const double per_clk_sm = ops_per_thread * threads * blocks_per_sm / best_cyc;
     printf("{\"op\": \"%s\", \"lane_ops_per_clk_per_sm\": %.2f, \"tera_lane_ops_per_s\": %.3f, "
-           "\"ms\": %.4f, \"eff_clock_mhz\": %.0f, \"warps_per_sm\": %d}\n",
-           op_name[OP], per_clk_sm, lane_ops / (best_ms * 1e-3) / 1e12, best_ms,
-           best_cyc / (best_ms * 1e-3) / 1e6, blocks_per_sm * threads / 32);
+           "\"ms\": %.4f, \"warps_per_sm\": %d}\n",
+           op_name[OP], per_clk_sm, lane_ops / (best_ms * 1e-3) / 1e12, best_ms, blocks_per_sm * threads / 32);
     fflush(stdout);
 }
 
@@ -596,6 +681,21 @@ int main(int argc, char **argv)
     long long *d_cyc;
     CK(cudaMalloc(&d_out, sizeof(uint32_t) * sms * bps * 256));
     CK(cudaMalloc(&d_cyc, sizeof(long long) * sms * bps));
+    Nvml nv;
+    nv.open(dev);
+    nv.start();
+    struct Fin { Nvml &n; ~Fin() { n.finish(); } } fin{nv};
+    if (argc > 2 && !strcmp(argv[2], "dp4a")) {
+        run<OP_PRMT>(sms, d_out, d_cyc, bps);
+        run<OP_IMAD>(sms, d_out, d_cyc, bps);
+        run<OP_VIADDMNMX_S32>(sms, d_out, d_cyc, bps);
+        run<OP_IDP4A>(sms, d_out, d_cyc, bps);
+        run<OP_MIX_IDP4A_VIADDMNMX>(sms, d_out, d_cyc, bps);
+        run<OP_MIX_IDP4A_IMAD>(sms, d_out, d_cyc, bps);
+        run<OP_SWCELL_S32>(sms, d_out, d_cyc, bps);
+        run<OP_SWCELL_S32_DP4A>(sms, d_out, d_cyc, bps);
+        return 0;
+    }
     const bool only_fp = argc > 2 && !strcmp(argv[2], "fp");
     const bool only_hm = argc > 2 && !strcmp(argv[2], "hm");
     if (only_hm) {

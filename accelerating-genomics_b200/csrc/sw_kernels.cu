@@ -160,11 +160,15 @@ __device__ __forceinline__ uint32_t base_code(uint32_t ch, bool &ok)
     return code;
 }
 
+// Resident 128-thread CTAs per SM the register budget is cut for.  The state is 3 K registers (sel, Gp, F), so
+// one budget for every class spills the wide ones (K = 32 at 5 CTAs / 96 registers: ~400 LDL/STL in the cell
+// loop): 5 CTAs up to K = 19, 3 (168 registers) for K = 24, 2 (255) for K = 32.
 #ifndef AGX_DUO_MINBLOCKS
 #define AGX_DUO_MINBLOCKS 5
 #endif
+__host__ __device__ constexpr int duo_min_blocks_sw(int K) { return K <= 19 ? AGX_DUO_MINBLOCKS : K <= 24 ? 3 : 2; }
 template <int G, int K>
-__global__ void __launch_bounds__(DUO_THREADS, AGX_DUO_MINBLOCKS)
+__global__ void __launch_bounds__(DUO_THREADS, duo_min_blocks_sw(K))
 sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
               const int32_t *__restrict__ len, const int32_t *__restrict__ order_cls,
               int32_t n_in_class, DuoConst kc, int32_t *__restrict__ scores,

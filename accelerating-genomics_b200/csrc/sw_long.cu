@@ -45,6 +45,8 @@ struct LongArgs {
     SwScoring sc;
     const uint8_t *lut;       // CODED kernels: byte -> symbol code 0..6 (both sequences use <= 7 distinct bytes)
     int32_t one;              // the constant 1, opaque to ptxas: x + y as IMAD (FMA pipe) instead of IADD3 (ALU pipe)
+    const int2 *rowtab;       // sw_longr_kernel: 8-byte score table of every row (long_rowtab_kernel), padded
+    int32_t bsteps;           // sw_longr_kernel: row steps per hand-off block (<= LR_BMAX)
 };
 
 // prmt.b32 in its default mode: selector nibble bit 3 replicates the sign of the selected byte
@@ -452,6 +454,287 @@ sw_long2_kernel(LongArgs g)
     if (lane == 0 && best > 0) atomicMax(g.best, best);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// R rows per step.  The general form of the two kernels above for symbol-coded sequences: lane t holds K
+// columns and advances R rows per step (rows R(s-t) .. R(s-t)+R-1), i.e. an R x K tile of cells whose R row
+// chains run one column apart.  Why: with one warp per scheduler (the per-GPU share of an 8-GPU run) a step
+// is a latency chain -- shuffle in, dependent cells, shuffle out -- and the per-step costs (2R shuffles, row
+// tables, lane-0 boundary, staging, loop) are paid once per R*K cells; the total run is
+//     (stripes * (32 + B) + rows / R) steps            (32 = lane skew, B = steps per hand-off block)
+// so R trades the row term against the stripe-fill term, and B (a run-time argument) trims the fill.
+//   - Row score tables come from a pre-pass (long_rowtab_kernel: one coalesced 8-byte load per row instead of
+//     two dependent ones) and are requested a block ahead.
+//   - The ring holds neutral rows for the 31 steps in which high lanes have no row yet, so the step has no
+//     "is this lane live" predicate.
+//   - DP4A: ONE PRMT fetches the substitution bytes of four columns and each cell adds its byte to the
+//     diagonal with dp4a (one-hot multiplier) -- PRMT work per cell drops from 1 to 1/4 ALU-pipe instruction.
+// Everything else (tagged 16-byte entries, staged flush, warp-uniform polling, peer stores) as above.
+constexpr int LR_BMAX = 32;
+
+template <int R> __device__ __forceinline__ void lds_vec(const int32_t *p, int32_t (&v)[R])
+{
+    if constexpr (R == 4) { const int4 x = *reinterpret_cast<const int4 *>(p); v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; }
+    else if constexpr (R == 2) { const int2 x = *reinterpret_cast<const int2 *>(p); v[0] = x.x; v[1] = x.y; }
+    else {
+#pragma unroll
+        for (int i = 0; i < R; ++i) v[i] = p[i];
+    }
+}
+
+template <int K, int R, bool SHORT, bool DP4A>
+__global__ void __launch_bounds__(LONG_WARPS * 32)
+sw_longr_kernel(LongArgs g)
+{
+    constexpr int W = 32 * K;
+    constexpr int RROWS = 64 * R;                      // ring rows: 31 steps of lane skew + a block of <= 32 steps
+    constexpr int K4 = (K + 3) / 4;
+    __shared__ __align__(16) int32_t r_lo[LONG_WARPS][RROWS];
+    __shared__ __align__(16) int32_t r_hi[LONG_WARPS][RROWS];
+    __shared__ __align__(16) int32_t r_g[LONG_WARPS][RROWS];
+    __shared__ __align__(16) int32_t r_e[LONG_WARPS][RROWS];
+    __shared__ __align__(16) int2 stage[LONG_WARPS][LR_BMAX * R];
+
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int warp = blockIdx.x * LONG_WARPS + wib;
+    const int n_warps = gridDim.x * LONG_WARPS;
+    const int32_t goe = g.sc.gap_open + g.sc.gap_extend;
+    const int32_t ext = g.sc.gap_extend;
+    const int32_t lb = g.lb;
+    const int n_stripes = (g.la + W - 1) / W;
+    const int B = g.bsteps;
+    int32_t bestg = goe;
+    const int32_t one = g.one;
+    const int32_t xb4 = (int32_t)((uint32_t)(uint8_t)(int8_t)(g.sc.mismatch - goe) * 0x01010101u);
+    const int S = (lb + R - 1) / R + 31;               // lane 31 finishes the last row block at step (lb-1)/R + 31
+
+    for (int st = warp; st < n_stripes; st += n_warps) {
+        const int c0 = st * W + lane * K;
+        // column symbols: one PRMT selector per column, or (DP4A) four 3-bit codes per selector
+        int32_t acol[DP4A ? K4 : K], Gp[K], F[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) { Gp[j] = goe; F[j] = goe; }
+        if constexpr (DP4A) {
+#pragma unroll
+            for (int q = 0; q < K4; ++q) {
+                uint32_t sel = 0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = 4 * q + e;
+                    const uint32_t c = (j < K && c0 + j < g.la) ? (uint32_t)g.lut[g.a[c0 + j]] : 7u;
+                    sel |= c << (4 * e);
+                }
+                acol[q] = (int32_t)sel;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const uint32_t c = (c0 + j < g.la) ? (uint32_t)g.lut[g.a[c0 + j]] : 7u;
+                acol[j] = (int32_t)(c | ((8u | c) * 0x1110u));              // byte c, sign-extended to 32 bits
+            }
+        }
+        int32_t g_out[R], e_out[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) { g_out[i] = goe; e_out[i] = goe; }
+        int32_t g_in_prev = goe;
+        const int32_t gst = g.stripe_base + st;                          // global stripe index = my tag
+        const bool left_edge = (gst == 0);
+        const bool last = (st == n_stripes - 1);
+        int4 *out_bnd = last ? g.next_bnd : g.bnd;                       // nullptr: nothing to hand on
+        const bool out_remote = last;
+        const bool in_remote = (st == 0);
+        const int4 fresh = make_int4(goe, gst - 1, goe, gst - 1);
+
+        // neutral rows -31R .. -1 (what a lane sees before its first real row)
+        __syncwarp();
+        for (int i = lane; i < 31 * R; i += 32) {
+            const int slot = (RROWS - 31 * R) + i;
+            r_lo[wib][slot] = xb4; r_hi[wib][slot] = xb4; r_g[wib][slot] = goe; r_e[wib][slot] = goe;
+        }
+        // inputs of the first block: this lane owns rows base + 32 q + lane of every block
+        int2 nt[R];
+        int4 nx[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            const int idx = 32 * q + lane;
+            nt[q] = make_int2(xb4, xb4);
+            nx[q] = fresh;
+            if (idx < B * R) {
+                nt[q] = g.rowtab[idx];
+                if (!left_edge && idx < lb) nx[q] = ld_entry(g.bnd + idx, in_remote);
+            }
+        }
+        for (int s0 = 0; s0 < S; s0 += B) {
+            const int base = R * s0;
+            if (!left_edge) {
+                // wait until the left neighbour has handed this block's rows on
+                unsigned ns = 20;
+                for (;;) {
+                    bool missing = false;
+#pragma unroll
+                    for (int q = 0; q < R; ++q) missing = missing || nx[q].y != gst - 1 || nx[q].w != gst - 1;
+                    if (!__any_sync(0xffffffffu, missing)) break;
+                    __nanosleep(ns);
+                    if (ns < 320) ns *= 2;
+#pragma unroll
+                    for (int q = 0; q < R; ++q)
+                        if (nx[q].y != gst - 1 || nx[q].w != gst - 1) nx[q] = ld_entry(g.bnd + base + 32 * q + lane, in_remote);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int idx = 32 * q + lane;
+                if (idx < B * R) {
+                    const int slot = (base + idx) & (RROWS - 1);
+                    r_lo[wib][slot] = nt[q].x; r_hi[wib][slot] = nt[q].y;
+                    r_g[wib][slot] = nx[q].x;  r_e[wib][slot] = nx[q].z;
+                }
+            }
+            __syncwarp();
+            // row tables of the next block: requested now, consumed after this block's steps
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int idx = 32 * q + lane;
+                if (idx < B * R) nt[q] = g.rowtab[base + B * R + idx];       // rowtab is padded past the last block
+            }
+            const int send = min(B, S - s0);
+#pragma unroll(R == 1 ? 2 : 1)
+            for (int u = 0; u < send; ++u) {
+                const int s = s0 + u;
+                const int sl = (R * (s - lane)) & (RROWS - 1);
+                const int sl0 = (R * s) & (RROWS - 1);
+                int32_t tlo[R], thi[R], g_in[R], e[R], bg[R], be[R];
+                lds_vec<R>(&r_lo[wib][sl], tlo);
+                lds_vec<R>(&r_hi[wib][sl], thi);
+                lds_vec<R>(&r_g[wib][sl0], bg);            // same address in every lane: a broadcast
+                lds_vec<R>(&r_e[wib][sl0], be);
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    g_in[i] = __shfl_up_sync(0xffffffffu, g_out[i], 1);
+                    e[i] = __shfl_up_sync(0xffffffffu, e_out[i], 1);
+                    if (lane == 0) { g_in[i] = bg[i]; e[i] = be[i]; }
+                }
+                int32_t gdiag[R], gleft[R], tgp[R];
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    gdiag[i] = i == 0 ? g_in_prev : g_in[i - 1];           // (H+goe)[row-1][c0-1]
+                    gleft[i] = g_in[i];
+                    tgp[i] = g_in[i];
+                }
+                g_in_prev = g_in[R - 1];
+                uint32_t sc4[R];
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    if constexpr (DP4A) {
+                        if ((j & 3) == 0) {
+#pragma unroll
+                            for (int i = 0; i < R; ++i) sc4[i] = __byte_perm((uint32_t)tlo[i], (uint32_t)thi[i], (uint32_t)acol[j >> 2]);
+                        }
+                    }
+                    int32_t up = Gp[j], f = F[j];
+#pragma unroll
+                    for (int i = 0; i < R; ++i) {
+                        int32_t d;
+                        if constexpr (DP4A) d = __dp4a((int32_t)sc4[i], (int32_t)(1u << (8 * (j & 3))), gdiag[i]);
+                        else d = add_fma(gdiag[i], prmt_s((uint32_t)tlo[i], (uint32_t)thi[i], (uint32_t)acol[j]), one);
+                        f = __viaddmax_s32(f, ext, up);                              // F[i][j]
+                        int32_t gnew;
+                        if constexpr (SHORT) {
+                            const int32_t tg = add_fma(__vimax_s32_relu(f, d), goe, one);      // T + goe, T = max(F, diag + s, 0)
+                            e[i] = __viaddmax_s32(e[i], ext, tgp[i]);                // E[i][j] = max(E[i][j-1] + ext, T[i][j-1] + goe)
+                            gnew = __viaddmax_s32(e[i], goe, tg);                    // H[i][j] + goe
+                            tgp[i] = tg;
+                        } else {
+                            e[i] = __viaddmax_s32(e[i], ext, gleft[i]);              // E[i][j]
+                            gnew = add_fma(__vimax3_s32_relu(e[i], f, d), goe, one); // H[i][j] + goe
+                        }
+                        gdiag[i] = up;
+                        up = gnew;
+                        gleft[i] = gnew;
+                        if constexpr (R % 2 == 0) { if (i & 1) bestg = __vimax3_s32(bestg, gleft[i - 1], gnew); }
+                        else if (R == 1) { if (j & 1) bestg = __vimax3_s32(bestg, Gp[j - 1], gnew); else if (j == K - 1) bestg = max(bestg, gnew); }
+                        else bestg = max(bestg, gnew);
+                    }
+                    Gp[j] = up; F[j] = f;
+                }
+#pragma unroll
+                for (int i = 0; i < R; ++i) { g_out[i] = gleft[i]; e_out[i] = e[i]; }
+                // lane 31 has just finished rows R(s-31) .. +R-1 of the stripe's last column: stage them
+                if (lane == 31) {
+#pragma unroll
+                    for (int i = 0; i < R; ++i) stage[wib][u * R + i] = make_int2(g_out[i], e_out[i]);
+                }
+            }
+            // boundary entries of the next block (first attempt; the poll at the top repeats what is missing)
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int r = base + B * R + 32 * q + lane;
+                nx[q] = fresh;
+                if (!left_edge && 32 * q + lane < B * R && r < lb) nx[q] = ld_entry(g.bnd + r, in_remote);
+            }
+            // hand on the rows lane 31 finished in this block: rows R(s0-31) .. R(s0-31) + R*send - 1
+            if (out_bnd != nullptr) {
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    const int idx = 32 * q + lane;
+                    const int r = R * (s0 - 31) + idx;
+                    if (idx < R * send && r >= 0 && r < lb) {
+                        const int2 ge = stage[wib][idx];
+                        st_entry(out_bnd + r, make_int4(ge.x, gst, ge.y, gst), out_remote);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) bestg = max(bestg, __shfl_xor_sync(0xffffffffu, bestg, m));
+    const int32_t best = bestg - goe;
+    if (lane == 0 && best > 0) atomicMax(g.best, best);
+}
+
+// row r -> its 8-byte score table (byte k = substitution score - goe against symbol code k; code 7 and the
+// padding rows past the last one never match), laid out for one coalesced 8-byte load per row
+__global__ void __launch_bounds__(256)
+long_rowtab_kernel(const uint8_t *__restrict__ b, int32_t lb, int64_t n_padded, const uint8_t *__restrict__ lut,
+                   SwScoring sc, int2 *__restrict__ rowtab)
+{
+    const int32_t goe = sc.gap_open + sc.gap_extend;
+    const uint32_t xb4 = (uint32_t)(uint8_t)(int8_t)(sc.mismatch - goe) * 0x01010101u;
+    const uint32_t mxor = (uint32_t)(uint8_t)(int8_t)(sc.mismatch - goe) ^ (uint32_t)(uint8_t)(int8_t)(sc.match - goe);
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_padded; r += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t lo = xb4, hi = xb4;
+        if (r < lb) {
+            const uint32_t c = lut[b[r]];
+            if (c < 4) lo ^= mxor << (8 * c); else hi ^= mxor << (8 * (c - 4));
+        }
+        rowtab[r] = make_int2((int32_t)lo, (int32_t)hi);
+    }
+}
+// rows of padding behind the last real row: one block of row tables is always requested ahead
+constexpr int64_t LR_ROW_PAD = 512;        // > 95 R for R <= 4
+__host__ __device__ constexpr int64_t lr_rows_padded(int64_t lb) { return lb + LR_ROW_PAD; }
+
+template <int K, int R, bool SHORT, bool DP4A> int long_launch_r(const LongArgs &args, int n_stripes, cudaStream_t st)
+{
+    int dev = 0, sms = 0, per_sm = 0;
+    AGX_CUDA(cudaGetDevice(&dev));
+    AGX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    AGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_longr_kernel<K, R, SHORT, DP4A>, LONG_WARPS * 32, 0));
+    if (per_sm < 1) return fail(AGX_ECUDA, "sw_long: kernel does not fit on an SM");
+    int blocks = sms * per_sm;                        // all co-resident: required by the stripe wavefront
+    const int want = (n_stripes + LONG_WARPS - 1) / LONG_WARPS;
+    if (blocks > want) blocks = want;
+    LongArgs a = args;
+    void *params[] = {&a};
+    AGX_CUDA(cudaLaunchCooperativeKernel((const void *)sw_longr_kernel<K, R, SHORT, DP4A>, dim3(blocks), dim3(LONG_WARPS * 32),
+                                         params, 0, st));
+    count_launch();
+    return AGX_OK;
+}
+
 template <int K, bool SHORT> int long_launch2(const LongArgs &args, int n_stripes, cudaStream_t st)
 {
     int dev = 0, sms = 0, per_sm = 0;
@@ -492,6 +775,13 @@ int env_int(const char *name, int dflt)
 {
     const char *e = getenv(name);
     return (e && atoi(e) > 0) ? atoi(e) : dflt;
+}
+
+// row steps per hand-off block of sw_longr_kernel (the stripe-fill term of the run is stripes x (32 + B) steps)
+int long_block_steps()
+{
+    const int b = env_int("AGX_LONG_B", 8);
+    return b < 1 ? 1 : b > LR_BMAX ? LR_BMAX : b;
 }
 
 // Stripe width.  The stripe wavefront costs (stripes x hop + rows) row steps, and a step costs about
@@ -550,6 +840,38 @@ template <int I = 0> int long_dispatch_raw(int k, bool short_chain, const LongAr
     }
 }
 
+// sw_longr_kernel instantiations: stripe widths x rows per step x chain form x substitution form
+#ifdef AGX_LONG_SWEEP
+constexpr int LONGR_KS[] = {6, 7, 8, 14, 27};
+#define AGX_LONGR_VARIANTS(X) X(1, false, false) X(1, true, false) X(2, false, false) X(2, true, false) X(4, false, false) \
+    X(4, true, false) X(1, false, true) X(1, true, true) X(2, false, true) X(2, true, true) X(4, false, true) X(4, true, true)
+#else
+constexpr int LONGR_KS[] = {2, 4, 6, 7, 8, 10, 12, 14, 16, 20, 24, 27, 32};
+#define AGX_LONGR_VARIANTS(X) X(2, false, false) X(2, true, false)
+#endif
+constexpr int N_LONGR_KS = (int)(sizeof(LONGR_KS) / sizeof(LONGR_KS[0]));
+
+template <int I = 0> int long_dispatch_r(int k, int rows, bool short_chain, bool dp4a, const LongArgs &args, int n, cudaStream_t st)
+{
+    if constexpr (I < N_LONGR_KS) {
+        if (LONGR_KS[I] == k) {
+#define AGX_X(RR, SS, DD) if (rows == RR && short_chain == SS && dp4a == DD) return long_launch_r<LONGR_KS[I], RR, SS, DD>(args, n, st);
+            AGX_LONGR_VARIANTS(AGX_X)
+#undef AGX_X
+            return fail(AGX_EINVAL, "sw_long: rows-per-step / chain / dp4a combination not instantiated");
+        }
+        return long_dispatch_r<I + 1>(k, rows, short_chain, dp4a, args, n, st);
+    } else {
+        return fail(AGX_EINVAL, "sw_long: stripe width not instantiated");
+    }
+}
+bool longr_has_k(int k)
+{
+    for (int i = 0; i < N_LONGR_KS; ++i)
+        if (LONGR_KS[i] == k) return true;
+    return false;
+}
+
 int long_dispatch(int k, const LongArgs &args, cudaStream_t st)
 {
     const int n = (args.la + 32 * k - 1) / (32 * k);
@@ -559,10 +881,15 @@ int long_dispatch(int k, const LongArgs &args, cudaStream_t st)
     // one warp per scheduler: latency-bound, take the short E chain; more: issue-bound, take the lean one
     bool short_chain = n <= sms * 4;
     if (const char *e = getenv("AGX_LONG_CHAIN")) short_chain = atoi(e) != 0;
-    // one warp per scheduler: two rows per step (see sw_long2_kernel)
-    bool two_rows = n <= sms * 4;
-    if (const char *e = getenv("AGX_LONG_ROWS")) two_rows = atoi(e) == 2;
-    return args.lut ? long_dispatch_coded<0>(k, short_chain, two_rows, args, n, st) : long_dispatch_raw<0>(k, short_chain, args, n, st);
+    if (!args.lut) return long_dispatch_raw<0>(k, short_chain, args, n, st);
+    if (getenv("AGX_LONG_OLD")) {                         // A/B switch: the round-1 kernels
+        bool two_rows = n <= sms * 4;
+        if (const char *e = getenv("AGX_LONG_ROWS")) two_rows = atoi(e) == 2;
+        return long_dispatch_coded<0>(k, short_chain, two_rows, args, n, st);
+    }
+    const int rows = env_int("AGX_LONG_R", 2);
+    const bool dp4a = env_int("AGX_LONG_DP4A", 0) != 0;
+    return long_dispatch_r<0>(k, rows, short_chain, dp4a, args, n, st);
 }
 
 // byte -> symbol code for sequences with at most 7 distinct bytes (code 7 is the "matches nothing" padding);
@@ -620,7 +947,9 @@ int sw_long_device(SwLongWorkspace &ws, const uint8_t *d_a, int64_t la, const ui
     int dev = 0, sms = 148;
     AGX_CUDA(cudaGetDevice(&dev));
     AGX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int64_t need = 4 * lb + 4 + 8 + 64;              // int32 words: entries, best, presence mask, code table
+    const int64_t lbp = lr_rows_padded(lb);
+    // int32 words: entries, best, presence mask, code table, row score tables
+    const int64_t need = 4 * lb + 4 + 8 + 64 + 2 * lbp + 4;
     if (need > ws.cap) {
         if (ws.buf) cudaFree(ws.buf);
         ws.buf = nullptr; ws.cap = 0;
@@ -644,6 +973,13 @@ int sw_long_device(SwLongWorkspace &ws, const uint8_t *d_a, int64_t la, const ui
     args.lut = coded ? d_lut : nullptr;
     args.one = 1;
     args.a = d_a; args.la = (int32_t)la; args.b = d_b; args.lb = (int32_t)lb;
+    args.bsteps = long_block_steps();
+    int2 *d_rowtab = reinterpret_cast<int2 *>(ws.buf + (4 * lb + 4 + 8 + 64 + 1) / 2 * 2);
+    args.rowtab = d_rowtab;
+    if (coded) {
+        long_rowtab_kernel<<<sms * 2, 256, 0, st>>>(d_b, (int32_t)lb, lbp, d_lut, sc, d_rowtab);
+        count_launch();
+    }
     args.bnd = reinterpret_cast<int4 *>(ws.buf);
     args.next_bnd = nullptr;
     args.best = d_best;
@@ -707,7 +1043,8 @@ int sw_long_host_multi(int n_dev, const int *dev, cudaStream_t *st, SwLongWorksp
         ks[gidx] = k;
         const int64_t n_stripes = (cols + 32 * k - 1) / (32 * k);
         SwLongWorkspace &w = *ws[gidx];
-        const int64_t need = 4 * lb + 4;                   // one 16-byte entry per row + the best score
+        const int64_t lbp = lr_rows_padded(lb);
+        const int64_t need = 4 * lb + 4 + 2 * lbp;         // one 16-byte entry per row + the best score + row score tables
         if (need > w.cap) {
             if (w.buf) cudaFree(w.buf);
             w.buf = nullptr; w.cap = 0;
@@ -732,6 +1069,13 @@ int sw_long_host_multi(int n_dev, const int *dev, cudaStream_t *st, SwLongWorksp
         x.bnd = reinterpret_cast<int4 *>(w.buf);
         x.best = w.buf + 4 * lb;
         x.next_bnd = nullptr;
+        x.bsteps = long_block_steps();
+        int2 *d_rowtab = reinterpret_cast<int2 *>(w.buf + 4 * lb + 4);
+        x.rowtab = d_rowtab;
+        if (coded) {
+            long_rowtab_kernel<<<sms * 2, 256, 0, st[gidx]>>>(x.b, (int32_t)lb, lbp, d_lut, sc, d_rowtab);
+            count_launch();
+        }
         x.stripe_base = stripe_base;
         stripe_base += (int32_t)n_stripes;
         x.sc = sc;

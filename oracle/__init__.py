@@ -26,12 +26,15 @@ _lib = None
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        if not LIB.exists():
+        srcs = [HERE / "oracle.c", HERE / "sw_blocked.c", HERE / "oracle.h"]
+        if not LIB.exists() or any(p.exists() and p.stat().st_mtime > LIB.stat().st_mtime for p in srcs):
             subprocess.run(["make", "-C", str(HERE), "liboracle.so"], check=True, capture_output=True)
         l = C.CDLL(str(LIB))
         l.oracle_sw_score.restype = C.c_int32
         l.oracle_sw_score.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32] + [C.c_int32] * 4 + \
             [C.POINTER(C.c_int32)]
+        l.oracle_sw_score_blocked.restype = C.c_int32
+        l.oracle_sw_score_blocked.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64] + [C.c_int32] * 6
         l.oracle_sw_file.restype = C.c_int64
         l.oracle_sw_file.argtypes = [C.c_char_p, C.c_int32, C.c_void_p, C.c_int64, C.POINTER(C.c_int32)]
         l.oracle_pairhmm_prob.restype = C.c_double
@@ -48,6 +51,11 @@ def sw_score(a: bytes, b: bytes, scoring=(1, -1, -3, -1), want_corner: bool = Fa
     corner = C.c_int32(0)
     s = lib().oracle_sw_score(a, len(a), b, len(b), *scoring, C.byref(corner))
     return (int(s), int(corner.value)) if want_corner else int(s)
+
+
+def sw_score_blocked(a: bytes, b: bytes, scoring=(1, -1, -3, -1), tile: int = 4096, threads: int = 0) -> int:
+    """oracle_sw_score_blocked: the same recurrence, tile by tile on several host threads (long pairs)."""
+    return int(lib().oracle_sw_score_blocked(a, len(a), b, len(b), *scoring, int(tile), int(threads)))
 
 
 def sw_scores_flat(buf: np.ndarray, off: np.ndarray, ln: np.ndarray, scoring=(1, -1, -3, -1)) -> np.ndarray:

@@ -30,6 +30,13 @@ int32_t oracle_sw_score(const uint8_t *a, int32_t la, const uint8_t *b, int32_t 
                         int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend,
                         int32_t *corner_out);
 
+/* The same recurrence evaluated tile by tile on `threads` host threads (sw_blocked.c; pthreads, threads <= 0:
+ * one per online core): what makes a 1 Mbp x 1 Mbp expected score (BASELINE configs[4]) computable.
+ * Pinned to oracle_sw_score() by tests/test_oracle.py.  tile <= 0 picks 4096. */
+int32_t oracle_sw_score_blocked(const uint8_t *a, int64_t la, const uint8_t *b, int64_t lb,
+                                int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend,
+                                int32_t tile, int32_t threads);
+
 /* File-level restatement of antidiagonalSmithWaterman.c:205-227, 348 (header = number of LINES to
  * consume, fgets into a `line_buf`-byte buffer so longer lines split, trailing '\n' kept as a
  * symbol, EOF mid-pair stops).  line_buf = 1000 reproduces the unmodified program.
