@@ -26,7 +26,8 @@ SYMBOLS = [
     "sw_score_batch", "sw_score_batch_flat", "sw_score_batch_device", "sw_score_file_image",
     "pairhmm_forward_batch", "pairhmm_forward_batches_flat", "pairhmm_forward_batches_device",
     "pairhmm_forward_file_image",
-    "agx_pairhmm_set_gatk_mode", "agx_pairhmm_set_force_fp64",
+    "agx_pairhmm_set_gatk_mode", "agx_pairhmm_set_force_fp64", "agx_pairhmm_rescue_count",
+    "sw_score_shards_device", "pairhmm_forward_shards_device",
 ]
 
 # the reference's scoring constants, antidiagonalSmithWaterman.c:40-43
@@ -90,6 +91,12 @@ def load_library() -> C.CDLL:
         C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
         C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p,
         C.c_void_p]
+    lib.agx_pairhmm_rescue_count.argtypes = [C.c_int32]
+    lib.agx_pairhmm_rescue_count.restype = C.c_int64
+    lib.sw_score_shards_device.argtypes = [C.c_void_p, C.c_int32] + [C.c_int32] * 4
+    lib.sw_score_shards_device.restype = C.c_int
+    lib.pairhmm_forward_shards_device.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+    lib.pairhmm_forward_shards_device.restype = C.c_int
     lib.agx_pairhmm_set_gatk_mode.argtypes = [C.c_int32]
     lib.agx_pairhmm_set_force_fp64.argtypes = [C.c_int32]
     for name in ("agx_init", "agx_init_devices", "sw_score_batch", "sw_score_batch_flat",
@@ -149,8 +156,38 @@ def profile_ms(device: int, which: int) -> float:
     return float(load_library().agx_profile_ms(int(device), int(which)))
 
 
-def set_pairhmm_gatk_mode(on: bool) -> None:
-    _check(load_library().agx_pairhmm_set_gatk_mode(1 if on else 0))
+def set_pairhmm_gatk_mode(on) -> None:
+    """0 / False: the reference's priors; 1 / True: mismatch prior Qr/3; 3: that plus GATK's base-quality floor 6"""
+    _check(load_library().agx_pairhmm_set_gatk_mode(int(on)))
+
+
+def pairhmm_rescue_count(device: int) -> int:
+    return int(load_library().agx_pairhmm_rescue_count(int(device)))
+
+
+class SwShard(C.Structure):
+    _fields_ = [("device", C.c_int32), ("d_seqs", C.c_void_p), ("seqs_bytes", C.c_int64), ("d_off", C.c_void_p),
+                ("d_len", C.c_void_p), ("n_pairs", C.c_int64), ("d_scores_out", C.c_void_p)]
+
+
+class HmmShard(C.Structure):
+    _fields_ = [("device", C.c_int32), ("d_buf", C.c_void_p), ("buf_bytes", C.c_int64), ("d_read_field_off", C.c_void_p),
+                ("d_read_len", C.c_void_p), ("d_read_batch", C.c_void_p), ("d_read_out_off", C.c_void_p),
+                ("n_reads", C.c_int64), ("d_hap_off", C.c_void_p), ("d_hap_len", C.c_void_p), ("n_haps", C.c_int64),
+                ("d_batch_hap_start", C.c_void_p), ("n_batches", C.c_int64), ("n_pairs", C.c_int64),
+                ("d_log10_out", C.c_void_p)]
+
+
+def sw_score_shards_device(shards: Sequence[SwShard],
+                           scoring=(1, -1, -3, -1)) -> None:
+    """sw_score_shards_device: one device-resident shard per GPU, the library's in-process dispatcher."""
+    arr = (SwShard * len(shards))(*shards)
+    _check(load_library().sw_score_shards_device(arr, len(shards), *[int(s) for s in scoring]))
+
+
+def pairhmm_forward_shards_device(shards: Sequence[HmmShard], fp64_rescue: bool = True) -> None:
+    arr = (HmmShard * len(shards))(*shards)
+    _check(load_library().pairhmm_forward_shards_device(arr, len(shards), 1 if fp64_rescue else 0))
 
 
 def set_pairhmm_force_fp64(on: bool) -> None:

@@ -480,7 +480,7 @@ int hmm_shard(DeviceCtx &c, const HmmHost &h, int64_t r0, int64_t r1, double *ou
     v.n_reads = nr;
     v.n_haps = nh;
     v.n_batches = nb;
-    rc = hmm_run_device(c.hmm, v, nbytes, d_roo, n_out, g_gatk.load() != 0, g_force64.load() != 0, 1,
+    rc = hmm_run_device(c.hmm, v, nbytes, d_roo, n_out, g_gatk.load(), g_force64.load() != 0, 1,
                         c.d_out.as<double>(), st);
     if (rc != AGX_OK) return rc;
     AGX_CUDA(cudaMemcpyAsync(out + o0, c.d_out.p, (size_t)n_out * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -541,6 +541,37 @@ int hmm_flat_impl(HmmHost &h, double *out)
     return for_each_device(n_dev, [&](DeviceCtx &c, int k) {
         return hmm_shard(c, h, cuts[k], cuts[k + 1], out);
     });
+}
+
+// One host thread per shard, each on its own GPU and stream; returns the first failure.
+template <typename Shard, typename Fn> int for_each_shard(const Shard *shards, int32_t n_shards, Fn fn)
+{
+    if (n_shards < 0 || (n_shards > 0 && !shards)) return fail(AGX_EINVAL, "shards: null argument");
+    std::vector<DeviceCtx *> ctx(n_shards, nullptr);
+    for (int k = 0; k < n_shards; ++k) {
+        ctx[k] = ctx_for_device(shards[k].device);
+        if (!ctx[k]) return fail(AGX_ENODEVICE, "shards: device " + std::to_string(shards[k].device) + " was not passed to agx_init");
+        for (int j = 0; j < k; ++j)
+            if (ctx[j] == ctx[k]) return fail(AGX_EINVAL, "shards: device " + std::to_string(shards[k].device) + " appears twice");
+    }
+    std::vector<int> rcs(n_shards, AGX_OK);
+    std::vector<std::string> errs(n_shards);
+    auto body = [&](int k) {
+        if (cudaSetDevice(ctx[k]->device) != cudaSuccess) { rcs[k] = AGX_ECUDA; errs[k] = "cudaSetDevice failed"; return; }
+        rcs[k] = fn(*ctx[k], shards[k]);
+        if (rcs[k] == AGX_OK && cudaStreamSynchronize(ctx[k]->stream) != cudaSuccess) { rcs[k] = AGX_ECUDA; t_error = "stream synchronisation failed"; }
+        if (rcs[k] != AGX_OK) errs[k] = t_error;
+    };
+    if (n_shards == 1) {
+        body(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int k = 0; k < n_shards; ++k) th.emplace_back(body, k);
+        for (auto &t : th) t.join();
+    }
+    for (int k = 0; k < n_shards; ++k)
+        if (rcs[k] != AGX_OK) return fail(rcs[k], "gpu " + std::to_string(shards[k].device) + ": " + errs[k]);
+    return AGX_OK;
 }
 
 }  // namespace
@@ -632,12 +663,12 @@ double agx_profile_ms(int32_t device, int32_t which)
     case AGX_PROF_HMM_STREAM: return c->hmm.prof_stream.ms();
     case AGX_PROF_HMM_FP64: return c->hmm.prof_fp64.ms();
     case AGX_PROF_HMM_CLASSIFY: return c->hmm.prof_classify.ms();
-    case AGX_PROF_SW_LONG: return c->sw.prof_long.ms();
+    case AGX_PROF_SW_LONG: { const double v = c->sw.lng.prof.ms(); return v >= 0 ? v : c->sw.prof_long.ms(); }
     default: return -1.0;
     }
 }
 
-int agx_pairhmm_set_gatk_mode(int32_t on) { g_gatk.store(on ? 1 : 0); return AGX_OK; }
+int agx_pairhmm_set_gatk_mode(int32_t on) { g_gatk.store(on & 3); return AGX_OK; }
 int agx_pairhmm_set_force_fp64(int32_t on) { g_force64.store(on ? 1 : 0); return AGX_OK; }
 
 int sw_score_batch_flat(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *off, const int32_t *len,
@@ -963,6 +994,41 @@ int sw_score_batch_device(int32_t device, const uint8_t *d_seqs, int64_t seqs_by
                          d_scores_out, st);
 }
 
+int sw_score_shards_device(const agx_sw_shard *shards, int32_t n_shards, int32_t match, int32_t mismatch,
+                           int32_t gap_open, int32_t gap_extend)
+{
+    const SwScoring sc{match, mismatch, gap_open, gap_extend};
+    return for_each_shard(shards, n_shards, [&](DeviceCtx &c, const agx_sw_shard &s) -> int {
+        if (s.n_pairs < 0) return fail(AGX_EINVAL, "sw: n_pairs < 0");
+        if (s.n_pairs == 0) return AGX_OK;
+        if (!s.d_seqs || !s.d_off || !s.d_len || !s.d_scores_out) return fail(AGX_EINVAL, "sw: null argument");
+        return sw_run_device(c.sw, s.d_seqs, s.d_off, s.d_len, s.n_pairs, sc, s.d_scores_out, c.stream);
+    });
+}
+
+int pairhmm_forward_shards_device(const agx_hmm_shard *shards, int32_t n_shards, int32_t fp64_rescue)
+{
+    return for_each_shard(shards, n_shards, [&](DeviceCtx &c, const agx_hmm_shard &s) -> int {
+        if (s.n_reads < 0 || s.n_haps < 0 || s.n_batches < 0 || s.n_pairs < 0) return fail(AGX_EINVAL, "pairhmm: negative count");
+        if (s.n_reads == 0 || s.n_pairs == 0) return AGX_OK;
+        if (!s.d_buf || !s.d_read_field_off || !s.d_read_len || !s.d_read_batch || !s.d_read_out_off || !s.d_hap_off ||
+            !s.d_hap_len || !s.d_batch_hap_start || !s.d_log10_out)
+            return fail(AGX_EINVAL, "pairhmm: null argument");
+        HmmBatchView v;
+        v.buf = s.d_buf; v.read_field_off = s.d_read_field_off; v.read_len = s.d_read_len; v.read_batch = s.d_read_batch;
+        v.n_reads = s.n_reads; v.hap_off = s.d_hap_off; v.hap_len = s.d_hap_len; v.n_haps = s.n_haps;
+        v.batch_hap_start = s.d_batch_hap_start; v.n_batches = s.n_batches;
+        return hmm_run_device(c.hmm, v, s.buf_bytes, s.d_read_out_off, s.n_pairs, g_gatk.load(), g_force64.load() != 0,
+                              fp64_rescue != 0, s.d_log10_out, c.stream);
+    });
+}
+
+int64_t agx_pairhmm_rescue_count(int32_t device)
+{
+    DeviceCtx *c = ctx_for_device(device);
+    return c ? c->hmm.last_rescue : -1;
+}
+
 int pairhmm_forward_batches_flat(const uint8_t *buf, int64_t buf_bytes, const int64_t *read_field_off,
                                  const int32_t *read_len, int64_t n_reads, const int64_t *hap_off,
                                  const int32_t *hap_len, int64_t n_haps, const int64_t *batch_read_start,
@@ -1041,6 +1107,7 @@ int pairhmm_forward_file_image(const uint8_t *image, int64_t image_bytes, const 
     std::vector<int32_t> bp_all;
     int64_t out_done = 0, begin = 0, region = 0;
     int32_t inc = 0;
+    int32_t carry_nr = 0, carry_nh = 0;       // header counts of the batch before `begin` (antidiagsPairHMM.c:345-346)
     cudaStream_t prep = c.prep_stream;
     for (int64_t k = 0; k < n_seg; ++k) {
         if ((rc = upload_through(k + 1)) != AGX_OK) break;
@@ -1056,7 +1123,11 @@ int pairhmm_forward_file_image(const uint8_t *image, int64_t image_bytes, const 
         AGX_CUDA(cudaStreamWaitEvent(prep, c.seg_events[k], 0));
         if (region >= 2) AGX_CUDA(cudaStreamWaitEvent(prep, c.lane_done[li], 0));   // the lane's arrays are free again
         HmmParsed ps;
-        if ((rc = hmm_parse_device(*lane_parse[li], c.d_bytes.as<uint8_t>(), begin, end, image[end - 1], &ps, prep)) != AGX_OK) break;
+        if ((rc = hmm_parse_device(*lane_parse[li], c.d_bytes.as<uint8_t>(), begin, end, image[end - 1], &ps, prep, carry_nr,
+                                   carry_nh)) != AGX_OK)
+            break;
+        carry_nr = ps.last_nr;
+        carry_nh = ps.last_nh;
         const bool last_region = (k + 1 == n_seg);
         if (last_region) inc = ps.incomplete;
         if (ps.n_batches == 0) {
@@ -1094,7 +1165,7 @@ int pairhmm_forward_file_image(const uint8_t *image, int64_t image_bytes, const 
             v.n_haps = ps.n_haps;
             v.batch_hap_start = ps.batch_hap_start;
             v.n_batches = ps.n_batches;
-            rc = hmm_run_device(*lane_ws[li], v, image_bytes, ps.read_out_off, ps.n_out, g_gatk.load() != 0,
+            rc = hmm_run_device(*lane_ws[li], v, image_bytes, ps.read_out_off, ps.n_out, g_gatk.load(),
                                 g_force64.load() != 0, 2, c.d_out.as<double>() + out_done, lane_st[li], prep);
             if (rc != AGX_OK) break;
             out_done += ps.n_out;
@@ -1197,7 +1268,7 @@ int pairhmm_forward_batches_device(int32_t device, const uint8_t *d_buf, int64_t
     v.n_haps = n_haps;
     v.batch_hap_start = d_batch_hap_start;
     v.n_batches = n_batches;
-    return hmm_run_device(c->hmm, v, buf_bytes, d_read_out_off, n_pairs, g_gatk.load() != 0, g_force64.load() != 0,
+    return hmm_run_device(c->hmm, v, buf_bytes, d_read_out_off, n_pairs, g_gatk.load(), g_force64.load() != 0,
                           fp64_rescue != 0, d_log10_out, st);
 }
 

@@ -59,6 +59,7 @@ struct SwLongWorkspace {
     int64_t cap = 0;          // in int32 elements
     uint8_t *seq = nullptr;   // device copies of the two sequences (host entry point)
     int64_t cap_seq = 0;
+    ProfSpan prof;            // the long-alignment kernel of the last host-entry call on this GPU
 };
 int sw_long_device(SwLongWorkspace &ws, const uint8_t *d_a, int64_t la, const uint8_t *d_b, int64_t lb,
                    SwScoring sc, int32_t *d_best, cudaStream_t st);
@@ -116,6 +117,7 @@ struct HmmWorkspace {
     int64_t *rescue = nullptr;    // [cap_pairs] flat output indices needing FP64
     int64_t cap_reads = 0;
     int64_t cap_pairs = 0;
+    int64_t last_rescue = -1;     // pairs re-run in FP64 by the last call that read the count back
     double *d_lut = nullptr;      // 256-entry Phred+33 -> probability table (host libm pow)
     void *scratch = nullptr;      // boundary rows of the striped kernel
     int64_t cap_scratch = 0;
@@ -156,12 +158,15 @@ struct HmmParsed {            // device pointers into the workspace
     int64_t n_batches = 0, n_reads = 0, n_haps = 0, n_out = 0;
     int32_t incomplete = 0;   // the file ends inside a last batch (dropped): 2 = "Error reading haplotypes.", 1 = "... reads."
     int64_t next_begin = 0;   // where parsing resumes: the dropped batch's header, else the end of the region
+    int32_t last_nr = 0, last_nh = 0;   // header counts of the last complete batch (what a following header inherits)
     int64_t *read_field_off = nullptr, *read_out_off = nullptr, *hap_off = nullptr;
     int32_t *read_len = nullptr, *read_batch = nullptr, *hap_len = nullptr, *batch_pairs = nullptr;
     int64_t *batch_read_start = nullptr, *batch_hap_start = nullptr, *batch_out_start = nullptr;
 };
+// carry_nr / carry_nh: the counts of the batch parsed before `begin` (0, 0 at the start of a file): a header with
+// fewer than two integers keeps them, as the reference's sscanf() does (antidiagsPairHMM.c:345-346, :378)
 int hmm_parse_device(HmmParseWorkspace &ws, const uint8_t *d_img, int64_t begin, int64_t bytes, int last_byte,
-                     HmmParsed *out, cudaStream_t st);
+                     HmmParsed *out, cudaStream_t st, int32_t carry_nr = 0, int32_t carry_nh = 0);
 void hmm_parse_workspace_free(HmmParseWorkspace &ws);
 
 int hmm_workspace_reserve(HmmWorkspace &ws, int64_t n_reads, int64_t n_pairs, int64_t n_batches);
@@ -170,8 +175,9 @@ void hmm_workspace_free(HmmWorkspace &ws);
 // rescue: 0 = leave pairs FP32 cannot be trusted with as NaN, 1 = re-run them in FP64 (one more stream
 // synchronisation to size that launch), 2 = the same without the synchronisation (the FP64 kernel reads the
 // count on the device; it is launched even when there is nothing to do).
+// gatk_mode: 0 the reference's priors, bit 0 mismatch prior Qr/3, bit 1 base-quality floor 6 (see agx.h)
 int hmm_run_device(HmmWorkspace &ws, const HmmBatchView &v, int64_t buf_bytes, const int64_t *d_read_out_off,
-                   int64_t n_pairs, bool gatk_mode, bool force_fp64, int rescue, double *d_out,
+                   int64_t n_pairs, int gatk_mode, bool force_fp64, int rescue, double *d_out,
                    cudaStream_t st, cudaStream_t prep_st = nullptr);
 
 }  // namespace agx

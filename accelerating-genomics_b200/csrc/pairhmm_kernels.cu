@@ -196,6 +196,12 @@ struct __align__(16) HapInfo {
 
 constexpr int HMM_NSYM = 6;
 
+// base-quality character as the prior setup reads it: GATK mode with the floor reads qualities below 6 as 6
+__device__ __forceinline__ uint32_t base_qual(uint32_t ch, int gatk)
+{
+    return ((gatk & 2) && (int)(signed char)ch < 33 + 6) ? 33u + 6u : ch;
+}
+
 __device__ __forceinline__ uint32_t hap_symbol(uint32_t ch)
 {
     const uint32_t code = (ch >> 1) & 3u;                       // A 0, C 1, T 2, G 3
@@ -282,14 +288,14 @@ hmm_stream_kernel(HmmBatchView v, const int64_t *__restrict__ read_out_off,
                 // padding rows reproduce row 0: M = X = 0 and Y stays at its initial value
                 ca[jj] = cbx[jj] = cby[jj] = ccx[jj] = 0.f; cg[jj] = 1.f;
             } else {
-                const double Qr = lut[f_q[i]], Qi = lut[f_i[i]], Qd = lut[f_d[i]], Qg = lut[f_g[i]];
+                const double Qr = lut[base_qual(f_q[i], gatk)], Qi = lut[f_i[i]], Qd = lut[f_d[i]], Qg = lut[f_g[i]];
                 // previous row's Qi / Qd un-scale X' and Y' of the diagonal cell; row 0 is unscaled
                 const double Qi_up = (i > 0) ? lut[f_i[i - 1]] : 1.0;
                 const double Qd_up = (i > 0) ? lut[f_d[i - 1]] : 1.0;
                 const uint32_t base = f_b[i];
                 const double mm = 1.0 - (Qi + Qd), gm = 1.0 - Qg;
                 pm[jj] = (float)(1.0 - Qr);
-                px[jj] = (float)(gatk ? Qr / 3.0 : Qr);
+                px[jj] = (float)((gatk & 1) ? Qr / 3.0 : Qr);
                 rsym[jj] = (base == 'N') ? 4u : hap_symbol(base);   // 5: matches nothing but N
                 ca[jj] = (float)mm;
                 cbx[jj] = (float)(gm * Qi_up);
@@ -484,14 +490,14 @@ hmm_duo_kernel(HmmBatchView v, const int64_t *__restrict__ read_out_off, const i
                 const int i = t * K + jj - pad;      // 0-based read position of this row
                 float a = 0.f, bx = 0.f, by = 0.f, cx = 0.f, g = 1.f;   // padding rows reproduce row 0
                 if (i >= 0) {
-                    const double Qr = __ldg(lut + f_q[i]), Qi = __ldg(lut + f_i[i]), Qd = __ldg(lut + f_d[i]),
+                    const double Qr = __ldg(lut + base_qual(f_q[i], gatk)), Qi = __ldg(lut + f_i[i]), Qd = __ldg(lut + f_d[i]),
                                  Qg = __ldg(lut + f_g[i]);
                     const double Qi_up = (i > 0) ? __ldg(lut + f_i[i - 1]) : 1.0;
                     const double Qd_up = (i > 0) ? __ldg(lut + f_d[i - 1]) : 1.0;
                     const uint32_t base = f_b[i];
                     const double mm = 1.0 - (Qi + Qd), gm = 1.0 - Qg;
                     pm[h][jj] = (float)(1.0 - Qr);
-                    px[h][jj] = (float)(gatk ? Qr / 3.0 : Qr);
+                    px[h][jj] = (float)((gatk & 1) ? Qr / 3.0 : Qr);
                     rsym[h][jj] = (base == 'N') ? 4u : hap_symbol(base);
                     a = (float)mm;
                     bx = (float)(gm * Qi_up);
@@ -710,10 +716,10 @@ __device__ void hmm_striped_pair(const HmmBatchView &v, const double *lut, int32
                 rb[jj] = 0x100;
                 Y[jj] = init;
             } else {
-                const double Qr = lut[f_q[i]], Qi = lut[f_i[i]], Qd = lut[f_d[i]], Qg = lut[f_g[i]];
+                const double Qr = lut[base_qual(f_q[i], gatk)], Qi = lut[f_i[i]], Qd = lut[f_d[i]], Qg = lut[f_g[i]];
                 const int32_t base = f_b[i];
                 pm[jj] = (T)(1 - Qr);
-                px[jj] = (base == 'N') ? pm[jj] : (T)(gatk ? Qr / 3 : Qr);
+                px[jj] = (base == 'N') ? pm[jj] : (T)((gatk & 1) ? Qr / 3 : Qr);
                 cmm[jj] = (T)(1 - (Qi + Qd));
                 cgm[jj] = (T)(1 - Qg);
                 cqi[jj] = (T)Qi; cqd[jj] = (T)Qd; cqg[jj] = (T)Qg;
@@ -935,10 +941,11 @@ static int hmm_scratch_reserve(HmmWorkspace &ws, int64_t bytes)
 }
 
 int hmm_run_device(HmmWorkspace &ws, const HmmBatchView &v, int64_t buf_bytes, const int64_t *d_read_out_off,
-                   int64_t n_pairs, bool gatk_mode, bool force_fp64, int do_rescue, double *d_out,
+                   int64_t n_pairs, int gatk_mode, bool force_fp64, int do_rescue, double *d_out,
                    cudaStream_t st, cudaStream_t prep_st)
 {
     if (v.n_reads == 0 || n_pairs == 0) return AGX_OK;
+    ws.last_rescue = -1;
     if (v.n_reads > (int64_t)1 << 30 || v.n_haps > (int64_t)1 << 30)
         return fail(AGX_ERANGE, "pairhmm: more than 2^30 reads or haplotypes in one call");
     int rc = hmm_workspace_reserve(ws, v.n_reads, n_pairs, v.n_batches);
@@ -986,7 +993,7 @@ int hmm_run_device(HmmWorkspace &ws, const HmmBatchView &v, int64_t buf_bytes, c
     for (int c = 0; c < HMM_N_CLASSES; ++c) counts[c] = ws.h_counters[c];
     for (int c = 0; c < HMM_MAX_K; ++c) pair_counts[c] = paired ? ws.h_counters[HCNT_PAIRS + c] : 0;
     const int32_t max_hap = ws.h_counters[HCNT_MAXHAP];
-    const int gatk = gatk_mode ? 1 : 0;
+    const int gatk = gatk_mode & 3;     // bit 0: mismatch prior Qr/3, bit 1: base-quality floor 6 (GATK semantics)
     int2 *rescue = reinterpret_cast<int2 *>(ws.rescue);
     int32_t *rescue_count = ws.counters + HCNT_RESCUE;
 
@@ -1087,6 +1094,7 @@ int hmm_run_device(HmmWorkspace &ws, const HmmBatchView &v, int64_t buf_bytes, c
                                      cudaMemcpyDeviceToHost, st));
             AGX_CUDA(cudaStreamSynchronize(st));
             n_rescue = ws.h_counters[HCNT_RESCUE];
+            ws.last_rescue = n_rescue;
             if (n_rescue == 0) return AGX_OK;
         } else {
             n_rescue = (int32_t)std::min<int64_t>(n_pairs, (int64_t)sms * 4);   // grid only; the count stays on the device

@@ -37,6 +37,8 @@ enum {
     PI_ERROR = 7,        // validation: 1 read length, 2 haplotype length, 3 field outside line, 4 long line, 5 too many pairs
     PI_ERROR_AT = 8,     // line of the first validation error
     PI_NEXT_BEGIN = 9,   // byte offset of the header of the dropped (incomplete) last batch, else the region end
+    PI_LAST_NR = 10,     // header counts of the last complete batch: what a header with fewer than two integers
+    PI_LAST_NH = 11,     // right after it inherits
     PI_WORDS = 12
 };
 
@@ -53,9 +55,11 @@ __device__ __forceinline__ LineSpan line_span(const int64_t *nl_pos, int64_t n_n
 }
 
 // sscanf(line, "%d %d", &a, &b) with a = b = 0 beforehand (antidiagsPairHMM.c:375-376)
+// sscanf(line, "%d %d", &num_read, &num_haplotypes) (antidiagsPairHMM.c:378): a field that does not parse
+// leaves its variable as it was -- the reference declares both once, outside the batch loop (:345-346), so a
+// header that holds fewer than two integers keeps the previous batch's count(s).  a / b come in holding those.
 __device__ void scan_two_ints(const uint8_t *img, LineSpan sp, int32_t &a, int32_t &b)
 {
-    a = b = 0;
     int64_t p = sp.s;
     for (int f = 0; f < 2; ++f) {
         while (p < sp.e && (is_blank(img[p]) || img[p] == '\r' || img[p] == '\v' || img[p] == '\f')) ++p;
@@ -91,14 +95,21 @@ hmm_header_flag_kernel(const uint8_t *__restrict__ img, const int64_t *__restric
 __global__ void __launch_bounds__(256)
 hmm_headers_kernel(const uint8_t *__restrict__ img, const int64_t *__restrict__ nl_pos, int64_t n_nl, Bounds end,
                    int64_t n_lines, const int32_t *__restrict__ flag, const int64_t *__restrict__ rank,
-                   int32_t *__restrict__ hdr_line, int32_t *__restrict__ nr, int32_t *__restrict__ nh,
+                   const uint64_t *__restrict__ walked, int32_t *__restrict__ hdr_line, int32_t *__restrict__ nr, int32_t *__restrict__ nh,
                    int32_t *__restrict__ npairs, int64_t *__restrict__ info)
 {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_lines || !flag[k]) return;
     const int64_t b = rank[k];
-    int32_t a, c;
-    scan_two_ints(img, line_span(nl_pos, n_nl, end, k), a, c);
+    int32_t a = 0, c = 0;
+    if (walked) {
+        // the serial walk already resolved this header (counts carried over from the batch before included)
+        a = (int32_t)(uint32_t)walked[k];
+        c = (int32_t)(uint32_t)(walked[k] >> 32);
+    } else {
+        // strict-shape headers always hold two integers: nothing to carry
+        scan_two_ints(img, line_span(nl_pos, n_nl, end, k), a, c);
+    }
     if (a < 0) a = 0;          // for (i = 0; i < num_read; i++) runs zero times
     if (c < 0) c = 0;
     hdr_line[b] = (int32_t)k;
@@ -130,17 +141,18 @@ hmm_check_chain_kernel(const int32_t *__restrict__ hdr_line, const int32_t *__re
 
 // the reference's own walk, one thread: flags the lines it would read as headers
 __global__ void hmm_walk_kernel(const uint8_t *__restrict__ img, const int64_t *__restrict__ nl_pos, int64_t n_nl,
-                                Bounds end, int64_t n_lines, int32_t *__restrict__ flag, int64_t *__restrict__ info)
+                                Bounds end, int64_t n_lines, int32_t carry_nr, int32_t carry_nh,
+                                int32_t *__restrict__ flag, uint64_t *__restrict__ walked, int64_t *__restrict__ info)
 {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     int64_t line = 0;
     info[PI_INCOMPLETE] = 0;
+    int32_t num_read = carry_nr, num_haplotypes = carry_nh;      // live across batches, as in the reference
     while (line < n_lines) {
-        int32_t a, c;
-        scan_two_ints(img, line_span(nl_pos, n_nl, end, line), a, c);
-        if (a < 0) a = 0;
-        if (c < 0) c = 0;
+        scan_two_ints(img, line_span(nl_pos, n_nl, end, line), num_read, num_haplotypes);
+        const int32_t a = num_read < 0 ? 0 : num_read, c = num_haplotypes < 0 ? 0 : num_haplotypes;
         flag[line] = 1;
+        walked[line] = (uint64_t)(uint32_t)num_read | ((uint64_t)(uint32_t)num_haplotypes << 32);
         if (line + 1 + a + c > n_lines) { info[PI_INCOMPLETE] = c > 0 ? 2 : 1; break; }
         line += 1 + (int64_t)a + c;
     }
@@ -168,6 +180,7 @@ __global__ void hmm_totals_kernel(const int64_t *__restrict__ nl_pos, Bounds bd,
     info[PI_READS] = r;
     info[PI_HAPS] = h;
     info[PI_OUT] = o;
+    if (nb > 0) { info[PI_LAST_NR] = nr[nb - 1]; info[PI_LAST_NH] = nh[nb - 1]; }
     if (nb >= 0) { brs[nb] = r; bhs[nb] = h; bos[nb] = o; }
 }
 
@@ -257,7 +270,7 @@ void hmm_parse_workspace_free(HmmParseWorkspace &ws)
 // dropped and reported through out->incomplete / out->next_begin, so a caller that holds only a prefix of the
 // file can parse it region by region.  Synchronises `st` four times.
 int hmm_parse_device(HmmParseWorkspace &ws, const uint8_t *d_img, int64_t begin, int64_t bytes, int last_byte,
-                     HmmParsed *out, cudaStream_t st)
+                     HmmParsed *out, cudaStream_t st, int32_t carry_nr, int32_t carry_nh)
 {
     *out = HmmParsed();
     out->next_begin = bytes;
@@ -276,7 +289,7 @@ int hmm_parse_device(HmmParseWorkspace &ws, const uint8_t *d_img, int64_t begin,
     // per-line scratch: flag, rank; scan temporaries; info block
     const int64_t scan_tmp = device_scan_tmp_elems(n_lines);
     const int64_t sz_flag = align(n_lines * 4), sz_rank = align(n_lines * 8), sz_tmp = align(scan_tmp * 8);
-    const int64_t need = sz_flag + sz_rank + 4 * sz_tmp + 2 * 256;
+    const int64_t need = sz_flag + 2 * sz_rank + 4 * sz_tmp + 2 * 256;       // + the walk's per-line counts
     if (need > ws.cap) {
         if (ws.buf) cudaFree(ws.buf);
         ws.buf = nullptr; ws.cap = 0;
@@ -288,6 +301,8 @@ int hmm_parse_device(HmmParseWorkspace &ws, const uint8_t *d_img, int64_t begin,
     int64_t *rank = reinterpret_cast<int64_t *>(wb + sz_flag);
     int64_t *tmp = reinterpret_cast<int64_t *>(wb + sz_flag + sz_rank);
     int64_t *info = reinterpret_cast<int64_t *>(wb + sz_flag + sz_rank + 4 * sz_tmp);
+    uint64_t *walked = reinterpret_cast<uint64_t *>(wb + sz_flag + sz_rank + 4 * sz_tmp + 2 * 256);
+    bool use_walk = false;
     int64_t *tot = info + PI_WORDS;                      // three scan totals
     AGX_CUDA(cudaMemsetAsync(info, 0, 256 + 64, st));
 
@@ -320,8 +335,8 @@ int hmm_parse_device(HmmParseWorkspace &ws, const uint8_t *d_img, int64_t begin,
         out->batch_hap_start = reinterpret_cast<int64_t *>(tb + 5 * sz_i32 + sz_i64);
         out->batch_out_start = reinterpret_cast<int64_t *>(tb + 5 * sz_i32 + 2 * sz_i64);
         if (H > 0) {
-            hmm_headers_kernel<<<lblocks, 256, 0, st>>>(d_img, nl_pos, n_nl, bd, n_lines, flag, rank, hdr_line, nr,
-                                                        nh, npairs, info);
+            hmm_headers_kernel<<<lblocks, 256, 0, st>>>(d_img, nl_pos, n_nl, bd, n_lines, flag, rank,
+                                                        use_walk ? walked : nullptr, hdr_line, nr, nh, npairs, info);
             count_launch();
         }
         if (attempt == 0) {
@@ -334,8 +349,9 @@ int hmm_parse_device(HmmParseWorkspace &ws, const uint8_t *d_img, int64_t begin,
             // not a tiling of header-shaped lines: follow the reference's walk, then redo scan + headers
             AGX_CUDA(cudaMemsetAsync(flag, 0, (size_t)n_lines * sizeof(int32_t), st));
             AGX_CUDA(cudaMemsetAsync(info, 0, PI_WORDS * sizeof(int64_t), st));
-            hmm_walk_kernel<<<1, 32, 0, st>>>(d_img, nl_pos, n_nl, bd, n_lines, flag, info);
+            hmm_walk_kernel<<<1, 32, 0, st>>>(d_img, nl_pos, n_nl, bd, n_lines, carry_nr, carry_nh, flag, walked, info);
             count_launch();
+            use_walk = true;
         }
     }
     AGX_CUDA(cudaGetLastError());
@@ -351,6 +367,9 @@ int hmm_parse_device(HmmParseWorkspace &ws, const uint8_t *d_img, int64_t begin,
     if (ws.h_info[PI_ERROR] == 5) return fail(AGX_ERANGE, "pairhmm: a batch holds more than 2^31 pairs");
     out->incomplete = (int32_t)ws.h_info[PI_INCOMPLETE];
     out->next_begin = ws.h_info[PI_NEXT_BEGIN];
+    out->last_nr = carry_nr;
+    out->last_nh = carry_nh;
+    if (ws.h_info[PI_BATCHES] > 0) { out->last_nr = (int32_t)ws.h_info[PI_LAST_NR]; out->last_nh = (int32_t)ws.h_info[PI_LAST_NH]; }
     out->n_batches = ws.h_info[PI_BATCHES];
     out->n_reads = ws.h_info[PI_READS];
     out->n_haps = ws.h_info[PI_HAPS];

@@ -659,6 +659,81 @@ template <int PACKED, int K> void run_hmm_loop(int sms, int warps_per_sm, const 
     CK(cudaFree(d_codes));
 }
 
+// ---- issue rate of ONE warp (and of 2, 4, 8) per SM sub-partition ---------------------------------------
+// CH independent chains per thread, every operand in its own register (no operand-reuse cache, no uniform
+// register): what a lone warp of the long-alignment kernel can get out of a pipe.
+enum IssueOp { IS_VIADDMNMX, IS_VIMNMX3, IS_IMAD, IS_IDP4A, IS_CELL, IS_COUNT };
+template <int IOP, int CH>
+__global__ void __launch_bounds__(256) issue_kernel(uint32_t *out, uint32_t seed, int iters)
+{
+    int32_t x[CH], y[CH], z[CH];
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) { x[i] = (int32_t)(seed * (tid + i + 1)); y[i] = (int32_t)(seed + tid * 7 + i); z[i] = (int32_t)(seed ^ (tid + 3 * i)); }
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                if constexpr (IOP == IS_VIADDMNMX) x[i] = __viaddmax_s32(x[i], y[i], z[i]);
+                else if constexpr (IOP == IS_VIMNMX3) x[i] = __vimax3_s32_relu(x[i], y[i], z[i]) - 1;
+                else if constexpr (IOP == IS_IMAD) asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(y[i]), "r"(z[i]));
+                else if constexpr (IOP == IS_IDP4A) x[i] = __dp4a(y[i], z[i], x[i]);
+                else {
+                    // the lean symbol-coded cell: x = E chain, y = H + goe above, z = F
+                    const int32_t d = __dp4a(z[i], 0x100, y[i]);
+                    x[i] = __viaddmax_s32(x[i], -1, y[i]);
+                    z[i] = __viaddmax_s32(z[i], -1, y[i]);
+                    int32_t g;
+                    const int32_t h = __vimax3_s32_relu(x[i], z[i], d);
+                    asm volatile("mad.lo.s32 %0, %1, %2, %3;" : "=r"(g) : "r"(h), "r"((int32_t)(seed | 1)), "r"(-4));
+                    y[i] = g;
+                }
+            }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) acc ^= (uint32_t)(x[i] ^ y[i] ^ z[i]);
+    out[tid] = acc;
+}
+template <int IOP, int CH> void run_issue(int sms, uint32_t *d_out, int warps_per_smsp, const char *name, double ops_per_step)
+{
+    const int iters = 4096;
+    const int threads = warps_per_smsp >= 2 ? 256 : 128;
+    const int bps = warps_per_smsp >= 2 ? warps_per_smsp / 2 : 1;
+    const int blocks = sms * bps;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    issue_kernel<IOP, CH><<<blocks, threads>>>(d_out, 3u, iters);
+    CK(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(e0));
+        issue_kernel<IOP, CH><<<blocks, threads>>>(d_out, 5u + rep, iters);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    const double warp_instr_per_smsp = (double)iters * 8 * CH * ops_per_step * warps_per_smsp;
+    printf("{\"issue_test\": \"%s\", \"chains\": %d, \"warps_per_smsp\": %d, \"ms\": %.4f, "
+           "\"clk_per_warp_instr_at_1965MHz\": %.3f}\n",
+           name, CH, warps_per_smsp, best, best * 1e-3 * 1.965e9 / warp_instr_per_smsp);
+    fflush(stdout);
+}
+template <int IOP> void run_issue_all(int sms, uint32_t *d_out, const char *name, double ops)
+{
+    for (int w : {1, 2, 4, 8}) {
+        run_issue<IOP, 1>(sms, d_out, w, name, ops);
+        run_issue<IOP, 2>(sms, d_out, w, name, ops);
+        run_issue<IOP, 4>(sms, d_out, w, name, ops);
+        run_issue<IOP, 8>(sms, d_out, w, name, ops);
+    }
+}
+
 template <int OP> void run_all(int sms, uint32_t *d_out, long long *d_cyc, int bps)
 {
     if constexpr (OP < OP_COUNT) {
@@ -685,6 +760,14 @@ int main(int argc, char **argv)
     nv.open(dev);
     nv.start();
     struct Fin { Nvml &n; ~Fin() { n.finish(); } } fin{nv};
+    if (argc > 2 && !strcmp(argv[2], "issue")) {
+        run_issue_all<IS_VIADDMNMX>(sms, d_out, "VIADDMNMX.S32 (3 registers)", 1);
+        run_issue_all<IS_VIMNMX3>(sms, d_out, "VIMNMX3.S32.RELU + IADD (3 registers)", 2);
+        run_issue_all<IS_IMAD>(sms, d_out, "IMAD (3 registers)", 1);
+        run_issue_all<IS_IDP4A>(sms, d_out, "IDP.4A (3 registers)", 1);
+        run_issue_all<IS_CELL>(sms, d_out, "lean coded cell: IDP + 2 VIADDMNMX + VIMNMX3.RELU + IMAD", 5);
+        return 0;
+    }
     if (argc > 2 && !strcmp(argv[2], "dp4a")) {
         run<OP_PRMT>(sms, d_out, d_cyc, bps);
         run<OP_IMAD>(sms, d_out, d_cyc, bps);

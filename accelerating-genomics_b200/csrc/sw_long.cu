@@ -74,34 +74,37 @@ constexpr int LONG_UNROLL = AGX_LONG_UNROLL;
 // accesses at the narrowest scope that covers writer and reader -- .gpu inside one GPU, .sys across NVLink.
 // (ld/st.volatile and plain .cg stores were measured too: no difference.)  Requesting the next block's entries
 // a block ahead was also tried: it needs a two-block start-up slack and came out 5-10 % slower.
+// An entry is two 64-bit halves, {H+goe, tag} and {E, tag}, read and written as .v2.b64: the memory model makes each
+// 64-bit ELEMENT of a vector access single-copy atomic, so a value can never be seen with another write's tag
+// (a .v4.s32 access only guarantees that per 32-bit element), also for peer stores over NVLink.
 __device__ __forceinline__ int4 ld_entry(const int4 *p, bool sys)
 {
-    int4 v;
+    unsigned long long a, b;
     if (sys)
-        asm volatile("ld.relaxed.sys.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+        asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
     else
-        asm volatile("ld.relaxed.gpu.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
+        asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+    return make_int4((int32_t)(uint32_t)a, (int32_t)(uint32_t)(a >> 32), (int32_t)(uint32_t)b, (int32_t)(uint32_t)(b >> 32));
 }
 __device__ __forceinline__ void st_entry(int4 *p, int4 v, bool sys)
 {
+    const unsigned long long a = (unsigned long long)(uint32_t)v.x | ((unsigned long long)(uint32_t)v.y << 32);
+    const unsigned long long b = (unsigned long long)(uint32_t)v.z | ((unsigned long long)(uint32_t)v.w << 32);
     if (sys)
-        asm volatile("st.relaxed.sys.global.v4.s32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        asm volatile("st.relaxed.sys.global.v2.b64 [%0], {%1, %2};" :: "l"(p), "l"(a), "l"(b) : "memory");
     else
-        asm volatile("st.relaxed.gpu.global.v4.s32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" :: "l"(p), "l"(a), "l"(b) : "memory");
 }
 
-// CODED: both sequences use at most 7 distinct bytes.  Columns carry a PRMT selector instead of their byte,
-// rows an 8-byte table (substitution score - goe for each symbol code), and the substitution score of a cell
-// is ONE PRMT (sign-extending byte select) instead of ISETP + SEL; the two additions of a cell go to the FMA
-// pipe as IMADs.  ALU-pipe instructions per cell: 7.5 -> 4.5 (lean chain), 8.5 -> 5.5 (short chain).
-template <int K, bool SHORT, bool CODED>
+// Raw-byte kernel: sequences with more than 7 distinct bytes (or scores that do not fit a byte table).  One row per
+// step, substitution score by ISETP + SEL: 7.5 (lean chain) / 8.5 (short chain) ALU-pipe instructions per cell.
+// Sequences with at most 7 distinct bytes -- all DNA -- take the symbol-coded sw_longr_kernel below.
+template <int K, bool SHORT>
 __global__ void __launch_bounds__(LONG_WARPS * 32)
 sw_long_kernel(LongArgs g)
 {
     constexpr int W = 32 * K;
-    __shared__ int32_t r_byte[LONG_WARPS][LONG_RING];      // row byte, or the low half of the row's score table
-    __shared__ int32_t r_hi[CODED ? LONG_WARPS : 1][CODED ? LONG_RING : 1];
+    __shared__ int32_t r_byte[LONG_WARPS][LONG_RING];      // row byte
     __shared__ int32_t r_g[LONG_WARPS][LONG_RING];
     __shared__ int32_t r_e[LONG_WARPS][LONG_RING];
     __shared__ int2 stage[LONG_WARPS][32];      // boundary of the rows finished in the current block
@@ -116,29 +119,13 @@ sw_long_kernel(LongArgs g)
     const int32_t lb = g.lb;
     const int n_stripes = (g.la + W - 1) / W;
     int32_t bestg = goe;          // running max of H + goe
-    const int32_t one = g.one;
-    const uint32_t xb4 = (uint32_t)(uint8_t)(int8_t)sub_mis * 0x01010101u;          // every symbol: mismatch
-    const uint32_t mxor = (uint32_t)(uint8_t)(int8_t)sub_mis ^ (uint32_t)(uint8_t)(int8_t)sub_match;
-    // row symbol -> its 8-byte score table (byte k = score against symbol code k); code 7 never matches
-    auto row_table = [&](int32_t r, uint32_t &lo, uint32_t &hi) {
-        lo = xb4; hi = xb4;
-        if (r < lb) {
-            const uint32_t c = g.lut[g.b[r]];
-            if (c < 4) lo ^= mxor << (8 * c); else hi ^= mxor << (8 * (c - 4));
-        }
-    };
 
     for (int st = warp; st < n_stripes; st += n_warps) {
         const int c0 = st * W + lane * K;
         int32_t acol[K], Gp[K], F[K];
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-            if constexpr (CODED) {
-                const uint32_t c = (c0 + j < g.la) ? (uint32_t)g.lut[g.a[c0 + j]] : 7u;
-                acol[j] = (int32_t)(c | ((8u | c) * 0x1110u));              // byte c, sign-extended to 32 bits
-            } else {
-                acol[j] = (c0 + j < g.la) ? (int32_t)g.a[c0 + j] : 0x100;
-            }
+            acol[j] = (c0 + j < g.la) ? (int32_t)g.a[c0 + j] : 0x100;        // 0x100 never equals a byte
             Gp[j] = goe;
             F[j] = goe;
         }
@@ -153,11 +140,9 @@ sw_long_kernel(LongArgs g)
 
         // inputs of the first 32 rows
         int32_t nb = 0x200;
-        uint32_t nhi = 0;
         int4 nx = make_int4(goe, gst - 1, goe, gst - 1);
-        if constexpr (CODED) { uint32_t lo; row_table(lane, lo, nhi); nb = (int32_t)lo; }
         if (lane < lb) {
-            if constexpr (!CODED) nb = g.b[lane];
+            nb = g.b[lane];
             if (!left_edge) nx = ld_entry(g.bnd + lane, in_remote);
         }
         for (int s0 = 0; s0 < S; s0 += 32) {
@@ -173,7 +158,6 @@ sw_long_kernel(LongArgs g)
                     }
                 }
                 r_byte[wib][r & (LONG_RING - 1)] = nb;
-                if constexpr (CODED) r_hi[wib][r & (LONG_RING - 1)] = (int32_t)nhi;
                 r_g[wib][r & (LONG_RING - 1)] = nx.x;
                 r_e[wib][r & (LONG_RING - 1)] = nx.z;
             }
@@ -183,9 +167,7 @@ sw_long_kernel(LongArgs g)
             for (int u = 0; u < send; ++u) {
                 const int s = s0 + u;
                 const int slot = (s - lane) & (LONG_RING - 1);
-                int32_t rb = (s - lane >= 0) ? r_byte[wib][slot] : (CODED ? (int32_t)xb4 : 0x200);
-                uint32_t rhi = xb4;
-                if constexpr (CODED) { if (s - lane >= 0) rhi = (uint32_t)r_hi[wib][slot]; }
+                const int32_t rb = (s - lane >= 0) ? r_byte[wib][slot] : 0x200;
                 int32_t g_in = __shfl_up_sync(0xffffffffu, g_out, 1);
                 int32_t e = __shfl_up_sync(0xffffffffu, e_out, 1);
                 if (lane == 0) { g_in = r_g[wib][slot]; e = r_e[wib][slot]; }
@@ -201,12 +183,9 @@ sw_long_kernel(LongArgs g)
                     int32_t tg_prev = g_in;
 #pragma unroll
                     for (int j = 0; j < K; ++j) {
-                        int32_t d, tg;
-                        if constexpr (CODED) d = add_fma(gdiag, prmt_s((uint32_t)rb, rhi, (uint32_t)acol[j]), one);
-                        else d = gdiag + ((acol[j] == rb) ? sub_match : sub_mis);
+                        const int32_t d = gdiag + ((acol[j] == rb) ? sub_match : sub_mis);
                         F[j] = __viaddmax_s32(F[j], ext, Gp[j]);
-                        if constexpr (CODED) tg = add_fma(__vimax_s32_relu(F[j], d), goe, one);
-                        else tg = __vimax_s32_relu(F[j], d) + goe;                 // T[j] + goe
+                        const int32_t tg = __vimax_s32_relu(F[j], d) + goe;        // T[j] + goe
                         e = __viaddmax_s32(e, ext, tg_prev);                       // E[i][j]
                         gdiag = Gp[j];
                         gleft = __viaddmax_s32(e, goe, tg);                        // H[i][j] + goe
@@ -218,14 +197,12 @@ sw_long_kernel(LongArgs g)
                 } else {
 #pragma unroll
                     for (int j = 0; j < K; ++j) {
-                        int32_t d;
-                        if constexpr (CODED) d = add_fma(gdiag, prmt_s((uint32_t)rb, rhi, (uint32_t)acol[j]), one);
-                        else d = gdiag + ((acol[j] == rb) ? sub_match : sub_mis);
+                        const int32_t d = gdiag + ((acol[j] == rb) ? sub_match : sub_mis);
                         e = __viaddmax_s32(e, ext, gleft);
                         F[j] = __viaddmax_s32(F[j], ext, Gp[j]);
                         const int32_t hcell = __vimax3_s32_relu(e, F[j], d);
                         gdiag = Gp[j];
-                        if constexpr (CODED) gleft = add_fma(hcell, goe, one); else gleft = hcell + goe;
+                        gleft = hcell + goe;
                         Gp[j] = gleft;
                         if (j & 1) bestg = __vimax3_s32(bestg, Gp[j - 1], gleft);
                         else if (j == K - 1) bestg = max(bestg, gleft);
@@ -241,9 +218,8 @@ sw_long_kernel(LongArgs g)
                 const int r = s0 + 32 + lane;
                 nb = 0x200;
                 nx = make_int4(goe, gst - 1, goe, gst - 1);
-                if constexpr (CODED) { uint32_t lo; row_table(r, lo, nhi); nb = (int32_t)lo; }
                 if (r < lb) {
-                    if constexpr (!CODED) nb = g.b[r];
+                    nb = g.b[r];
                     if (!left_edge) nx = ld_entry(g.bnd + r, in_remote);
                 }
             }
@@ -254,194 +230,6 @@ sw_long_kernel(LongArgs g)
                 if (lane < send && r >= 0 && r < lb) {
                     const int2 ge = stage[wib][lane];
                     st_entry(out_bnd + r, make_int4(ge.x, gst, ge.y, gst), out_remote);
-                }
-                __syncwarp();
-            }
-        }
-        __syncwarp();
-    }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) bestg = max(bestg, __shfl_xor_sync(0xffffffffu, bestg, m));
-    const int32_t best = bestg - goe;
-    if (lane == 0 && best > 0) atomicMax(g.best, best);
-}
-
-// Two rows per step (symbol-coded cells only).  With one warp per scheduler a row step is a latency chain --
-// shuffle in, K dependent cells, shuffle out: ~200 clocks whatever K is -- so lane t advances TWO rows per
-// step (rows 2(s-t), 2(s-t)+1): the shuffle latency and the loop are paid once per two rows, and the two
-// rows' chains run one column apart, which doubles the instruction-level parallelism a lone warp offers.
-// A block is 32 steps = 64 rows; everything else (tagged entries, staged flush, uniform polling) as above.
-template <int K, bool SHORT>
-__global__ void __launch_bounds__(LONG_WARPS * 32)
-sw_long2_kernel(LongArgs g)
-{
-    constexpr int W = 32 * K;
-    constexpr int RING = 128;
-    __shared__ int32_t r_lo[LONG_WARPS][RING];
-    __shared__ int32_t r_hi[LONG_WARPS][RING];
-    __shared__ int32_t r_g[LONG_WARPS][RING];
-    __shared__ int32_t r_e[LONG_WARPS][RING];
-    __shared__ int2 stage[LONG_WARPS][64];
-
-    const int lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    const int warp = blockIdx.x * LONG_WARPS + wib;
-    const int n_warps = gridDim.x * LONG_WARPS;
-    const int32_t goe = g.sc.gap_open + g.sc.gap_extend;
-    const int32_t ext = g.sc.gap_extend;
-    const int32_t sub_match = g.sc.match - goe, sub_mis = g.sc.mismatch - goe;
-    const int32_t lb = g.lb;
-    const int n_stripes = (g.la + W - 1) / W;
-    int32_t bestg = goe;
-    const int32_t one = g.one;
-    const uint32_t xb4 = (uint32_t)(uint8_t)(int8_t)sub_mis * 0x01010101u;
-    const uint32_t mxor = (uint32_t)(uint8_t)(int8_t)sub_mis ^ (uint32_t)(uint8_t)(int8_t)sub_match;
-    auto row_table = [&](int32_t r, uint32_t &lo, uint32_t &hi) {
-        lo = xb4; hi = xb4;
-        if (r < lb) {
-            const uint32_t c = g.lut[g.b[r]];
-            if (c < 4) lo ^= mxor << (8 * c); else hi ^= mxor << (8 * (c - 4));
-        }
-    };
-
-    for (int st = warp; st < n_stripes; st += n_warps) {
-        const int c0 = st * W + lane * K;
-        int32_t acol[K], Gp[K], F[K];
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-            const uint32_t c = (c0 + j < g.la) ? (uint32_t)g.lut[g.a[c0 + j]] : 7u;
-            acol[j] = (int32_t)(c | ((8u | c) * 0x1110u));
-            Gp[j] = goe;
-            F[j] = goe;
-        }
-        int32_t g_out0 = goe, e_out0 = goe, g_out1 = goe, e_out1 = goe, g_in_prev = goe;
-        const int32_t gst = g.stripe_base + st;
-        const bool left_edge = (gst == 0);
-        const bool last = (st == n_stripes - 1);
-        int4 *out_bnd = last ? g.next_bnd : g.bnd;
-        const bool out_remote = last;
-        const bool in_remote = (st == 0);
-        const int S = (lb + 1) / 2 + 31;                 // steps: lane 31 finishes row lb-1 at step (lb-1)/2 + 31
-
-        // inputs of the first 64 rows: this lane loads rows lane and 32 + lane of every block
-        const int4 fresh = make_int4(goe, gst - 1, goe, gst - 1);
-        int4 nxa = fresh, nxb = fresh;
-        uint32_t la_lo, la_hi, lb_lo, lb_hi;
-        row_table(lane, la_lo, la_hi);
-        row_table(32 + lane, lb_lo, lb_hi);
-        if (!left_edge) {
-            if (lane < lb) nxa = ld_entry(g.bnd + lane, in_remote);
-            if (32 + lane < lb) nxb = ld_entry(g.bnd + 32 + lane, in_remote);
-        }
-        for (int s0 = 0; s0 < S; s0 += 32) {
-            {
-                const int ra = 2 * s0 + lane, rb_ = ra + 32;
-                if (!left_edge) {
-                    unsigned ns = 32;
-                    while (__any_sync(0xffffffffu, nxa.y != gst - 1 || nxa.w != gst - 1 || nxb.y != gst - 1 || nxb.w != gst - 1)) {
-                        __nanosleep(ns);
-                        if (ns < 512) ns *= 2;
-                        if (ra < lb && (nxa.y != gst - 1 || nxa.w != gst - 1)) nxa = ld_entry(g.bnd + ra, in_remote);
-                        if (rb_ < lb && (nxb.y != gst - 1 || nxb.w != gst - 1)) nxb = ld_entry(g.bnd + rb_, in_remote);
-                    }
-                }
-                r_lo[wib][ra & (RING - 1)] = (int32_t)la_lo;  r_hi[wib][ra & (RING - 1)] = (int32_t)la_hi;
-                r_g[wib][ra & (RING - 1)] = nxa.x;            r_e[wib][ra & (RING - 1)] = nxa.z;
-                r_lo[wib][rb_ & (RING - 1)] = (int32_t)lb_lo; r_hi[wib][rb_ & (RING - 1)] = (int32_t)lb_hi;
-                r_g[wib][rb_ & (RING - 1)] = nxb.x;           r_e[wib][rb_ & (RING - 1)] = nxb.z;
-            }
-            __syncwarp();
-            const int send = min(32, S - s0);
-            // two steps per loop trip: 90.6 -> 83.3 ms on the 125 kbp x 1 Mbp share
-#pragma unroll 2
-            for (int u = 0; u < send; ++u) {
-                const int s = s0 + u;
-                const bool live = (s - lane) >= 0;
-                const int slot0 = (2 * (s - lane)) & (RING - 1), slot1 = slot0 + 1;
-                uint32_t t0lo = xb4, t0hi = xb4, t1lo = xb4, t1hi = xb4;
-                if (live) {
-                    t0lo = (uint32_t)r_lo[wib][slot0]; t0hi = (uint32_t)r_hi[wib][slot0];
-                    t1lo = (uint32_t)r_lo[wib][slot1]; t1hi = (uint32_t)r_hi[wib][slot1];
-                }
-                int32_t g_in0 = __shfl_up_sync(0xffffffffu, g_out0, 1);
-                int32_t e0 = __shfl_up_sync(0xffffffffu, e_out0, 1);
-                int32_t g_in1 = __shfl_up_sync(0xffffffffu, g_out1, 1);
-                int32_t e1 = __shfl_up_sync(0xffffffffu, e_out1, 1);
-                if (lane == 0) {
-                    g_in0 = r_g[wib][slot0]; e0 = r_e[wib][slot0];
-                    g_in1 = r_g[wib][slot1]; e1 = r_e[wib][slot1];
-                }
-                int32_t gdiag0 = g_in_prev;              // (H+goe)[i0-1][c0-1]
-                g_in_prev = g_in1;
-                int32_t gdiag1 = g_in0;                  // (H+goe)[i0][c0-1]
-                int32_t gleft0 = g_in0, gleft1 = g_in1;
-                if constexpr (SHORT) {
-                    int32_t tgp0 = g_in0, tgp1 = g_in1;
-#pragma unroll
-                    for (int j = 0; j < K; ++j) {
-                        const int32_t d0 = add_fma(gdiag0, prmt_s(t0lo, t0hi, (uint32_t)acol[j]), one);
-                        const int32_t F0 = __viaddmax_s32(F[j], ext, Gp[j]);
-                        const int32_t tg0 = add_fma(__vimax_s32_relu(F0, d0), goe, one);
-                        e0 = __viaddmax_s32(e0, ext, tgp0);
-                        gdiag0 = Gp[j];
-                        const int32_t g0 = __viaddmax_s32(e0, goe, tg0);          // (H+goe)[i0][j]
-                        const int32_t d1 = add_fma(gdiag1, prmt_s(t1lo, t1hi, (uint32_t)acol[j]), one);
-                        const int32_t F1 = __viaddmax_s32(F0, ext, g0);
-                        const int32_t tg1 = add_fma(__vimax_s32_relu(F1, d1), goe, one);
-                        e1 = __viaddmax_s32(e1, ext, tgp1);
-                        gdiag1 = g0;
-                        const int32_t g1 = __viaddmax_s32(e1, goe, tg1);          // (H+goe)[i1][j]
-                        tgp0 = tg0; tgp1 = tg1;
-                        gleft0 = g0; gleft1 = g1;
-                        Gp[j] = g1; F[j] = F1;
-                        bestg = __vimax3_s32(bestg, g0, g1);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < K; ++j) {
-                        const int32_t d0 = add_fma(gdiag0, prmt_s(t0lo, t0hi, (uint32_t)acol[j]), one);
-                        e0 = __viaddmax_s32(e0, ext, gleft0);
-                        const int32_t F0 = __viaddmax_s32(F[j], ext, Gp[j]);
-                        const int32_t g0 = add_fma(__vimax3_s32_relu(e0, F0, d0), goe, one);
-                        gdiag0 = Gp[j];
-                        const int32_t d1 = add_fma(gdiag1, prmt_s(t1lo, t1hi, (uint32_t)acol[j]), one);
-                        e1 = __viaddmax_s32(e1, ext, gleft1);
-                        const int32_t F1 = __viaddmax_s32(F0, ext, g0);
-                        const int32_t g1 = add_fma(__vimax3_s32_relu(e1, F1, d1), goe, one);
-                        gdiag1 = g0;
-                        gleft0 = g0; gleft1 = g1;
-                        Gp[j] = g1; F[j] = F1;
-                        bestg = __vimax3_s32(bestg, g0, g1);
-                    }
-                }
-                g_out0 = gleft0; e_out0 = e0; g_out1 = gleft1; e_out1 = e1;
-                if (lane == 31) {
-                    stage[wib][2 * u] = make_int2(g_out0, e_out0);
-                    stage[wib][2 * u + 1] = make_int2(g_out1, e_out1);
-                }
-            }
-            // inputs of the next block
-            {
-                const int ra = 2 * (s0 + 32) + lane, rb_ = ra + 32;
-                row_table(ra, la_lo, la_hi);
-                row_table(rb_, lb_lo, lb_hi);
-                nxa = fresh; nxb = fresh;
-                if (!left_edge) {
-                    if (ra < lb) nxa = ld_entry(g.bnd + ra, in_remote);
-                    if (rb_ < lb) nxb = ld_entry(g.bnd + rb_, in_remote);
-                }
-            }
-            // hand on the rows lane 31 finished in this block: rows 2(s0-31) .. 2(s0-31) + 2*send - 1
-            if (out_bnd != nullptr) {
-                __syncwarp();
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int q = lane + 32 * h;
-                    const int r = 2 * (s0 - 31) + q;
-                    if (q < 2 * send && r >= 0 && r < lb) {
-                        const int2 ge = stage[wib][q];
-                        st_entry(out_bnd + r, make_int4(ge.x, gst, ge.y, gst), out_remote);
-                    }
                 }
                 __syncwarp();
             }
@@ -474,8 +262,10 @@ constexpr int LR_BMAX = 32;
 template <int R> __device__ __forceinline__ void lds_vec(const int32_t *p, int32_t (&v)[R])
 {
     if constexpr (R == 4) { const int4 x = *reinterpret_cast<const int4 *>(p); v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; }
-    else if constexpr (R == 2) { const int2 x = *reinterpret_cast<const int2 *>(p); v[0] = x.x; v[1] = x.y; }
-    else {
+    else if constexpr (R % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < R; i += 2) { const int2 x = *reinterpret_cast<const int2 *>(p + i); v[i] = x.x; v[i + 1] = x.y; }
+    } else {
 #pragma unroll
         for (int i = 0; i < R; ++i) v[i] = p[i];
     }
@@ -695,6 +485,230 @@ sw_longr_kernel(LongArgs g)
     if (lane == 0 && best > 0) atomicMax(g.best, best);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Software-pipelined form of sw_longr_kernel (lean chain).  An R x K tile has low parallelism in its first and
+// last cell diagonals, and because the next step's first cell needs this step's last shuffle, a lone warp
+// (issue is in order) idles through both: measured 440 clocks per step for 190 instructions at K = 7, R = 4.
+// Here row i of a tile runs i columns behind row 0 and WRAPS into the next iteration: at time c of an
+// iteration (c = 0 .. K-1) row i computes column c - i of the lane's current row block when c >= i, and
+// column K + c - i of the previous row block otherwise.  Every time slot then holds exactly R independent
+// cells, one per row, and all column indices stay compile-time constants.  A row's boundary value leaves for
+// the next lane right after its last column (time i - 1 of the following iteration) and is consumed at time i:
+// no shuffle waits at a step boundary any more.  Lane 31 finishes row block b in iteration b + 32.
+template <int K, int R, bool DP4A>
+__global__ void __launch_bounds__(LONG_WARPS * 32)
+sw_longp_kernel(LongArgs g)
+{
+    static_assert(R >= 1 && R <= K, "rows per step must not exceed columns per lane");
+    constexpr int W = 32 * K;
+    constexpr int RROWS = 64 * R;                      // ring rows: 31 steps of lane skew + a block of <= 32 steps
+    auto slot_of = [](int row) { return (row + RROWS) % RROWS; };       // rows >= -32 R; a mask when R is a power of two
+    constexpr int K4 = (K + 3) / 4;
+    __shared__ __align__(16) int32_t r_lo[LONG_WARPS][RROWS];
+    __shared__ __align__(16) int32_t r_hi[LONG_WARPS][RROWS];
+    __shared__ __align__(16) int32_t r_g[LONG_WARPS][RROWS];
+    __shared__ __align__(16) int32_t r_e[LONG_WARPS][RROWS];
+    __shared__ __align__(16) int2 stage[LONG_WARPS][RROWS];      // ring of finished boundary rows (row & (RROWS-1))
+
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int warp = blockIdx.x * LONG_WARPS + wib;
+    const int n_warps = gridDim.x * LONG_WARPS;
+    const int32_t goe = g.sc.gap_open + g.sc.gap_extend;
+    const int32_t ext = g.sc.gap_extend;
+    const int32_t lb = g.lb;
+    const int n_stripes = (g.la + W - 1) / W;
+    const int B = g.bsteps;
+    int32_t bestg[(R + 1) / 2];
+#pragma unroll
+    for (int i = 0; i < (R + 1) / 2; ++i) bestg[i] = goe;
+    const int32_t one = g.one;
+    const int32_t xb4 = (int32_t)((uint32_t)(uint8_t)(int8_t)(g.sc.mismatch - goe) * 0x01010101u);
+    const int S = (lb + R - 1) / R + 32;               // lane 31 finishes the wrapped rows of the last block in iteration nb + 31
+
+    for (int st = warp; st < n_stripes; st += n_warps) {
+        const int c0 = st * W + lane * K;
+        int32_t acol[DP4A ? K4 : K], Gp[K], F[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) { Gp[j] = goe; F[j] = goe; }
+        if constexpr (DP4A) {
+#pragma unroll
+            for (int q = 0; q < K4; ++q) {
+                uint32_t sel = 0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = 4 * q + e;
+                    const uint32_t c = (j < K && c0 + j < g.la) ? (uint32_t)g.lut[g.a[c0 + j]] : 7u;
+                    sel |= c << (4 * e);
+                }
+                acol[q] = (int32_t)sel;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const uint32_t c = (c0 + j < g.la) ? (uint32_t)g.lut[g.a[c0 + j]] : 7u;
+                acol[j] = (int32_t)(c | ((8u | c) * 0x1110u));
+            }
+        }
+        // per-row state (a row that has not entered a real block yet is neutral: H = 0 everywhere)
+        int32_t e[R], gleft[R], gdiag[R], tlo[R], thi[R], gs[R], es[R];
+        uint32_t sc4[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            e[i] = goe; gleft[i] = goe; gdiag[i] = goe; tlo[i] = xb4; thi[i] = xb4; gs[i] = goe; es[i] = goe;
+            sc4[i] = (uint32_t)xb4;
+        }
+        int32_t gcarry = goe;                                            // (H+goe) left of the row above the entering one
+        const int32_t gst = g.stripe_base + st;
+        const bool left_edge = (gst == 0);
+        const bool last = (st == n_stripes - 1);
+        int4 *out_bnd = last ? g.next_bnd : g.bnd;
+        const bool out_remote = last;
+        const bool in_remote = (st == 0);
+        const int4 fresh = make_int4(goe, gst - 1, goe, gst - 1);
+
+        __syncwarp();
+        for (int i = lane; i < 31 * R; i += 32) {
+            const int slot = (RROWS - 31 * R) + i;
+            r_lo[wib][slot] = xb4; r_hi[wib][slot] = xb4; r_g[wib][slot] = goe; r_e[wib][slot] = goe;
+        }
+        int2 nt[R];
+        int4 nx[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            const int idx = 32 * q + lane;
+            nt[q] = make_int2(xb4, xb4);
+            nx[q] = fresh;
+            if (idx < B * R) {
+                nt[q] = g.rowtab[idx];
+                if (!left_edge && idx < lb) nx[q] = ld_entry(g.bnd + idx, in_remote);
+            }
+        }
+        for (int s0 = 0; s0 < S; s0 += B) {
+            const int base = R * s0;
+            if (!left_edge) {
+                unsigned ns = 20;
+                for (;;) {
+                    bool missing = false;
+#pragma unroll
+                    for (int q = 0; q < R; ++q) missing = missing || nx[q].y != gst - 1 || nx[q].w != gst - 1;
+                    if (!__any_sync(0xffffffffu, missing)) break;
+                    __nanosleep(ns);
+                    if (ns < 320) ns *= 2;
+#pragma unroll
+                    for (int q = 0; q < R; ++q)
+                        if (nx[q].y != gst - 1 || nx[q].w != gst - 1) nx[q] = ld_entry(g.bnd + base + 32 * q + lane, in_remote);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int idx = 32 * q + lane;
+                if (idx < B * R) {
+                    const int slot = slot_of(base + idx);
+                    r_lo[wib][slot] = nt[q].x; r_hi[wib][slot] = nt[q].y;
+                    r_g[wib][slot] = nx[q].x;  r_e[wib][slot] = nx[q].z;
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int idx = 32 * q + lane;
+                nx[q] = fresh;
+                if (idx < B * R) nt[q] = g.rowtab[base + B * R + idx];
+            }
+            const int send = min(B, S - s0);
+            const int half = send >> 1;
+#pragma unroll 1
+            for (int u = 0; u < send; ++u) {
+                const int s = s0 + u;
+                if (u == half && !left_edge) {
+                    // boundary entries of the next block, requested half a block early so that their latency is
+                    // covered by the remaining steps (the poll at the top repeats what had not arrived yet)
+#pragma unroll
+                    for (int q = 0; q < R; ++q) {
+                        const int r = base + B * R + 32 * q + lane;
+                        if (32 * q + lane < B * R && r < lb) nx[q] = ld_entry(g.bnd + r, in_remote);
+                    }
+                }
+                const int sl = R * ((s - lane) & 63);
+                const int sl0 = R * (s & 63);
+                int32_t nlo[R], nhi[R], bg[R], be[R];
+                lds_vec<R>(&r_lo[wib][sl], nlo);
+                lds_vec<R>(&r_hi[wib][sl], nhi);
+                lds_vec<R>(&r_g[wib][sl0], bg);
+                lds_vec<R>(&r_e[wib][sl0], be);
+                const int srow = R * (s - 31);                           // lane 31: first row of its current block
+#pragma unroll
+                for (int c = 0; c < K; ++c) {
+#pragma unroll
+                    for (int i = 0; i < R; ++i) {
+                        const int j = (c >= i) ? c - i : K + c - i;
+                        if (j == 0) {
+                            // row i enters the lane's current row block
+                            const int32_t gin = (lane == 0) ? bg[i] : gs[i];
+                            const int32_t ein = (lane == 0) ? be[i] : es[i];
+                            gdiag[i] = gcarry;
+                            gcarry = gin;
+                            gleft[i] = gin;
+                            e[i] = ein;
+                            tlo[i] = nlo[i];
+                            thi[i] = nhi[i];
+                        }
+                        int32_t d;
+                        if constexpr (DP4A) {
+                            if ((j & 3) == 0) sc4[i] = __byte_perm((uint32_t)tlo[i], (uint32_t)thi[i], (uint32_t)acol[j >> 2]);
+                            d = __dp4a((int32_t)sc4[i], (int32_t)(1u << (8 * (j & 3))), gdiag[i]);
+                        } else {
+                            d = add_fma(gdiag[i], prmt_s((uint32_t)tlo[i], (uint32_t)thi[i], (uint32_t)acol[j]), one);
+                        }
+                        const int32_t f = __viaddmax_s32(F[j], ext, Gp[j]);          // F[row][j]
+                        e[i] = __viaddmax_s32(e[i], ext, gleft[i]);                  // E[row][j]
+                        const int32_t gnew = add_fma(__vimax3_s32_relu(e[i], f, d), goe, one);
+                        gdiag[i] = Gp[j];
+                        Gp[j] = gnew;
+                        F[j] = f;
+                        gleft[i] = gnew;
+                        if constexpr (R == 1) bestg[0] = max(bestg[0], gnew);
+                        else if (i & 1) bestg[i >> 1] = __vimax3_s32(bestg[i >> 1], gleft[i - 1], gnew);
+                        else if (i == R - 1) bestg[i >> 1] = max(bestg[i >> 1], gnew);
+                        if (j == K - 1) {
+                            // the row leaves this lane: hand its boundary to the next lane (lane 31: stage it)
+                            gs[i] = __shfl_up_sync(0xffffffffu, gnew, 1);
+                            es[i] = __shfl_up_sync(0xffffffffu, e[i], 1);
+                            if (lane == 31) {
+                                const int row = (c >= i ? srow : srow - R) + i;
+                                stage[wib][slot_of(row)] = make_int2(gnew, e[i]);
+                            }
+                        }
+                    }
+                }
+            }
+            // hand on the row blocks lane 31 completed by now: blocks s0 - 32 .. s0 + send - 33
+            if (out_bnd != nullptr) {
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    const int idx = 32 * q + lane;
+                    const int r = R * (s0 - 32) + idx;
+                    if (idx < R * send && r >= 0 && r < lb) {
+                        const int2 ge = stage[wib][slot_of(r)];
+                        st_entry(out_bnd + r, make_int4(ge.x, gst, ge.y, gst), out_remote);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+    }
+    int32_t best_all = bestg[0];
+#pragma unroll
+    for (int i = 1; i < (R + 1) / 2; ++i) best_all = max(best_all, bestg[i]);
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) best_all = max(best_all, __shfl_xor_sync(0xffffffffu, best_all, m));
+    const int32_t best = best_all - goe;
+    if (lane == 0 && best > 0) atomicMax(g.best, best);
+}
+
 // row r -> its 8-byte score table (byte k = substitution score - goe against symbol code k; code 7 and the
 // padding rows past the last one never match), laid out for one coalesced 8-byte load per row
 __global__ void __launch_bounds__(256)
@@ -735,37 +749,19 @@ template <int K, int R, bool SHORT, bool DP4A> int long_launch_r(const LongArgs 
     return AGX_OK;
 }
 
-template <int K, bool SHORT> int long_launch2(const LongArgs &args, int n_stripes, cudaStream_t st)
+template <int K, bool SHORT> int long_launch(const LongArgs &args, int n_stripes, cudaStream_t st)
 {
     int dev = 0, sms = 0, per_sm = 0;
     AGX_CUDA(cudaGetDevice(&dev));
     AGX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    AGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_long2_kernel<K, SHORT>, LONG_WARPS * 32, 0));
-    if (per_sm < 1) return fail(AGX_ECUDA, "sw_long: kernel does not fit on an SM");
-    int blocks = sms * per_sm;
-    const int want = (n_stripes + LONG_WARPS - 1) / LONG_WARPS;
-    if (blocks > want) blocks = want;
-    LongArgs a = args;
-    void *params[] = {&a};
-    AGX_CUDA(cudaLaunchCooperativeKernel((const void *)sw_long2_kernel<K, SHORT>, dim3(blocks), dim3(LONG_WARPS * 32),
-                                         params, 0, st));
-    count_launch();
-    return AGX_OK;
-}
-
-template <int K, bool SHORT, bool CODED> int long_launch(const LongArgs &args, int n_stripes, cudaStream_t st)
-{
-    int dev = 0, sms = 0, per_sm = 0;
-    AGX_CUDA(cudaGetDevice(&dev));
-    AGX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    AGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_long_kernel<K, SHORT, CODED>, LONG_WARPS * 32, 0));
+    AGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_long_kernel<K, SHORT>, LONG_WARPS * 32, 0));
     if (per_sm < 1) return fail(AGX_ECUDA, "sw_long: kernel does not fit on an SM");
     int blocks = sms * per_sm;                        // all co-resident: required by the stripe wavefront
     const int want = (n_stripes + LONG_WARPS - 1) / LONG_WARPS;
     if (blocks > want) blocks = want;
     LongArgs a = args;
     void *params[] = {&a};
-    AGX_CUDA(cudaLaunchCooperativeKernel((const void *)sw_long_kernel<K, SHORT, CODED>, dim3(blocks), dim3(LONG_WARPS * 32),
+    AGX_CUDA(cudaLaunchCooperativeKernel((const void *)sw_long_kernel<K, SHORT>, dim3(blocks), dim3(LONG_WARPS * 32),
                                          params, 0, st));
     count_launch();
     return AGX_OK;
@@ -774,13 +770,13 @@ template <int K, bool SHORT, bool CODED> int long_launch(const LongArgs &args, i
 int env_int(const char *name, int dflt)
 {
     const char *e = getenv(name);
-    return (e && atoi(e) > 0) ? atoi(e) : dflt;
+    return (e && *e && atoi(e) >= 0) ? atoi(e) : dflt;
 }
 
 // row steps per hand-off block of sw_longr_kernel (the stripe-fill term of the run is stripes x (32 + B) steps)
 int long_block_steps()
 {
-    const int b = env_int("AGX_LONG_B", 8);
+    const int b = env_int("AGX_LONG_B", 32);
     return b < 1 ? 1 : b > LR_BMAX ? LR_BMAX : b;
 }
 
@@ -814,30 +810,33 @@ int pick_k(int64_t cols_per_gpu, int64_t rows, int sms, bool coded)
     return best_k;
 }
 
-template <int I = 0> int long_dispatch_coded(int k, bool short_chain, bool two_rows, const LongArgs &args, int n, cudaStream_t st)
-{
-    if constexpr (I < (int)(sizeof(LONG_KS) / sizeof(LONG_KS[0]))) {
-        if (LONG_KS[I] == k) {
-            if (two_rows)
-                return short_chain ? long_launch2<LONG_KS[I], true>(args, n, st) : long_launch2<LONG_KS[I], false>(args, n, st);
-            return short_chain ? long_launch<LONG_KS[I], true, true>(args, n, st)
-                               : long_launch<LONG_KS[I], false, true>(args, n, st);
-        }
-        return long_dispatch_coded<I + 1>(k, short_chain, two_rows, args, n, st);
-    } else {
-        return fail(AGX_EINVAL, "sw_long: stripe width not instantiated");
-    }
-}
 template <int I = 0> int long_dispatch_raw(int k, bool short_chain, const LongArgs &args, int n, cudaStream_t st)
 {
     if constexpr (I < (int)(sizeof(LONG_KS_RAW) / sizeof(LONG_KS_RAW[0]))) {
         if (LONG_KS_RAW[I] == k)
-            return short_chain ? long_launch<LONG_KS_RAW[I], true, false>(args, n, st)
-                               : long_launch<LONG_KS_RAW[I], false, false>(args, n, st);
+            return short_chain ? long_launch<LONG_KS_RAW[I], true>(args, n, st) : long_launch<LONG_KS_RAW[I], false>(args, n, st);
         return long_dispatch_raw<I + 1>(k, short_chain, args, n, st);
     } else {
         return fail(AGX_EINVAL, "sw_long: stripe width not instantiated");
     }
+}
+
+template <int K, int R, bool DP4A> int long_launch_p(const LongArgs &args, int n_stripes, cudaStream_t st)
+{
+    int dev = 0, sms = 0, per_sm = 0;
+    AGX_CUDA(cudaGetDevice(&dev));
+    AGX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    AGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_longp_kernel<K, R, DP4A>, LONG_WARPS * 32, 0));
+    if (per_sm < 1) return fail(AGX_ECUDA, "sw_long: kernel does not fit on an SM");
+    int blocks = sms * per_sm;
+    const int want = (n_stripes + LONG_WARPS - 1) / LONG_WARPS;
+    if (blocks > want) blocks = want;
+    LongArgs a = args;
+    void *params[] = {&a};
+    AGX_CUDA(cudaLaunchCooperativeKernel((const void *)sw_longp_kernel<K, R, DP4A>, dim3(blocks), dim3(LONG_WARPS * 32),
+                                         params, 0, st));
+    count_launch();
+    return AGX_OK;
 }
 
 // sw_longr_kernel instantiations: stripe widths x rows per step x chain form x substitution form
@@ -845,9 +844,11 @@ template <int I = 0> int long_dispatch_raw(int k, bool short_chain, const LongAr
 constexpr int LONGR_KS[] = {6, 7, 8, 14, 27};
 #define AGX_LONGR_VARIANTS(X) X(1, false, false) X(1, true, false) X(2, false, false) X(2, true, false) X(4, false, false) \
     X(4, true, false) X(1, false, true) X(1, true, true) X(2, false, true) X(2, true, true) X(4, false, true) X(4, true, true)
+#define AGX_LONGP_VARIANTS(X) X(1, false) X(2, false) X(3, false) X(4, false) X(1, true) X(2, true) X(3, true) X(4, true) X(6, true)
 #else
+#define AGX_LONGP_VARIANTS(X) X(4, true)
 constexpr int LONGR_KS[] = {2, 4, 6, 7, 8, 10, 12, 14, 16, 20, 24, 27, 32};
-#define AGX_LONGR_VARIANTS(X) X(2, false, false) X(2, true, false)
+#define AGX_LONGR_VARIANTS(X) X(2, false, true) X(4, false, true)
 #endif
 constexpr int N_LONGR_KS = (int)(sizeof(LONGR_KS) / sizeof(LONGR_KS[0]));
 
@@ -865,11 +866,19 @@ template <int I = 0> int long_dispatch_r(int k, int rows, bool short_chain, bool
         return fail(AGX_EINVAL, "sw_long: stripe width not instantiated");
     }
 }
-bool longr_has_k(int k)
+template <int I = 0> int long_dispatch_p(int k, int rows, bool dp4a, const LongArgs &args, int n, cudaStream_t st)
 {
-    for (int i = 0; i < N_LONGR_KS; ++i)
-        if (LONGR_KS[i] == k) return true;
-    return false;
+    if constexpr (I < N_LONGR_KS) {
+        if (LONGR_KS[I] == k) {
+#define AGX_X(RR, DD) if constexpr (RR <= LONGR_KS[I]) { if (rows == RR && dp4a == DD) return long_launch_p<LONGR_KS[I], RR, DD>(args, n, st); }
+            AGX_LONGP_VARIANTS(AGX_X)
+#undef AGX_X
+            return fail(AGX_EINVAL, "sw_long: rows-per-step / dp4a combination not instantiated");
+        }
+        return long_dispatch_p<I + 1>(k, rows, dp4a, args, n, st);
+    } else {
+        return fail(AGX_EINVAL, "sw_long: stripe width not instantiated");
+    }
 }
 
 int long_dispatch(int k, const LongArgs &args, cudaStream_t st)
@@ -882,13 +891,14 @@ int long_dispatch(int k, const LongArgs &args, cudaStream_t st)
     bool short_chain = n <= sms * 4;
     if (const char *e = getenv("AGX_LONG_CHAIN")) short_chain = atoi(e) != 0;
     if (!args.lut) return long_dispatch_raw<0>(k, short_chain, args, n, st);
-    if (getenv("AGX_LONG_OLD")) {                         // A/B switch: the round-1 kernels
-        bool two_rows = n <= sms * 4;
-        if (const char *e = getenv("AGX_LONG_ROWS")) two_rows = atoi(e) == 2;
-        return long_dispatch_coded<0>(k, short_chain, two_rows, args, n, st);
-    }
-    const int rows = env_int("AGX_LONG_R", 2);
-    const bool dp4a = env_int("AGX_LONG_DP4A", 0) != 0;
+    // Measured on the per-GPU share of an 8-GPU run (125 kbp x 1 Mbp, one warp per scheduler) and on 1 Mbp x 1 Mbp
+    // on one GPU (two warps per scheduler), profiles/r2a_long_sweep_*.jsonl: the lean chain with the dp4a
+    // substitution wins everywhere; four rows per step when a scheduler holds a single warp (68 vs 92 ms), two
+    // when it holds two (348 vs 388 ms).  The software-pipelined form is kept for experiments (AGX_LONG_PIPE=1).
+    const int rows = env_int("AGX_LONG_R", n <= sms * 4 ? 4 : 2);
+    const bool dp4a = env_int("AGX_LONG_DP4A", 1) != 0;
+    if (getenv("AGX_LONG_CHAIN") == nullptr) short_chain = false;
+    if (env_int("AGX_LONG_PIPE", 0) != 0 && rows <= k) return long_dispatch_p<0>(k, rows, dp4a, args, n, st);
     return long_dispatch_r<0>(k, rows, short_chain, dp4a, args, n, st);
 }
 
@@ -994,6 +1004,7 @@ void sw_long_workspace_free(SwLongWorkspace &ws)
 {
     if (ws.buf) cudaFree(ws.buf);
     if (ws.seq) cudaFree(ws.seq);
+    ws.prof.destroy();
     ws = SwLongWorkspace();
 }
 
@@ -1089,7 +1100,9 @@ int sw_long_host_multi(int n_dev, const int *dev, cudaStream_t *st, SwLongWorksp
     }
     for (int gidx = 0; gidx < n_dev; ++gidx) {
         AGX_CUDA(cudaSetDevice(dev[gidx]));
+        ws[gidx]->prof.begin(st[gidx]);
         int rc = long_dispatch(ks[gidx], args[gidx], st[gidx]);
+        ws[gidx]->prof.end(st[gidx]);
         if (rc != AGX_OK) return rc;
     }
     int32_t best = 0;

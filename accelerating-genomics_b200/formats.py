@@ -44,6 +44,35 @@ def _c_atoi(b: bytes) -> int:
     return sign * n
 
 
+def _c_sscanf_d(s: bytes):
+    """One "%d" of sscanf on s: (value or None when nothing parses, rest of s)."""
+    t = s.lstrip(b" \t\n\v\f\r")
+    sign, i = 1, 0
+    if t[:1] in (b"+", b"-"):
+        sign, i = (-1 if t[:1] == b"-" else 1), 1
+    j = i
+    while j < len(t) and 48 <= t[j] <= 57:
+        j += 1
+    if j == i:
+        return None, s
+    return sign * int(t[i:j]), t[j:]
+
+
+def sscanf_two_ints(line: bytes, prev):
+    """sscanf(line, "%d %d", &num_read, &num_haplotypes) (antidiagsPairHMM.c:378) on variables that keep their
+    previous values (prev) where a field does not parse: the reference declares them once, outside the batch
+    loop (:345-346)."""
+    nr, nh = prev
+    v, rest = _c_sscanf_d(line)
+    if v is None:
+        return nr, nh
+    nr = v
+    v, _ = _c_sscanf_d(rest)
+    if v is not None:
+        nh = v
+    return nr, nh
+
+
 def fgets_chunks(data: np.ndarray, start: int, bufsize: int) -> Tuple[np.ndarray, np.ndarray]:
     """(offsets, lengths) of successive fgets(buf, bufsize) results over data[start:]."""
     n = data.size
@@ -159,10 +188,10 @@ def parse_pairhmm(data: bytes | np.ndarray) -> HmmInput:
     brs, bhs = [0], [0]
     i = 0
     n_lines = off.size
+    nr = nh = 0
     while i < n_lines:
-        head = buf[off[i]:off[i] + ln[i]].tobytes().split()
-        nr = _c_atoi(head[0]) if len(head) > 0 else 0
-        nh = _c_atoi(head[1]) if len(head) > 1 else 0
+        nr, nh = sscanf_two_ints(buf[off[i]:off[i] + ln[i]].tobytes(), (nr, nh))
+        nr, nh = max(nr, 0), max(nh, 0)
         i += 1
         if i + nr + nh > n_lines:
             break                                            # "Error reading ..." in the reference

@@ -1,28 +1,38 @@
 #!/usr/bin/env python
-"""bench.py -- BASELINE.json's metric ("SW and PairHMM GCUPS at 1/2/4/8 B200 vs reference C on host
-cores") measured on BASELINE.json's two batch configurations:
-
-    configs[2]  SW short-read batch: 10^6 pairs 150 bp x 150 bp (synthetic)          <- headline
-    configs[3]  PairHMM HaplotypeCaller-shaped batch: 10^6 (read, haplotype) pairs,
-                reads 100-250 bp x haplotypes 200-500 bp (synthetic)                  <- "pairhmm" object
+"""bench.py -- BASELINE.json's metric ("SW and PairHMM GCUPS at 1/2/4/8 B200 vs reference C on host cores").
 
     python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
     python bench.py --impl reference ...                     (the reference C programs on the host cores)
 
-A "step" is one pass of the hot path over one batch.  Per-GPU work is fixed as N grows (every rank
-scores its own 10^6-pair shard: "scaling": "weak"); pairs are independent, so there is no data-path
-collective -- torch.distributed is used only for the barrier and the max-over-ranks of the timings.
+A "step" is one pass of the hot path over one batch.  ONE JSON line comes out; its top level is the headline
+workload, the other BASELINE configurations are objects inside it:
 
-  value        GCUPS with the batch already resident in HBM (raw file bytes + offsets): classify kernel,
-               grid-sizing read-back, DP kernels; CUDA events on the launching stream, max over ranks.
-  e2e          the same metric through the host C-ABI call (sw_score_batch_flat /
-               pairhmm_forward_batches_flat) on PINNED HOST buffers: H2D of the batch, kernels, D2H of
-               the results all inside the timed region.
-  roofline     dominant kernel (SW: sw_duo_kernel<8,19>; PairHMM: hmm_stream_kernel<K>) timed alone with
-               CUDA events inside libagx (agx_profile_ms): algorithmic ALU lane-ops / s over the measured
-               ALU peak of profiles/peaks_*.json (nominal fallback stated).
-  cpu_baseline the reference C programs (oracle/_ref, kind "reference") or the oracle port, on all host
-               cores, on a bounded sample of the same workload.
+  top level      configs[2]  SW short-read batch, 10^6 pairs of 150 x 150 per GPU ("scaling": "weak": every rank
+                 scores its own batch; pairs are independent, so there is no data-path collective --
+                 torch.distributed only carries the barrier and the max-over-ranks of the timings).
+  "pairhmm"      configs[3]  10^6 (read, haplotype) pairs per GPU, reads 100-250 x haplotypes 200-500, with the
+                 <= 0.1 % tail of unrelated reads that exercises the FP64 rescue (count and kernel ms reported).
+  "sw_long"      configs[4]  ONE pair of 1 Mbp x 1 Mbp, columns striped over ALL N GPUs of the box inside ONE
+                 process (rank 0; the other ranks park on a CPU barrier): NVLink peer boundary exchange, strong
+                 scaling, pipeline efficiency = T(1 GPU) / (N x T(N GPUs)), score checked against the CPU-computed
+                 expected score committed in tests/golden/sw_long_expected.json.
+  "strong"       configs[2] / [3] again as ONE 10^6-pair batch through the library's own in-process multi-GPU
+                 dispatcher (agx_init(N); rank 0): end to end from host buffers and resident (one shard per GPU).
+  "pairhmm_gatk" configs[3] with the corrected GATK priors (mismatch prior Qr/3, optional base-quality floor):
+                 never used for parity with the reference, reported separately.
+  "sw_lengths"   the inter-task SW kernel at the published MI210 sweep lengths (64 ... 1024) and at generator.py's
+                 own 450-500 bp, one length class each.
+  "parity"       (N = 1) GPU results against the reference C programs' own output on the cpu_baseline shards.
+
+  value        GCUPS with the batch already resident in HBM; CUDA events on the launching stream, max over ranks.
+  e2e          the same metric through the reference-facing C-ABI call on PINNED HOST buffers: H2D of the batch,
+               kernels, D2H of the results all inside the timed region; h2d_only_ms = the bare upload of the same
+               bytes by every rank at once (the floor that bounds e2e scaling).
+  roofline     dominant kernel timed alone with CUDA events inside libagx (agx_profile_ms):
+               frac = cells/s x ops_per_cell_executed / measured pipe peak (profiles/peaks_r*.json); the SURVEY's
+               algorithmic count is given beside it.
+  cpu_baseline the reference C programs (oracle/_ref, kind "reference") -- or the oracle port where they are
+               absent -- on all host cores, one process per core, each on its own shard of the same generator.
 """
 from __future__ import annotations
 
@@ -42,8 +52,11 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 SW_LEN = 150
-SW_OPS_PER_CELL = 4.0       # s16x2: 8 INT32-pipe lane-ops per cell pair
-HMM_OPS_PER_CELL = 8.0      # 8 FP32-pipe lane-instructions = 11 FLOP per cell
+# lane-ops per cell on the pipe that bounds each kernel: "algorithmic" = SURVEY.md section 8(d)'s count, "executed" =
+# what the kernel issues on that pipe
+SW_OPS = {"algorithmic": 4.0, "executed": 2.25}        # s16x2: 4.5 alu-pipe (+ 2 fma-pipe) instructions per cell PAIR
+HMM_OPS = {"algorithmic": 8.0, "executed": 6.0}        # FP32 lane-instructions per cell (X' / Y' form)
+LONG_OPS = {"algorithmic": 8.0, "executed": 3.75}      # s32 coded cell: 2 VIADDMNMX + VIMNMX3.RELU + 1/2 VIMNMX3 + 1/4 PRMT
 NOMINAL_ALU = 148 * 64 * 1.965e9     # INT32/DPX lane-ops/s   
 NOMINAL_FP32 = 148 * 128 * 1.965e9   # FP32 lane-instr/s
 
@@ -62,6 +75,34 @@ def measured_peaks():
         except Exception:
             pass
     return best
+
+
+def pipe_peak(kind: str):
+    """(lane-ops/s, where the number comes from) for kind in {"alu", "fp32"}"""
+    peaks = measured_peaks()
+    key = "alu_tlaneops" if kind == "alu" else "fp32_tlaneops"
+    if peaks and peaks.get(key):
+        return peaks[key] * 1e12, f"measured ({peaks.get('source', 'profiles/peaks')})"
+    nominal = NOMINAL_ALU if kind == "alu" else NOMINAL_FP32
+    return nominal, "nominal 148 SM x %d lanes/clk x 1.965 GHz (no measured peak committed)" % (64 if kind == "alu" else 128)
+
+
+def roofline_obj(kind, kernel, cells, kernel_ms, ops, unit, ncu_key=None, extra=None):
+    """frac is computed from the instructions the kernel EXECUTES on its binding pipe, so it cannot exceed 1."""
+    peak, src = pipe_peak(kind)
+    peaks = measured_peaks() or {}
+    executed = cells * ops["executed"] / (kernel_ms * 1e-3)
+    out = {"bound": "alu", "pipe": "INT32/DPX alu pipe" if kind == "alu" else "FP32 fma pipe", "kernel": kernel,
+           "achieved": executed / 1e12, "peak": peak / 1e12, "unit": unit, "frac": executed / peak, "peak_source": src,
+           "ops_per_cell_executed": ops["executed"], "ops_per_cell_algorithmic": ops["algorithmic"],
+           "frac_algorithmic": cells * ops["algorithmic"] / (kernel_ms * 1e-3) / peak,
+           "kernel_ms": kernel_ms, "kernel_gcups": cells / (kernel_ms * 1e-3) / 1e9}
+    if ncu_key and peaks.get("ncu", {}).get(ncu_key) is not None:
+        out["pipe_active_ncu"] = peaks["ncu"][ncu_key]
+        out["pipe_active_ncu_source"] = peaks["ncu"].get(ncu_key + "_source")
+    if extra:
+        out.update(extra)
+    return out
 
 
 class ClockSampler:
@@ -140,12 +181,17 @@ def merge_clocks(a, b):
 
 
 # --------------------------------------------------------------------------------------- CPU reference arm
-def _run_parallel(cmds, timeout=900):
+def _run_parallel(cmds, stdouts=None, timeout=1800):
+    """One process per command, all at once; stdouts[i] (a path) receives command i's stdout."""
     t0 = time.perf_counter()
-    procs = [subprocess.Popen(c, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for c in cmds]
+    files = [open(s, "wb") if s else subprocess.DEVNULL for s in (stdouts or [None] * len(cmds))]
+    procs = [subprocess.Popen(c, stdout=f, stderr=subprocess.DEVNULL) for c, f in zip(cmds, files)]
     for p in procs:
         p.wait(timeout=timeout)
     dt = time.perf_counter() - t0
+    for f in files:
+        if f is not subprocess.DEVNULL:
+            f.close()
     bad = [p.returncode for p in procs if p.returncode != 0]
     if bad:
         raise RuntimeError(f"reference process failed: exit codes {bad[:4]}")
@@ -157,14 +203,17 @@ def _port_worker(args):
     import oracle
     if kind == "sw":
         s, _ = oracle.sw_file(path)
+        np.savetxt(path + ".scores", s, fmt="Score: %d")
         return len(s)
     v, _ = oracle.pairhmm_file(path)
+    np.savetxt(path + ".out", v, fmt="%f")
     return len(v)
 
 
 class CpuReference:
     """Times the reference C programs (oracle/_ref) -- or, where they are absent, the oracle port --
-    on every host core, one process per core, each on its own shard of the synthetic workload."""
+    on every host core, one process per core, each on its own shard of the synthetic workload, and KEEPS what
+    they print: the GPU is then checked against it on the same shard files (parity())."""
 
     def __init__(self):
         import agxpkg
@@ -186,19 +235,22 @@ class CpuReference:
             p.write_bytes(inp.buf.tobytes())
             files.append(str(p))
         self._sw_files = files
+        self._sw_pairs = pairs_per_core * self.cores
         self._sw_cells = float(self.cores) * pairs_per_core * SW_LEN * SW_LEN
         self._sw_sample = (f"{self.cores} processes x {pairs_per_core} pairs of {SW_LEN}x{SW_LEN} "
                            f"({'oracle/_ref/sw_antidiag = antidiagonalSmithWaterman.c -O3' if self.kind == 'reference' else 'oracle port'})")
 
-    def prepare_hmm(self, batches_per_core: int, seed: int = 99):
-        files, cells = [], 0
+    def prepare_hmm(self, batches_per_core: int, seed: int = 99, unrelated_frac: float = 0.001):
+        files, cells, pairs = [], 0, 0
         for c in range(self.cores):
-            inp = self.agx.synth.pairhmm_batches(batches_per_core, 200, 5, seed=seed + c)
+            inp = self.agx.synth.pairhmm_batches(batches_per_core, 200, 5, seed=seed + c, unrelated_frac=unrelated_frac)
             p = Path(self.tmp.name) / f"hmm_{c}.in"
             p.write_bytes(inp.buf.tobytes())
             files.append(str(p))
             cells += inp.cells()
+            pairs += inp.n_pairs
         self._hmm_files = files
+        self._hmm_pairs = pairs
         self._hmm_cells = float(cells)
         self._hmm_sample = (f"{self.cores} processes x {batches_per_core} batches of 200 reads x 5 haplotypes "
                             f"({'oracle/_ref/pairhmm_matrix = pairHMMmatrix.c -O3, output byte-identical to antidiagsPairHMM.c' if self.kind == 'reference' else 'oracle port'})")
@@ -207,10 +259,8 @@ class CpuReference:
         files = self._sw_files if which == "sw" else self._hmm_files
         if self.kind == "reference":
             if which == "sw":
-                cmds = [[str(self.sw_exe), f] for f in files]
-            else:
-                cmds = [[str(self.hmm_exe), f, f + ".out"] for f in files]
-            return _run_parallel(cmds)
+                return _run_parallel([[str(self.sw_exe), f] for f in files], [f + ".scores" for f in files])
+            return _run_parallel([[str(self.hmm_exe), f, f + ".out"] for f in files])
         import multiprocessing as mp
         t0 = time.perf_counter()
         with mp.get_context("fork").Pool(self.cores) as pool:
@@ -228,6 +278,36 @@ class CpuReference:
     def baseline_obj(self, which: str, value: float):
         return {"value": value, "unit": "GCUPS", "cores": self.cores, "kind": self.kind,
                 "sample": self._sw_sample if which == "sw" else self._hmm_sample}
+
+    # ---- the GPU against what the CPU programs printed, on the same shard files (agx arm only) ----
+    def parity_sw(self, cap):
+        pairs = bad = 0
+        for f in self._sw_files:
+            want = np.array([int(l.split()[1]) for l in Path(f + ".scores").read_bytes().splitlines() if l.startswith(b"Score:")],
+                            dtype=np.int32)
+            got, _, _ = cap.sw_score_file_image(np.fromfile(f, dtype=np.uint8), max_pairs=want.size + 1)
+            pairs += want.size
+            bad += int(want.size != got.size) + int(np.count_nonzero(want[:got.size] != got[:want.size]))
+        return {"sw_pairs": pairs, "sw_mismatches": bad}
+
+    def parity_hmm(self, cap):
+        pairs = bad = 0
+        worst = 0.0
+        for f in self._hmm_files:
+            want = np.array(Path(f + ".out").read_bytes().split(), dtype=np.float64)     # "%f" lines; "-inf" parses
+            got, _, _ = cap.pairhmm_forward_file_image(np.fromfile(f, dtype=np.uint8))
+            pairs += want.size
+            if want.size != got.size:
+                bad += 1
+                continue
+            fin = np.isfinite(want)
+            bad += int(np.count_nonzero(got[~fin] != want[~fin]))
+            # the reference prints six decimals: half a unit of the last one is print rounding, not error
+            rel = np.maximum(np.abs(got[fin] - want[fin]) - 5e-7, 0.0) / np.maximum(np.abs(want[fin]), 1e-300)
+            if rel.size:
+                worst = max(worst, float(rel.max()))
+                bad += int(np.count_nonzero(rel > 1e-5))
+        return {"hmm_pairs": pairs, "hmm_mismatches": bad, "hmm_max_rel": worst, "hmm_tolerance": 1e-5}
 
 
 def run_reference_arm(args):
@@ -285,6 +365,23 @@ def barrier(world: int):
         import torch.distributed as dist
         dist.barrier()
     torch.cuda.synchronize()
+
+
+def h2d_only_ms(h_tensor, device, world, reps=3):
+    """The bare upload of one step's input bytes from pinned memory, by every rank at the same time."""
+    import torch
+    d = torch.empty_like(h_tensor, device=device)
+    best = 1e30
+    for _ in range(reps):
+        barrier(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        d.copy_(h_tensor, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, max_over_ranks(e0.elapsed_time(e1), world, device))
+    del d
+    return best
 
 
 def bench_sw(agx, args, rank, local_rank, world, device):
@@ -348,78 +445,83 @@ def bench_sw(agx, args, rank, local_rank, world, device):
     torch.cuda.synchronize()
     flat_ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / args.steps, world, device)
     assert np.array_equal(e2e_scores, res_scores), "host and device entry points disagree"
+    copy_ms = h2d_only_ms(h_buf, device, world)
 
     k_ms = float(np.mean(kern_ms))
-    peaks = measured_peaks()
-    if peaks and peaks.get("alu_tlaneops"):
-        peak, peak_src = peaks["alu_tlaneops"] * 1e12, f"measured ({peaks.get('source', 'profiles/peaks')})"
-    else:
-        peak, peak_src = NOMINAL_ALU, "nominal 148 SM x 64 lanes/clk x 1.965 GHz (no measured ALU peak committed yet)"
-    achieved = cells * SW_OPS_PER_CELL / (k_ms * 1e-3)
+    peaks = measured_peaks() or {}
     return {
         "value": world * cells / (ms * 1e-3) / 1e9, "ms_per_step": ms,
         "e2e": {"value": world * cells / (e2e_ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(np_buf.nbytes), "d2h_bytes_per_step": int(4 * n),
+                "h2d_only_ms": copy_ms, "h2d_only_gbs_per_rank": np_buf.nbytes / (copy_ms * 1e-3) / 1e9,
                 "entry_point": "sw_score_file_image (pinned file image in, pinned scores out)"},
         "e2e_flat": {"value": world * cells / (flat_ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": flat_ms,
                      "h2d_bytes_per_step": int(np_buf.nbytes + np_off.nbytes + np_len.nbytes),
                      "d2h_bytes_per_step": int(4 * n), "entry_point": "sw_score_batch_flat"},
-        "roofline": {"bound": "alu", "kernel": "sw_duo_kernel<8,19> (s16x2 DPX)", "achieved": achieved / 1e12,
-                     "peak": peak / 1e12, "unit": "Tlaneop/s (INT32/DPX pipe)", "frac": achieved / peak,
-                     "peak_source": peak_src, "ops_per_cell": SW_OPS_PER_CELL, "kernel_ms": k_ms,
-                     "kernel_gcups": cells / (k_ms * 1e-3) / 1e9, "kernel_share_of_step": k_ms / ms,
-                     "traffic": (peaks["sw_duo_dram_bytes_per_pair_150x150"] * n
-                                 if peaks and peaks.get("sw_duo_dram_bytes_per_pair_150x150") else None),
-                     "traffic_note": "DRAM bytes per launch from the committed ncu capture (profiles/r1f_sw_duo_ncu.txt), "
-                                     "scaled by pairs; the kernel is ALU-bound, HBM time for this is ~0.05 ms",
-                     "loader": {"kernel": "sw_classify_kernel", "ms": float(np.mean(cls_ms)), "bound": "hbm"}},
+        "roofline": roofline_obj(
+            "alu", "sw_duo_kernel<8,19> (s16x2 DPX)", cells, k_ms, SW_OPS, "Tlaneop/s (INT32/DPX alu pipe)", "sw_duo_alu_pipe_active_pct",
+            {"kernel_share_of_step": k_ms / ms,
+             "traffic": (peaks["sw_duo_dram_bytes_per_pair_150x150"] * n if peaks.get("sw_duo_dram_bytes_per_pair_150x150") else None),
+             "traffic_note": "DRAM bytes per launch from the committed ncu capture, scaled by pairs; the kernel is ALU-bound, "
+                             "HBM time for this is ~0.05 ms",
+             "loader": {"kernel": "sw_classify_kernel", "ms": float(np.mean(cls_ms)), "bound": "hbm"}}),
         "gpu_launches": int(launches), "clocks": clk.summary(),
         "pairs_per_gpu": n, "cells_per_gpu": cells,
     }
 
 
-def bench_hmm(agx, args, rank, local_rank, world, device):
+def hmm_device_arrays(inp, device):
+    """Index arrays of an HmmInput as the device entry points take them (torch tensors on `device`)."""
     import torch
-    cap = agx.capi
-    inp = agx.synth.pairhmm_batches(args.hmm_batches, 200, 5, seed=2000 + rank)
-    cells = float(inp.cells())
-    n_pairs = inp.n_pairs
     nb = inp.n_batches
     nh_b = np.diff(inp.batch_hap_start)
     read_batch = np.repeat(np.arange(nb, dtype=np.int32), np.diff(inp.batch_read_start))
     out_off = np.concatenate(([0], np.cumsum(nh_b[read_batch])))[:-1].astype(np.int64)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    return {"buf": t(inp.buf), "rfo": t(inp.read_field_off.reshape(-1)), "rl": t(inp.read_len), "rb": t(read_batch),
+            "roo": t(out_off), "ho": t(inp.hap_off), "hl": t(inp.hap_len), "bhs": t(inp.batch_hap_start),
+            "out": torch.empty(inp.n_pairs, dtype=torch.float64, device=device)}
+
+
+def bench_hmm(agx, args, rank, local_rank, world, device):
+    import torch
+    cap = agx.capi
+    inp = agx.synth.pairhmm_batches(args.hmm_batches, 200, 5, seed=2000 + rank, unrelated_frac=args.hmm_unrelated)
+    cells = float(inp.cells())
+    n_pairs = inp.n_pairs
+    nb = inp.n_batches
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     h_buf = pin(inp.buf)
     h_rfo, h_rl, h_ho, h_hl = pin(inp.read_field_off.reshape(-1)), pin(inp.read_len), pin(inp.hap_off), pin(inp.hap_len)
     h_brs, h_bhs = pin(inp.batch_read_start), pin(inp.batch_hap_start)
-    d_buf, d_rfo, d_rl, d_ho, d_hl, d_bhs = (x.to(device) for x in (h_buf, h_rfo, h_rl, h_ho, h_hl, h_bhs))
-    d_rb, d_roo = torch.from_numpy(read_batch).to(device), torch.from_numpy(out_off).to(device)
-    d_out = torch.empty(n_pairs, dtype=torch.float64, device=device)
+    d = hmm_device_arrays(inp, device)
     stream = torch.cuda.current_stream().cuda_stream
 
     def step_resident():
-        cap.pairhmm_forward_device(local_rank, d_buf.data_ptr(), d_buf.numel(), d_rfo.data_ptr(), d_rl.data_ptr(),
-                                   d_rb.data_ptr(), d_roo.data_ptr(), inp.read_len.size, d_ho.data_ptr(),
-                                   d_hl.data_ptr(), inp.hap_len.size, d_bhs.data_ptr(), nb, n_pairs,
-                                   d_out.data_ptr(), stream, True)
+        cap.pairhmm_forward_device(local_rank, d["buf"].data_ptr(), d["buf"].numel(), d["rfo"].data_ptr(), d["rl"].data_ptr(),
+                                   d["rb"].data_ptr(), d["roo"].data_ptr(), inp.read_len.size, d["ho"].data_ptr(),
+                                   d["hl"].data_ptr(), inp.hap_len.size, d["bhs"].data_ptr(), nb, n_pairs,
+                                   d["out"].data_ptr(), stream, True)
 
     for _ in range(args.warmup):
         step_resident()
     sampler = ClockSampler(local_rank)
     barrier(world)
     cap.reset_launch_count()
-    kern_ms = []
+    kern_ms, fp64_ms = [], []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with sampler as clk:
         ev0.record()
         for _ in range(args.steps):
             step_resident()
             kern_ms.append(cap.profile_ms(local_rank, cap.PROF_HMM_STREAM))
+            fp64_ms.append(cap.profile_ms(local_rank, cap.PROF_HMM_FP64))
         ev1.record()
         torch.cuda.synchronize()
     launches = cap.launch_count()
+    rescued = cap.pairhmm_rescue_count(local_rank)
     ms = max_over_ranks(ev0.elapsed_time(ev1) / args.steps, world, device)
-    res = d_out.cpu().numpy()
+    res = d["out"].cpu().numpy()
 
     # end to end.  Headline: pairhmm_forward_file_image(), the call the drop-in driver makes -- the raw
     # pairHMM/test_set-format file image in pinned host memory in, log10 likelihoods in pinned host memory
@@ -445,91 +547,383 @@ def bench_hmm(agx, args, rank, local_rank, world, device):
     torch.cuda.synchronize()
     flat_ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / args.steps, world, device)
     assert np.array_equal(e2e, res, equal_nan=True), "host and device entry points disagree"
-    assert np.all(np.isfinite(res)), "non-finite PairHMM result"
+    assert not np.any(np.isnan(res)), "NaN PairHMM result"
+    copy_ms = h2d_only_ms(h_buf, device, world)
 
     k_ms = float(np.mean(kern_ms))
-    peaks = measured_peaks()
-    if peaks and peaks.get("fp32_tlaneops"):
-        peak, peak_src = peaks["fp32_tlaneops"] * 1e12, f"measured ({peaks.get('source', 'profiles/peaks')})"
-    else:
-        peak, peak_src = NOMINAL_FP32, "nominal 148 SM x 128 lanes/clk x 1.965 GHz (no measured FP32 peak committed yet)"
-    achieved = cells * HMM_OPS_PER_CELL / (k_ms * 1e-3)
+    f_ms = [x for x in fp64_ms if x >= 0]
+    peaks = measured_peaks() or {}
     return {
         "value": world * cells / (ms * 1e-3) / 1e9, "unit": "GCUPS", "dtype": "f32 (+f64 rescue)", "ms_per_step": ms,
         "e2e": {"value": world * cells / (e2e_ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(arrs[0].nbytes), "d2h_bytes_per_step": int(8 * n_pairs + 4 * nb),
+                "h2d_only_ms": copy_ms, "h2d_only_gbs_per_rank": arrs[0].nbytes / (copy_ms * 1e-3) / 1e9,
                 "entry_point": "pairhmm_forward_file_image (pinned file image in, pinned results out)"},
         "e2e_flat": {"value": world * cells / (flat_ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": flat_ms,
                      "h2d_bytes_per_step": int(sum(a.nbytes for a in arrs)), "d2h_bytes_per_step": int(8 * n_pairs),
                      "entry_point": "pairhmm_forward_batches_flat"},
-        "roofline": {"bound": "alu", "kernel": "hmm_duo_kernel<K=4..8> (FP32, two reads per warp, f32x2) + hmm_stream_kernel for unpaired reads", "achieved": achieved / 1e12,
-                     "peak": peak / 1e12, "unit": "Tlaneinstr/s (FP32 pipe)", "frac": achieved / peak,
-                     "peak_source": peak_src, "ops_per_cell": HMM_OPS_PER_CELL, "kernel_ms": k_ms,
-                     "kernel_gcups": cells / (k_ms * 1e-3) / 1e9, "kernel_share_of_step": k_ms / ms,
-                     "traffic": (peaks["hmm_dram_bytes_per_step_config4"] * (args.hmm_batches / 1000.0)
-                                 if peaks and peaks.get("hmm_dram_bytes_per_step_config4") else None),
-                     "traffic_note": "DRAM bytes of the stream-kernel launches of one step from the committed ncu launch "
-                                     "list (profiles/r1f_launch_shares.txt), scaled by batches; FP32-bound, HBM time ~0.04 ms"},
+        "roofline": roofline_obj(
+            "fp32", "hmm_duo_kernel<K=4..8> (FP32, two reads per warp, f32x2) + hmm_stream_kernel for unpaired reads",
+            cells, k_ms, HMM_OPS, "Tlaneinstr/s (FP32 pipe)", "hmm_duo_fma_pipe_active_pct",
+            {"kernel_share_of_step": k_ms / ms,
+             "traffic": (peaks["hmm_dram_bytes_per_step_config4"] * (args.hmm_batches / 1000.0)
+                         if peaks.get("hmm_dram_bytes_per_step_config4") else None),
+             "traffic_note": "DRAM bytes of the stream-kernel launches of one step from the committed ncu launch list, "
+                             "scaled by batches; FP32-bound, HBM time ~0.04 ms"}),
+        "fp64_rescue": {"unrelated_read_fraction": args.hmm_unrelated, "pairs_rescued": int(rescued),
+                        "fraction_of_pairs": (rescued / n_pairs if rescued >= 0 else None),
+                        "fp64_kernel_ms": (float(np.mean(f_ms)) if f_ms else 0.0),
+                        "note": "pairs whose FP32 forward sum fell below 2^-100 (or was not finite) re-run by "
+                                "hmm_striped_kernel<double,4>; inside the timed region"},
         "gpu_launches": int(launches), "clocks": clk.summary(),
         "pairs_per_gpu": n_pairs, "cells_per_gpu": cells,
     }
 
 
-def run_sw_long(args):
-    """BASELINE configs[4]: ONE pair of --long-len x --long-len, columns striped over --gpus B200s of this
-    box inside one process (NVLink peer boundary exchange), through the host C ABI."""
-    import torch
-    import agxpkg
-    import oracle
-    agx = agxpkg.load()
+# ----------------------------------------------------------------- rank 0, one process, all N GPUs of the box
+def expected_long_score(length, seed, related):
+    try:
+        for rec in json.loads((ROOT / "tests" / "golden" / "sw_long_expected.json").read_text()):
+            if (rec["len"], rec["seed"], rec["related"]) == (length, seed, related):
+                return rec["score"]
+    except Exception:
+        pass
+    return None
+
+
+def bench_sw_long(agx, args, n_gpus):
+    """BASELINE configs[4]: one pair, columns striped over the GPUs inside this process (sw_long.cu)."""
     cap = agx.capi
-    n_gpus = min(args.gpus, torch.cuda.device_count())
-    cap.init(n_gpus)
-    cap.set_profiling(True)
     L = args.long_len
     inp = agx.formats.parse_sw(agx.synth.sw_long_pair(L, seed=5, related=True), line_buf=1 << 30)
     cells = float(L) * float(L)
-    for _ in range(max(1, min(args.warmup, 2))):
-        score = int(cap.sw_score_flat(inp.buf, inp.off, inp.len)[0])
-    cap.reset_launch_count()
-    with ClockSampler(0) as clk:
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
+    steps = max(1, min(args.steps, 5))
+
+    def timed(devices):
+        cap.shutdown()
+        cap.init_devices(devices)
+        cap.set_profiling(True)
+        for _ in range(2):
             score = int(cap.sw_score_flat(inp.buf, inp.off, inp.len)[0])
-        dt = (time.perf_counter() - t0) / args.steps
-    launches = cap.launch_count()
-    # CPU: the MAX_LINE_LENGTH-raised reference build on a smaller square, extrapolation labelled
-    cpu = None
-    ref_exe = ROOT / "oracle" / "_ref" / "sw_antidiag_long"
-    if not args.no_cpu_baseline and ref_exe.exists():
-        n_small = 20000
-        with tempfile.TemporaryDirectory() as td:
-            pth = Path(td) / "small.in"
-            pth.write_bytes(agx.synth.sw_long_pair(n_small, seed=6, related=True))
-            t1 = time.perf_counter()
-            oracle.run_ref_sw(str(pth), long_lines=True)
-            cdt = time.perf_counter() - t1
-        g = n_small * n_small / cdt / 1e9
-        cpu = {"value": g, "unit": "GCUPS", "cores": 1, "kind": "reference",
-               "sample": f"oracle/_ref/sw_antidiag_long (MAX_LINE_LENGTH raised, arithmetic untouched) on one {n_small}x{n_small} pair; "
-                         f"the reference is single-threaded per pair; {L}x{L} would take ~{cells / (g * 1e9) / 3600:.1f} core-hours (extrapolated)"}
-    peaks = measured_peaks()
-    peak = peaks["alu_tlaneops"] * 1e12 if peaks and peaks.get("alu_tlaneops") else NOMINAL_ALU
-    line = {"metric": "SW and PairHMM GCUPS", "value": cells / dt / 1e9, "unit": "GCUPS", "n_gpus": n_gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        cap.reset_launch_count()
+        with ClockSampler(devices[0]) as clk:
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                score = int(cap.sw_score_flat(inp.buf, inp.off, inp.len)[0])
+            dt = (time.perf_counter() - t0) / steps
+        k_ms = [cap.profile_ms(dv, cap.PROF_SW_LONG) for dv in devices]
+        return dt * 1e3, score, k_ms, cap.launch_count() // steps, clk.summary()
+
+    ms1, score1, k1, launches1, clocks1 = timed([0])
+    out = {"workload": f"one pair {L} x {L} (synth.sw_long_pair seed 5, 2 % substitutions + 0.5 % indels), through sw_score_batch_flat",
+           "unit": "GCUPS", "n_gpus": n_gpus, "scaling": "strong", "dtype": "int32", "steps": steps,
+           "ms_1gpu": ms1, "gcups_1gpu": cells / (ms1 * 1e-3) / 1e9, "kernel_ms_1gpu": k1[0]}
+    ms, score, k_ms, launches, clocks = ms1, score1, k1, launches1, clocks1
+    if n_gpus > 1:
+        ms, score, k_ms, launches, clocks = timed(list(range(n_gpus)))
+        out["score_matches_1gpu"] = bool(score == score1)
+    expected = expected_long_score(L, 5, True)
+    out.update({"ms": ms, "value": cells / (ms * 1e-3) / 1e9, "speedup_vs_1gpu": ms1 / ms,
+                "pipeline_efficiency": ms1 / (n_gpus * ms), "kernel_ms_per_gpu": k_ms, "gpu_launches": int(launches),
+                "score": score, "score_expected": expected,
+                "score_expected_source": "tests/golden/sw_long_expected.json: oracle/sw_blocked.c on host cores (tests/golden/make_long_expected.py)",
+                "score_ok": (None if expected is None else bool(score == expected and score1 == expected)),
+                "h2d_bytes_per_step": int(2 * (L + 1)) if n_gpus == 1 else int((L + 1) * (n_gpus + 1)),
+                "d2h_bytes_per_step": 4 * n_gpus, "clocks": clocks,
+                "roofline": roofline_obj("alu", "sw_longr_kernel<K,R> (s32 DPX, symbol-coded, dp4a substitution), one GPU",
+                                         cells, k1[0] if k1[0] > 0 else ms1, LONG_OPS, "Tlaneop/s (INT32/DPX alu pipe)",
+                                         "sw_long_alu_pipe_active_pct", {"traffic": None})})
+    return out
+
+
+def split_hmm(inp, parts):
+    """`parts` contiguous groups of whole batches, each as its own HmmInput (offsets rebased)."""
+    from types import SimpleNamespace
+    nb = inp.n_batches
+    cuts = [nb * k // parts for k in range(parts + 1)]
+    out = []
+    for k in range(parts):
+        b0, b1 = cuts[k], cuts[k + 1]
+        r0, r1 = int(inp.batch_read_start[b0]), int(inp.batch_read_start[b1])
+        h0, h1 = int(inp.batch_hap_start[b0]), int(inp.batch_hap_start[b1])
+        lo = int(min(inp.read_field_off[r0:r1].min(), inp.hap_off[h0:h1].min()))
+        hi = int(max((inp.read_field_off[r0:r1, 4] + inp.read_len[r0:r1]).max(), (inp.hap_off[h0:h1] + inp.hap_len[h0:h1]).max()))
+        nr_b = np.diff(inp.batch_read_start[b0:b1 + 1])
+        nh_b = np.diff(inp.batch_hap_start[b0:b1 + 1])
+        out.append(SimpleNamespace(
+            buf=inp.buf[lo:hi], read_field_off=inp.read_field_off[r0:r1] - lo, read_len=inp.read_len[r0:r1],
+            hap_off=inp.hap_off[h0:h1] - lo, hap_len=inp.hap_len[h0:h1],
+            batch_read_start=inp.batch_read_start[b0:b1 + 1] - r0, batch_hap_start=inp.batch_hap_start[b0:b1 + 1] - h0,
+            n_batches=b1 - b0, n_pairs=int(np.sum(nr_b * nh_b))))
+    return out
+
+
+def bench_strong(agx, args, n_gpus):
+    """ONE 10^6-pair batch of each kind through the library's in-process dispatcher bound to all n_gpus GPUs:
+    end to end from pinned host buffers, and resident (one device-resident shard per GPU)."""
+    import torch
+    cap = agx.capi
+    steps = max(1, args.steps)
+    out = {"n_gpus": n_gpus, "scaling": "strong", "unit": "GCUPS",
+           "note": "one process, agx_init over all GPUs, one host thread + stream per GPU, no collective"}
+
+    def wall(fn, warm=2):
+        for _ in range(warm):
+            r = fn()
+        for dv in range(n_gpus):
+            torch.cuda.synchronize(dv)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            r = fn()
+        return 1e3 * (time.perf_counter() - t0) / steps, r
+
+    # ---- Smith-Waterman -------------------------------------------------------------------------------
+    n = args.sw_pairs
+    inp = agx.synth.sw_uniform_pairs(n, SW_LEN, seed=1000)
+    cells = float(n) * SW_LEN * SW_LEN
+    h_buf = torch.from_numpy(inp.buf).pin_memory()
+    np_buf = h_buf.numpy()
+    h_scores = torch.empty(n, dtype=torch.int32).pin_memory()
+    res = {}
+    for label, devs in (("1gpu", [0]), ("ngpu", list(range(n_gpus)))):
+        if label == "ngpu" and n_gpus == 1:
+            res["ngpu"] = res["1gpu"]
+            break
+        cap.shutdown()
+        cap.init_devices(devs)
+        cap.set_profiling(True)
+        img_ms, (img_scores, _, _) = wall(lambda: cap.sw_score_file_image(np_buf, out=h_scores.numpy()))
+        flat_ms, flat_scores = wall(lambda: cap.sw_score_flat(np_buf, inp.off, inp.len))
+        assert np.array_equal(img_scores, flat_scores), "file-image and flat entry points disagree"
+        # resident: contiguous shards of equal pair count, uploaded once
+        g = len(devs)
+        shards, keep = [], []
+        for k, dv in enumerate(devs):
+            p0, p1 = n * k // g, n * (k + 1) // g
+            b0 = int(inp.off[2 * p0]) if p0 < n else int(inp.buf.size)
+            b1 = int(inp.off[2 * p1 - 1] + inp.len[2 * p1 - 1])
+            dev = torch.device("cuda", dv)
+            t_buf = torch.from_numpy(inp.buf[b0:b1]).to(dev)
+            t_off = torch.from_numpy(inp.off[2 * p0:2 * p1] - b0).to(dev)
+            t_len = torch.from_numpy(inp.len[2 * p0:2 * p1]).to(dev)
+            t_out = torch.empty(p1 - p0, dtype=torch.int32, device=dev)
+            keep.append((t_buf, t_off, t_len, t_out))
+            shards.append(cap.SwShard(dv, t_buf.data_ptr(), t_buf.numel(), t_off.data_ptr(), t_len.data_ptr(), p1 - p0, t_out.data_ptr()))
+        res_ms, _ = wall(lambda: cap.sw_score_shards_device(shards), warm=3)
+        k_ms = max(cap.profile_ms(dv, cap.PROF_SW_DUO) for dv in devs)
+        got = np.concatenate([t[3].cpu().numpy() for t in keep])
+        assert np.array_equal(got, flat_scores), "resident shards and host entry points disagree"
+        res[label] = {"e2e_file_image_ms": img_ms, "e2e_flat_ms": flat_ms, "resident_ms": res_ms, "kernel_ms_max_over_gpus": k_ms}
+        del keep, shards
+    one, many = res["1gpu"], res["ngpu"]
+    out["sw"] = {"workload": f"{n} pairs of {SW_LEN}x{SW_LEN} in ONE batch",
+                 "resident": {"value": cells / (many["resident_ms"] * 1e-3) / 1e9, "ms": many["resident_ms"], "ms_1gpu": one["resident_ms"],
+                              "speedup_vs_1gpu": one["resident_ms"] / many["resident_ms"],
+                              "kernel_ms_max_over_gpus": many["kernel_ms_max_over_gpus"], "entry_point": "sw_score_shards_device"},
+                 "e2e": {"value": cells / (many["e2e_file_image_ms"] * 1e-3) / 1e9, "ms": many["e2e_file_image_ms"],
+                         "ms_1gpu": one["e2e_file_image_ms"], "speedup_vs_1gpu": one["e2e_file_image_ms"] / many["e2e_file_image_ms"],
+                         "h2d_bytes_per_step": int(np_buf.nbytes), "d2h_bytes_per_step": int(4 * n), "entry_point": "sw_score_file_image"},
+                 "e2e_flat": {"value": cells / (many["e2e_flat_ms"] * 1e-3) / 1e9, "ms": many["e2e_flat_ms"], "ms_1gpu": one["e2e_flat_ms"],
+                              "speedup_vs_1gpu": one["e2e_flat_ms"] / many["e2e_flat_ms"], "entry_point": "sw_score_batch_flat"}}
+    del h_buf, h_scores
+
+    # ---- PairHMM --------------------------------------------------------------------------------------
+    hin = agx.synth.pairhmm_batches(args.hmm_batches, 200, 5, seed=2000, unrelated_frac=args.hmm_unrelated)
+    hcells = float(hin.cells())
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    arrs = [pin(x).numpy() for x in (hin.buf, hin.read_field_off.reshape(-1), hin.read_len, hin.hap_off, hin.hap_len,
+                                     hin.batch_read_start, hin.batch_hap_start)]
+    res = {}
+    for label, devs in (("1gpu", [0]), ("ngpu", list(range(n_gpus)))):
+        if label == "ngpu" and n_gpus == 1:
+            res["ngpu"] = res["1gpu"]
+            break
+        cap.shutdown()
+        cap.init_devices(devs)
+        cap.set_profiling(True)
+        img_ms, (img_vals, _, _) = wall(lambda: cap.pairhmm_forward_file_image(arrs[0]))
+        flat_ms, flat_vals = wall(lambda: cap.pairhmm_forward_flat(*arrs))
+        assert np.array_equal(img_vals, flat_vals, equal_nan=True), "file-image and flat entry points disagree"
+        parts = split_hmm(hin, len(devs))
+        shards, keep = [], []
+        for part, dv in zip(parts, devs):
+            d = hmm_device_arrays(part, torch.device("cuda", dv))
+            keep.append(d)
+            shards.append(cap.HmmShard(dv, d["buf"].data_ptr(), d["buf"].numel(), d["rfo"].data_ptr(), d["rl"].data_ptr(),
+                                       d["rb"].data_ptr(), d["roo"].data_ptr(), part.read_len.size, d["ho"].data_ptr(),
+                                       d["hl"].data_ptr(), part.hap_len.size, d["bhs"].data_ptr(), part.n_batches, part.n_pairs,
+                                       d["out"].data_ptr()))
+        res_ms, _ = wall(lambda: cap.pairhmm_forward_shards_device(shards, True), warm=3)
+        k_ms = max(cap.profile_ms(dv, cap.PROF_HMM_STREAM) for dv in devs)
+        got = np.concatenate([d["out"].cpu().numpy() for d in keep])
+        assert np.array_equal(got, flat_vals, equal_nan=True), "resident shards and host entry points disagree"
+        res[label] = {"e2e_file_image_ms": img_ms, "e2e_flat_ms": flat_ms, "resident_ms": res_ms, "kernel_ms_max_over_gpus": k_ms}
+        del keep, shards
+    one, many = res["1gpu"], res["ngpu"]
+    out["pairhmm"] = {"workload": f"{hin.n_pairs} (read, haplotype) pairs in ONE call ({hin.n_batches} batches)",
+                      "resident": {"value": hcells / (many["resident_ms"] * 1e-3) / 1e9, "ms": many["resident_ms"], "ms_1gpu": one["resident_ms"],
+                                   "speedup_vs_1gpu": one["resident_ms"] / many["resident_ms"],
+                                   "kernel_ms_max_over_gpus": many["kernel_ms_max_over_gpus"], "entry_point": "pairhmm_forward_shards_device"},
+                      "e2e": {"value": hcells / (many["e2e_file_image_ms"] * 1e-3) / 1e9, "ms": many["e2e_file_image_ms"],
+                              "ms_1gpu": one["e2e_file_image_ms"], "speedup_vs_1gpu": one["e2e_file_image_ms"] / many["e2e_file_image_ms"],
+                              "h2d_bytes_per_step": int(arrs[0].nbytes), "d2h_bytes_per_step": int(8 * hin.n_pairs),
+                              "entry_point": "pairhmm_forward_file_image"},
+                      "e2e_flat": {"value": hcells / (many["e2e_flat_ms"] * 1e-3) / 1e9, "ms": many["e2e_flat_ms"], "ms_1gpu": one["e2e_flat_ms"],
+                                   "speedup_vs_1gpu": one["e2e_flat_ms"] / many["e2e_flat_ms"], "entry_point": "pairhmm_forward_batches_flat"}}
+    return out
+
+
+def bench_gatk(agx, args, device_index):
+    """configs[3] with the corrected GATK priors -- reported separately, never a parity claim against the reference."""
+    import torch
+    cap = agx.capi
+    device = torch.device("cuda", device_index)
+    inp = agx.synth.pairhmm_batches(args.hmm_batches, 200, 5, seed=2000, unrelated_frac=args.hmm_unrelated)
+    d = hmm_device_arrays(inp, device)
+    stream = torch.cuda.current_stream(device).cuda_stream
+    cells = float(inp.cells())
+    out = {"unit": "GCUPS", "workload": "the \"pairhmm\" workload of rank 0"}
+
+    def step():
+        cap.pairhmm_forward_device(device_index, d["buf"].data_ptr(), d["buf"].numel(), d["rfo"].data_ptr(), d["rl"].data_ptr(),
+                                   d["rb"].data_ptr(), d["roo"].data_ptr(), inp.read_len.size, d["ho"].data_ptr(),
+                                   d["hl"].data_ptr(), inp.hap_len.size, d["bhs"].data_ptr(), inp.n_batches, inp.n_pairs,
+                                   d["out"].data_ptr(), stream, True)
+
+    results = {}
+    try:
+        for mode, name in ((0, "reference"), (1, "gatk"), (3, "gatk_qual_floor")):
+            cap.set_pairhmm_gatk_mode(mode)
+            for _ in range(2):
+                step()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize(device)
+            results[name] = d["out"].cpu().numpy().copy()
+            if mode:
+                ms = e0.elapsed_time(e1) / args.steps
+                out[name] = {"value": cells / (ms * 1e-3) / 1e9, "ms_per_step": ms}
+    finally:
+        cap.set_pairhmm_gatk_mode(0)
+    diff = results["reference"] - results["gatk"]                     # >= 0: the /3 can only lower a likelihood
+    fin = np.isfinite(diff)
+    out["gatk"].update({"mismatch_prior": "Qr/3", "pairs_that_differ_from_reference_mode": int(np.count_nonzero(np.abs(diff[fin]) > 1e-9)),
+                        "mean_log10_shift": float(diff[fin].mean()), "max_log10_shift": float(diff[fin].max()),
+                        "log10_3": float(np.log10(3.0))})
+    out["gatk_qual_floor"].update({"mismatch_prior": "Qr/3", "base_quality_floor": 6,
+                                   "pairs_that_differ_from_gatk_mode": int(np.count_nonzero(results["gatk"] != results["gatk_qual_floor"]))})
+    out["_results"] = results
+    out["_input"] = inp
+    return out
+
+
+def bench_sw_lengths(agx, args, device_index):
+    """The inter-task kernel one length class at a time: the published MI210 sweep lengths (hiprun.sh:18) and
+    generator.py's own 450-500 bp (generator.py:4-5)."""
+    import torch
+    cap = agx.capi
+    device = torch.device("cuda", device_index)
+    stream = torch.cuda.current_stream(device).cuda_stream
+    peak, _ = pipe_peak("alu")
+    rows = []
+    rng = np.random.default_rng(4242)
+    for spec in args.sw_len.split(","):
+        spec = spec.strip()
+        if not spec:
+            continue
+        if "-" in spec:
+            lo, hi = (int(x) for x in spec.split("-"))
+            n = max(2000, int(args.sw_len_cells / (0.25 * (lo + hi) ** 2)))
+            inp = agx.formats.parse_sw(agx.synth.sw_random_file(rng, n, lo, hi), line_buf=1 << 20)
+        else:
+            lo = hi = int(spec)
+            n = max(2000, int(args.sw_len_cells / (lo * lo)))
+            inp = agx.synth.sw_uniform_pairs(n, lo, seed=500 + lo)
+        plain = inp.len.astype(np.int64) - (inp.buf[inp.off + inp.len - 1] == 10)      # without the newline symbol
+        cells = float(np.sum(plain[0::2] * plain[1::2]))
+        d_buf, d_off, d_len = (torch.from_numpy(x).to(device) for x in (inp.buf, inp.off, inp.len))
+        d_out = torch.empty(inp.off.size // 2, dtype=torch.int32, device=device)
+        step = lambda: cap.sw_score_device(device_index, d_buf.data_ptr(), d_buf.numel(), d_off.data_ptr(), d_len.data_ptr(),
+                                           inp.off.size // 2, d_out.data_ptr(), stream)
+        for _ in range(3):
+            step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k_ms = []
+        e0.record()
+        for _ in range(args.steps):
+            step()
+            k_ms.append(cap.profile_ms(device_index, cap.PROF_SW_DUO))
+        e1.record()
+        torch.cuda.synchronize(device)
+        ms = e0.elapsed_time(e1) / args.steps
+        k = float(np.mean(k_ms))
+        rows.append({"len": spec, "pairs": int(inp.off.size // 2), "cells": cells, "ms_per_step": ms, "value": cells / (ms * 1e-3) / 1e9,
+                     "kernel_ms": k, "kernel_gcups": cells / (k * 1e-3) / 1e9,
+                     "alu_frac_executed": cells * SW_OPS["executed"] / (k * 1e-3) / peak})
+    return {"unit": "GCUPS", "ops_per_cell_executed": SW_OPS["executed"],
+            "note": "resident batch of one length class; cells = len_a x len_b without the newline symbol; padding columns/rows "
+                    "of the class count as lost throughput", "lengths": rows}
+
+
+def cpu_leg(agx, args, gatk):
+    """cpu_baseline (rank 0, N = 1): the reference C programs on the host cores, the GPU against their output on
+    the same shards, and the GATK mode against the oracle's GATK branch.  The one place bench.py's GPU arm runs
+    anything under oracle/."""
+    cap = agx.capi
+    ref = CpuReference()
+    out = {}
+    # >= 10^6 pairs of each configuration once per run when the box has the cores for it (16 cores: ~20 s each)
+    budget_pairs = args.cpu_seconds * ref.cores * 60e6 / (SW_LEN * SW_LEN)
+    sw_pairs = int(min(args.sw_pairs, budget_pairs)) // ref.cores
+    ref.prepare_sw(max(200, sw_pairs))
+    v, dt = ref.sw_gcups()
+    out["cpu_sw"] = ref.baseline_obj("sw", v)
+    out["cpu_sw"]["seconds"] = dt
+    budget_batches = args.cpu_seconds * ref.cores * 160e6 / 6.1e7
+    hmm_batches = int(min(args.hmm_batches, budget_batches)) // ref.cores
+    ref.prepare_hmm(max(1, hmm_batches), unrelated_frac=args.hmm_unrelated)
+    v, dt = ref.hmm_gcups()
+    out["cpu_hmm"] = ref.baseline_obj("hmm", v)
+    out["cpu_hmm"]["seconds"] = dt
+    par = {"reference": ("oracle/_ref programs' own output (Score: %d lines / %f file)" if ref.kind == "reference" else "oracle port"),
+           "gpu_entry_points": "sw_score_file_image / pairhmm_forward_file_image on the same shard files"}
+    par.update(ref.parity_sw(cap))
+    par.update(ref.parity_hmm(cap))
+    out["parity"] = par
+    if gatk is not None:
+        import oracle
+        inp, results = gatk["_input"], gatk["_results"]
+        n_check = 400
+        for name, mode in (("gatk", 1), ("gatk_qual_floor", 3)):
+            want = oracle.pairhmm_flat(inp, gatk=mode, limit=n_check)
+            got = results[name][:want.size]
+            fin = np.isfinite(want)
+            assert np.array_equal(got[~fin], want[~fin]), "GATK mode: non-finite results differ from the oracle's"
+            gatk[name]["max_rel_vs_oracle_gatk_branch"] = float(np.max(np.abs(got[fin] - want[fin]) / np.abs(want[fin])))
+            gatk[name]["pairs_checked"] = int(want.size)
+    return out
+
+
+def run_sw_long(args):
+    """--workload sw_long: BASELINE configs[4] alone, as the headline of the line."""
+    import torch
+    import agxpkg
+    agx = agxpkg.load()
+    n_gpus = min(args.gpus, torch.cuda.device_count())
+    obj = bench_sw_long(agx, args, n_gpus)
+    L = args.long_len
+    line = {"metric": "SW and PairHMM GCUPS", "value": obj["value"], "unit": "GCUPS", "n_gpus": n_gpus,
+            "steps": obj["steps"], "warmup": 2, "ms_per_step": obj["ms"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": f"sw_long: one pair {L}x{L} (BASELINE configs[4]), column stripes over {n_gpus} GPU(s) in one process",
-                       "score": score},
-            "e2e": {"value": cells / dt / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": int(2 * (L + 1)) * n_gpus,
-                    "d2h_bytes_per_step": 4 * n_gpus},
-            "roofline": {"bound": "alu", "kernel": "sw_long_kernel<K> (s32 DPX)", "achieved": cells * 8 / dt / 1e12 / n_gpus,
-                         "peak": peak / 1e12, "unit": "Tlaneop/s per GPU (INT32/DPX pipe)", "frac": cells * 8 / dt / n_gpus / peak,
-                         "ops_per_cell": 8.0, "traffic": None},
-            "gpu_launches": int(launches), "clocks": clk.summary()}
-    if cpu:
-        line["cpu_baseline"] = cpu
+            "config": {"workload": f"sw_long: one pair {L}x{L} (BASELINE configs[4]), column stripes over {n_gpus} GPU(s) in one process"},
+            "e2e": {"value": obj["value"], "unit": "GCUPS", "h2d_bytes_per_step": obj["h2d_bytes_per_step"],
+                    "d2h_bytes_per_step": obj["d2h_bytes_per_step"]},
+            "roofline": obj["roofline"], "gpu_launches": obj["gpu_launches"], "clocks": obj["clocks"], "sw_long": obj}
     emit(line)
-    cap.shutdown()
+    agx.capi.shutdown()
     return 0
 
 
@@ -562,9 +956,11 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     bind_to_gpu_numa_node(local_rank)
+    park = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
+        park = dist.new_group(backend="gloo")          # CPU-side barrier: parked ranks must not hold an SM
     cap = agx.capi
     cap.init_devices([local_rank])
     cap.set_profiling(True)
@@ -572,17 +968,34 @@ def run_gpu_arm(args):
     sw = bench_sw(agx, args, rank, local_rank, world, device) if args.workload in ("both", "sw") else None
     hmm = bench_hmm(agx, args, rank, local_rank, world, device) if args.workload in ("both", "pairhmm") else None
 
-    cpu_sw = cpu_hmm = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ref = CpuReference()
-        if sw is not None:
-            ref.prepare_sw(max(200, int(args.cpu_seconds * 37e6 / (SW_LEN * SW_LEN))))
-            v, _ = ref.sw_gcups()
-            cpu_sw = ref.baseline_obj("sw", v)
-        if hmm is not None:
-            ref.prepare_hmm(max(1, int(round(args.cpu_seconds * 78e6 / 6.1e7))))
-            v, _ = ref.hmm_gcups()
-            cpu_hmm = ref.baseline_obj("hmm", v)
+    # ---- sections that one process runs over ALL GPUs of the box: the other ranks release their GPUs and wait ----
+    extras = {}
+    if world > 1:
+        barrier(world)
+        if rank != 0:
+            cap.shutdown()
+            torch.cuda.empty_cache()
+    if rank == 0 and args.workload == "both":
+        n_box = world if world > 1 else 1
+        try:
+            if not args.no_sw_long:
+                extras["sw_long"] = bench_sw_long(agx, args, n_box)
+            if not args.no_strong:
+                extras["strong"] = bench_strong(agx, args, n_box)
+        finally:
+            cap.shutdown()
+            cap.init_devices([local_rank])
+            cap.set_profiling(True)
+        gatk = bench_gatk(agx, args, local_rank) if not args.no_gatk else None
+        if world == 1 and args.sw_len:
+            extras["sw_lengths"] = bench_sw_lengths(agx, args, local_rank)
+        if world == 1 and not args.no_cpu_baseline:
+            extras.update(cpu_leg(agx, args, gatk))
+        if gatk is not None:
+            extras["pairhmm_gatk"] = {k: v for k, v in gatk.items() if not k.startswith("_")}
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier(group=park)
 
     if rank == 0:
         head = sw if sw is not None else hmm
@@ -599,7 +1012,9 @@ def run_gpu_arm(args):
                 "workload": ("sw_short: %d pairs of %dx%d per GPU (BASELINE configs[2], headline value)" %
                              (args.sw_pairs, SW_LEN, SW_LEN) if sw is not None else "") +
                             (" + pairhmm_hc: %d batches x 200 reads x 5 haplotypes per GPU (BASELINE configs[3], "
-                             "\"pairhmm\" object)" % args.hmm_batches if hmm is not None else ""),
+                             "\"pairhmm\" object)" % args.hmm_batches if hmm is not None else "") +
+                            (" + sw_long 1 Mbp x 1 Mbp over all GPUs in one process (BASELINE configs[4], \"sw_long\" object)"
+                             if "sw_long" in extras else ""),
                 "parallelism": f"pair-sharded x{world}, no collective",
                 "l2": "inputs larger than L2 (302 MB SW batch, 176 MB PairHMM batch; 126 MB L2); no explicit flush",
                 "cells_counted": "len_a*len_b per pair, newline row/column excluded",
@@ -609,21 +1024,24 @@ def run_gpu_arm(args):
         }
         if "e2e_flat" in head:
             line["e2e_flat"] = head["e2e_flat"]
-        if cpu_sw is not None:
-            line["cpu_baseline"] = cpu_sw
-        elif cpu_hmm is not None and sw is None:
-            line["cpu_baseline"] = cpu_hmm
+        if "cpu_sw" in extras:
+            line["cpu_baseline"] = extras["cpu_sw"]
+        elif "cpu_hmm" in extras and sw is None:
+            line["cpu_baseline"] = extras["cpu_hmm"]
         if hmm is not None and sw is not None:
-            sub = {k: hmm[k] for k in ("value", "unit", "dtype", "ms_per_step", "e2e", "e2e_flat", "roofline", "gpu_launches",
-                                       "clocks", "pairs_per_gpu", "cells_per_gpu")}
-            if cpu_hmm is not None:
-                sub["cpu_baseline"] = cpu_hmm
+            sub = {k: hmm[k] for k in ("value", "unit", "dtype", "ms_per_step", "e2e", "e2e_flat", "roofline", "fp64_rescue",
+                                       "gpu_launches", "clocks", "pairs_per_gpu", "cells_per_gpu")}
+            if "cpu_hmm" in extras:
+                sub["cpu_baseline"] = extras["cpu_hmm"]
             line["pairhmm"] = sub
+        for key in ("sw_long", "strong", "pairhmm_gatk", "sw_lengths", "parity"):
+            if key in extras:
+                line[key] = extras[key]
         emit(line)
     cap.shutdown()
     if world > 1:
         import torch.distributed as dist
-        dist.barrier()
+        dist.barrier(group=park)
         dist.destroy_process_group()
     return 0
 
@@ -669,8 +1087,16 @@ def main():
     ap.add_argument("--long-len", type=int, default=1_000_000, help="sw_long: side of the single pair")
     ap.add_argument("--sw-pairs", type=int, default=1_000_000, help="SW pairs per GPU per step")
     ap.add_argument("--hmm-batches", type=int, default=1000, help="PairHMM batches (200 reads x 5 haps) per GPU per step")
-    ap.add_argument("--cpu-seconds", type=float, default=8.0, help="CPU-baseline sample size, seconds of work per core")
+    ap.add_argument("--hmm-unrelated", type=float, default=0.001, help="fraction of unrelated reads (the FP64-rescue tail)")
+    ap.add_argument("--sw-len", default="64,128,256,512,1024,450-500",
+                    help="length classes of the \"sw_lengths\" sweep (L or LO-HI, comma separated; empty = skip)")
+    ap.add_argument("--sw-len-cells", type=float, default=5e9, help="cells per length class of that sweep")
+    ap.add_argument("--cpu-seconds", type=float, default=25.0,
+                    help="CPU-baseline sample: seconds of reference work per core (capped at one full 10^6-pair batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sw-long", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--no-gatk", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "agx":
         args.warmup = max(args.warmup, 3)

@@ -72,8 +72,10 @@ static int split_on_host(const unsigned char *img, size_t size, double **lh_out,
     push64(&bhs, 0);
     size_t pos = 0, start, l;
     const char *err = NULL;
+    /* declared once, outside the batch loop, as in the reference (antidiagsPairHMM.c:345-346): a header that
+     * sscanf() cannot (fully) parse keeps the previous batch's count(s) */
+    int num_read = 0, num_haplotypes = 0;
     while (next_line(img, size, &pos, &start, &l)) {
-        int num_read = 0, num_haplotypes = 0;
         char head[64];
         size_t c = l < sizeof head - 1 ? l : sizeof head - 1;
         memcpy(head, img + start, c);

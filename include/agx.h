@@ -129,6 +129,23 @@ int sw_score_batch_device(int32_t device, const uint8_t *d_seqs, int64_t seqs_by
                           int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend,
                           int32_t *d_scores_out, void *stream);
 
+/* Several device-resident shards in ONE call, one per GPU: the library's multi-GPU dispatcher (one host thread
+ * + one stream per GPU, no collective -- pairs are independent) without the host<->device copies, i.e. what
+ * sw_score_batch_flat does after its uploads.  Every pointer of shards[k] is a device pointer on
+ * shards[k].device (a CUDA ordinal that was passed to agx_init*; each device at most once).  Returns when every
+ * shard's scores are complete in its d_scores_out. */
+typedef struct {
+    int32_t device;
+    const uint8_t *d_seqs;
+    int64_t seqs_bytes;
+    const int64_t *d_off;
+    const int32_t *d_len;
+    int64_t n_pairs;
+    int32_t *d_scores_out;
+} agx_sw_shard;
+int sw_score_shards_device(const agx_sw_shard *shards, int32_t n_shards,
+                           int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend);
+
 /* ------------------------------------------------------------------ PairHMM forward */
 
 /* One batch: every read against every haplotype (the Cartesian loop of
@@ -194,9 +211,35 @@ int pairhmm_forward_batches_device(int32_t device, const uint8_t *d_buf, int64_t
                                    int64_t n_pairs, int32_t fp64_rescue, double *d_log10_out,
                                    void *stream);
 
+/* The same for several device-resident shards, one per GPU (see sw_score_shards_device); the fields are the
+ * arguments of pairhmm_forward_batches_device. */
+typedef struct {
+    int32_t device;
+    const uint8_t *d_buf;
+    int64_t buf_bytes;
+    const int64_t *d_read_field_off;
+    const int32_t *d_read_len;
+    const int32_t *d_read_batch;
+    const int64_t *d_read_out_off;
+    int64_t n_reads;
+    const int64_t *d_hap_off;
+    const int32_t *d_hap_len;
+    int64_t n_haps;
+    const int64_t *d_batch_hap_start;
+    int64_t n_batches;
+    int64_t n_pairs;
+    double *d_log10_out;
+} agx_hmm_shard;
+int pairhmm_forward_shards_device(const agx_hmm_shard *shards, int32_t n_shards, int32_t fp64_rescue);
+
+/* Pairs the FP64 kernel re-ran in the last PairHMM call on `device` that read the count back (the host entry
+ * points and the device variants with fp64_rescue != 0); -1 when unknown. */
+int64_t agx_pairhmm_rescue_count(int32_t device);
+
 /* PairHMM numeric mode (process-wide).  0 (default) = the reference's semantics (mismatch prior
- * Qr).  1 = corrected GATK semantics (mismatch prior Qr/3), reported separately and never used
- * for parity claims. */
+ * Qr, antidiagsPairHMM.c:111-113).  Bit 0 = corrected GATK semantics (mismatch prior Qr/3); bit 1 (with bit 0)
+ * = GATK's base-quality floor as well (base qualities below 6 are read as 6).  Reported separately and never
+ * used for parity claims. */
 int agx_pairhmm_set_gatk_mode(int32_t on);
 
 /* Force every PairHMM pair through the FP64 kernel (debug / accuracy studies). */

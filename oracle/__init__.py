@@ -78,9 +78,10 @@ def sw_file(path: str, line_buf: int = 1000, cap: int = 1 << 22):
     return out[:min(n, cap)].copy(), int(header.value)
 
 
-def pairhmm_forward(read, hap: bytes, gatk: bool = False) -> float:
+def pairhmm_forward(read, hap: bytes, gatk=False) -> float:
+    """gatk: False / 0 the reference's priors; True / 1 mismatch prior Qr/3; 3 = that plus the base-quality floor 6"""
     bases, q, qi, qd, qg = read
-    return float(lib().oracle_pairhmm_forward(bases, q, qi, qd, qg, len(bases), hap, len(hap), 1 if gatk else 0))
+    return float(lib().oracle_pairhmm_forward(bases, q, qi, qd, qg, len(bases), hap, len(hap), int(gatk)))
 
 
 def pairhmm_file(path: str, cap: int = 1 << 22):

@@ -107,7 +107,9 @@ double oracle_pairhmm_forward(const uint8_t *bases, const uint8_t *q, const uint
     for (int32_t j = 0; j <= hap_len; j++) y0[j] = init;
 
     for (int32_t i = 1; i <= read_len; i++) {
-        const double Qr = oracle_pairhmm_prob(q[i - 1]);
+        /* gatk_mode bit 1: GATK reads base qualities below 6 as 6 (NOT the reference) */
+        const uint8_t qc = ((gatk_mode & 2) && (char)q[i - 1] < 33 + 6) ? 33 + 6 : q[i - 1];
+        const double Qr = oracle_pairhmm_prob(qc);
         const double Qi = oracle_pairhmm_prob(qi[i - 1]);
         const double Qd = oracle_pairhmm_prob(qd[i - 1]);
         const double Qg = oracle_pairhmm_prob(qg[i - 1]);
@@ -116,7 +118,7 @@ double oracle_pairhmm_forward(const uint8_t *bases, const uint8_t *q, const uint
         for (int32_t j = 1; j <= hap_len; j++) {
             const char h = (char)hap[j - 1];
             /* p(): :32-34 -- match prior 1-Qr; mismatch prior Qr (no /3: quirk HMM-Q1) */
-            double prior = (r == h || r == 'N' || h == 'N') ? 1 - Qr : (gatk_mode ? Qr / 3 : Qr);
+            double prior = (r == h || r == 'N' || h == 'N') ? 1 - Qr : ((gatk_mode & 1) ? Qr / 3 : Qr);
             /* :51-53, same association order as the reference expression */
             m1[j] = prior * ((1 - (Qi + Qd)) * m0[j - 1] + (1 - Qg) * (x0[j - 1] + y0[j - 1]));
             x1[j] = m0[j] * Qi + x0[j] * Qg;
@@ -143,8 +145,9 @@ int64_t oracle_pairhmm_file(const char *path, double *out, int64_t cap, int32_t 
     char line[HMM_LINE];
     int64_t n = 0;
     int32_t batches = 0;
+    int nr = 0, nh = 0;                                      /* :345-346: declared once, so a header that sscanf
+                                                                cannot (fully) parse keeps the previous count(s) */
     while (fgets(line, sizeof line, f)) {                    /* :375 */
-        int nr = 0, nh = 0;
         sscanf(line, "%d %d", &nr, &nh);                     /* :378 */
         char **reads = calloc((size_t)(nr > 0 ? nr : 1), sizeof(char *));
         char **haps = calloc((size_t)(nh > 0 ? nh : 1), sizeof(char *));

@@ -53,8 +53,9 @@ double oracle_pairhmm_prob(uint8_t phred33);
  * Restates pairHMMmatrix.c:41-56 (init + M/X/Y recurrences, identical maths to
  * antidiagsPairHMM.c:157-202), p() :32-34 (mismatch prior is Qr, NOT Qr/3 -- the reference's
  * quirk HMM-Q1, reproduced), mm() :36-38, and the final sum + log10 of :59-66
- * (= antidiagsPairHMM.c:206-212, 242).  gatk_mode != 0 switches the mismatch prior to Qr/3
- * (the corrected semantics the north star reports separately; NOT the reference). */
+ * (= antidiagsPairHMM.c:206-212, 242).  gatk_mode bit 0 switches the mismatch prior to Qr/3,
+ * bit 1 adds GATK's base-quality floor of 6 (the corrected semantics the north star reports separately; NOT
+ * the reference). */
 double oracle_pairhmm_forward(const uint8_t *bases, const uint8_t *q, const uint8_t *qi,
                               const uint8_t *qd, const uint8_t *qg, int32_t read_len,
                               const uint8_t *hap, int32_t hap_len, int32_t gatk_mode);

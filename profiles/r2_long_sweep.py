@@ -35,19 +35,41 @@ def run(cols, rows, env, reps=2):
         score = s; best = min(best, dt)
     return best * 1e3, score
 
+def sweep_pipe(cols, rows, ks, rs, bs, dp=(0, 1)):
+    """the software-pipelined kernel (sw_longp_kernel, AGX_LONG_PIPE=1)"""
+    ref_ms, ref_score = run(cols, rows, {"AGX_LONG_OLD": 1, "AGX_LONG_K": ks[0]})
+    print(json.dumps({"cols": cols, "rows": rows, "variant": "round-1 kernel", "K": ks[0], "ms": round(ref_ms, 2), "score": ref_score}), flush=True)
+    for k, r, d, bb in itertools.product(ks, rs, dp, bs):
+        if r > k or (r == 6 and not d):
+            continue
+        try:
+            ms, sc = run(cols, rows, {"AGX_LONG_K": k, "AGX_LONG_R": r, "AGX_LONG_PIPE": 1, "AGX_LONG_DP4A": d, "AGX_LONG_B": bb})
+        except Exception as e:
+            print(json.dumps({"K": k, "R": r, "pipe": 1, "dp4a": d, "B": bb, "error": str(e)[:80]}), flush=True)
+            continue
+        print(json.dumps({"cols": cols, "rows": rows, "K": k, "R": r, "pipe": 1, "dp4a": d, "B": bb, "ms": round(ms, 2),
+                          "gcups": round(cols * rows / ms / 1e6), "ok": sc == ref_score}), flush=True)
+
+
 def sweep(cols, rows, ks, rs, bs, dp=(0, 1), chains=(0, 1)):
     ref_ms, ref_score = run(cols, rows, {"AGX_LONG_OLD": 1, "AGX_LONG_K": ks[0]})
     print(json.dumps({"cols": cols, "rows": rows, "variant": "round-1 kernel", "K": ks[0], "ms": round(ref_ms, 2), "score": ref_score}), flush=True)
     for k, r, ch, d, bb in itertools.product(ks, rs, chains, dp, bs):
         try:
-            ms, sc = run(cols, rows, {"AGX_LONG_K": k, "AGX_LONG_R": r, "AGX_LONG_CHAIN": ch, "AGX_LONG_DP4A": d, "AGX_LONG_B": bb})
+            ms, sc = run(cols, rows, {"AGX_LONG_K": k, "AGX_LONG_R": r, "AGX_LONG_CHAIN": ch, "AGX_LONG_DP4A": d, "AGX_LONG_B": bb,
+                                      "AGX_LONG_PIPE": 0})
         except Exception as e:      # a variant that was not instantiated
             print(json.dumps({"K": k, "R": r, "short": ch, "dp4a": d, "B": bb, "error": str(e)[:80]}), flush=True)
             continue
         print(json.dumps({"cols": cols, "rows": rows, "K": k, "R": r, "short": ch, "dp4a": d, "B": bb, "ms": round(ms, 2),
                           "gcups": round(cols * rows / ms / 1e6), "ok": sc == ref_score}), flush=True)
 
-if mode == "quick":
+if mode == "pipe_share":
+    sweep_pipe(125_000, 1_000_000, [6, 7, 8], [1, 2, 3, 4, 6], [4, 8, 16, 32])
+    sweep_pipe(125_000, 500_000, [7], [1, 2, 3, 4, 6], [8])
+elif mode == "pipe_full":
+    sweep_pipe(1_000_000, 1_000_000, [14, 27], [1, 2, 3, 4, 6], [8, 32])
+elif mode == "quick":
     sweep(125_000, 200_000, [7], [1, 2, 4], [8])
 elif mode == "share":
     sweep(125_000, 1_000_000, [6, 7, 8], [1, 2, 4], [4, 8, 16, 32])

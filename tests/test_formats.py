@@ -149,3 +149,46 @@ def test_pairhmm_truncated_file_message_of_the_reference(agx, oracle_mod, tmp_pa
     path.write_bytes(b"\n".join(lines[:keep]) + b"\n" + extra)
     r = subprocess.run([str(oracle_mod.REF / "pairhmm_antidiag_noleak"), str(path), str(tmp_path / "o")], capture_output=True)
     assert r.returncode != 0 and r.stderr.startswith(message)
+
+
+def _inherited_header_file(agx, trailing_blank=False):
+    """Batch 2's header holds one integer, batch 3's is a blank line: sscanf("%d %d") leaves what it cannot parse
+    as it was, and the reference declares both counts once (antidiagsPairHMM.c:345-346, :378), so both batches
+    inherit from the batch before them."""
+    inp = agx.synth.pairhmm_batches(4, 9, 3, seed=11)
+    lines = bytes(inp.buf).split(b"\n")[:-1]                      # a batch = 1 + 9 + 3 lines
+    assert lines[13] == b"9 3" and lines[26] == b"9 3"
+    lines[13] = b"9"
+    lines[26] = b""
+    return b"\n".join(lines) + b"\n" + (b"\n" if trailing_blank else b"")
+
+
+@pytest.mark.parametrize("which", ["pairhmm_matrix", "pairhmm_antidiag_noleak"])
+def test_pairhmm_header_counts_are_inherited_like_the_references(agx, oracle_mod, tmp_path, which):
+    if not oracle_mod.ref_available(which):
+        pytest.skip("compiled reference not available")
+    data = _inherited_header_file(agx)
+    path = tmp_path / "inherit.in"
+    path.write_bytes(data)
+    vals, _ = oracle_mod.run_ref_pairhmm(str(path), which)
+    host = agx.formats.parse_pairhmm(data)
+    assert host.n_batches == 4 and len(vals) == host.n_pairs == 4 * 27
+    assert np.max(np.abs(vals - oracle_mod.pairhmm_flat(host))) <= 1e-6
+    port, nb = oracle_mod.pairhmm_file(str(path))
+    assert nb == 4 and np.max(np.abs(vals - port)) <= 1e-6
+
+
+def test_pairhmm_trailing_blank_line_is_a_truncated_batch_in_the_reference(agx, oracle_mod, tmp_path):
+    """A blank line after the last batch is read as one more header that inherits the last counts; the file
+    then ends inside that batch: "Error reading haplotypes." and a non-zero exit, the earlier batches kept."""
+    import subprocess
+    if not oracle_mod.ref_available("pairhmm_antidiag_noleak"):
+        pytest.skip("compiled reference not available")
+    data = _inherited_header_file(agx, trailing_blank=True)
+    path = tmp_path / "blank.in"
+    path.write_bytes(data)
+    r = subprocess.run([str(oracle_mod.REF / "pairhmm_antidiag_noleak"), str(path), str(tmp_path / "o")], capture_output=True)
+    assert r.returncode != 0 and r.stderr.startswith(b"Error reading haplotypes.")
+    assert agx.formats.parse_pairhmm(data).n_batches == 4
+    _, nb = oracle_mod.pairhmm_file(str(path))
+    assert nb == 4

@@ -99,3 +99,42 @@ def test_oracle_vs_compiled_reference_random(oracle_mod, agx, tmp_path):
     ref_vals, _ = oracle_mod.run_ref_pairhmm(str(p2), "pairhmm_antidiag")
     mine_vals, _ = oracle_mod.pairhmm_file(str(p2))
     assert np.max(np.abs(ref_vals - mine_vals)) <= 1e-6
+
+
+def test_blocked_oracle_equals_the_plain_one(agx, oracle_mod):
+    """oracle_sw_score_blocked (tile by tile on several threads: what computes the 1 Mbp x 1 Mbp expected score)
+    is the same function as oracle_sw_score: random and related pairs, alphabets with N and the newline symbol,
+    other scoring parameters, tiles that do not divide the lengths, more threads than tiles."""
+    rng = np.random.default_rng(20)
+    for t in range(160):
+        la, lb = int(rng.integers(1, 500)), int(rng.integers(1, 500))
+        alpha = np.frombuffer(b"ACGT" if t % 3 else b"ACGTN\n", np.uint8)
+        a = alpha[rng.integers(0, alpha.size, la)]
+        if t % 2:
+            b = a.copy()
+            m = rng.random(la) < 0.1
+            b[m] = alpha[rng.integers(0, alpha.size, int(m.sum()))]
+            b = b[:max(1, lb)]
+        else:
+            b = alpha[rng.integers(0, alpha.size, lb)]
+        sc = (1, -1, -3, -1) if t % 5 else (3, -2, -5, -2)
+        want = oracle_mod.sw_score(a.tobytes(), b.tobytes(), sc)
+        got = oracle_mod.sw_score_blocked(a.tobytes(), b.tobytes(), sc, tile=int(rng.integers(1, 90)), threads=int(rng.integers(1, 6)))
+        assert got == want
+    data = agx.synth.sw_long_pair(6000, seed=3, related=True)
+    inp = agx.formats.parse_sw(data, line_buf=1 << 30)
+    a = inp.buf[inp.off[0]:inp.off[0] + inp.len[0]].tobytes()
+    b = inp.buf[inp.off[1]:inp.off[1] + inp.len[1]].tobytes()
+    assert oracle_mod.sw_score_blocked(a, b, tile=1024) == oracle_mod.sw_score(a, b)
+
+
+def test_committed_long_expected_scores_are_well_formed():
+    """tests/golden/sw_long_expected.json (made by tests/golden/make_long_expected.py with the blocked oracle)
+    holds the pair bench.py's "sw_long" object and the slow GPU test score."""
+    import json
+    from conftest import GOLDEN
+    recs = json.loads((GOLDEN / "sw_long_expected.json").read_text())
+    keys = {(r["len"], r["seed"], r["related"]) for r in recs}
+    assert (1_000_000, 5, True) in keys
+    for r in recs:
+        assert r["cells"] == r["line_bytes"][0] * r["line_bytes"][1] and 0 < r["score"] <= min(r["line_bytes"])

@@ -298,3 +298,17 @@ def test_device_entry_point_with_reads_in_any_order(agx, gpu_lib):
                                    d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert np.array_equal(d_out.cpu().numpy(), want)
+
+
+def test_file_image_header_counts_are_inherited(agx, gpu_lib, oracle_mod):
+    """A header with fewer than two integers keeps the previous batch's count(s) (antidiagsPairHMM.c:345-346, :378);
+    a blank line after the last batch is then one more, truncated, batch: "Error reading haplotypes."."""
+    from test_formats import _inherited_header_file
+    data = _inherited_header_file(agx)
+    host = agx.formats.parse_pairhmm(data)
+    vals, batch_pairs, incomplete = gpu_lib.pairhmm_forward_file_image(data)
+    assert incomplete == 0 and batch_pairs.tolist() == [27] * 4
+    want = oracle_mod.pairhmm_flat(host)
+    assert np.max(np.abs(vals - want) / np.abs(want)) <= 1e-5
+    vals2, batch_pairs2, incomplete2 = gpu_lib.pairhmm_forward_file_image(_inherited_header_file(agx, trailing_blank=True))
+    assert incomplete2 == 2 and batch_pairs2.tolist() == [27] * 4 and np.array_equal(vals2, vals)

@@ -183,9 +183,42 @@ def test_long_alignment_whole_gpu_kernel(agx, gpu_lib, oracle_mod, n, related):
         assert got[0] > n // 2
 
 
-@pytest.mark.parametrize("k,chain", [(2, 0), (4, 1), (7, 0), (8, 0), (14, 1), (16, 1), (27, 0), (32, 0), (32, 1)])
-def test_long_alignment_stripe_widths_and_chain_forms(agx, gpu_lib, oracle_mod, k, chain, monkeypatch):
-    """Every instantiated stripe width, both chain forms; DNA takes the symbol-coded (PRMT) kernels."""
+@pytest.mark.parametrize("k,rows", [(2, 2), (4, 4), (7, 4), (7, 2), (8, 2), (14, 4), (16, 2), (27, 2), (27, 4), (32, 2), (32, 4)])
+def test_long_alignment_stripe_widths_and_rows_per_step(agx, gpu_lib, oracle_mod, k, rows, monkeypatch):
+    """sw_longr_kernel: instantiated stripe widths, two and four rows per step; DNA takes the symbol-coded kernels."""
+    monkeypatch.setenv("AGX_LONG_K", str(k))
+    monkeypatch.setenv("AGX_LONG_R", str(rows))
+    inp = _long_pair(agx, 17000 + 111 * k + rows, seed=k + rows, related=bool(rows & 4))
+    got = gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len)
+    assert got.tolist() == oracle_mod.sw_scores_flat(inp.buf, inp.off, inp.len).tolist()
+
+
+@pytest.mark.parametrize("bsteps,rows,n", [(1, 4, 16411), (3, 2, 17003), (8, 4, 16999), (16, 2, 21001), (32, 4, 18001)])
+def test_long_alignment_hand_off_block_sizes(agx, gpu_lib, oracle_mod, bsteps, rows, n, monkeypatch):
+    """Row steps per hand-off block (AGX_LONG_B) from 1 to the ring's limit, row counts that do not divide R * B."""
+    monkeypatch.setenv("AGX_LONG_B", str(bsteps))
+    monkeypatch.setenv("AGX_LONG_R", str(rows))
+    monkeypatch.setenv("AGX_LONG_K", "7")
+    inp = _long_pair(agx, n, seed=n + bsteps, related=True)
+    got = gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len)
+    assert got.tolist() == oracle_mod.sw_scores_flat(inp.buf, inp.off, inp.len).tolist()
+
+
+@pytest.mark.parametrize("k,n", [(7, 16777), (8, 17001), (27, 18500)])
+def test_long_alignment_software_pipelined_kernel(agx, gpu_lib, oracle_mod, k, n, monkeypatch):
+    """sw_longp_kernel (rows of a tile run one column apart and wrap into the next step; AGX_LONG_PIPE=1)."""
+    monkeypatch.setenv("AGX_LONG_PIPE", "1")
+    monkeypatch.setenv("AGX_LONG_R", "4")
+    monkeypatch.setenv("AGX_LONG_K", str(k))
+    inp = _long_pair(agx, n, seed=n, related=True)
+    got = gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len)
+    assert got.tolist() == oracle_mod.sw_scores_flat(inp.buf, inp.off, inp.len).tolist()
+
+
+@pytest.mark.parametrize("k,chain", [(4, 0), (8, 1), (16, 0), (32, 1)])
+def test_long_alignment_raw_byte_kernels(agx, gpu_lib, oracle_mod, k, chain, monkeypatch):
+    """More than 7 distinct bytes cannot be symbol-coded: sw_long_kernel, both chain forms (forced here on DNA)."""
+    monkeypatch.setenv("AGX_LONG_RAW", "1")
     monkeypatch.setenv("AGX_LONG_K", str(k))
     monkeypatch.setenv("AGX_LONG_CHAIN", str(chain))
     inp = _long_pair(agx, 17000 + 111 * k, seed=k + chain, related=bool(chain))
@@ -212,25 +245,14 @@ def test_long_alignment_alphabets(agx, gpu_lib, oracle_mod, alphabet, k, monkeyp
     assert got.tolist() == oracle_mod.sw_scores_flat(buf, off, ln).tolist()
 
 
-@pytest.mark.parametrize("k,chain,n", [(2, 1, 16500), (7, 1, 16411), (7, 0, 17003), (8, 1, 21001), (27, 0, 16999), (32, 1, 18000)])
-def test_long_alignment_two_rows_per_step(agx, gpu_lib, oracle_mod, k, chain, n, monkeypatch):
-    """sw_long2_kernel (two rows per step, 64-row hand-off blocks): odd and even row counts, both chain forms."""
-    monkeypatch.setenv("AGX_LONG_ROWS", "2")
-    monkeypatch.setenv("AGX_LONG_K", str(k))
-    monkeypatch.setenv("AGX_LONG_CHAIN", str(chain))
-    inp = _long_pair(agx, n, seed=n + k, related=bool(chain))
-    got = gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len)
-    assert got.tolist() == oracle_mod.sw_scores_flat(inp.buf, inp.off, inp.len).tolist()
-
-
 def test_long_alignment_raw_and_coded_kernels_agree(agx, gpu_lib, monkeypatch):
     inp = _long_pair(agx, 60000, seed=3, related=True)
     coded = gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len)
     monkeypatch.setenv("AGX_LONG_RAW", "1")
     assert gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len).tolist() == coded.tolist()
     monkeypatch.delenv("AGX_LONG_RAW")
-    for rows in ("1", "2"):
-        monkeypatch.setenv("AGX_LONG_ROWS", rows)
+    for rows in ("2", "4"):
+        monkeypatch.setenv("AGX_LONG_R", rows)
         assert gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len).tolist() == coded.tolist()
 
 
@@ -269,6 +291,27 @@ def test_long_alignment_properties_100kbp(agx, gpu_lib):
     half = inp.len.copy()
     half[:] = 50_000
     assert int(gpu_lib.sw_score_flat(inp.buf, inp.off, half)[0]) <= s
+
+
+def test_long_alignment_200kbp_against_the_oracle(agx, gpu_lib, oracle_mod):
+    """200 kbp x 200 kbp (4 * 10^10 cells) against the oracle's recurrence evaluated tile by tile on the host
+    cores (oracle_sw_score_blocked, itself pinned to the plain oracle in tests/test_oracle.py)."""
+    inp = _long_pair(agx, 200_000, seed=12, related=True)
+    a = inp.buf[inp.off[0]:inp.off[0] + inp.len[0]].tobytes()
+    b = inp.buf[inp.off[1]:inp.off[1] + inp.len[1]].tobytes()
+    want = oracle_mod.sw_score_blocked(a, b)
+    assert int(gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len)[0]) == want > 100_000
+
+
+@pytest.mark.parametrize("related", [True, False])
+def test_long_alignment_1mbp_against_the_committed_expected_score(agx, gpu_lib, related):
+    """BASELINE configs[4] at full size: 1 Mbp x 1 Mbp (10^12 cells).  The expected scores were computed once on
+    the CPU by tests/golden/make_long_expected.py (blocked oracle, ~11 minutes per pair on 8 cores)."""
+    import json
+    recs = json.loads((GOLDEN / "sw_long_expected.json").read_text())
+    want = [r["score"] for r in recs if (r["len"], r["seed"], r["related"]) == (1_000_000, 5, related)][0]
+    inp = _long_pair(agx, 1_000_000, seed=5, related=related)
+    assert int(gpu_lib.sw_score_flat(inp.buf, inp.off, inp.len)[0]) == want
 
 
 # ---------------------------------------------------------------- device-side file parser (sw_score_file_image)
