@@ -1043,25 +1043,21 @@ int pairhmm_forward_batches_flat(const uint8_t *buf, int64_t buf_bytes, const in
     return hmm_flat_impl(h, log10_out);
 }
 
+// What one GPU did with (its range of) a PairHMM file image: results stay in c.d_out on the device.
+struct HmmImageRun {
+    int64_t n_out = 0;              // results in c.d_out
+    std::vector<int32_t> bp;        // reads x haplotypes of every complete batch
+    int32_t incomplete = 0;         // the range ends inside a batch (see agx.h)
+    int64_t parsed_end = 0;         // where parsing stopped: the range's size when every byte belongs to a complete batch
+};
+
 // Like sw_score_file_image: the image is uploaded in segments on the copy stream; each region (whole batches)
 // is parsed and paired on the high-priority stream and scored on one of two alternating lanes, so the upload
 // and the host round trips of region k+1 hide behind the stream kernels of region k.  A batch that straddles
-// a region boundary is parsed again at the start of the next region.
-int pairhmm_forward_file_image(const uint8_t *image, int64_t image_bytes, const double **log10_out, int64_t *n_out,
-                               const int32_t **batch_pairs, int64_t *n_batches, int32_t *incomplete)
+// a region boundary is parsed again at the start of the next region.  All streams are idle on return.
+static int hmm_image_run(DeviceCtx &c, const uint8_t *image, int64_t image_bytes, HmmImageRun &run)
 {
-    if (log10_out) *log10_out = nullptr;
-    if (n_out) *n_out = 0;
-    if (batch_pairs) *batch_pairs = nullptr;
-    if (n_batches) *n_batches = 0;
-    if (incomplete) *incomplete = 0;
-    if (image_bytes < 0 || (image_bytes > 0 && !image)) return fail(AGX_EINVAL, "pairhmm: null file image");
-    if (!log10_out || !n_out || !batch_pairs || !n_batches) return fail(AGX_EINVAL, "pairhmm: null argument");
-    if (image_bytes == 0) return AGX_OK;
-    int rc = require_init();
-    if (rc != AGX_OK) return rc;
-    DeviceCtx &c = *g_ctx[0];
-    AGX_CUDA(cudaSetDevice(c.device));
+    int rc;
     cudaStream_t lane_st[2] = {c.lane[0].st, c.lane[1].st};
     HmmWorkspace *lane_ws[2] = {&c.hmm, &c.hmm_b};
     HmmParseWorkspace *lane_parse[2] = {&c.hmm_parse, &c.hmm_parse_b};
@@ -1104,7 +1100,8 @@ int pairhmm_forward_file_image(const uint8_t *image, int64_t image_bytes, const 
 
     // results: the number of outputs is not known before the last region is parsed, so the device buffer
     // grows region by region (regions are few); batch counts go to the host as they are parsed
-    std::vector<int32_t> bp_all;
+    std::vector<int32_t> &bp_all = run.bp;
+    bp_all.clear();
     int64_t out_done = 0, begin = 0, region = 0;
     int32_t inc = 0;
     int32_t carry_nr = 0, carry_nh = 0;       // header counts of the batch before `begin` (antidiagsPairHMM.c:345-346)
@@ -1173,29 +1170,114 @@ int pairhmm_forward_file_image(const uint8_t *image, int64_t image_bytes, const 
         AGX_CUDA(cudaEventRecord(c.lane_done[li], lane_st[li]));
         begin = ps.next_begin;
     }
-    if (rc != AGX_OK) {
-        cudaStreamSynchronize(c.copy_stream);
-        cudaStreamSynchronize(prep);
-        cudaStreamSynchronize(lane_st[0]);
-        cudaStreamSynchronize(lane_st[1]);
-        return rc;
+    cudaStreamSynchronize(c.copy_stream);
+    cudaStreamSynchronize(prep);
+    cudaStreamSynchronize(lane_st[0]);
+    cudaStreamSynchronize(lane_st[1]);
+    if (rc != AGX_OK) return rc;
+    AGX_CUDA(cudaGetLastError());
+    run.n_out = out_done;
+    run.incomplete = inc;
+    run.parsed_end = begin;
+    return AGX_OK;
+}
+
+// Several GPUs: the image is cut at header-shaped lines near the even split points and every GPU runs the
+// single-GPU pipeline on its own byte range (one host thread per GPU, no collective).  A cut is a true batch
+// boundary exactly when the range before it parses to its last byte without a dangling batch -- by induction
+// from the start of the file that is where the reference's own walk reads its next header -- so the ranges are
+// checked for that and anything else (irregular headers, a "header" inside a batch) returns 1: the caller then
+// takes the single-GPU path, which follows the reference's walk.
+static int hmm_file_image_multi(const uint8_t *image, int64_t image_bytes, std::vector<HmmImageRun> &runs, std::vector<int64_t> &cut)
+{
+    const int n_dev = (int)g_ctx.size();
+    if (n_dev < 2 || image_bytes < (int64_t)n_dev * (8 << 20) || getenv("AGX_HMM_IMAGE_ONE_GPU")) return 1;
+    auto header_shaped = [&](int64_t s, int64_t e) {         // [s, e): a line without its newline
+        int64_t p = s;
+        int d0 = 0, bl = 0, d1 = 0;
+        while (p < e && image[p] >= '0' && image[p] <= '9') { ++p; ++d0; }
+        while (p < e && (image[p] == ' ' || image[p] == '\t')) { ++p; ++bl; }
+        while (p < e && image[p] >= '0' && image[p] <= '9') { ++p; ++d1; }
+        return p == e && d0 >= 1 && d0 <= 9 && bl >= 1 && d1 >= 1 && d1 <= 9;
+    };
+    cut.assign(n_dev + 1, image_bytes);
+    cut[0] = 0;
+    for (int d = 1; d < n_dev; ++d) {
+        const int64_t nominal = image_bytes * d / n_dev;
+        const void *nl = memchr(image + nominal, '\n', (size_t)(image_bytes - nominal));
+        int64_t s = nl ? (const uint8_t *)nl - image + 1 : image_bytes;
+        int64_t found = -1;
+        for (int lines = 0; s < image_bytes && lines < (1 << 16); ++lines) {
+            const void *e = memchr(image + s, '\n', (size_t)(image_bytes - s));
+            const int64_t le = e ? (const uint8_t *)e - image : image_bytes;
+            if (header_shaped(s, le)) { found = s; break; }
+            s = le + 1;
+        }
+        if (found < 0 || found <= cut[d - 1]) return 1;
+        cut[d] = found;
     }
-    AGX_CUDA(cudaStreamSynchronize(lane_st[1]));
-    if (out_done > 0) {
-        if ((rc = c.h_out.reserve((size_t)out_done * sizeof(double))) != AGX_OK) return rc;
-        AGX_CUDA(cudaMemcpyAsync(c.h_out.p, c.d_out.p, (size_t)out_done * sizeof(double), cudaMemcpyDeviceToHost, lane_st[0]));
+    runs.assign(n_dev, HmmImageRun());
+    int rc = for_each_device(n_dev, [&](DeviceCtx &c, int d) -> int {
+        return hmm_image_run(c, image + cut[d], cut[d + 1] - cut[d], runs[d]);
+    });
+    if (rc != AGX_OK) return rc;
+    for (int d = 0; d + 1 < n_dev; ++d)
+        if (runs[d].incomplete != 0 || runs[d].parsed_end != cut[d + 1] - cut[d]) return 1;
+    return AGX_OK;
+}
+
+int pairhmm_forward_file_image(const uint8_t *image, int64_t image_bytes, const double **log10_out, int64_t *n_out,
+                               const int32_t **batch_pairs, int64_t *n_batches, int32_t *incomplete)
+{
+    if (log10_out) *log10_out = nullptr;
+    if (n_out) *n_out = 0;
+    if (batch_pairs) *batch_pairs = nullptr;
+    if (n_batches) *n_batches = 0;
+    if (incomplete) *incomplete = 0;
+    if (image_bytes < 0 || (image_bytes > 0 && !image)) return fail(AGX_EINVAL, "pairhmm: null file image");
+    if (!log10_out || !n_out || !batch_pairs || !n_batches) return fail(AGX_EINVAL, "pairhmm: null argument");
+    if (image_bytes == 0) return AGX_OK;
+    int rc = require_init();
+    if (rc != AGX_OK) return rc;
+    DeviceCtx &c0 = *g_ctx[0];
+
+    std::vector<HmmImageRun> runs;
+    std::vector<int64_t> cut;
+    rc = hmm_file_image_multi(image, image_bytes, runs, cut);
+    if (rc < 0) return rc;
+    if (rc == 1) {
+        // one GPU (or an image the ranges could not be validated on)
+        runs.assign(1, HmmImageRun());
+        AGX_CUDA(cudaSetDevice(c0.device));
+        if ((rc = hmm_image_run(c0, image, image_bytes, runs[0])) != AGX_OK) return rc;
     }
-    AGX_CUDA(cudaStreamSynchronize(lane_st[0]));
-    AGX_CUDA(cudaStreamSynchronize(c.copy_stream));
-    if (!bp_all.empty()) {
-        if ((rc = c.h_b.reserve(bp_all.size() * sizeof(int32_t))) != AGX_OK) return rc;
-        memcpy(c.h_b.p, bp_all.data(), bp_all.size() * sizeof(int32_t));
+    // gather: every GPU copies its results to their place in one pinned array; batch counts are concatenated
+    const int n_used = (int)runs.size();
+    std::vector<int64_t> out_at(n_used + 1, 0);
+    size_t n_bp = 0;
+    for (int d = 0; d < n_used; ++d) { out_at[d + 1] = out_at[d] + runs[d].n_out; n_bp += runs[d].bp.size(); }
+    const int64_t total = out_at[n_used];
+    AGX_CUDA(cudaSetDevice(c0.device));
+    if (total > 0 && (rc = c0.h_out.reserve((size_t)total * sizeof(double))) != AGX_OK) return rc;
+    if (n_bp > 0 && (rc = c0.h_b.reserve(n_bp * sizeof(int32_t))) != AGX_OK) return rc;
+    double *h_all = c0.h_out.as<double>();
+    rc = for_each_device(n_used, [&](DeviceCtx &c, int d) -> int {
+        if (runs[d].n_out == 0) return AGX_OK;
+        AGX_CUDA(cudaMemcpyAsync(h_all + out_at[d], c.d_out.p, (size_t)runs[d].n_out * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        AGX_CUDA(cudaStreamSynchronize(c.stream));
+        return AGX_OK;
+    });
+    if (rc != AGX_OK) return rc;
+    size_t w = 0;
+    for (int d = 0; d < n_used; ++d) {
+        if (!runs[d].bp.empty()) memcpy(c0.h_b.as<int32_t>() + w, runs[d].bp.data(), runs[d].bp.size() * sizeof(int32_t));
+        w += runs[d].bp.size();
     }
-    if (incomplete) *incomplete = inc;
-    *n_out = out_done;
-    *n_batches = (int64_t)bp_all.size();
-    *log10_out = out_done > 0 ? c.h_out.as<double>() : nullptr;
-    *batch_pairs = bp_all.empty() ? nullptr : c.h_b.as<int32_t>();
+    if (incomplete) *incomplete = runs[n_used - 1].incomplete;
+    *n_out = total;
+    *n_batches = (int64_t)n_bp;
+    *log10_out = total > 0 ? h_all : nullptr;
+    *batch_pairs = n_bp ? c0.h_b.as<int32_t>() : nullptr;
     return AGX_OK;
 }
 

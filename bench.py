@@ -877,13 +877,13 @@ def cpu_leg(agx, args, gatk):
     out = {}
     # >= 10^6 pairs of each configuration once per run when the box has the cores for it (16 cores: ~20 s each)
     budget_pairs = args.cpu_seconds * ref.cores * 60e6 / (SW_LEN * SW_LEN)
-    sw_pairs = int(min(args.sw_pairs, budget_pairs)) // ref.cores
+    sw_pairs = -(-int(min(args.sw_pairs, budget_pairs)) // ref.cores)
     ref.prepare_sw(max(200, sw_pairs))
     v, dt = ref.sw_gcups()
     out["cpu_sw"] = ref.baseline_obj("sw", v)
     out["cpu_sw"]["seconds"] = dt
     budget_batches = args.cpu_seconds * ref.cores * 160e6 / 6.1e7
-    hmm_batches = int(min(args.hmm_batches, budget_batches)) // ref.cores
+    hmm_batches = -(-int(min(args.hmm_batches, budget_batches)) // ref.cores)
     ref.prepare_hmm(max(1, hmm_batches), unrelated_frac=args.hmm_unrelated)
     v, dt = ref.hmm_gcups()
     out["cpu_hmm"] = ref.baseline_obj("hmm", v)

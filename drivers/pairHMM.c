@@ -167,8 +167,8 @@ int main(int argc, const char *argv[])
         fprintf(stderr, "Error: %s\n", agx_last_error());
         return EXIT_FAILURE;
     }
-    env = getenv("AGX_PAIRHMM_GATK");
-    if (env && atoi(env)) agx_pairhmm_set_gatk_mode(1);
+    env = getenv("AGX_PAIRHMM_GATK");   /* 1: mismatch prior Qr/3; 3: that plus the base-quality floor 6 (not the reference) */
+    if (env && atoi(env)) agx_pairhmm_set_gatk_mode(atoi(env));
     env = getenv("AGX_PAIRHMM_FP64");   /* every pair through the exact-order FP64 kernel */
     if (env && atoi(env)) agx_pairhmm_set_force_fp64(1);
 
@@ -179,16 +179,9 @@ int main(int argc, const char *argv[])
     int32_t incomplete = 0;
     double *lh_host = NULL;          /* host-split path only */
     int32_t *bp_host = NULL;
-    int rc;
-    if (agx_device_count() > 1) {
-        /* several GPUs bound (AGX_NUM_GPUS > 1): the file-image entry point runs on one GPU, the flat one
-           shards the reads over all of them, so split on the host and take that one */
-        rc = split_on_host(img, size, &lh_host, &n_out, &bp_host, &n_batches, &err);
-        lh = lh_host;
-        batch_pairs = bp_host;
-    } else {
-        rc = pairhmm_forward_file_image(img, (int64_t)size, &lh, &n_out, &batch_pairs, &n_batches, &incomplete);
-    }
+    /* the whole file image goes to the library: batch walk and field splitting on the GPU(s); with several GPUs
+       bound (AGX_NUM_GPUS > 1) the image is cut into one range of whole batches per GPU */
+    int rc = pairhmm_forward_file_image(img, (int64_t)size, &lh, &n_out, &batch_pairs, &n_batches, &incomplete);
     if (rc == AGX_OK) {
         if (incomplete == 1) err = "Error reading reads.\n";
         if (incomplete == 2) err = "Error reading haplotypes.\n";

@@ -191,7 +191,9 @@ int pairhmm_forward_batches_flat(const uint8_t *buf, int64_t buf_bytes,
  * what it prints whenever the batch has haplotypes) or "Error reading reads." (*incomplete = 1: a batch
  * without haplotypes, :411-414).
  * AGX_ERANGE when a line exceeds the reference's 5000-byte line buffer (:353) or a read length falls
- * outside [1, 8192].  Runs on the first configured GPU. */
+ * outside [1, 8192].  With several GPUs bound and an image of at least 8 MiB per GPU the image is cut at
+ * header lines into one range of whole batches per GPU (no collective: every GPU parses and scores its own
+ * range; the cuts are verified to be batch boundaries, else the first GPU takes the whole image). */
 int pairhmm_forward_file_image(const uint8_t *image, int64_t image_bytes, const double **log10_out,
                                int64_t *n_out, const int32_t **batch_pairs, int64_t *n_batches,
                                int32_t *incomplete);

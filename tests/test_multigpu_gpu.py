@@ -108,3 +108,66 @@ def test_sw_file_image_is_cut_into_one_range_per_gpu(agx, multi, seed, header_fr
     scores, hdr, dangling = cap.sw_score_file_image(data)
     assert hdr == header and dangling == host.dangling
     assert scores.tolist() == want.tolist()
+
+
+def test_pairhmm_file_image_is_cut_into_one_range_per_gpu(agx, multi, oracle_mod):
+    """pairhmm_forward_file_image on several GPUs: ranges of whole batches, cut at header lines and verified to be
+    batch boundaries; results in file order, a truncated last batch reported like on one GPU."""
+    cap, n = multi
+    inp = agx.synth.pairhmm_batches(60 * n, 200, 5, seed=77, unrelated_frac=0.002)
+    assert inp.buf.size >= n * (8 << 20)
+    vals, batch_pairs, incomplete = cap.pairhmm_forward_file_image(inp.buf)
+    assert incomplete == 0 and batch_pairs.tolist() == [1000] * (60 * n)
+    flat = cap.pairhmm_forward_flat(inp.buf, inp.read_field_off, inp.read_len, inp.hap_off, inp.hap_len,
+                                    inp.batch_read_start, inp.batch_hap_start)
+    assert np.array_equal(vals, flat, equal_nan=True)
+    want = oracle_mod.pairhmm_flat(inp, limit=300)
+    fin = np.isfinite(want)
+    assert np.max(np.abs(vals[:300][fin] - want[fin]) / np.abs(want[fin])) <= 1e-5
+    # the file ends inside its last batch
+    lines = bytes(inp.buf).split(b"\n")[:-1]
+    cut = b"\n".join(lines[:-3]) + b"\n"
+    vals2, batch_pairs2, incomplete2 = cap.pairhmm_forward_file_image(cut)
+    assert incomplete2 == 2 and batch_pairs2.size == 60 * n - 1 and np.array_equal(vals2, vals[:vals2.size], equal_nan=True)
+
+
+def test_pairhmm_file_image_with_a_header_shaped_line_inside_a_batch_falls_back(agx, multi):
+    """A haplotype line that looks like a header near a cut point: the range check fails and the first GPU takes the
+    whole image (the reference reads that line as a haplotype)."""
+    cap, n = multi
+    inp = agx.synth.pairhmm_batches(60 * n, 200, 5, seed=78)
+    data = bytearray(bytes(inp.buf))
+    # overwrite the first haplotype line after the middle of the file with "12 34" padded by spaces... it must
+    # keep its length; a haplotype of digits and blanks is legal input for the reference (bytes are bytes)
+    mid = len(data) // 2
+    h = int(inp.hap_off[np.searchsorted(inp.hap_off, mid)])
+    L = int(inp.hap_len[np.searchsorted(inp.hap_off, mid)])
+    data[h:h + L] = b"7" * (L - 3) + b" 55"
+    one_gpu, bp1, inc1 = cap.pairhmm_forward_file_image(bytes(data))
+    cap.shutdown()
+    cap.init(1)
+    ref, bp0, inc0 = cap.pairhmm_forward_file_image(bytes(data))
+    cap.shutdown()
+    cap.init(0)
+    assert inc1 == inc0 == 0 and bp1.tolist() == bp0.tolist() and np.array_equal(one_gpu, ref, equal_nan=True)
+
+
+def test_sharded_device_entry_points(agx, multi):
+    """sw_score_shards_device / pairhmm_forward_shards_device: one device-resident shard per GPU in one call."""
+    import torch
+    cap, n = multi
+    sw = agx.synth.sw_uniform_pairs(20000, 150, seed=5)
+    want = cap.sw_score_flat(sw.buf, sw.off, sw.len)
+    shards, keep = [], []
+    for k in range(n):
+        p0, p1 = 20000 * k // n, 20000 * (k + 1) // n
+        b0, b1 = int(sw.off[2 * p0]), int(sw.off[2 * p1 - 1] + sw.len[2 * p1 - 1])
+        dev = torch.device("cuda", k)
+        t = [torch.from_numpy(x).to(dev) for x in (sw.buf[b0:b1], sw.off[2 * p0:2 * p1] - b0, sw.len[2 * p0:2 * p1])]
+        out = torch.zeros(p1 - p0, dtype=torch.int32, device=dev)
+        keep.append((t, out))
+        shards.append(cap.SwShard(k, t[0].data_ptr(), t[0].numel(), t[1].data_ptr(), t[2].data_ptr(), p1 - p0, out.data_ptr()))
+    cap.sw_score_shards_device(shards)
+    assert np.array_equal(np.concatenate([o.cpu().numpy() for _, o in keep]), want)
+    with pytest.raises(agx.capi.AgxError):
+        cap.sw_score_shards_device([shards[0], shards[0]])          # one shard per device
