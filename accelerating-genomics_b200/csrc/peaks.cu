@@ -734,6 +734,176 @@ template <int IOP> void run_issue_all(int sms, uint32_t *d_out, const char *name
     }
 }
 
+// ---- the R x K tile of the long-alignment kernel in isolation: one warp per SM sub-partition -------------
+// Same cell (dp4a substitution, lean chain), same loop-carried structure (the next step's first cells need this
+// step's last column through a shuffle).  ORDER picks how the source lists the cells of a step: 0 column by column
+// (rows inner), 1 row by row, 2 anti-diagonals, 3 the parallelogram (row i runs i columns behind and wraps into
+// the next step).  FLAGS add the per-step costs of the real kernel one at a time: 1 row tables from a shared-memory
+// ring, 2 requested one step ahead, 4 lane 0 takes its boundary from the ring (loads + selects), 8 lane 31 stages
+// its boundary in shared memory, 16 two running-max accumulators instead of one.
+template <int K, int R, int ORDER, int FLAGS>
+__global__ void __launch_bounds__(128) tile_kernel(uint32_t *out, int steps, int goe_, int ext_)
+{
+    __shared__ __align__(16) int32_t tab[4][64 * 8];
+    __shared__ __align__(16) int32_t rge[4][64 * 8];
+    __shared__ __align__(16) int2 stage[4][64 * 4];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    for (int i = lane; i < 64 * 8; i += 32) { tab[wib][i] = (int32_t)(0xfbfbfbfbu ^ (0x04u << (8 * ((i * 7 + lane) & 3)))); rge[wib][i] = goe_; }
+    __syncwarp();
+    const int32_t goe = goe_, ext = ext_;
+    int32_t Gp[K], F[K], acol[(K + 3) / 4];
+#pragma unroll
+    for (int j = 0; j < K; ++j) { Gp[j] = goe; F[j] = goe; }
+#pragma unroll
+    for (int q = 0; q < (K + 3) / 4; ++q) acol[q] = 0x3210 + lane + q;
+    int32_t g_out[R], e_out[R], e[R], gleft[R], gdiag[R], tlo[R], thi[R];
+    uint32_t sc4[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) { g_out[i] = goe; e_out[i] = goe; e[i] = goe; gleft[i] = goe; gdiag[i] = goe; tlo[i] = thi[i] = (int32_t)0xfbfbfbfb; sc4[i] = 0; }
+    int32_t best[2] = {goe, goe}, gprev = goe, gcarry = goe;
+    auto cell = [&](int i, int j) {
+        if ((j & 3) == 0) sc4[i] = __byte_perm((uint32_t)tlo[i], (uint32_t)thi[i], (uint32_t)acol[j >> 2]);
+        const int32_t d = __dp4a((int32_t)sc4[i], (int32_t)(1u << (8 * (j & 3))), gdiag[i]);
+        const int32_t f = __viaddmax_s32(F[j], ext, Gp[j]);
+        e[i] = __viaddmax_s32(e[i], ext, gleft[i]);
+        int32_t gn = __vimax3_s32_relu(e[i], f, d);
+        asm volatile("mad.lo.s32 %0, %1, %2, %3;" : "=r"(gn) : "r"(gn), "r"(ext_ * ext_), "r"(goe));
+        gdiag[i] = Gp[j]; Gp[j] = gn; F[j] = f; gleft[i] = gn;
+        if ((FLAGS & 16) && (i & 1)) best[1] = max(best[1], gn); else best[0] = max(best[0], gn);
+    };
+    auto load_tab = [&](int s, int32_t (&lo)[R], int32_t (&hi)[R]) {
+        if constexpr (FLAGS & 1) {
+            const int sl = (R * (s - lane)) & (64 * R - 1);
+#pragma unroll
+            for (int i = 0; i < R; ++i) { lo[i] = tab[wib][sl + i]; hi[i] = tab[wib][(sl + i + 256) & 511]; }
+        } else {
+#pragma unroll
+            for (int i = 0; i < R; ++i) { lo[i] = (int32_t)0xfbfbfbfb ^ (s & 4); hi[i] = (int32_t)0xfbfbfbfb; }
+        }
+    };
+    int32_t nlo[R], nhi[R];
+    load_tab(0, nlo, nhi);
+#pragma unroll 1
+    for (int s = 0; s < steps; ++s) {
+        int32_t plo[R], phi[R];
+        if constexpr (FLAGS & 2) load_tab(s + 1, plo, phi); else load_tab(s, nlo, nhi);
+        int32_t bg[R], be[R];
+        if constexpr (FLAGS & 4) {
+            const int sl0 = (R * s) & (64 * R - 1);
+#pragma unroll
+            for (int i = 0; i < R; ++i) { bg[i] = rge[wib][sl0 + i]; be[i] = rge[wib][(sl0 + i + 256) & 511]; }
+        } else {
+#pragma unroll
+            for (int i = 0; i < R; ++i) { bg[i] = goe; be[i] = goe; }
+        }
+        if constexpr (ORDER != 3) {
+            int32_t g_in[R];
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                g_in[i] = __shfl_up_sync(0xffffffffu, g_out[i], 1);
+                e[i] = __shfl_up_sync(0xffffffffu, e_out[i], 1);
+                if (lane == 0) { g_in[i] = bg[i]; e[i] = be[i]; }
+                gdiag[i] = i == 0 ? gprev : g_in[i - 1];
+                gleft[i] = g_in[i];
+                tlo[i] = nlo[i]; thi[i] = nhi[i];
+            }
+            gprev = g_in[R - 1];
+            if constexpr (ORDER == 0) {
+#pragma unroll
+                for (int j = 0; j < K; ++j)
+#pragma unroll
+                    for (int i = 0; i < R; ++i) cell(i, j);
+            } else if constexpr (ORDER == 1) {
+#pragma unroll
+                for (int i = 0; i < R; ++i)
+#pragma unroll
+                    for (int j = 0; j < K; ++j) cell(i, j);
+            } else {
+#pragma unroll
+                for (int dg = 0; dg < K + R - 1; ++dg)
+#pragma unroll
+                    for (int i = 0; i < R; ++i)
+                        if (dg - i >= 0 && dg - i < K) cell(i, dg - i);
+            }
+#pragma unroll
+            for (int i = 0; i < R; ++i) { g_out[i] = gleft[i]; e_out[i] = e[i]; }
+            if constexpr (FLAGS & 8) {
+                if (lane == 31) {
+#pragma unroll
+                    for (int i = 0; i < R; ++i) stage[wib][((s & 31) * R + i) & 255] = make_int2(g_out[i], e_out[i]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < K; ++c) {
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    const int j = (c >= i) ? c - i : K + c - i;
+                    if (j == 0) {
+                        const int32_t gin = (lane == 0) ? bg[i] : g_out[i];
+                        const int32_t ein = (lane == 0) ? be[i] : e_out[i];
+                        gdiag[i] = gcarry; gcarry = gin; gleft[i] = gin; e[i] = ein; tlo[i] = nlo[i]; thi[i] = nhi[i];
+                    }
+                    cell(i, j);
+                    if (j == K - 1) {
+                        g_out[i] = __shfl_up_sync(0xffffffffu, gleft[i], 1);
+                        e_out[i] = __shfl_up_sync(0xffffffffu, e[i], 1);
+                        if constexpr (FLAGS & 8) { if (lane == 31) stage[wib][((s & 31) * R + i) & 255] = make_int2(gleft[i], e[i]); }
+                    }
+                }
+            }
+        }
+        if constexpr (FLAGS & 2) {
+#pragma unroll
+            for (int i = 0; i < R; ++i) { nlo[i] = plo[i]; nhi[i] = phi[i]; }
+        }
+    }
+    uint32_t acc = (uint32_t)(best[0] ^ best[1]);
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc ^= (uint32_t)(Gp[j] + F[j]);
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc + stage[wib][lane].x;
+}
+template <int K, int R, int ORDER, int FLAGS> void run_tile(int sms, uint32_t *d_out)
+{
+    const int steps = 20000;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    tile_kernel<K, R, ORDER, FLAGS><<<sms, 128>>>(d_out, steps, -4, -1);
+    CK(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(e0));
+        tile_kernel<K, R, ORDER, FLAGS><<<sms, 128>>>(d_out, steps, -4, -1);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    const double clk = best * 1e-3 * 1.965e9 / steps;
+    printf("{\"tile_test\": 1, \"K\": %d, \"R\": %d, \"order\": %d, \"flags\": %d, \"clk_per_step\": %.1f, \"clk_per_cell\": %.2f}\n", K, R,
+           ORDER, FLAGS, clk, clk / (K * R));
+    fflush(stdout);
+}
+template <int K, int R, int ORDER> void run_tile_flags(int sms, uint32_t *d_out)
+{
+    run_tile<K, R, ORDER, 0>(sms, d_out);
+    run_tile<K, R, ORDER, 16>(sms, d_out);
+    run_tile<K, R, ORDER, 1>(sms, d_out);
+    run_tile<K, R, ORDER, 3>(sms, d_out);
+    run_tile<K, R, ORDER, 5>(sms, d_out);
+    run_tile<K, R, ORDER, 13>(sms, d_out);
+    run_tile<K, R, ORDER, 15>(sms, d_out);
+    run_tile<K, R, ORDER, 31>(sms, d_out);
+}
+template <int K, int R> void run_tile_orders(int sms, uint32_t *d_out)
+{
+    run_tile_flags<K, R, 0>(sms, d_out);
+    run_tile_flags<K, R, 1>(sms, d_out);
+    if constexpr (R <= K) run_tile_flags<K, R, 3>(sms, d_out);
+}
+
 template <int OP> void run_all(int sms, uint32_t *d_out, long long *d_cyc, int bps)
 {
     if constexpr (OP < OP_COUNT) {
@@ -760,6 +930,11 @@ int main(int argc, char **argv)
     nv.open(dev);
     nv.start();
     struct Fin { Nvml &n; ~Fin() { n.finish(); } } fin{nv};
+    if (argc > 2 && !strcmp(argv[2], "tile")) {
+        run_tile_orders<7, 2>(sms, d_out);
+        run_tile_orders<7, 4>(sms, d_out);
+        return 0;
+    }
     if (argc > 2 && !strcmp(argv[2], "issue")) {
         run_issue_all<IS_VIADDMNMX>(sms, d_out, "VIADDMNMX.S32 (3 registers)", 1);
         run_issue_all<IS_VIMNMX3>(sms, d_out, "VIMNMX3.S32.RELU + IADD (3 registers)", 2);

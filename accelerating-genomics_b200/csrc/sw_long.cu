@@ -293,7 +293,9 @@ sw_longr_kernel(LongArgs g)
     const int32_t lb = g.lb;
     const int n_stripes = (g.la + W - 1) / W;
     const int B = g.bsteps;
-    int32_t bestg = goe;
+    int32_t bestg[(R + 1) / 2];
+#pragma unroll
+    for (int i = 0; i < (R + 1) / 2; ++i) bestg[i] = goe;
     const int32_t one = g.one;
     const int32_t xb4 = (int32_t)((uint32_t)(uint8_t)(int8_t)(g.sc.mismatch - goe) * 0x01010101u);
     const int S = (lb + R - 1) / R + 31;               // lane 31 finishes the last row block at step (lb-1)/R + 31
@@ -385,19 +387,42 @@ sw_longr_kernel(LongArgs g)
 #pragma unroll
             for (int q = 0; q < R; ++q) {
                 const int idx = 32 * q + lane;
+                nx[q] = fresh;
                 if (idx < B * R) nt[q] = g.rowtab[base + B * R + idx];       // rowtab is padded past the last block
             }
             const int send = min(B, S - s0);
-#pragma unroll(R == 1 ? 2 : 1)
-            for (int u = 0; u < send; ++u) {
-                const int s = s0 + u;
-                const int sl = (R * (s - lane)) & (RROWS - 1);
-                const int sl0 = (R * s) & (RROWS - 1);
-                int32_t tlo[R], thi[R], g_in[R], e[R], bg[R], be[R];
+            const int half = send >> 1;
+            // row tables / lane-0 boundary of this block's first step; later steps get theirs one step ahead (a lone
+            // warp has nothing else to cover the shared-memory latency with)
+            int32_t tlo[R], thi[R], bg[R], be[R];
+            {
+                const int sl = (R * (s0 - lane)) & (RROWS - 1), sl0 = (R * s0) & (RROWS - 1);
                 lds_vec<R>(&r_lo[wib][sl], tlo);
                 lds_vec<R>(&r_hi[wib][sl], thi);
-                lds_vec<R>(&r_g[wib][sl0], bg);            // same address in every lane: a broadcast
+                lds_vec<R>(&r_g[wib][sl0], bg);
                 lds_vec<R>(&r_e[wib][sl0], be);
+            }
+#pragma unroll 1
+            for (int u = 0; u < send; ++u) {
+                const int s = s0 + u;
+                if (u == half && !left_edge) {
+                    // boundary entries of the next block: requested half a block early, so that their way through L2
+                    // (or NVLink) is covered by the remaining steps; the poll at the top repeats what was not there yet
+#pragma unroll
+                    for (int q = 0; q < R; ++q) {
+                        const int r = base + B * R + 32 * q + lane;
+                        if (32 * q + lane < B * R && r < lb) nx[q] = ld_entry(g.bnd + r, in_remote);
+                    }
+                }
+                int32_t plo[R], phi[R], pg[R], pe[R];             // the next step's (dropped at the end of a block)
+                {
+                    const int sl = (R * (s + 1 - lane)) & (RROWS - 1), sl0 = (R * (s + 1)) & (RROWS - 1);
+                    lds_vec<R>(&r_lo[wib][sl], plo);
+                    lds_vec<R>(&r_hi[wib][sl], phi);
+                    lds_vec<R>(&r_g[wib][sl0], pg);
+                    lds_vec<R>(&r_e[wib][sl0], pe);
+                }
+                int32_t g_in[R], e[R];
 #pragma unroll
                 for (int i = 0; i < R; ++i) {
                     g_in[i] = __shfl_up_sync(0xffffffffu, g_out[i], 1);
@@ -441,9 +466,10 @@ sw_longr_kernel(LongArgs g)
                         gdiag[i] = up;
                         up = gnew;
                         gleft[i] = gnew;
-                        if constexpr (R % 2 == 0) { if (i & 1) bestg = __vimax3_s32(bestg, gleft[i - 1], gnew); }
-                        else if (R == 1) { if (j & 1) bestg = __vimax3_s32(bestg, Gp[j - 1], gnew); else if (j == K - 1) bestg = max(bestg, gnew); }
-                        else bestg = max(bestg, gnew);
+                        // running maximum: one accumulator per pair of rows (independent chains)
+                        if constexpr (R == 1) { if (j & 1) bestg[0] = __vimax3_s32(bestg[0], Gp[j - 1], gnew); else if (j == K - 1) bestg[0] = max(bestg[0], gnew); }
+                        else if (i & 1) bestg[i >> 1] = __vimax3_s32(bestg[i >> 1], gleft[i - 1], gnew);
+                        else if (i == R - 1) bestg[i >> 1] = max(bestg[i >> 1], gnew);
                     }
                     Gp[j] = up; F[j] = f;
                 }
@@ -454,13 +480,8 @@ sw_longr_kernel(LongArgs g)
 #pragma unroll
                     for (int i = 0; i < R; ++i) stage[wib][u * R + i] = make_int2(g_out[i], e_out[i]);
                 }
-            }
-            // boundary entries of the next block (first attempt; the poll at the top repeats what is missing)
 #pragma unroll
-            for (int q = 0; q < R; ++q) {
-                const int r = base + B * R + 32 * q + lane;
-                nx[q] = fresh;
-                if (!left_edge && 32 * q + lane < B * R && r < lb) nx[q] = ld_entry(g.bnd + r, in_remote);
+                for (int i = 0; i < R; ++i) { tlo[i] = plo[i]; thi[i] = phi[i]; bg[i] = pg[i]; be[i] = pe[i]; }
             }
             // hand on the rows lane 31 finished in this block: rows R(s0-31) .. R(s0-31) + R*send - 1
             if (out_bnd != nullptr) {
@@ -479,9 +500,12 @@ sw_longr_kernel(LongArgs g)
         }
         __syncwarp();
     }
+    int32_t best_all = bestg[0];
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) bestg = max(bestg, __shfl_xor_sync(0xffffffffu, bestg, m));
-    const int32_t best = bestg - goe;
+    for (int i = 1; i < (R + 1) / 2; ++i) best_all = max(best_all, bestg[i]);
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) best_all = max(best_all, __shfl_xor_sync(0xffffffffu, best_all, m));
+    const int32_t best = best_all - goe;
     if (lane == 0 && best > 0) atomicMax(g.best, best);
 }
 
@@ -618,6 +642,16 @@ sw_longp_kernel(LongArgs g)
             }
             const int send = min(B, S - s0);
             const int half = send >> 1;
+            // row tables / lane-0 boundary of the first iteration of this block; later ones are requested one
+            // iteration ahead (a lone warp cannot hide the shared-memory latency otherwise)
+            int32_t nlo[R], nhi[R], bg[R], be[R];
+            {
+                const int sl = R * ((s0 - lane) & 63), sl0 = R * (s0 & 63);
+                lds_vec<R>(&r_lo[wib][sl], nlo);
+                lds_vec<R>(&r_hi[wib][sl], nhi);
+                lds_vec<R>(&r_g[wib][sl0], bg);
+                lds_vec<R>(&r_e[wib][sl0], be);
+            }
 #pragma unroll 1
             for (int u = 0; u < send; ++u) {
                 const int s = s0 + u;
@@ -630,16 +664,23 @@ sw_longp_kernel(LongArgs g)
                         if (32 * q + lane < B * R && r < lb) nx[q] = ld_entry(g.bnd + r, in_remote);
                     }
                 }
-                const int sl = R * ((s - lane) & 63);
-                const int sl0 = R * (s & 63);
-                int32_t nlo[R], nhi[R], bg[R], be[R];
-                lds_vec<R>(&r_lo[wib][sl], nlo);
-                lds_vec<R>(&r_hi[wib][sl], nhi);
-                lds_vec<R>(&r_g[wib][sl0], bg);
-                lds_vec<R>(&r_e[wib][sl0], be);
-                const int srow = R * (s - 31);                           // lane 31: first row of its current block
+                // next iteration's tables (for lane 0 the last iteration of a block reads rows that are not in
+                // the ring yet: those values are dropped, the block start above reads them again)
+                int32_t plo[R], phi[R], pg[R], pe[R];
+                {
+                    const int sl = R * ((s + 1 - lane) & 63), sl0 = R * ((s + 1) & 63);
+                    lds_vec<R>(&r_lo[wib][sl], plo);
+                    lds_vec<R>(&r_hi[wib][sl], phi);
+                    lds_vec<R>(&r_g[wib][sl0], pg);
+                    lds_vec<R>(&r_e[wib][sl0], pe);
+                }
+                // lane 31 stages finished rows: row i of its current block (s - 31) or, wrapped, of the one before
+                int2 *stage_cur = &stage[wib][R * ((s - 31) & 63)], *stage_prev = &stage[wib][R * ((s - 32) & 63)];
 #pragma unroll
                 for (int c = 0; c < K; ++c) {
+                    // the R cells of this time slot, one per row, all independent: written stage by stage so that
+                    // the instruction stream interleaves them
+                    int32_t d[R], f[R], gnew[R];
 #pragma unroll
                     for (int i = 0; i < R; ++i) {
                         const int j = (c >= i) ? c - i : K + c - i;
@@ -654,34 +695,47 @@ sw_longp_kernel(LongArgs g)
                             tlo[i] = nlo[i];
                             thi[i] = nhi[i];
                         }
-                        int32_t d;
                         if constexpr (DP4A) {
                             if ((j & 3) == 0) sc4[i] = __byte_perm((uint32_t)tlo[i], (uint32_t)thi[i], (uint32_t)acol[j >> 2]);
-                            d = __dp4a((int32_t)sc4[i], (int32_t)(1u << (8 * (j & 3))), gdiag[i]);
-                        } else {
-                            d = add_fma(gdiag[i], prmt_s((uint32_t)tlo[i], (uint32_t)thi[i], (uint32_t)acol[j]), one);
                         }
-                        const int32_t f = __viaddmax_s32(F[j], ext, Gp[j]);          // F[row][j]
-                        e[i] = __viaddmax_s32(e[i], ext, gleft[i]);                  // E[row][j]
-                        const int32_t gnew = add_fma(__vimax3_s32_relu(e[i], f, d), goe, one);
+                    }
+#pragma unroll
+                    for (int i = 0; i < R; ++i) {
+                        const int j = (c >= i) ? c - i : K + c - i;
+                        if constexpr (DP4A) d[i] = __dp4a((int32_t)sc4[i], (int32_t)(1u << (8 * (j & 3))), gdiag[i]);
+                        else d[i] = add_fma(gdiag[i], prmt_s((uint32_t)tlo[i], (uint32_t)thi[i], (uint32_t)acol[j]), one);
+                    }
+#pragma unroll
+                    for (int i = 0; i < R; ++i) {
+                        const int j = (c >= i) ? c - i : K + c - i;
+                        f[i] = __viaddmax_s32(F[j], ext, Gp[j]);                     // F[row][j]
+                    }
+#pragma unroll
+                    for (int i = 0; i < R; ++i) e[i] = __viaddmax_s32(e[i], ext, gleft[i]);     // E[row][j]
+#pragma unroll
+                    for (int i = 0; i < R; ++i) gnew[i] = __vimax3_s32_relu(e[i], f[i], d[i]);
+#pragma unroll
+                    for (int i = 0; i < R; ++i) gnew[i] = add_fma(gnew[i], goe, one);           // H[row][j] + goe
+#pragma unroll
+                    for (int i = 0; i < R; ++i) {
+                        const int j = (c >= i) ? c - i : K + c - i;
                         gdiag[i] = Gp[j];
-                        Gp[j] = gnew;
-                        F[j] = f;
-                        gleft[i] = gnew;
-                        if constexpr (R == 1) bestg[0] = max(bestg[0], gnew);
-                        else if (i & 1) bestg[i >> 1] = __vimax3_s32(bestg[i >> 1], gleft[i - 1], gnew);
-                        else if (i == R - 1) bestg[i >> 1] = max(bestg[i >> 1], gnew);
+                        Gp[j] = gnew[i];
+                        F[j] = f[i];
+                        gleft[i] = gnew[i];
+                        if constexpr (R == 1) bestg[0] = max(bestg[0], gnew[i]);
+                        else if (i & 1) bestg[i >> 1] = __vimax3_s32(bestg[i >> 1], gnew[i - 1], gnew[i]);
+                        else if (i == R - 1) bestg[i >> 1] = max(bestg[i >> 1], gnew[i]);
                         if (j == K - 1) {
                             // the row leaves this lane: hand its boundary to the next lane (lane 31: stage it)
-                            gs[i] = __shfl_up_sync(0xffffffffu, gnew, 1);
+                            gs[i] = __shfl_up_sync(0xffffffffu, gnew[i], 1);
                             es[i] = __shfl_up_sync(0xffffffffu, e[i], 1);
-                            if (lane == 31) {
-                                const int row = (c >= i ? srow : srow - R) + i;
-                                stage[wib][slot_of(row)] = make_int2(gnew, e[i]);
-                            }
+                            if (lane == 31) (c >= i ? stage_cur : stage_prev)[i] = make_int2(gnew[i], e[i]);
                         }
                     }
                 }
+#pragma unroll
+                for (int i = 0; i < R; ++i) { nlo[i] = plo[i]; nhi[i] = phi[i]; bg[i] = pg[i]; be[i] = pe[i]; }
             }
             // hand on the row blocks lane 31 completed by now: blocks s0 - 32 .. s0 + send - 33
             if (out_bnd != nullptr) {
@@ -691,7 +745,7 @@ sw_longp_kernel(LongArgs g)
                     const int idx = 32 * q + lane;
                     const int r = R * (s0 - 32) + idx;
                     if (idx < R * send && r >= 0 && r < lb) {
-                        const int2 ge = stage[wib][slot_of(r)];
+                        const int2 ge = stage[wib][R * ((r / R) & 63) + r % R];
                         st_entry(out_bnd + r, make_int4(ge.x, gst, ge.y, gst), out_remote);
                     }
                 }

@@ -64,7 +64,17 @@ def sweep(cols, rows, ks, rs, bs, dp=(0, 1), chains=(0, 1)):
         print(json.dumps({"cols": cols, "rows": rows, "K": k, "R": r, "short": ch, "dp4a": d, "B": bb, "ms": round(ms, 2),
                           "gcups": round(cols * rows / ms / 1e6), "ok": sc == ref_score}), flush=True)
 
-if mode == "pipe_share":
+if mode == "tune":
+    # 125 kbp x 125 kbp on one GPU has the stripe-fill : row ratio of 1 Mbp x 1 Mbp on eight (x 8 = the 8-GPU time)
+    sweep(125_000, 125_000, [7], [2, 4], [2, 4, 8, 16, 32], dp=(1,), chains=(0, 1))
+    sweep(125_000, 1_000_000, [7], [2, 4], [4, 8, 32], dp=(1,), chains=(0,))
+    sweep(1_000_000, 1_000_000, [27], [2, 4], [8, 32], dp=(1,), chains=(0,))
+    sweep_pipe(125_000, 125_000, [7], [2, 4], [4, 8, 16], dp=(1,))
+elif mode == "pipe2":
+    sweep_pipe(125_000, 1_000_000, [7, 8], [2, 3, 4, 6], [4, 8, 16, 32], dp=(1,))
+    sweep_pipe(125_000, 500_000, [7], [2, 3, 4, 6], [8], dp=(1,))
+    sweep_pipe(1_000_000, 1_000_000, [27], [2, 4], [8, 32], dp=(1,))
+elif mode == "pipe_share":
     sweep_pipe(125_000, 1_000_000, [6, 7, 8], [1, 2, 3, 4, 6], [4, 8, 16, 32])
     sweep_pipe(125_000, 500_000, [7], [1, 2, 3, 4, 6], [8])
 elif mode == "pipe_full":
