@@ -26,7 +26,7 @@ _lib = None
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        srcs = [HERE / "oracle.c", HERE / "sw_blocked.c", HERE / "oracle.h"]
+        srcs = [HERE / "oracle.c", HERE / "sw_blocked.c", HERE / "sw_align.c", HERE / "oracle.h"]
         if not LIB.exists() or any(p.exists() and p.stat().st_mtime > LIB.stat().st_mtime for p in srcs):
             subprocess.run(["make", "-C", str(HERE), "liboracle.so"], check=True, capture_output=True)
         l = C.CDLL(str(LIB))
@@ -35,6 +35,12 @@ def lib() -> C.CDLL:
             [C.POINTER(C.c_int32)]
         l.oracle_sw_score_blocked.restype = C.c_int32
         l.oracle_sw_score_blocked.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64] + [C.c_int32] * 6
+        l.oracle_sw_align.restype = C.c_int32
+        l.oracle_sw_align.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32] + [C.c_int32] * 4 + \
+            [C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.c_int32, C.POINTER(C.c_int32)]
+        l.oracle_sw_cigar_score.restype = C.c_int32
+        l.oracle_sw_cigar_score.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32] + [C.c_int32] * 4 + \
+            [C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.c_int32]
         l.oracle_sw_file.restype = C.c_int64
         l.oracle_sw_file.argtypes = [C.c_char_p, C.c_int32, C.c_void_p, C.c_int64, C.POINTER(C.c_int32)]
         l.oracle_pairhmm_prob.restype = C.c_double
@@ -67,6 +73,46 @@ def sw_scores_flat(buf: np.ndarray, off: np.ndarray, ln: np.ndarray, scoring=(1,
         b = data[off[2 * p + 1]:off[2 * p + 1] + ln[2 * p + 1]]
         out[p] = sw_score(a, b, scoring)
     return out
+
+
+def sw_align(a: bytes, b: bytes, scoring=(1, -1, -3, -1)):
+    """oracle_sw_align: (score, (a_start, a_end, b_start, b_end), [cigar words]); coordinates -1 when score == 0"""
+    cap = len(a) + len(b) + 2
+    coords = (C.c_int32 * 4)()
+    cig = (C.c_uint32 * cap)()
+    n = C.c_int32(0)
+    s = lib().oracle_sw_align(a, len(a), b, len(b), *scoring, coords, cig, cap, C.byref(n))
+    assert s != -(1 << 31)
+    return int(s), tuple(int(x) for x in coords), [int(cig[k]) for k in range(n.value)]
+
+
+def sw_cigar_score(a: bytes, b: bytes, coords, cigar, scoring=(1, -1, -3, -1)) -> int:
+    """score spelled by a CIGAR between the given coordinates (None when the path does not fit them)"""
+    c = (C.c_int32 * 4)(*coords)
+    g = (C.c_uint32 * max(1, len(cigar)))(*cigar)
+    s = int(lib().oracle_sw_cigar_score(a, len(a), b, len(b), *scoring, c, g, len(cigar)))
+    return None if s == -(1 << 31) else s
+
+
+def sw_align_flat(buf: np.ndarray, off: np.ndarray, ln: np.ndarray, scoring=(1, -1, -3, -1)):
+    """(scores[n], coords[n, 4], list of cigar lists) over a flat batch"""
+    data = np.ascontiguousarray(buf, dtype=np.uint8).tobytes()
+    n = off.size // 2
+    scores = np.empty(n, dtype=np.int32)
+    coords = np.empty((n, 4), dtype=np.int32)
+    cigars = []
+    for p in range(n):
+        a = data[off[2 * p]:off[2 * p] + ln[2 * p]]
+        b = data[off[2 * p + 1]:off[2 * p + 1] + ln[2 * p + 1]]
+        s, c, g = sw_align(a, b, scoring)
+        scores[p] = s
+        coords[p] = c
+        cigars.append(g)
+    return scores, coords, cigars
+
+
+def cigar_string(cigar) -> str:
+    return "".join(f"{w >> 4}{'MID'[w & 15]}" for w in cigar)
 
 
 def sw_file(path: str, line_buf: int = 1000, cap: int = 1 << 22):
@@ -128,6 +174,30 @@ def run_ref_sw(path: str, long_lines: bool = False, timeout: float = 600.0):
         if l.startswith("line_num:"):
             header = int(l.split()[1])
     return np.asarray(scores, dtype=np.int32), header, text
+
+
+def run_ref_sw_ends(path: str, timeout: float = 600.0):
+    """oracle/_ref/sw_antidiag_ends (the reference + position bookkeeping beside its running maximum, see
+    oracle/Makefile): rows of (score, end_iy, end_ix, sx_line) -- 1-based DP indices, sx_line 1 or 2."""
+    r = subprocess.run([str(REF / "sw_antidiag_ends"), str(path)], capture_output=True, timeout=timeout)
+    return parse_ref_sw_ends(r.stdout.decode(errors="replace"))
+
+
+def parse_ref_sw_ends(text: str):
+    rows = []
+    for l in text.splitlines():
+        if l.startswith("Score:"):
+            t = l.split()
+            rows.append((int(t[1]), int(t[3]), int(t[4]), int(t[6])))
+    return rows
+
+
+def ref_ends_to_coords(row):
+    """(score, iy, ix, sx_line) of the instrumented reference -> (a_end, b_end), 0-based, -1 when score == 0"""
+    s, iy, ix, sx = row
+    if s == 0:
+        return (-1, -1)
+    return (ix - 1, iy - 1) if sx == 1 else (iy - 1, ix - 1)
 
 
 def run_ref_pairhmm(path: str, which: str = "pairhmm_matrix", timeout: float = 600.0):

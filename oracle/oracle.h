@@ -37,6 +37,25 @@ int32_t oracle_sw_score_blocked(const uint8_t *a, int64_t la, const uint8_t *b, 
                                 int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend,
                                 int32_t tile, int32_t threads);
 
+/* Alignment END CELL, START CELL and CIGAR of one pair (sw_align.c; a = line 1, b = line 2, RAW BYTES).
+ * Returns the score (== oracle_sw_score).  coords = {a_start, a_end, b_start, b_end}: 0-based indices of the first
+ * and last aligned symbol of each sequence, all -1 when the score is 0.  The END is the cell the reference's
+ * running maximum comes from (antidiagonalSmithWaterman.c:335, strict `>`, cells visited by anti-diagonals
+ * :270-347 with ix -- the shorter line, line 1 on ties, :229-244 -- ascending); pinned to the reference's own scan
+ * by oracle/_ref/sw_antidiag_ends.  START and CIGAR follow the traceback rule stated in sw_align.c (this
+ * repository's definition; the reference has none).  cigar[k] = length << 4 | op with op 0 = M (one symbol of
+ * each), 1 = I (symbols of a only), 2 = D (symbols of b only), start -> end; *n_ops_out = number of runs (may exceed
+ * cigar_cap, then only cigar_cap are written). */
+int32_t oracle_sw_align(const uint8_t *a, int32_t la, const uint8_t *b, int32_t lb, int32_t match,
+                        int32_t mismatch, int32_t gap_open, int32_t gap_extend, int32_t coords[4],
+                        uint32_t *cigar, int32_t cigar_cap, int32_t *n_ops_out);
+
+/* Independent re-scoring of a CIGAR (walks the path, adds up substitutions and gaps): INT32_MIN when the path
+ * does not run exactly from the start to the end coordinates. */
+int32_t oracle_sw_cigar_score(const uint8_t *a, int32_t la, const uint8_t *b, int32_t lb, int32_t match,
+                              int32_t mismatch, int32_t gap_open, int32_t gap_extend, const int32_t coords[4],
+                              const uint32_t *cigar, int32_t n_ops);
+
 /* File-level restatement of antidiagonalSmithWaterman.c:205-227, 348 (header = number of LINES to
  * consume, fgets into a `line_buf`-byte buffer so longer lines split, trailing '\n' kept as a
  * symbol, EOF mid-pair stops).  line_buf = 1000 reproduces the unmodified program.

@@ -35,8 +35,49 @@ def ref_sw(path: Path, long_lines=False) -> str:
     return "".join(l + "\n" for l in text.splitlines() if not l.startswith("elapsed"))
 
 
+def make_ends() -> None:
+    """END CELLS of the reference's own scan: oracle/_ref/sw_antidiag_ends is the reference source with position
+    bookkeeping added beside its running maximum (oracle/Makefile); its "Score: s End: iy ix Sx: line" lines are
+    recorded for tie-rich inputs (two-letter alphabets, tandem repeats, equal and unequal lengths, a last line
+    without newline)."""
+    rng = np.random.default_rng(20261019)
+    S = agx.synth
+
+    def repeats(n_pairs):
+        out = [str(2 * n_pairs).encode()]
+        for _ in range(n_pairs):
+            unit = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, size=int(rng.integers(1, 5)))].tobytes()
+            a = unit * int(rng.integers(3, 30))
+            b = unit * int(rng.integers(3, 30))
+            if rng.random() < 0.5:
+                a = a[int(rng.integers(0, 3)):] + np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, size=5)].tobytes()
+            out += [a, b]
+        return b"\n".join(out) + b"\n"
+
+    files = {
+        "sw_ends_two_letter.in": S.sw_random_file(rng, 120, 1, 90, alphabet=b"AC"),
+        "sw_ends_repeats.in": repeats(120),
+        "sw_ends_ragged.in": S.sw_random_file(rng, 120, 1, 150, related_frac=0.5),
+        "sw_ends_150.in": bytes(S.sw_uniform_pairs(96, 150, seed=11).buf),
+        "sw_ends_no_trailing_nl.in": S.sw_random_file(rng, 7, 20, 60, alphabet=b"AC", trailing_newline=False),
+        "sw_ends_mid.in": S.sw_random_file(rng, 16, 300, 900, related_frac=0.5),
+        "sw_ends_alphabet.in": S.sw_random_file(rng, 60, 5, 120, alphabet=b"ACGTNacgt"),
+    }
+    for name, data in files.items():
+        p = HERE / name
+        p.write_bytes(data)
+        r = subprocess.run([str(ROOT / "oracle" / "_ref" / "sw_antidiag_ends"), str(p)], capture_output=True, check=True)
+        text = "".join(l + "\n" for l in r.stdout.decode().splitlines() if not l.startswith("elapsed"))
+        (HERE / (name[:-3] + ".ref_ends.out")).write_text(text)
+    print("end-cell golden files written")
+
+
 def main() -> None:
     subprocess.run(["make", "-C", str(ROOT / "oracle"), "ref", "liboracle.so"], check=True)
+    if "--ends-only" in sys.argv:
+        make_ends()
+        return
+    make_ends()
     rng = np.random.default_rng(20261018)
     S = agx.synth
 
