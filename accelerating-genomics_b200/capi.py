@@ -28,6 +28,7 @@ SYMBOLS = [
     "pairhmm_forward_file_image",
     "agx_pairhmm_set_gatk_mode", "agx_pairhmm_set_force_fp64", "agx_pairhmm_rescue_count",
     "sw_score_shards_device", "pairhmm_forward_shards_device",
+    "sw_ends_batch_flat", "sw_align_batch_flat",
 ]
 
 # the reference's scoring constants, antidiagonalSmithWaterman.c:40-43
@@ -94,6 +95,12 @@ def load_library() -> C.CDLL:
     lib.agx_pairhmm_rescue_count.argtypes = [C.c_int32]
     lib.agx_pairhmm_rescue_count.restype = C.c_int64
     lib.sw_score_shards_device.argtypes = [C.c_void_p, C.c_int32] + [C.c_int32] * 4
+    lib.sw_ends_batch_flat.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_int32] * 4 + \
+        [C.c_void_p, C.c_void_p]
+    lib.sw_ends_batch_flat.restype = C.c_int
+    lib.sw_align_batch_flat.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_int32] * 4 + \
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    lib.sw_align_batch_flat.restype = C.c_int
     lib.sw_score_shards_device.restype = C.c_int
     lib.pairhmm_forward_shards_device.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
     lib.pairhmm_forward_shards_device.restype = C.c_int
@@ -223,6 +230,43 @@ def sw_score_flat(seqs: np.ndarray, off: np.ndarray, length: np.ndarray,
     _check(load_library().sw_score_batch_flat(_ptr(seqs), seqs.size, _ptr(off), _ptr(length), n,
                                               *[int(s) for s in scoring], _ptr(out)))
     return out
+
+
+def sw_ends_flat(seqs: np.ndarray, off: np.ndarray, length: np.ndarray, scoring=(SW_MATCH, SW_MISMATCH, SW_GAP_OPEN, SW_GAP_EXTEND)):
+    """sw_ends_batch_flat: (scores[n], ends[n, 2]) -- ends = index of the last aligned symbol in a and in b"""
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    length = np.ascontiguousarray(length, dtype=np.int32)
+    n = off.size // 2
+    scores = np.empty(n, dtype=np.int32)
+    ends = np.empty((n, 2), dtype=np.int32)
+    _check(load_library().sw_ends_batch_flat(_ptr(seqs), seqs.size, _ptr(off), _ptr(length), n,
+                                             *[int(s) for s in scoring], _ptr(scores), _ptr(ends)))
+    return scores, ends
+
+
+def sw_align_flat(seqs: np.ndarray, off: np.ndarray, length: np.ndarray, scoring=(SW_MATCH, SW_MISMATCH, SW_GAP_OPEN, SW_GAP_EXTEND),
+                  cigar_cap: Optional[int] = None):
+    """sw_align_batch_flat: (scores[n], coords[n, 4] = a_start a_end b_start b_end, cigar_off[n + 1], cigar runs)"""
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    length = np.ascontiguousarray(length, dtype=np.int32)
+    n = off.size // 2
+    scores = np.empty(n, dtype=np.int32)
+    coords = np.empty((n, 4), dtype=np.int32)
+    cig_off = np.empty(n + 1, dtype=np.int64)
+    cap = int(cigar_cap) if cigar_cap is not None else max(16, 8 * n)
+    lib = load_library()
+    while True:
+        cigar = np.empty(max(cap, 1), dtype=np.uint32)
+        total = C.c_int64(0)
+        rc = lib.sw_align_batch_flat(_ptr(seqs), seqs.size, _ptr(off), _ptr(length), n, *[int(s) for s in scoring],
+                                     _ptr(scores), _ptr(coords), _ptr(cig_off), _ptr(cigar), cap, C.byref(total))
+        if rc == -5 and cigar_cap is None and total.value > cap:      # AGX_ERANGE: the runs did not fit; ask again
+            cap = int(total.value)
+            continue
+        _check(rc)
+        return scores, coords, cig_off, cigar[:int(total.value)]
 
 
 def sw_score_batch(a: Sequence[bytes], b: Sequence[bytes],

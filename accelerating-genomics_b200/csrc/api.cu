@@ -127,6 +127,9 @@ struct DeviceCtx {
     HmmWorkspace hmm, hmm_b;                 // hmm_b / hmm_parse_b: second lane of pairhmm_forward_file_image
     HmmParseWorkspace hmm_parse, hmm_parse_b;
     DevBuf d_bytes, d_a, d_b, d_c, d_d, d_e, d_f, d_out;   // staging for the host entry points
+    SwAlignWorkspace align;                                 // sw_ends_* / sw_align_*
+    DevBuf al_bytes, al_off, al_len, al_scores, al_ends, al_coords, al_cigar;
+    PinBuf h_al_off, h_al_res;
     PinBuf h_a, h_b, h_out;
     std::string error;   // error raised on this device's worker thread
     std::string name;    // agx_device_name()
@@ -389,6 +392,161 @@ int sw_flat_impl(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *off, co
     });
 }
 
+// ---------------------------------------------------------------- SW alignment (end cell / start cell / CIGAR)
+// One shard = a contiguous range of pairs on one GPU, cut into chunks whose H-byte matrices fit the budget.
+// mode 1: scores + ends; mode 2: + coords and CIGAR runs (appended to `cigar`, run offsets relative to the shard).
+struct AlignOut {
+    int32_t *scores, *ends, *coords;
+    int64_t *cigar_off;               // [n + 1], mode 2
+    std::vector<uint32_t> *cigar;     // mode 2: runs of this shard (only filled while keep_cigar)
+    bool keep_cigar;
+};
+
+int sw_align_shard(DeviceCtx &c, const uint8_t *seqs, const int64_t *off, const int32_t *len, int64_t p0, int64_t p1,
+                   SwScoring sc, int mode, AlignOut out)
+{
+    cudaStream_t st = c.stream;
+    int64_t budget = (int64_t)8 << 30;
+    if (mode == 2) {
+        size_t fr = 0, tot = 0;
+        AGX_CUDA(cudaMemGetInfo(&fr, &tot));
+        // what is free now + what the scratch already holds, half of it, at most 32 GiB
+        const int64_t avail = (int64_t)fr + c.align.cap_tb + c.align.cap_tb_gen;
+        budget = std::min<int64_t>(avail / 2, (int64_t)32 << 30);
+        if (const char *e = getenv("AGX_ALIGN_TB_BYTES")) budget = std::max<long long>(atoll(e), 1 << 20);
+    }
+    int64_t cig_base = 0;
+    int64_t q0 = p0;
+    int shrink = 0;
+    while (q0 < p1) {
+        // chunk: at most 2^20 pairs and, in mode 2, matrices within the budget (the class layout rounds rows up to
+        // the longest of the class, so the per-pair bound is scaled by what the chunk's longest line adds)
+        int64_t q1 = q0, bytes = 0;
+        int32_t longest = 1;
+        while (q1 < p1 && q1 - q0 < ((int64_t)1 << 20) >> shrink) {
+            if (mode == 2) {
+                const int32_t la = len[2 * q1], lb = len[2 * q1 + 1];
+                const int32_t lg = std::max(la, lb);
+                const int64_t b = sw_align_tb_bound(la, lb);
+                const int32_t new_longest = std::max(longest, lg);
+                // bound of the chunk if this pair joins: every pair may be padded to the longest line seen
+                const double grown = ((double)bytes * new_longest / longest + (double)b * new_longest / std::max(lg, 1)) * 1.02;
+                if (q1 > q0 && grown > (double)(budget >> shrink)) break;
+                bytes = (int64_t)grown;
+                longest = new_longest;
+            }
+            ++q1;
+        }
+        const int64_t m = q1 - q0;
+        int64_t l = INT64_MAX, h = 0;
+        for (int64_t i = 2 * q0; i < 2 * q1; ++i) {
+            l = std::min(l, off[i]);
+            h = std::max(h, off[i] + len[i]);
+        }
+        if (h < l) { l = 0; h = 0; }
+        int rc;
+        if ((rc = c.al_bytes.reserve((size_t)(h - l) + 16)) != AGX_OK) return rc;
+        if ((rc = c.al_off.reserve((size_t)m * 2 * sizeof(int64_t))) != AGX_OK) return rc;
+        if ((rc = c.al_len.reserve((size_t)m * 2 * sizeof(int32_t))) != AGX_OK) return rc;
+        if ((rc = c.al_scores.reserve((size_t)m * sizeof(int32_t))) != AGX_OK) return rc;
+        if ((rc = c.al_ends.reserve((size_t)m * 2 * sizeof(int32_t))) != AGX_OK) return rc;
+        if (mode == 2 && (rc = c.al_coords.reserve((size_t)m * 4 * sizeof(int32_t))) != AGX_OK) return rc;
+        if ((rc = c.h_al_off.reserve((size_t)m * 2 * sizeof(int64_t))) != AGX_OK) return rc;
+        int64_t *roff = c.h_al_off.as<int64_t>();
+        for (int64_t i = 0; i < 2 * m; ++i) roff[i] = off[2 * q0 + i] - l;       // offsets relative to the uploaded range
+        AGX_CUDA(cudaMemcpyAsync(c.al_bytes.p, seqs + l, (size_t)(h - l), cudaMemcpyHostToDevice, st));
+        AGX_CUDA(cudaMemcpyAsync(c.al_off.p, roff, (size_t)m * 2 * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        AGX_CUDA(cudaMemcpyAsync(c.al_len.p, len + 2 * q0, (size_t)m * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        int64_t total = 0;
+        rc = sw_align_run_device(c.align, c.al_bytes.as<uint8_t>(), c.al_off.as<int64_t>(), c.al_len.as<int32_t>(), m, sc,
+                                 mode, budget, c.al_scores.as<int32_t>(), c.al_ends.as<int32_t>(),
+                                 c.al_coords.as<int32_t>(), &total, st);
+        if (rc == AGX_ENOMEM && mode == 2 && m > 1 && shrink < 24) { ++shrink; continue; }   // the bound was too optimistic
+        if (rc != AGX_OK) return rc;
+        AGX_CUDA(cudaMemcpyAsync(out.scores + q0, c.al_scores.p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (out.ends)
+            AGX_CUDA(cudaMemcpyAsync(out.ends + 2 * q0, c.al_ends.p, (size_t)m * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (mode == 2) {
+            AGX_CUDA(cudaMemcpyAsync(out.coords + 4 * q0, c.al_coords.p, (size_t)m * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            AGX_CUDA(cudaMemcpyAsync(out.cigar_off + (q0 - p0), c.align.cig_off, (size_t)(m + 1) * sizeof(int64_t),
+                                     cudaMemcpyDeviceToHost, st));
+            if (out.keep_cigar && total > 0) {
+                if ((rc = c.al_cigar.reserve((size_t)total * sizeof(uint32_t))) != AGX_OK) return rc;
+                if ((rc = sw_align_gather_device(c.align, m, c.al_cigar.as<uint32_t>(), st)) != AGX_OK) return rc;
+                const size_t at = out.cigar->size();
+                out.cigar->resize(at + (size_t)total);
+                AGX_CUDA(cudaMemcpyAsync(out.cigar->data() + at, c.al_cigar.p, (size_t)total * sizeof(uint32_t),
+                                         cudaMemcpyDeviceToHost, st));
+            }
+            AGX_CUDA(cudaStreamSynchronize(st));
+            for (int64_t i = 0; i <= m; ++i) out.cigar_off[(q0 - p0) + i] += cig_base;
+            cig_base += total;
+        }
+        AGX_CUDA(cudaStreamSynchronize(st));
+        q0 = q1;
+    }
+    return AGX_OK;
+}
+
+int sw_align_impl(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *off, const int32_t *len, int64_t n_pairs,
+                  SwScoring sc, int mode, int32_t *scores_out, int32_t *ends_out, int32_t *coords_out,
+                  int64_t *cigar_off_out, uint32_t *cigar_out, int64_t cigar_cap, int64_t *cigar_total_out)
+{
+    if (cigar_total_out) *cigar_total_out = 0;
+    if (n_pairs < 0) return fail(AGX_EINVAL, "sw align: n_pairs < 0");
+    if (n_pairs == 0) { if (mode == 2 && cigar_off_out) cigar_off_out[0] = 0; return AGX_OK; }
+    if (!seqs || !off || !len || !scores_out) return fail(AGX_EINVAL, "sw align: null argument");
+    if (mode == 1 && !ends_out) return fail(AGX_EINVAL, "sw ends: null argument");
+    if (mode == 2 && (!coords_out || !cigar_off_out || (!cigar_out && cigar_cap > 0) || cigar_cap < 0))
+        return fail(AGX_EINVAL, "sw align: null argument");
+    for (int64_t i = 0; i < 2 * n_pairs; ++i)
+        if (len[i] < 0 || off[i] < 0 || off[i] + len[i] > seqs_bytes)
+            return fail(AGX_EINVAL, "sw align: sequence " + std::to_string(i) + " lies outside the buffer");
+    int rc = require_init();
+    if (rc != AGX_OK) return rc;
+    const int n_dev = (int)std::min<int64_t>((int64_t)g_ctx.size(), n_pairs);
+    std::vector<int64_t> cuts{0, n_pairs};
+    if (n_dev > 1) {
+        std::vector<double> prefix(n_pairs + 1, 0.0);
+        for (int64_t p = 0; p < n_pairs; ++p)
+            prefix[p + 1] = prefix[p] + (double)(len[2 * p] + 1) * (double)(len[2 * p + 1] + 1);
+        cuts = balanced_cuts(prefix, n_dev);
+    }
+    std::vector<std::vector<uint32_t>> cig(n_dev);
+    std::vector<std::vector<int64_t>> coff(n_dev);
+    std::vector<int32_t> ends_tmp;
+    if (mode == 2) {
+        ends_tmp.resize((size_t)n_pairs * 2);
+        for (int k = 0; k < n_dev; ++k) coff[k].assign((size_t)(cuts[k + 1] - cuts[k] + 1), 0);
+    }
+    rc = for_each_device(n_dev, [&](DeviceCtx &c, int k) {
+        AlignOut o;
+        o.scores = scores_out;
+        o.ends = mode == 2 ? ends_tmp.data() : ends_out;
+        o.coords = coords_out;
+        o.cigar_off = mode == 2 ? coff[k].data() : nullptr;
+        o.cigar = &cig[k];
+        o.keep_cigar = true;
+        return sw_align_shard(c, seqs, off, len, cuts[k], cuts[k + 1], sc, mode, o);
+    });
+    if (rc != AGX_OK) return rc;
+    if (mode != 2) return AGX_OK;
+    int64_t base = 0;
+    for (int k = 0; k < n_dev; ++k) {
+        const int64_t m = cuts[k + 1] - cuts[k];
+        for (int64_t i = 0; i < m; ++i) cigar_off_out[cuts[k] + i] = coff[k][i] + base;
+        const int64_t tot = coff[k][m];
+        if (base + tot <= cigar_cap && tot > 0) memcpy(cigar_out + base, cig[k].data(), (size_t)tot * sizeof(uint32_t));
+        base += tot;
+    }
+    cigar_off_out[n_pairs] = base;
+    if (cigar_total_out) *cigar_total_out = base;
+    if (base > cigar_cap)
+        return fail(AGX_ERANGE, "sw align: " + std::to_string(base) + " CIGAR runs do not fit cigar_cap = " +
+                                    std::to_string(cigar_cap) + " (scores, coordinates and offsets are complete)");
+    return AGX_OK;
+}
+
 // ---------------------------------------------------------------- PairHMM on one shard
 struct HmmHost {
     const uint8_t *buf;
@@ -637,8 +795,10 @@ void agx_shutdown(void)
         hmm_workspace_free(c->hmm_b);
         hmm_parse_workspace_free(c->hmm_parse);
         hmm_parse_workspace_free(c->hmm_parse_b);
-        for (DevBuf *b : {&c->d_bytes, &c->d_a, &c->d_b, &c->d_c, &c->d_d, &c->d_e, &c->d_f, &c->d_out}) b->release();
-        for (PinBuf *b : {&c->h_a, &c->h_b, &c->h_out}) b->release();
+        for (DevBuf *b : {&c->d_bytes, &c->d_a, &c->d_b, &c->d_c, &c->d_d, &c->d_e, &c->d_f, &c->d_out, &c->al_bytes, &c->al_off,
+                          &c->al_len, &c->al_scores, &c->al_ends, &c->al_coords, &c->al_cigar}) b->release();
+        for (PinBuf *b : {&c->h_a, &c->h_b, &c->h_out, &c->h_al_off, &c->h_al_res}) b->release();
+        sw_align_workspace_free(c->align);
         if (c->stream) cudaStreamDestroy(c->stream);
     }
     g_ctx.clear();
@@ -663,6 +823,8 @@ double agx_profile_ms(int32_t device, int32_t which)
     case AGX_PROF_HMM_STREAM: return c->hmm.prof_stream.ms();
     case AGX_PROF_HMM_FP64: return c->hmm.prof_fp64.ms();
     case AGX_PROF_HMM_CLASSIFY: return c->hmm.prof_classify.ms();
+    case AGX_PROF_SW_ALIGN_DP: return c->align.prof_dp.ms();
+    case AGX_PROF_SW_ALIGN_WALK: return c->align.prof_walk.ms();
     case AGX_PROF_SW_LONG: { const double v = c->sw.lng.prof.ms(); return v >= 0 ? v : c->sw.prof_long.ms(); }
     default: return -1.0;
     }
@@ -677,6 +839,23 @@ int sw_score_batch_flat(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *
 {
     return sw_flat_impl(seqs, seqs_bytes, off, len, n_pairs, SwScoring{match, mismatch, gap_open, gap_extend},
                         scores_out);
+}
+
+int sw_ends_batch_flat(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *off, const int32_t *len, int64_t n_pairs,
+                       int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend, int32_t *scores_out,
+                       int32_t *ends_out)
+{
+    return sw_align_impl(seqs, seqs_bytes, off, len, n_pairs, SwScoring{match, mismatch, gap_open, gap_extend}, 1,
+                         scores_out, ends_out, nullptr, nullptr, nullptr, 0, nullptr);
+}
+
+int sw_align_batch_flat(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *off, const int32_t *len, int64_t n_pairs,
+                        int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend, int32_t *scores_out,
+                        int32_t *coords_out, int64_t *cigar_off_out, uint32_t *cigar_out, int64_t cigar_cap,
+                        int64_t *cigar_total_out)
+{
+    return sw_align_impl(seqs, seqs_bytes, off, len, n_pairs, SwScoring{match, mismatch, gap_open, gap_extend}, 2,
+                         scores_out, nullptr, coords_out, cigar_off_out, cigar_out, cigar_cap, cigar_total_out);
 }
 
 // sw_score_file_image over several GPUs: the image is cut into one byte range per GPU at line starts; every

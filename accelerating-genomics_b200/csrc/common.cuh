@@ -36,7 +36,8 @@ struct ProfSpan {
 };
 extern std::atomic<int> g_profiling;
 enum { AGX_PROF_SW_DUO = 0, AGX_PROF_SW_WAVE = 1, AGX_PROF_HMM_STREAM = 2, AGX_PROF_HMM_FP64 = 3,
-       AGX_PROF_SW_CLASSIFY = 4, AGX_PROF_HMM_CLASSIFY = 5, AGX_PROF_SW_LONG = 6, AGX_PROF_COUNT = 7 };
+       AGX_PROF_SW_CLASSIFY = 4, AGX_PROF_HMM_CLASSIFY = 5, AGX_PROF_SW_LONG = 6, AGX_PROF_SW_ALIGN_DP = 7,
+       AGX_PROF_SW_ALIGN_WALK = 8, AGX_PROF_COUNT = 9 };
 
 // ---- Smith-Waterman -----------------------------------------------------------------------
 struct SwScoring {
@@ -66,6 +67,59 @@ int sw_long_device(SwLongWorkspace &ws, const uint8_t *d_a, int64_t la, const ui
 int sw_long_host_multi(int n_dev, const int *dev, cudaStream_t *st, SwLongWorkspace **ws, const uint8_t *a,
                        int64_t la, const uint8_t *b, int64_t lb, SwScoring sc, int32_t *score_out);
 void sw_long_workspace_free(SwLongWorkspace &ws);
+
+// ---- Smith-Waterman alignment: end cell, start cell, CIGAR (sw_align.cuh) -------------------------------------
+// One per pair, written by the DP kernels (MODE 2), read by the traceback walk.
+struct SwWalkRec {
+    int64_t tb_off;            // byte offset of the H-byte matrix (of the pair's duo / of the pair) in the scratch
+    int32_t r_end, c_end;      // cell the walk starts from, kernel row / column
+    int32_t row_off, col_off;  // kernel row / column of symbol 0 of the row / column sequence
+    int32_t rstride;           // rows of one strip (duo layout) / rows of the pair (wavefront layout)
+    int16_t cls;               // duo class, -1 = wavefront layout
+    uint8_t half;              // 16-bit half of the duo
+    uint8_t flags;
+};
+static_assert(sizeof(SwWalkRec) == 32, "SwWalkRec");
+enum { SW_WK_A_IS_X = 1,       // the column sequence is line 1
+       SW_WK_NL_END = 2,       // the alignment ends on the newline symbols; the walk starts one cell before
+       SW_WK_NONE = 4,         // score 0: no alignment
+       SW_WK_RAW = 8,          // the kernel saw raw lines (newline symbols are ordinary rows / columns)
+       SW_WK_TRIVIAL = 16 };   // a line holds nothing but its newline: score and the one-cell alignment are known
+
+struct SwAlignWorkspace {
+    int32_t *order = nullptr;        // [SW_N_CLASSES][n_pairs]
+    int32_t *cap32 = nullptr;        // [n_pairs] most CIGAR runs a pair can have; later its run count
+    int64_t *tmp_off = nullptr;      // [n_pairs + 1] exclusive scan of cap32
+    int64_t *cig_off = nullptr;      // [n_pairs + 1] exclusive scan of the run counts
+    int32_t *gen_units = nullptr;    // [n_pairs] 256-byte units of each listed wavefront pair's matrix
+    int64_t *gen_off = nullptr;      // [n_pairs + 1] their scan (in units, turned into bytes in place)
+    int64_t *scan_tmp = nullptr;
+    int64_t *d_total = nullptr;      // 4 totals
+    int64_t *h_total = nullptr;      // pinned
+    SwWalkRec *wk = nullptr;         // [n_pairs]
+    int64_t cap_pairs = 0;
+    int32_t *counters = nullptr, *h_counters = nullptr;
+    uint8_t *tb = nullptr;           // H-byte matrices of the duo classes
+    int64_t cap_tb = 0;
+    uint8_t *tb_gen = nullptr;       // ... of the wavefront pairs (sized after the duo kernels bounced theirs)
+    int64_t cap_tb_gen = 0;
+    uint32_t *tmp_ops = nullptr;     // runs as the walk finds them (end -> start)
+    int64_t cap_tmp = 0;
+    int32_t *wave_scratch = nullptr;
+    int64_t cap_wave = 0;
+    ProfSpan prof_dp, prof_walk;
+};
+// mode 1: scores + end cells; mode 2: + start cells, run counts and (in ws.tmp_ops, reversed) the CIGAR runs.
+// d_ends [2n] (index in line 1, index in line 2); d_coords [4n] a_start a_end b_start b_end (mode 2).
+// tb_budget: bytes the H-byte matrices of this call may take (AGX_ENOMEM beyond it: the caller cuts smaller chunks).
+int sw_align_run_device(SwAlignWorkspace &ws, const uint8_t *d_seqs, const int64_t *d_off, const int32_t *d_len,
+                        int64_t n_pairs, SwScoring sc, int mode, int64_t tb_budget, int32_t *d_scores, int32_t *d_ends,
+                        int32_t *d_coords, int64_t *cigar_total, cudaStream_t st);
+// after a mode-2 run: runs of pair p go to d_cigar[ws.cig_off[p] ...), start -> end
+int sw_align_gather_device(SwAlignWorkspace &ws, int64_t n_pairs, uint32_t *d_cigar, cudaStream_t st);
+void sw_align_workspace_free(SwAlignWorkspace &ws);
+// upper bound of the H-byte matrix one pair can take (host-side chunking)
+int64_t sw_align_tb_bound(int32_t len_a, int32_t len_b);
 
 // Per-call device scratch for the SW path (owned by the device context).
 struct SwWorkspace {

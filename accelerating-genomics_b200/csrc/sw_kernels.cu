@@ -152,6 +152,25 @@ __device__ __forceinline__ DuoSeq load_pair(const uint8_t *seqs, const int64_t *
     return d;
 }
 
+// Alignment modes keep the reference's orientation: ix (the columns here) walks line 2 only when line 1 is
+// strictly longer, newline symbols counted (antidiagonalSmithWaterman.c:229-244) -- the end cell's tie rule is
+// stated in that frame.  a_is_x: the columns are line 1.
+__device__ __forceinline__ DuoSeq load_pair_oriented(const uint8_t *seqs, const int64_t *off,
+                                                     const int32_t *len, int32_t p, bool &a_is_x)
+{
+    DuoSeq d;
+    const uint8_t *x = seqs + off[2 * (int64_t)p];
+    const uint8_t *y = seqs + off[2 * (int64_t)p + 1];
+    int32_t lx = len[2 * (int64_t)p], ly = len[2 * (int64_t)p + 1];
+    a_is_x = !(lx > ly);
+    const bool nx = strip_newline(x, lx);
+    const bool ny = strip_newline(y, ly);
+    d.both_nl = nx && ny;
+    if (a_is_x) { d.a = x; d.la = lx; d.b = y; d.lb = ly; }
+    else        { d.a = y; d.la = ly; d.b = x; d.lb = lx; }
+    return d;
+}
+
 // ASCII -> 2-bit code (A 0, C 1, T 2, G 3); ok is cleared for anything outside "ACGT".
 __device__ __forceinline__ uint32_t base_code(uint32_t ch, bool &ok)
 {
@@ -166,15 +185,33 @@ __device__ __forceinline__ uint32_t base_code(uint32_t ch, bool &ok)
 #ifndef AGX_DUO_MINBLOCKS
 #define AGX_DUO_MINBLOCKS 5
 #endif
-__host__ __device__ constexpr int duo_min_blocks_sw(int K) { return K <= 19 ? AGX_DUO_MINBLOCKS : K <= 24 ? 3 : 2; }
-template <int G, int K>
-__global__ void __launch_bounds__(DUO_THREADS, duo_min_blocks_sw(K))
+// MODE 0: score only.  MODE 1: + END CELL.  MODE 2: + the low byte of every H, for the traceback walk.
+// The alignment modes carry ~10 more live registers (keys, store pointer, packed bytes): one CTA fewer.
+__host__ __device__ constexpr int duo_min_blocks_sw(int K, int MODE = 0)
+{
+    return K <= 19 ? (MODE ? 4 : AGX_DUO_MINBLOCKS) : K <= 24 ? 3 : 2;
+}
+// what the alignment modes hand over besides the score
+struct DuoAlignOut {
+    int32_t *ends;        // [2 * n_pairs] end cell as (index in line 1, index in line 2), -1 -1 when the score is 0
+    SwWalkRec *wk;        // [n_pairs]     MODE 2: where the traceback walk starts
+    uint8_t *tb;          // MODE 2: H-byte matrices of this class, one per duo
+    int64_t tb_class_off; //         where this class starts in the scratch (the walk addresses from the scratch base)
+    int64_t tb_duo_bytes; //         G * rstride * K2 * 4
+    int32_t rstride;      //         rows of one strip (>= every lb of the class)
+    int32_t k32;          // 32, opaque to ptxas: key = H * 32 + tag as one IMAD on the FMA pipe
+    int16_t cls;
+};
+template <int G, int K, int MODE>
+__global__ void __launch_bounds__(DUO_THREADS, duo_min_blocks_sw(K, MODE))
 sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
               const int32_t *__restrict__ len, const int32_t *__restrict__ order_cls,
               int32_t n_in_class, DuoConst kc, int32_t *__restrict__ scores,
-              int32_t *__restrict__ generic_list, int32_t *__restrict__ generic_cursor)
+              int32_t *__restrict__ generic_list, int32_t *__restrict__ generic_cursor, DuoAlignOut ao)
 {
     constexpr int CAP = G * K;
+    constexpr int K2 = (K + 1) / 2;       // MODE 2: 32-bit words per thread row (2 columns x 2 pairs, one byte each)
+    static_assert(K2 % 2 == 0, "thread rows are stored as 64-bit words");
     constexpr int SUBS = DUO_THREADS / G;
     // row steps per loop trip: 8 measured +3 % over 2 at K = 19 (16 overflows the instruction cache: -17 %);
     // the wide classes keep 2
@@ -189,13 +226,15 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
     // ---- the two pairs of this sub-warp ------------------------------------------------------
     int32_t pid[2] = {-1, -1};
     DuoSeq sq[2];
+    bool a_is_x[2] = {true, true};
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int32_t slot = 2 * duo + h;
         sq[h].a = sq[h].b = nullptr; sq[h].la = sq[h].lb = 0; sq[h].both_nl = false;
         if (slot < n_in_class) {
             pid[h] = order_cls[slot];
-            sq[h] = load_pair(seqs, off, len, pid[h]);
+            if constexpr (MODE == 0) sq[h] = load_pair(seqs, off, len, pid[h]);
+            else sq[h] = load_pair_oriented(seqs, off, len, pid[h], a_is_x[h]);
         }
     }
     // ---- column selectors (columns right-aligned; padding columns select "sign of byte 0") ----
@@ -256,7 +295,8 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 if (__ballot_sync(0xffffffffu, saw_n[h]) & submask) {   // uniform inside the sub-warp
-                    if (attempt == 0 && sq[h].lb <= CAP) {
+                    // (the alignment modes never swap: their tie rule is tied to the orientation)
+                    if (MODE == 0 && attempt == 0 && sq[h].lb <= CAP) {
                         const uint8_t *tp = sq[h].a; sq[h].a = sq[h].b; sq[h].b = tp;
                         const int32_t tl = sq[h].la; sq[h].la = sq[h].lb; sq[h].lb = tl;
                         redo = true;
@@ -279,6 +319,16 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
 #pragma unroll
     for (int j = 0; j < K; ++j) { Gp[j] = kc.goe2; F[j] = kc.goe2; }
     uint32_t rmax = kc.goe2, g_out = kc.goe2, e_out = kc.goe2, g_in_prev = kc.goe2;
+    // Alignment modes.  Every cell gets a 15-bit key H * 32 + (31 - j) per half (one IMAD for both halves; H <= 1023),
+    // the row maximum of the keys names the row's best H and its FIRST column, and once per row that is widened
+    // to a 32-bit key that orders cells as the reference visits them:
+    //     H << 22 | (4095 - d) << 10 | (1023 - c),   c = kernel column, d = kernel row + c + 31
+    // (larger H first, then the earlier anti-diagonal, then the smaller ix).  best32 = max of those keys.
+    uint32_t best32[2] = {0u, 0u};
+    uint32_t kbase = ((uint32_t)(4033 - t * K + t) << 10) + (uint32_t)(992 - t * K);   // row -t: the first step of lane t
+    uint2 *tbp = nullptr;
+    if constexpr (MODE == 2)
+        tbp = reinterpret_cast<uint2 *>(ao.tb + (int64_t)duo * ao.tb_duo_bytes) + ((int64_t)t * ao.rstride - t) * (K2 / 2);
 
     for (int i = t; i < DUO_RING; i += G) ring[sub][i] = make_uint2(kc.xb4, kc.xb4);
 
@@ -316,6 +366,8 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
             uint32_t gdiag = g_in_prev;
             g_in_prev = g_in;
             uint32_t gleft = g_in;
+            uint32_t rk = 0u, kprev = 0u, hprev = 0u;
+            uint32_t pk[MODE == 2 ? K2 : 1];
 #pragma unroll
             for (int j = 0; j < K; ++j) {
                 const uint32_t tt = prmt(R.x, R.y, sel[j]);                  // (subst - goe) per half
@@ -326,17 +378,54 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
                 gdiag = Gp[j];
                 gleft = __vadd2(hcell, kc.goe2);                          // H[i][j] + goe
                 Gp[j] = gleft;
-                if (j & 1) rmax = __vimax3_s16x2(rmax, Gp[j - 1], gleft);
-                else if (j == K - 1) rmax = __vmaxs2(rmax, gleft);
+                if constexpr (MODE == 0) {
+                    if (j & 1) rmax = __vimax3_s16x2(rmax, Gp[j - 1], gleft);
+                    else if (j == K - 1) rmax = __vmaxs2(rmax, gleft);
+                } else {
+                    uint32_t key;
+                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(key) : "r"(hcell), "r"((uint32_t)ao.k32), "r"((uint32_t)(31 - j) * 0x00010001u));
+                    if (j & 1) rk = __vimax3_s16x2(rk, kprev, key);
+                    else if (j == K - 1) rk = __vmaxs2(rk, key);
+                    kprev = key;
+                }
+                if constexpr (MODE == 2) {
+                    // bytes [lo pair col j-1, lo pair col j, hi pair col j-1, hi pair col j]
+                    if (j & 1) pk[j >> 1] = prmt(hprev, hcell, 0x6240u);
+                    else if (j == K - 1) pk[j >> 1] = prmt(hcell, 0u, 0x6240u);
+                    hprev = hcell;
+                }
             }
             g_out = gleft;
             e_out = e;
+            if constexpr (MODE != 0) {
+                const uint32_t m = rk & 0xffe0ffe0u;             // H << 5 per half
+                const uint32_t jj = rk & 0x001f001fu;            // 31 - (first column with that H) per half
+                uint32_t k0, k1;
+                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(k0) : "r"(jj & 0xffffu), "r"(1025u), "r"(kbase));
+                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(k1) : "r"(jj >> 16), "r"(1025u), "r"(kbase));
+                best32[0] = max(best32[0], k0 + (m << 17));
+                best32[1] = max(best32[1], k1 + ((m >> 16) << 17));
+                kbase -= 1024u;
+            }
+            if constexpr (MODE == 2) {
+                if ((unsigned)(s - t) < (unsigned)Lb) {
+#pragma unroll
+                    for (int q = 0; q < K2 / 2; ++q) tbp[q] = make_uint2(pk[2 * q], pk[2 * q + 1]);
+                }
+                tbp += K2 / 2;
+            }
         }
     }
 
     // ---- results ---------------------------------------------------------------------------------
 #pragma unroll
     for (int m = G / 2; m >= 1; m >>= 1) rmax = __vmaxs2(rmax, __shfl_xor_sync(0xffffffffu, rmax, m, G));
+    if constexpr (MODE != 0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int m = G / 2; m >= 1; m >>= 1) best32[h] = max(best32[h], __shfl_xor_sync(0xffffffffu, best32[h], m, G));
+    }
     const uint32_t corner2 = __shfl_sync(0xffffffffu, Gp[K - 1], G - 1, G);
     const uint32_t okbits0 = __ballot_sync(0xffffffffu, okh[0]), okbits1 = __ballot_sync(0xffffffffu, okh[1]);
     const bool all_ok[2] = {(okbits0 & submask) == submask, (okbits1 & submask) == submask};
@@ -350,10 +439,40 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
                 generic_list[atomicAdd(generic_cursor, 1)] = pid[h];
                 continue;
             }
-            const int32_t best = (int32_t)(int16_t)(rmax >> (16 * h)) - kc.goe;
             const int32_t corner = (int32_t)(int16_t)(corner2 >> (16 * h)) - kc.goe;
-            // '\n' is the last symbol of both lines: it can only match at the corner cell
-            scores[pid[h]] = sq[h].both_nl ? max(best, corner + kc.match) : best;
+            if constexpr (MODE == 0) {
+                const int32_t best = (int32_t)(int16_t)(rmax >> (16 * h)) - kc.goe;
+                // '\n' is the last symbol of both lines: it can only match at the corner cell
+                scores[pid[h]] = sq[h].both_nl ? max(best, corner + kc.match) : best;
+            } else {
+                const uint32_t key = best32[h];
+                int32_t best = (int32_t)(key >> 22);
+                const int32_t c_end = 1023 - (int32_t)(key & 1023u);
+                const int32_t r_end = 4095 - (int32_t)((key >> 10) & 4095u) - c_end - 31;
+                // kernel row / column of symbol 0 of the row / column sequence
+                const int32_t row_off = Lb - sq[h].lb, col_off = CAP - sq[h].la;
+                int32_t ea = c_end - col_off, eb = r_end - row_off;     // in the column / row sequence
+                // the newline corner is the LAST cell the reference visits: it takes the maximum only when larger
+                const bool nl_end = sq[h].both_nl && corner + kc.match > best;
+                if (nl_end) { best = corner + kc.match; ea = sq[h].la; eb = sq[h].lb; }
+                if (best == 0) ea = eb = -1;
+                scores[pid[h]] = best;
+                ao.ends[2 * (int64_t)pid[h]] = a_is_x[h] ? ea : eb;
+                ao.ends[2 * (int64_t)pid[h] + 1] = a_is_x[h] ? eb : ea;
+                if constexpr (MODE == 2) {
+                    SwWalkRec w;
+                    w.tb_off = ao.tb_class_off + (int64_t)duo * ao.tb_duo_bytes;
+                    w.r_end = nl_end ? Lb - 1 : r_end;
+                    w.c_end = nl_end ? CAP - 1 : c_end;
+                    w.row_off = row_off;
+                    w.col_off = col_off;
+                    w.rstride = ao.rstride;
+                    w.cls = ao.cls;
+                    w.half = (uint8_t)h;
+                    w.flags = (uint8_t)((a_is_x[h] ? SW_WK_A_IS_X : 0) | (nl_end ? SW_WK_NL_END : 0) | (best == 0 ? SW_WK_NONE : 0));
+                    ao.wk[pid[h]] = w;
+                }
+            }
         }
     }
 }
@@ -389,10 +508,16 @@ __device__ __forceinline__ uint32_t wave_code(uint32_t ch, bool &ok)
 // One pair on one warp.  CODED: substitution score = one sign-extending PRMT from an 8-byte per-row table,
 // additions on the FMA pipe (4.5 instead of 7.5 ALU-pipe instructions per cell, as in sw_long.cu); it gives
 // up (returns false) when it meets a byte outside its alphabet and the raw-byte pass redoes the pair.
-template <bool CODED>
+// MODE as in sw_duo_kernel.  The alignment modes order cells with a 64-bit key,
+//     H << 43 | (2^29 - 1 - (row + column)) << 14 | (16383 - column)
+// (H < 2^21, row + column < 2^29, column < 2^14: checked on the host); MODE 2 stores the low byte of every H at
+// tb[((stripe * lb + row) * 32 + lane) * 8 + j].
+constexpr uint32_t WAVE_DMAX = (1u << 29) - 1u;
+template <bool CODED, int MODE>
 __device__ bool wave_pair(const uint8_t *a, int32_t la, const uint8_t *b, int32_t lb, SwScoring sc, int32_t one,
                           int32_t *bnd, int32_t (*r_byte)[WAVE_RING], int32_t (*r_hi)[WAVE_RING],
-                          int32_t (*r_g)[WAVE_RING], int32_t (*r_e)[WAVE_RING], int2 (*stage)[32], int32_t &best_out)
+                          int32_t (*r_g)[WAVE_RING], int32_t (*r_e)[WAVE_RING], int2 (*stage)[32], int32_t &best_out,
+                          unsigned long long &key_out, uint8_t *tb, int32_t k32)
 {
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -403,6 +528,7 @@ __device__ bool wave_pair(const uint8_t *a, int32_t la, const uint8_t *b, int32_
     const uint32_t mxor = (uint32_t)(uint8_t)(int8_t)sub_mis ^ (uint32_t)(uint8_t)(int8_t)sub_match;
     bool ok = true;
     int32_t bestg = goe;
+    unsigned long long best64 = 0ull;
     const int n_stripes = (la + WAVE_W - 1) / WAVE_W;
     for (int st = 0; st < n_stripes; ++st) {
         const int c0 = st * WAVE_W + lane * WAVE_K;
@@ -466,6 +592,8 @@ __device__ bool wave_pair(const uint8_t *a, int32_t la, const uint8_t *b, int32_
                 int32_t gdiag = g_in_prev;
                 g_in_prev = g_in;
                 int32_t gleft = g_in;
+                int32_t rk = 0, kprev = 0;
+                uint32_t hb[MODE == 2 ? WAVE_K : 1];
 #pragma unroll
                 for (int j = 0; j < WAVE_K; ++j) {
                     int32_t d;
@@ -477,11 +605,35 @@ __device__ bool wave_pair(const uint8_t *a, int32_t la, const uint8_t *b, int32_
                     gdiag = Gp[j];
                     if constexpr (CODED) gleft = add_fma(hcell, goe, one); else gleft = hcell + goe;
                     Gp[j] = gleft;
-                    if (j & 1) bestg = __vimax3_s32(bestg, Gp[j - 1], gleft);
-                    else if (j == WAVE_K - 1) bestg = max(bestg, gleft);
+                    if constexpr (MODE == 0) {
+                        if (j & 1) bestg = __vimax3_s32(bestg, Gp[j - 1], gleft);
+                        else if (j == WAVE_K - 1) bestg = max(bestg, gleft);
+                    } else {
+                        int32_t key;                                   // H * 32 + (31 - j): the row maximum names H and its first column
+                        asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(key) : "r"(hcell), "r"(k32), "r"(31 - j));
+                        if (j & 1) rk = __vimax3_s32(rk, kprev, key);
+                        else if (j == WAVE_K - 1) rk = max(rk, key);
+                        kprev = key;
+                    }
+                    if constexpr (MODE == 2) hb[j] = (uint32_t)hcell;
                 }
                 g_out = gleft;
                 e_out = e;
+                if constexpr (MODE != 0) {
+                    const int r = s - lane;
+                    const uint32_t col = (uint32_t)(c0 + 31 - (rk & 31));
+                    const uint32_t dd = WAVE_DMAX - ((uint32_t)r + col);        // junk rows (r < 0) have H = 0
+                    const unsigned long long k64 = ((unsigned long long)(uint32_t)(rk >> 5) << 43) |
+                                                   ((unsigned long long)(dd & WAVE_DMAX) << 14) | (16383u - col);
+                    best64 = max(best64, k64);
+                    if constexpr (MODE == 2) {
+                        if ((unsigned)r < (unsigned)lb) {
+                            const uint32_t w0 = prmt(prmt(hb[0], hb[1], 0x0040u), prmt(hb[2], hb[3], 0x0040u), 0x5410u);
+                            const uint32_t w1 = prmt(prmt(hb[4], hb[5], 0x0040u), prmt(hb[6], hb[7], 0x0040u), 0x5410u);
+                            reinterpret_cast<uint2 *>(tb)[((int64_t)st * lb + r) * 32 + lane] = make_uint2(w0, w1);
+                        }
+                    }
+                }
                 if (lane == 31) stage[wib][u] = make_int2(g_out, e_out);     // row s - 31 of the last column
             }
             // one coalesced store per block instead of a global store per row step
@@ -500,14 +652,28 @@ __device__ bool wave_pair(const uint8_t *a, int32_t la, const uint8_t *b, int32_
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) bestg = max(bestg, __shfl_xor_sync(0xffffffffu, bestg, m));
     best_out = max(bestg - goe, 0);
+    if constexpr (MODE != 0) {
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) best64 = max(best64, __shfl_xor_sync(0xffffffffu, best64, m));
+        key_out = best64;
+        best_out = (int32_t)(best64 >> 43);
+    }
     return true;
 }
 
+struct WaveAlignOut {
+    int32_t *ends;             // [2 * n_pairs]
+    SwWalkRec *wk;             // [n_pairs]   MODE 2
+    uint8_t *tb;               // MODE 2: H-byte matrices of the listed pairs
+    const int64_t *tb_off;     //         [list position] byte offset of that pair's matrix
+    int32_t k32;
+};
+template <int MODE>
 __global__ void __launch_bounds__(WAVE_WARPS * 32)
 sw_wave_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
                const int32_t *__restrict__ len, const int32_t *__restrict__ list,
                const int32_t *__restrict__ list_count, SwScoring sc, int32_t one, int32_t coded_ok,
-               int32_t *__restrict__ scores, int32_t *__restrict__ scratch, int64_t scratch_stride)
+               int32_t *__restrict__ scores, int32_t *__restrict__ scratch, int64_t scratch_stride, WaveAlignOut ao)
 {
     __shared__ int32_t r_byte[WAVE_WARPS][WAVE_RING];
     __shared__ int32_t r_hi[WAVE_WARPS][WAVE_RING];
@@ -533,10 +699,37 @@ sw_wave_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off
         if (lx > ly) { a = y; la = ly; b = x; lb = lx; }
 
         int32_t best = 0;
+        unsigned long long key = 0ull;
+        uint8_t *tb = nullptr;
+        if constexpr (MODE == 2) tb = ao.tb + ao.tb_off[it];
         bool done = false;
-        if (coded_ok) done = wave_pair<true>(a, la, b, lb, sc, one, bnd, r_byte, r_hi, r_g, r_e, stage, best);
-        if (!done) wave_pair<false>(a, la, b, lb, sc, one, bnd, r_byte, r_hi, r_g, r_e, stage, best);
-        if (lane == 0) scores[p] = best;
+        if (coded_ok) done = wave_pair<true, MODE>(a, la, b, lb, sc, one, bnd, r_byte, r_hi, r_g, r_e, stage, best, key, tb, ao.k32);
+        if (!done) wave_pair<false, MODE>(a, la, b, lb, sc, one, bnd, r_byte, r_hi, r_g, r_e, stage, best, key, tb, ao.k32);
+        if (lane == 0) {
+            scores[p] = best;
+            if constexpr (MODE != 0) {
+                // the wavefront kernel sees raw bytes (newline symbols included) in the reference's orientation
+                const int32_t col = 16383 - (int32_t)(key & 16383u);
+                const int32_t row = (int32_t)(WAVE_DMAX - (uint32_t)((key >> 14) & WAVE_DMAX)) - col;
+                const bool a_is_x = !(lx > ly);
+                const int32_t ea = best > 0 ? col : -1, eb = best > 0 ? row : -1;
+                ao.ends[2 * (int64_t)p] = a_is_x ? ea : eb;
+                ao.ends[2 * (int64_t)p + 1] = a_is_x ? eb : ea;
+                if constexpr (MODE == 2) {
+                    SwWalkRec w;
+                    w.tb_off = ao.tb_off[it];
+                    w.r_end = row;
+                    w.c_end = col;
+                    w.row_off = 0;
+                    w.col_off = 0;
+                    w.rstride = lb;
+                    w.cls = -1;
+                    w.half = 0;
+                    w.flags = (uint8_t)((a_is_x ? SW_WK_A_IS_X : 0) | SW_WK_RAW | (best == 0 ? SW_WK_NONE : 0));
+                    ao.wk[p] = w;
+                }
+            }
+        }
     }
 }
 
@@ -550,13 +743,15 @@ int launch_duo_class(const uint8_t *d_seqs, const int64_t *d_off, const int32_t 
     const int duos = (count + 1) / 2;
     const int blocks = (duos + SUBS - 1) / SUBS;
     if (blocks == 0) return AGX_OK;
-    sw_duo_kernel<G, K><<<blocks, DUO_THREADS, 0, st>>>(
+    sw_duo_kernel<G, K, 0><<<blocks, DUO_THREADS, 0, st>>>(
         d_seqs, d_off, d_len, order + (int64_t)C * n_pairs, count, kc, d_scores,
-        const_cast<int32_t *>(order) + (int64_t)GENERIC * n_pairs, counters + GENERIC);
+        const_cast<int32_t *>(order) + (int64_t)GENERIC * n_pairs, counters + GENERIC, DuoAlignOut{});
     count_launch();
     AGX_CUDA(cudaGetLastError());
     return AGX_OK;
 }
+
+#include "sw_align.cuh"
 
 template <int C>
 int launch_all_duo(const uint8_t *d_seqs, const int64_t *d_off, const int32_t *d_len,
@@ -714,13 +909,229 @@ int sw_run_device(SwWorkspace &ws, const uint8_t *d_seqs, const int64_t *d_off, 
         // the coded pass needs the two substitution scores (minus goe) to fit a signed byte
         const bool coded_ok = (sc.match - goe) <= 127 && (sc.match - goe) >= -128 && (sc.mismatch - goe) <= 127 &&
                               (sc.mismatch - goe) >= -128 && getenv("AGX_WAVE_RAW") == nullptr;
-        sw_wave_kernel<<<blocks, WAVE_WARPS * 32, 0, st>>>(
+        sw_wave_kernel<0><<<blocks, WAVE_WARPS * 32, 0, st>>>(
             d_seqs, d_off, d_len, ws.order + (int64_t)GENERIC * n_pairs, ws.counters + GENERIC, sc, 1,
-            coded_ok ? 1 : 0, d_scores, ws.wave_scratch, stride);
+            coded_ok ? 1 : 0, d_scores, ws.wave_scratch, stride, WaveAlignOut{});
         ws.prof_wave.end(st);
         count_launch();
         AGX_CUDA(cudaGetLastError());
     }
+    return AGX_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side of the alignment path (end cell / start cell / CIGAR)
+// ------------------------------------------------------------------------------------------
+namespace {
+template <typename T> int grow(T *&p, int64_t &cap, int64_t need)
+{
+    if (need <= cap) return AGX_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    const int64_t want = need + need / 8 + 64;
+    cudaError_t e = cudaMalloc(&p, (size_t)want * sizeof(T));
+    if (e != cudaSuccess) return fail(AGX_ENOMEM, std::string("cudaMalloc (alignment scratch): ") + cudaGetErrorString(e));
+    cap = want;
+    return AGX_OK;
+}
+}  // namespace
+
+void sw_align_workspace_free(SwAlignWorkspace &ws)
+{
+    for (void *p : {(void *)ws.order, (void *)ws.cap32, (void *)ws.tmp_off, (void *)ws.cig_off, (void *)ws.gen_units,
+                    (void *)ws.gen_off, (void *)ws.scan_tmp, (void *)ws.d_total, (void *)ws.wk, (void *)ws.counters,
+                    (void *)ws.tb, (void *)ws.tb_gen, (void *)ws.tmp_ops, (void *)ws.wave_scratch})
+        if (p) cudaFree(p);
+    if (ws.h_total) cudaFreeHost(ws.h_total);
+    if (ws.h_counters) cudaFreeHost(ws.h_counters);
+    ws.prof_dp.destroy();
+    ws.prof_walk.destroy();
+    ws = SwAlignWorkspace();
+}
+
+int64_t sw_align_tb_bound(int32_t len_a, int32_t len_b)
+{
+    // the larger of the two layouts a pair can end up in: its duo class (half a duo: CAP/2 words x 2 pairs = CAP
+    // bytes per row) and the wavefront layout (256-byte stripes)
+    const int32_t ra = len_a > len_b ? len_b : len_a, rb = len_a > len_b ? len_a : len_b;
+    int64_t duo = 0;
+    for (int c = SW_N_DUO_CLASSES - 1; c >= 0; --c)
+        if (ra <= duo_cap(c) + 1) duo = (int64_t)duo_class(c).g * ((duo_class(c).k + 1) / 2) * 2 * rb;
+    const int64_t wave = (int64_t)((ra + 255) / 256) * 256 * rb;
+    return duo > wave ? duo : wave;
+}
+
+int sw_align_run_device(SwAlignWorkspace &ws, const uint8_t *d_seqs, const int64_t *d_off, const int32_t *d_len,
+                        int64_t n_pairs, SwScoring sc, int mode, int64_t tb_budget, int32_t *d_scores, int32_t *d_ends,
+                        int32_t *d_coords, int64_t *cigar_total, cudaStream_t st)
+{
+    if (cigar_total) *cigar_total = 0;
+    if (n_pairs == 0) return AGX_OK;
+    if (n_pairs > (int64_t)1 << 30) return fail(AGX_ERANGE, "sw align: more than 2^30 pairs in one call");
+    if (!(sc.match > 0 && sc.mismatch < 0 && sc.gap_open <= 0 && sc.gap_extend < 0))
+        return fail(AGX_ERANGE, "sw: scoring must satisfy match > 0 > mismatch, gap_open <= 0, gap_extend < 0");
+    const int32_t goe = sc.gap_open + sc.gap_extend;
+    // neighbouring H values must differ by less than 128 (the walk rebuilds H from byte differences) and the
+    // keys hold 21 bits of score
+    if (sc.match - goe > 127 || -sc.mismatch > 127 || -goe > 127)
+        return fail(AGX_ERANGE, "sw align: match - (gap_open + gap_extend), -mismatch and -(gap_open + gap_extend) must be <= 127");
+
+    int rc;
+    if (n_pairs > ws.cap_pairs) {
+        int64_t c;
+        const int64_t n = n_pairs + n_pairs / 8 + 64;
+#define AGX_REGROW(ptr, T, elems) c = 0; if (ptr) { cudaFree(ptr); ptr = nullptr; } if ((rc = grow(ptr, c, (int64_t)(elems))) != AGX_OK) return rc;
+        ws.cap_pairs = 0;
+        AGX_REGROW(ws.order, int32_t, n * SW_N_CLASSES)
+        AGX_REGROW(ws.cap32, int32_t, n)
+        AGX_REGROW(ws.tmp_off, int64_t, n + 1)
+        AGX_REGROW(ws.cig_off, int64_t, n + 1)
+        AGX_REGROW(ws.gen_units, int32_t, n)
+        AGX_REGROW(ws.gen_off, int64_t, n + 1)
+        AGX_REGROW(ws.scan_tmp, int64_t, device_scan_tmp_elems(n) + 8)
+        AGX_REGROW(ws.wk, SwWalkRec, n)
+#undef AGX_REGROW
+        ws.cap_pairs = n;
+    }
+    if (!ws.counters) {
+        AGX_CUDA(cudaMalloc(&ws.counters, CNT_A_WORDS * sizeof(int32_t)));
+        AGX_CUDA(cudaMallocHost(&ws.h_counters, CNT_A_WORDS * sizeof(int32_t)));
+        AGX_CUDA(cudaMalloc(&ws.d_total, 4 * sizeof(int64_t)));
+        AGX_CUDA(cudaMallocHost(&ws.h_total, 4 * sizeof(int64_t)));
+    }
+
+    // s16x2 path: as in sw_run_device, and every H must fit the 10 score bits of the row keys
+    const bool s16_ok = (sc.match - goe) <= 127 && (sc.mismatch - goe) >= -128 && goe >= -1024 && sc.match <= 30;
+    const int32_t s16_max_short = s16_ok ? min(DUO_MAX_CAP, 1023 / sc.match) : 0;
+
+    AGX_CUDA(cudaMemsetAsync(ws.counters, 0, CNT_A_WORDS * sizeof(int32_t), st));
+    const int cblocks = (int)((n_pairs + 255) / 256);
+    sw_align_classify_kernel<<<cblocks, 256, 0, st>>>(d_seqs, d_off, d_len, n_pairs, s16_max_short, sw_long_cells(), sc.match,
+                                                      mode, ws.order, ws.counters, d_scores, d_ends, ws.cap32, ws.wk);
+    count_launch();
+    AGX_CUDA(cudaGetLastError());
+    AGX_CUDA(cudaMemcpyAsync(ws.h_counters, ws.counters, CNT_A_WORDS * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    AGX_CUDA(cudaStreamSynchronize(st));
+    if (ws.h_counters[CNT_A_BAD] > 0)
+        return fail(AGX_ERANGE, "sw align: " + std::to_string(ws.h_counters[CNT_A_BAD]) +
+                                    " pair(s) outside the supported range (whole-GPU pairs of >= 2^28 cells, a shorter "
+                                    "line above 16000 symbols, or lengths adding up to 2^29)");
+    int32_t counts[SW_N_CLASSES], rows[SW_N_DUO_CLASSES];
+    int64_t n_duo = 0, tb_base[SW_N_DUO_CLASSES], duo_total = 0;
+    for (int c = 0; c < SW_N_CLASSES; ++c) counts[c] = ws.h_counters[c];
+    for (int c = 0; c < SW_N_DUO_CLASSES; ++c) {
+        n_duo += counts[c];
+        rows[c] = ws.h_counters[CNT_A_ROWS + c];
+        tb_base[c] = duo_total;
+        if (mode == 2) {
+            const int64_t duos = (counts[c] + 1) / 2;
+            duo_total += (duos * duo_class(c).g * rows[c] * ((duo_class(c).k + 1) / 2) * 4 + 255) / 256 * 256;
+        }
+    }
+    const int32_t max_len = ws.h_counters[CNT_MAXLEN];
+    if (mode == 2) {
+        if (duo_total > tb_budget) return fail(AGX_ENOMEM, "sw align: traceback matrices exceed the budget");
+        if ((rc = grow(ws.tb, ws.cap_tb, duo_total + 256)) != AGX_OK) return rc;
+    }
+
+    DuoConst kc;
+    kc.goe = goe;
+    kc.match = sc.match;
+    kc.goe2 = ((uint32_t)(uint16_t)(int16_t)goe) * 0x00010001u;
+    kc.ext2 = ((uint32_t)(uint16_t)(int16_t)sc.gap_extend) * 0x00010001u;
+    const uint32_t xb = (uint32_t)(uint8_t)(int8_t)(sc.mismatch - goe);
+    const uint32_t mb = (uint32_t)(uint8_t)(int8_t)(sc.match - goe);
+    kc.xb4 = xb * 0x01010101u;
+    kc.mxor = xb ^ mb;
+
+    DuoAlignOut ao = {};
+    ao.ends = d_ends;
+    ao.wk = ws.wk;
+    ao.tb = mode == 2 ? ws.tb : nullptr;
+    ao.k32 = 32;
+    ws.prof_dp.begin(st);
+    rc = launch_duo_align<0>(d_seqs, d_off, d_len, ws.order, n_pairs, counts, rows, tb_base, mode, kc, d_scores,
+                             ws.counters, ao, st);
+    if (rc != AGX_OK) return rc;
+
+    // wavefront pairs: those classified so + those the duo kernels bounced (bytes outside ACGT)
+    const int64_t generic_upper = (int64_t)counts[GENERIC] + n_duo;
+    if (generic_upper > 0) {
+        const int32_t *glist = ws.order + (int64_t)GENERIC * n_pairs;
+        if (mode == 2) {
+            const int gb = (int)((generic_upper + 255) / 256);
+            sw_wave_tb_units_kernel<<<gb, 256, 0, st>>>(d_len, glist, ws.counters + GENERIC, ws.gen_units, generic_upper);
+            count_launch();
+            if ((rc = device_exclusive_scan(ws.gen_units, generic_upper, ws.gen_off, ws.scan_tmp, ws.d_total, st)) != AGX_OK) return rc;
+            AGX_CUDA(cudaMemcpyAsync(ws.h_total, ws.d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+            AGX_CUDA(cudaStreamSynchronize(st));
+            const int64_t gen_bytes = ws.h_total[0] * 256;
+            if (duo_total + gen_bytes > tb_budget) return fail(AGX_ENOMEM, "sw align: traceback matrices exceed the budget");
+            if ((rc = grow(ws.tb_gen, ws.cap_tb_gen, gen_bytes + 256)) != AGX_OK) return rc;
+            units_to_bytes_kernel<<<gb, 256, 0, st>>>(ws.gen_off, generic_upper, 0);
+            count_launch();
+        }
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int64_t want_warps = generic_upper;
+        const int64_t max_warps = (int64_t)sms * 16;
+        if (want_warps > max_warps) want_warps = max_warps;
+        const int64_t stride = 2 * (int64_t)max_len + 64;
+        const int64_t fit = ((int64_t)1 << 29) / stride;
+        if (want_warps > fit) want_warps = fit > WAVE_WARPS ? fit : WAVE_WARPS;
+        const int blocks = (int)((want_warps + WAVE_WARPS - 1) / WAVE_WARPS);
+        if ((rc = grow(ws.wave_scratch, ws.cap_wave, stride * blocks * WAVE_WARPS)) != AGX_OK) return rc;
+        const bool coded_ok = (sc.match - goe) <= 127 && (sc.match - goe) >= -128 && (sc.mismatch - goe) <= 127 &&
+                              (sc.mismatch - goe) >= -128 && getenv("AGX_WAVE_RAW") == nullptr;
+        WaveAlignOut wo = {};
+        wo.ends = d_ends;
+        wo.wk = ws.wk;
+        wo.tb = ws.tb_gen;
+        wo.tb_off = ws.gen_off;
+        wo.k32 = 32;
+        if (mode == 2)
+            sw_wave_kernel<2><<<blocks, WAVE_WARPS * 32, 0, st>>>(d_seqs, d_off, d_len, glist, ws.counters + GENERIC, sc, 1,
+                                                               coded_ok ? 1 : 0, d_scores, ws.wave_scratch, stride, wo);
+        else
+            sw_wave_kernel<1><<<blocks, WAVE_WARPS * 32, 0, st>>>(d_seqs, d_off, d_len, glist, ws.counters + GENERIC, sc, 1,
+                                                               coded_ok ? 1 : 0, d_scores, ws.wave_scratch, stride, wo);
+        count_launch();
+        AGX_CUDA(cudaGetLastError());
+    }
+    ws.prof_dp.end(st);
+    if (mode != 2) return AGX_OK;
+
+    // the walk: room for the runs of every pair, then one thread per pair
+    if ((rc = device_exclusive_scan(ws.cap32, n_pairs, ws.tmp_off, ws.scan_tmp, ws.d_total + 1, st)) != AGX_OK) return rc;
+    AGX_CUDA(cudaMemcpyAsync(ws.h_total + 1, ws.d_total + 1, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    AGX_CUDA(cudaStreamSynchronize(st));
+    if ((rc = grow(ws.tmp_ops, ws.cap_tmp, ws.h_total[1] + 16)) != AGX_OK) return rc;
+    AGX_CUDA(cudaMemsetAsync(ws.d_total + 2, 0, sizeof(int64_t), st));
+    ws.prof_walk.begin(st);
+    // the two matrix buffers are addressed from one base: wavefront records carry an offset relative to tb_gen
+    sw_walk_kernel<<<(int)((n_pairs + 127) / 128), 128, 0, st>>>(d_seqs, d_off, d_len, n_pairs, sc, ws.wk, ws.tb, ws.tb_gen, d_scores,
+                                                                d_ends, d_coords, ws.tmp_ops, ws.tmp_off, ws.cap32,
+                                                                reinterpret_cast<int32_t *>(ws.d_total + 2));
+    count_launch();
+    ws.prof_walk.end(st);
+    AGX_CUDA(cudaGetLastError());
+    if ((rc = device_exclusive_scan(ws.cap32, n_pairs, ws.cig_off, ws.scan_tmp, ws.cig_off + n_pairs, st)) != AGX_OK) return rc;
+    AGX_CUDA(cudaMemcpyAsync(ws.h_total + 2, ws.d_total + 2, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    AGX_CUDA(cudaMemcpyAsync(ws.h_total + 3, ws.cig_off + n_pairs, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    AGX_CUDA(cudaStreamSynchronize(st));
+    if (ws.h_total[2] != 0) return fail(AGX_ECUDA, "sw align: the traceback walk lost its path (internal error)");
+    if (cigar_total) *cigar_total = ws.h_total[3];
+    return AGX_OK;
+}
+
+int sw_align_gather_device(SwAlignWorkspace &ws, int64_t n_pairs, uint32_t *d_cigar, cudaStream_t st)
+{
+    if (n_pairs == 0) return AGX_OK;
+    sw_cigar_gather_kernel<<<(int)((n_pairs + 255) / 256), 256, 0, st>>>(ws.tmp_ops, ws.tmp_off, ws.cap32, ws.cig_off, n_pairs, d_cigar);
+    count_launch();
+    AGX_CUDA(cudaGetLastError());
     return AGX_OK;
 }
 

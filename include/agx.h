@@ -73,7 +73,7 @@ void agx_reset_launch_count(void);
  * returns the duration (ms) of the LAST recorded span on `device`, or a negative number if that
  * span never ran.  which: 0 SW inter-task (duo) kernels, 1 SW wavefront kernel, 2 PairHMM FP32
  * stream kernels, 3 PairHMM FP64 kernel, 4 SW classify kernel, 5 PairHMM classify kernel,
- * 6 SW whole-GPU long-alignment kernel(s). */
+ * 6 SW whole-GPU long-alignment kernel(s), 7 DP kernels of the last sw_ends_* / sw_align_* chunk, 8 its traceback walk. */
 int agx_set_profiling(int32_t on);
 double agx_profile_ms(int32_t device, int32_t which);
 
@@ -145,6 +145,36 @@ typedef struct {
 } agx_sw_shard;
 int sw_score_shards_device(const agx_sw_shard *shards, int32_t n_shards,
                            int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend);
+
+/* ------------------------------------------- Smith-Waterman alignment: end cell, start cell, CIGAR */
+
+/* What comes after the score (the reference leaves traceback out, README.md:2).
+ * Same recurrence, same raw-byte symbols (a trailing '\n' is a symbol and can be the last aligned column).
+ * scores_out[p] equals sw_score_batch_flat's.  ends_out[2p], ends_out[2p+1] = 0-based index in sequence 2p / 2p+1
+ * of the LAST aligned symbol: the cell the reference's running maximum comes from
+ * (antidiagonalSmithWaterman.c:335 `max = val > max ? val : max`: the first cell with the final value in its
+ * visiting order -- anti-diagonals :270-347, inside one with ix ascending, ix walking the shorter line, line 1
+ * when both are equally long :229-244).  Both -1 when the score is 0.
+ * Limits (AGX_ERANGE): whole-GPU pairs (>= 2^28 cells with a shorter side above 1024) are not supported here;
+ * shorter line <= 16000 symbols; match - (gap_open + gap_extend), -mismatch, -(gap_open + gap_extend) <= 127. */
+int sw_ends_batch_flat(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *off, const int32_t *len,
+                       int64_t n_pairs, int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend,
+                       int32_t *scores_out, int32_t *ends_out);
+
+/* Full local alignment.  coords_out[4p ..] = a_start, a_end, b_start, b_end (0-based, inclusive, a = sequence 2p,
+ * b = sequence 2p+1; all -1 when the score is 0); the runs of pair p are cigar_out[cigar_off_out[p] ..
+ * cigar_off_out[p+1]), start -> end, each length << 4 | op with op 0 = M (one symbol of each sequence, equal or
+ * not), 1 = I (symbols of a only), 2 = D (symbols of b only) -- BAM's encoding.  cigar_off_out has n_pairs + 1
+ * entries.  The path is the one this rule picks from the score matrix, walking back from the end cell: the
+ * diagonal when D[i][j] == D[i-1][j-1] + subst, else the shortest gap that explains D[i][j] (symbols of a before
+ * symbols of b at equal length), until a cell with D == 0; re-scoring the CIGAR gives exactly scores_out[p].
+ * *cigar_total_out = runs of the whole batch; when that exceeds cigar_cap the call returns AGX_ERANGE with
+ * scores, coordinates and offsets complete and no runs written beyond the capacity's last whole shard.
+ * The score matrices live on the GPU one byte per cell (the batch is cut into chunks that fit device memory). */
+int sw_align_batch_flat(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *off, const int32_t *len,
+                        int64_t n_pairs, int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend,
+                        int32_t *scores_out, int32_t *coords_out, int64_t *cigar_off_out, uint32_t *cigar_out,
+                        int64_t cigar_cap, int64_t *cigar_total_out);
 
 /* ------------------------------------------------------------------ PairHMM forward */
 
