@@ -418,10 +418,12 @@ int sw_align_shard(DeviceCtx &c, const uint8_t *seqs, const int64_t *off, const 
     int64_t cig_base = 0;
     int64_t q0 = p0;
     int shrink = 0;
+    c.align.dp_ms_sum = c.align.walk_ms_sum = -1.0;
     while (q0 < p1) {
         // chunk: at most 2^20 pairs and, in mode 2, matrices within the budget (the class layout rounds rows up to
         // the longest of the class, so the per-pair bound is scaled by what the chunk's longest line adds)
-        int64_t q1 = q0, bytes = 0;
+        int64_t q1 = q0;
+        double bytes = 0.0;
         int32_t longest = 1;
         while (q1 < p1 && q1 - q0 < ((int64_t)1 << 20) >> shrink) {
             if (mode == 2) {
@@ -430,9 +432,9 @@ int sw_align_shard(DeviceCtx &c, const uint8_t *seqs, const int64_t *off, const 
                 const int64_t b = sw_align_tb_bound(la, lb);
                 const int32_t new_longest = std::max(longest, lg);
                 // bound of the chunk if this pair joins: every pair may be padded to the longest line seen
-                const double grown = ((double)bytes * new_longest / longest + (double)b * new_longest / std::max(lg, 1)) * 1.02;
-                if (q1 > q0 && grown > (double)(budget >> shrink)) break;
-                bytes = (int64_t)grown;
+                const double grown = bytes * new_longest / longest + (double)b * new_longest / std::max(lg, 1);
+                if (q1 > q0 && grown * 1.02 > (double)(budget >> shrink)) break;
+                bytes = grown;
                 longest = new_longest;
             }
             ++q1;
@@ -483,6 +485,11 @@ int sw_align_shard(DeviceCtx &c, const uint8_t *seqs, const int64_t *off, const 
             cig_base += total;
         }
         AGX_CUDA(cudaStreamSynchronize(st));
+        if (g_profiling.load()) {
+            const double d = c.align.prof_dp.ms(), w = mode == 2 ? c.align.prof_walk.ms() : -1.0;
+            if (d >= 0) c.align.dp_ms_sum = std::max(c.align.dp_ms_sum, 0.0) + d;
+            if (w >= 0) c.align.walk_ms_sum = std::max(c.align.walk_ms_sum, 0.0) + w;
+        }
         q0 = q1;
     }
     return AGX_OK;
@@ -823,8 +830,8 @@ double agx_profile_ms(int32_t device, int32_t which)
     case AGX_PROF_HMM_STREAM: return c->hmm.prof_stream.ms();
     case AGX_PROF_HMM_FP64: return c->hmm.prof_fp64.ms();
     case AGX_PROF_HMM_CLASSIFY: return c->hmm.prof_classify.ms();
-    case AGX_PROF_SW_ALIGN_DP: return c->align.prof_dp.ms();
-    case AGX_PROF_SW_ALIGN_WALK: return c->align.prof_walk.ms();
+    case AGX_PROF_SW_ALIGN_DP: return c->align.dp_ms_sum;
+    case AGX_PROF_SW_ALIGN_WALK: return c->align.walk_ms_sum;
     case AGX_PROF_SW_LONG: { const double v = c->sw.lng.prof.ms(); return v >= 0 ? v : c->sw.prof_long.ms(); }
     default: return -1.0;
     }

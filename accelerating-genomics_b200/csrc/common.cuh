@@ -108,6 +108,7 @@ struct SwAlignWorkspace {
     int32_t *wave_scratch = nullptr;
     int64_t cap_wave = 0;
     ProfSpan prof_dp, prof_walk;
+    double dp_ms_sum = -1.0, walk_ms_sum = -1.0;   // over the chunks of the last host call (profiling on)
 };
 // mode 1: scores + end cells; mode 2: + start cells, run counts and (in ws.tmp_ops, reversed) the CIGAR runs.
 // d_ends [2n] (index in line 1, index in line 2); d_coords [4n] a_start a_end b_start b_end (mode 2).

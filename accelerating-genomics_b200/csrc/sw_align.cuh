@@ -118,8 +118,9 @@ struct WalkLayout {
     __device__ __forceinline__ uint32_t at(int32_t r, int32_t c) const
     {
         if (duo) {
+            // step-major: lane t of the sub-warp holds row r at step r + t; a step is 32 lanes x K2 words
             const int32_t t = c / K, jj = c - t * K;
-            return __ldg(tb + (((int64_t)t * rstride + r) * K2 + (jj >> 1)) * 4 + (jj & 1) + 2 * half);
+            return __ldg(tb + ((int64_t)(r + t) * 32 + t) * (K2 * 4) + (jj >> 1) * 4 + (jj & 1) + 2 * half);
         }
         return __ldg(tb + ((int64_t)(c >> 8) * rstride + r) * 256 + (c & 255));
     }
@@ -242,6 +243,19 @@ sw_cigar_gather_kernel(const uint32_t *__restrict__ tmp_ops, const int64_t *__re
     for (int32_t k = 0; k < n; ++k) dst[k] = src[n - 1 - k];
 }
 
+// bytes of one warp's step-major matrix in class c when the class's longest row sequence has `rows` symbols
+__host__ __device__ constexpr int64_t duo_tb_warp_bytes(int c, int32_t rows)
+{
+    return (int64_t)(rows + duo_class(c).g - 1) * 32 * ((duo_class(c).k + 1) / 2) * 4;
+}
+// ... of the whole class: the grid is whole CTAs of DUO_THREADS / 32 warps
+inline int64_t duo_tb_class_bytes(int c, int32_t count, int32_t rows)
+{
+    const int subs = DUO_THREADS / duo_class(c).g;
+    const int64_t duos = (count + 1) / 2, blocks = (duos + subs - 1) / subs;
+    return (blocks * (DUO_THREADS / 32) * duo_tb_warp_bytes(c, rows) + 255) / 256 * 256;
+}
+
 template <int C>
 int launch_duo_align(const uint8_t *d_seqs, const int64_t *d_off, const int32_t *d_len, const int32_t *order,
                      int64_t n_pairs, const int32_t *counts, const int32_t *rows, const int64_t *tb_base, int mode,
@@ -255,8 +269,7 @@ int launch_duo_align(const uint8_t *d_seqs, const int64_t *d_off, const int32_t 
         if (blocks > 0) {
             DuoAlignOut a = ao;
             a.cls = (int16_t)C;
-            a.rstride = rows[C];
-            a.tb_duo_bytes = (int64_t)G * rows[C] * ((K + 1) / 2) * 4;
+            a.tb_warp_bytes = duo_tb_warp_bytes(C, rows[C]);
             a.tb = ao.tb ? ao.tb + tb_base[C] : nullptr;
             a.tb_class_off = tb_base[C];
             int32_t *glist = const_cast<int32_t *>(order) + (int64_t)GENERIC * n_pairs;

@@ -187,6 +187,11 @@ __device__ __forceinline__ uint32_t base_code(uint32_t ch, bool &ok)
 #endif
 // MODE 0: score only.  MODE 1: + END CELL.  MODE 2: + the low byte of every H, for the traceback walk.
 // The alignment modes carry ~10 more live registers (keys, store pointer, packed bytes): one CTA fewer.
+__host__ __device__ constexpr int duo_tb_steps(int K)
+{
+    const int b = 40 / ((K + 1) / 2);          // 40 KB of staging per 4-warp CTA: 1024 * TB * K2 bytes
+    return b < 1 ? 1 : b > 8 ? 8 : b;
+}
 __host__ __device__ constexpr int duo_min_blocks_sw(int K, int MODE = 0)
 {
     return K <= 19 ? (MODE ? 4 : AGX_DUO_MINBLOCKS) : K <= 24 ? 3 : 2;
@@ -195,10 +200,10 @@ __host__ __device__ constexpr int duo_min_blocks_sw(int K, int MODE = 0)
 struct DuoAlignOut {
     int32_t *ends;        // [2 * n_pairs] end cell as (index in line 1, index in line 2), -1 -1 when the score is 0
     SwWalkRec *wk;        // [n_pairs]     MODE 2: where the traceback walk starts
-    uint8_t *tb;          // MODE 2: H-byte matrices of this class, one per duo
+    uint8_t *tb;          // MODE 2: H-byte matrices of this class, one per WARP, step-major:
+                          //         [step s][lane][K2 words], lane t of a sub-warp holding row s - t at step s
     int64_t tb_class_off; //         where this class starts in the scratch (the walk addresses from the scratch base)
-    int64_t tb_duo_bytes; //         G * rstride * K2 * 4
-    int32_t rstride;      //         rows of one strip (>= every lb of the class)
+    int64_t tb_warp_bytes; //        steps * 32 * K2 * 4, steps = (most rows of the class) + G - 1
     int32_t k32;          // 32, opaque to ptxas: key = H * 32 + tag as one IMAD on the FMA pipe
     int16_t cls;
 };
@@ -212,6 +217,10 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
     constexpr int CAP = G * K;
     constexpr int K2 = (K + 1) / 2;       // MODE 2: 32-bit words per thread row (2 columns x 2 pairs, one byte each)
     static_assert(K2 % 2 == 0, "thread rows are stored as 64-bit words");
+    // MODE 2 stages TB steps of the whole warp in shared memory (TB * 32 * K2 words, contiguous in the step-major
+    // global layout as well) and hands them to the copy engine as ONE bulk store; two buffers per warp
+    constexpr int TB = duo_tb_steps(K);
+    __shared__ __align__(128) uint2 tbuf[MODE == 2 ? DUO_THREADS / 32 : 1][2][MODE == 2 ? TB * 32 * (K2 / 2) : 1];
     constexpr int SUBS = DUO_THREADS / G;
     // row steps per loop trip: 8 measured +3 % over 2 at K = 19 (16 overflows the instruction cache: -17 %);
     // the wide classes keep 2
@@ -326,9 +335,28 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
     // (larger H first, then the earlier anti-diagonal, then the smaller ix).  best32 = max of those keys.
     uint32_t best32[2] = {0u, 0u};
     uint32_t kbase = ((uint32_t)(4033 - t * K + t) << 10) + (uint32_t)(992 - t * K);   // row -t: the first step of lane t
-    uint2 *tbp = nullptr;
-    if constexpr (MODE == 2)
-        tbp = reinterpret_cast<uint2 *>(ao.tb + (int64_t)duo * ao.tb_duo_bytes) + ((int64_t)t * ao.rstride - t) * (K2 / 2);
+    const int wib = threadIdx.x >> 5;
+    uint8_t *tb_warp = nullptr;               // this warp's matrix
+    int tb_u = 0, tb_cur = 0;                 // step inside the staged batch, buffer in use
+    int64_t tb_done = 0;                      // bytes handed to the copy engine so far
+    if constexpr (MODE == 2) tb_warp = ao.tb + ((int64_t)blockIdx.x * (DUO_THREADS / 32) + wib) * ao.tb_warp_bytes;
+    // hand the staged steps to the copy engine: the writes of every lane become visible to the async proxy, one
+    // lane issues the bulk store and makes sure the store that read the OTHER buffer (a batch ago) is done reading
+    auto tb_flush = [&]() {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)tb_u * 32u * K2 * 4u;
+            const uint32_t src = (uint32_t)__cvta_generic_to_shared(&tbuf[wib][tb_cur][0]);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(tb_warp + tb_done), "r"(src), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
+        __syncwarp();
+        tb_done += (int64_t)tb_u * 32 * K2 * 4;
+        tb_u = 0;
+        tb_cur ^= 1;
+    };
 
     for (int i = t; i < DUO_RING; i += G) ring[sub][i] = make_uint2(kc.xb4, kc.xb4);
 
@@ -408,16 +436,19 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
                 kbase -= 1024u;
             }
             if constexpr (MODE == 2) {
-                if ((unsigned)(s - t) < (unsigned)Lb) {
+                uint2 *dst = &tbuf[wib][tb_cur][(tb_u * 32 + lane) * (K2 / 2)];
 #pragma unroll
-                    for (int q = 0; q < K2 / 2; ++q) tbp[q] = make_uint2(pk[2 * q], pk[2 * q + 1]);
-                }
-                tbp += K2 / 2;
+                for (int q = 0; q < K2 / 2; ++q) dst[q] = make_uint2(pk[2 * q], pk[2 * q + 1]);
+                if (++tb_u == TB) tb_flush();
             }
         }
     }
 
     // ---- results ---------------------------------------------------------------------------------
+    if constexpr (MODE == 2) {
+        if (tb_u > 0) tb_flush();
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
 #pragma unroll
     for (int m = G / 2; m >= 1; m >>= 1) rmax = __vmaxs2(rmax, __shfl_xor_sync(0xffffffffu, rmax, m, G));
     if constexpr (MODE != 0) {
@@ -461,12 +492,14 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
                 ao.ends[2 * (int64_t)pid[h] + 1] = a_is_x[h] ? eb : ea;
                 if constexpr (MODE == 2) {
                     SwWalkRec w;
-                    w.tb_off = ao.tb_class_off + (int64_t)duo * ao.tb_duo_bytes;
+                    // the warp's matrix + this sub-warp's lanes inside a step
+                    w.tb_off = ao.tb_class_off + ((int64_t)blockIdx.x * (DUO_THREADS / 32) + wib) * ao.tb_warp_bytes +
+                               (int64_t)(lane & ~(G - 1)) * K2 * 4;
                     w.r_end = nl_end ? Lb - 1 : r_end;
                     w.c_end = nl_end ? CAP - 1 : c_end;
                     w.row_off = row_off;
                     w.col_off = col_off;
-                    w.rstride = ao.rstride;
+                    w.rstride = 0;
                     w.cls = ao.cls;
                     w.half = (uint8_t)h;
                     w.flags = (uint8_t)((a_is_x[h] ? SW_WK_A_IS_X : 0) | (nl_end ? SW_WK_NL_END : 0) | (best == 0 ? SW_WK_NONE : 0));
@@ -957,7 +990,7 @@ int64_t sw_align_tb_bound(int32_t len_a, int32_t len_b)
     const int32_t ra = len_a > len_b ? len_b : len_a, rb = len_a > len_b ? len_a : len_b;
     int64_t duo = 0;
     for (int c = SW_N_DUO_CLASSES - 1; c >= 0; --c)
-        if (ra <= duo_cap(c) + 1) duo = (int64_t)duo_class(c).g * ((duo_class(c).k + 1) / 2) * 2 * rb;
+        if (ra <= duo_cap(c) + 1) duo = (int64_t)duo_class(c).g * ((duo_class(c).k + 1) / 2) * 2 * (rb + duo_class(c).g);
     const int64_t wave = (int64_t)((ra + 255) / 256) * 256 * rb;
     return duo > wave ? duo : wave;
 }
@@ -1024,10 +1057,7 @@ int sw_align_run_device(SwAlignWorkspace &ws, const uint8_t *d_seqs, const int64
         n_duo += counts[c];
         rows[c] = ws.h_counters[CNT_A_ROWS + c];
         tb_base[c] = duo_total;
-        if (mode == 2) {
-            const int64_t duos = (counts[c] + 1) / 2;
-            duo_total += (duos * duo_class(c).g * rows[c] * ((duo_class(c).k + 1) / 2) * 4 + 255) / 256 * 256;
-        }
+        if (mode == 2) duo_total += duo_tb_class_bytes(c, counts[c], rows[c]);
     }
     const int32_t max_len = ws.h_counters[CNT_MAXLEN];
     if (mode == 2) {

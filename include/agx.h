@@ -73,7 +73,7 @@ void agx_reset_launch_count(void);
  * returns the duration (ms) of the LAST recorded span on `device`, or a negative number if that
  * span never ran.  which: 0 SW inter-task (duo) kernels, 1 SW wavefront kernel, 2 PairHMM FP32
  * stream kernels, 3 PairHMM FP64 kernel, 4 SW classify kernel, 5 PairHMM classify kernel,
- * 6 SW whole-GPU long-alignment kernel(s), 7 DP kernels of the last sw_ends_* / sw_align_* chunk, 8 its traceback walk. */
+ * 6 SW whole-GPU long-alignment kernel(s), 7 DP kernels of the last sw_ends_* / sw_align_* call (summed over its chunks), 8 its traceback walks. */
 int agx_set_profiling(int32_t on);
 double agx_profile_ms(int32_t device, int32_t which);
 

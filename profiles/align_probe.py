@@ -18,9 +18,12 @@ cap.init(1)
 cap.set_profiling(True)
 inp = agx.synth.sw_uniform_pairs(n, L, seed=3)
 cells = float(n) * L * L
+only = sys.argv[3] if len(sys.argv) > 3 else None
 for name, fn in (("score", lambda: cap.sw_score_flat(inp.buf, inp.off, inp.len)),
                  ("ends", lambda: cap.sw_ends_flat(inp.buf, inp.off, inp.len)),
                  ("align", lambda: cap.sw_align_flat(inp.buf, inp.off, inp.len, cigar_cap=16 * n))):
+    if only and name != only:
+        continue
     fn()
     best = 1e30
     for _ in range(3):
@@ -29,8 +32,8 @@ for name, fn in (("score", lambda: cap.sw_score_flat(inp.buf, inp.off, inp.len))
         best = min(best, time.perf_counter() - t0)
     rec = {"what": name, "pairs": n, "len": L, "ms": best * 1e3, "gcups_e2e": cells / best / 1e9}
     if name != "score":
-        rec["dp_ms_last_chunk"] = cap.profile_ms(0, 7)
-        rec["walk_ms_last_chunk"] = cap.profile_ms(0, 8)
+        rec["dp_ms"] = cap.profile_ms(0, 7)
+        rec["walk_ms"] = cap.profile_ms(0, 8)
     if name == "align":
         rec["cigar_runs"] = int(r[3].size)
     print(json.dumps(rec), flush=True)
