@@ -56,7 +56,7 @@ def build_lib(force: bool = False, verbose_ptxas: bool = False) -> Path:
 def build_drivers(force: bool = False) -> None:
     BIN.mkdir(parents=True, exist_ok=True)
     gcc = shutil.which("gcc") or "gcc"
-    for name in ("smithWaterman", "smithWatermanGpu", "pairHMM"):
+    for name in ("smithWaterman", "smithWatermanGpu", "smithWatermanAlign", "pairHMM"):
         src = ROOT / "drivers" / f"{name}.c"
         if not src.exists():
             continue

@@ -398,8 +398,9 @@ int sw_flat_impl(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *off, co
 struct AlignOut {
     int32_t *scores, *ends, *coords;
     int64_t *cigar_off;               // [n + 1], mode 2
-    std::vector<uint32_t> *cigar;     // mode 2: runs of this shard (only filled while keep_cigar)
-    bool keep_cigar;
+    std::vector<uint32_t> *cigar;     // mode 2, several GPUs: runs of this shard, concatenated by the caller
+    uint32_t *cigar_direct;           // mode 2, one GPU: the caller's array, runs land there as long as they fit
+    int64_t cigar_cap;
 };
 
 int sw_align_shard(DeviceCtx &c, const uint8_t *seqs, const int64_t *off, const int32_t *len, int64_t p0, int64_t p1,
@@ -419,27 +420,28 @@ int sw_align_shard(DeviceCtx &c, const uint8_t *seqs, const int64_t *off, const 
     int64_t q0 = p0;
     int shrink = 0;
     c.align.dp_ms_sum = c.align.walk_ms_sum = -1.0;
+    const bool trace = getenv("AGX_ALIGN_TRACE") != nullptr;      // host-side timeline of the chunks on stderr
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
     while (q0 < p1) {
         // chunk: at most 2^20 pairs and, in mode 2, matrices within the budget (the class layout rounds rows up to
         // the longest of the class, so the per-pair bound is scaled by what the chunk's longest line adds)
-        int64_t q1 = q0;
-        double bytes = 0.0;
+        int64_t q1 = q0, row_bytes = 0;
         int32_t longest = 1;
         while (q1 < p1 && q1 - q0 < ((int64_t)1 << 20) >> shrink) {
             if (mode == 2) {
                 const int32_t la = len[2 * q1], lb = len[2 * q1 + 1];
-                const int32_t lg = std::max(la, lb);
-                const int64_t b = sw_align_tb_bound(la, lb);
-                const int32_t new_longest = std::max(longest, lg);
-                // bound of the chunk if this pair joins: every pair may be padded to the longest line seen
-                const double grown = bytes * new_longest / longest + (double)b * new_longest / std::max(lg, 1);
-                if (q1 > q0 && grown * 1.02 > (double)(budget >> shrink)) break;
-                bytes = grown;
+                const int32_t new_longest = std::max(longest, std::max(la, lb));
+                const int64_t grown = row_bytes + sw_align_tb_row_bytes(la, lb);
+                // every pair of a class is padded to the class's longest row sequence (+ the systolic skew)
+                if (q1 > q0 && (double)grown * (new_longest + 32) * 1.02 > (double)(budget >> shrink)) break;
+                row_bytes = grown;
                 longest = new_longest;
             }
             ++q1;
         }
         const int64_t m = q1 - q0;
+        if (trace) fprintf(stderr, "[agx align] +%.2f ms: chunk of %lld pairs cut\n", now() - t_begin, (long long)m);
         int64_t l = INT64_MAX, h = 0;
         for (int64_t i = 2 * q0; i < 2 * q1; ++i) {
             l = std::min(l, off[i]);
@@ -459,12 +461,14 @@ int sw_align_shard(DeviceCtx &c, const uint8_t *seqs, const int64_t *off, const 
         AGX_CUDA(cudaMemcpyAsync(c.al_bytes.p, seqs + l, (size_t)(h - l), cudaMemcpyHostToDevice, st));
         AGX_CUDA(cudaMemcpyAsync(c.al_off.p, roff, (size_t)m * 2 * sizeof(int64_t), cudaMemcpyHostToDevice, st));
         AGX_CUDA(cudaMemcpyAsync(c.al_len.p, len + 2 * q0, (size_t)m * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        if (trace) { cudaStreamSynchronize(st); fprintf(stderr, "[agx align] +%.2f ms: uploaded\n", now() - t_begin); }
         int64_t total = 0;
         rc = sw_align_run_device(c.align, c.al_bytes.as<uint8_t>(), c.al_off.as<int64_t>(), c.al_len.as<int32_t>(), m, sc,
                                  mode, budget, c.al_scores.as<int32_t>(), c.al_ends.as<int32_t>(),
                                  c.al_coords.as<int32_t>(), &total, st);
         if (rc == AGX_ENOMEM && mode == 2 && m > 1 && shrink < 24) { ++shrink; continue; }   // the bound was too optimistic
         if (rc != AGX_OK) return rc;
+        if (trace) fprintf(stderr, "[agx align] +%.2f ms: kernels done (%lld runs)\n", now() - t_begin, (long long)total);
         AGX_CUDA(cudaMemcpyAsync(out.scores + q0, c.al_scores.p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         if (out.ends)
             AGX_CUDA(cudaMemcpyAsync(out.ends + 2 * q0, c.al_ends.p, (size_t)m * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -472,19 +476,24 @@ int sw_align_shard(DeviceCtx &c, const uint8_t *seqs, const int64_t *off, const 
             AGX_CUDA(cudaMemcpyAsync(out.coords + 4 * q0, c.al_coords.p, (size_t)m * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
             AGX_CUDA(cudaMemcpyAsync(out.cigar_off + (q0 - p0), c.align.cig_off, (size_t)(m + 1) * sizeof(int64_t),
                                      cudaMemcpyDeviceToHost, st));
-            if (out.keep_cigar && total > 0) {
+            const bool fits = !out.cigar_direct || cig_base + total <= out.cigar_cap;
+            if (total > 0 && fits) {
                 if ((rc = c.al_cigar.reserve((size_t)total * sizeof(uint32_t))) != AGX_OK) return rc;
                 if ((rc = sw_align_gather_device(c.align, m, c.al_cigar.as<uint32_t>(), st)) != AGX_OK) return rc;
-                const size_t at = out.cigar->size();
-                out.cigar->resize(at + (size_t)total);
-                AGX_CUDA(cudaMemcpyAsync(out.cigar->data() + at, c.al_cigar.p, (size_t)total * sizeof(uint32_t),
-                                         cudaMemcpyDeviceToHost, st));
+                uint32_t *dst = out.cigar_direct ? out.cigar_direct + cig_base : nullptr;
+                if (!dst) {
+                    const size_t at = out.cigar->size();
+                    out.cigar->resize(at + (size_t)total);
+                    dst = out.cigar->data() + at;
+                }
+                AGX_CUDA(cudaMemcpyAsync(dst, c.al_cigar.p, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             }
             AGX_CUDA(cudaStreamSynchronize(st));
             for (int64_t i = 0; i <= m; ++i) out.cigar_off[(q0 - p0) + i] += cig_base;
             cig_base += total;
         }
         AGX_CUDA(cudaStreamSynchronize(st));
+        if (trace) fprintf(stderr, "[agx align] +%.2f ms: results on the host\n", now() - t_begin);
         if (g_profiling.load()) {
             const double d = c.align.prof_dp.ms(), w = mode == 2 ? c.align.prof_walk.ms() : -1.0;
             if (d >= 0) c.align.dp_ms_sum = std::max(c.align.dp_ms_sum, 0.0) + d;
@@ -521,29 +530,28 @@ int sw_align_impl(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *off, c
     }
     std::vector<std::vector<uint32_t>> cig(n_dev);
     std::vector<std::vector<int64_t>> coff(n_dev);
-    std::vector<int32_t> ends_tmp;
-    if (mode == 2) {
-        ends_tmp.resize((size_t)n_pairs * 2);
+    if (mode == 2 && n_dev > 1) {
         for (int k = 0; k < n_dev; ++k) coff[k].assign((size_t)(cuts[k + 1] - cuts[k] + 1), 0);
     }
     rc = for_each_device(n_dev, [&](DeviceCtx &c, int k) {
         AlignOut o;
         o.scores = scores_out;
-        o.ends = mode == 2 ? ends_tmp.data() : ends_out;
+        o.ends = mode == 2 ? nullptr : ends_out;       // mode 2: the ends are part of coords
         o.coords = coords_out;
-        o.cigar_off = mode == 2 ? coff[k].data() : nullptr;
+        o.cigar_off = mode == 2 ? (n_dev == 1 ? cigar_off_out : coff[k].data()) : nullptr;
         o.cigar = &cig[k];
-        o.keep_cigar = true;
+        o.cigar_direct = n_dev == 1 ? cigar_out : nullptr;
+        o.cigar_cap = cigar_cap;
         return sw_align_shard(c, seqs, off, len, cuts[k], cuts[k + 1], sc, mode, o);
     });
     if (rc != AGX_OK) return rc;
     if (mode != 2) return AGX_OK;
-    int64_t base = 0;
-    for (int k = 0; k < n_dev; ++k) {
+    int64_t base = n_dev == 1 ? cigar_off_out[n_pairs] : 0;
+    for (int k = 0; n_dev > 1 && k < n_dev; ++k) {
         const int64_t m = cuts[k + 1] - cuts[k];
         for (int64_t i = 0; i < m; ++i) cigar_off_out[cuts[k] + i] = coff[k][i] + base;
         const int64_t tot = coff[k][m];
-        if (base + tot <= cigar_cap && tot > 0) memcpy(cigar_out + base, cig[k].data(), (size_t)tot * sizeof(uint32_t));
+        if (n_dev > 1 && base + tot <= cigar_cap && tot > 0) memcpy(cigar_out + base, cig[k].data(), (size_t)tot * sizeof(uint32_t));
         base += tot;
     }
     cigar_off_out[n_pairs] = base;

@@ -119,8 +119,8 @@ int sw_align_run_device(SwAlignWorkspace &ws, const uint8_t *d_seqs, const int64
 // after a mode-2 run: runs of pair p go to d_cigar[ws.cig_off[p] ...), start -> end
 int sw_align_gather_device(SwAlignWorkspace &ws, int64_t n_pairs, uint32_t *d_cigar, cudaStream_t st);
 void sw_align_workspace_free(SwAlignWorkspace &ws);
-// upper bound of the H-byte matrix one pair can take (host-side chunking)
-int64_t sw_align_tb_bound(int32_t len_a, int32_t len_b);
+// bytes per row of the H-byte matrix one pair can take (host-side chunking)
+int64_t sw_align_tb_row_bytes(int32_t len_a, int32_t len_b);
 
 // Per-call device scratch for the SW path (owned by the device context).
 struct SwWorkspace {

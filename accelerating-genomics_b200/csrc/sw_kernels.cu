@@ -182,6 +182,9 @@ __device__ __forceinline__ uint32_t base_code(uint32_t ch, bool &ok)
 // Resident 128-thread CTAs per SM the register budget is cut for.  The state is 3 K registers (sel, Gp, F), so
 // one budget for every class spills the wide ones (K = 32 at 5 CTAs / 96 registers: ~400 LDL/STL in the cell
 // loop): 5 CTAs up to K = 19, 3 (168 registers) for K = 24, 2 (255) for K = 32.
+#ifndef AGX_DUO_ALIGN_UNROLL
+#define AGX_DUO_ALIGN_UNROLL 4
+#endif
 #ifndef AGX_DUO_MINBLOCKS
 #define AGX_DUO_MINBLOCKS 5
 #endif
@@ -224,6 +227,8 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
     constexpr int SUBS = DUO_THREADS / G;
     // row steps per loop trip: 8 measured +3 % over 2 at K = 19 (16 overflows the instruction cache: -17 %);
     // the wide classes keep 2
+    // (MODE 2 adds ~35 % to a step: 8 of those no longer fit the instruction cache -- measured per 8 * 10^5 pairs
+    // of 150 x 150: 8 -> 5.29 ms, 4 -> 4.61 ms, 2 -> 4.69 ms, 1 -> 4.75 ms; it unrolls its staged batch of TB steps)
     constexpr int STEP_UNROLL = (K <= 19) ? 8 : 2;
     __shared__ uint2 ring[SUBS][DUO_RING];
 
@@ -337,24 +342,23 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
     uint32_t kbase = ((uint32_t)(4033 - t * K + t) << 10) + (uint32_t)(992 - t * K);   // row -t: the first step of lane t
     const int wib = threadIdx.x >> 5;
     uint8_t *tb_warp = nullptr;               // this warp's matrix
-    int tb_u = 0, tb_cur = 0;                 // step inside the staged batch, buffer in use
+    int tb_cur = 0;                           // staging buffer in use
     int64_t tb_done = 0;                      // bytes handed to the copy engine so far
     if constexpr (MODE == 2) tb_warp = ao.tb + ((int64_t)blockIdx.x * (DUO_THREADS / 32) + wib) * ao.tb_warp_bytes;
     // hand the staged steps to the copy engine: the writes of every lane become visible to the async proxy, one
     // lane issues the bulk store and makes sure the store that read the OTHER buffer (a batch ago) is done reading
-    auto tb_flush = [&]() {
+    auto tb_flush = [&](const int n_steps) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-            const uint32_t bytes = (uint32_t)tb_u * 32u * K2 * 4u;
+            const uint32_t bytes = (uint32_t)n_steps * 32u * K2 * 4u;
             const uint32_t src = (uint32_t)__cvta_generic_to_shared(&tbuf[wib][tb_cur][0]);
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(tb_warp + tb_done), "r"(src), "r"(bytes) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         }
         __syncwarp();
-        tb_done += (int64_t)tb_u * 32 * K2 * 4;
-        tb_u = 0;
+        tb_done += (int64_t)n_steps * 32 * K2 * 4;
         tb_cur ^= 1;
     };
 
@@ -384,9 +388,8 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
         __syncwarp();
 
         const int send = min(DUO_CH, S - s0);
-#pragma unroll STEP_UNROLL
-        for (int u = 0; u < send; ++u) {
-            const int s = s0 + u;
+        // one row step of every lane; slot = position of the step in the staged batch (MODE 2)
+        auto step = [&](const int s, const int slot) {
             const uint2 R = ring[sub][(s - t) & (DUO_RING - 1)];
             uint32_t g_in = __shfl_up_sync(0xffffffffu, g_out, 1, G);
             uint32_t e = __shfl_up_sync(0xffffffffu, e_out, 1, G);
@@ -394,7 +397,7 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
             uint32_t gdiag = g_in_prev;
             g_in_prev = g_in;
             uint32_t gleft = g_in;
-            uint32_t rk = 0u, kprev = 0u, hprev = 0u;
+            uint32_t rk = 0u, kprev = 0u;
             uint32_t pk[MODE == 2 ? K2 : 1];
 #pragma unroll
             for (int j = 0; j < K; ++j) {
@@ -417,10 +420,10 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
                     kprev = key;
                 }
                 if constexpr (MODE == 2) {
-                    // bytes [lo pair col j-1, lo pair col j, hi pair col j-1, hi pair col j]
-                    if (j & 1) pk[j >> 1] = prmt(hprev, hcell, 0x6240u);
-                    else if (j == K - 1) pk[j >> 1] = prmt(hcell, 0u, 0x6240u);
-                    hprev = hcell;
+                    // bytes [lo pair col j-1, lo pair col j, hi pair col j-1, hi pair col j] of H + goe: the walk uses
+                    // differences of neighbouring bytes only, so the constant does not matter
+                    if (j & 1) pk[j >> 1] = prmt(Gp[j - 1], gleft, 0x6240u);
+                    else if (j == K - 1) pk[j >> 1] = prmt(gleft, 0u, 0x6240u);
                 }
             }
             g_out = gleft;
@@ -436,17 +439,32 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
                 kbase -= 1024u;
             }
             if constexpr (MODE == 2) {
-                uint2 *dst = &tbuf[wib][tb_cur][(tb_u * 32 + lane) * (K2 / 2)];
+                uint2 *dst = &tbuf[wib][tb_cur][(slot * 32 + lane) * (K2 / 2)];
 #pragma unroll
                 for (int q = 0; q < K2 / 2; ++q) dst[q] = make_uint2(pk[2 * q], pk[2 * q + 1]);
-                if (++tb_u == TB) tb_flush();
             }
+        };
+        if constexpr (MODE == 2) {
+            // batches of TB steps, each handed to the copy engine as one bulk store
+            for (int u0 = 0; u0 < send; u0 += TB) {
+                const int ue = min(TB, send - u0);
+                if (ue == TB) {
+#pragma unroll
+                    for (int k = 0; k < TB; ++k) step(s0 + u0 + k, k);
+                } else {
+#pragma unroll 1
+                    for (int k = 0; k < ue; ++k) step(s0 + u0 + k, k);
+                }
+                tb_flush(ue);
+            }
+        } else {
+#pragma unroll STEP_UNROLL
+            for (int u = 0; u < send; ++u) step(s0 + u, 0);
         }
     }
 
     // ---- results ---------------------------------------------------------------------------------
     if constexpr (MODE == 2) {
-        if (tb_u > 0) tb_flush();
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 #pragma unroll
@@ -983,15 +1001,16 @@ void sw_align_workspace_free(SwAlignWorkspace &ws)
     ws = SwAlignWorkspace();
 }
 
-int64_t sw_align_tb_bound(int32_t len_a, int32_t len_b)
+int64_t sw_align_tb_row_bytes(int32_t len_a, int32_t len_b)
 {
-    // the larger of the two layouts a pair can end up in: its duo class (half a duo: CAP/2 words x 2 pairs = CAP
-    // bytes per row) and the wavefront layout (256-byte stripes)
-    const int32_t ra = len_a > len_b ? len_b : len_a, rb = len_a > len_b ? len_a : len_b;
+    // bytes per ROW of the larger of the two layouts a pair can end up in: its duo class (half a duo: K2 words x 2
+    // bytes of the pair per lane, G lanes) or the wavefront layout (256-byte stripes); a chunk of pairs then takes
+    // at most (sum of these) x (its longest line + 32) bytes
+    const int32_t ra = len_a > len_b ? len_b : len_a;
     int64_t duo = 0;
-    for (int c = SW_N_DUO_CLASSES - 1; c >= 0; --c)
-        if (ra <= duo_cap(c) + 1) duo = (int64_t)duo_class(c).g * ((duo_class(c).k + 1) / 2) * 2 * (rb + duo_class(c).g);
-    const int64_t wave = (int64_t)((ra + 255) / 256) * 256 * rb;
+    for (int c = 0; c < SW_N_DUO_CLASSES; ++c)
+        if (ra <= duo_cap(c) + 1) { duo = (int64_t)duo_class(c).g * ((duo_class(c).k + 1) / 2) * 2; break; }
+    const int64_t wave = (int64_t)((ra + 255) / 256) * 256;
     return duo > wave ? duo : wave;
 }
 

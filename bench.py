@@ -22,6 +22,9 @@ workload, the other BASELINE configurations are objects inside it:
                  never used for parity with the reference, reported separately.
   "sw_lengths"   the inter-task SW kernel at the published MI210 sweep lengths (64 ... 1024) and at generator.py's
                  own 450-500 bp, one length class each.
+  "sw_align"     (rank 0) alignment END CELLS and full alignments (start cell + CIGAR) of the headline batch:
+                 sw_ends_batch_flat / sw_align_batch_flat end to end from pinned host buffers, the device spans, the
+                 storing kernel against the alu pipe and against HBM; at N = 1 a sample against the oracle.
   "parity"       (N = 1) GPU results against the reference C programs' own output on the cpu_baseline shards.
 
   value        GCUPS with the batch already resident in HBM; CUDA events on the launching stream, max over ranks.
@@ -56,6 +59,10 @@ SW_LEN = 150
 # what the kernel issues on that pipe
 SW_OPS = {"algorithmic": 4.0, "executed": 2.25}        # s16x2: 4.5 alu-pipe (+ 2 fma-pipe) instructions per cell PAIR
 HMM_OPS = {"algorithmic": 8.0, "executed": 6.0}        # FP32 lane-instructions per cell (X' / Y' form)
+# alu-pipe instructions per cell of the alignment modes (SASS of the unrolled loop, per 32-bit word of two cells:
+# 2 VIADDMNMX + 1 VIMNMX3.RELU + 1/2 VIMNMX3 + 1 PRMT as in the score kernel, + per row the widening of the row key;
+# MODE 2 adds 1/2 PRMT per word for the byte packing)
+ALIGN_OPS = {"ends": 2.45, "align": 2.75}
 LONG_OPS = {"algorithmic": 8.0, "executed": 3.75}      # s32 coded cell: 2 VIADDMNMX + VIMNMX3.RELU + 1/2 VIMNMX3 + 1/4 PRMT
 NOMINAL_ALU = 148 * 64 * 1.965e9     # INT32/DPX lane-ops/s   
 NOMINAL_FP32 = 148 * 128 * 1.965e9   # FP32 lane-instr/s
@@ -868,7 +875,92 @@ def bench_sw_lengths(agx, args, device_index):
                     "of the class count as lost throughput", "lengths": rows}
 
 
-def cpu_leg(agx, args, gatk):
+def bench_sw_align(agx, args, device_index):
+    """The alignment path on top of the headline batch: end cells
+    (sw_ends_batch_flat) and full alignments (sw_align_batch_flat: start cells + CIGAR) of the same 150 x 150
+    pairs, end to end from pinned host buffers, with the device spans libagx times itself (DP kernels; traceback
+    walk) and the two resources the storing kernel leans on."""
+    import torch
+    cap = agx.capi
+    n = min(args.sw_pairs, args.align_pairs)
+    inp = agx.synth.sw_uniform_pairs(n, SW_LEN, seed=1234)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    buf, off, ln = pin(inp.buf), pin(inp.off), pin(inp.len)
+    cells = float(n) * SW_LEN * SW_LEN
+    out = {"unit": "GCUPS", "workload": "%d pairs of %dx%d (sw_uniform_pairs seed 1234)" % (n, SW_LEN, SW_LEN),
+           "end_cell": "the cell the reference's running maximum comes from (antidiagonalSmithWaterman.c:335; its visiting "
+                       "order); start cell + CIGAR: oracle/sw_align.c's rule"}
+    scores = torch.empty(n, dtype=torch.int32).pin_memory().numpy()
+    ends = torch.empty((n, 2), dtype=torch.int32).pin_memory().numpy()
+    coords = torch.empty((n, 4), dtype=torch.int32).pin_memory().numpy()
+    coff = torch.empty(n + 1, dtype=torch.int64).pin_memory().numpy()
+    cig = torch.empty(16 * n, dtype=torch.uint32 if hasattr(torch, "uint32") else torch.int32).pin_memory().numpy().view(np.uint32)
+    lib = cap.load_library()
+    import ctypes as C
+    total = C.c_int64(0)
+    sc = [cap.SW_MATCH, cap.SW_MISMATCH, cap.SW_GAP_OPEN, cap.SW_GAP_EXTEND]
+    P = lambda a: a.ctypes.data
+
+    def run_ends():
+        rc = lib.sw_ends_batch_flat(P(buf), buf.size, P(off), P(ln), n, *sc, P(scores), P(ends))
+        assert rc == 0, lib.agx_last_error().decode()
+
+    def run_align():
+        rc = lib.sw_align_batch_flat(P(buf), buf.size, P(off), P(ln), n, *sc, P(scores), P(coords), P(coff), P(cig), cig.size,
+                                     C.byref(total))
+        assert rc == 0, lib.agx_last_error().decode()
+
+    peak_alu, src = pipe_peak("alu")
+    hbm = (measured_peaks() or {}).get("hbm_gbs")
+    for name, fn in (("ends", run_ends), ("align", run_align)):
+        for _ in range(max(2, args.warmup - 1)):
+            fn()
+        cap.reset_launch_count()
+        t, dp, wk = [], [], []
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            fn()
+            t.append(time.perf_counter() - t0)
+            dp.append(cap.profile_ms(device_index, 7))
+            wk.append(cap.profile_ms(device_index, 8))
+        ms, dp_ms = 1e3 * float(np.mean(t)), float(np.mean(dp))
+        rec = {"e2e": {"value": cells / (ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": ms,
+                       "h2d_bytes_per_step": int(buf.nbytes + off.nbytes + ln.nbytes),
+                       "entry_point": "sw_ends_batch_flat" if name == "ends" else "sw_align_batch_flat"},
+               "dp_kernel_ms": dp_ms, "gpu_launches": cap.launch_count() // args.steps}
+        ops = ALIGN_OPS[name]
+        rec["roofline"] = {"bound": "alu", "pipe": "INT32/DPX alu pipe", "kernel": "sw_duo_kernel<8,19,%d>" % (1 if name == "ends" else 2),
+                           "achieved": cells * ops / (dp_ms * 1e-3) / 1e12, "peak": peak_alu / 1e12,
+                           "unit": "Tlaneop/s (INT32/DPX alu pipe)", "frac": cells * ops / (dp_ms * 1e-3) / peak_alu,
+                           "ops_per_cell_executed": ops, "peak_source": src, "kernel_ms": dp_ms,
+                           "kernel_gcups": cells / (dp_ms * 1e-3) / 1e9}
+        if name == "ends":
+            rec["value"] = cells / (dp_ms * 1e-3) / 1e9
+            rec["e2e"]["d2h_bytes_per_step"] = int(scores.nbytes + ends.nbytes)
+        else:
+            walk_ms = float(np.mean(wk))
+            runs = int(total.value)
+            # the storing kernel writes one byte per computed cell: 164 steps x 32 lanes x 40 bytes per warp of 8 pairs
+            tb_bytes = float(-(-n // 8)) * (SW_LEN + 1 + 7) * 32 * 40
+            rec.update({"walk_kernel_ms": walk_ms, "value": cells / ((dp_ms + walk_ms) * 1e-3) / 1e9,
+                        "value_note": "cells / (DP kernels + traceback walk), device spans summed over the call's chunks",
+                        "cigar_runs": runs, "matrix_bytes": tb_bytes})
+            rec["e2e"]["d2h_bytes_per_step"] = int(scores.nbytes + coords.nbytes + coff.nbytes + 4 * runs)
+            rec["roofline"]["hbm"] = {"bound": "hbm", "achieved": tb_bytes / (dp_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                      "frac": (tb_bytes / (dp_ms * 1e-3) / 1e9 / hbm) if hbm else None,
+                                      "traffic": tb_bytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy, read + write)",
+                                      "note": "bulk stores of the H-byte matrices (cp.async.bulk shared -> global); the kernel is "
+                                              "shared between this and the alu pipe"}
+        out[name] = rec
+    # consistency inside the run: alignment scores = end-cell scores = score-only scores; ends agree
+    s0 = cap.sw_score_flat(buf, off, ln)
+    out["scores_equal_score_only"] = bool(np.array_equal(s0, scores))
+    out["ends_equal"] = bool(np.array_equal(coords[:, 1], ends[:, 0]) and np.array_equal(coords[:, 3], ends[:, 1]))
+    out["_check"] = (inp, scores.copy(), coords.copy(), coff.copy(), cig[:int(total.value)].copy())
+    return out
+
+
+def cpu_leg(agx, args, gatk, align=None):
     """cpu_baseline (rank 0, N = 1): the reference C programs on the host cores, the GPU against their output on
     the same shards, and the GATK mode against the oracle's GATK branch.  The one place bench.py's GPU arm runs
     anything under oracle/."""
@@ -893,6 +985,27 @@ def cpu_leg(agx, args, gatk):
     par.update(ref.parity_sw(cap))
     par.update(ref.parity_hmm(cap))
     out["parity"] = par
+    if align is not None:
+        # alignments of a sample against the oracle (end cell, start cell, CIGAR) and EVERY CIGAR of a larger sample
+        # re-scored to its Smith-Waterman score
+        import oracle
+        inp, scores, coords, coff, cig = align["_check"]
+        data = inp.buf.tobytes()
+        rng = np.random.default_rng(9)
+        n = scores.size
+        exact = rescored = bad = 0
+        for k, p in enumerate(rng.choice(n, size=min(n, 6000), replace=False).tolist()):
+            a = data[inp.off[2 * p]:inp.off[2 * p] + inp.len[2 * p]]
+            b = data[inp.off[2 * p + 1]:inp.off[2 * p + 1] + inp.len[2 * p + 1]]
+            runs = cig[coff[p]:coff[p + 1]].tolist()
+            if k < 1500:
+                ws, wc, wg = oracle.sw_align(a, b)
+                bad += int((ws, list(wc), wg) != (int(scores[p]), coords[p].tolist(), runs))
+                exact += 1
+            elif scores[p] > 0:
+                bad += int(oracle.sw_cigar_score(a, b, coords[p].tolist(), runs) != int(scores[p]))
+                rescored += 1
+        align["parity"] = {"pairs_vs_oracle": exact, "cigars_rescored": rescored, "mismatches": bad}
     if gatk is not None:
         import oracle
         inp, results = gatk["_input"], gatk["_results"]
@@ -989,8 +1102,11 @@ def run_gpu_arm(args):
         gatk = bench_gatk(agx, args, local_rank) if not args.no_gatk else None
         if world == 1 and args.sw_len:
             extras["sw_lengths"] = bench_sw_lengths(agx, args, local_rank)
+        align = bench_sw_align(agx, args, local_rank) if not args.no_align else None
         if world == 1 and not args.no_cpu_baseline:
-            extras.update(cpu_leg(agx, args, gatk))
+            extras.update(cpu_leg(agx, args, gatk, align))
+        if align is not None:
+            extras["sw_align"] = {k: v for k, v in align.items() if not k.startswith("_")}
         if gatk is not None:
             extras["pairhmm_gatk"] = {k: v for k, v in gatk.items() if not k.startswith("_")}
     if world > 1:
@@ -1034,7 +1150,7 @@ def run_gpu_arm(args):
             if "cpu_hmm" in extras:
                 sub["cpu_baseline"] = extras["cpu_hmm"]
             line["pairhmm"] = sub
-        for key in ("sw_long", "strong", "pairhmm_gatk", "sw_lengths", "parity"):
+        for key in ("sw_long", "strong", "pairhmm_gatk", "sw_lengths", "sw_align", "parity"):
             if key in extras:
                 line[key] = extras[key]
         emit(line)
@@ -1097,6 +1213,8 @@ def main():
     ap.add_argument("--no-sw-long", action="store_true")
     ap.add_argument("--no-strong", action="store_true")
     ap.add_argument("--no-gatk", action="store_true")
+    ap.add_argument("--no-align", action="store_true")
+    ap.add_argument("--align-pairs", type=int, default=1_000_000, help="pairs of the \"sw_align\" object (at most --sw-pairs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "agx":
         args.warmup = max(args.warmup, 3)

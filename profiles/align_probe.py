@@ -17,6 +17,12 @@ L = int(sys.argv[2]) if len(sys.argv) > 2 else 150
 cap.init(1)
 cap.set_profiling(True)
 inp = agx.synth.sw_uniform_pairs(n, L, seed=3)
+try:                                     # pinned host buffers, as bench.py's end-to-end legs use
+    import torch
+    for f in ("buf", "off", "len"):
+        setattr(inp, f, torch.from_numpy(np.ascontiguousarray(getattr(inp, f))).pin_memory().numpy())
+except Exception as e:                   # pageable buffers still work, only slower
+    print(json.dumps({"note": f"not pinned: {e}"}), flush=True)
 cells = float(n) * L * L
 only = sys.argv[3] if len(sys.argv) > 3 else None
 for name, fn in (("score", lambda: cap.sw_score_flat(inp.buf, inp.off, inp.len)),

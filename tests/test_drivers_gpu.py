@@ -100,3 +100,30 @@ def test_sw_gpu_cli_of_the_reference(tmp_path, agx, oracle_mod):
     r = subprocess.run([str(BIN / "smithWatermanGpu"), str(inp)], capture_output=True, text=True,
                        env=dict(os.environ, AGX_NUM_GPUS="1"))
     assert r.returncode == 1 and "<input_file_path> <output_file_path> <block_size>" in r.stderr
+
+
+@pytest.mark.parametrize("name", ["sw_ends_ragged", "sw_ends_repeats", "sw_dangling", "sw_linebuf", "sw_ends_no_trailing_nl"])
+def test_sw_align_driver(agx, oracle_mod, name):
+    """drivers/smithWatermanAlign.c: the reference's line structure with the alignment on every score line; scores
+    equal the recorded reference scores, coordinates and CIGAR the oracle's."""
+    r = subprocess.run([str(BIN / "smithWatermanAlign"), str(GOLDEN / f"{name}.in")], capture_output=True, text=True,
+                       env=dict(os.environ, AGX_NUM_GPUS="1"))
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    assert lines[0].startswith("line_num: ") and lines[-1].startswith("elapsed ")
+    inp = agx.formats.parse_sw((GOLDEN / f"{name}.in").read_bytes())
+    rows = [l for l in lines if l.startswith("Score: ")]
+    assert len(rows) == inp.n_pairs
+    data = inp.buf.tobytes()
+    for p, row in enumerate(rows):
+        a = data[inp.off[2 * p]:inp.off[2 * p] + inp.len[2 * p]]
+        b = data[inp.off[2 * p + 1]:inp.off[2 * p + 1] + inp.len[2 * p + 1]]
+        s, c, cig = oracle_mod.sw_align(a, b)
+        want = f"Score: {s} a[{c[0]},{c[1]}] b[{c[2]},{c[3]}] {oracle_mod.cigar_string(cig)}" if s > 0 else "Score: 0 - - -"
+        assert row == want
+    if inp.dangling:
+        assert inp.dangling.decode().rstrip("\n") in lines
+    ref = GOLDEN / f"{name}.ref.out"
+    if ref.exists():
+        from conftest import ref_scores
+        assert [int(l.split()[1]) for l in rows] == ref_scores(f"{name}.ref.out")
