@@ -56,6 +56,14 @@ int fail(int code, const std::string &msg)
 
 namespace {
 
+// Device address p with p + x == base + (x - bias): callers keep ABSOLUTE offsets (of a host buffer / file image)
+// while only the byte range [bias, bias + size) is resident.  Formed with integer arithmetic -- pointer arithmetic
+// may not leave the allocation -- and every access through it lands inside the buffer.
+inline const uint8_t *biased(const void *base, int64_t bias)
+{
+    return reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(base) - (uintptr_t)bias);
+}
+
 // grow-only device buffer
 struct DevBuf {
     void *p = nullptr;
@@ -295,7 +303,7 @@ int sw_shard(DeviceCtx &c, const uint8_t *seqs, int64_t seqs_bytes, const int64_
         const int64_t q0 = p0 + k * chunk, q1 = std::min(p1, q0 + chunk), m = q1 - q0;
         if ((rc = L.h_out.reserve((size_t)m * sizeof(int32_t))) != AGX_OK) return rc;
         // blocks until chunk k is on the device and classified, then queues its DP kernels
-        rc = sw_run_device(L.ws, L.bytes.as<uint8_t>() - lo[k], L.off.as<int64_t>(), L.len.as<int32_t>(), m, sc,
+        rc = sw_run_device(L.ws, biased(L.bytes.p, lo[k]), L.off.as<int64_t>(), L.len.as<int32_t>(), m, sc,
                            L.out.as<int32_t>(), L.st);
         if (rc != AGX_OK) return rc;
         AGX_CUDA(cudaMemcpyAsync(L.h_out.p, L.out.p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, L.st));
@@ -411,9 +419,10 @@ int sw_align_shard(DeviceCtx &c, const uint8_t *seqs, const int64_t *off, const 
     if (mode == 2) {
         size_t fr = 0, tot = 0;
         AGX_CUDA(cudaMemGetInfo(&fr, &tot));
-        // what is free now + what the scratch already holds, half of it, at most 32 GiB
+        // what is free now + what the scratch already holds, half of it, at most 80 GiB
         const int64_t avail = (int64_t)fr + c.align.cap_tb + c.align.cap_tb_gen;
-        budget = std::min<int64_t>(avail / 2, (int64_t)32 << 30);
+        // (a bound, not an allocation: the scratch grows to what the chunks really take)
+        budget = std::min<int64_t>(avail / 2, (int64_t)80 << 30);
         if (const char *e = getenv("AGX_ALIGN_TB_BYTES")) budget = std::max<long long>(atoll(e), 1 << 20);
     }
     int64_t cig_base = 0;
@@ -900,11 +909,13 @@ static int sw_file_image_multi(const uint8_t *image, int64_t image_bytes, int64_
     int rc = for_each_device(n_dev, [&](DeviceCtx &c, int d) -> int {
         SwLane &L = c.lane[0];
         int r;
-        if ((r = L.bytes.reserve((size_t)image_bytes + 64)) != AGX_OK) return r;
         if (cut[d + 1] <= cut[d]) return AGX_OK;
-        const int64_t up0 = std::max<int64_t>(hlen, cut[d] - (line_buf - 1));       // + the chunk before the range
-        AGX_CUDA(cudaMemcpyAsync(L.bytes.as<uint8_t>() + up0, image + up0, (size_t)(cut[d + 1] - up0), cudaMemcpyHostToDevice, L.st));
-        return sw_parse_device(c.parse[0], L.bytes.as<uint8_t>(), cut[d], cut[d + 1], line_buf, max_chunks,
+        // this GPU holds its own byte range only (+ the chunk before it); offsets stay those of the whole image
+        // (from a multiple of 16: the newline scan reads the image in aligned 128-bit words)
+        const int64_t up0 = std::max<int64_t>(hlen, cut[d] - (line_buf - 1)) & ~(int64_t)15;
+        if ((r = L.bytes.reserve((size_t)(cut[d + 1] - up0) + 64)) != AGX_OK) return r;
+        AGX_CUDA(cudaMemcpyAsync(L.bytes.p, image + up0, (size_t)(cut[d + 1] - up0), cudaMemcpyHostToDevice, L.st));
+        return sw_parse_device(c.parse[0], biased(L.bytes.p, up0), cut[d], cut[d + 1], line_buf, max_chunks,
                                image[cut[d + 1] - 1], &part[d].d_off, &part[d].d_len, &part[d].n_chunks, &part[d].last_off,
                                &part[d].last_len, L.st);
     });
@@ -933,7 +944,8 @@ static int sw_file_image_multi(const uint8_t *image, int64_t image_bytes, int64_
         int r;
         if ((r = L.out.reserve((size_t)m * sizeof(int32_t))) != AGX_OK) return r;
         if ((r = L.h_out.reserve((size_t)m * sizeof(int32_t))) != AGX_OK) return r;
-        r = sw_run_device(L.ws, L.bytes.as<uint8_t>(), part[d].d_off - shift, part[d].d_len - shift, m, sc, L.out.as<int32_t>(), L.st);
+        const int64_t up0 = std::max<int64_t>(hlen, cut[d] - (line_buf - 1)) & ~(int64_t)15;
+        r = sw_run_device(L.ws, biased(L.bytes.p, up0), part[d].d_off - shift, part[d].d_len - shift, m, sc, L.out.as<int32_t>(), L.st);
         if (r != AGX_OK) return r;
         AGX_CUDA(cudaMemcpyAsync(L.h_out.p, L.out.p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, L.st));
         AGX_CUDA(cudaStreamSynchronize(L.st));

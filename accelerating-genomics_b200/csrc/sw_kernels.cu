@@ -1005,13 +1005,21 @@ int64_t sw_align_tb_row_bytes(int32_t len_a, int32_t len_b)
 {
     // bytes per ROW of the larger of the two layouts a pair can end up in: its duo class (half a duo: K2 words x 2
     // bytes of the pair per lane, G lanes) or the wavefront layout (256-byte stripes); a chunk of pairs then takes
-    // at most (sum of these) x (its longest line + 32) bytes
+    // at most (sum of these) x (its longest line + 32) bytes.  Tabulated for the lengths the duo classes cover.
+    static const std::vector<int32_t> table = [] {
+        std::vector<int32_t> t(DUO_MAX_CAP + 2, 0);
+        for (int ra = 0; ra <= DUO_MAX_CAP + 1; ++ra) {
+            int32_t duo = 0;
+            for (int c = 0; c < SW_N_DUO_CLASSES; ++c)
+                if (ra <= duo_cap(c) + 1) { duo = duo_class(c).g * ((duo_class(c).k + 1) / 2) * 2; break; }
+            const int32_t wave = ((ra + 255) / 256) * 256;
+            t[ra] = duo > wave ? duo : wave;
+        }
+        return t;
+    }();
     const int32_t ra = len_a > len_b ? len_b : len_a;
-    int64_t duo = 0;
-    for (int c = 0; c < SW_N_DUO_CLASSES; ++c)
-        if (ra <= duo_cap(c) + 1) { duo = (int64_t)duo_class(c).g * ((duo_class(c).k + 1) / 2) * 2; break; }
-    const int64_t wave = (int64_t)((ra + 255) / 256) * 256;
-    return duo > wave ? duo : wave;
+    if (ra <= DUO_MAX_CAP + 1) return table[ra];
+    return (int64_t)((ra + 255) / 256) * 256;
 }
 
 int sw_align_run_device(SwAlignWorkspace &ws, const uint8_t *d_seqs, const int64_t *d_off, const int32_t *d_len,
