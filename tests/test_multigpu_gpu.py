@@ -171,3 +171,29 @@ def test_sharded_device_entry_points(agx, multi):
     assert np.array_equal(np.concatenate([o.cpu().numpy() for _, o in keep]), want)
     with pytest.raises(agx.capi.AgxError):
         cap.sw_score_shards_device([shards[0], shards[0]])          # one shard per device
+
+
+def test_alignments_are_sharded_over_all_gpus(agx, multi, oracle_mod):
+    """sw_ends_batch_flat / sw_align_batch_flat with several GPUs bound: ranges of pairs per GPU, CIGAR runs and
+    offsets concatenated in pair order; equal to the one-GPU result and (a sample) to the oracle."""
+    cap, n = multi
+    rng = np.random.default_rng(5)
+    data = agx.synth.sw_random_file(rng, 5000, 1, 300, alphabet=b"ACGT", related_frac=0.7)
+    inp = agx.formats.parse_sw(data)
+    got = cap.sw_align_flat(inp.buf, inp.off, inp.len)
+    got_e = cap.sw_ends_flat(inp.buf, inp.off, inp.len)
+    cap.shutdown()
+    cap.init(1)
+    one = cap.sw_align_flat(inp.buf, inp.off, inp.len)
+    one_e = cap.sw_ends_flat(inp.buf, inp.off, inp.len)
+    cap.shutdown()
+    cap.init(0)
+    for g, w in zip(got + got_e, one + one_e):
+        assert np.array_equal(g, w)
+    scores, coords, coff, cig = got
+    raw = inp.buf.tobytes()
+    for p in rng.choice(inp.n_pairs, size=300, replace=False).tolist():
+        a = raw[inp.off[2 * p]:inp.off[2 * p] + inp.len[2 * p]]
+        b = raw[inp.off[2 * p + 1]:inp.off[2 * p + 1] + inp.len[2 * p + 1]]
+        ws, wc, wg = oracle_mod.sw_align(a, b)
+        assert (ws, list(wc), wg) == (int(scores[p]), coords[p].tolist(), cig[coff[p]:coff[p + 1]].tolist())
