@@ -529,6 +529,53 @@ int sw_align_impl(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *off, c
             return fail(AGX_EINVAL, "sw align: sequence " + std::to_string(i) + " lies outside the buffer");
     int rc = require_init();
     if (rc != AGX_OK) return rc;
+    if (mode == 1) {
+        // whole-GPU pairs: score and end cell from the striped long-alignment kernel, one pair at a time over every
+        // configured GPU (the traceback of such a pair would need its 10^12-cell matrix: mode 2 refuses them)
+        std::vector<int64_t> giants;
+        for (int64_t p = 0; p < n_pairs; ++p)
+            if ((int64_t)len[2 * p] * (int64_t)len[2 * p + 1] >= sw_long_cells() && std::min(len[2 * p], len[2 * p + 1]) > 1025)
+                giants.push_back(p);
+        if (!giants.empty()) {
+            if (!(sc.match > 0 && sc.mismatch < 0 && sc.gap_open <= 0 && sc.gap_extend < 0))
+                return fail(AGX_ERANGE, "sw: scoring must satisfy match > 0 > mismatch, gap_open <= 0, gap_extend < 0");
+            std::vector<int> devs;
+            std::vector<cudaStream_t> sts;
+            std::vector<SwLongWorkspace *> wss;
+            for (auto &c : g_ctx) { devs.push_back(c->device); sts.push_back(c->stream); wss.push_back(&c->sw.lng); }
+            for (int64_t p : giants) {
+                const int hi = len[2 * p] >= len[2 * p + 1] ? 0 : 1;          // columns = the longer sequence
+                const int sx = len[2 * p] > len[2 * p + 1] ? 1 : 0;           // antidiagonalSmithWaterman.c:229
+                int32_t ec = -1, er = -1;
+                rc = sw_long_host_multi((int)devs.size(), devs.data(), sts.data(), wss.data(), seqs + off[2 * p + hi],
+                                        len[2 * p + hi], seqs + off[2 * p + 1 - hi], len[2 * p + 1 - hi], sc, scores_out + p,
+                                        &ec, &er, sx == hi);
+                if (rc != AGX_OK) return rc;
+                ends_out[2 * p + hi] = ec;
+                ends_out[2 * p + 1 - hi] = er;
+            }
+            if ((int64_t)giants.size() == n_pairs) return AGX_OK;
+            std::vector<int64_t> off2, idx;
+            std::vector<int32_t> len2;
+            size_t gi = 0;
+            for (int64_t p = 0; p < n_pairs; ++p) {
+                if (gi < giants.size() && giants[gi] == p) { ++gi; continue; }
+                idx.push_back(p);
+                off2.push_back(off[2 * p]); off2.push_back(off[2 * p + 1]);
+                len2.push_back(len[2 * p]); len2.push_back(len[2 * p + 1]);
+            }
+            std::vector<int32_t> sc2(idx.size()), en2(2 * idx.size());
+            rc = sw_align_impl(seqs, seqs_bytes, off2.data(), len2.data(), (int64_t)idx.size(), sc, 1, sc2.data(), en2.data(),
+                               nullptr, nullptr, nullptr, 0, nullptr);
+            if (rc != AGX_OK) return rc;
+            for (size_t k = 0; k < idx.size(); ++k) {
+                scores_out[idx[k]] = sc2[k];
+                ends_out[2 * idx[k]] = en2[2 * k];
+                ends_out[2 * idx[k] + 1] = en2[2 * k + 1];
+            }
+            return AGX_OK;
+        }
+    }
     const int n_dev = (int)std::min<int64_t>((int64_t)g_ctx.size(), n_pairs);
     std::vector<int64_t> cuts{0, n_pairs};
     if (n_dev > 1) {

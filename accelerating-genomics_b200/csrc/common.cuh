@@ -64,8 +64,11 @@ struct SwLongWorkspace {
 };
 int sw_long_device(SwLongWorkspace &ws, const uint8_t *d_a, int64_t la, const uint8_t *d_b, int64_t lb,
                    SwScoring sc, int32_t *d_best, cudaStream_t st);
+// end_col_out / end_row_out (both or neither): 0-based END CELL, the cell the reference's running maximum comes from
+// (-1 -1 when the score is 0); col_is_sx: the reference's ix walks `a` (else `b`)
 int sw_long_host_multi(int n_dev, const int *dev, cudaStream_t *st, SwLongWorkspace **ws, const uint8_t *a,
-                       int64_t la, const uint8_t *b, int64_t lb, SwScoring sc, int32_t *score_out);
+                       int64_t la, const uint8_t *b, int64_t lb, SwScoring sc, int32_t *score_out,
+                       int32_t *end_col_out = nullptr, int32_t *end_row_out = nullptr, int col_is_sx = 0);
 void sw_long_workspace_free(SwLongWorkspace &ws);
 
 // ---- Smith-Waterman alignment: end cell, start cell, CIGAR (sw_align.cuh) -------------------------------------

@@ -39,8 +39,14 @@ namespace {
 struct DuoClass { int g, k; };
 __host__ __device__ constexpr DuoClass duo_class(int c)
 {
+#if defined(AGX_DUO_TABLE) && AGX_DUO_TABLE == 1
+    // wider sub-warps, fewer columns per lane for 192 .. 512 columns (experiment: occupancy against row skew)
+    constexpr DuoClass t[SW_N_DUO_CLASSES] = {{8, 4},  {8, 8},  {8, 12},  {8, 16},  {8, 19}, {16, 12},
+                                              {16, 16}, {32, 12}, {32, 16}, {32, 24}, {32, 32}};
+#else
     constexpr DuoClass t[SW_N_DUO_CLASSES] = {{8, 4},  {8, 8},  {8, 12},  {8, 16},  {8, 19}, {8, 24},
                                               {8, 32}, {16, 24}, {16, 32}, {32, 24}, {32, 32}};
+#endif
     return t[c];
 }
 __host__ __device__ constexpr int duo_cap(int c) { return duo_class(c).g * duo_class(c).k; }

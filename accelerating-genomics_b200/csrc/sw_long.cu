@@ -47,7 +47,16 @@ struct LongArgs {
     int32_t one;              // the constant 1, opaque to ptxas: x + y as IMAD (FMA pipe) instead of IADD3 (ALU pipe)
     const int2 *rowtab;       // sw_longr_kernel: 8-byte score table of every row (long_rowtab_kernel), padded
     int32_t bsteps;           // sw_longr_kernel: row steps per hand-off block (<= LR_BMAX)
+    // END CELL (sw_longr_kernel<..., ENDS>): the cell the reference's running maximum comes from, as a 64-bit key
+    //     H << 43 | (2^22 - 1 - (row + column)) << 21 | (2^21 - 1 - ix)
+    // ix = the index along the reference's sx (the shorter line, line 1 on ties): the column when col_is_sx,
+    // else the row.  atomicMax over all warps (and, on the host, over the GPUs).
+    unsigned long long *best_key;
+    int32_t col_base;         // global column of this GPU's column 0
+    int32_t col_is_sx;
+    int32_t k32;              // 32, opaque to ptxas (key = (H + goe) * 32 + tag as one IMAD)
 };
+constexpr uint32_t LONG_DMAX = (1u << 22) - 1u, LONG_XMAX = (1u << 21) - 1u;
 
 // prmt.b32 in its default mode: selector nibble bit 3 replicates the sign of the selected byte
 __device__ __forceinline__ int32_t prmt_s(uint32_t a, uint32_t b, uint32_t sel)
@@ -271,7 +280,7 @@ template <int R> __device__ __forceinline__ void lds_vec(const int32_t *p, int32
     }
 }
 
-template <int K, int R, bool SHORT, bool DP4A>
+template <int K, int R, bool SHORT, bool DP4A, bool ENDS>
 __global__ void __launch_bounds__(LONG_WARPS * 32)
 sw_longr_kernel(LongArgs g)
 {
@@ -296,6 +305,7 @@ sw_longr_kernel(LongArgs g)
     int32_t bestg[(R + 1) / 2];
 #pragma unroll
     for (int i = 0; i < (R + 1) / 2; ++i) bestg[i] = goe;
+    unsigned long long best64 = 0ull;                  // ENDS
     const int32_t one = g.one;
     const int32_t xb4 = (int32_t)((uint32_t)(uint8_t)(int8_t)(g.sc.mismatch - goe) * 0x01010101u);
     const int S = (lb + R - 1) / R + 31;               // lane 31 finishes the last row block at step (lb-1)/R + 31
@@ -438,6 +448,7 @@ sw_longr_kernel(LongArgs g)
                 }
                 g_in_prev = g_in[R - 1];
                 uint32_t sc4[R];
+                int32_t rk[ENDS ? R : 1];                          // ENDS: row maximum of (H + goe) * 32 + (31 - j)
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
                     if constexpr (DP4A) {
@@ -466,12 +477,35 @@ sw_longr_kernel(LongArgs g)
                         gdiag[i] = up;
                         up = gnew;
                         gleft[i] = gnew;
-                        // running maximum: one accumulator per pair of rows (independent chains)
-                        if constexpr (R == 1) { if (j & 1) bestg[0] = __vimax3_s32(bestg[0], Gp[j - 1], gnew); else if (j == K - 1) bestg[0] = max(bestg[0], gnew); }
-                        else if (i & 1) bestg[i >> 1] = __vimax3_s32(bestg[i >> 1], gleft[i - 1], gnew);
-                        else if (i == R - 1) bestg[i >> 1] = max(bestg[i >> 1], gnew);
+                        if constexpr (ENDS) {
+                            // the row maximum of these keys names the row's best H and its first column
+                            int32_t key;
+                            asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(key) : "r"(gnew), "r"(g.k32), "r"(31 - j));
+                            rk[i] = j == 0 ? key : max(rk[i], key);
+                        } else {
+                            // running maximum: one accumulator per pair of rows (independent chains)
+                            if constexpr (R == 1) { if (j & 1) bestg[0] = __vimax3_s32(bestg[0], Gp[j - 1], gnew); else if (j == K - 1) bestg[0] = max(bestg[0], gnew); }
+                            else if (i & 1) bestg[i >> 1] = __vimax3_s32(bestg[i >> 1], gleft[i - 1], gnew);
+                            else if (i == R - 1) bestg[i >> 1] = max(bestg[i >> 1], gnew);
+                        }
                     }
                     Gp[j] = up; F[j] = f;
+                }
+                if constexpr (ENDS) {
+                    // widen each row's key to the order the reference visits cells in: larger H, then the earlier
+                    // anti-diagonal, then the smaller ix.  Rows before the first / behind the last real row and padding
+                    // columns hold values that only decay from real cells: never the maximum.
+#pragma unroll
+                    for (int i = 0; i < R; ++i) {
+                        const int32_t h = (rk[i] >> 5) - goe;
+                        const uint32_t col = (uint32_t)(g.col_base + c0 + 31 - (rk[i] & 31));
+                        const uint32_t row = (uint32_t)(R * (s - lane) + i);
+                        const uint32_t x = g.col_is_sx ? col : row;
+                        const unsigned long long k64 = ((unsigned long long)(uint32_t)max(h, 0) << 43) |
+                                                       ((unsigned long long)((LONG_DMAX - (row + col)) & LONG_DMAX) << 21) |
+                                                       (unsigned long long)((LONG_XMAX - x) & LONG_XMAX);
+                        best64 = max(best64, k64);
+                    }
                 }
 #pragma unroll
                 for (int i = 0; i < R; ++i) { g_out[i] = gleft[i]; e_out[i] = e[i]; }
@@ -499,6 +533,15 @@ sw_longr_kernel(LongArgs g)
             __syncwarp();
         }
         __syncwarp();
+    }
+    if constexpr (ENDS) {
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) best64 = max(best64, __shfl_xor_sync(0xffffffffu, best64, m));
+        if (lane == 0 && (best64 >> 43) > 0) {
+            atomicMax(g.best_key, best64);
+            atomicMax(g.best, (int32_t)(best64 >> 43));
+        }
+        return;
     }
     int32_t best_all = bestg[0];
 #pragma unroll
@@ -785,19 +828,19 @@ long_rowtab_kernel(const uint8_t *__restrict__ b, int32_t lb, int64_t n_padded, 
 constexpr int64_t LR_ROW_PAD = 512;        // > 95 R for R <= 4
 __host__ __device__ constexpr int64_t lr_rows_padded(int64_t lb) { return lb + LR_ROW_PAD; }
 
-template <int K, int R, bool SHORT, bool DP4A> int long_launch_r(const LongArgs &args, int n_stripes, cudaStream_t st)
+template <int K, int R, bool SHORT, bool DP4A, bool ENDS = false> int long_launch_r(const LongArgs &args, int n_stripes, cudaStream_t st)
 {
     int dev = 0, sms = 0, per_sm = 0;
     AGX_CUDA(cudaGetDevice(&dev));
     AGX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    AGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_longr_kernel<K, R, SHORT, DP4A>, LONG_WARPS * 32, 0));
+    AGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_longr_kernel<K, R, SHORT, DP4A, ENDS>, LONG_WARPS * 32, 0));
     if (per_sm < 1) return fail(AGX_ECUDA, "sw_long: kernel does not fit on an SM");
     int blocks = sms * per_sm;                        // all co-resident: required by the stripe wavefront
     const int want = (n_stripes + LONG_WARPS - 1) / LONG_WARPS;
     if (blocks > want) blocks = want;
     LongArgs a = args;
     void *params[] = {&a};
-    AGX_CUDA(cudaLaunchCooperativeKernel((const void *)sw_longr_kernel<K, R, SHORT, DP4A>, dim3(blocks), dim3(LONG_WARPS * 32),
+    AGX_CUDA(cudaLaunchCooperativeKernel((const void *)sw_longr_kernel<K, R, SHORT, DP4A, ENDS>, dim3(blocks), dim3(LONG_WARPS * 32),
                                          params, 0, st));
     count_launch();
     return AGX_OK;
@@ -910,6 +953,12 @@ template <int I = 0> int long_dispatch_r(int k, int rows, bool short_chain, bool
 {
     if constexpr (I < N_LONGR_KS) {
         if (LONGR_KS[I] == k) {
+#ifndef AGX_LONG_SWEEP
+            if (args.best_key != nullptr) {      // END CELL wanted: the lean chain with the dp4a substitution
+                if (rows == 2) return long_launch_r<LONGR_KS[I], 2, false, true, true>(args, n, st);
+                return long_launch_r<LONGR_KS[I], 4, false, true, true>(args, n, st);
+            }
+#endif
 #define AGX_X(RR, SS, DD) if (rows == RR && short_chain == SS && dp4a == DD) return long_launch_r<LONGR_KS[I], RR, SS, DD>(args, n, st);
             AGX_LONGR_VARIANTS(AGX_X)
 #undef AGX_X
@@ -944,7 +993,10 @@ int long_dispatch(int k, const LongArgs &args, cudaStream_t st)
     // one warp per scheduler: latency-bound, take the short E chain; more: issue-bound, take the lean one
     bool short_chain = n <= sms * 4;
     if (const char *e = getenv("AGX_LONG_CHAIN")) short_chain = atoi(e) != 0;
-    if (!args.lut) return long_dispatch_raw<0>(k, short_chain, args, n, st);
+    if (!args.lut) {
+        if (args.best_key) return fail(AGX_ERANGE, "sw_long: end cells need sequences with at most 7 distinct bytes");
+        return long_dispatch_raw<0>(k, short_chain, args, n, st);
+    }
     // Measured on the per-GPU share of an 8-GPU run (125 kbp x 1 Mbp, one warp per scheduler) and on 1 Mbp x 1 Mbp
     // on one GPU (two warps per scheduler), profiles/r2a_long_sweep_*.jsonl: the lean chain with the dp4a
     // substitution wins everywhere; four rows per step when a scheduler holds a single warp (68 vs 92 ms), two
@@ -1033,7 +1085,7 @@ int sw_long_device(SwLongWorkspace &ws, const uint8_t *d_a, int64_t la, const ui
     const bool coded = build_lut(present, sc, lut);
     if (coded) AGX_CUDA(cudaMemcpyAsync(d_lut, lut, sizeof lut, cudaMemcpyHostToDevice, st));
     const int k = pick_k(la, lb, sms, coded);
-    LongArgs args;
+    LongArgs args = {};
     args.lut = coded ? d_lut : nullptr;
     args.one = 1;
     args.a = d_a; args.la = (int32_t)la; args.b = d_b; args.lb = (int32_t)lb;
@@ -1065,9 +1117,14 @@ void sw_long_workspace_free(SwLongWorkspace &ws)
 // Host form over n_dev GPUs (device ordinals dev[], streams st[], workspaces ws[]): columns of `a`
 // are split into n_dev contiguous ranges; `b` is replicated.  Returns the score in *score_out.
 int sw_long_host_multi(int n_dev, const int *dev, cudaStream_t *st, SwLongWorkspace **ws, const uint8_t *a,
-                       int64_t la, const uint8_t *b, int64_t lb, SwScoring sc, int32_t *score_out)
+                       int64_t la, const uint8_t *b, int64_t lb, SwScoring sc, int32_t *score_out, int32_t *end_col_out,
+                       int32_t *end_row_out, int col_is_sx)
 {
+    const bool want_ends = end_col_out != nullptr;
+    if (want_ends) { *end_col_out = -1; *end_row_out = -1; }
     if (la <= 0 || lb <= 0) { *score_out = 0; return AGX_OK; }
+    if (want_ends && (la > (int64_t)LONG_XMAX || lb > (int64_t)LONG_XMAX || (int64_t)std::min(la, lb) * sc.match > (int64_t)LONG_XMAX))
+        return fail(AGX_ERANGE, "sw_long: end cells are kept for sequences up to 2^21 - 1 symbols");
     if (la > INT32_MAX - 1024 || lb > INT32_MAX / 2 - 1024) return fail(AGX_ERANGE, "sw_long: sequence too long");
     if (n_dev > 1 && la < (int64_t)n_dev * 8192) n_dev = 1;       // not worth splitting
     // peer access between neighbours
@@ -1133,6 +1190,10 @@ int sw_long_host_multi(int n_dev, const int *dev, cudaStream_t *st, SwLongWorksp
         x.a = w.seq; x.la = (int32_t)cols; x.b = w.seq + cols; x.lb = (int32_t)lb;
         x.bnd = reinterpret_cast<int4 *>(w.buf);
         x.best = w.buf + 4 * lb;
+        x.best_key = want_ends ? reinterpret_cast<unsigned long long *>(w.buf + 4 * lb + 2) : nullptr;
+        x.col_base = (int32_t)c_lo[gidx];
+        x.col_is_sx = col_is_sx;
+        x.k32 = 32;
         x.next_bnd = nullptr;
         x.bsteps = long_block_steps();
         int2 *d_rowtab = reinterpret_cast<int2 *>(w.buf + 4 * lb + 4);
@@ -1145,7 +1206,7 @@ int sw_long_host_multi(int n_dev, const int *dev, cudaStream_t *st, SwLongWorksp
         stripe_base += (int32_t)n_stripes;
         x.sc = sc;
         AGX_CUDA(cudaMemsetAsync(x.bnd, 0xff, (size_t)lb * sizeof(int4), st[gidx]));   // tag -1: written by nobody
-        AGX_CUDA(cudaMemsetAsync(x.best, 0, sizeof(int32_t), st[gidx]));
+        AGX_CUDA(cudaMemsetAsync(x.best, 0, 4 * sizeof(int32_t), st[gidx]));      // the score and the end-cell key
     }
     for (int gidx = 0; gidx + 1 < n_dev; ++gidx) args[gidx].next_bnd = args[gidx + 1].bnd;
     for (int gidx = 0; gidx < n_dev; ++gidx) {
@@ -1160,14 +1221,24 @@ int sw_long_host_multi(int n_dev, const int *dev, cudaStream_t *st, SwLongWorksp
         if (rc != AGX_OK) return rc;
     }
     int32_t best = 0;
+    unsigned long long key = 0ull;
     for (int gidx = 0; gidx < n_dev; ++gidx) {
         AGX_CUDA(cudaSetDevice(dev[gidx]));
-        int32_t v = 0;
-        AGX_CUDA(cudaMemcpyAsync(&v, args[gidx].best, sizeof v, cudaMemcpyDeviceToHost, st[gidx]));
+        int32_t v[4] = {0, 0, 0, 0};
+        AGX_CUDA(cudaMemcpyAsync(v, args[gidx].best, sizeof v, cudaMemcpyDeviceToHost, st[gidx]));
         AGX_CUDA(cudaStreamSynchronize(st[gidx]));
-        best = std::max(best, v);
+        best = std::max(best, v[0]);
+        key = std::max(key, (unsigned long long)(uint32_t)v[2] | ((unsigned long long)(uint32_t)v[3] << 32));
     }
     *score_out = best;
+    if (want_ends && best > 0) {
+        // key = H << 43 | (2^22 - 1 - (row + column)) << 21 | (2^21 - 1 - ix)
+        const int64_t d = (int64_t)LONG_DMAX - (int64_t)((key >> 21) & LONG_DMAX);
+        const int64_t x = (int64_t)LONG_XMAX - (int64_t)(key & LONG_XMAX);
+        if ((int64_t)(key >> 43) != best) return fail(AGX_ECUDA, "sw_long: end-cell key and score disagree (internal error)");
+        *end_col_out = (int32_t)(col_is_sx ? x : d - x);
+        *end_row_out = (int32_t)(col_is_sx ? d - x : x);
+    }
     return AGX_OK;
 }
 

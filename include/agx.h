@@ -155,8 +155,10 @@ int sw_score_shards_device(const agx_sw_shard *shards, int32_t n_shards,
  * (antidiagonalSmithWaterman.c:335 `max = val > max ? val : max`: the first cell with the final value in its
  * visiting order -- anti-diagonals :270-347, inside one with ix ascending, ix walking the shorter line, line 1
  * when both are equally long :229-244).  Both -1 when the score is 0.
- * Limits (AGX_ERANGE): whole-GPU pairs (>= 2^28 cells with a shorter side above 1024) are not supported here;
- * shorter line <= 16000 symbols; match - (gap_open + gap_extend), -mismatch, -(gap_open + gap_extend) <= 127. */
+ * A whole-GPU pair (>= 2^28 cells with a shorter side above 1024, see sw_score_batch) gets its end cell from the
+ * striped long-alignment kernel over every configured GPU, like its score; that needs both lines <= 2^21 - 1 symbols
+ * made of at most 7 distinct bytes (else AGX_ERANGE).  Other limits (AGX_ERANGE): match - (gap_open + gap_extend),
+ * -mismatch, -(gap_open + gap_extend) <= 127. */
 int sw_ends_batch_flat(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *off, const int32_t *len,
                        int64_t n_pairs, int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend,
                        int32_t *scores_out, int32_t *ends_out);
@@ -170,7 +172,8 @@ int sw_ends_batch_flat(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *o
  * symbols of b at equal length), until a cell with D == 0; re-scoring the CIGAR gives exactly scores_out[p].
  * *cigar_total_out = runs of the whole batch; when that exceeds cigar_cap the call returns AGX_ERANGE with
  * scores, coordinates and offsets complete and no runs written beyond the capacity's last whole shard.
- * The score matrices live on the GPU one byte per cell (the batch is cut into chunks that fit device memory). */
+ * The score matrices live on the GPU one byte per cell (the batch is cut into chunks that fit device memory);
+ * whole-GPU pairs (>= 2^28 cells, see sw_score_batch) are refused here (AGX_ERANGE): use sw_ends_batch_flat. */
 int sw_align_batch_flat(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *off, const int32_t *len,
                         int64_t n_pairs, int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend,
                         int32_t *scores_out, int32_t *coords_out, int64_t *cigar_off_out, uint32_t *cigar_out,

@@ -38,6 +38,8 @@ def lib() -> C.CDLL:
         l.oracle_sw_align.restype = C.c_int32
         l.oracle_sw_align.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32] + [C.c_int32] * 4 + \
             [C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.c_int32, C.POINTER(C.c_int32)]
+        l.oracle_sw_ends.restype = C.c_int32
+        l.oracle_sw_ends.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32] + [C.c_int32] * 4 + [C.POINTER(C.c_int32)]
         l.oracle_sw_cigar_score.restype = C.c_int32
         l.oracle_sw_cigar_score.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32] + [C.c_int32] * 4 + \
             [C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.c_int32]
@@ -84,6 +86,13 @@ def sw_align(a: bytes, b: bytes, scoring=(1, -1, -3, -1)):
     s = lib().oracle_sw_align(a, len(a), b, len(b), *scoring, coords, cig, cap, C.byref(n))
     assert s != -(1 << 31)
     return int(s), tuple(int(x) for x in coords), [int(cig[k]) for k in range(n.value)]
+
+
+def sw_ends(a: bytes, b: bytes, scoring=(1, -1, -3, -1)):
+    """oracle_sw_ends: (score, (a_end, b_end)) with two rolling rows"""
+    e = (C.c_int32 * 2)()
+    s = lib().oracle_sw_ends(a, len(a), b, len(b), *scoring, e)
+    return int(s), (int(e[0]), int(e[1]))
 
 
 def sw_cigar_score(a: bytes, b: bytes, coords, cigar, scoring=(1, -1, -3, -1)) -> int:

@@ -50,6 +50,11 @@ int32_t oracle_sw_align(const uint8_t *a, int32_t la, const uint8_t *b, int32_t 
                         int32_t mismatch, int32_t gap_open, int32_t gap_extend, int32_t coords[4],
                         uint32_t *cigar, int32_t cigar_cap, int32_t *n_ops_out);
 
+/* The END CELL alone (ends = {a_end, b_end}, 0-based, -1 -1 when the score is 0) with two rolling rows: what checks
+ * long pairs, whose full matrix oracle_sw_align could not hold.  Returns the score. */
+int32_t oracle_sw_ends(const uint8_t *a, int32_t la, const uint8_t *b, int32_t lb, int32_t match, int32_t mismatch,
+                       int32_t gap_open, int32_t gap_extend, int32_t ends[2]);
+
 /* Independent re-scoring of a CIGAR (walks the path, adds up substitutions and gaps): INT32_MIN when the path
  * does not run exactly from the start to the end coordinates. */
 int32_t oracle_sw_cigar_score(const uint8_t *a, int32_t la, const uint8_t *b, int32_t lb, int32_t match,

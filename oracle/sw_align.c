@@ -118,6 +118,41 @@ int32_t oracle_sw_align(const uint8_t *a, int32_t la, const uint8_t *b, int32_t 
     return best;
 }
 
+int32_t oracle_sw_ends(const uint8_t *a, int32_t la, const uint8_t *b, int32_t lb, int32_t match, int32_t mismatch,
+                       int32_t gap_open, int32_t gap_extend, int32_t ends[2])
+{
+    /* the END CELL alone with two rolling rows (long pairs): same recurrence, same visiting-order rule as
+     * oracle_sw_align -- a later cell replaces the kept one only with a larger value, or with the same value on an
+     * earlier anti-diagonal / the same anti-diagonal and a smaller ix */
+    ends[0] = ends[1] = -1;
+    if (la <= 0 || lb <= 0) return 0;
+    const size_t w = (size_t)la + 1;
+    int32_t *h = calloc(w, sizeof(int32_t)), *vgap = malloc(w * sizeof(int32_t));
+    if (!h || !vgap) { free(h); free(vgap); return INT32_MIN; }
+    const int32_t NEG = -(1 << 29), first_gap = gap_open + gap_extend;
+    const int a_is_sx = !(la > lb);
+    for (int32_t j = 0; j <= la; j++) vgap[j] = NEG;
+    int32_t best = 0;
+    int64_t best_key = 0;
+    for (int32_t i = 1; i <= lb; i++) {
+        int32_t hgap = NEG, diag = h[0], left = 0;
+        for (int32_t j = 1; j <= la; j++) {
+            const int32_t up = h[j];
+            const int32_t p = max2(up + first_gap, vgap[j] + gap_extend);
+            const int32_t q = max2(left + first_gap, hgap + gap_extend);
+            const int32_t s = diag + (b[i - 1] == a[j - 1] ? match : mismatch);
+            const int32_t v = max2(max2(p, q), max2(s, 0));
+            if (v >= best && v > 0) {
+                const int64_t key = ((int64_t)(i + j) << 32) | (uint32_t)(a_is_sx ? j : i);
+                if (v > best || key < best_key) { best = v; best_key = key; ends[0] = j - 1; ends[1] = i - 1; }
+            }
+            vgap[j] = p; hgap = q; diag = up; h[j] = v; left = v;
+        }
+    }
+    free(h); free(vgap);
+    return best;
+}
+
 int32_t oracle_sw_cigar_score(const uint8_t *a, int32_t la, const uint8_t *b, int32_t lb, int32_t match,
                               int32_t mismatch, int32_t gap_open, int32_t gap_extend, const int32_t coords[4],
                               const uint32_t *cigar, int32_t n_ops)

@@ -64,7 +64,11 @@ def sweep(cols, rows, ks, rs, bs, dp=(0, 1), chains=(0, 1)):
         print(json.dumps({"cols": cols, "rows": rows, "K": k, "R": r, "short": ch, "dp4a": d, "B": bb, "ms": round(ms, 2),
                           "gcups": round(cols * rows / ms / 1e6), "ok": sc == ref_score}), flush=True)
 
-if mode == "tune":
+if mode == "smallk":
+    # two warps per scheduler instead of one: narrower stripes on the per-GPU share of an 8-GPU run
+    sweep(125_000, 1_000_000, [7, 2, 4, 6], [2, 4], [8, 16, 32], dp=(1,), chains=(0,))
+    sweep(125_000, 125_000, [7, 2, 4, 6], [2, 4], [8, 16], dp=(1,), chains=(0,))
+elif mode == "tune":
     # 125 kbp x 125 kbp on one GPU has the stripe-fill : row ratio of 1 Mbp x 1 Mbp on eight (x 8 = the 8-GPU time)
     sweep(125_000, 125_000, [7], [2, 4], [2, 4, 8, 16, 32], dp=(1,), chains=(0, 1))
     sweep(125_000, 1_000_000, [7], [2, 4], [4, 8, 32], dp=(1,), chains=(0,))

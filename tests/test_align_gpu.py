@@ -206,3 +206,37 @@ def test_config3_batch_properties(agx, gpu_lib, oracle_mod):
         if p in pick:
             ws, wc, wg = oracle_mod.sw_align(a, b)
             assert (ws, list(wc), wg) == (int(scores[p]), coords[p].tolist(), runs), p
+
+
+@pytest.mark.parametrize("n,related,alphabet", [(17000, True, b"ACGT"), (17500, False, b"ACGT"), (18000, True, b"AC")])
+def test_whole_gpu_pairs_report_their_end_cell(agx, gpu_lib, oracle_mod, n, related, alphabet):
+    """sw_ends_batch_flat on pairs of >= 2^28 cells: the striped long-alignment kernel keeps the end cell too
+    (64-bit keys in the reference's visiting order); mixed with ordinary pairs in one call."""
+    rng = np.random.default_rng(n)
+    alpha = np.frombuffer(alphabet, np.uint8)
+    x = alpha[rng.integers(0, alpha.size, size=n)]
+    if related:
+        y = x.copy()
+        m = rng.random(n) < 0.03
+        y[m] = alpha[rng.integers(0, alpha.size, size=int(m.sum()))]
+        y = y[rng.random(n) > 0.004]
+    else:
+        y = alpha[rng.integers(0, alpha.size, size=n - 321)]
+    big_a, big_b = x.tobytes() + b"\n", y.tobytes() + b"\n"
+    a, b = _pairs(rng, 40, 10, 200)
+    a.insert(7, big_a)
+    b.insert(7, big_b)
+    a.append(big_b)                 # the same pair the other way round: line 1 shorter / longer decides ix
+    b.append(big_a)
+    buf, off, ln = _flat(a, b)
+    scores, ends = gpu_lib.sw_ends_flat(buf, off, ln)
+    assert scores.tolist() == gpu_lib.sw_score_flat(buf, off, ln).tolist()
+    for p in (7, len(a) - 1):
+        ws, we = oracle_mod.sw_ends(a[p], b[p])
+        assert (int(scores[p]), tuple(ends[p].tolist())) == (ws, we)
+    for p in (0, 20, 40):
+        ws, wc, _ = oracle_mod.sw_align(a[p], b[p])
+        assert (int(scores[p]), tuple(ends[p].tolist())) == (ws, (wc[1], wc[3]))
+    with pytest.raises(agx.capi.AgxError) as e:
+        gpu_lib.sw_align_flat(buf, off, ln)             # the traceback of such a pair is refused
+    assert e.value.code == -5

@@ -72,6 +72,7 @@ def test_traceback_properties(oracle_mod):
         a, b = a.tobytes(), b.tobytes()
         s, c, cig = oracle_mod.sw_align(a, b, sc)
         assert s == oracle_mod.sw_score(a, b, sc)
+        assert oracle_mod.sw_ends(a, b, sc) == (s, (c[1], c[3]))         # the rolling-row form used for long pairs
         if s == 0:
             assert c == (-1, -1, -1, -1) and cig == []
             continue
