@@ -873,7 +873,9 @@ int env_int(const char *name, int dflt)
 // row steps per hand-off block of sw_longr_kernel (the stripe-fill term of the run is stripes x (32 + B) steps)
 int long_block_steps()
 {
-    const int b = env_int("AGX_LONG_B", 32);
+    // measured at 1 Mbp x 1 Mbp (profiles/r2v_sw_long_b.jsonl): 8 GPUs 148 / 134 / 133 ms for 32 / 16 / 8 steps (the
+    // wavefront crosses 4464 stripes, each hop costs 31 + B steps), one GPU 350 / 344 / 355 ms
+    const int b = env_int("AGX_LONG_B", 16);
     return b < 1 ? 1 : b > LR_BMAX ? LR_BMAX : b;
 }
 

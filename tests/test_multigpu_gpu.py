@@ -96,7 +96,7 @@ def test_sw_file_image_is_cut_into_one_range_per_gpu(agx, multi, seed, header_fr
     cap, n = multi
     rng = np.random.default_rng(seed)
     alpha = np.frombuffer(b"ACGT", np.uint8)
-    n_lines = 60001                                              # odd: the last line dangles when all are asked for
+    n_lines = 14000 * n + 1                                      # >= 4 MiB per GPU; odd: the last line dangles when all are asked for
     lens = rng.integers(1, 700, size=n_lines)
     lens[rng.integers(0, n_lines, size=40)] = rng.integers(1000, 2600, size=40)   # split by the 1000-byte buffer
     lines = [alpha[rng.integers(0, 4, size=int(l))].tobytes() for l in lens]
