@@ -586,7 +586,14 @@ def bench_hmm(agx, args, rank, local_rank, world, device):
              "traffic": (peaks["hmm_dram_bytes_per_step_config4"] * (args.hmm_batches / 1000.0)
                          if peaks.get("hmm_dram_bytes_per_step_config4") else None),
              "traffic_note": "DRAM bytes of the stream-kernel launches of one step from the committed ncu launch list, "
-                             "scaled by batches; FP32-bound, HBM time ~0.04 ms"}),
+                             "scaled by batches; FP32-bound, HBM time ~0.04 ms",
+             # the pipe's measured rate depends on how many distinct registers an instruction reads: the cell is four
+             # three-source FFMA2 and two two-source FMUL2
+             "operand_limited_peak": (6.0 / (4.0 / peaks["fp32_three_source_tlaneops"] + 2.0 / peaks["fp32_tlaneops"])
+                                      if peaks.get("fp32_three_source_tlaneops") else None),
+             "operand_limited_peak_note": "measured 21.8 T lane-instr/s for FP32 instructions with three distinct register "
+                                          "sources vs 35.09 with two (profiles/r1e_peaks_fp2.jsonl): the instruction mix of "
+                                          "the cell cannot exceed this; frac is still quoted against the 35.09 peak"}),
         "fp64_rescue": {"unrelated_read_fraction": args.hmm_unrelated, "pairs_rescued": int(rescued),
                         "fraction_of_pairs": (rescued / n_pairs if rescued >= 0 else None),
                         "fp64_kernel_ms": (float(np.mean(f_ms)) if f_ms else 0.0),
