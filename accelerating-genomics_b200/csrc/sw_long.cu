@@ -47,6 +47,7 @@ struct LongArgs {
     int32_t one;              // the constant 1, opaque to ptxas: x + y as IMAD (FMA pipe) instead of IADD3 (ALU pipe)
     const int2 *rowtab;       // sw_longr_kernel: 8-byte score table of every row (long_rowtab_kernel), padded
     int32_t bsteps;           // sw_longr_kernel: row steps per hand-off block (<= LR_BMAX)
+    int32_t slack;            // sw_longr_kernel: blocks a stripe lets its left neighbour get ahead before it starts
     // END CELL (sw_longr_kernel<..., ENDS>): the cell the reference's running maximum comes from, as a 64-bit key
     //     H << 43 | (2^22 - 1 - (row + column)) << 21 | (2^21 - 1 - ix)
     // ix = the index along the reference's sx (the shorter line, line 1 on ties): the column when col_is_sx,
@@ -86,14 +87,31 @@ constexpr int LONG_UNROLL = AGX_LONG_UNROLL;
 // An entry is two 64-bit halves, {H+goe, tag} and {E, tag}, read and written as .v2.b64: the memory model makes each
 // 64-bit ELEMENT of a vector access single-copy atomic, so a value can never be seen with another write's tag
 // (a .v4.s32 access only guarantees that per 32-bit element), also for peer stores over NVLink.
-__device__ __forceinline__ int4 ld_entry(const int4 *p, bool sys)
-{
+// What a load of an entry returns: the two 64-bit halves as they came.  The fields are taken apart where they are
+// USED -- unpacking them next to the load made the warp wait for every early request on the spot (15 % of a lone
+// warp's stall samples sat on those moves: profiles/r2y_longr_7_4_ncu.txt).
+struct LEntry {
     unsigned long long a, b;
+    __device__ __forceinline__ int32_t x() const { return (int32_t)(uint32_t)a; }            // H + goe
+    __device__ __forceinline__ int32_t y() const { return (int32_t)(uint32_t)(a >> 32); }    // tag
+    __device__ __forceinline__ int32_t z() const { return (int32_t)(uint32_t)b; }            // E
+    __device__ __forceinline__ int32_t w() const { return (int32_t)(uint32_t)(b >> 32); }    // tag
+};
+__device__ __forceinline__ LEntry make_lentry(int32_t x, int32_t y, int32_t z, int32_t w)
+{
+    LEntry e;
+    e.a = (unsigned long long)(uint32_t)x | ((unsigned long long)(uint32_t)y << 32);
+    e.b = (unsigned long long)(uint32_t)z | ((unsigned long long)(uint32_t)w << 32);
+    return e;
+}
+__device__ __forceinline__ LEntry ld_entry(const int4 *p, bool sys)
+{
+    LEntry e;
     if (sys)
-        asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+        asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(e.a), "=l"(e.b) : "l"(p) : "memory");
     else
-        asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
-    return make_int4((int32_t)(uint32_t)a, (int32_t)(uint32_t)(a >> 32), (int32_t)(uint32_t)b, (int32_t)(uint32_t)(b >> 32));
+        asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(e.a), "=l"(e.b) : "l"(p) : "memory");
+    return e;
 }
 __device__ __forceinline__ void st_entry(int4 *p, int4 v, bool sys)
 {
@@ -149,7 +167,7 @@ sw_long_kernel(LongArgs g)
 
         // inputs of the first 32 rows
         int32_t nb = 0x200;
-        int4 nx = make_int4(goe, gst - 1, goe, gst - 1);
+        LEntry nx = make_lentry(goe, gst - 1, goe, gst - 1);
         if (lane < lb) {
             nb = g.b[lane];
             if (!left_edge) nx = ld_entry(g.bnd + lane, in_remote);
@@ -160,15 +178,15 @@ sw_long_kernel(LongArgs g)
                 if (!left_edge) {
                     // wait until the left neighbour has handed these 32 rows on
                     unsigned ns = 32;
-                    while (__any_sync(0xffffffffu, nx.y != gst - 1 || nx.w != gst - 1)) {
+                    while (__any_sync(0xffffffffu, nx.y() != gst - 1 || nx.w() != gst - 1)) {
                         __nanosleep(ns);
                         if (ns < 512) ns *= 2;
-                        if (r < lb && (nx.y != gst - 1 || nx.w != gst - 1)) nx = ld_entry(g.bnd + r, in_remote);
+                        if (r < lb && (nx.y() != gst - 1 || nx.w() != gst - 1)) nx = ld_entry(g.bnd + r, in_remote);
                     }
                 }
                 r_byte[wib][r & (LONG_RING - 1)] = nb;
-                r_g[wib][r & (LONG_RING - 1)] = nx.x;
-                r_e[wib][r & (LONG_RING - 1)] = nx.z;
+                r_g[wib][r & (LONG_RING - 1)] = nx.x();
+                r_e[wib][r & (LONG_RING - 1)] = nx.z();
             }
             __syncwarp();
             const int send = min(32, S - s0);
@@ -226,7 +244,7 @@ sw_long_kernel(LongArgs g)
                 // inputs of the next block
                 const int r = s0 + 32 + lane;
                 nb = 0x200;
-                nx = make_int4(goe, gst - 1, goe, gst - 1);
+                nx = make_lentry(goe, gst - 1, goe, gst - 1);
                 if (r < lb) {
                     nb = g.b[r];
                     if (!left_edge) nx = ld_entry(g.bnd + r, in_remote);
@@ -345,7 +363,7 @@ sw_longr_kernel(LongArgs g)
         int4 *out_bnd = last ? g.next_bnd : g.bnd;                       // nullptr: nothing to hand on
         const bool out_remote = last;
         const bool in_remote = (st == 0);
-        const int4 fresh = make_int4(goe, gst - 1, goe, gst - 1);
+        const LEntry fresh = make_lentry(goe, gst - 1, goe, gst - 1);
 
         // neutral rows -31R .. -1 (what a lane sees before its first real row)
         __syncwarp();
@@ -353,9 +371,23 @@ sw_longr_kernel(LongArgs g)
             const int slot = (RROWS - 31 * R) + i;
             r_lo[wib][slot] = xb4; r_hi[wib][slot] = xb4; r_g[wib][slot] = goe; r_e[wib][slot] = goe;
         }
+        // Start slack.  A stripe that starts the moment its first block has been handed on stays "just in time" for
+        // good: every later block's entries are requested before they exist and fetched again at the top of the block
+        // (an L2 round trip per block, a third of a lone warp's cycles: ncu, long_scoreboard on ld_entry).  Letting
+        // the left neighbour get `slack` blocks further ahead first makes the early request find its data.
+        if (!left_edge && g.slack > 0) {
+            const int probe = min(lb - 1, (1 + g.slack) * B * R - 1);
+            unsigned ns = 32;
+            for (;;) {
+                const LEntry v = ld_entry(g.bnd + probe, in_remote);
+                if (v.y() == gst - 1 && v.w() == gst - 1) break;
+                __nanosleep(ns);
+                if (ns < 512) ns *= 2;
+            }
+        }
         // inputs of the first block: this lane owns rows base + 32 q + lane of every block
         int2 nt[R];
-        int4 nx[R];
+        LEntry nx[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) {
             const int idx = 32 * q + lane;
@@ -374,13 +406,13 @@ sw_longr_kernel(LongArgs g)
                 for (;;) {
                     bool missing = false;
 #pragma unroll
-                    for (int q = 0; q < R; ++q) missing = missing || nx[q].y != gst - 1 || nx[q].w != gst - 1;
+                    for (int q = 0; q < R; ++q) missing = missing || nx[q].y() != gst - 1 || nx[q].w() != gst - 1;
                     if (!__any_sync(0xffffffffu, missing)) break;
                     __nanosleep(ns);
                     if (ns < 320) ns *= 2;
 #pragma unroll
                     for (int q = 0; q < R; ++q)
-                        if (nx[q].y != gst - 1 || nx[q].w != gst - 1) nx[q] = ld_entry(g.bnd + base + 32 * q + lane, in_remote);
+                        if (nx[q].y() != gst - 1 || nx[q].w() != gst - 1) nx[q] = ld_entry(g.bnd + base + 32 * q + lane, in_remote);
                 }
             }
 #pragma unroll
@@ -389,7 +421,7 @@ sw_longr_kernel(LongArgs g)
                 if (idx < B * R) {
                     const int slot = (base + idx) & (RROWS - 1);
                     r_lo[wib][slot] = nt[q].x; r_hi[wib][slot] = nt[q].y;
-                    r_g[wib][slot] = nx[q].x;  r_e[wib][slot] = nx[q].z;
+                    r_g[wib][slot] = nx[q].x();  r_e[wib][slot] = nx[q].z();
                 }
             }
             __syncwarp();
@@ -632,7 +664,7 @@ sw_longp_kernel(LongArgs g)
         int4 *out_bnd = last ? g.next_bnd : g.bnd;
         const bool out_remote = last;
         const bool in_remote = (st == 0);
-        const int4 fresh = make_int4(goe, gst - 1, goe, gst - 1);
+        const LEntry fresh = make_lentry(goe, gst - 1, goe, gst - 1);
 
         __syncwarp();
         for (int i = lane; i < 31 * R; i += 32) {
@@ -640,7 +672,7 @@ sw_longp_kernel(LongArgs g)
             r_lo[wib][slot] = xb4; r_hi[wib][slot] = xb4; r_g[wib][slot] = goe; r_e[wib][slot] = goe;
         }
         int2 nt[R];
-        int4 nx[R];
+        LEntry nx[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) {
             const int idx = 32 * q + lane;
@@ -658,13 +690,13 @@ sw_longp_kernel(LongArgs g)
                 for (;;) {
                     bool missing = false;
 #pragma unroll
-                    for (int q = 0; q < R; ++q) missing = missing || nx[q].y != gst - 1 || nx[q].w != gst - 1;
+                    for (int q = 0; q < R; ++q) missing = missing || nx[q].y() != gst - 1 || nx[q].w() != gst - 1;
                     if (!__any_sync(0xffffffffu, missing)) break;
                     __nanosleep(ns);
                     if (ns < 320) ns *= 2;
 #pragma unroll
                     for (int q = 0; q < R; ++q)
-                        if (nx[q].y != gst - 1 || nx[q].w != gst - 1) nx[q] = ld_entry(g.bnd + base + 32 * q + lane, in_remote);
+                        if (nx[q].y() != gst - 1 || nx[q].w() != gst - 1) nx[q] = ld_entry(g.bnd + base + 32 * q + lane, in_remote);
                 }
             }
 #pragma unroll
@@ -673,7 +705,7 @@ sw_longp_kernel(LongArgs g)
                 if (idx < B * R) {
                     const int slot = slot_of(base + idx);
                     r_lo[wib][slot] = nt[q].x; r_hi[wib][slot] = nt[q].y;
-                    r_g[wib][slot] = nx[q].x;  r_e[wib][slot] = nx[q].z;
+                    r_g[wib][slot] = nx[q].x();  r_e[wib][slot] = nx[q].z();
                 }
             }
             __syncwarp();
@@ -870,6 +902,7 @@ int env_int(const char *name, int dflt)
     return (e && *e && atoi(e) >= 0) ? atoi(e) : dflt;
 }
 
+constexpr int LONG_SLACK_DEFAULT = 0;
 // row steps per hand-off block of sw_longr_kernel (the stripe-fill term of the run is stripes x (32 + B) steps)
 int long_block_steps()
 {
@@ -1092,6 +1125,7 @@ int sw_long_device(SwLongWorkspace &ws, const uint8_t *d_a, int64_t la, const ui
     args.one = 1;
     args.a = d_a; args.la = (int32_t)la; args.b = d_b; args.lb = (int32_t)lb;
     args.bsteps = long_block_steps();
+    args.slack = env_int("AGX_LONG_SLACK", LONG_SLACK_DEFAULT);
     int2 *d_rowtab = reinterpret_cast<int2 *>(ws.buf + (4 * lb + 4 + 8 + 64 + 1) / 2 * 2);
     args.rowtab = d_rowtab;
     if (coded) {
@@ -1198,6 +1232,7 @@ int sw_long_host_multi(int n_dev, const int *dev, cudaStream_t *st, SwLongWorksp
         x.k32 = 32;
         x.next_bnd = nullptr;
         x.bsteps = long_block_steps();
+        x.slack = env_int("AGX_LONG_SLACK", LONG_SLACK_DEFAULT);
         int2 *d_rowtab = reinterpret_cast<int2 *>(w.buf + 4 * lb + 4);
         x.rowtab = d_rowtab;
         if (coded) {
