@@ -48,6 +48,7 @@ struct LongArgs {
     const int2 *rowtab;       // sw_longr_kernel: 8-byte score table of every row (long_rowtab_kernel), padded
     int32_t bsteps;           // sw_longr_kernel: row steps per hand-off block (<= LR_BMAX)
     int32_t slack;            // sw_longr_kernel: blocks a stripe lets its left neighbour get ahead before it starts
+    int32_t req_eighths;      // sw_longr_kernel: the next block's entries are requested at step send * req_eighths / 8
     // END CELL (sw_longr_kernel<..., ENDS>): the cell the reference's running maximum comes from, as a 64-bit key
     //     H << 43 | (2^22 - 1 - (row + column)) << 21 | (2^21 - 1 - ix)
     // ix = the index along the reference's sx (the shorter line, line 1 on ties): the column when col_is_sx,
@@ -433,7 +434,7 @@ sw_longr_kernel(LongArgs g)
                 if (idx < B * R) nt[q] = g.rowtab[base + B * R + idx];       // rowtab is padded past the last block
             }
             const int send = min(B, S - s0);
-            const int half = send >> 1;
+            const int half = (send * g.req_eighths) >> 3;
             // row tables / lane-0 boundary of this block's first step; later steps get theirs one step ahead (a lone
             // warp has nothing else to cover the shared-memory latency with)
             int32_t tlo[R], thi[R], bg[R], be[R];
@@ -1126,6 +1127,7 @@ int sw_long_device(SwLongWorkspace &ws, const uint8_t *d_a, int64_t la, const ui
     args.a = d_a; args.la = (int32_t)la; args.b = d_b; args.lb = (int32_t)lb;
     args.bsteps = long_block_steps();
     args.slack = env_int("AGX_LONG_SLACK", LONG_SLACK_DEFAULT);
+    args.req_eighths = env_int("AGX_LONG_REQ", 4);
     int2 *d_rowtab = reinterpret_cast<int2 *>(ws.buf + (4 * lb + 4 + 8 + 64 + 1) / 2 * 2);
     args.rowtab = d_rowtab;
     if (coded) {
@@ -1233,6 +1235,7 @@ int sw_long_host_multi(int n_dev, const int *dev, cudaStream_t *st, SwLongWorksp
         x.next_bnd = nullptr;
         x.bsteps = long_block_steps();
         x.slack = env_int("AGX_LONG_SLACK", LONG_SLACK_DEFAULT);
+        x.req_eighths = env_int("AGX_LONG_REQ", 4);
         int2 *d_rowtab = reinterpret_cast<int2 *>(w.buf + 4 * lb + 4);
         x.rowtab = d_rowtab;
         if (coded) {
