@@ -1007,6 +1007,30 @@ def cpu_leg(agx, args, gatk, align=None):
     par.update(ref.parity_sw(cap))
     par.update(ref.parity_hmm(cap))
     out["parity"] = par
+    # BASELINE configs[4]'s CPU side: the reference with a raised line buffer (oracle/_ref/sw_antidiag_long, arithmetic
+    # untouched) on a square the core finishes in seconds, the GPU's long-alignment kernel on the same pair, and the
+    # time 1 Mbp x 1 Mbp would take -- an EXTRAPOLATION by cell count, labelled as one
+    long_exe = ROOT / "oracle" / "_ref" / "sw_antidiag_long"
+    if long_exe.exists() and args.long_cpu_len > 0:
+        L = args.long_cpu_len
+        data = agx.synth.sw_long_pair(L, seed=21, related=True)
+        pth = Path(ref.tmp.name) / "long.in"
+        pth.write_bytes(data)
+        t0 = time.perf_counter()
+        r = subprocess.run(["bash", "-c", f"ulimit -s unlimited 2>/dev/null; exec {long_exe} {pth}"], capture_output=True)
+        dt = time.perf_counter() - t0
+        want = [int(l.split()[1]) for l in r.stdout.decode(errors="replace").splitlines() if l.startswith("Score:")]
+        inp = agx.formats.parse_sw(data, line_buf=1 << 30)
+        # (4 * 10^8 cells >= 2^28: the pair takes the whole-GPU long-alignment kernel)
+        got = cap.sw_score_flat(inp.buf, inp.off, inp.len)
+        cells = float(inp.len[0]) * float(inp.len[1])
+        out["cpu_sw_long"] = {"value": cells / dt / 1e9, "unit": "GCUPS", "cores": 1, "kind": "reference",
+                              "sample": f"one pair {L} x {L} (oracle/_ref/sw_antidiag_long = antidiagonalSmithWaterman.c -O3 with "
+                                        f"MAX_LINE_LENGTH raised), {dt:.1f} s",
+                              "extrapolated_seconds_1mbp_one_core": dt * (1e12 / cells),
+                              "extrapolation": "by cell count from the sample above; not measured",
+                              "gpu_score_equals_reference": bool(len(want) == 1 and got.size == 1 and int(got[0]) == want[0]),
+                              "score": int(got[0]) if got.size else None}
     if align is not None:
         # alignments of a sample against the oracle (end cell, start cell, CIGAR) and EVERY CIGAR of a larger sample
         # re-scored to its Smith-Waterman score
@@ -1172,6 +1196,8 @@ def run_gpu_arm(args):
             if "cpu_hmm" in extras:
                 sub["cpu_baseline"] = extras["cpu_hmm"]
             line["pairhmm"] = sub
+        if "cpu_sw_long" in extras and "sw_long" in extras:
+            extras["sw_long"]["cpu_baseline"] = extras["cpu_sw_long"]
         for key in ("sw_long", "strong", "pairhmm_gatk", "sw_lengths", "sw_align", "parity"):
             if key in extras:
                 line[key] = extras[key]
@@ -1236,6 +1262,8 @@ def main():
     ap.add_argument("--no-strong", action="store_true")
     ap.add_argument("--no-gatk", action="store_true")
     ap.add_argument("--no-align", action="store_true")
+    ap.add_argument("--long-cpu-len", type=int, default=20000,
+                    help="side of the square the reference C is timed on for the sw_long CPU baseline (0 = skip)")
     ap.add_argument("--align-pairs", type=int, default=1_000_000, help="pairs of the \"sw_align\" object (at most --sw-pairs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "agx":
