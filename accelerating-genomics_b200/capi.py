@@ -28,7 +28,7 @@ SYMBOLS = [
     "pairhmm_forward_file_image",
     "agx_pairhmm_set_gatk_mode", "agx_pairhmm_set_force_fp64", "agx_pairhmm_rescue_count",
     "sw_score_shards_device", "pairhmm_forward_shards_device",
-    "sw_ends_batch_flat", "sw_align_batch_flat",
+    "sw_ends_batch_flat", "sw_align_batch_flat", "sw_ends_batch", "sw_align_batch",
 ]
 
 # the reference's scoring constants, antidiagonalSmithWaterman.c:40-43
@@ -101,6 +101,11 @@ def load_library() -> C.CDLL:
     lib.sw_align_batch_flat.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_int32] * 4 + \
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
     lib.sw_align_batch_flat.restype = C.c_int
+    lib.sw_ends_batch.argtypes = [pp, i32p, pp, i32p, C.c_int64] + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p]
+    lib.sw_ends_batch.restype = C.c_int
+    lib.sw_align_batch.argtypes = [pp, i32p, pp, i32p, C.c_int64] + [C.c_int32] * 4 + \
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    lib.sw_align_batch.restype = C.c_int
     lib.sw_score_shards_device.restype = C.c_int
     lib.pairhmm_forward_shards_device.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
     lib.pairhmm_forward_shards_device.restype = C.c_int
@@ -267,6 +272,41 @@ def sw_align_flat(seqs: np.ndarray, off: np.ndarray, length: np.ndarray, scoring
             continue
         _check(rc)
         return scores, coords, cig_off, cigar[:int(total.value)]
+
+
+def sw_align_batch(a: Sequence[bytes], b: Sequence[bytes], scoring=(SW_MATCH, SW_MISMATCH, SW_GAP_OPEN, SW_GAP_EXTEND)):
+    """sw_align_batch: pointer-array form; (scores, coords[n, 4], cigar_off[n + 1], cigar runs)"""
+    n = len(a)
+    assert len(b) == n
+    pa = (C.c_char_p * n)(*a)
+    pb = (C.c_char_p * n)(*b)
+    la = (C.c_int32 * n)(*[len(x) for x in a])
+    lb = (C.c_int32 * n)(*[len(x) for x in b])
+    scores = np.empty(n, dtype=np.int32)
+    coords = np.empty((n, 4), dtype=np.int32)
+    cig_off = np.empty(n + 1, dtype=np.int64)
+    cap = max(16, sum(len(x) + len(y) + 2 for x, y in zip(a, b)))      # no pair has more runs than symbols
+    cigar = np.empty(cap, dtype=np.uint32)
+    total = C.c_int64(0)
+    _check(load_library().sw_align_batch(C.cast(pa, C.POINTER(C.c_void_p)), la, C.cast(pb, C.POINTER(C.c_void_p)), lb, n,
+                                         *[int(s) for s in scoring], _ptr(scores), _ptr(coords), _ptr(cig_off),
+                                         _ptr(cigar), cap, C.byref(total)))
+    return scores, coords, cig_off, cigar[:int(total.value)]
+
+
+def sw_ends_batch(a: Sequence[bytes], b: Sequence[bytes], scoring=(SW_MATCH, SW_MISMATCH, SW_GAP_OPEN, SW_GAP_EXTEND)):
+    """sw_ends_batch: pointer-array form; (scores, ends[n, 2])"""
+    n = len(a)
+    assert len(b) == n
+    pa = (C.c_char_p * n)(*a)
+    pb = (C.c_char_p * n)(*b)
+    la = (C.c_int32 * n)(*[len(x) for x in a])
+    lb = (C.c_int32 * n)(*[len(x) for x in b])
+    scores = np.empty(n, dtype=np.int32)
+    ends = np.empty((n, 2), dtype=np.int32)
+    _check(load_library().sw_ends_batch(C.cast(pa, C.POINTER(C.c_void_p)), la, C.cast(pb, C.POINTER(C.c_void_p)), lb, n,
+                                        *[int(s) for s in scoring], _ptr(scores), _ptr(ends)))
+    return scores, ends
 
 
 def sw_score_batch(a: Sequence[bytes], b: Sequence[bytes],

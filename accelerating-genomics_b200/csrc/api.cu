@@ -465,9 +465,10 @@ int sw_align_shard(DeviceCtx &c, const uint8_t *seqs, const int64_t *off, const 
         if ((rc = c.al_ends.reserve((size_t)m * 2 * sizeof(int32_t))) != AGX_OK) return rc;
         if (mode == 2 && (rc = c.al_coords.reserve((size_t)m * 4 * sizeof(int32_t))) != AGX_OK) return rc;
         if ((rc = c.h_al_off.reserve((size_t)m * 2 * sizeof(int64_t))) != AGX_OK) return rc;
+        // the sequence bytes first: their upload runs while the host rebases the offsets
+        AGX_CUDA(cudaMemcpyAsync(c.al_bytes.p, seqs + l, (size_t)(h - l), cudaMemcpyHostToDevice, st));
         int64_t *roff = c.h_al_off.as<int64_t>();
         for (int64_t i = 0; i < 2 * m; ++i) roff[i] = off[2 * q0 + i] - l;       // offsets relative to the uploaded range
-        AGX_CUDA(cudaMemcpyAsync(c.al_bytes.p, seqs + l, (size_t)(h - l), cudaMemcpyHostToDevice, st));
         AGX_CUDA(cudaMemcpyAsync(c.al_off.p, roff, (size_t)m * 2 * sizeof(int64_t), cudaMemcpyHostToDevice, st));
         AGX_CUDA(cudaMemcpyAsync(c.al_len.p, len + 2 * q0, (size_t)m * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         if (trace) { cudaStreamSynchronize(st); fprintf(stderr, "[agx align] +%.2f ms: uploaded\n", now() - t_begin); }
@@ -927,6 +928,59 @@ int sw_align_batch_flat(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *
 {
     return sw_align_impl(seqs, seqs_bytes, off, len, n_pairs, SwScoring{match, mismatch, gap_open, gap_extend}, 2,
                          scores_out, nullptr, coords_out, cigar_off_out, cigar_out, cigar_cap, cigar_total_out);
+}
+
+// pointer-array forms: gathered into one flat image (a0 b0 a1 b1 ...), then the flat entry points
+static int gather_pairs(const uint8_t *const *a, const int32_t *a_len, const uint8_t *const *b, const int32_t *b_len,
+                        int64_t n_pairs, std::vector<uint8_t> &flat, std::vector<int64_t> &off, std::vector<int32_t> &len)
+{
+    if (n_pairs < 0) return fail(AGX_EINVAL, "sw: n_pairs < 0");
+    if (n_pairs > 0 && (!a || !a_len || !b || !b_len)) return fail(AGX_EINVAL, "sw: null argument");
+    off.resize((size_t)n_pairs * 2);
+    len.resize((size_t)n_pairs * 2);
+    int64_t total = 0;
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        if (a_len[p] < 0 || b_len[p] < 0 || (a_len[p] && !a[p]) || (b_len[p] && !b[p]))
+            return fail(AGX_EINVAL, "sw: bad sequence " + std::to_string(p));
+        off[2 * p] = total; len[2 * p] = a_len[p];
+        total += a_len[p];
+        off[2 * p + 1] = total; len[2 * p + 1] = b_len[p];
+        total += b_len[p];
+    }
+    flat.resize((size_t)total + 1);
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        if (a_len[p]) memcpy(flat.data() + off[2 * p], a[p], (size_t)a_len[p]);
+        if (b_len[p]) memcpy(flat.data() + off[2 * p + 1], b[p], (size_t)b_len[p]);
+    }
+    return AGX_OK;
+}
+
+int sw_ends_batch(const uint8_t *const *a, const int32_t *a_len, const uint8_t *const *b, const int32_t *b_len,
+                  int64_t n_pairs, int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend,
+                  int32_t *scores_out, int32_t *ends_out)
+{
+    std::vector<uint8_t> flat;
+    std::vector<int64_t> off;
+    std::vector<int32_t> len;
+    int rc = gather_pairs(a, a_len, b, b_len, n_pairs, flat, off, len);
+    if (rc != AGX_OK) return rc;
+    return sw_ends_batch_flat(flat.data(), (int64_t)flat.size() - 1, off.data(), len.data(), n_pairs, match, mismatch,
+                              gap_open, gap_extend, scores_out, ends_out);
+}
+
+int sw_align_batch(const uint8_t *const *a, const int32_t *a_len, const uint8_t *const *b, const int32_t *b_len,
+                   int64_t n_pairs, int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend,
+                   int32_t *scores_out, int32_t *coords_out, int64_t *cigar_off_out, uint32_t *cigar_out,
+                   int64_t cigar_cap, int64_t *cigar_total_out)
+{
+    std::vector<uint8_t> flat;
+    std::vector<int64_t> off;
+    std::vector<int32_t> len;
+    int rc = gather_pairs(a, a_len, b, b_len, n_pairs, flat, off, len);
+    if (rc != AGX_OK) return rc;
+    return sw_align_batch_flat(flat.data(), (int64_t)flat.size() - 1, off.data(), len.data(), n_pairs, match, mismatch,
+                               gap_open, gap_extend, scores_out, coords_out, cigar_off_out, cigar_out, cigar_cap,
+                               cigar_total_out);
 }
 
 // sw_score_file_image over several GPUs: the image is cut into one byte range per GPU at line starts; every

@@ -179,6 +179,15 @@ int sw_align_batch_flat(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *
                         int32_t *scores_out, int32_t *coords_out, int64_t *cigar_off_out, uint32_t *cigar_out,
                         int64_t cigar_cap, int64_t *cigar_total_out);
 
+/* The same two calls on pointer arrays, pair p = (a[p], a_len[p]) vs (b[p], b_len[p]) as in sw_score_batch. */
+int sw_ends_batch(const uint8_t *const *a, const int32_t *a_len, const uint8_t *const *b, const int32_t *b_len,
+                  int64_t n_pairs, int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend,
+                  int32_t *scores_out, int32_t *ends_out);
+int sw_align_batch(const uint8_t *const *a, const int32_t *a_len, const uint8_t *const *b, const int32_t *b_len,
+                   int64_t n_pairs, int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend,
+                   int32_t *scores_out, int32_t *coords_out, int64_t *cigar_off_out, uint32_t *cigar_out,
+                   int64_t cigar_cap, int64_t *cigar_total_out);
+
 /* ------------------------------------------------------------------ PairHMM forward */
 
 /* One batch: every read against every haplotype (the Cartesian loop of

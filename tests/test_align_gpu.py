@@ -240,3 +240,17 @@ def test_whole_gpu_pairs_report_their_end_cell(agx, gpu_lib, oracle_mod, n, rela
     with pytest.raises(agx.capi.AgxError) as e:
         gpu_lib.sw_align_flat(buf, off, ln)             # the traceback of such a pair is refused
     assert e.value.code == -5
+
+
+def test_pointer_array_forms(gpu_lib, oracle_mod):
+    """sw_ends_batch / sw_align_batch: the pointer-array signatures (pair p = a[p] vs b[p]), embedded NUL bytes kept"""
+    rng = np.random.default_rng(108)
+    a, b = _pairs(rng, 300, 1, 160)
+    a.append(b"AC\0GTAC\0GT")
+    b.append(b"AC\0GTTC\0GT")
+    s1, ends = gpu_lib.sw_ends_batch(a, b)
+    s2, coords, coff, cig = gpu_lib.sw_align_batch(a, b)
+    for p, (x, y) in enumerate(zip(a, b)):
+        ws, wc, wg = oracle_mod.sw_align(x, y)
+        assert (int(s1[p]), tuple(ends[p].tolist())) == (ws, (wc[1], wc[3]))
+        assert (int(s2[p]), tuple(coords[p].tolist()), cig[coff[p]:coff[p + 1]].tolist()) == (ws, wc, wg)
