@@ -113,14 +113,15 @@ __global__ void __launch_bounds__(256) units_to_bytes_kernel(int64_t *__restrict
 // ---- the traceback walk ---------------------------------------------------------------------------------------
 struct WalkLayout {
     const uint8_t *tb;      // the pair's matrix
-    int32_t rstride, K, K2, half;
+    int32_t rstride, K, TB, LS, half;
     bool duo;
     __device__ __forceinline__ uint32_t at(int32_t r, int32_t c) const
     {
         if (duo) {
-            // step-major: lane t of the sub-warp holds row r at step r + t; a step is 32 lanes x K2 words
-            const int32_t t = c / K, jj = c - t * K;
-            return __ldg(tb + ((int64_t)(r + t) * 32 + t) * (K2 * 4) + (jj >> 1) * 4 + (jj & 1) + 2 * half);
+            // lane t of the sub-warp holds row r at step r + t; batches of TB steps, a lane block of LS words per
+            // batch, word (q, step in batch) at q * TB + step (see duo_tb_steps)
+            const int32_t t = c / K, jj = c - t * K, s = r + t;
+            return __ldg(tb + ((int64_t)(s / TB) * 32 + t) * (LS * 4) + ((jj >> 1) * TB + (s & (TB - 1))) * 4 + (jj & 1) + 2 * half);
         }
         return __ldg(tb + ((int64_t)(c >> 8) * rstride + r) * 256 + (c & 255));
     }
@@ -159,8 +160,9 @@ sw_walk_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off
     L.duo = w.cls >= 0;
     L.tb = (L.duo ? tb : tb_gen) + w.tb_off;
     L.rstride = w.rstride;
-    L.K = L.duo ? duo_class(w.cls).k : 0;
-    L.K2 = (L.K + 1) / 2;
+    L.K = L.duo ? duo_class(w.cls).k : 1;
+    L.TB = duo_tb_steps(L.K);
+    L.LS = duo_tb_block_words(L.K);
     L.half = w.half;
     const int32_t goe_open = sc.gap_open, ext = sc.gap_extend;
     // runs, end -> start, merged as they come
@@ -260,7 +262,8 @@ sw_cigar_gather_kernel(const uint32_t *__restrict__ tmp_ops, const int64_t *__re
 // bytes of one warp's step-major matrix in class c when the class's longest row sequence has `rows` symbols
 __host__ __device__ constexpr int64_t duo_tb_warp_bytes(int c, int32_t rows)
 {
-    return (int64_t)(rows + duo_class(c).g - 1) * 32 * ((duo_class(c).k + 1) / 2) * 4;
+    const int tb = duo_tb_steps(duo_class(c).k);
+    return (int64_t)((rows + duo_class(c).g - 1 + tb - 1) / tb) * duo_tb_batch_bytes(duo_class(c).k);
 }
 // ... of the whole class: the grid is whole CTAs of DUO_THREADS / 32 warps
 inline int64_t duo_tb_class_bytes(int c, int32_t count, int32_t rows)
@@ -287,9 +290,12 @@ int launch_duo_align(const uint8_t *d_seqs, const int64_t *d_off, const int32_t 
             a.tb = ao.tb ? ao.tb + tb_base[C] : nullptr;
             a.tb_class_off = tb_base[C];
             int32_t *glist = const_cast<int32_t *>(order) + (int64_t)GENERIC * n_pairs;
-            if (mode == 2)
-                sw_duo_kernel<G, K, 2><<<blocks, DUO_THREADS, 0, st>>>(d_seqs, d_off, d_len, order + (int64_t)C * n_pairs,
+            if (mode == 2) {
+                // staging buffers in dynamic shared memory (with the 8 KB row ring they pass the 48 KB static limit)
+                AGX_CUDA(cudaFuncSetAttribute(sw_duo_kernel<G, K, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, duo_tb_smem_bytes(K)));
+                sw_duo_kernel<G, K, 2><<<blocks, DUO_THREADS, duo_tb_smem_bytes(K), st>>>(d_seqs, d_off, d_len, order + (int64_t)C * n_pairs,
                                                                      counts[C], kc, d_scores, glist, counters + GENERIC, a);
+            }
             else
                 sw_duo_kernel<G, K, 1><<<blocks, DUO_THREADS, 0, st>>>(d_seqs, d_off, d_len, order + (int64_t)C * n_pairs,
                                                                      counts[C], kc, d_scores, glist, counters + GENERIC, a);

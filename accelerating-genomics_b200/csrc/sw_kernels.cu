@@ -193,11 +193,19 @@ __device__ __forceinline__ uint32_t base_code(uint32_t ch, bool &ok)
 #endif
 // MODE 0: score only.  MODE 1: + END CELL.  MODE 2: + the low byte of every H, for the traceback walk.
 // The alignment modes carry ~10 more live registers (keys, store pointer, packed bytes): one CTA fewer.
+// MODE 2 matrix layout.  A warp's matrix is a sequence of BATCHES of TB steps; in a batch every lane owns a block of
+// K2 x TB words, word (q, r) = columns 2q, 2q+1 (both pairs) of the lane's row of step r, stored at q * TB + r: the
+// TB rows of a column pair sit side by side, so the traceback walk -- one row and one column back per step -- finds
+// up to TB consecutive cells of its diagonal inside one 64-byte line.  Blocks are padded to an ODD number of words
+// (the lanes' 32-bit shared-memory stores then fall into 32 different banks); the padding travels to HBM.
 __host__ __device__ constexpr int duo_tb_steps(int K)
 {
-    const int b = 40 / ((K + 1) / 2);          // 40 KB of staging per 4-warp CTA: 1024 * TB * K2 bytes
-    return b < 1 ? 1 : b > 8 ? 8 : b;
+    const int k2 = (K + 1) / 2;                // a power of two that divides the 32-row refill; ~40 KB of staging per CTA
+    return k2 <= 4 ? 8 : k2 <= 10 ? 4 : 2;
 }
+__host__ __device__ constexpr int duo_tb_block_words(int K) { return ((K + 1) / 2) * duo_tb_steps(K) + 1; }
+__host__ __device__ constexpr int duo_tb_batch_bytes(int K) { return 32 * duo_tb_block_words(K) * 4; }
+__host__ __device__ constexpr int duo_tb_smem_bytes(int K) { return (DUO_THREADS / 32) * 2 * duo_tb_batch_bytes(K); }
 __host__ __device__ constexpr int duo_min_blocks_sw(int K, int MODE = 0)
 {
     return K <= 19 ? (MODE ? 4 : AGX_DUO_MINBLOCKS) : K <= 24 ? 3 : 2;
@@ -209,7 +217,7 @@ struct DuoAlignOut {
     uint8_t *tb;          // MODE 2: H-byte matrices of this class, one per WARP, step-major:
                           //         [step s][lane][K2 words], lane t of a sub-warp holding row s - t at step s
     int64_t tb_class_off; //         where this class starts in the scratch (the walk addresses from the scratch base)
-    int64_t tb_warp_bytes; //        steps * 32 * K2 * 4, steps = (most rows of the class) + G - 1
+    int64_t tb_warp_bytes; //        batches * duo_tb_batch_bytes(K), batches = ceil(((most rows of the class) + G - 1) / TB)
     int32_t k32;          // 32, opaque to ptxas: key = H * 32 + tag as one IMAD on the FMA pipe
     int16_t cls;
 };
@@ -226,7 +234,8 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
     // MODE 2 stages TB steps of the whole warp in shared memory (TB * 32 * K2 words, contiguous in the step-major
     // global layout as well) and hands them to the copy engine as ONE bulk store; two buffers per warp
     constexpr int TB = duo_tb_steps(K);
-    __shared__ __align__(128) uint2 tbuf[MODE == 2 ? DUO_THREADS / 32 : 1][2][MODE == 2 ? TB * 32 * (K2 / 2) : 1];
+    constexpr int LS = duo_tb_block_words(K);          // words of a lane's block in a batch
+    extern __shared__ __align__(128) uint32_t tb_stage[];   // MODE 2: [warp][2 buffers][32 lanes][LS]
     constexpr int SUBS = DUO_THREADS / G;
     // row steps per loop trip: 8 measured +3 % over 2 at K = 19 (16 overflows the instruction cache: -17 %);
     // the wide classes keep 2
@@ -354,14 +363,15 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-            const uint32_t bytes = (uint32_t)n_steps * 32u * K2 * 4u;
-            const uint32_t src = (uint32_t)__cvta_generic_to_shared(&tbuf[wib][tb_cur][0]);
+            const uint32_t bytes = (uint32_t)duo_tb_batch_bytes(K);     // always a whole batch (unused steps: stale words)
+            const uint32_t src = (uint32_t)__cvta_generic_to_shared(tb_stage + (wib * 2 + tb_cur) * 32 * LS);
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(tb_warp + tb_done), "r"(src), "r"(bytes) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         }
         __syncwarp();
-        tb_done += (int64_t)n_steps * 32 * K2 * 4;
+        (void)n_steps;
+        tb_done += duo_tb_batch_bytes(K);
         tb_cur ^= 1;
     };
 
@@ -442,9 +452,9 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
                 kbase -= 1024u;
             }
             if constexpr (MODE == 2) {
-                uint2 *dst = &tbuf[wib][tb_cur][(slot * 32 + lane) * (K2 / 2)];
+                uint32_t *dst = tb_stage + ((wib * 2 + tb_cur) * 32 + lane) * LS + slot;
 #pragma unroll
-                for (int q = 0; q < K2 / 2; ++q) dst[q] = make_uint2(pk[2 * q], pk[2 * q + 1]);
+                for (int q = 0; q < K2; ++q) dst[q * TB] = pk[q];
             }
         };
         if constexpr (MODE == 2) {
@@ -515,7 +525,7 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
                     SwWalkRec w;
                     // the warp's matrix + this sub-warp's lanes inside a step
                     w.tb_off = ao.tb_class_off + ((int64_t)blockIdx.x * (DUO_THREADS / 32) + wib) * ao.tb_warp_bytes +
-                               (int64_t)(lane & ~(G - 1)) * K2 * 4;
+                               (int64_t)(lane & ~(G - 1)) * LS * 4;
                     w.r_end = nl_end ? Lb - 1 : r_end;
                     w.c_end = nl_end ? CAP - 1 : c_end;
                     w.row_off = row_off;
@@ -1014,7 +1024,7 @@ int64_t sw_align_tb_row_bytes(int32_t len_a, int32_t len_b)
         for (int ra = 0; ra <= DUO_MAX_CAP + 1; ++ra) {
             int32_t duo = 0;
             for (int c = 0; c < SW_N_DUO_CLASSES; ++c)
-                if (ra <= duo_cap(c) + 1) { duo = duo_class(c).g * ((duo_class(c).k + 1) / 2) * 2; break; }
+                if (ra <= duo_cap(c) + 1) { duo = duo_class(c).g * (((duo_class(c).k + 1) / 2) * 2 + 1); break; }   // + the block padding
             const int32_t wave = ((ra + 255) / 256) * 256;
             t[ra] = duo > wave ? duo : wave;
         }
