@@ -94,7 +94,8 @@ struct SwAlignWorkspace {
     int32_t *cap32 = nullptr;        // [n_pairs] most CIGAR runs a pair can have; later its run count
     int64_t *tmp_off = nullptr;      // [n_pairs + 1] exclusive scan of cap32
     int64_t *cig_off = nullptr;      // [n_pairs + 1] exclusive scan of the run counts
-    int32_t *gen_units = nullptr;    // [n_pairs] 256-byte units of each listed wavefront pair's matrix
+    int32_t *gen_units = nullptr;    // [n_pairs] 256-byte units of each listed wavefront pair's matrix; later the walk order
+    int32_t *walk_bins = nullptr;    // score-size histogram + cursors of that order
     int64_t *gen_off = nullptr;      // [n_pairs + 1] their scan (in units, turned into bytes in place)
     int64_t *scan_tmp = nullptr;
     int64_t *d_total = nullptr;      // 4 totals

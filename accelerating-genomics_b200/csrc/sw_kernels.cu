@@ -1005,7 +1005,7 @@ void sw_align_workspace_free(SwAlignWorkspace &ws)
 {
     for (void *p : {(void *)ws.order, (void *)ws.cap32, (void *)ws.tmp_off, (void *)ws.cig_off, (void *)ws.gen_units,
                     (void *)ws.gen_off, (void *)ws.scan_tmp, (void *)ws.d_total, (void *)ws.wk, (void *)ws.counters,
-                    (void *)ws.tb, (void *)ws.tb_gen, (void *)ws.tmp_ops, (void *)ws.wave_scratch})
+                    (void *)ws.tb, (void *)ws.tb_gen, (void *)ws.tmp_ops, (void *)ws.wave_scratch, (void *)ws.walk_bins})
         if (p) cudaFree(p);
     if (ws.h_total) cudaFreeHost(ws.h_total);
     if (ws.h_counters) cudaFreeHost(ws.h_counters);
@@ -1071,6 +1071,7 @@ int sw_align_run_device(SwAlignWorkspace &ws, const uint8_t *d_seqs, const int64
         AGX_CUDA(cudaMalloc(&ws.counters, CNT_A_WORDS * sizeof(int32_t)));
         AGX_CUDA(cudaMallocHost(&ws.h_counters, CNT_A_WORDS * sizeof(int32_t)));
         AGX_CUDA(cudaMalloc(&ws.d_total, 4 * sizeof(int64_t)));
+        AGX_CUDA(cudaMalloc(&ws.walk_bins, 2 * WALK_BINS * sizeof(int32_t)));
         AGX_CUDA(cudaMallocHost(&ws.h_total, 4 * sizeof(int64_t)));
     }
 
@@ -1180,10 +1181,16 @@ int sw_align_run_device(SwAlignWorkspace &ws, const uint8_t *d_seqs, const int64
     if ((rc = grow(ws.tmp_ops, ws.cap_tmp, ws.h_total[1] + 16)) != AGX_OK) return rc;
     AGX_CUDA(cudaMemsetAsync(ws.d_total + 2, 0, sizeof(int64_t), st));
     ws.prof_walk.begin(st);
+    // walks of similar length side by side: pairs ordered by the size of their score (ws.gen_units is free again)
+    int32_t *walk_bins = ws.walk_bins, *walk_perm = ws.gen_units;
+    AGX_CUDA(cudaMemsetAsync(walk_bins, 0, 2 * WALK_BINS * sizeof(int32_t), st));
+    sw_walk_count_kernel<<<cblocks, 256, 0, st>>>(d_scores, n_pairs, walk_bins);
+    sw_walk_order_kernel<<<cblocks, 256, 0, st>>>(d_scores, n_pairs, walk_bins, walk_perm);
+    count_launch(2);
     // the two matrix buffers are addressed from one base: wavefront records carry an offset relative to tb_gen
     sw_walk_kernel<<<(int)((n_pairs + 127) / 128), 128, 0, st>>>(d_seqs, d_off, d_len, n_pairs, sc, ws.wk, ws.tb, ws.tb_gen, d_scores,
                                                                 d_ends, d_coords, ws.tmp_ops, ws.tmp_off, ws.cap32,
-                                                                reinterpret_cast<int32_t *>(ws.d_total + 2));
+                                                                reinterpret_cast<int32_t *>(ws.d_total + 2), walk_perm);
     count_launch();
     ws.prof_walk.end(st);
     AGX_CUDA(cudaGetLastError());
