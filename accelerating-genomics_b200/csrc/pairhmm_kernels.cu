@@ -57,8 +57,10 @@ constexpr int HCNT_WORDS = HCNT_PAIRS + HMM_MAX_K;
 #define AGX_HMM_MINBLOCKS 20
 #endif
 constexpr int HMM_WARPS = AGX_HMM_WARPS;
+// measured on BASELINE configs[3] (profiles/r2ag_hmm_variants.jsonl, r2ah_hmm_variants.jsonl; kernel ms per 10^6 pairs):
+// 4 -> 21.39, 8 -> 21.07, 12 -> 20.70, 16 -> 20.62, 24 -> 20.76, 32 -> 21.44
 #ifndef AGX_HMM_FAST
-#define AGX_HMM_FAST 8
+#define AGX_HMM_FAST 16
 #endif
 constexpr int HMM_FAST = AGX_HMM_FAST;           // branch-free column steps per loop trip of hmm_duo_kernel
 
@@ -435,8 +437,10 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b)
 // Resident one-warp blocks per SM the register budget is cut for.  Each of the four SM sub-partitions has
 // its own 16 K registers, so the useful targets are multiples of four: 12 blocks -> 168 registers per
 // thread, 16 -> 128, 20 -> 96.
+// (same sweep: the "tight" table below -- 128 registers for K = 6, 96 for K = 4 -- 21.07 -> 20.91 ms, 20.58 ms together
+// with 16 steps per trip; the roomy one 21.48 ms)
 #ifndef AGX_DUO_OCC
-#define AGX_DUO_OCC 0
+#define AGX_DUO_OCC 2
 #endif
 __host__ __device__ constexpr int duo_min_blocks(int K)
 {

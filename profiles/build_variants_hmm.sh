@@ -1,0 +1,17 @@
+#!/bin/bash
+# builds build/libagx_<name>.so: libagx with pairhmm_kernels.cu compiled under extra -D flags (kernel-tuning experiments)
+#   usage: profiles/build_variants_hmm.sh name "-DAGX_X=1" [name2 "flags2" ...]
+set -e
+cd "$(dirname "$0")/.."
+C=accelerating-genomics_b200/csrc
+mkdir -p build
+while [ $# -ge 2 ]; do
+  name=$1; flags=$2; shift 2
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-O3,-Wall --expt-relaxed-constexpr $flags -c $C/pairhmm_kernels.cu -o build/pairhmm_kernels_$name.o &
+  names="$names $name"
+done
+wait
+for name in $names; do
+  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/libagx_$name.so $C/api.o $C/sw_kernels.o $C/sw_long.o $C/sw_parse.o build/pairhmm_kernels_$name.o $C/pairhmm_parse.o -lpthread
+  echo built build/libagx_$name.so
+done
