@@ -185,8 +185,8 @@ __device__ __forceinline__ uint32_t base_code(uint32_t ch, bool &ok)
 // Resident 128-thread CTAs per SM the register budget is cut for.  The state is 3 K registers (sel, Gp, F), so
 // one budget for every class spills the wide ones (K = 32 at 5 CTAs / 96 registers: ~400 LDL/STL in the cell
 // loop): 5 CTAs up to K = 19, 3 (168 registers) for K = 24, 2 (255) for K = 32.
-#ifndef AGX_DUO_ALIGN_UNROLL
-#define AGX_DUO_ALIGN_UNROLL 4
+#ifndef AGX_DUO_ALIGN_MINBLOCKS
+#define AGX_DUO_ALIGN_MINBLOCKS 4
 #endif
 #ifndef AGX_DUO_MINBLOCKS
 #define AGX_DUO_MINBLOCKS 5
@@ -208,7 +208,7 @@ __host__ __device__ constexpr int duo_tb_batch_bytes(int K) { return 32 * duo_tb
 __host__ __device__ constexpr int duo_tb_smem_bytes(int K) { return (DUO_THREADS / 32) * 2 * duo_tb_batch_bytes(K); }
 __host__ __device__ constexpr int duo_min_blocks_sw(int K, int MODE = 0)
 {
-    return K <= 19 ? (MODE ? 4 : AGX_DUO_MINBLOCKS) : K <= 24 ? 3 : 2;
+    return K <= 19 ? (MODE ? AGX_DUO_ALIGN_MINBLOCKS : AGX_DUO_MINBLOCKS) : K <= 24 ? 3 : 2;
 }
 // what the alignment modes hand over besides the score
 struct DuoAlignOut {
