@@ -130,8 +130,12 @@ sw_classify_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__
 // inter-task duo kernel (s16x2 DPX)
 // ------------------------------------------------------------------------------------------
 constexpr int DUO_THREADS = 128;
-constexpr int DUO_CH = 32;    // rows converted per refill
-constexpr int DUO_RING = 64;  // row ring slots (>= DUO_CH + G)
+#ifndef AGX_DUO_CH
+#define AGX_DUO_CH 32
+#endif
+// rows converted per refill (the storing mode keeps 32: its staging buffers need the shared memory) and row ring
+// slots (>= rows per refill + G)
+__host__ __device__ constexpr int duo_ch(int MODE) { return MODE == 2 ? 32 : AGX_DUO_CH; }
 
 struct DuoSeq {
     const uint8_t *a;  // columns (shorter sequence)
@@ -242,6 +246,7 @@ sw_duo_kernel(const uint8_t *__restrict__ seqs, const int64_t *__restrict__ off,
     // (MODE 2 adds ~35 % to a step: 8 of those no longer fit the instruction cache -- measured per 8 * 10^5 pairs
     // of 150 x 150: 8 -> 5.29 ms, 4 -> 4.61 ms, 2 -> 4.69 ms, 1 -> 4.75 ms; it unrolls its staged batch of TB steps)
     constexpr int STEP_UNROLL = (K <= 19) ? 8 : 2;
+    constexpr int DUO_CH = duo_ch(MODE), DUO_RING = 2 * DUO_CH;
     __shared__ uint2 ring[SUBS][DUO_RING];
 
     const int lane = threadIdx.x & 31;
