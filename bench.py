@@ -708,6 +708,9 @@ def bench_strong(agx, args, n_gpus):
     h_buf = torch.from_numpy(inp.buf).pin_memory()
     np_buf = h_buf.numpy()
     h_scores = torch.empty(n, dtype=torch.int32).pin_memory()
+    off_pin = torch.from_numpy(inp.off).pin_memory().numpy()
+    len_pin = torch.from_numpy(inp.len).pin_memory().numpy()
+    align_keep = {}
     res = {}
     for label, devs in (("1gpu", [0]), ("ngpu", list(range(n_gpus)))):
         if label == "ngpu" and n_gpus == 1:
@@ -719,6 +722,10 @@ def bench_strong(agx, args, n_gpus):
         img_ms, (img_scores, _, _) = wall(lambda: cap.sw_score_file_image(np_buf, out=h_scores.numpy()))
         flat_ms, flat_scores = wall(lambda: cap.sw_score_flat(np_buf, inp.off, inp.len))
         assert np.array_equal(img_scores, flat_scores), "file-image and flat entry points disagree"
+        # full alignments (end cell, start cell, CIGAR) of the same batch, pairs sharded over the GPUs
+        align_ms, align_res = wall(lambda: cap.sw_align_flat(np_buf, off_pin, len_pin, cigar_cap=8 * n), warm=1)
+        assert np.array_equal(align_res[0], flat_scores), "alignment scores and score-only scores disagree"
+        align_keep[label] = align_res
         # resident: contiguous shards of equal pair count, uploaded once
         g = len(devs)
         shards, keep = [], []
@@ -737,7 +744,8 @@ def bench_strong(agx, args, n_gpus):
         k_ms = max(cap.profile_ms(dv, cap.PROF_SW_DUO) for dv in devs)
         got = np.concatenate([t[3].cpu().numpy() for t in keep])
         assert np.array_equal(got, flat_scores), "resident shards and host entry points disagree"
-        res[label] = {"e2e_file_image_ms": img_ms, "e2e_flat_ms": flat_ms, "resident_ms": res_ms, "kernel_ms_max_over_gpus": k_ms}
+        res[label] = {"e2e_file_image_ms": img_ms, "e2e_flat_ms": flat_ms, "resident_ms": res_ms, "kernel_ms_max_over_gpus": k_ms,
+                      "align_ms": align_ms}
         del keep, shards
     one, many = res["1gpu"], res["ngpu"]
     out["sw"] = {"workload": f"{n} pairs of {SW_LEN}x{SW_LEN} in ONE batch",
@@ -748,8 +756,14 @@ def bench_strong(agx, args, n_gpus):
                          "ms_1gpu": one["e2e_file_image_ms"], "speedup_vs_1gpu": one["e2e_file_image_ms"] / many["e2e_file_image_ms"],
                          "h2d_bytes_per_step": int(np_buf.nbytes), "d2h_bytes_per_step": int(4 * n), "entry_point": "sw_score_file_image"},
                  "e2e_flat": {"value": cells / (many["e2e_flat_ms"] * 1e-3) / 1e9, "ms": many["e2e_flat_ms"], "ms_1gpu": one["e2e_flat_ms"],
-                              "speedup_vs_1gpu": one["e2e_flat_ms"] / many["e2e_flat_ms"], "entry_point": "sw_score_batch_flat"}}
-    del h_buf, h_scores
+                              "speedup_vs_1gpu": one["e2e_flat_ms"] / many["e2e_flat_ms"], "entry_point": "sw_score_batch_flat"},
+                 "e2e_align": {"value": cells / (many["align_ms"] * 1e-3) / 1e9, "ms": many["align_ms"], "ms_1gpu": one["align_ms"],
+                               "speedup_vs_1gpu": one["align_ms"] / many["align_ms"], "entry_point": "sw_align_batch_flat",
+                               "note": "scores, start / end cells and CIGAR of every pair; pairs sharded over the GPUs, runs "
+                                       "concatenated in pair order",
+                               "equal_to_1gpu": bool(len(align_keep) < 2 or all(np.array_equal(x, y) for x, y in
+                                                                                 zip(align_keep["1gpu"], align_keep["ngpu"])))}}
+    del h_buf, h_scores, align_keep
 
     # ---- PairHMM --------------------------------------------------------------------------------------
     hin = agx.synth.pairhmm_batches(args.hmm_batches, 200, 5, seed=2000, unrelated_frac=args.hmm_unrelated)
