@@ -434,12 +434,14 @@ int sw_align_shard(DeviceCtx &c, const uint8_t *seqs, const int64_t *off, const 
     const double t_begin = now();
     while (q0 < p1) {
         // chunk: at most 2^20 pairs and, in mode 2, matrices within the budget (the class layout rounds rows up to
-        // the longest of the class, so the per-pair bound is scaled by what the chunk's longest line adds)
+        // the longest of the class, so the per-pair bound is scaled by what the chunk's longest line adds); the same
+        // pass finds the byte range [l, h) the chunk's sequences lie in
         int64_t q1 = q0, row_bytes = 0;
         int32_t longest = 1;
+        int64_t l = INT64_MAX, h = 0;
         while (q1 < p1 && q1 - q0 < ((int64_t)1 << 20) >> shrink) {
+            const int32_t la = len[2 * q1], lb = len[2 * q1 + 1];
             if (mode == 2) {
-                const int32_t la = len[2 * q1], lb = len[2 * q1 + 1];
                 const int32_t new_longest = std::max(longest, std::max(la, lb));
                 const int64_t grown = row_bytes + sw_align_tb_row_bytes(la, lb);
                 // every pair of a class is padded to the class's longest row sequence (+ the systolic skew)
@@ -447,15 +449,13 @@ int sw_align_shard(DeviceCtx &c, const uint8_t *seqs, const int64_t *off, const 
                 row_bytes = grown;
                 longest = new_longest;
             }
+            const int64_t oa = off[2 * q1], ob = off[2 * q1 + 1];
+            l = std::min(l, std::min(oa, ob));
+            h = std::max(h, std::max(oa + la, ob + lb));
             ++q1;
         }
         const int64_t m = q1 - q0;
         if (trace) fprintf(stderr, "[agx align] +%.2f ms: chunk of %lld pairs cut\n", now() - t_begin, (long long)m);
-        int64_t l = INT64_MAX, h = 0;
-        for (int64_t i = 2 * q0; i < 2 * q1; ++i) {
-            l = std::min(l, off[i]);
-            h = std::max(h, off[i] + len[i]);
-        }
         if (h < l) { l = 0; h = 0; }
         int rc;
         if ((rc = c.al_bytes.reserve((size_t)(h - l) + 16)) != AGX_OK) return rc;
@@ -464,16 +464,13 @@ int sw_align_shard(DeviceCtx &c, const uint8_t *seqs, const int64_t *off, const 
         if ((rc = c.al_scores.reserve((size_t)m * sizeof(int32_t))) != AGX_OK) return rc;
         if ((rc = c.al_ends.reserve((size_t)m * 2 * sizeof(int32_t))) != AGX_OK) return rc;
         if (mode == 2 && (rc = c.al_coords.reserve((size_t)m * 4 * sizeof(int32_t))) != AGX_OK) return rc;
-        if ((rc = c.h_al_off.reserve((size_t)m * 2 * sizeof(int64_t))) != AGX_OK) return rc;
-        // the sequence bytes first: their upload runs while the host rebases the offsets
+        // only the bytes [l, h) are resident; the offsets go up as they are and the kernels address a biased base
         AGX_CUDA(cudaMemcpyAsync(c.al_bytes.p, seqs + l, (size_t)(h - l), cudaMemcpyHostToDevice, st));
-        int64_t *roff = c.h_al_off.as<int64_t>();
-        for (int64_t i = 0; i < 2 * m; ++i) roff[i] = off[2 * q0 + i] - l;       // offsets relative to the uploaded range
-        AGX_CUDA(cudaMemcpyAsync(c.al_off.p, roff, (size_t)m * 2 * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        AGX_CUDA(cudaMemcpyAsync(c.al_off.p, off + 2 * q0, (size_t)m * 2 * sizeof(int64_t), cudaMemcpyHostToDevice, st));
         AGX_CUDA(cudaMemcpyAsync(c.al_len.p, len + 2 * q0, (size_t)m * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         if (trace) { cudaStreamSynchronize(st); fprintf(stderr, "[agx align] +%.2f ms: uploaded\n", now() - t_begin); }
         int64_t total = 0;
-        rc = sw_align_run_device(c.align, c.al_bytes.as<uint8_t>(), c.al_off.as<int64_t>(), c.al_len.as<int32_t>(), m, sc,
+        rc = sw_align_run_device(c.align, biased(c.al_bytes.p, l), c.al_off.as<int64_t>(), c.al_len.as<int32_t>(), m, sc,
                                  mode, budget, c.al_scores.as<int32_t>(), c.al_ends.as<int32_t>(),
                                  c.al_coords.as<int32_t>(), &total, st);
         if (rc == AGX_ENOMEM && mode == 2 && m > 1 && shrink < 24) { ++shrink; continue; }   // the bound was too optimistic
