@@ -197,3 +197,22 @@ def test_alignments_are_sharded_over_all_gpus(agx, multi, oracle_mod):
         b = raw[inp.off[2 * p + 1]:inp.off[2 * p + 1] + inp.len[2 * p + 1]]
         ws, wc, wg = oracle_mod.sw_align(a, b)
         assert (ws, list(wc), wg) == (int(scores[p]), coords[p].tolist(), cig[coff[p]:coff[p + 1]].tolist())
+
+
+@pytest.mark.parametrize("n,related", [(20000, True), (22000, False)])
+def test_long_alignment_end_cell_across_gpus(agx, multi, oracle_mod, n, related):
+    """sw_ends_batch_flat on a whole-GPU pair with several GPUs bound: column stripes over the GPUs, the END CELL is
+    the maximum of the per-GPU 64-bit keys (global columns); both orientations of the pair."""
+    cap, ngpu = multi
+    data = agx.synth.sw_long_pair(n, seed=n + 3, related=related)
+    inp = agx.formats.parse_sw(data, line_buf=1 << 30)
+    raw = inp.buf.tobytes()
+    a = raw[inp.off[0]:inp.off[0] + inp.len[0]]
+    b = raw[inp.off[1]:inp.off[1] + inp.len[1]][:-1 - 7]          # a little shorter, no newline: line 2 becomes sx
+    for x, y in ((a, b), (b, a)):
+        buf = np.frombuffer(x + y, np.uint8)
+        off = np.array([0, len(x)], np.int64)
+        ln = np.array([len(x), len(y)], np.int32)
+        scores, ends = cap.sw_ends_flat(buf, off, ln)
+        ws, we = oracle_mod.sw_ends(x, y)
+        assert (int(scores[0]), tuple(ends[0].tolist())) == (ws, we)
