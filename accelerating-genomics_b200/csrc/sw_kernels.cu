@@ -42,13 +42,10 @@ __host__ __device__ constexpr DuoClass duo_class(int c)
     // 256 and 512 columns: K = 16 on wider sub-warps instead of K = 32 (255 registers, two CTAs per SM) -- measured
     // 5598 -> 5783 and 5341 -> 5688 GCUPS (450-500 bp pairs: 4873 -> 5201); for 192 and 384 columns the narrower
     // sub-warp with K = 24 stays ahead of {16,12} / {32,12} (profiles/r2t_bench_*.json)
-#if defined(AGX_DUO_TABLE) && AGX_DUO_TABLE == 2
+    // up to 64 columns: FOUR lanes per pair of pairs (3 steps of systolic skew instead of 7 on 24 .. 64 rows): 32 bp
+    // 3208 -> 3813, 64 bp 4588 -> 5147 GCUPS (profiles/r2ao_bench_*.json)
     constexpr DuoClass t[SW_N_DUO_CLASSES] = {{4, 8},   {4, 16},  {8, 12},  {8, 16},  {8, 19}, {8, 24},
                                               {16, 16}, {16, 24}, {32, 16}, {32, 24}, {32, 32}};
-#else
-    constexpr DuoClass t[SW_N_DUO_CLASSES] = {{8, 4},   {8, 8},   {8, 12},  {8, 16},  {8, 19}, {8, 24},
-                                              {16, 16}, {16, 24}, {32, 16}, {32, 24}, {32, 32}};
-#endif
     return t[c];
 }
 __host__ __device__ constexpr int duo_cap(int c) { return duo_class(c).g * duo_class(c).k; }

@@ -158,7 +158,8 @@ int sw_score_shards_device(const agx_sw_shard *shards, int32_t n_shards,
  * A whole-GPU pair (>= 2^28 cells with a shorter side above 1024, see sw_score_batch) gets its end cell from the
  * striped long-alignment kernel over every configured GPU, like its score; that needs both lines <= 2^21 - 1 symbols
  * made of at most 7 distinct bytes (else AGX_ERANGE).  Other limits (AGX_ERANGE): match - (gap_open + gap_extend),
- * -mismatch, -(gap_open + gap_extend) <= 127. */
+ * -mismatch, -(gap_open + gap_extend) <= 127; every other pair: shorter line <= 16000 symbols, the two lengths
+ * adding up to less than 2^29. */
 int sw_ends_batch_flat(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *off, const int32_t *len,
                        int64_t n_pairs, int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend,
                        int32_t *scores_out, int32_t *ends_out);
