@@ -80,6 +80,11 @@ __device__ __forceinline__ int32_t add_fma(int32_t a, int32_t b, int32_t one)
 #define AGX_LONG_UNROLL 2
 #endif
 constexpr int LONG_UNROLL = AGX_LONG_UNROLL;
+// row steps of sw_longr_kernel per loop trip
+#ifndef AGX_LONGR_UNROLL
+#define AGX_LONGR_UNROLL 1
+#endif
+constexpr int LONGR_UNROLL = AGX_LONGR_UNROLL;
 
 // A boundary entry may be (re)written by another SM or by a peer GPU while it is polled: relaxed (strong)
 // accesses at the narrowest scope that covers writer and reader -- .gpu inside one GPU, .sys across NVLink.
@@ -445,7 +450,7 @@ sw_longr_kernel(LongArgs g)
                 lds_vec<R>(&r_g[wib][sl0], bg);
                 lds_vec<R>(&r_e[wib][sl0], be);
             }
-#pragma unroll 1
+#pragma unroll LONGR_UNROLL
             for (int u = 0; u < send; ++u) {
                 const int s = s0 + u;
                 if (u == half && !left_edge) {
