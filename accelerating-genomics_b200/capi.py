@@ -29,6 +29,7 @@ SYMBOLS = [
     "agx_pairhmm_set_gatk_mode", "agx_pairhmm_set_force_fp64", "agx_pairhmm_rescue_count",
     "sw_score_shards_device", "pairhmm_forward_shards_device",
     "sw_ends_batch_flat", "sw_align_batch_flat", "sw_ends_batch", "sw_align_batch",
+    "sw_ends_batch_device", "sw_align_batch_device",
 ]
 
 # the reference's scoring constants, antidiagonalSmithWaterman.c:40-43
@@ -101,6 +102,12 @@ def load_library() -> C.CDLL:
     lib.sw_align_batch_flat.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_int32] * 4 + \
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
     lib.sw_align_batch_flat.restype = C.c_int
+    lib.sw_ends_batch_device.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_int32] * 4 + \
+        [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sw_ends_batch_device.restype = C.c_int
+    lib.sw_align_batch_device.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_int32] * 4 + \
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]
+    lib.sw_align_batch_device.restype = C.c_int
     lib.sw_ends_batch.argtypes = [pp, i32p, pp, i32p, C.c_int64] + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p]
     lib.sw_ends_batch.restype = C.c_int
     lib.sw_align_batch.argtypes = [pp, i32p, pp, i32p, C.c_int64] + [C.c_int32] * 4 + \
@@ -354,6 +361,24 @@ def sw_score_device(device: int, d_seqs: int, seqs_bytes: int, d_off: int, d_len
     _check(load_library().sw_score_batch_device(int(device), d_seqs, int(seqs_bytes), d_off, d_len,
                                                 int(n_pairs), *[int(s) for s in scoring], d_scores,
                                                 stream or None))
+
+
+def sw_ends_device(device: int, d_seqs: int, seqs_bytes: int, d_off: int, d_len: int, n_pairs: int, d_scores: int, d_ends: int,
+                   stream: int = 0, scoring=(SW_MATCH, SW_MISMATCH, SW_GAP_OPEN, SW_GAP_EXTEND)) -> None:
+    """sw_ends_batch_device: raw device pointers"""
+    _check(load_library().sw_ends_batch_device(int(device), d_seqs, int(seqs_bytes), d_off, d_len, int(n_pairs),
+                                               *[int(s) for s in scoring], d_scores, d_ends, stream or None))
+
+
+def sw_align_device(device: int, d_seqs: int, seqs_bytes: int, d_off: int, d_len: int, n_pairs: int, d_scores: int, d_coords: int,
+                    d_cigar_off: int, d_cigar: int, cigar_cap: int, stream: int = 0,
+                    scoring=(SW_MATCH, SW_MISMATCH, SW_GAP_OPEN, SW_GAP_EXTEND)) -> int:
+    """sw_align_batch_device: raw device pointers; returns the number of CIGAR runs of the batch"""
+    total = C.c_int64(0)
+    _check(load_library().sw_align_batch_device(int(device), d_seqs, int(seqs_bytes), d_off, d_len, int(n_pairs),
+                                                *[int(s) for s in scoring], d_scores, d_coords, d_cigar_off, d_cigar,
+                                                int(cigar_cap), C.byref(total), stream or None))
+    return int(total.value)
 
 
 # ------------------------------------------------------------------------------- PairHMM

@@ -136,6 +136,7 @@ struct DeviceCtx {
     HmmParseWorkspace hmm_parse, hmm_parse_b;
     DevBuf d_bytes, d_a, d_b, d_c, d_d, d_e, d_f, d_out;   // staging for the host entry points
     SwAlignWorkspace align;                                 // sw_ends_* / sw_align_*
+    int64_t align_free = 0;                                 // free device memory + what the alignment scratch holds, as last asked
     DevBuf al_bytes, al_off, al_len, al_scores, al_ends, al_coords, al_cigar;
     PinBuf h_al_off, h_al_res;
     PinBuf h_a, h_b, h_out;
@@ -400,6 +401,20 @@ int sw_flat_impl(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *off, co
     });
 }
 
+// Device memory the traceback matrices may count on: what is free + what the alignment scratch already holds.
+// cudaMemGetInfo() is not cheap (measured up to milliseconds next to a caching allocator), so the answer is kept
+// and asked again only after a call ran out of memory.
+int align_memory(DeviceCtx &c, bool refresh, int64_t *out)
+{
+    if (refresh || c.align_free == 0) {
+        size_t fr = 0, tot = 0;
+        AGX_CUDA(cudaMemGetInfo(&fr, &tot));
+        c.align_free = (int64_t)fr + c.align.cap_tb + c.align.cap_tb_gen;
+    }
+    *out = c.align_free;
+    return AGX_OK;
+}
+
 // ---------------------------------------------------------------- SW alignment (end cell / start cell / CIGAR)
 // One shard = a contiguous range of pairs on one GPU, cut into chunks whose H-byte matrices fit the budget.
 // mode 1: scores + ends; mode 2: + coords and CIGAR runs (appended to `cigar`, run offsets relative to the shard).
@@ -417,10 +432,10 @@ int sw_align_shard(DeviceCtx &c, const uint8_t *seqs, const int64_t *off, const 
     cudaStream_t st = c.stream;
     int64_t budget = (int64_t)8 << 30;
     if (mode == 2) {
-        size_t fr = 0, tot = 0;
-        AGX_CUDA(cudaMemGetInfo(&fr, &tot));
-        // what is free now + what the scratch already holds, half of it, at most 80 GiB
-        const int64_t avail = (int64_t)fr + c.align.cap_tb + c.align.cap_tb_gen;
+        // half of what is free + what the scratch already holds, at most 80 GiB
+        int64_t avail = 0;
+        int rc0 = align_memory(c, false, &avail);
+        if (rc0 != AGX_OK) return rc0;
         // (a bound, not an allocation: the scratch grows to what the chunks really take)
         budget = std::min<int64_t>(avail / 2, (int64_t)80 << 30);
         if (const char *e = getenv("AGX_ALIGN_TB_BYTES")) budget = std::max<long long>(atoll(e), 1 << 20);
@@ -473,7 +488,12 @@ int sw_align_shard(DeviceCtx &c, const uint8_t *seqs, const int64_t *off, const 
         rc = sw_align_run_device(c.align, biased(c.al_bytes.p, l), c.al_off.as<int64_t>(), c.al_len.as<int32_t>(), m, sc,
                                  mode, budget, c.al_scores.as<int32_t>(), c.al_ends.as<int32_t>(),
                                  c.al_coords.as<int32_t>(), &total, st);
-        if (rc == AGX_ENOMEM && mode == 2 && m > 1 && shrink < 24) { ++shrink; continue; }   // the bound was too optimistic
+        if (rc == AGX_ENOMEM && mode == 2 && m > 1 && shrink < 24) {     // the bound was too optimistic (or memory went elsewhere)
+            int64_t avail = 0;
+            if (align_memory(c, true, &avail) == AGX_OK && !getenv("AGX_ALIGN_TB_BYTES")) budget = std::min<int64_t>(avail / 2, (int64_t)80 << 30);
+            ++shrink;
+            continue;
+        }
         if (rc != AGX_OK) return rc;
         if (trace) fprintf(stderr, "[agx align] +%.2f ms: kernels done (%lld runs)\n", now() - t_begin, (long long)total);
         AGX_CUDA(cudaMemcpyAsync(out.scores + q0, c.al_scores.p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -1296,6 +1316,58 @@ int sw_score_batch_device(int32_t device, const uint8_t *d_seqs, int64_t seqs_by
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     return sw_run_device(c->sw, d_seqs, d_off, d_len, n_pairs, SwScoring{match, mismatch, gap_open, gap_extend},
                          d_scores_out, st);
+}
+
+// Device-resident alignment entry points (one GPU, everything a device pointer on `device`)
+int sw_ends_batch_device(int32_t device, const uint8_t *d_seqs, int64_t seqs_bytes, const int64_t *d_off,
+                         const int32_t *d_len, int64_t n_pairs, int32_t match, int32_t mismatch, int32_t gap_open,
+                         int32_t gap_extend, int32_t *d_scores_out, int32_t *d_ends_out, void *stream)
+{
+    (void)seqs_bytes;
+    if (n_pairs < 0) return fail(AGX_EINVAL, "sw ends: n_pairs < 0");
+    if (n_pairs == 0) return AGX_OK;
+    if (!d_seqs || !d_off || !d_len || !d_scores_out || !d_ends_out) return fail(AGX_EINVAL, "sw ends: null argument");
+    DeviceCtx *c = ctx_for_device(device);
+    if (!c) return fail(AGX_ENODEVICE, "sw_ends_batch_device: device " + std::to_string(device) + " was not passed to agx_init");
+    AGX_CUDA(cudaSetDevice(device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    return sw_align_run_device(c->align, d_seqs, d_off, d_len, n_pairs, SwScoring{match, mismatch, gap_open, gap_extend}, 1,
+                               0, d_scores_out, d_ends_out, nullptr, nullptr, st);
+}
+
+int sw_align_batch_device(int32_t device, const uint8_t *d_seqs, int64_t seqs_bytes, const int64_t *d_off,
+                          const int32_t *d_len, int64_t n_pairs, int32_t match, int32_t mismatch, int32_t gap_open,
+                          int32_t gap_extend, int32_t *d_scores_out, int32_t *d_coords_out, int64_t *d_cigar_off_out,
+                          uint32_t *d_cigar_out, int64_t cigar_cap, int64_t *cigar_total_out, void *stream)
+{
+    (void)seqs_bytes;
+    if (cigar_total_out) *cigar_total_out = 0;
+    if (n_pairs < 0) return fail(AGX_EINVAL, "sw align: n_pairs < 0");
+    if (n_pairs == 0) return AGX_OK;
+    if (!d_seqs || !d_off || !d_len || !d_scores_out || !d_coords_out || !d_cigar_off_out || (!d_cigar_out && cigar_cap > 0) ||
+        cigar_cap < 0)
+        return fail(AGX_EINVAL, "sw align: null argument");
+    DeviceCtx *c = ctx_for_device(device);
+    if (!c) return fail(AGX_ENODEVICE, "sw_align_batch_device: device " + std::to_string(device) + " was not passed to agx_init");
+    AGX_CUDA(cudaSetDevice(device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    // one chunk: the score matrices of the whole batch must fit what is free (else AGX_ENOMEM: cut the batch)
+    int rc;
+    if ((rc = c->al_ends.reserve((size_t)n_pairs * 2 * sizeof(int32_t))) != AGX_OK) return rc;
+    int64_t total = 0, avail = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if ((rc = align_memory(*c, attempt == 1, &avail)) != AGX_OK) return rc;
+        rc = sw_align_run_device(c->align, d_seqs, d_off, d_len, n_pairs, SwScoring{match, mismatch, gap_open, gap_extend}, 2,
+                                 avail - ((int64_t)1 << 30), d_scores_out, c->al_ends.as<int32_t>(), d_coords_out, &total, st);
+        if (rc != AGX_ENOMEM) break;            // out of memory against a remembered figure: ask again once
+    }
+    if (rc != AGX_OK) return rc;
+    AGX_CUDA(cudaMemcpyAsync(d_cigar_off_out, c->align.cig_off, (size_t)(n_pairs + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    if (cigar_total_out) *cigar_total_out = total;
+    if (total > cigar_cap)
+        return fail(AGX_ERANGE, "sw align: " + std::to_string(total) + " CIGAR runs do not fit cigar_cap = " + std::to_string(cigar_cap) +
+                                    " (scores, coordinates and offsets are complete)");
+    return sw_align_gather_device(c->align, n_pairs, d_cigar_out, st);
 }
 
 int sw_score_shards_device(const agx_sw_shard *shards, int32_t n_shards, int32_t match, int32_t mismatch,

@@ -24,6 +24,8 @@
 //                        additions on the FMA pipe) runs first; a pair with any other byte is redone by
 //                        the raw-byte pass, so '\n', 'N', lower case ... behave exactly as in the
 //                        reference (:332).
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -1049,6 +1051,12 @@ int sw_align_run_device(SwAlignWorkspace &ws, const uint8_t *d_seqs, const int64
     if (cigar_total) *cigar_total = 0;
     if (n_pairs == 0) return AGX_OK;
     if (n_pairs > (int64_t)1 << 30) return fail(AGX_ERANGE, "sw align: more than 2^30 pairs in one call");
+    const bool trace = getenv("AGX_ALIGN_TRACE") != nullptr;       // host-side timeline on stderr
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto mark = [&](const char *what) {
+        if (trace) fprintf(stderr, "[agx align run] +%.3f ms: %s\n",
+                           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(), what);
+    };
     if (!(sc.match > 0 && sc.mismatch < 0 && sc.gap_open <= 0 && sc.gap_extend < 0))
         return fail(AGX_ERANGE, "sw: scoring must satisfy match > 0 > mismatch, gap_open <= 0, gap_extend < 0");
     const int32_t goe = sc.gap_open + sc.gap_extend;
@@ -1094,6 +1102,7 @@ int sw_align_run_device(SwAlignWorkspace &ws, const uint8_t *d_seqs, const int64
     AGX_CUDA(cudaGetLastError());
     AGX_CUDA(cudaMemcpyAsync(ws.h_counters, ws.counters, CNT_A_WORDS * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     AGX_CUDA(cudaStreamSynchronize(st));
+    mark("length classes read back");
     if (ws.h_counters[CNT_A_BAD] > 0)
         return fail(AGX_ERANGE, "sw align: " + std::to_string(ws.h_counters[CNT_A_BAD]) +
                                     " pair(s) outside the supported range (whole-GPU pairs of >= 2^28 cells, a shorter "
@@ -1179,12 +1188,14 @@ int sw_align_run_device(SwAlignWorkspace &ws, const uint8_t *d_seqs, const int64
         AGX_CUDA(cudaGetLastError());
     }
     ws.prof_dp.end(st);
+    mark("DP kernels queued");
     if (mode != 2) return AGX_OK;
 
     // the walk: room for the runs of every pair, then one thread per pair
     if ((rc = device_exclusive_scan(ws.cap32, n_pairs, ws.tmp_off, ws.scan_tmp, ws.d_total + 1, st)) != AGX_OK) return rc;
     AGX_CUDA(cudaMemcpyAsync(ws.h_total + 1, ws.d_total + 1, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     AGX_CUDA(cudaStreamSynchronize(st));
+    mark("DP kernels done, run capacities scanned");
     if ((rc = grow(ws.tmp_ops, ws.cap_tmp, ws.h_total[1] + 16)) != AGX_OK) return rc;
     AGX_CUDA(cudaMemsetAsync(ws.d_total + 2, 0, sizeof(int64_t), st));
     ws.prof_walk.begin(st);
@@ -1205,6 +1216,7 @@ int sw_align_run_device(SwAlignWorkspace &ws, const uint8_t *d_seqs, const int64
     AGX_CUDA(cudaMemcpyAsync(ws.h_total + 2, ws.d_total + 2, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     AGX_CUDA(cudaMemcpyAsync(ws.h_total + 3, ws.cig_off + n_pairs, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     AGX_CUDA(cudaStreamSynchronize(st));
+    mark("walk done, runs scanned");
     if (ws.h_total[2] != 0) return fail(AGX_ECUDA, "sw align: the traceback walk lost its path (internal error)");
     if (cigar_total) *cigar_total = ws.h_total[3];
     return AGX_OK;

@@ -189,6 +189,18 @@ int sw_align_batch(const uint8_t *const *a, const int32_t *a_len, const uint8_t 
                    int32_t *scores_out, int32_t *coords_out, int64_t *cigar_off_out, uint32_t *cigar_out,
                    int64_t cigar_cap, int64_t *cigar_total_out);
 
+/* Device-resident variants for one GPU (every pointer a device pointer on `device`, work ordered on `stream`, see
+ * sw_score_batch_device).  The calls read small counters back to size their grids (a few stream synchronisations);
+ * sw_align_batch_device keeps the score matrices of the WHOLE batch at once (AGX_ENOMEM when they do not fit the free
+ * device memory: cut the batch) and returns *cigar_total_out on the host; whole-GPU pairs are refused (AGX_ERANGE). */
+int sw_ends_batch_device(int32_t device, const uint8_t *d_seqs, int64_t seqs_bytes, const int64_t *d_off,
+                         const int32_t *d_len, int64_t n_pairs, int32_t match, int32_t mismatch, int32_t gap_open,
+                         int32_t gap_extend, int32_t *d_scores_out, int32_t *d_ends_out, void *stream);
+int sw_align_batch_device(int32_t device, const uint8_t *d_seqs, int64_t seqs_bytes, const int64_t *d_off,
+                          const int32_t *d_len, int64_t n_pairs, int32_t match, int32_t mismatch, int32_t gap_open,
+                          int32_t gap_extend, int32_t *d_scores_out, int32_t *d_coords_out, int64_t *d_cigar_off_out,
+                          uint32_t *d_cigar_out, int64_t cigar_cap, int64_t *cigar_total_out, void *stream);
+
 /* ------------------------------------------------------------------ PairHMM forward */
 
 /* One batch: every read against every haplotype (the Cartesian loop of

@@ -270,3 +270,37 @@ def test_randomised_against_the_oracle(gpu_lib):
         gpu_lib.init(1)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert '"mismatches": 0' in r.stdout
+
+
+def test_device_resident_entry_points(agx, gpu_lib, oracle_mod):
+    """sw_ends_batch_device / sw_align_batch_device on torch tensors: equal to the host entry points"""
+    import torch
+    rng = np.random.default_rng(109)
+    a, b = _pairs(rng, 3000, 1, 300)
+    buf, off, ln = _flat(a, b)
+    n = len(a)
+    dev = torch.device("cuda", 0)
+    d_buf, d_off, d_len = (torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (buf, off, ln))
+    d_scores = torch.empty(n, dtype=torch.int32, device=dev)
+    d_ends = torch.empty((n, 2), dtype=torch.int32, device=dev)
+    d_coords = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    d_coff = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    d_cig = torch.empty(8 * n, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    gpu_lib.sw_ends_device(0, d_buf.data_ptr(), d_buf.numel(), d_off.data_ptr(), d_len.data_ptr(), n, d_scores.data_ptr(),
+                           d_ends.data_ptr(), st)
+    torch.cuda.synchronize(dev)
+    want_s, want_e = gpu_lib.sw_ends_flat(buf, off, ln)
+    assert np.array_equal(d_scores.cpu().numpy(), want_s) and np.array_equal(d_ends.cpu().numpy(), want_e)
+    total = gpu_lib.sw_align_device(0, d_buf.data_ptr(), d_buf.numel(), d_off.data_ptr(), d_len.data_ptr(), n, d_scores.data_ptr(),
+                                    d_coords.data_ptr(), d_coff.data_ptr(), d_cig.data_ptr(), d_cig.numel(), st)
+    torch.cuda.synchronize(dev)
+    ws, wc, wo, wg = gpu_lib.sw_align_flat(buf, off, ln)
+    assert total == wg.size
+    assert np.array_equal(d_scores.cpu().numpy(), ws) and np.array_equal(d_coords.cpu().numpy(), wc)
+    assert np.array_equal(d_coff.cpu().numpy(), wo)
+    assert np.array_equal(d_cig.cpu().numpy()[:total].view(np.uint32), wg)
+    with pytest.raises(agx.capi.AgxError) as e:
+        gpu_lib.sw_align_device(0, d_buf.data_ptr(), d_buf.numel(), d_off.data_ptr(), d_len.data_ptr(), n, d_scores.data_ptr(),
+                                d_coords.data_ptr(), d_coff.data_ptr(), d_cig.data_ptr(), 5, st)
+    assert e.value.code == -5
