@@ -334,10 +334,12 @@ def sw_score_batch(a: Sequence[bytes], b: Sequence[bytes],
 
 
 def sw_score_file_image(image, line_buf: int = 1000,
-                        scoring=(SW_MATCH, SW_MISMATCH, SW_GAP_OPEN, SW_GAP_EXTEND), max_pairs=None, out=None):
+                        scoring=(SW_MATCH, SW_MISMATCH, SW_GAP_OPEN, SW_GAP_EXTEND), max_pairs=None, out=None,
+                        copy: bool = True):
     """sw_score_file_image: the whole file image, chunked into fgets() lines on the GPU.
     Returns (scores, header, dangling_bytes).  `out` (int32, optionally pinned) receives the scores;
-    by default a buffer for `max_pairs` (or the worst case image_bytes / 2) is allocated."""
+    by default a buffer for `max_pairs` (or the worst case image_bytes / 2) is allocated.
+    copy=False returns a view of `out` (what the C caller sees) instead of a private copy."""
     img = np.frombuffer(image, dtype=np.uint8) if isinstance(image, (bytes, bytearray)) else _as(image, np.uint8)
     if out is None:
         cap = max(1, img.size // 2 + 2) if max_pairs is None else max(1, int(max_pairs))
@@ -351,7 +353,7 @@ def sw_score_file_image(image, line_buf: int = 1000,
                                               *[int(s) for s in scoring], _ptr(out), cap, C.byref(n),
                                               C.byref(header), C.byref(d_off), C.byref(d_len)))
     dangling = img[d_off.value:d_off.value + d_len.value].tobytes() if d_off.value >= 0 else b""
-    return out[:n.value].copy(), int(header.value), dangling
+    return (out[:n.value].copy() if copy else out[:n.value]), int(header.value), dangling
 
 
 def sw_score_device(device: int, d_seqs: int, seqs_bytes: int, d_off: int, d_len: int, n_pairs: int,

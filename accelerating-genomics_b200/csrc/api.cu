@@ -9,6 +9,7 @@
 #include <memory>
 #include <mutex>
 #include <thread>
+#include <deque>
 #include <vector>
 
 #include "common.cuh"
@@ -113,6 +114,14 @@ struct PinBuf {
     template <typename T> T *as() { return reinterpret_cast<T *>(p); }
 };
 
+// stream + scratch + staging buffers of one in-flight alignment chunk (sw_align_shard)
+struct AlignLane {
+    cudaStream_t st = nullptr;         // the context's stream / its second lane's stream
+    SwAlignWorkspace ws;
+    DevBuf bytes, off, len, scores, ends, coords, cigar;
+    int64_t pend_q0 = 0, pend_m = 0, pend_base = 0;   // chunk whose results are on their way home; its first run's index
+};
+
 // stream + workspace + staging buffers of one in-flight SW chunk
 struct SwLane {
     cudaStream_t st = nullptr;
@@ -135,10 +144,9 @@ struct DeviceCtx {
     HmmWorkspace hmm, hmm_b;                 // hmm_b / hmm_parse_b: second lane of pairhmm_forward_file_image
     HmmParseWorkspace hmm_parse, hmm_parse_b;
     DevBuf d_bytes, d_a, d_b, d_c, d_d, d_e, d_f, d_out;   // staging for the host entry points
-    SwAlignWorkspace align;                                 // sw_ends_* / sw_align_*
+    AlignLane al[2];                                        // sw_ends_* / sw_align_*: two chunks in flight
+    SwAlignWorkspace &align = al[0].ws;                     // (the device-resident entry points use the first)
     int64_t align_free = 0;                                 // free device memory + what the alignment scratch holds, as last asked
-    DevBuf al_bytes, al_off, al_len, al_scores, al_ends, al_coords, al_cigar;
-    PinBuf h_al_off, h_al_res;
     PinBuf h_a, h_b, h_out;
     std::string error;   // error raised on this device's worker thread
     std::string name;    // agx_device_name()
@@ -243,6 +251,48 @@ int require_init()
     return AGX_OK;
 }
 
+// Validates every (offset, length) of a flat batch before any device work and returns the longest sequence.
+// Branch-free passes over slices of the arrays, on up to four host threads for large batches (2 * 10^6 entries take
+// 1.3 ms on one core -- as long as a fifth of the batch takes the GPU).
+int validate_sequences(const char *what, int64_t seqs_bytes, const int64_t *off, const int32_t *len, int64_t n_seqs,
+                       int32_t *longest_out)
+{
+    struct Acc { int32_t longest = 0, shortest = 0; int64_t min_off = 0, max_end = 0; };
+    const int parts = n_seqs >= ((int64_t)1 << 19) ? 4 : 1;
+    Acc acc[4];
+    auto pass = [&](int k) {
+        Acc a;
+        for (int64_t i = n_seqs * k / parts, e = n_seqs * (k + 1) / parts; i < e; ++i) {
+            a.longest = std::max(a.longest, len[i]);
+            a.shortest = std::min(a.shortest, len[i]);
+            a.min_off = std::min(a.min_off, off[i]);
+            a.max_end = std::max(a.max_end, off[i] + len[i]);
+        }
+        acc[k] = a;
+    };
+    if (parts == 1) {
+        pass(0);
+    } else {
+        std::thread th[3];
+        for (int k = 1; k < parts; ++k) th[k - 1] = std::thread(pass, k);
+        pass(0);
+        for (int k = 1; k < parts; ++k) th[k - 1].join();
+    }
+    Acc t = acc[0];
+    for (int k = 1; k < parts; ++k) {
+        t.longest = std::max(t.longest, acc[k].longest);
+        t.shortest = std::min(t.shortest, acc[k].shortest);
+        t.min_off = std::min(t.min_off, acc[k].min_off);
+        t.max_end = std::max(t.max_end, acc[k].max_end);
+    }
+    if (t.shortest < 0 || t.min_off < 0 || t.max_end > seqs_bytes)
+        for (int64_t i = 0; i < n_seqs; ++i)
+            if (len[i] < 0 || off[i] < 0 || off[i] + len[i] > seqs_bytes)
+                return fail(AGX_EINVAL, std::string(what) + ": sequence " + std::to_string(i) + " lies outside the buffer");
+    *longest_out = t.longest;
+    return AGX_OK;
+}
+
 // ---------------------------------------------------------------- SW on one shard
 // One shard = a contiguous range of pairs on one GPU.  It is cut into chunks that alternate between the
 // context's two lanes (stream + workspace + staging buffers each): the host->device copy of chunk k+1 is
@@ -329,21 +379,10 @@ int sw_flat_impl(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *off, co
     if (n_pairs < 0) return fail(AGX_EINVAL, "sw: n_pairs < 0");
     if (n_pairs == 0) return AGX_OK;
     if (!seqs || !off || !len || !scores_out) return fail(AGX_EINVAL, "sw: null argument");
-    // one branch-free pass validates every (offset, length) before any device work
-    int32_t longest = 0, shortest = 0;
-    int64_t min_off = 0, max_end = 0;
-    for (int64_t i = 0; i < 2 * n_pairs; ++i) {
-        longest = std::max(longest, len[i]);
-        shortest = std::min(shortest, len[i]);
-        min_off = std::min(min_off, off[i]);
-        max_end = std::max(max_end, off[i] + len[i]);
-    }
-    if (shortest < 0 || min_off < 0 || max_end > seqs_bytes) {
-        for (int64_t i = 0; i < 2 * n_pairs; ++i)
-            if (len[i] < 0 || off[i] < 0 || off[i] + len[i] > seqs_bytes)
-                return fail(AGX_EINVAL, "sw: sequence " + std::to_string(i) + " lies outside the buffer");
-    }
-    int rc = require_init();
+    int32_t longest = 0;
+    int rc = validate_sequences("sw", seqs_bytes, off, len, 2 * n_pairs, &longest);
+    if (rc != AGX_OK) return rc;
+    rc = require_init();
     if (rc != AGX_OK) return rc;
 
     // very long alignments: one at a time, columns striped over every configured GPU (sw_long.cu)
@@ -409,7 +448,8 @@ int align_memory(DeviceCtx &c, bool refresh, int64_t *out)
     if (refresh || c.align_free == 0) {
         size_t fr = 0, tot = 0;
         AGX_CUDA(cudaMemGetInfo(&fr, &tot));
-        c.align_free = (int64_t)fr + c.align.cap_tb + c.align.cap_tb_gen;
+        c.align_free = (int64_t)fr;
+        for (const AlignLane &L : c.al) c.align_free += L.ws.cap_tb + L.ws.cap_tb_gen;
     }
     *out = c.align_free;
     return AGX_OK;
@@ -429,105 +469,194 @@ struct AlignOut {
 int sw_align_shard(DeviceCtx &c, const uint8_t *seqs, const int64_t *off, const int32_t *len, int64_t p0, int64_t p1,
                    SwScoring sc, int mode, AlignOut out)
 {
-    cudaStream_t st = c.stream;
+    // Two lanes (stream + scratch + staging buffers each) alternate over the chunks: chunk k+1 is cut and its upload
+    // queued BEFORE the host blocks on chunk k's kernels (the call returns the run total, so it waits for them), and
+    // chunk k's results travel home while chunk k+1 computes.  The host waits for a lane only when it comes back to
+    // it two chunks later.
+    AlignLane *lanes[2] = {&c.al[0], &c.al[1]};
+    lanes[0]->st = c.stream;
+    lanes[1]->st = c.lane[1].st;
+    const int64_t n = p1 - p0;
     int64_t budget = (int64_t)8 << 30;
-    if (mode == 2) {
-        // half of what is free + what the scratch already holds, at most 80 GiB
-        int64_t avail = 0;
-        int rc0 = align_memory(c, false, &avail);
-        if (rc0 != AGX_OK) return rc0;
+    auto tb_budget = [&](bool refresh) -> int {
+        if (mode != 2) return AGX_OK;
+        // a quarter of (what is free + what the scratch already holds) per lane, at most 40 GiB
         // (a bound, not an allocation: the scratch grows to what the chunks really take)
-        budget = std::min<int64_t>(avail / 2, (int64_t)80 << 30);
+        int64_t avail = 0;
+        int rc0 = align_memory(c, refresh, &avail);
+        if (rc0 != AGX_OK) return rc0;
+        budget = std::min<int64_t>(avail / 4, (int64_t)40 << 30);
         if (const char *e = getenv("AGX_ALIGN_TB_BYTES")) budget = std::max<long long>(atoll(e), 1 << 20);
+        return AGX_OK;
+    };
+    int rc = tb_budget(false);
+    if (rc != AGX_OK) return rc;
+    // pairs per chunk: a quarter of the shard, 64 Ki .. 256 Ki pairs (one chunk up to 64 Ki pairs); a short first
+    // chunk, to start computing earlier, was measured and loses to its own fixed costs (profiles/r2bc_*)
+    int64_t chunk_pairs = n <= 65536 ? n : std::min<int64_t>(262144, std::max<int64_t>(65536, (n + 3) / 4));
+    if (const char *e = getenv("AGX_ALIGN_CHUNK")) {         // tuning knob: pairs per chunk (0 = as many as fit)
+        const long long v = atoll(e);
+        chunk_pairs = v > 0 ? v : (int64_t)1 << 20;
     }
-    int64_t cig_base = 0;
-    int64_t q0 = p0;
     int shrink = 0;
     c.align.dp_ms_sum = c.align.walk_ms_sum = -1.0;
     const bool trace = getenv("AGX_ALIGN_TRACE") != nullptr;      // host-side timeline of the chunks on stderr
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = now();
-    while (q0 < p1) {
-        // chunk: at most 2^20 pairs and, in mode 2, matrices within the budget (the class layout rounds rows up to
-        // the longest of the class, so the per-pair bound is scaled by what the chunk's longest line adds); the same
-        // pass finds the byte range [l, h) the chunk's sequences lie in
-        int64_t q1 = q0, row_bytes = 0;
-        int32_t longest = 1;
-        int64_t l = INT64_MAX, h = 0;
-        while (q1 < p1 && q1 - q0 < ((int64_t)1 << 20) >> shrink) {
-            const int32_t la = len[2 * q1], lb = len[2 * q1 + 1];
-            if (mode == 2) {
-                const int32_t new_longest = std::max(longest, std::max(la, lb));
-                const int64_t grown = row_bytes + sw_align_tb_row_bytes(la, lb);
-                // every pair of a class is padded to the class's longest row sequence (+ the systolic skew)
-                if (q1 > q0 && (double)grown * (new_longest + 32) * 1.02 > (double)(budget >> shrink)) break;
-                row_bytes = grown;
-                longest = new_longest;
-            }
-            const int64_t oa = off[2 * q1], ob = off[2 * q1 + 1];
+
+    struct Chunk { int64_t q0, q1, l, h; };
+    // chunk: at most chunk_pairs pairs and, in mode 2, matrices within the budget (the class layout rounds rows up to
+    // the longest of the class, so the per-pair bound is scaled by what the chunk's longest line adds); the same
+    // pass finds the byte range [l, h) the chunk's sequences lie in
+    int32_t tb_cap = 0;
+    const int32_t *tb_tab = sw_align_tb_row_table(&tb_cap);
+    auto row_bytes_of = [&](int32_t la, int32_t lb) -> int64_t {
+        const int32_t ra = la > lb ? lb : la;
+        return ra <= tb_cap ? tb_tab[ra] : (int64_t)((ra + 255) / 256) * 256;
+    };
+    auto cut = [&](int64_t q0) {
+        Chunk ch{q0, q0, INT64_MAX, 0};
+        const int64_t most = std::max<int64_t>(1, chunk_pairs >> shrink);
+        const int64_t qe = std::min(p1, q0 + most);
+        // the usual case in one branch-free pass: all `most` pairs fit
+        int64_t rows = 0, l = INT64_MAX, h = 0;
+        int32_t lng = 1;
+        for (int64_t q = q0; q < qe; ++q) {
+            const int32_t la = len[2 * q], lb = len[2 * q + 1];
+            const int64_t oa = off[2 * q], ob = off[2 * q + 1];
+            if (mode == 2) rows += row_bytes_of(la, lb);
+            lng = std::max(lng, std::max(la, lb));
             l = std::min(l, std::min(oa, ob));
             h = std::max(h, std::max(oa + la, ob + lb));
-            ++q1;
         }
-        const int64_t m = q1 - q0;
-        if (trace) fprintf(stderr, "[agx align] +%.2f ms: chunk of %lld pairs cut\n", now() - t_begin, (long long)m);
-        if (h < l) { l = 0; h = 0; }
-        int rc;
-        if ((rc = c.al_bytes.reserve((size_t)(h - l) + 16)) != AGX_OK) return rc;
-        if ((rc = c.al_off.reserve((size_t)m * 2 * sizeof(int64_t))) != AGX_OK) return rc;
-        if ((rc = c.al_len.reserve((size_t)m * 2 * sizeof(int32_t))) != AGX_OK) return rc;
-        if ((rc = c.al_scores.reserve((size_t)m * sizeof(int32_t))) != AGX_OK) return rc;
-        if ((rc = c.al_ends.reserve((size_t)m * 2 * sizeof(int32_t))) != AGX_OK) return rc;
-        if (mode == 2 && (rc = c.al_coords.reserve((size_t)m * 4 * sizeof(int32_t))) != AGX_OK) return rc;
-        // only the bytes [l, h) are resident; the offsets go up as they are and the kernels address a biased base
-        AGX_CUDA(cudaMemcpyAsync(c.al_bytes.p, seqs + l, (size_t)(h - l), cudaMemcpyHostToDevice, st));
-        AGX_CUDA(cudaMemcpyAsync(c.al_off.p, off + 2 * q0, (size_t)m * 2 * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-        AGX_CUDA(cudaMemcpyAsync(c.al_len.p, len + 2 * q0, (size_t)m * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        if (trace) { cudaStreamSynchronize(st); fprintf(stderr, "[agx align] +%.2f ms: uploaded\n", now() - t_begin); }
-        int64_t total = 0;
-        rc = sw_align_run_device(c.align, biased(c.al_bytes.p, l), c.al_off.as<int64_t>(), c.al_len.as<int32_t>(), m, sc,
-                                 mode, budget, c.al_scores.as<int32_t>(), c.al_ends.as<int32_t>(),
-                                 c.al_coords.as<int32_t>(), &total, st);
-        if (rc == AGX_ENOMEM && mode == 2 && m > 1 && shrink < 24) {     // the bound was too optimistic (or memory went elsewhere)
-            int64_t avail = 0;
-            if (align_memory(c, true, &avail) == AGX_OK && !getenv("AGX_ALIGN_TB_BYTES")) budget = std::min<int64_t>(avail / 2, (int64_t)80 << 30);
-            ++shrink;
-            continue;
-        }
-        if (rc != AGX_OK) return rc;
-        if (trace) fprintf(stderr, "[agx align] +%.2f ms: kernels done (%lld runs)\n", now() - t_begin, (long long)total);
-        AGX_CUDA(cudaMemcpyAsync(out.scores + q0, c.al_scores.p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        if (out.ends)
-            AGX_CUDA(cudaMemcpyAsync(out.ends + 2 * q0, c.al_ends.p, (size_t)m * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        if (mode == 2) {
-            AGX_CUDA(cudaMemcpyAsync(out.coords + 4 * q0, c.al_coords.p, (size_t)m * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-            AGX_CUDA(cudaMemcpyAsync(out.cigar_off + (q0 - p0), c.align.cig_off, (size_t)(m + 1) * sizeof(int64_t),
-                                     cudaMemcpyDeviceToHost, st));
-            const bool fits = !out.cigar_direct || cig_base + total <= out.cigar_cap;
-            if (total > 0 && fits) {
-                if ((rc = c.al_cigar.reserve((size_t)total * sizeof(uint32_t))) != AGX_OK) return rc;
-                if ((rc = sw_align_gather_device(c.align, m, c.al_cigar.as<uint32_t>(), st)) != AGX_OK) return rc;
-                uint32_t *dst = out.cigar_direct ? out.cigar_direct + cig_base : nullptr;
-                if (!dst) {
-                    const size_t at = out.cigar->size();
-                    out.cigar->resize(at + (size_t)total);
-                    dst = out.cigar->data() + at;
-                }
-                AGX_CUDA(cudaMemcpyAsync(dst, c.al_cigar.p, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        if (mode != 2 || qe - q0 <= 1 || (double)rows * (lng + 32) * 1.02 <= (double)(budget >> shrink)) {
+            ch.q1 = qe; ch.l = l; ch.h = h;
+        } else {
+            int64_t row_bytes = 0;
+            int32_t longest_c = 1;
+            while (ch.q1 < qe) {
+                const int32_t la = len[2 * ch.q1], lb = len[2 * ch.q1 + 1];
+                const int32_t new_longest = std::max(longest_c, std::max(la, lb));
+                const int64_t grown = row_bytes + row_bytes_of(la, lb);
+                // every pair of a class is padded to the class's longest row sequence (+ the systolic skew)
+                if (ch.q1 > q0 && (double)grown * (new_longest + 32) * 1.02 > (double)(budget >> shrink)) break;
+                row_bytes = grown;
+                longest_c = new_longest;
+                const int64_t oa = off[2 * ch.q1], ob = off[2 * ch.q1 + 1];
+                ch.l = std::min(ch.l, std::min(oa, ob));
+                ch.h = std::max(ch.h, std::max(oa + la, ob + lb));
+                ++ch.q1;
             }
-            AGX_CUDA(cudaStreamSynchronize(st));
-            for (int64_t i = 0; i <= m; ++i) out.cigar_off[(q0 - p0) + i] += cig_base;
-            cig_base += total;
         }
-        AGX_CUDA(cudaStreamSynchronize(st));
-        if (trace) fprintf(stderr, "[agx align] +%.2f ms: results on the host\n", now() - t_begin);
+        if (ch.h < ch.l) { ch.l = 0; ch.h = 0; }
+        return ch;
+    };
+    // results of a lane's previous chunk: wait for them; run offsets of later chunks are rebased on the host
+    auto drain = [&](AlignLane &L) -> int {
+        if (L.pend_m == 0) return AGX_OK;
+        AGX_CUDA(cudaStreamSynchronize(L.st));
+        if (mode == 2 && L.pend_base != 0)
+            for (int64_t i = 0; i < L.pend_m; ++i) out.cigar_off[(L.pend_q0 - p0) + i] += L.pend_base;
         if (g_profiling.load()) {
-            const double d = c.align.prof_dp.ms(), w = mode == 2 ? c.align.prof_walk.ms() : -1.0;
+            const double d = L.ws.prof_dp.ms(), w = mode == 2 ? L.ws.prof_walk.ms() : -1.0;
             if (d >= 0) c.align.dp_ms_sum = std::max(c.align.dp_ms_sum, 0.0) + d;
             if (w >= 0) c.align.walk_ms_sum = std::max(c.align.walk_ms_sum, 0.0) + w;
         }
-        q0 = q1;
+        if (trace) fprintf(stderr, "[agx align] +%.2f ms: results of pairs [%lld, %lld) on the host\n", now() - t_begin,
+                           (long long)L.pend_q0, (long long)(L.pend_q0 + L.pend_m));
+        L.pend_m = 0;
+        return AGX_OK;
+    };
+    // (no host wait: the uploads queue up behind the lane's previous results on their way home)
+    auto stage = [&](AlignLane &L, const Chunk &ch) -> int {
+        int r;
+        const int64_t m = ch.q1 - ch.q0;
+        if ((r = L.bytes.reserve((size_t)(ch.h - ch.l) + 16)) != AGX_OK) return r;
+        if ((r = L.off.reserve((size_t)m * 2 * sizeof(int64_t))) != AGX_OK) return r;
+        if ((r = L.len.reserve((size_t)m * 2 * sizeof(int32_t))) != AGX_OK) return r;
+        if ((r = L.scores.reserve((size_t)m * sizeof(int32_t))) != AGX_OK) return r;
+        if ((r = L.ends.reserve((size_t)m * 2 * sizeof(int32_t))) != AGX_OK) return r;
+        if (mode == 2 && (r = L.coords.reserve((size_t)m * 4 * sizeof(int32_t))) != AGX_OK) return r;
+        // only the bytes [l, h) are resident; the offsets go up as they are and the kernels address a biased base
+        AGX_CUDA(cudaMemcpyAsync(L.bytes.p, seqs + ch.l, (size_t)(ch.h - ch.l), cudaMemcpyHostToDevice, L.st));
+        AGX_CUDA(cudaMemcpyAsync(L.off.p, off + 2 * ch.q0, (size_t)m * 2 * sizeof(int64_t), cudaMemcpyHostToDevice, L.st));
+        AGX_CUDA(cudaMemcpyAsync(L.len.p, len + 2 * ch.q0, (size_t)m * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, L.st));
+        if (trace) fprintf(stderr, "[agx align] +%.2f ms: pairs [%lld, %lld) cut, upload queued\n", now() - t_begin,
+                           (long long)ch.q0, (long long)ch.q1);
+        return AGX_OK;
+    };
+
+    std::deque<std::vector<uint32_t>> parts;          // several GPUs: the runs of every chunk, joined at the end
+    int64_t cig_base = 0;
+    int li = 0;
+    c.al[0].pend_m = c.al[1].pend_m = 0;
+    Chunk cur = cut(p0), pre{p1, p1, 0, 0};
+    bool pre_ok = false;
+    if ((rc = stage(*lanes[li], cur)) != AGX_OK) return rc;
+    while (cur.q0 < p1) {
+        AlignLane &L = *lanes[li];
+        const int64_t m = cur.q1 - cur.q0;
+        if ((rc = drain(L)) != AGX_OK) return rc;      // the chunk before last (long home by now): offsets, profiling spans
+        Chunk nxt{p1, p1, 0, 0};
+        if (cur.q1 < p1) {
+            nxt = (pre_ok && pre.q0 == cur.q1) ? pre : cut(cur.q1);
+            if ((rc = stage(*lanes[li ^ 1], nxt)) != AGX_OK) return rc;
+        }
+        // the chunk after next is cut by a helper thread while this one computes (the host is about to block)
+        pre_ok = false;
+        std::thread helper;
+        if (nxt.q1 < p1) helper = std::thread([&cut, &pre, q = nxt.q1] { pre = cut(q); });
+        int64_t total = 0;
+        rc = sw_align_run_device(L.ws, biased(L.bytes.p, cur.l), L.off.as<int64_t>(), L.len.as<int32_t>(), m, sc, mode, budget,
+                                 L.scores.as<int32_t>(), L.ends.as<int32_t>(), L.coords.as<int32_t>(), &total, L.st);
+        if (helper.joinable()) { helper.join(); pre_ok = rc == AGX_OK; }     // (cut with this shrink / budget)
+        if (rc == AGX_ENOMEM && mode == 2 && m > 1 && shrink < 24) {     // the bound was too optimistic (or memory went elsewhere)
+            if ((rc = tb_budget(true)) != AGX_OK) return rc;
+            ++shrink;
+            cur = cut(cur.q0);               // (the chunk staged on the other lane is cut again after this one)
+            if ((rc = stage(L, cur)) != AGX_OK) return rc;
+            continue;
+        }
+        if (rc != AGX_OK) return rc;
+        if (trace) fprintf(stderr, "[agx align] +%.2f ms: kernels of pairs [%lld, %lld) done (%lld runs)\n", now() - t_begin,
+                           (long long)cur.q0, (long long)cur.q1, (long long)total);
+        AGX_CUDA(cudaMemcpyAsync(out.scores + cur.q0, L.scores.p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, L.st));
+        if (out.ends)
+            AGX_CUDA(cudaMemcpyAsync(out.ends + 2 * cur.q0, L.ends.p, (size_t)m * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, L.st));
+        if (mode == 2) {
+            AGX_CUDA(cudaMemcpyAsync(out.coords + 4 * cur.q0, L.coords.p, (size_t)m * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, L.st));
+            // (m entries: the entry after them belongs to the next chunk, or is the shard's total set below)
+            AGX_CUDA(cudaMemcpyAsync(out.cigar_off + (cur.q0 - p0), L.ws.cig_off, (size_t)m * sizeof(int64_t),
+                                     cudaMemcpyDeviceToHost, L.st));
+            const bool fits = !out.cigar_direct || cig_base + total <= out.cigar_cap;
+            if (total > 0 && fits) {
+                if ((rc = L.cigar.reserve((size_t)total * sizeof(uint32_t))) != AGX_OK) return rc;
+                if ((rc = sw_align_gather_device(L.ws, m, L.cigar.as<uint32_t>(), L.st)) != AGX_OK) return rc;
+                uint32_t *dst = out.cigar_direct ? out.cigar_direct + cig_base : nullptr;
+                if (!dst) {
+                    parts.emplace_back((size_t)total);
+                    dst = parts.back().data();
+                }
+                AGX_CUDA(cudaMemcpyAsync(dst, L.cigar.p, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost, L.st));
+            }
+        }
+        L.pend_q0 = cur.q0;
+        L.pend_m = m;
+        L.pend_base = cig_base;
+        cig_base += total;
+        cur = nxt;
+        li ^= 1;
     }
+    if ((rc = drain(c.al[0])) != AGX_OK) return rc;
+    if ((rc = drain(c.al[1])) != AGX_OK) return rc;
+    if (mode == 2) {
+        out.cigar_off[n] = cig_base;
+        if (!out.cigar_direct) {
+            out.cigar->reserve(out.cigar->size() + (size_t)cig_base);
+            for (auto &v : parts) out.cigar->insert(out.cigar->end(), v.begin(), v.end());
+        }
+    }
+    if (trace) fprintf(stderr, "[agx align] +%.2f ms: shard done\n", now() - t_begin);
     return AGX_OK;
 }
 
@@ -542,17 +671,19 @@ int sw_align_impl(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *off, c
     if (mode == 1 && !ends_out) return fail(AGX_EINVAL, "sw ends: null argument");
     if (mode == 2 && (!coords_out || !cigar_off_out || (!cigar_out && cigar_cap > 0) || cigar_cap < 0))
         return fail(AGX_EINVAL, "sw align: null argument");
-    for (int64_t i = 0; i < 2 * n_pairs; ++i)
-        if (len[i] < 0 || off[i] < 0 || off[i] + len[i] > seqs_bytes)
-            return fail(AGX_EINVAL, "sw align: sequence " + std::to_string(i) + " lies outside the buffer");
-    int rc = require_init();
+    int32_t longest = 0;
+    int rc = validate_sequences("sw align", seqs_bytes, off, len, 2 * n_pairs, &longest);
+    if (rc != AGX_OK) return rc;
+    rc = require_init();
     if (rc != AGX_OK) return rc;
     if (mode == 1) {
         // whole-GPU pairs: score and end cell from the striped long-alignment kernel, one pair at a time over every
         // configured GPU (the traceback of such a pair would need its 10^12-cell matrix: mode 2 refuses them)
         std::vector<int64_t> giants;
-        for (int64_t p = 0; p < n_pairs; ++p)
-            if ((int64_t)len[2 * p] * (int64_t)len[2 * p + 1] >= sw_long_cells() && std::min(len[2 * p], len[2 * p + 1]) > 1025)
+        const int64_t long_cells = sw_long_cells();
+        const bool maybe_giant = (int64_t)longest * (int64_t)longest >= long_cells && longest > 1025;
+        for (int64_t p = 0; maybe_giant && p < n_pairs; ++p)
+            if ((int64_t)len[2 * p] * (int64_t)len[2 * p + 1] >= long_cells && std::min(len[2 * p], len[2 * p + 1]) > 1025)
                 giants.push_back(p);
         if (!giants.empty()) {
             if (!(sc.match > 0 && sc.mismatch < 0 && sc.gap_open <= 0 && sc.gap_extend < 0))
@@ -884,10 +1015,12 @@ void agx_shutdown(void)
         hmm_workspace_free(c->hmm_b);
         hmm_parse_workspace_free(c->hmm_parse);
         hmm_parse_workspace_free(c->hmm_parse_b);
-        for (DevBuf *b : {&c->d_bytes, &c->d_a, &c->d_b, &c->d_c, &c->d_d, &c->d_e, &c->d_f, &c->d_out, &c->al_bytes, &c->al_off,
-                          &c->al_len, &c->al_scores, &c->al_ends, &c->al_coords, &c->al_cigar}) b->release();
-        for (PinBuf *b : {&c->h_a, &c->h_b, &c->h_out, &c->h_al_off, &c->h_al_res}) b->release();
-        sw_align_workspace_free(c->align);
+        for (DevBuf *b : {&c->d_bytes, &c->d_a, &c->d_b, &c->d_c, &c->d_d, &c->d_e, &c->d_f, &c->d_out}) b->release();
+        for (PinBuf *b : {&c->h_a, &c->h_b, &c->h_out}) b->release();
+        for (AlignLane &L : c->al) {
+            for (DevBuf *b : {&L.bytes, &L.off, &L.len, &L.scores, &L.ends, &L.coords, &L.cigar}) b->release();
+            sw_align_workspace_free(L.ws);
+        }
         if (c->stream) cudaStreamDestroy(c->stream);
     }
     g_ctx.clear();
@@ -1130,17 +1263,17 @@ int sw_score_file_image(const uint8_t *image, int64_t image_bytes, int32_t line_
     // ---- upload in segments, one event per segment ------------------------------------------------
     // Every region costs the host three stream round trips (newline count, chunk count, length-class
     // counts: ~0.3 ms in all), so regions must be few and none shorter than the ~16 MiB that arrive in
-    // that time; what is left to do when the last byte lands is one region, so the last ones are short:
-    // eighths of the image first, then half of what is left each time.
+    // that time; what is left to do when the last byte lands is one region, so they must not be long either:
+    // about eleven equal segments, 16 .. 32 MiB.  Segment boundaries are multiples of 1 MiB: a copy that starts
+    // at an odd byte runs visibly slower (image / 8 = an odd size cost 0.35 ms per 302 MB, profiles/r2ay_*).
     std::vector<int64_t> seg_end;
     {
-        const int64_t floor_sz = (int64_t)16 << 20;
-        int64_t fixed = 0;
-        if (const char *e = getenv("AGX_SW_IMAGE_SEGMENT")) fixed = atoll(e);   // tuning knob: bytes per segment
+        const int64_t mib = (int64_t)1 << 20;
+        int64_t uniform = std::max(16 * mib, std::min(32 * mib, image_bytes / 11 / mib * mib));
+        if (const char *e = getenv("AGX_SW_IMAGE_SEGMENT")) uniform = std::max<int64_t>(atoll(e), 4096);   // tuning knob
         for (int64_t pos = 0; pos < image_bytes;) {
             const int64_t left = image_bytes - pos;
-            int64_t sz = fixed > 0 ? fixed : std::max(floor_sz, std::min(image_bytes / 8, left / 2));
-            if (left - sz < floor_sz / 2) sz = left;
+            const int64_t sz = left - uniform < uniform / 2 ? left : uniform;
             pos += sz;
             seg_end.push_back(pos);
         }
@@ -1155,6 +1288,9 @@ int sw_score_file_image(const uint8_t *image, int64_t image_bytes, int32_t line_
     // stages through the driver and blocks the host, so stay one segment ahead of the region being scored
     cudaPointerAttributes img_attr;
     const bool img_pinned = cudaPointerGetAttributes(&img_attr, image) == cudaSuccess && img_attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    cudaPointerAttributes out_attr;
+    const bool out_pinned = cudaPointerGetAttributes(&out_attr, scores_out) == cudaSuccess && out_attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
     int64_t queued = 0;
     auto upload_through = [&](int64_t k_last) -> int {
@@ -1212,6 +1348,10 @@ int sw_score_file_image(const uint8_t *image, int64_t image_bytes, int32_t line_
             rc = sw_run_device(ctx.lane[li].ws, L.bytes.as<uint8_t>(), d_off, d_len, m, sc,
                                L.out.as<int32_t>() + pairs_done, st, prep);
             if (rc != AGX_OK) break;
+            // pinned result array: every region's scores go home behind its own DP kernels
+            if (out_pinned)
+                AGX_CUDA(cudaMemcpyAsync(scores_out + pairs_done, L.out.as<int32_t>() + pairs_done, (size_t)m * sizeof(int32_t),
+                                         cudaMemcpyDeviceToHost, st));
         }
         AGX_CUDA(cudaEventRecord(ctx.lane_done[li], st));
         if (trace)
@@ -1233,12 +1373,8 @@ int sw_score_file_image(const uint8_t *image, int64_t image_bytes, int32_t line_
     }
     AGX_CUDA(cudaStreamSynchronize(ctx.lane[1].st));
     if (pairs_done > 0) {
-        cudaPointerAttributes attr;
-        const bool pinned = cudaPointerGetAttributes(&attr, scores_out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-        cudaGetLastError();
-        if (pinned) {
-            AGX_CUDA(cudaMemcpyAsync(scores_out, L.out.p, (size_t)pairs_done * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-            AGX_CUDA(cudaStreamSynchronize(st));
+        if (out_pinned) {
+            AGX_CUDA(cudaStreamSynchronize(st));           // (copied region by region)
         } else {
             if ((rc = L.h_out.reserve((size_t)pairs_done * sizeof(int32_t))) != AGX_OK) return rc;
             AGX_CUDA(cudaMemcpyAsync(L.h_out.p, L.out.p, (size_t)pairs_done * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -1353,12 +1489,12 @@ int sw_align_batch_device(int32_t device, const uint8_t *d_seqs, int64_t seqs_by
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     // one chunk: the score matrices of the whole batch must fit what is free (else AGX_ENOMEM: cut the batch)
     int rc;
-    if ((rc = c->al_ends.reserve((size_t)n_pairs * 2 * sizeof(int32_t))) != AGX_OK) return rc;
+    if ((rc = c->al[0].ends.reserve((size_t)n_pairs * 2 * sizeof(int32_t))) != AGX_OK) return rc;
     int64_t total = 0, avail = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
         if ((rc = align_memory(*c, attempt == 1, &avail)) != AGX_OK) return rc;
         rc = sw_align_run_device(c->align, d_seqs, d_off, d_len, n_pairs, SwScoring{match, mismatch, gap_open, gap_extend}, 2,
-                                 avail - ((int64_t)1 << 30), d_scores_out, c->al_ends.as<int32_t>(), d_coords_out, &total, st);
+                                 avail - ((int64_t)1 << 30), d_scores_out, c->al[0].ends.as<int32_t>(), d_coords_out, &total, st);
         if (rc != AGX_ENOMEM) break;            // out of memory against a remembered figure: ask again once
     }
     if (rc != AGX_OK) return rc;

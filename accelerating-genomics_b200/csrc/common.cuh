@@ -125,6 +125,8 @@ int sw_align_gather_device(SwAlignWorkspace &ws, int64_t n_pairs, uint32_t *d_ci
 void sw_align_workspace_free(SwAlignWorkspace &ws);
 // bytes per row of the H-byte matrix one pair can take (host-side chunking)
 int64_t sw_align_tb_row_bytes(int32_t len_a, int32_t len_b);
+// the table behind it, indexed by the shorter length up to *max_len (beyond: 256-byte stripes)
+const int32_t *sw_align_tb_row_table(int32_t *max_len);
 
 // Per-call device scratch for the SW path (owned by the device context).
 struct SwWorkspace {

@@ -1023,11 +1023,12 @@ void sw_align_workspace_free(SwAlignWorkspace &ws)
     ws = SwAlignWorkspace();
 }
 
-int64_t sw_align_tb_row_bytes(int32_t len_a, int32_t len_b)
+// bytes per ROW of the larger of the two layouts a pair can end up in: its duo class (half a duo: K2 words x 2
+// bytes of the pair per lane, G lanes) or the wavefront layout (256-byte stripes); a chunk of pairs then takes
+// at most (sum of these) x (its longest line + 32) bytes.  Tabulated by the shorter length for the lengths the duo
+// classes cover (*max_len = the last tabulated one); longer: 256-byte stripes.
+const int32_t *sw_align_tb_row_table(int32_t *max_len)
 {
-    // bytes per ROW of the larger of the two layouts a pair can end up in: its duo class (half a duo: K2 words x 2
-    // bytes of the pair per lane, G lanes) or the wavefront layout (256-byte stripes); a chunk of pairs then takes
-    // at most (sum of these) x (its longest line + 32) bytes.  Tabulated for the lengths the duo classes cover.
     static const std::vector<int32_t> table = [] {
         std::vector<int32_t> t(DUO_MAX_CAP + 2, 0);
         for (int ra = 0; ra <= DUO_MAX_CAP + 1; ++ra) {
@@ -1039,8 +1040,16 @@ int64_t sw_align_tb_row_bytes(int32_t len_a, int32_t len_b)
         }
         return t;
     }();
+    *max_len = DUO_MAX_CAP + 1;
+    return table.data();
+}
+
+int64_t sw_align_tb_row_bytes(int32_t len_a, int32_t len_b)
+{
+    int32_t cap = 0;
+    const int32_t *table = sw_align_tb_row_table(&cap);
     const int32_t ra = len_a > len_b ? len_b : len_a;
-    if (ra <= DUO_MAX_CAP + 1) return table[ra];
+    if (ra <= cap) return table[ra];
     return (int64_t)((ra + 255) / 256) * 256;
 }
 

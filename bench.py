@@ -445,11 +445,11 @@ def bench_sw(agx, args, rank, local_rank, world, device):
     h_scores = torch.empty(n, dtype=torch.int32).pin_memory()
     np_scores = h_scores.numpy()
     for _ in range(min(args.warmup, 2)):
-        img_scores, header, _ = cap.sw_score_file_image(np_buf, out=np_scores)
+        img_scores, header, _ = cap.sw_score_file_image(np_buf, out=np_scores, copy=False)
     barrier(world)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        img_scores, header, _ = cap.sw_score_file_image(np_buf, out=np_scores)
+        img_scores, header, _ = cap.sw_score_file_image(np_buf, out=np_scores, copy=False)
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / args.steps, world, device)
     assert header == 2 * n and np.array_equal(img_scores, res_scores), "file-image and device entry points disagree"
@@ -719,7 +719,8 @@ def bench_strong(agx, args, n_gpus):
         cap.shutdown()
         cap.init_devices(devs)
         cap.set_profiling(True)
-        img_ms, (img_scores, _, _) = wall(lambda: cap.sw_score_file_image(np_buf, out=h_scores.numpy()))
+        img_ms, (img_scores, _, _) = wall(lambda: cap.sw_score_file_image(np_buf, out=h_scores.numpy(), copy=False))
+        img_scores = img_scores.copy()       # (a view of h_scores until here)
         flat_ms, flat_scores = wall(lambda: cap.sw_score_flat(np_buf, inp.off, inp.len))
         assert np.array_equal(img_scores, flat_scores), "file-image and flat entry points disagree"
         # full alignments (end cell, start cell, CIGAR) of the same batch, pairs sharded over the GPUs
@@ -779,7 +780,8 @@ def bench_strong(agx, args, n_gpus):
         cap.shutdown()
         cap.init_devices(devs)
         cap.set_profiling(True)
-        img_ms, (img_vals, _, _) = wall(lambda: cap.pairhmm_forward_file_image(arrs[0]))
+        img_ms, (img_vals, _, _) = wall(lambda: cap.pairhmm_forward_file_image(arrs[0], copy=False))
+        img_vals = img_vals.copy()           # (a view of the library's pinned result buffer until here)
         flat_ms, flat_vals = wall(lambda: cap.pairhmm_forward_flat(*arrs))
         assert np.array_equal(img_vals, flat_vals, equal_nan=True), "file-image and flat entry points disagree"
         parts = split_hmm(hin, len(devs))
@@ -853,9 +855,41 @@ def bench_gatk(agx, args, device_index):
                         "log10_3": float(np.log10(3.0))})
     out["gatk_qual_floor"].update({"mismatch_prior": "Qr/3", "base_quality_floor": 6,
                                    "pairs_that_differ_from_gatk_mode": int(np.count_nonzero(results["gatk"] != results["gatk_qual_floor"]))})
+    out["pin"] = gatk_pin(agx)
     out["_results"] = results
     out["_input"] = inp
     return out
+
+
+def gatk_pin(agx):
+    """libagx's GATK mode against tests/golden/pairhmm_gatk.json: values of an independent full-matrix LoglessPairHMM
+    statement (tests/golden/make_gatk_golden.py) on the reference's own test_set inputs (test.in, 10s.in)."""
+    import gzip
+    import json as js
+    cap = agx.capi
+    gold = ROOT / "tests" / "golden"
+    if not (gold / "pairhmm_gatk.json").exists():
+        return None
+    files = js.loads((gold / "pairhmm_gatk.json").read_text())["files"]
+    rec = {"source": "tests/golden/pairhmm_gatk.json (independent LoglessPairHMM statement, make_gatk_golden.py)", "pairs": 0,
+           "max_rel": 0.0, "tolerance": 1e-5}
+    try:
+        for name, rows in files.items():
+            inp = agx.formats.parse_pairhmm(gzip.decompress((gold / name).read_bytes()))
+            nh, nr = np.diff(inp.batch_hap_start), np.diff(inp.batch_read_start)
+            base = np.concatenate(([0], np.cumsum(nr * nh)))
+            for mode, key in ((1, "gatk"), (3, "gatk_floor")):
+                cap.set_pairhmm_gatk_mode(mode)
+                got = cap.pairhmm_forward_flat(inp.buf, inp.read_field_off, inp.read_len, inp.hap_off, inp.hap_len,
+                                               inp.batch_read_start, inp.batch_hap_start)
+                for r in rows:
+                    k = int(base[r["batch"]] + r["read"] * nh[r["batch"]] + r["hap"])
+                    rec["max_rel"] = max(rec["max_rel"], abs(got[k] - r[key]) / abs(r[key]))
+                    rec["pairs"] += 1
+    finally:
+        cap.set_pairhmm_gatk_mode(0)
+    rec["ok"] = bool(rec["max_rel"] <= rec["tolerance"])
+    return rec
 
 
 def bench_sw_lengths(agx, args, device_index):

@@ -186,6 +186,30 @@ def test_chunked_matrices_give_the_same_result(gpu_lib, oracle_mod):
         assert g.tolist() == w.tolist()
 
 
+@pytest.mark.parametrize("chunk", [1, 37, 1000])
+def test_two_lane_chunk_pipeline_gives_the_same_result(gpu_lib, oracle_mod, chunk):
+    """the shard alternates its chunks between two lanes (upload of chunk k+1 under the kernels of chunk k, results of
+    chunk k under chunk k+1): any chunk size gives the single-chunk answer (AGX_ALIGN_CHUNK)"""
+    rng = np.random.default_rng(108)
+    a, b = _pairs(rng, 2500, 1, 200)
+    buf, off, ln = _flat(a, b)
+    os.environ["AGX_ALIGN_CHUNK"] = "0"
+    try:
+        want = gpu_lib.sw_align_flat(buf, off, ln)
+        want_ends = gpu_lib.sw_ends_flat(buf, off, ln)
+        os.environ["AGX_ALIGN_CHUNK"] = str(chunk)
+        got = gpu_lib.sw_align_flat(buf, off, ln)
+        got_ends = gpu_lib.sw_ends_flat(buf, off, ln)
+    finally:
+        del os.environ["AGX_ALIGN_CHUNK"]
+    for g, w in zip(got + got_ends, want + want_ends):
+        assert g.tolist() == w.tolist()
+    assert got[2][0] == 0 and got[2][-1] == got[3].size and np.all(np.diff(got[2]) >= 0)
+    for p in (0, 36, 37, 38, 999, 1000, 2499):           # chunk seams, against the oracle
+        ws, wc, wg = oracle_mod.sw_align(a[p], b[p], (1, -1, -3, -1))
+        assert (int(got[0][p]), tuple(got[1][p].tolist()), got[3][got[2][p]:got[2][p + 1]].tolist()) == (ws, wc, wg)
+
+
 def test_config3_batch_properties(agx, gpu_lib, oracle_mod):
     """BASELINE configs[2] shape (150 x 150): 60 000 pairs; every CIGAR re-scored, 1 000 pairs against the oracle."""
     inp = agx.synth.sw_uniform_pairs(60000, 150, seed=31)
