@@ -258,17 +258,26 @@ def sw_ends_flat(seqs: np.ndarray, off: np.ndarray, length: np.ndarray, scoring=
 
 
 def sw_align_flat(seqs: np.ndarray, off: np.ndarray, length: np.ndarray, scoring=(SW_MATCH, SW_MISMATCH, SW_GAP_OPEN, SW_GAP_EXTEND),
-                  cigar_cap: Optional[int] = None):
-    """sw_align_batch_flat: (scores[n], coords[n, 4] = a_start a_end b_start b_end, cigar_off[n + 1], cigar runs)"""
+                  cigar_cap: Optional[int] = None, out=None):
+    """sw_align_batch_flat: (scores[n], coords[n, 4] = a_start a_end b_start b_end, cigar_off[n + 1], cigar runs).
+    out = (scores, coords, cigar_off, cigar) arrays to fill (e.g. pinned ones: results then come home by DMA while the
+    next chunk computes); the returned cigar is a view of the given array."""
     seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
     off = np.ascontiguousarray(off, dtype=np.int64)
     length = np.ascontiguousarray(length, dtype=np.int32)
     n = off.size // 2
+    lib = load_library()
+    if out is not None:
+        scores, coords, cig_off, cigar = out
+        assert scores.size >= n and coords.size >= 4 * n and cig_off.size >= n + 1
+        total = C.c_int64(0)
+        _check(lib.sw_align_batch_flat(_ptr(seqs), seqs.size, _ptr(off), _ptr(length), n, *[int(s) for s in scoring],
+                                       _ptr(scores), _ptr(coords), _ptr(cig_off), _ptr(cigar), cigar.size, C.byref(total)))
+        return scores[:n], coords.reshape(-1, 4)[:n], cig_off[:n + 1], cigar[:int(total.value)]
     scores = np.empty(n, dtype=np.int32)
     coords = np.empty((n, 4), dtype=np.int32)
     cig_off = np.empty(n + 1, dtype=np.int64)
     cap = int(cigar_cap) if cigar_cap is not None else max(16, 8 * n)
-    lib = load_library()
     while True:
         cigar = np.empty(max(cap, 1), dtype=np.uint32)
         total = C.c_int64(0)

@@ -711,6 +711,9 @@ def bench_strong(agx, args, n_gpus):
     off_pin = torch.from_numpy(inp.off).pin_memory().numpy()
     len_pin = torch.from_numpy(inp.len).pin_memory().numpy()
     align_keep = {}
+    pinned = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+    align_out = (pinned(n, torch.int32), pinned((n, 4), torch.int32), pinned(n + 1, torch.int64),
+                 pinned(8 * n, torch.int32).view(np.uint32))
     res = {}
     for label, devs in (("1gpu", [0]), ("ngpu", list(range(n_gpus)))):
         if label == "ngpu" and n_gpus == 1:
@@ -724,9 +727,9 @@ def bench_strong(agx, args, n_gpus):
         flat_ms, flat_scores = wall(lambda: cap.sw_score_flat(np_buf, inp.off, inp.len))
         assert np.array_equal(img_scores, flat_scores), "file-image and flat entry points disagree"
         # full alignments (end cell, start cell, CIGAR) of the same batch, pairs sharded over the GPUs
-        align_ms, align_res = wall(lambda: cap.sw_align_flat(np_buf, off_pin, len_pin, cigar_cap=8 * n), warm=1)
+        align_ms, align_res = wall(lambda: cap.sw_align_flat(np_buf, off_pin, len_pin, out=align_out), warm=1)
         assert np.array_equal(align_res[0], flat_scores), "alignment scores and score-only scores disagree"
-        align_keep[label] = align_res
+        align_keep[label] = tuple(a.copy() for a in align_res)      # (views of the pinned result arrays until here)
         # resident: contiguous shards of equal pair count, uploaded once
         g = len(devs)
         shards, keep = [], []
@@ -764,7 +767,7 @@ def bench_strong(agx, args, n_gpus):
                                        "concatenated in pair order",
                                "equal_to_1gpu": bool(len(align_keep) < 2 or all(np.array_equal(x, y) for x, y in
                                                                                  zip(align_keep["1gpu"], align_keep["ngpu"])))}}
-    del h_buf, h_scores, align_keep
+    del h_buf, h_scores, align_keep, align_out
 
     # ---- PairHMM --------------------------------------------------------------------------------------
     hin = agx.synth.pairhmm_batches(args.hmm_batches, 200, 5, seed=2000, unrelated_frac=args.hmm_unrelated)

@@ -63,3 +63,27 @@ def test_argument_validation(agx):
     assert e.value.code == -1 and b"outside" in lib.agx_last_error()
     assert cap.sw_score_flat(buf, off[:0], ln[:0]).size == 0       # empty batch is a no-op
     assert lib.agx_launch_count() >= 0
+
+
+@pytest.mark.parametrize("bad", [3, 700_001, 1_199_999])
+def test_large_batches_are_validated_on_several_host_threads(agx, bad):
+    """2^19 and more (offset, length) entries are checked in slices on four host threads; the message still names
+    the first offending sequence, for the score and the alignment entry points alike (no device work happens)."""
+    cap = agx.capi
+    lib = cap.load_library()
+    n_seq = 1_200_000
+    buf = np.zeros(64, dtype=np.uint8)
+    off = np.zeros(n_seq, dtype=np.int64)
+    ln = np.full(n_seq, 8, dtype=np.int32)
+    off[bad] = 60                                    # 60 + 8 > 64
+    off[-1] = 61 if bad != n_seq - 1 else 60         # a later offender must not be the one reported
+    for call in (cap.sw_score_flat, cap.sw_ends_flat, cap.sw_align_flat):
+        with pytest.raises(cap.AgxError) as e:
+            call(buf, off, ln)
+        assert e.value.code == -1
+        assert f"sequence {bad} lies outside".encode() in lib.agx_last_error()
+    ln[bad] = -1
+    off[bad] = 0
+    with pytest.raises(cap.AgxError) as e:
+        cap.sw_score_flat(buf, off, ln)
+    assert e.value.code == -1 and f"sequence {bad} ".encode() in lib.agx_last_error()
