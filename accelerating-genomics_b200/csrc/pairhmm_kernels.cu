@@ -457,7 +457,12 @@ hmm_duo_kernel(HmmBatchView v, const int64_t *__restrict__ read_out_off, const i
                float *__restrict__ sums)
 {
     constexpr int CH = (K + 1) / 2;                    // float4 = (row 2c: A, B; row 2c+1: A, B)
-    __shared__ float4 prior_tab[HMM_NSYM][CH][32];
+    constexpr int CH4 = K / 2;                         // whole float4 chunks; an odd K leaves one row over
+    // The odd row has its own float2 table: as the half-used last float4 of prior_tab the compiler fetched it with a
+    // 64-bit load at a 16-byte lane stride -- a two-way bank conflict in every step (74 M / 84 M conflicts in the K = 7
+    // and K = 5 launches, 9 % of their shared-memory wavefronts, against 5 M for K = 8: profiles/r2be_hmm_duo_ncu.txt)
+    __shared__ float4 prior_tab[HMM_NSYM][CH4 > 0 ? CH4 : 1][32];
+    __shared__ float2 prior_odd[HMM_NSYM][(K & 1) ? 32 : 1];
 
     const int t = threadIdx.x;
     const int item = blockIdx.x;
@@ -530,7 +535,8 @@ hmm_duo_kernel(HmmBatchView v, const int64_t *__restrict__ read_out_off, const i
                         const bool match = (sym == 4) || (rsym[h][jj] == 4u) || (sym < 4 && rsym[h][jj] == (uint32_t)sym);
                         q[e][h] = match ? pm[h][jj] : px[h][jj];
                     }
-                prior_tab[sym][ch][t] = make_float4(q[0][0], q[0][1], q[1][0], q[1][1]);
+                if (ch < CH4) prior_tab[sym][ch][t] = make_float4(q[0][0], q[0][1], q[1][0], q[1][1]);
+                else prior_odd[sym][t] = make_float2(q[0][0], q[0][1]);
             }
         }
     }
@@ -556,7 +562,8 @@ hmm_duo_kernel(HmmBatchView v, const int64_t *__restrict__ read_out_off, const i
     for (int32_t h = h0; h < h1; ++h) total += hapinfo[h].len;
 
     const float4 *tab_lane = &prior_tab[0][0][t];
-    constexpr int SYM_STRIDE = CH * 32;              // float4 elements between symbols
+    const float2 *odd_lane = &prior_odd[0][(K & 1) ? t : 0];
+    constexpr int SYM_STRIDE = (CH4 > 0 ? CH4 : 1) * 32;   // float4 elements between symbols
     const bool lane0 = (t == 0);
 
     // One column step (no haplotype switch inside: see the driver loop below).
@@ -566,7 +573,11 @@ hmm_duo_kernel(HmmBatchView v, const int64_t *__restrict__ read_out_off, const i
             code_next = *cp;                                  // prefetch the next column's symbol
             float4 pr4[CH];
 #pragma unroll
-            for (int ch = 0; ch < CH; ++ch) pr4[ch] = tab_lane[code * SYM_STRIDE + ch * 32];
+            for (int ch = 0; ch < CH4; ++ch) pr4[ch] = tab_lane[code * SYM_STRIDE + ch * 32];
+            if (K & 1) {
+                const float2 po = odd_lane[code * 32];
+                pr4[CH - 1] = make_float4(po.x, po.y, 0.f, 0.f);
+            }
 
             float2 upM, upX, upY;
             upM.x = __shfl_up_sync(0xffffffffu, bM.x, 1); upM.y = __shfl_up_sync(0xffffffffu, bM.y, 1);
