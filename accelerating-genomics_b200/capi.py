@@ -231,17 +231,20 @@ def _byte_ptr_array(items: Sequence[bytes]):
 
 # ------------------------------------------------------------------------------- Smith-Waterman
 def sw_score_flat(seqs: np.ndarray, off: np.ndarray, length: np.ndarray,
-                  scoring=(SW_MATCH, SW_MISMATCH, SW_GAP_OPEN, SW_GAP_EXTEND)) -> np.ndarray:
-    """sw_score_batch_flat: seqs uint8 buffer, off/len of 2*n_pairs sequences (a0 b0 a1 b1 ...)."""
+                  scoring=(SW_MATCH, SW_MISMATCH, SW_GAP_OPEN, SW_GAP_EXTEND), out=None) -> np.ndarray:
+    """sw_score_batch_flat: seqs uint8 buffer, off/len of 2*n_pairs sequences (a0 b0 a1 b1 ...).
+    out: an int32 array to fill (a pinned one receives every chunk's scores by DMA, without a staging copy)."""
     seqs = _as(seqs, np.uint8)
     off = _as(off, np.int64)
     length = _as(length, np.int32)
     assert off.size == length.size and off.size % 2 == 0
     n = off.size // 2
-    out = np.empty(n, dtype=np.int32)
+    if out is None:
+        out = np.empty(n, dtype=np.int32)
+    assert out.dtype == np.int32 and out.size >= n and out.flags["C_CONTIGUOUS"]
     _check(load_library().sw_score_batch_flat(_ptr(seqs), seqs.size, _ptr(off), _ptr(length), n,
                                               *[int(s) for s in scoring], _ptr(out)))
-    return out
+    return out[:n]
 
 
 def sw_ends_flat(seqs: np.ndarray, off: np.ndarray, length: np.ndarray, scoring=(SW_MATCH, SW_MISMATCH, SW_GAP_OPEN, SW_GAP_EXTEND)):
@@ -413,8 +416,9 @@ def pairhmm_forward_batch(reads: Sequence[Sequence[bytes]], haps: Sequence[bytes
 
 def pairhmm_forward_flat(buf: np.ndarray, read_field_off: np.ndarray, read_len: np.ndarray,
                          hap_off: np.ndarray, hap_len: np.ndarray, batch_read_start: np.ndarray,
-                         batch_hap_start: np.ndarray) -> np.ndarray:
-    """pairhmm_forward_batches_flat on host arrays; returns the flat log10 vector."""
+                         batch_hap_start: np.ndarray, out=None) -> np.ndarray:
+    """pairhmm_forward_batches_flat on host arrays; returns the flat log10 vector.
+    out: a float64 array to fill (a pinned one receives the results by DMA, without a staging copy)."""
     buf = _as(buf, np.uint8)
     rfo = _as(read_field_off, np.int64).reshape(-1)
     rl = _as(read_len, np.int32)
@@ -424,7 +428,9 @@ def pairhmm_forward_flat(buf: np.ndarray, read_field_off: np.ndarray, read_len: 
     bhs = _as(batch_hap_start, np.int64)
     nb = brs.size - 1
     n_out = int(np.sum((brs[1:] - brs[:-1]) * (bhs[1:] - bhs[:-1])))
-    out = np.empty(max(n_out, 1), dtype=np.float64)
+    if out is None:
+        out = np.empty(max(n_out, 1), dtype=np.float64)
+    assert out.dtype == np.float64 and out.size >= n_out and out.flags["C_CONTIGUOUS"]
     _check(load_library().pairhmm_forward_batches_flat(_ptr(buf), buf.size, _ptr(rfo), _ptr(rl), rl.size,
                                                        _ptr(ho), _ptr(hl), hl.size, _ptr(brs), _ptr(bhs),
                                                        nb, _ptr(out)))

@@ -122,6 +122,16 @@ struct AlignLane {
     int64_t pend_q0 = 0, pend_m = 0, pend_base = 0;   // chunk whose results are on their way home; its first run's index
 };
 
+// stream + workspace + staging buffers of one in-flight part of a PairHMM shard (hmm_shard)
+struct HmmLane {
+    cudaStream_t st = nullptr;         // the context's stream / its second lane's stream
+    HmmWorkspace *ws = nullptr;        // the context's hmm / hmm_b
+    DevBuf bytes, idx, out;
+    PinBuf h_idx;                      // shard-local index arrays, built on the host
+    PinBuf h_out;                      // results on their way to a PAGEABLE result array (a D2H copy into one would
+    int64_t pend_o0 = 0, pend_n = 0;   // block the host until the kernels are done); pend_*: what still sits there
+};
+
 // stream + workspace + staging buffers of one in-flight SW chunk
 struct SwLane {
     cudaStream_t st = nullptr;
@@ -143,6 +153,7 @@ struct DeviceCtx {
     SwWorkspace &sw = lane[0].ws;
     HmmWorkspace hmm, hmm_b;                 // hmm_b / hmm_parse_b: second lane of pairhmm_forward_file_image
     HmmParseWorkspace hmm_parse, hmm_parse_b;
+    HmmLane hl[2];                           // pairhmm_forward_batches_flat: two parts of a shard in flight
     DevBuf d_bytes, d_a, d_b, d_c, d_d, d_e, d_f, d_out;   // staging for the host entry points
     AlignLane al[2];                                        // sw_ends_* / sw_align_*: two chunks in flight
     SwAlignWorkspace &align = al[0].ws;                     // (the device-resident entry points use the first)
@@ -295,17 +306,21 @@ int validate_sequences(const char *what, int64_t seqs_bytes, const int64_t *off,
 
 // ---------------------------------------------------------------- SW on one shard
 // One shard = a contiguous range of pairs on one GPU.  It is cut into chunks that alternate between the
-// context's two lanes (stream + workspace + staging buffers each): the host->device copy of chunk k+1 is
-// queued before the host blocks on chunk k's grid-sizing read-back, so copies overlap the DP kernels.
-// Offsets are uploaded as they are; the device base pointer is shifted by the chunk's first byte instead.
+// context's two lanes (stream + workspace + staging buffers each).  The host->device copies of chunk k+1 are
+// queued BEFORE the host blocks on chunk k's grid-sizing read-back, so the link never waits for the host and the
+// DP kernels run under the copies; results go straight to a pinned result array (a pageable one is filled from a
+// pinned staging buffer).  Offsets are uploaded as they are; the device base pointer is shifted by the chunk's
+// first byte instead.
 int sw_shard(DeviceCtx &c, const uint8_t *seqs, int64_t seqs_bytes, const int64_t *off, const int32_t *len,
              int64_t p0, int64_t p1, SwScoring sc, int32_t *scores_out)
 {
     const int64_t n = p1 - p0;
     if (n <= 0) return AGX_OK;
+    // chunks: an eighth of the shard, 64 Ki .. 512 Ki pairs (what is left to do when the last byte has landed is one
+    // chunk's kernels); one chunk up to 96 Ki pairs
     int64_t chunk = n;
     if (n > 98304) {
-        chunk = (n + 3) / 4;
+        chunk = (n + 7) / 8;
         if (chunk < 65536) chunk = 65536;
         if (chunk > 524288) chunk = 524288;
     }
@@ -314,18 +329,36 @@ int sw_shard(DeviceCtx &c, const uint8_t *seqs, int64_t seqs_bytes, const int64_
         chunk = v > 0 ? std::min<int64_t>(v, n) : n;
     }
     const int64_t n_chunks = (n + chunk - 1) / chunk;
-    std::vector<int64_t> lo(n_chunks, 0);
+    // byte range [lo, hi) every chunk's sequences lie in (offsets were validated by sw_flat_impl); the passes over
+    // the offsets run on up to four host threads
+    std::vector<int64_t> lo(n_chunks, 0), hi(n_chunks, 0);
+    {
+        auto range_of = [&](int64_t k) {
+            const int64_t q0 = p0 + k * chunk, q1 = std::min(p1, q0 + chunk);
+            int64_t l = INT64_MAX, h = 0;
+            for (int64_t i = 2 * q0; i < 2 * q1; ++i) {
+                l = std::min(l, off[i]);
+                h = std::max(h, off[i] + len[i]);
+            }
+            if (h < l) { l = 0; h = 0; }
+            lo[k] = l;
+            hi[k] = h;
+        };
+        const int parts = (n >= ((int64_t)1 << 18) && n_chunks > 1) ? (int)std::min<int64_t>(4, n_chunks) : 1;
+        auto slice = [&](int t) { for (int64_t k = t; k < n_chunks; k += parts) range_of(k); };
+        std::thread th[3];
+        for (int t = 1; t < parts; ++t) th[t - 1] = std::thread(slice, t);
+        slice(0);
+        for (int t = 1; t < parts; ++t) th[t - 1].join();
+    }
+    cudaPointerAttributes attr;
+    const bool out_pinned = cudaPointerGetAttributes(&attr, scores_out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
 
     auto stage = [&](int64_t k) -> int {
         SwLane &L = c.lane[k & 1];
         const int64_t q0 = p0 + k * chunk, q1 = std::min(p1, q0 + chunk), m = q1 - q0;
-        int64_t l = INT64_MAX, h = 0;
-        for (int64_t i = 2 * q0; i < 2 * q1; ++i) {      // offsets were validated by sw_flat_impl
-            l = std::min(l, off[i]);
-            h = std::max(h, off[i] + len[i]);
-        }
-        if (h < l) { l = 0; h = 0; }
-        lo[k] = l;
+        const int64_t l = lo[k], h = hi[k];
         int rc;
         if ((rc = L.bytes.reserve((size_t)(h - l) + 16)) != AGX_OK) return rc;
         if ((rc = L.off.reserve((size_t)m * 2 * sizeof(int64_t))) != AGX_OK) return rc;
@@ -337,11 +370,11 @@ int sw_shard(DeviceCtx &c, const uint8_t *seqs, int64_t seqs_bytes, const int64_
         return AGX_OK;
     };
 
-    // results of a lane's previous chunk: wait for them and hand them to the caller
+    // results of a lane's previous chunk: wait for them and (pageable result array) hand them to the caller
     auto drain = [&](SwLane &L) -> int {
         if (L.pend_m == 0) return AGX_OK;
         AGX_CUDA(cudaStreamSynchronize(L.st));
-        memcpy(scores_out + L.pend_q0, L.h_out.p, (size_t)L.pend_m * sizeof(int32_t));
+        if (!out_pinned) memcpy(scores_out + L.pend_q0, L.h_out.p, (size_t)L.pend_m * sizeof(int32_t));
         L.pend_m = 0;
         return AGX_OK;
     };
@@ -352,19 +385,21 @@ int sw_shard(DeviceCtx &c, const uint8_t *seqs, int64_t seqs_bytes, const int64_
     for (int64_t k = 0; k < n_chunks; ++k) {
         SwLane &L = c.lane[k & 1];
         const int64_t q0 = p0 + k * chunk, q1 = std::min(p1, q0 + chunk), m = q1 - q0;
-        if ((rc = L.h_out.reserve((size_t)m * sizeof(int32_t))) != AGX_OK) return rc;
+        if (k + 1 < n_chunks) {
+            // the other lane still owns chunk k-1: collect its results (its kernels ran under chunk k's upload), then
+            // queue chunk k+1's upload behind chunk k's
+            if ((rc = drain(c.lane[(k + 1) & 1])) != AGX_OK) return rc;
+            if ((rc = stage(k + 1)) != AGX_OK) return rc;
+        }
+        if (!out_pinned && (rc = L.h_out.reserve((size_t)m * sizeof(int32_t))) != AGX_OK) return rc;
         // blocks until chunk k is on the device and classified, then queues its DP kernels
         rc = sw_run_device(L.ws, biased(L.bytes.p, lo[k]), L.off.as<int64_t>(), L.len.as<int32_t>(), m, sc,
                            L.out.as<int32_t>(), L.st);
         if (rc != AGX_OK) return rc;
-        AGX_CUDA(cudaMemcpyAsync(L.h_out.p, L.out.p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, L.st));
+        AGX_CUDA(cudaMemcpyAsync(out_pinned ? (void *)(scores_out + q0) : L.h_out.p, L.out.p, (size_t)m * sizeof(int32_t),
+                                 cudaMemcpyDeviceToHost, L.st));
         L.pend_q0 = q0;
         L.pend_m = m;
-        if (k + 1 < n_chunks) {
-            // the other lane still owns chunk k-1's results; collect them, then refill it with chunk k+1
-            if ((rc = drain(c.lane[(k + 1) & 1])) != AGX_OK) return rc;
-            if ((rc = stage(k + 1)) != AGX_OK) return rc;
-        }
     }
     if ((rc = drain(c.lane[0])) != AGX_OK) return rc;
     if ((rc = drain(c.lane[1])) != AGX_OK) return rc;
@@ -785,7 +820,20 @@ struct HmmHost {
     int64_t n_pairs;
 };
 
-int hmm_shard(DeviceCtx &c, const HmmHost &h, int64_t r0, int64_t r1, double *out)
+// Waits for what a lane has in flight and hands staged results to a pageable result array.
+int hmm_lane_wait(HmmLane &L, double *out)
+{
+    const cudaError_t e = cudaStreamSynchronize(L.st);
+    if (e == cudaSuccess && L.pend_n > 0) memcpy(out + L.pend_o0, L.h_out.p, (size_t)L.pend_n * sizeof(double));
+    L.pend_n = 0;
+    AGX_CUDA(e);
+    return AGX_OK;
+}
+
+// Reads [r0, r1) on one lane (stream + workspace + staging buffers).  wait = true: the call returns with the results
+// in `out`; false: everything is queued on the lane's stream (the FP64 rescue reads its work count on the device, so
+// no host round trip follows the stream kernels) and the caller synchronises the lane before it uses it again.
+int hmm_part(HmmLane &L, const HmmHost &h, int64_t r0, int64_t r1, double *out, bool wait)
 {
     const int64_t nr = r1 - r0;
     if (nr <= 0) return AGX_OK;
@@ -818,11 +866,11 @@ int hmm_shard(DeviceCtx &c, const HmmHost &h, int64_t r0, int64_t r1, double *ou
                  sz_hl = (size_t)nh * sizeof(int32_t);
     const size_t total = sz_rfo + sz_roo + sz_ho + sz_bhs + sz_rl + sz_rb + sz_hl;
     int rc;
-    if ((rc = c.h_a.reserve(total)) != AGX_OK) return rc;
-    if ((rc = c.d_a.reserve(total)) != AGX_OK) return rc;
-    if ((rc = c.d_bytes.reserve((size_t)nbytes + 16)) != AGX_OK) return rc;
-    if ((rc = c.d_out.reserve((size_t)n_out * sizeof(double))) != AGX_OK) return rc;
-    uint8_t *hp = c.h_a.as<uint8_t>();
+    if ((rc = L.h_idx.reserve(total)) != AGX_OK) return rc;
+    if ((rc = L.idx.reserve(total)) != AGX_OK) return rc;
+    if ((rc = L.bytes.reserve((size_t)nbytes + 16)) != AGX_OK) return rc;
+    if ((rc = L.out.reserve((size_t)n_out * sizeof(double))) != AGX_OK) return rc;
+    uint8_t *hp = L.h_idx.as<uint8_t>();
     int64_t *p_rfo = (int64_t *)hp;
     int64_t *p_roo = (int64_t *)(hp + sz_rfo);
     int64_t *p_ho = (int64_t *)(hp + sz_rfo + sz_roo);
@@ -842,12 +890,12 @@ int hmm_shard(DeviceCtx &c, const HmmHost &h, int64_t r0, int64_t r1, double *ou
     }
     for (int64_t b = 0; b <= nb; ++b) p_bhs[b] = h.batch_hap_start[b0 + b] - hh0;
 
-    cudaStream_t st = c.stream;
-    AGX_CUDA(cudaMemcpyAsync(c.d_bytes.p, h.buf + lo, (size_t)nbytes, cudaMemcpyHostToDevice, st));
-    AGX_CUDA(cudaMemcpyAsync(c.d_a.p, hp, total, cudaMemcpyHostToDevice, st));
-    uint8_t *dp = c.d_a.as<uint8_t>();
+    cudaStream_t st = L.st;
+    AGX_CUDA(cudaMemcpyAsync(L.bytes.p, h.buf + lo, (size_t)nbytes, cudaMemcpyHostToDevice, st));
+    AGX_CUDA(cudaMemcpyAsync(L.idx.p, hp, total, cudaMemcpyHostToDevice, st));
+    uint8_t *dp = L.idx.as<uint8_t>();
     HmmBatchView v;
-    v.buf = c.d_bytes.as<uint8_t>();
+    v.buf = L.bytes.as<uint8_t>();
     v.read_field_off = (const int64_t *)dp;
     const int64_t *d_roo = (const int64_t *)(dp + sz_rfo);
     v.hap_off = (const int64_t *)(dp + sz_rfo + sz_roo);
@@ -858,13 +906,55 @@ int hmm_shard(DeviceCtx &c, const HmmHost &h, int64_t r0, int64_t r1, double *ou
     v.n_reads = nr;
     v.n_haps = nh;
     v.n_batches = nb;
-    rc = hmm_run_device(c.hmm, v, nbytes, d_roo, n_out, g_gatk.load(), g_force64.load() != 0, 1,
-                        c.d_out.as<double>(), st);
+    rc = hmm_run_device(*L.ws, v, nbytes, d_roo, n_out, g_gatk.load(), g_force64.load() != 0, wait ? 1 : 2,
+                        L.out.as<double>(), st);
     if (rc != AGX_OK) return rc;
-    AGX_CUDA(cudaMemcpyAsync(out + o0, c.d_out.p, (size_t)n_out * sizeof(double), cudaMemcpyDeviceToHost, st));
-    AGX_CUDA(cudaStreamSynchronize(st));
+    cudaPointerAttributes attr;
+    const bool out_pinned = cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (out_pinned) {
+        AGX_CUDA(cudaMemcpyAsync(out + o0, L.out.p, (size_t)n_out * sizeof(double), cudaMemcpyDeviceToHost, st));
+    } else {
+        if ((rc = L.h_out.reserve((size_t)n_out * sizeof(double))) != AGX_OK) return rc;
+        AGX_CUDA(cudaMemcpyAsync(L.h_out.p, L.out.p, (size_t)n_out * sizeof(double), cudaMemcpyDeviceToHost, st));
+        L.pend_o0 = o0;
+        L.pend_n = n_out;
+    }
+    if (wait) return hmm_lane_wait(L, out);
     return AGX_OK;
 }
+
+// ---------------------------------------------------------------- PairHMM on one shard
+// One shard = a contiguous range of reads on one GPU.  A large shard is cut into parts that alternate between two
+// lanes: while the stream kernels of part k run, the host builds the index arrays of part k+1 and its upload goes
+// out, and the results of part k travel home under part k+1 (the call used to upload, compute and download in turn).
+int hmm_shard(DeviceCtx &c, const HmmHost &h, int64_t r0, int64_t r1, double *out)
+{
+    const int64_t nr = r1 - r0;
+    if (nr <= 0) return AGX_OK;
+    c.hl[0].st = c.stream;
+    c.hl[0].ws = &c.hmm;
+    c.hl[1].st = c.lane[1].st;
+    c.hl[1].ws = &c.hmm_b;
+    // parts of at least 32 Ki reads (a part must still fill the GPU: ~10^4 two-read warps over five row classes), four at
+    // most (200 000 reads: 28.2 ms in one part, 25.8 / 24.4 / 24.7 / 26.1 ms in 2 / 4 / 6 / 8, profiles/r2bl_hmm_flat.jsonl)
+    int parts = (int)std::max<int64_t>(1, std::min<int64_t>(4, nr / 32768));
+    if (const char *e = getenv("AGX_HMM_PARTS")) parts = std::max(1, atoi(e));       // tuning knob
+    parts = (int)std::min<int64_t>(parts, nr);
+    if (parts == 1) return hmm_part(c.hl[0], h, r0, r1, out, true);
+    int rc = AGX_OK;
+    for (int k = 0; k < parts && rc == AGX_OK; ++k) {
+        HmmLane &L = c.hl[k & 1];
+        // the lane's previous part (two parts back) must be done before its buffers are filled again; the part in
+        // between keeps the GPU busy meanwhile
+        if (k >= 2 && (rc = hmm_lane_wait(L, out)) != AGX_OK) break;
+        rc = hmm_part(L, h, r0 + nr * k / parts, r0 + nr * (k + 1) / parts, out, false);
+    }
+    const int w0 = hmm_lane_wait(c.hl[0], out), w1 = hmm_lane_wait(c.hl[1], out);
+    if (rc != AGX_OK) return rc;
+    return w0 != AGX_OK ? w0 : w1;
+}
+
 
 int hmm_flat_impl(HmmHost &h, double *out)
 {
@@ -1017,6 +1107,11 @@ void agx_shutdown(void)
         hmm_parse_workspace_free(c->hmm_parse_b);
         for (DevBuf *b : {&c->d_bytes, &c->d_a, &c->d_b, &c->d_c, &c->d_d, &c->d_e, &c->d_f, &c->d_out}) b->release();
         for (PinBuf *b : {&c->h_a, &c->h_b, &c->h_out}) b->release();
+        for (HmmLane &L : c->hl) {
+            for (DevBuf *b : {&L.bytes, &L.idx, &L.out}) b->release();
+            L.h_idx.release();
+            L.h_out.release();
+        }
         for (AlignLane &L : c->al) {
             for (DevBuf *b : {&L.bytes, &L.off, &L.len, &L.scores, &L.ends, &L.coords, &L.cigar}) b->release();
             sw_align_workspace_free(L.ws);

@@ -457,11 +457,11 @@ def bench_sw(agx, args, rank, local_rank, world, device):
     e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / args.steps, world, device)
     assert header == 2 * n and np.array_equal(img_scores, res_scores), "file-image and device entry points disagree"
     for _ in range(min(args.warmup, 2)):
-        e2e_scores = cap.sw_score_flat(np_buf, np_off, np_len)
+        e2e_scores = cap.sw_score_flat(np_buf, np_off, np_len, out=np_scores)
     barrier(world)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        e2e_scores = cap.sw_score_flat(np_buf, np_off, np_len)
+        e2e_scores = cap.sw_score_flat(np_buf, np_off, np_len, out=np_scores)
     torch.cuda.synchronize()
     flat_ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / args.steps, world, device)
     assert np.array_equal(e2e_scores, res_scores), "host and device entry points disagree"
@@ -560,12 +560,13 @@ def bench_hmm(agx, args, rank, local_rank, world, device):
     e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / args.steps, world, device)
     assert img_inc == 0 and img_bp.size == nb and np.array_equal(img_vals, res, equal_nan=True), \
         "file-image and device entry points disagree"
+    h_flat = torch.empty(n_pairs, dtype=torch.float64).pin_memory().numpy()     # pinned result array, like the inputs
     for _ in range(min(args.warmup, 2)):
-        e2e = cap.pairhmm_forward_flat(*arrs)
+        e2e = cap.pairhmm_forward_flat(*arrs, out=h_flat)
     barrier(world)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        e2e = cap.pairhmm_forward_flat(*arrs)
+        e2e = cap.pairhmm_forward_flat(*arrs, out=h_flat)
     torch.cuda.synchronize()
     flat_ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / args.steps, world, device)
     assert np.array_equal(e2e, res, equal_nan=True), "host and device entry points disagree"
@@ -730,7 +731,8 @@ def bench_strong(agx, args, n_gpus):
         cap.set_profiling(False)                # end-to-end calls without libagx's timing events (see bench_sw)
         img_ms, (img_scores, _, _) = wall(lambda: cap.sw_score_file_image(np_buf, out=h_scores.numpy(), copy=False))
         img_scores = img_scores.copy()       # (a view of h_scores until here)
-        flat_ms, flat_scores = wall(lambda: cap.sw_score_flat(np_buf, inp.off, inp.len))
+        flat_ms, flat_scores = wall(lambda: cap.sw_score_flat(np_buf, off_pin, len_pin, out=h_scores.numpy()))
+        flat_scores = flat_scores.copy()
         assert np.array_equal(img_scores, flat_scores), "file-image and flat entry points disagree"
         # full alignments (end cell, start cell, CIGAR) of the same batch, pairs sharded over the GPUs
         align_ms, align_res = wall(lambda: cap.sw_align_flat(np_buf, off_pin, len_pin, out=align_out), warm=1)

@@ -312,3 +312,23 @@ def test_file_image_header_counts_are_inherited(agx, gpu_lib, oracle_mod):
     assert np.max(np.abs(vals - want) / np.abs(want)) <= 1e-5
     vals2, batch_pairs2, incomplete2 = gpu_lib.pairhmm_forward_file_image(_inherited_header_file(agx, trailing_blank=True))
     assert incomplete2 == 2 and batch_pairs2.tolist() == [27] * 4 and np.array_equal(vals2, vals)
+
+
+@pytest.mark.parametrize("parts", [2, 3, 7])
+def test_shard_parts_on_two_lanes_give_the_same_result(agx, gpu_lib, oracle_mod, parts, monkeypatch):
+    """a large shard is cut into parts that alternate between two lanes (index arrays of part k+1 built and uploaded
+    under the kernels of part k, FP64 rescue without a host round trip): any number of parts -- cuts inside batches
+    included -- gives the one-part answer bit for bit, for pageable and for pinned result arrays"""
+    import torch
+    inp = agx.synth.pairhmm_batches(9, 31, 4, seed=77, unrelated_frac=0.05)
+    args = (inp.buf, inp.read_field_off, inp.read_len, inp.hap_off, inp.hap_len, inp.batch_read_start, inp.batch_hap_start)
+    monkeypatch.setenv("AGX_HMM_PARTS", "1")
+    want = gpu_lib.pairhmm_forward_flat(*args)
+    monkeypatch.setenv("AGX_HMM_PARTS", str(parts))
+    got = gpu_lib.pairhmm_forward_flat(*args)
+    pinned = torch.empty(want.size, dtype=torch.float64).pin_memory().numpy()
+    got_pinned = gpu_lib.pairhmm_forward_flat(*args, out=pinned)
+    assert np.array_equal(got, want, equal_nan=True) and np.array_equal(got_pinned, want, equal_nan=True)
+    ref = oracle_mod.pairhmm_flat(inp)
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(got), fin) and _rel_err(got[fin], ref[fin]) <= REL_TOL
