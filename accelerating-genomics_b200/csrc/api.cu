@@ -156,6 +156,7 @@ struct DeviceCtx {
     HmmLane hl[2];                           // pairhmm_forward_batches_flat: two parts of a shard in flight
     DevBuf d_bytes, d_a, d_b, d_c, d_d, d_e, d_f, d_out;   // staging for the host entry points
     AlignLane al[2];                                        // sw_ends_* / sw_align_*: two chunks in flight
+    PinBuf h_cigar;                                         // several GPUs: the CIGAR runs of this GPU's shard
     SwAlignWorkspace &align = al[0].ws;                     // (the device-resident entry points use the first)
     int64_t align_free = 0;                                 // free device memory + what the alignment scratch holds, as last asked
     PinBuf h_a, h_b, h_out;
@@ -222,6 +223,33 @@ std::vector<int64_t> balanced_cuts(const std::vector<double> &prefix, int parts)
         cuts[k] = std::lower_bound(prefix.begin(), prefix.end(), target) - prefix.begin();
         if (cuts[k] < cuts[k - 1]) cuts[k] = cuts[k - 1];
         if (cuts[k] > n) cuts[k] = n;
+    }
+    return cuts;
+}
+
+// The same for pairs weighted by their cell count, without a prefix array of the whole batch (8 MB of fresh pages
+// per 10^6 pairs): sums over blocks of 1024 pairs, then a scan inside the block a cut falls into.
+std::vector<int64_t> balanced_pair_cuts(const int32_t *len, int64_t n_pairs, int parts)
+{
+    const int64_t B = 1024, nb = (n_pairs + B - 1) / B;
+    auto weight = [&](int64_t p) { return (double)(len[2 * p] + 1) * (double)(len[2 * p + 1] + 1); };
+    std::vector<double> block(nb + 1, 0.0);
+    for (int64_t b = 0; b < nb; ++b) {
+        double w = 0.0;
+        for (int64_t p = b * B, e = std::min(n_pairs, p + B); p < e; ++p) w += weight(p);
+        block[b + 1] = block[b] + w;
+    }
+    std::vector<int64_t> cuts(parts + 1, n_pairs);
+    cuts[0] = 0;
+    const double total = block[nb];
+    for (int k = 1; k < parts; ++k) {
+        const double target = total * k / parts;
+        int64_t b = std::lower_bound(block.begin(), block.end(), target) - block.begin();     // block[b] >= target
+        b = std::max<int64_t>(b - 1, 0);
+        double w = block[b];
+        int64_t p = b * B;
+        while (p < n_pairs && w < target) w += weight(p++);
+        cuts[k] = std::max(std::min(p, n_pairs), cuts[k - 1]);
     }
     return cuts;
 }
@@ -464,12 +492,7 @@ int sw_flat_impl(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *off, co
 
     const int n_dev = (int)std::min<int64_t>((int64_t)g_ctx.size(), n_pairs);
     std::vector<int64_t> cuts{0, n_pairs};
-    if (n_dev > 1) {
-        std::vector<double> prefix(n_pairs + 1, 0.0);
-        for (int64_t p = 0; p < n_pairs; ++p)
-            prefix[p + 1] = prefix[p] + (double)(len[2 * p] + 1) * (double)(len[2 * p + 1] + 1);
-        cuts = balanced_cuts(prefix, n_dev);
-    }
+    if (n_dev > 1) cuts = balanced_pair_cuts(len, n_pairs, n_dev);
     return for_each_device(n_dev, [&](DeviceCtx &c, int k) {
         return sw_shard(c, seqs, seqs_bytes, off, len, cuts[k], cuts[k + 1], sc, scores_out);
     });
@@ -495,11 +518,12 @@ int align_memory(DeviceCtx &c, bool refresh, int64_t *out)
 // mode 1: scores + ends; mode 2: + coords and CIGAR runs (appended to `cigar`, run offsets relative to the shard).
 struct AlignOut {
     int32_t *scores, *ends, *coords;
-    int64_t *cigar_off;               // [n + 1], mode 2
-    std::vector<uint32_t> *cigar;     // mode 2, several GPUs: runs of this shard, concatenated by the caller
+    int64_t *cigar_off;               // mode 2: [n] run offsets relative to the shard (+ the total as entry n when `whole`)
+    bool whole;                       // the shard is the whole batch (one GPU)
     uint32_t *cigar_direct;           // mode 2, one GPU: the caller's array, runs land there as long as they fit
     int64_t cigar_cap;
-};
+    int64_t *total;                   // mode 2, several GPUs: runs of this shard; they wait in the context's pinned
+};                                    // h_cigar for the caller, who knows their place once every shard is done
 
 int sw_align_shard(DeviceCtx &c, const uint8_t *seqs, const int64_t *off, const int32_t *len, int64_t p0, int64_t p1,
                    SwScoring sc, int mode, AlignOut out)
@@ -587,6 +611,7 @@ int sw_align_shard(DeviceCtx &c, const uint8_t *seqs, const int64_t *off, const 
         return ch;
     };
     // results of a lane's previous chunk: wait for them; run offsets of later chunks are rebased on the host
+    int64_t cig_held = 0;                             // runs already on their way into h_cigar
     auto drain = [&](AlignLane &L) -> int {
         if (L.pend_m == 0) return AGX_OK;
         AGX_CUDA(cudaStreamSynchronize(L.st));
@@ -621,7 +646,20 @@ int sw_align_shard(DeviceCtx &c, const uint8_t *seqs, const int64_t *off, const 
         return AGX_OK;
     };
 
-    std::deque<std::vector<uint32_t>> parts;          // several GPUs: the runs of every chunk, joined at the end
+    // several GPUs: the runs collect in pinned memory of the context (grown with its contents kept; both lanes idle then)
+    auto keep_runs = [&](int64_t runs) -> int {
+        const size_t need = (size_t)runs * sizeof(uint32_t);
+        if (need <= c.h_cigar.cap) return AGX_OK;
+        AGX_CUDA(cudaStreamSynchronize(lanes[0]->st));
+        AGX_CUDA(cudaStreamSynchronize(lanes[1]->st));
+        PinBuf bigger;
+        int r = bigger.reserve(std::max(need * 2, (size_t)16 << 20));
+        if (r != AGX_OK) return r;
+        if (c.h_cigar.p && cig_held > 0) memcpy(bigger.p, c.h_cigar.p, (size_t)cig_held * sizeof(uint32_t));
+        c.h_cigar.release();
+        c.h_cigar = bigger;
+        return AGX_OK;
+    };
     int64_t cig_base = 0;
     int li = 0;
     c.al[0].pend_m = c.al[1].pend_m = 0;
@@ -669,8 +707,9 @@ int sw_align_shard(DeviceCtx &c, const uint8_t *seqs, const int64_t *off, const 
                 if ((rc = sw_align_gather_device(L.ws, m, L.cigar.as<uint32_t>(), L.st)) != AGX_OK) return rc;
                 uint32_t *dst = out.cigar_direct ? out.cigar_direct + cig_base : nullptr;
                 if (!dst) {
-                    parts.emplace_back((size_t)total);
-                    dst = parts.back().data();
+                    if ((rc = keep_runs(cig_base + total)) != AGX_OK) return rc;
+                    dst = c.h_cigar.as<uint32_t>() + cig_base;
+                    cig_held = cig_base + total;
                 }
                 AGX_CUDA(cudaMemcpyAsync(dst, L.cigar.p, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost, L.st));
             }
@@ -685,11 +724,8 @@ int sw_align_shard(DeviceCtx &c, const uint8_t *seqs, const int64_t *off, const 
     if ((rc = drain(c.al[0])) != AGX_OK) return rc;
     if ((rc = drain(c.al[1])) != AGX_OK) return rc;
     if (mode == 2) {
-        out.cigar_off[n] = cig_base;
-        if (!out.cigar_direct) {
-            out.cigar->reserve(out.cigar->size() + (size_t)cig_base);
-            for (auto &v : parts) out.cigar->insert(out.cigar->end(), v.begin(), v.end());
-        }
+        if (out.whole) out.cigar_off[n] = cig_base;
+        if (out.total) *out.total = cig_base;
     }
     if (trace) fprintf(stderr, "[agx align] +%.2f ms: shard done\n", now() - t_begin);
     return AGX_OK;
@@ -762,37 +798,37 @@ int sw_align_impl(const uint8_t *seqs, int64_t seqs_bytes, const int64_t *off, c
     }
     const int n_dev = (int)std::min<int64_t>((int64_t)g_ctx.size(), n_pairs);
     std::vector<int64_t> cuts{0, n_pairs};
-    if (n_dev > 1) {
-        std::vector<double> prefix(n_pairs + 1, 0.0);
-        for (int64_t p = 0; p < n_pairs; ++p)
-            prefix[p + 1] = prefix[p] + (double)(len[2 * p] + 1) * (double)(len[2 * p + 1] + 1);
-        cuts = balanced_cuts(prefix, n_dev);
-    }
-    std::vector<std::vector<uint32_t>> cig(n_dev);
-    std::vector<std::vector<int64_t>> coff(n_dev);
-    if (mode == 2 && n_dev > 1) {
-        for (int k = 0; k < n_dev; ++k) coff[k].assign((size_t)(cuts[k + 1] - cuts[k] + 1), 0);
-    }
+    if (n_dev > 1) cuts = balanced_pair_cuts(len, n_pairs, n_dev);
+    std::vector<int64_t> totals(n_dev, 0);
     rc = for_each_device(n_dev, [&](DeviceCtx &c, int k) {
         AlignOut o;
         o.scores = scores_out;
         o.ends = mode == 2 ? nullptr : ends_out;       // mode 2: the ends are part of coords
         o.coords = coords_out;
-        o.cigar_off = mode == 2 ? (n_dev == 1 ? cigar_off_out : coff[k].data()) : nullptr;
-        o.cigar = &cig[k];
+        o.cigar_off = mode == 2 ? cigar_off_out + cuts[k] : nullptr;
+        o.whole = n_dev == 1;
         o.cigar_direct = n_dev == 1 ? cigar_out : nullptr;
-        o.cigar_cap = cigar_cap;
+        o.cigar_cap = n_dev == 1 ? cigar_cap : INT64_MAX;
+        o.total = &totals[k];
         return sw_align_shard(c, seqs, off, len, cuts[k], cuts[k + 1], sc, mode, o);
     });
     if (rc != AGX_OK) return rc;
     if (mode != 2) return AGX_OK;
-    int64_t base = n_dev == 1 ? cigar_off_out[n_pairs] : 0;
-    for (int k = 0; n_dev > 1 && k < n_dev; ++k) {
-        const int64_t m = cuts[k + 1] - cuts[k];
-        for (int64_t i = 0; i < m; ++i) cigar_off_out[cuts[k] + i] = coff[k][i] + base;
-        const int64_t tot = coff[k][m];
-        if (n_dev > 1 && base + tot <= cigar_cap && tot > 0) memcpy(cigar_out + base, cig[k].data(), (size_t)tot * sizeof(uint32_t));
-        base += tot;
+    int64_t base = totals[0];
+    if (n_dev > 1) {
+        // every shard's runs wait in its context's pinned memory and its offsets count from its own first run: each
+        // GPU's host thread moves them to their place in the caller's arrays
+        std::vector<int64_t> bases(n_dev + 1, 0);
+        for (int k = 0; k < n_dev; ++k) bases[k + 1] = bases[k] + totals[k];
+        base = bases[n_dev];
+        rc = for_each_device(n_dev, [&](DeviceCtx &c, int k) {
+            if (bases[k] != 0)
+                for (int64_t i = cuts[k]; i < cuts[k + 1]; ++i) cigar_off_out[i] += bases[k];
+            if (totals[k] > 0 && bases[k + 1] <= cigar_cap)
+                memcpy(cigar_out + bases[k], c.h_cigar.p, (size_t)totals[k] * sizeof(uint32_t));
+            return (int)AGX_OK;
+        });
+        if (rc != AGX_OK) return rc;
     }
     cigar_off_out[n_pairs] = base;
     if (cigar_total_out) *cigar_total_out = base;
@@ -1106,7 +1142,7 @@ void agx_shutdown(void)
         hmm_parse_workspace_free(c->hmm_parse);
         hmm_parse_workspace_free(c->hmm_parse_b);
         for (DevBuf *b : {&c->d_bytes, &c->d_a, &c->d_b, &c->d_c, &c->d_d, &c->d_e, &c->d_f, &c->d_out}) b->release();
-        for (PinBuf *b : {&c->h_a, &c->h_b, &c->h_out}) b->release();
+        for (PinBuf *b : {&c->h_a, &c->h_b, &c->h_out, &c->h_cigar}) b->release();
         for (HmmLane &L : c->hl) {
             for (DevBuf *b : {&L.bytes, &L.idx, &L.out}) b->release();
             L.h_idx.release();
