@@ -19,7 +19,8 @@ workload, the other BASELINE configurations are objects inside it:
   "strong"       configs[2] / [3] again as ONE 10^6-pair batch through the library's own in-process multi-GPU
                  dispatcher (agx_init(N); rank 0): end to end from host buffers and resident (one shard per GPU).
   "pairhmm_gatk" configs[3] with the corrected GATK priors (mismatch prior Qr/3, optional base-quality floor):
-                 never used for parity with the reference, reported separately.
+                 never used for parity with the reference, reported separately; "pin" = the mode against the values
+                 of an independent LoglessPairHMM statement on the reference's test_set inputs (tests/golden).
   "sw_lengths"   the inter-task SW kernel at the published MI210 sweep lengths (64 ... 1024) and at generator.py's
                  own 450-500 bp, one length class each.
   "sw_align"     (rank 0) alignment END CELLS and full alignments (start cell + CIGAR) of the headline batch:
@@ -30,7 +31,8 @@ workload, the other BASELINE configurations are objects inside it:
   value        GCUPS with the batch already resident in HBM; CUDA events on the launching stream, max over ranks.
   e2e          the same metric through the reference-facing C-ABI call on PINNED HOST buffers: H2D of the batch,
                kernels, D2H of the results all inside the timed region; h2d_only_ms = the bare upload of the same
-               bytes by every rank at once (the floor that bounds e2e scaling).
+               bytes by every rank at once (the floor that bounds e2e scaling).  These legs run with libagx's own
+               kernel spans (agx_set_profiling) off, as a caller's would: their timing events cost 0.65 ms per call.
   roofline     dominant kernel timed alone with CUDA events inside libagx (agx_profile_ms):
                frac = cells/s x ops_per_cell_executed / measured pipe peak (profiles/peaks_r*.json); the SURVEY's
                algorithmic count is given beside it.
