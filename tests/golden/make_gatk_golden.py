@@ -110,6 +110,26 @@ def main() -> None:
                                  "gatk_floor": gatk_forward(*rd, hp, qual_floor=True)})
         rec["files"][name] = rows
         print(name, len(rows), "pairs", file=sys.stderr)
+    # base qualities below 6 (the test_set files hold none: there the floor changes nothing): seeded synthetic pairs,
+    # inputs recorded beside the values
+    import random
+    rnd = random.Random(20261019)
+    low = []
+    for _ in range(24):
+        H = rnd.randint(12, 60)
+        hap = "".join(rnd.choice("ACGT") for _ in range(H))
+        R = rnd.randint(4, min(40, H))
+        at = rnd.randint(0, H - R)
+        bases = "".join(c if rnd.random() > 0.15 else rnd.choice("ACGTN") for c in hap[at:at + R])
+        quals = "".join(chr(33 + rnd.randint(0, 14)) for _ in range(R))
+        ins = "".join(chr(33 + rnd.randint(25, 45)) for _ in range(R))
+        dels = "".join(chr(33 + rnd.randint(25, 45)) for _ in range(R))
+        gcp = "".join(chr(33 + rnd.choice((10, 10, 10, 8, 12))) for _ in range(R))
+        rd = tuple(x.encode() for x in (bases, quals, ins, dels, gcp))
+        low.append({"read": [bases, quals, ins, dels, gcp], "hap": hap,
+                    "gatk": gatk_forward(*rd, hap.encode(), qual_floor=False),
+                    "gatk_floor": gatk_forward(*rd, hap.encode(), qual_floor=True)})
+    rec["synthetic_low_quality"] = low
     (HERE / "pairhmm_gatk.json").write_text(json.dumps(rec, indent=0) + "\n")
 
 

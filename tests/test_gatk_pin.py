@@ -48,6 +48,18 @@ def test_oracle_gatk_branch_equals_independent_statement(oracle_mod, name):
             assert abs(got - row[key]) <= 1e-11 * abs(row[key]), (name, row, mode, got)
 
 
+def test_oracle_base_quality_floor_on_low_qualities(oracle_mod):
+    """the reference's test_set files hold no base quality below 6, so there the floor changes nothing; seeded
+    synthetic pairs with qualities 0 .. 14 (inputs recorded in the golden file) separate the two GATK modes"""
+    rows = json.loads((GOLDEN / "pairhmm_gatk.json").read_text())["synthetic_low_quality"]
+    assert len(rows) >= 20 and sum(r["gatk"] != r["gatk_floor"] for r in rows) >= 15
+    for r in rows:
+        rd = tuple(x.encode() for x in r["read"])
+        for mode, key in ((1, "gatk"), (3, "gatk_floor")):
+            got = oracle_mod.pairhmm_forward(rd, r["hap"].encode(), gatk=mode)
+            assert abs(got - r[key]) <= 1e-11 * abs(r[key]), (r, mode, got)
+
+
 def test_golden_file_is_what_the_script_gives():
     """the committed json is reproducible: recompute a few rows with the independent statement"""
     ind = _load_independent()
